@@ -1,0 +1,162 @@
+/*
+ * mpcb200.h — C-ABI of the B200-native batched ProxDDP path (libmpcb200.so).
+ *
+ * This header is the drop-in boundary for the ONE hot path of edantec/MPC_benchmark:
+ * `aligator.SolverProxDDP.setup/run` on the three Talos walking OCPs
+ * (reference call sites: fulldynamic_talos.py:379-397,539-540; kinodynamic_talos.py:285-304,490;
+ *  centroidal_talos.py:270-288,462).  The reference crosses Python -> C++ through
+ * eigenpy/Boost.Python objects; here the Python shim (package `mpc_benchmark_b200`, importable
+ * `as aligator`) flattens its object graph into the plain structs below and calls these
+ * entry points through ctypes.  No torch types appear in any signature: device buffers are raw
+ * device pointers (uint64 from torch.Tensor.data_ptr()), the stream is a raw cudaStream_t.
+ *
+ * All arithmetic is fp64.  All matrices are row-major.  SE(3) placements are 12 doubles:
+ * rotation row-major (9) then translation (3).  Spatial vectors are [linear; angular].
+ */
+#ifndef MPCB200_H
+#define MPCB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPC_KIND_CENT 0 /* centroidal_talos.py   : n=9,  m=12, nc<=34 */
+#define MPC_KIND_KINO 1 /* kinodynamic_talos.py  : n=56, m=34, nc<=68 */
+#define MPC_KIND_FULL 2 /* fulldynamic_talos.py  : n=56, m=22, nc<=78 */
+
+#define MPC_NB 23  /* bodies: free-flyer base + 22 revolute (plot.py:488-490) */
+#define MPC_NV 28
+#define MPC_NQ 29
+#define MPC_NJ 22
+#define MPC_MAXU 34
+#define MPC_MAXC 78
+
+/* Robot tree = DATA.  Body 0 is the free-flyer base; bodies must be ordered
+ * parents-first.  Tangent index of body b>0 is 5+b. */
+typedef struct mpc_robot {
+  int32_t nb;
+  int32_t parent[MPC_NB];       /* -1 for the base */
+  double jplace[MPC_NB][12];    /* joint placement in the parent body frame */
+  double axis[MPC_NB][3];       /* revolute axis in the joint frame (unit); unused for body 0 */
+  double mass[MPC_NB];
+  double com[MPC_NB][3];        /* in body frame */
+  double inertia[MPC_NB][9];    /* rotational inertia about the com, body axes, row-major */
+  int32_t foot_body[2];         /* left, right sole frames: parent body + placement */
+  int32_t pad_;
+  double foot_place[2][12];
+  double q_lo[MPC_NJ], q_hi[MPC_NJ], tau_max[MPC_NJ];
+  double gravity[3];            /* (0,0,-9.81) */
+} mpc_robot_t;
+
+/* Global (per problem family) constants: SURVEY App. C. */
+typedef struct mpc_config {
+  int32_t kind;
+  int32_t T;                    /* knots in the horizon (100) */
+  double dt;
+  /* running costs */
+  double x_ref[MPC_NQ + MPC_NV];/* QuadraticStateCost target (full:175, kino:140) */
+  double wx[2 * MPC_NV];        /* diagonal of w_x */
+  double wu[MPC_MAXU];          /* diagonal of w_u / w_control */
+  double w_cent[6];             /* CentroidalMomentumResidual weight diag (full:141-143) */
+  double w_centder[6];          /* kino:103-105 */
+  double w_force[6];            /* ContactForceResidual weight diag (full:149-151) */
+  /* terminal cost (full:234-245); all-zero = empty CostStack (kino:175, cent:249) */
+  double wx_term[2 * MPC_NV];
+  double w_cent_term[6];
+  double w_foot_term[6];
+  /* contact / cone parameters */
+  double mu_fric, foot_L, foot_W;
+  double kp[6], kd[6];          /* Baumgarte corrector (full:93-94) */
+  double contact_place[2][12];  /* world placements of the two rigid contacts (full:83) */
+  double mu_contact;            /* ProximalSettings mu (full:77) */
+  /* centroidal model (cent:187-200) */
+  double mass;
+  double w_linmom[3], w_angmom[3], w_linacc[3], w_angacc[3], w_com[3], com_ref[3];
+  /* solver (full:374-386) */
+  double tol, mu_init;
+  int32_t max_iters;
+  int32_t force_initial_condition;
+} mpc_config_t;
+
+/* Per-knot parameter block (one per instance per knot). */
+typedef struct mpc_knot {
+  double cs[2];        /* contacts in the dynamics (left, right), 0/1 */
+  double fcost[2];     /* ContactForceResidual cost present (full:187-201) */
+  double w_lf[6], w_rf[6]; /* FramePlacement cost weight diag; 0 = off (full:177-185) */
+  double lf_ref[12], rf_ref[12];
+  double f_ref[12];    /* contact-force references L,R (full:188-201) */
+  double u_ref[MPC_MAXU]; /* control reference (cent:225, kino:142, full:176) */
+  double cpos[6];      /* centroidal contact positions L,R (cent:209-210) */
+} mpc_knot_t;
+
+typedef struct mpc_term {
+  double lf_ref[12], rf_ref[12];
+  double com_ref[3];
+  double has_com_cstr; /* terminal CoM equality (full:499-507, kino:176-180) */
+} mpc_term_t;
+
+/* Per-instance solve summary (mirrors aligator Results scalars). */
+typedef struct mpc_info {
+  double prim_infeas, dual_infeas, traj_cost, merit;
+  double mu;
+  int32_t num_iters, al_iters, conv, status; /* status: 0 converged,1 max-iters,2 non-finite,3 reg saturated */
+} mpc_info_t;
+
+typedef struct mpc_solver mpc_solver_t; /* opaque */
+
+/* Replaces SolverProxDDP(tol, mu_init) + the model carried by pin.Model (full:27-97, 379). */
+mpc_solver_t *mpc_create(const mpc_robot_t *robot, const mpc_config_t *cfg, int32_t batch, int32_t device);
+void mpc_destroy(mpc_solver_t *h);
+const char *mpc_last_error(void);
+
+/* solver.setup(problem): (re)allocate the device workspace for `batch` instances of T knots
+ * (full:388,539).  Host pointers: knots [batch][T], terms [batch], x0 [batch][nx]. */
+int32_t mpc_setup(mpc_solver_t *h, const mpc_knot_t *knots, const mpc_term_t *terms, const double *x0);
+/* setReference / contact_poses / u_ref updates of knots [first, first+count) of every instance. */
+int32_t mpc_update_knots(mpc_solver_t *h, const mpc_knot_t *knots, int32_t first, int32_t count);
+int32_t mpc_update_terms(mpc_solver_t *h, const mpc_term_t *terms);
+/* replaceStageCircular + cycleAppend (full:496-497): drop knot 0, append `last` ([batch]) at T-1. */
+int32_t mpc_cycle(mpc_solver_t *h, const mpc_knot_t *last);
+/* problem.x0_init = x (full:536); host pointer [batch][nx]. */
+int32_t mpc_set_x0(mpc_solver_t *h, const double *x0);
+
+/* solver.run(problem, xs_init, us_init) with HOST buffers (full:393-397,540):
+ * xs [batch][T+1][nx], us [batch][T][nu]; copies in, runs up to max_iters ProxDDP iterations
+ * per instance, copies results back with mpc_get_results. */
+int32_t mpc_run(mpc_solver_t *h, const double *xs_init, const double *us_init, int32_t max_iters);
+/* Same, with the trajectories already resident in device memory (device pointers, same layout),
+ * asynchronous on `stream` (a cudaStream_t); used when inputs live in HBM. */
+int32_t mpc_run_device(mpc_solver_t *h, uint64_t xs_dev, uint64_t us_dev, int32_t max_iters, uint64_t stream);
+
+/* solver.results: xs, us, controlFeedbacks() [batch][T][nu][ndx], vs, lams; any pointer may be NULL. */
+int32_t mpc_get_results(mpc_solver_t *h, double *xs, double *us, double *K, double *vs, double *lams,
+                        mpc_info_t *info);
+/* Device-resident result pointers (for NCCL gathers without a host bounce). */
+int32_t mpc_result_ptrs(mpc_solver_t *h, uint64_t *xs, uint64_t *us, uint64_t *K, uint64_t *info);
+/* workspace.problem_data.stage_data[k].dynamics_data.continuous_data.{xdot, contact_force}
+ * (full:467-480): xdot [batch][ndx], force [batch][12]. */
+int32_t mpc_get_stage_data(mpc_solver_t *h, int32_t k, double *xdot, double *contact_force);
+
+/* Number of kernels launched by the last mpc_run* call and device time (ms) between its first and
+ * last launch as measured with CUDA events on the launch stream. */
+int32_t mpc_last_launches(mpc_solver_t *h);
+double mpc_last_device_ms(mpc_solver_t *h);
+
+/* Test / measurement hooks on the same kernels (parity tests call these):
+ * one derivative evaluation of all knots: writes the LQ blocks to host arrays (NULL = skip). */
+int32_t mpc_debug_lq(mpc_solver_t *h, const double *xs, const double *us, int32_t inst,
+                     double *A, double *B, double *H, double *g, double *C, double *hval, double *fgap,
+                     double *cost);
+/* Batched proximal Riccati on caller-provided dense LQ data (device kernels only). */
+int32_t mpc_riccati_dense(int32_t n, int32_t m, int32_t nc, int32_t T, int32_t batch, double mu_dyn, double mu,
+                          const double *H, const double *g, const double *AB, const double *f,
+                          const double *CD, const double *d, const double *HT, const double *gT,
+                          double *dxs, double *dus, double *dvs, double *dlams, double *K, int32_t device);
+/* fp64 DFMA peak micro-benchmark (TFLOP/s) used as the roofline denominator. */
+double mpc_measure_fp64_peak(int32_t device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
