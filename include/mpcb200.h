@@ -143,16 +143,13 @@ int32_t mpc_get_stage_data(mpc_solver_t *h, int32_t k, double *xdot, double *con
 int32_t mpc_last_launches(mpc_solver_t *h);
 double mpc_last_device_ms(mpc_solver_t *h);
 
-/* Test / measurement hooks on the same kernels (parity tests call these):
- * one derivative evaluation of all knots: writes the LQ blocks to host arrays (NULL = skip). */
-int32_t mpc_debug_lq(mpc_solver_t *h, const double *xs, const double *us, int32_t inst,
-                     double *A, double *B, double *H, double *g, double *C, double *hval, double *fgap,
-                     double *cost);
-/* Batched proximal Riccati on caller-provided dense LQ data (device kernels only). */
-int32_t mpc_riccati_dense(int32_t n, int32_t m, int32_t nc, int32_t T, int32_t batch, double mu_dyn, double mu,
-                          const double *H, const double *g, const double *AB, const double *f,
-                          const double *CD, const double *d, const double *HT, const double *gT,
-                          double *dxs, double *dus, double *dvs, double *dlams, double *K, int32_t device);
+/* Test / measurement hook on the same kernels (parity tests call this): ONE derivative evaluation of every knot at
+ * (xs, us) [batch layouts as mpc_run]; copies the LQ blocks of instance `inst` to host arrays (NULL = skip):
+ * AB [T][n][n+m], H [T+1][n+m][n+m], g [T+1][n+m] (Lagrangian gradient), gap [T][n], h [T+1][nc], scal [T+1][8]. */
+int32_t mpc_debug_lq(mpc_solver_t *h, const double *xs, const double *us, int32_t inst, double *AB, double *H, double *g,
+                     double *gap, double *hval, double *scal);
+uint64_t mpc_workspace_bytes(mpc_solver_t *h);
+int32_t mpc_abi_sizeof(int32_t which); /* 0 robot, 1 config, 2 knot, 3 term, 4 info */
 /* fp64 DFMA peak micro-benchmark (TFLOP/s) used as the roofline denominator. */
 double mpc_measure_fp64_peak(int32_t device);
 

@@ -1,0 +1,138 @@
+"""BatchSolver — batched ProxDDP over flat problem descriptors (the layer under the aligator-compatible shim).
+
+One BatchSolver = one `mpc_solver_t` handle = one batch of independent MPC instances on one GPU
+(instances are the data-parallel axis).  Mirrors SolverProxDDP.setup / run / results
+(fulldynamic_talos.py:379-405) for a whole batch at once.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi, _native
+
+
+class BatchResults:
+    def __init__(self, xs, us, K, vs, lams, info):
+        self.xs, self.us, self.K, self.vs, self.lams, self.info = xs, us, K, vs, lams, info
+
+    @property
+    def num_iters(self):
+        return np.array([i.num_iters for i in self.info])
+
+    @property
+    def conv(self):
+        return np.array([bool(i.conv) for i in self.info])
+
+    @property
+    def prim_infeas(self):
+        return np.array([i.prim_infeas for i in self.info])
+
+    @property
+    def dual_infeas(self):
+        return np.array([i.dual_infeas for i in self.info])
+
+    @property
+    def traj_cost(self):
+        return np.array([i.traj_cost for i in self.info])
+
+
+class BatchSolver:
+    def __init__(self, robot, cfg, batch, device=0):
+        self.robot, self.cfg, self.batch, self.device = robot, cfg, int(batch), int(device)
+        self.nx, self.n, self.m, self.nc = _abi.DIMS[cfg.kind]
+        self.T = cfg.T
+        L = _native.lib()
+        self._h = L.mpc_create(C.byref(robot), C.byref(cfg), self.batch, self.device)
+        if not self._h:
+            raise _native.NativeError("mpc_create failed: " + _native.last_error())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _native.lib().mpc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # solver.setup(problem)
+    def setup(self, knots, terms, x0):
+        x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(self.batch, self.nx)
+        assert len(knots) == self.batch * self.T and len(terms) == self.batch
+        _native.check(_native.lib().mpc_setup(self._h, C.cast(knots, C.c_void_p), C.cast(terms, C.c_void_p), _native.ptr(x0)), "mpc_setup")
+
+    def update_knots(self, knots, first, count):
+        assert len(knots) == self.batch * count
+        _native.check(_native.lib().mpc_update_knots(self._h, C.cast(knots, C.c_void_p), first, count), "mpc_update_knots")
+
+    def update_terms(self, terms):
+        _native.check(_native.lib().mpc_update_terms(self._h, C.cast(terms, C.c_void_p)), "mpc_update_terms")
+
+    def cycle(self, last_knots):
+        assert len(last_knots) == self.batch
+        _native.check(_native.lib().mpc_cycle(self._h, C.cast(last_knots, C.c_void_p)), "mpc_cycle")
+
+    def set_x0(self, x0):
+        x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(self.batch, self.nx)
+        _native.check(_native.lib().mpc_set_x0(self._h, _native.ptr(x0)), "mpc_set_x0")
+
+    # solver.run(problem, xs_init, us_init) with host arrays
+    def run(self, xs, us, max_iters=None, fetch=True, gains=True):
+        xs = np.ascontiguousarray(xs, dtype=np.float64).reshape(self.batch, self.T + 1, self.nx)
+        us = np.ascontiguousarray(us, dtype=np.float64).reshape(self.batch, self.T, self.m)
+        mi = self.cfg.max_iters if max_iters is None else int(max_iters)
+        _native.check(_native.lib().mpc_run(self._h, _native.ptr(xs), _native.ptr(us), mi), "mpc_run")
+        return self.results(gains=gains) if fetch else None
+
+    # same with trajectories already in HBM (torch tensors or raw device pointers)
+    def run_device(self, xs_ptr, us_ptr, max_iters=None, stream=0):
+        mi = self.cfg.max_iters if max_iters is None else int(max_iters)
+        _native.check(_native.lib().mpc_run_device(self._h, int(xs_ptr), int(us_ptr), mi, int(stream)), "mpc_run_device")
+
+    def results(self, gains=True, multipliers=True):
+        B, T = self.batch, self.T
+        xs = np.empty((B, T + 1, self.nx))
+        us = np.empty((B, T, self.m))
+        K = np.empty((B, T, self.m, self.n)) if gains else None
+        vs = np.empty((B, T + 1, self.nc)) if multipliers else None
+        lams = np.empty((B, T + 1, self.n)) if multipliers else None
+        info = (_abi.Info * B)()
+        _native.check(_native.lib().mpc_get_results(self._h, _native.ptr(xs), _native.ptr(us), _native.ptr(K), _native.ptr(vs), _native.ptr(lams),
+                                                    C.cast(info, C.c_void_p)), "mpc_get_results")
+        return BatchResults(xs, us, K, vs, lams, info)
+
+    def result_ptrs(self):
+        p = [C.c_uint64(0) for _ in range(4)]
+        _native.check(_native.lib().mpc_result_ptrs(self._h, *[C.byref(x) for x in p]), "mpc_result_ptrs")
+        return tuple(x.value for x in p)
+
+    def stage_data(self, k=0):
+        nd = 9 if self.cfg.kind == _abi.KIND_CENT else 56
+        xdot = np.empty((self.batch, nd))
+        force = np.empty((self.batch, 12))
+        _native.check(_native.lib().mpc_get_stage_data(self._h, k, _native.ptr(xdot), _native.ptr(force)), "mpc_get_stage_data")
+        return xdot, force
+
+    def debug_lq(self, xs, us, inst=0):
+        B, T, n, nz, nc = self.batch, self.T, self.n, self.n + self.m, self.nc
+        xs = np.ascontiguousarray(xs, dtype=np.float64).reshape(B, T + 1, self.nx)
+        us = np.ascontiguousarray(us, dtype=np.float64).reshape(B, T, self.m)
+        o = dict(AB=np.empty((T, n, nz)), H=np.empty((T + 1, nz, nz)), g=np.empty((T + 1, nz)), gap=np.empty((T, n)), h=np.empty((T + 1, nc)),
+                 scal=np.empty((T + 1, 8)))
+        _native.check(_native.lib().mpc_debug_lq(self._h, _native.ptr(xs), _native.ptr(us), inst, _native.ptr(o["AB"]), _native.ptr(o["H"]),
+                                                 _native.ptr(o["g"]), _native.ptr(o["gap"]), _native.ptr(o["h"]), _native.ptr(o["scal"])), "mpc_debug_lq")
+        return o
+
+    @property
+    def last_launches(self):
+        return _native.lib().mpc_last_launches(self._h)
+
+    @property
+    def last_device_ms(self):
+        return _native.lib().mpc_last_device_ms(self._h)
+
+    @property
+    def workspace_bytes(self):
+        return _native.lib().mpc_workspace_bytes(self._h)

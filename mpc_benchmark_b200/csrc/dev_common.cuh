@@ -1,0 +1,289 @@
+// Common device helpers for the sm_100a kernels.
+//
+// Kernel bodies are written as block-cooperative phases: `PAR_FOR(i, n)` distributes n independent work
+// items over the threads of the CTA, `SYNC()` separates dependent phases, and every value that crosses a
+// phase boundary lives in shared memory.  Under MPC_HOST_EMU (tests/_emu only — never part of the product
+// library) the same source compiles with g++, PAR_FOR becomes a serial loop and SYNC a no-op, which lets the
+// CPU test-suite check kernel logic against the oracle without a GPU.  The product path has NO CPU fallback.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifdef MPC_HOST_EMU
+#define HD inline
+#define PAR_FOR(i, n) for (int i = 0; i < (n); i++)
+#define SYNC() ((void)0)
+#define ONE_THREAD if (true)
+#define TID 0
+#define NTHREADS 1
+#else
+#define HD __device__ __forceinline__
+#define PAR_FOR(i, n) for (int i = threadIdx.x; i < (n); i += blockDim.x)
+#define SYNC() __syncthreads()
+#define ONE_THREAD if (threadIdx.x == 0)
+#define TID ((int)threadIdx.x)
+#define NTHREADS ((int)blockDim.x)
+#endif
+
+namespace mpcdev {
+
+// ------------------------------------------------------------------ 3-vectors / 3x3 (row-major)
+HD void cross3(const double *a, const double *b, double *c) {
+  double c0 = a[1] * b[2] - a[2] * b[1], c1 = a[2] * b[0] - a[0] * b[2], c2 = a[0] * b[1] - a[1] * b[0];
+  c[0] = c0; c[1] = c1; c[2] = c2;
+}
+HD double dot3(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+HD double dot6(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5]; }
+HD void mat3_vec(const double *R, const double *x, double *y) {
+  double y0 = R[0] * x[0] + R[1] * x[1] + R[2] * x[2], y1 = R[3] * x[0] + R[4] * x[1] + R[5] * x[2], y2 = R[6] * x[0] + R[7] * x[1] + R[8] * x[2];
+  y[0] = y0; y[1] = y1; y[2] = y2;
+}
+HD void mat3T_vec(const double *R, const double *x, double *y) {
+  double y0 = R[0] * x[0] + R[3] * x[1] + R[6] * x[2], y1 = R[1] * x[0] + R[4] * x[1] + R[7] * x[2], y2 = R[2] * x[0] + R[5] * x[1] + R[8] * x[2];
+  y[0] = y0; y[1] = y1; y[2] = y2;
+}
+HD void mat3_mul(const double *A, const double *B, double *C) { // C = A B (C distinct from A,B)
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+HD void mat3_mulT(const double *A, const double *B, double *C) { // C = A^T B
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) C[3 * i + j] = A[i] * B[j] + A[3 + i] * B[3 + j] + A[6 + i] * B[6 + j];
+}
+HD void skew3(const double *a, double *S) {
+  S[0] = 0; S[1] = -a[2]; S[2] = a[1]; S[3] = a[2]; S[4] = 0; S[5] = -a[0]; S[6] = -a[1]; S[7] = a[0]; S[8] = 0;
+}
+
+// ------------------------------------------------------------------ SE3 (12 doubles: R row-major, p), spatial [lin; ang]
+HD void se3_mul(const double *a, const double *b, double *c) { // c = a b
+  double R[9], p[3];
+  mat3_mul(a, b, R);
+  mat3_vec(a, b + 9, p);
+  for (int i = 0; i < 9; i++) c[i] = R[i];
+  for (int i = 0; i < 3; i++) c[9 + i] = p[i] + a[9 + i];
+}
+HD void se3_inv_mul(const double *a, const double *b, double *c) { // c = a^-1 b
+  double R[9], d[3], p[3];
+  mat3_mulT(a, b, R);
+  for (int i = 0; i < 3; i++) d[i] = b[9 + i] - a[9 + i];
+  mat3T_vec(a, d, p);
+  for (int i = 0; i < 9; i++) c[i] = R[i];
+  for (int i = 0; i < 3; i++) c[9 + i] = p[i];
+}
+HD void se3_act_motion(const double *M, const double *m, double *o) { // local -> world
+  double w[3], v[3], c[3];
+  mat3_vec(M, m + 3, w); mat3_vec(M, m, v); cross3(M + 9, w, c);
+  for (int i = 0; i < 3; i++) { o[i] = v[i] + c[i]; o[3 + i] = w[i]; }
+}
+HD void se3_actinv_motion(const double *M, const double *m, double *o) { // world -> local
+  double c[3], t[3];
+  cross3(M + 9, m + 3, c);
+  for (int i = 0; i < 3; i++) t[i] = m[i] - c[i];
+  double ol[3], oa[3];
+  mat3T_vec(M, t, ol); mat3T_vec(M, m + 3, oa);
+  for (int i = 0; i < 3; i++) { o[i] = ol[i]; o[3 + i] = oa[i]; }
+}
+HD void se3_act_force(const double *M, const double *f, double *o) { // local -> world
+  double fl[3], fa[3], c[3];
+  mat3_vec(M, f, fl); mat3_vec(M, f + 3, fa); cross3(M + 9, fl, c);
+  for (int i = 0; i < 3; i++) { o[i] = fl[i]; o[3 + i] = fa[i] + c[i]; }
+}
+HD void cross_mm(const double *a, const double *b, double *o) { // motion x motion
+  double t1[3], t2[3], t3[3];
+  cross3(a + 3, b, t1); cross3(a, b + 3, t2); cross3(a + 3, b + 3, t3);
+  for (int i = 0; i < 3; i++) { o[i] = t1[i] + t2[i]; o[3 + i] = t3[i]; }
+}
+HD void cross_mf(const double *a, const double *f, double *o) { // motion x* force
+  double t1[3], t2[3], t3[3];
+  cross3(a + 3, f, t1); cross3(a + 3, f + 3, t2); cross3(a, f, t3);
+  for (int i = 0; i < 3; i++) { o[i] = t1[i]; o[3 + i] = t2[i] + t3[i]; }
+}
+// 6x6 motion action matrix of M (row-major 36)
+HD void se3_action_matrix(const double *M, double *A) {
+  double S[9], pR[9];
+  skew3(M + 9, S); mat3_mul(S, M, pR);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      A[6 * i + j] = M[3 * i + j]; A[6 * i + 3 + j] = pR[3 * i + j];
+      A[6 * (i + 3) + j] = 0; A[6 * (i + 3) + 3 + j] = M[3 * i + j];
+    }
+}
+HD void mat6_vec(const double *A, const double *x, double *y) {
+  double t[6];
+  for (int i = 0; i < 6; i++) t[i] = A[6 * i] * x[0] + A[6 * i + 1] * x[1] + A[6 * i + 2] * x[2] + A[6 * i + 3] * x[3] + A[6 * i + 4] * x[4] + A[6 * i + 5] * x[5];
+  for (int i = 0; i < 6; i++) y[i] = t[i];
+}
+HD void mat6_mul(const double *A, const double *B, double *C) { // C distinct
+  for (int i = 0; i < 6; i++)
+    for (int j = 0; j < 6; j++) { double s = 0; for (int k = 0; k < 6; k++) s += A[6 * i + k] * B[6 * k + j]; C[6 * i + j] = s; }
+}
+
+// Spatial inertia in 10-parameter form about the WORLD origin: I[0]=mass, I[1..3]=h=m*c, I[4..9]=Io (xx,xy,xz,yy,yz,zz)
+HD void inertia_mul(const double *I, const double *m, double *f) { // f = I m
+  double c1[3], c2[3];
+  cross3(I + 1, m + 3, c1); // h x w
+  cross3(I + 1, m, c2);     // h x v
+  double w0 = m[3], w1 = m[4], w2 = m[5];
+  double f0 = I[0] * m[0] - c1[0], f1 = I[0] * m[1] - c1[1], f2 = I[0] * m[2] - c1[2];
+  double f3 = c2[0] + I[4] * w0 + I[5] * w1 + I[6] * w2;
+  double f4 = c2[1] + I[5] * w0 + I[7] * w1 + I[8] * w2;
+  double f5 = c2[2] + I[6] * w0 + I[8] * w1 + I[9] * w2;
+  f[0] = f0; f[1] = f1; f[2] = f2; f[3] = f3; f[4] = f4; f[5] = f5;
+}
+
+// ------------------------------------------------------------------ SO3/SE3 exp, log and Jacobians
+HD void so3_coeffs(double t2, double &a, double &b, double &c) {
+  if (t2 < 1e-6) {
+    a = 1.0 - t2 / 6 + t2 * t2 / 120; b = 0.5 - t2 / 24 + t2 * t2 / 720; c = 1.0 / 6 - t2 / 120 + t2 * t2 / 5040;
+  } else {
+    double t = sqrt(t2), s, co;
+    sincos(t, &s, &co);
+    a = s / t; b = (1.0 - co) / t2; c = (t - s) / (t2 * t);
+  }
+}
+HD double vinv_coeff(double t2) {
+  if (t2 < 1e-6) return 1.0 / 12 + t2 / 720 + t2 * t2 / 30240;
+  double t = sqrt(t2), s, co;
+  sincos(t, &s, &co);
+  return (1.0 - t * s / (2.0 * (1.0 - co))) / t2;
+}
+HD void exp3(const double *w, double *R) {
+  double t2 = dot3(w, w), a, b, c;
+  so3_coeffs(t2, a, b, c);
+  double W[9], W2[9];
+  skew3(w, W); mat3_mul(W, W, W2);
+  for (int i = 0; i < 9; i++) R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + a * W[i] + b * W2[i];
+}
+HD void exp6(const double *xi, double *M) {
+  const double *w = xi + 3;
+  double t2 = dot3(w, w), a, b, c;
+  so3_coeffs(t2, a, b, c);
+  double W[9], W2[9], V[9];
+  skew3(w, W); mat3_mul(W, W, W2);
+  for (int i = 0; i < 9; i++) { double e = (i % 4 == 0) ? 1.0 : 0.0; M[i] = e + a * W[i] + b * W2[i]; V[i] = e + b * W[i] + c * W2[i]; }
+  mat3_vec(V, xi, M + 9);
+}
+HD void log3(const double *R, double *w) {
+  double s[3] = {(R[7] - R[5]) * 0.5, (R[2] - R[6]) * 0.5, (R[3] - R[1]) * 0.5};
+  double ct = (R[0] + R[4] + R[8] - 1.0) * 0.5;
+  double s2 = dot3(s, s), f;
+  if (s2 < 1e-6 && ct > 0) f = 1.0 + s2 / 6 + s2 * s2 * (3.0 / 40.0) + s2 * s2 * s2 * (15.0 / 336.0);
+  else { double sn = sqrt(s2); f = atan2(sn, ct) / sn; }
+  w[0] = s[0] * f; w[1] = s[1] * f; w[2] = s[2] * f;
+}
+HD void log6(const double *M, double *xi) {
+  double w[3];
+  log3(M, w);
+  double t2 = dot3(w, w), cp = vinv_coeff(t2);
+  double W[9], W2[9], Vi[9];
+  skew3(w, W); mat3_mul(W, W, W2);
+  for (int i = 0; i < 9; i++) Vi[i] = ((i % 4 == 0) ? 1.0 : 0.0) - 0.5 * W[i] + cp * W2[i];
+  mat3_vec(Vi, M + 9, xi);
+  xi[3] = w[0]; xi[4] = w[1]; xi[5] = w[2];
+}
+// Q block of the SE3 Jacobians (Barfoot 7.86) evaluated at (rho, phi)
+HD void q_block(const double *rho, const double *phi, double *Q) {
+  double t2 = dot3(phi, phi), c1, c2, c3;
+  if (t2 < 1e-6) {
+    c1 = 1.0 / 6 - t2 / 120 + t2 * t2 / 5040; c2 = 1.0 / 24 - t2 / 720 + t2 * t2 / 40320; c3 = 1.0 / 120 - t2 / 2520 + t2 * t2 / 120960;
+  } else {
+    double t = sqrt(t2), s, c;
+    sincos(t, &s, &c);
+    c1 = (t - s) / (t2 * t); c2 = (t2 + 2 * c - 2) / (2 * t2 * t2); c3 = (2 * t - 3 * s + t * c) / (2 * t2 * t2 * t);
+  }
+  double P[9], Rr[9], PR[9], RP[9], PRP[9], PPR[9], RPP[9], PRPP[9], PPRP[9];
+  skew3(phi, P); skew3(rho, Rr);
+  mat3_mul(P, Rr, PR); mat3_mul(Rr, P, RP); mat3_mul(PR, P, PRP);
+  mat3_mul(P, PR, PPR); mat3_mul(RP, P, RPP); mat3_mul(PRP, P, PRPP); mat3_mul(P, PRP, PPRP);
+  for (int i = 0; i < 9; i++)
+    Q[i] = 0.5 * Rr[i] + c1 * (PR[i] + RP[i] + PRP[i]) + c2 * (PPR[i] + RPP[i] - 3 * PRP[i]) + c3 * (PRPP[i] + PPRP[i]);
+}
+HD void Jexp6(const double *xi, double *J) { // right Jacobian of exp6 (6x6 row-major)
+  double t2 = dot3(xi + 3, xi + 3), a, b, c;
+  so3_coeffs(t2, a, b, c);
+  double W[9], W2[9], J3[9], Q[9], nr[3] = {-xi[0], -xi[1], -xi[2]}, np[3] = {-xi[3], -xi[4], -xi[5]};
+  skew3(xi + 3, W); mat3_mul(W, W, W2);
+  for (int i = 0; i < 9; i++) J3[i] = ((i % 4 == 0) ? 1.0 : 0.0) - b * W[i] + c * W2[i];
+  q_block(nr, np, Q);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) { J[6 * i + j] = J3[3 * i + j]; J[6 * i + 3 + j] = Q[3 * i + j]; J[6 * (i + 3) + j] = 0; J[6 * (i + 3) + 3 + j] = J3[3 * i + j]; }
+}
+HD void Jlog6_from_log(const double *xi, double *J) { // xi = log6(M)
+  double t2 = dot3(xi + 3, xi + 3), cp = vinv_coeff(t2);
+  double W[9], W2[9], J3i[9], Q[9], T1[9], B[9], nr[3] = {-xi[0], -xi[1], -xi[2]}, np[3] = {-xi[3], -xi[4], -xi[5]};
+  skew3(xi + 3, W); mat3_mul(W, W, W2);
+  for (int i = 0; i < 9; i++) J3i[i] = ((i % 4 == 0) ? 1.0 : 0.0) + 0.5 * W[i] + cp * W2[i];
+  q_block(nr, np, Q);
+  mat3_mul(J3i, Q, T1); mat3_mul(T1, J3i, B);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) { J[6 * i + j] = J3i[3 * i + j]; J[6 * i + 3 + j] = -B[3 * i + j]; J[6 * (i + 3) + j] = 0; J[6 * (i + 3) + 3 + j] = J3i[3 * i + j]; }
+}
+HD void quat_to_R(const double *q, double *R) {
+  double x = q[0], y = q[1], z = q[2], w = q[3];
+  double n = x * x + y * y + z * z + w * w, s = 2.0 / n;
+  R[0] = 1 - s * (y * y + z * z); R[1] = s * (x * y - z * w); R[2] = s * (x * z + y * w);
+  R[3] = s * (x * y + z * w); R[4] = 1 - s * (x * x + z * z); R[5] = s * (y * z - x * w);
+  R[6] = s * (x * z - y * w); R[7] = s * (y * z + x * w); R[8] = 1 - s * (x * x + y * y);
+}
+HD void quat_integrate(const double *q, const double *w, double *out) {
+  double t2 = dot3(w, w), sh, ch;
+  if (t2 < 1e-6) { sh = 0.5 - t2 / 48 + t2 * t2 / 3840; ch = 1.0 - t2 / 8 + t2 * t2 / 384; }
+  else { double t = sqrt(t2), s, c; sincos(0.5 * t, &s, &c); sh = s / t; ch = c; }
+  double dx = w[0] * sh, dy = w[1] * sh, dz = w[2] * sh, dw = ch;
+  double x = q[0], y = q[1], z = q[2], ww = q[3];
+  double ox = ww * dx + x * dw + y * dz - z * dy;
+  double oy = ww * dy - x * dz + y * dw + z * dx;
+  double oz = ww * dz + x * dy - y * dx + z * dw;
+  double ow = ww * dw - x * dx - y * dy - z * dz;
+  double n = 1.0 / sqrt(ox * ox + oy * oy + oz * oz + ow * ow);
+  out[0] = ox * n; out[1] = oy * n; out[2] = oz * n; out[3] = ow * n;
+}
+// 6x6 inverse by Gauss-Jordan with partial pivoting (single thread)
+HD void inv6(const double *A, double *Ai) {
+  double M[6][12];
+  for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) { M[i][j] = A[6 * i + j]; M[i][6 + j] = (i == j) ? 1.0 : 0.0; }
+  for (int c = 0; c < 6; c++) {
+    int p = c;
+    for (int r = c + 1; r < 6; r++) if (fabs(M[r][c]) > fabs(M[p][c])) p = r;
+    if (p != c) for (int j = 0; j < 12; j++) { double t = M[p][j]; M[p][j] = M[c][j]; M[c][j] = t; }
+    double d = 1.0 / M[c][c];
+    for (int j = 0; j < 12; j++) M[c][j] *= d;
+    for (int r = 0; r < 6; r++) if (r != c) { double f = M[r][c]; for (int j = 0; j < 12; j++) M[r][j] -= f * M[c][j]; }
+  }
+  for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) Ai[6 * i + j] = M[i][6 + j];
+}
+
+// ------------------------------------------------------------------ block-cooperative dense kernels (shared memory)
+// In-place lower Cholesky of the n x n matrix A (leading dimension ld). Right-looking, 2 barriers per column.
+HD void chol_par(double *A, int n, int ld) {
+  for (int j = 0; j < n; j++) {
+    double d = sqrt(A[j * ld + j]);
+    SYNC();
+    PAR_FOR(i, n - j) { int r = j + i; A[r * ld + j] = (i == 0) ? d : A[r * ld + j] / d; }
+    SYNC();
+    int rem = n - j - 1;
+    PAR_FOR(e, rem * rem) {
+      int r = j + 1 + e / rem, c = j + 1 + e % rem;
+      if (c <= r) A[r * ld + c] -= A[r * ld + j] * A[c * ld + j];
+    }
+    SYNC();
+  }
+}
+// Solve L L^T X = B in place for nrhs columns of B (row-major n x ldb); one work item per column.
+HD void chol_solve_par(const double *L, int n, int ld, double *B, int nrhs, int ldb) {
+  PAR_FOR(c, nrhs) {
+    for (int i = 0; i < n; i++) {
+      double s = B[i * ldb + c];
+      for (int k = 0; k < i; k++) s -= L[i * ld + k] * B[k * ldb + c];
+      B[i * ldb + c] = s / L[i * ld + i];
+    }
+    for (int i = n - 1; i >= 0; i--) {
+      double s = B[i * ldb + c];
+      for (int k = i + 1; k < n; k++) s -= L[k * ld + i] * B[k * ldb + c];
+      B[i * ldb + c] = s / L[i * ld + i];
+    }
+  }
+  SYNC();
+}
+
+} // namespace mpcdev

@@ -1,0 +1,730 @@
+// Per-knot evaluation of the FULL-DYNAMICS Talos stage: one CTA per (instance, knot).
+//
+// Replaces, for one knot, what the reference obtains from five independent Aligator objects that each re-run
+// pinocchio::constraintDynamics + computeConstraintDynamicsDerivatives (SURVEY finding 7):
+//   MultibodyConstraintFwdDynamics + IntegratorSemiImplEuler      fulldynamic_talos.py:100-111
+//   ContactForceResidual x2, MultibodyWrenchConeResidual x2        fulldynamic_talos.py:188-201, 211-225
+//   QuadraticState/Control cost, CentroidalMomentumResidual, FramePlacementResidual x2   :160-185
+//   torque / joint-limit boxes                                     :206-209
+// Here (a, lambda, da, dlambda) are computed ONCE in shared memory and every cost/constraint reads them.
+//
+// World-frame formulation (all spatial quantities at the world origin, world axes): subtree accumulations are
+// plain sums.  Derivative columns use composite quantities (DESIGN.md "RBD derivatives"):
+//   dtau_i/dq_j = -S_i.(Ic_m c_j + Bc_m w_j),  m = body(i) in subtree(body(j));  ancestors: S_i.(s_j x* F_J - g_J)
+//   dtau_i/dv_j = +S_i.(Ic_m c'_j + Bc_m s_j)
+#pragma once
+#include "model.cuh"
+
+namespace mpcdev {
+
+constexpr int FN = 56, FM = 22, FNZ = 78, FNC = 78;
+
+// merit / infeasibility partials written per knot
+enum { SC_COST = 0, SC_PEN, SC_PRIM, SC_DUAL, SC_INNER, SC_COUNT = 8 };
+
+struct KnotIO {
+  // inputs
+  const double *x, *u, *xn;        // x_k, u_k, x_{k+1}
+  const mpc_knot_t *kn;
+  const mpc_term_t *tm;
+  const double *v, *v_prev;        // constraint multipliers of this knot (current / BCL estimate)
+  const double *lam_k;             // co-state of x_k (dynamics k-1, or initial condition for k = 0)
+  const double *lam_n, *lam_n_prev;// co-state of x_{k+1}
+  double mu, preg;
+  int k, T;
+  // outputs (derivative pass)
+  double *AB, *H, *lxu, *g, *T6, *E6, *gE_next, *fbar, *dbar, *vplus, *lplus, *CDact;
+  int32_t *nca, *act_idx;
+  // outputs (both passes)
+  double *gap, *h, *scal, *xdot, *lamc;
+};
+
+struct FullWs {
+  double x[NQ + NV], u[FM], xn[NQ + NV];
+  double kn[sizeof(mpc_knot_t) / 8];
+  double oM[NB * 12], S[NV * 6], v[NB * 6], a[NB * 6], I[NB * 10], Ic[NB * 10];
+  double hb[NB * 6], hsub[NB * 6], f[NB * 6], Fsub[NB * 6];
+  double Bc[NB * 36];
+  double U[NV * 6];
+  double M[NV * NV], bvec[NV], acc[NV];
+  double ofoot[24], Jf[2 * 6 * NV];
+  double vc[12], gam[12], astar[12], c1Mc2[24], JlAd[72], lam[12];
+  double Y[NV * 13], G[144], rhs[12];
+  double X[NV * FNZ];
+  double DL[12 * FNZ];
+  double top[2 * NV * 6];
+  double Jcent[6 * FN], rcent[6];
+  double Jpose[2 * 6 * NV], rpose[12];
+  double estate[FN], Jls[36];
+  double dx[FN], xnext[NQ + NV];
+  double P1[36], P2[36], E6[36], T6[36];
+  double lxu[FNZ], g[FNZ];
+  double hval[FNC], vpl[FNC], dbr[FNC], rowtmp[FNC];
+  double lpl[FN], fbr[FN];
+  double com[3], scal[SC_COUNT];
+  int32_t act[2], nact, sidx[2], ctype[FNC], isact[FNC], act_idx[FNC], nca;
+};
+
+// ------------------------------------------------------------------ kinematics shared by running / terminal knots
+// fills oM, S, I, v, hb, Ic, hsub, com, ofoot, Jf
+HD void mb_kinematics(const DevModel &m, FullWs &w) {
+  const mpc_robot_t &rb = m.rb;
+  const double *q = w.x, *qd = w.x + NQ;
+  for (int l = 0; l < m.nlevels; l++) {
+    int n = m.level_start[l + 1] - m.level_start[l];
+    PAR_FOR(t, n) {
+      int b = m.level_body[m.level_start[l] + t];
+      double *o = w.oM + 12 * b;
+      if (b == 0) { quat_to_R(q + 3, o); o[9] = q[0]; o[10] = q[1]; o[11] = q[2]; }
+      else {
+        double ax[3] = {rb.axis[b][0] * q[6 + b], rb.axis[b][1] * q[6 + b], rb.axis[b][2] * q[6 + b]};
+        double jr[12], t1[12];
+        exp3(ax, jr); jr[9] = jr[10] = jr[11] = 0;
+        se3_mul(rb.jplace[b], jr, t1);
+        se3_mul(w.oM + 12 * rb.parent[b], t1, o);
+      }
+    }
+    SYNC();
+  }
+  PAR_FOR(j, NV) {
+    int b = body_of_dof(j);
+    double e[6] = {0, 0, 0, 0, 0, 0};
+    if (j < 6) e[j] = 1.0; else { e[3] = rb.axis[b][0]; e[4] = rb.axis[b][1]; e[5] = rb.axis[b][2]; }
+    se3_act_motion(w.oM + 12 * b, e, w.S + 6 * j);
+  }
+  PAR_FOR(b, NB) {
+    const double *o = w.oM + 12 * b;
+    double cw[3], RI[9], Iw[9];
+    mat3_vec(o, rb.com[b], cw);
+    for (int i = 0; i < 3; i++) cw[i] += o[9 + i];
+    mat3_mul(o, rb.inertia[b], RI);
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) Iw[3 * i + j] = RI[3 * i] * o[3 * j] + RI[3 * i + 1] * o[3 * j + 1] + RI[3 * i + 2] * o[3 * j + 2];
+    double ms = rb.mass[b], c2 = dot3(cw, cw);
+    double *I = w.I + 10 * b;
+    I[0] = ms; I[1] = ms * cw[0]; I[2] = ms * cw[1]; I[3] = ms * cw[2];
+    I[4] = Iw[0] + ms * (c2 - cw[0] * cw[0]); I[5] = Iw[1] - ms * cw[0] * cw[1]; I[6] = Iw[2] - ms * cw[0] * cw[2];
+    I[7] = Iw[4] + ms * (c2 - cw[1] * cw[1]); I[8] = Iw[5] - ms * cw[1] * cw[2]; I[9] = Iw[8] + ms * (c2 - cw[2] * cw[2]);
+  }
+  PAR_FOR(f, 2) se3_mul(w.oM + 12 * rb.foot_body[f], rb.foot_place[f], w.ofoot + 12 * f);
+  SYNC();
+  PAR_FOR(e, NB * 6) {
+    int b = e / 6, c = e % 6;
+    uint32_t mask = m.ancdof_mask[b];
+    double s = 0;
+    for (int j = 0; j < NV; j++) if (mask >> j & 1) s += w.S[6 * j + c] * qd[j];
+    w.v[e] = s;
+  }
+  PAR_FOR(e, 2 * NV) {
+    int f = e / NV, j = e % NV;
+    double col[6] = {0, 0, 0, 0, 0, 0};
+    if (m.ancdof_mask[rb.foot_body[f]] >> j & 1) se3_actinv_motion(w.ofoot + 12 * f, w.S + 6 * j, col);
+    for (int r = 0; r < 6; r++) w.Jf[(6 * f + r) * NV + j] = col[r];
+  }
+  PAR_FOR(e, NB * 10) {
+    int b = e / 10, c = e % 10;
+    uint32_t mask = m.sub_mask[b];
+    double s = 0;
+    for (int d = b; d < NB; d++) if (mask >> d & 1) s += w.I[10 * d + c];
+    w.Ic[e] = s;
+  }
+  SYNC();
+  PAR_FOR(b, NB) inertia_mul(w.I + 10 * b, w.v + 6 * b, w.hb + 6 * b);
+  PAR_FOR(j, NV) inertia_mul(w.Ic + 10 * body_of_dof(j), w.S + 6 * j, w.U + 6 * j);
+  SYNC();
+  PAR_FOR(e, NB * 6) {
+    int b = e / 6, c = e % 6;
+    uint32_t mask = m.sub_mask[b];
+    double s = 0;
+    for (int d = b; d < NB; d++) if (mask >> d & 1) s += w.hb[6 * d + c];
+    w.hsub[e] = s;
+  }
+  ONE_THREAD { for (int i = 0; i < 3; i++) w.com[i] = w.Ic[1 + i] / w.Ic[0]; }
+  SYNC();
+}
+
+// centroidal momentum residual + Jacobian [dh/dq | A_g] (6 x 56), pose residuals + Jacobians, state error.
+HD void mb_cost_terms(const DevModel &m, FullWs &w, const double *lf_ref, const double *rf_ref, bool derivs) {
+  const mpc_robot_t &rb = m.rb;
+  // small single-thread tasks spread over distinct warps
+  PAR_FOR(task, 4 * 32) {
+    if (task == 0) { // centroidal momentum value
+      const double *h = w.hsub;
+      double c[3];
+      cross3(w.com, h, c);
+      for (int i = 0; i < 3; i++) { w.rcent[i] = h[i]; w.rcent[3 + i] = h[3 + i] - c[i]; }
+    } else if (task == 32 || task == 64) { // foot pose residuals
+      int f = task == 32 ? 0 : 1;
+      double D[12];
+      se3_inv_mul(f == 0 ? lf_ref : rf_ref, w.ofoot + 12 * f, D);
+      log6(D, w.rpose + 6 * f);
+      if (derivs) Jlog6_from_log(w.rpose + 6 * f, w.JlAd + 36 * f); // temporarily parked in JlAd; consumed below
+    } else if (task == 96) { // state error e = x (-) x_ref
+      double Mr[12], Mx[12], D[12];
+      quat_to_R(m.cfg.x_ref + 3, Mr); Mr[9] = m.cfg.x_ref[0]; Mr[10] = m.cfg.x_ref[1]; Mr[11] = m.cfg.x_ref[2];
+      for (int i = 0; i < 12; i++) Mx[i] = w.oM[i];
+      se3_inv_mul(Mr, Mx, D);
+      log6(D, w.estate);
+      if (derivs) Jlog6_from_log(w.estate, w.Jls);
+    }
+  }
+  PAR_FOR(i, FN - 6) {
+    int a = 6 + i;
+    w.estate[a] = (a < NV) ? (w.x[7 + a - 6] - m.cfg.x_ref[7 + a - 6]) : (w.x[NQ + a - NV] - m.cfg.x_ref[NQ + a - NV]);
+  }
+  SYNC();
+  if (!derivs) return;
+  PAR_FOR(e, 2 * 6 * NV) { // Jpose = Jlog6 * Jf
+    int f = e / (6 * NV), r = (e / NV) % 6, j = e % NV;
+    const double *Jl = w.JlAd + 36 * f;
+    double s = 0;
+    for (int k = 0; k < 6; k++) s += Jl[6 * r + k] * w.Jf[(6 * f + k) * NV + j];
+    w.Jpose[e] = s;
+  }
+  PAR_FOR(j, NV) { // centroidal derivative columns
+    int J = body_of_dof(j), pJ = rb.parent[J];
+    const double *s = w.S + 6 * j;
+    double vp[6] = {0, 0, 0, 0, 0, 0};
+    if (pJ >= 0) for (int i = 0; i < 6; i++) vp[i] = w.v[6 * pJ + i];
+    double wj[6], t1[6], t2[6], dho[6], Is[6];
+    cross_mm(s, vp, wj);
+    cross_mf(s, w.hsub + 6 * J, t1);
+    inertia_mul(w.Ic + 10 * J, wj, t2);
+    for (int i = 0; i < 6; i++) dho[i] = t1[i] - t2[i];
+    inertia_mul(w.Ic + 10 * J, s, Is);
+    double dc[3] = {Is[0] / w.Ic[0], Is[1] / w.Ic[0], Is[2] / w.Ic[0]};
+    double c1[3], c2[3], c3[3];
+    cross3(dc, w.hsub, c1); cross3(w.com, dho, c2); cross3(w.com, Is, c3);
+    for (int r = 0; r < 3; r++) {
+      w.Jcent[r * FN + j] = dho[r]; w.Jcent[(3 + r) * FN + j] = dho[3 + r] - c1[r] - c2[r];
+      w.Jcent[r * FN + NV + j] = Is[r]; w.Jcent[(3 + r) * FN + NV + j] = Is[3 + r] - c3[r];
+    }
+  }
+  SYNC();
+}
+
+// value + gradient + Gauss-Newton Hessian contributions of the multibody cost stack at (a, b) / z
+HD double mb_cost_value(const FullWs &w, const double *wx, const double *wcent, const double *wlf, const double *wrf) {
+  double c = 0;
+  for (int i = 0; i < FN; i++) c += 0.5 * wx[i] * w.estate[i] * w.estate[i];
+  for (int i = 0; i < 6; i++) c += 0.5 * (wcent[i] * w.rcent[i] * w.rcent[i] + wlf[i] * w.rpose[i] * w.rpose[i] + wrf[i] * w.rpose[6 + i] * w.rpose[6 + i]);
+  return c;
+}
+HD double mb_cost_grad(const FullWs &w, const double *wx, const double *wcent, const double *wlf, const double *wrf, int z) {
+  double g = 0;
+  if (z < 6) { for (int r = 0; r < 6; r++) g += wx[r] * w.Jls[6 * r + z] * w.estate[r]; }
+  else if (z < FN) g += wx[z] * w.estate[z];
+  if (z < FN) for (int r = 0; r < 6; r++) g += wcent[r] * w.Jcent[r * FN + z] * w.rcent[r];
+  if (z < NV) for (int r = 0; r < 6; r++) g += wlf[r] * w.Jpose[r * NV + z] * w.rpose[r] + wrf[r] * w.Jpose[(6 + r) * NV + z] * w.rpose[6 + r];
+  return g;
+}
+HD double mb_cost_hess(const FullWs &w, const double *wx, const double *wcent, const double *wlf, const double *wrf, int a, int b) {
+  double h = 0; // a <= b
+  if (b < 6) { for (int r = 0; r < 6; r++) h += wx[r] * w.Jls[6 * r + a] * w.Jls[6 * r + b]; }
+  else if (a == b && a < FN) h += wx[a];
+  if (b < FN) for (int r = 0; r < 6; r++) if (wcent[r] != 0.0) h += wcent[r] * w.Jcent[r * FN + a] * w.Jcent[r * FN + b];
+  if (b < NV) for (int r = 0; r < 6; r++) h += wlf[r] * w.Jpose[r * NV + a] * w.Jpose[r * NV + b] + wrf[r] * w.Jpose[(6 + r) * NV + a] * w.Jpose[(6 + r) * NV + b];
+  return h;
+}
+
+// normal-cone projection pieces
+HD double vplus_row(int type, double h, double ve, double mu, double lo, double hi, int &act, double &prim) {
+  double wv = h + mu * ve;
+  if (type == 0) { act = 1; prim = h; return wv / mu; }
+  if (type == 1) { if (wv > 0) { act = 1; prim = h; return wv / mu; } act = 0; prim = h - wv; return 0.0; }
+  if (type == 2) {
+    if (wv > hi) { act = 1; prim = h - hi; return (wv - hi) / mu; }
+    if (wv < lo) { act = 1; prim = h - lo; return (wv - lo) / mu; }
+    act = 0; prim = h - wv; return 0.0;
+  }
+  act = 0; prim = 0; return 0.0;
+}
+
+// ------------------------------------------------------------------ running knot
+template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io, FullWs &w) {
+  const mpc_robot_t &rb = m.rb;
+  const mpc_config_t &cfg = m.cfg;
+  const double dt = cfg.dt;
+  PAR_FOR(i, NQ + NV) { w.x[i] = io.x[i]; w.xn[i] = io.xn[i]; }
+  PAR_FOR(i, FM) w.u[i] = io.u[i];
+  PAR_FOR(i, (int)(sizeof(mpc_knot_t) / 8)) w.kn[i] = reinterpret_cast<const double *>(io.kn)[i];
+  SYNC();
+  const mpc_knot_t &kn = *reinterpret_cast<const mpc_knot_t *>(w.kn);
+  ONE_THREAD {
+    bool l = kn.cs[0] != 0.0, r = kn.cs[1] != 0.0;
+    if (!l && !r) l = r = true; // fulldynamic_talos.py:108-110: no-contact falls through to both contacts
+    w.nact = 0; w.sidx[0] = w.sidx[1] = -1;
+    if (l) { w.sidx[0] = w.nact; w.act[w.nact++] = 0; }
+    if (r) { w.sidx[1] = w.nact; w.act[w.nact++] = 1; }
+  }
+  mb_kinematics(m, w);
+  const int nact = w.nact, nk = 6 * nact;
+  const double a0[6] = {-rb.gravity[0], -rb.gravity[1], -rb.gravity[2], 0, 0, 0};
+  // bias accelerations (qdd = 0, gravity folded in) and bias forces
+  PAR_FOR(b, NB) {
+    double acc[6] = {a0[0], a0[1], a0[2], 0, 0, 0};
+    uint32_t mask = m.anc_mask[b];
+    for (int k = 1; k <= b; k++)
+      if (mask >> k & 1) {
+        double sj[6], c[6];
+        for (int i = 0; i < 6; i++) sj[i] = w.S[6 * (5 + k) + i] * w.x[NQ + 5 + k];
+        cross_mm(w.v + 6 * k, sj, c);
+        for (int i = 0; i < 6; i++) acc[i] += c[i];
+      }
+    for (int i = 0; i < 6; i++) w.a[6 * b + i] = acc[i];
+    double t1[6], t2[6];
+    inertia_mul(w.I + 10 * b, acc, t1);
+    cross_mf(w.v + 6 * b, w.hb + 6 * b, t2);
+    for (int i = 0; i < 6; i++) w.f[6 * b + i] = t1[i] + t2[i];
+  }
+  SYNC();
+  PAR_FOR(e, NB * 6) {
+    int b = e / 6, c = e % 6;
+    uint32_t mask = m.sub_mask[b];
+    double s = 0;
+    for (int d = b; d < NB; d++) if (mask >> d & 1) s += w.f[6 * d + c];
+    w.Fsub[e] = s;
+  }
+  PAR_FOR(e, NV * NV) { // CRBA
+    int i = e / NV, j = e % NV, bi = body_of_dof(i), bj = body_of_dof(j);
+    double v = 0;
+    if (m.anc_mask[bj] >> bi & 1) v = dot6(w.S + 6 * i, w.U + 6 * j);
+    else if (m.anc_mask[bi] >> bj & 1) v = dot6(w.S + 6 * j, w.U + 6 * i);
+    w.M[e] = v;
+  }
+  PAR_FOR(c, nact) { // contact kinematics + Baumgarte terms
+    int f = w.act[c], fb = rb.foot_body[f];
+    se3_actinv_motion(w.ofoot + 12 * f, w.v + 6 * fb, w.vc + 6 * c);
+    double an[6];
+    for (int i = 0; i < 6; i++) an[i] = w.a[6 * fb + i] - a0[i];
+    se3_actinv_motion(w.ofoot + 12 * f, an, w.gam + 6 * c);
+    se3_inv_mul(w.ofoot + 12 * f, cfg.contact_place[f], w.c1Mc2 + 12 * c);
+    double lg[6];
+    log6(w.c1Mc2 + 12 * c, lg);
+    for (int r = 0; r < 6; r++) w.astar[6 * c + r] = cfg.kp[r] * lg[r] - cfg.kd[r] * w.vc[6 * c + r];
+    if (DERIV) w.rowtmp[6 * c] = lg[0], w.rowtmp[6 * c + 1] = lg[1], w.rowtmp[6 * c + 2] = lg[2], w.rowtmp[6 * c + 3] = lg[3], w.rowtmp[6 * c + 4] = lg[4], w.rowtmp[6 * c + 5] = lg[5];
+  }
+  SYNC();
+  PAR_FOR(j, NV) { // b = S^T Fsub ; rhs column 0 = tau - b ; columns 1.. = J^T
+    double bj = dot6(w.S + 6 * j, w.Fsub + 6 * body_of_dof(j));
+    w.bvec[j] = bj;
+    w.Y[j * 13] = (j >= 6 ? w.u[j - 6] : 0.0) - bj;
+    for (int r = 0; r < nk; r++) w.Y[j * 13 + 1 + r] = w.Jf[(6 * w.act[r / 6] + r % 6) * NV + j];
+  }
+  SYNC();
+  chol_par(w.M, NV, NV);
+  chol_solve_par(w.M, NV, NV, w.Y, 1 + nk, 13);
+  PAR_FOR(e, nk * (nk + 1)) {
+    int r = e / (nk + 1), c = e % (nk + 1);
+    const double *Jr = w.Jf + (6 * w.act[r / 6] + r % 6) * NV;
+    double s = 0;
+    for (int i = 0; i < NV; i++) s += Jr[i] * w.Y[i * 13 + c];
+    if (c == 0) w.rhs[r] = w.astar[r] - w.gam[r] - s;
+    else w.G[r * 12 + c - 1] = s + ((r == c - 1) ? cfg.mu_contact : 0.0);
+  }
+  SYNC();
+  chol_par(w.G, nk, 12);
+  chol_solve_par(w.G, nk, 12, w.rhs, 1, 1);
+  PAR_FOR(i, NV) {
+    double s = w.Y[i * 13];
+    for (int r = 0; r < nk; r++) s += w.Y[i * 13 + 1 + r] * w.rhs[r];
+    w.acc[i] = s;
+  }
+  PAR_FOR(i, 12) { int f = i / 6; w.lam[i] = (w.sidx[f] >= 0) ? w.rhs[6 * w.sidx[f] + i % 6] : 0.0; }
+  SYNC();
+  PAR_FOR(i, NV) { io.xdot[i] = w.x[NQ + i]; io.xdot[NV + i] = w.acc[i]; }
+  PAR_FOR(i, 12) io.lamc[i] = w.lam[i];
+
+  if (DERIV) {
+    // ---- inverse-dynamics tangent at (q, v, a) with the contact wrenches as external forces
+    PAR_FOR(c, nact) { // JlAd = Jlog6(c1Mc2) * Ad(c2Mc1)
+      double Jl[36], Ad[36], inv[12], id[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+      Jlog6_from_log(w.rowtmp + 6 * c, Jl);
+      se3_inv_mul(w.c1Mc2 + 12 * c, id, inv);
+      se3_action_matrix(inv, Ad);
+      mat6_mul(Jl, Ad, w.JlAd + 36 * c);
+    }
+    PAR_FOR(e, NB * 6) { // full accelerations
+      int b = e / 6, c = e % 6;
+      uint32_t mask = m.ancdof_mask[b];
+      double s = w.a[e];
+      for (int j = 0; j < NV; j++) if (mask >> j & 1) s += w.S[6 * j + c] * w.acc[j];
+      w.a[e] = s;
+    }
+    SYNC();
+    PAR_FOR(b, NB) {
+      double t1[6], t2[6];
+      inertia_mul(w.I + 10 * b, w.a + 6 * b, t1);
+      cross_mf(w.v + 6 * b, w.hb + 6 * b, t2);
+      for (int i = 0; i < 6; i++) t1[i] += t2[i];
+      for (int c = 0; c < nact; c++)
+        if (rb.foot_body[w.act[c]] == b) {
+          double fw[6];
+          se3_act_force(w.ofoot + 12 * w.act[c], w.rhs + 6 * c, fw);
+          for (int i = 0; i < 6; i++) t1[i] -= fw[i];
+        }
+      for (int i = 0; i < 6; i++) w.f[6 * b + i] = t1[i];
+    }
+    PAR_FOR(e, NV * FNZ) w.X[e] = 0.0;
+    PAR_FOR(e, 12 * FNZ) w.DL[e] = 0.0;
+    SYNC();
+    PAR_FOR(e, NB * 6) {
+      int b = e / 6, c = e % 6;
+      uint32_t mask = m.sub_mask[b];
+      double s = 0;
+      for (int d = b; d < NB; d++) if (mask >> d & 1) s += w.f[6 * d + c];
+      w.Fsub[e] = s;
+    }
+    PAR_FOR(e, NB * 6) { // composite B: Bc_b e_c = sum_{k in sub(b)} I_k (e_c x v_k) + e_c x* (I_k v_k) + v_k x* (I_k e_c)
+      int b = e / 6, c = e % 6;
+      uint32_t mask = m.sub_mask[b];
+      double ec[6] = {0, 0, 0, 0, 0, 0}, col[6] = {0, 0, 0, 0, 0, 0};
+      ec[c] = 1.0;
+      for (int k = b; k < NB; k++)
+        if (mask >> k & 1) {
+          double t0[6], t1[6], t2[6], t3[6], t4[6];
+          cross_mm(ec, w.v + 6 * k, t0);
+          inertia_mul(w.I + 10 * k, t0, t1);
+          cross_mf(ec, w.hb + 6 * k, t2);
+          inertia_mul(w.I + 10 * k, ec, t3);
+          cross_mf(w.v + 6 * k, t3, t4);
+          for (int i = 0; i < 6; i++) col[i] += t1[i] + t2[i] + t4[i];
+        }
+      for (int i = 0; i < 6; i++) w.Bc[36 * b + 6 * i + c] = col[i];
+    }
+    SYNC();
+    PAR_FOR(e, 2 * m.npairs) {
+      int kind = e / m.npairs, p = e % m.npairs;
+      int j = m.pair_j[p], mb = m.pair_m[p], J = body_of_dof(j), pJ = rb.parent[J];
+      const double *s = w.S + 6 * j;
+      double vp[6] = {0, 0, 0, 0, 0, 0}, ap[6] = {a0[0], a0[1], a0[2], 0, 0, 0};
+      if (pJ >= 0) for (int i = 0; i < 6; i++) { vp[i] = w.v[6 * pJ + i]; ap[i] = w.a[6 * pJ + i]; }
+      double cj[6], wj[6], t1[6], g[6], g2[6];
+      if (kind == 0) {
+        cross_mm(s, vp, wj);
+        cross_mm(s, ap, cj);
+        cross_mm(wj, vp, t1);
+        for (int i = 0; i < 6; i++) cj[i] -= t1[i];
+      } else {
+        for (int i = 0; i < 6; i++) { wj[i] = s[i]; t1[i] = w.v[6 * J + i] + vp[i]; }
+        cross_mm(s, t1, cj);
+        for (int i = 0; i < 6; i++) cj[i] = -cj[i];
+      }
+      inertia_mul(w.Ic + 10 * mb, cj, g);
+      mat6_vec(w.Bc + 36 * mb, wj, g2);
+      for (int i = 0; i < 6; i++) g[i] += g2[i];
+      int i0 = first_dof(mb), nd = ndof_of(mb);
+      for (int d = 0; d < nd; d++) {
+        double val = dot6(w.S + 6 * (i0 + d), g);
+        w.X[(i0 + d) * FNZ + kind * NV + j] = kind == 0 ? -val : val;
+      }
+      if (mb == J) {
+        if (kind == 0) { cross_mf(s, w.Fsub + 6 * J, t1); for (int i = 0; i < 6; i++) w.top[6 * j + i] = t1[i] - g[i]; }
+        else for (int i = 0; i < 6; i++) w.top[6 * (NV + j) + i] = g[i];
+      }
+    }
+    PAR_FOR(e, NJ) w.X[(6 + e) * FNZ + 2 * NV + e] = -1.0; // R1 for u: -B_act
+    // R2 = d(alpha - astar)/d(q,v) for the active contacts
+    PAR_FOR(e, nact * NV) {
+      int c = e / NV, j = e % NV, f = w.act[c], fb = rb.foot_body[f];
+      if (!(m.ancdof_mask[fb] >> j & 1)) continue;
+      int J = body_of_dof(j), pJ = rb.parent[J];
+      const double *s = w.S + 6 * j, *of = w.ofoot + 12 * f;
+      double vp[6] = {0, 0, 0, 0, 0, 0}, ap[6] = {0, 0, 0, 0, 0, 0};
+      if (pJ >= 0) for (int i = 0; i < 6; i++) { vp[i] = w.v[6 * pJ + i]; ap[i] = w.a[6 * pJ + i] - a0[i]; }
+      double wj[6], cj[6], t1[6], t2[6], dq_[6], dv_[6], wl[6], Jc[6], dlog[6];
+      cross_mm(s, vp, wj);
+      cross_mm(s, ap, cj);
+      cross_mm(wj, vp, t1);
+      cross_mm(wj, w.v + 6 * fb, t2);
+      for (int i = 0; i < 6; i++) t1[i] = cj[i] - t1[i] + t2[i];
+      se3_actinv_motion(of, t1, dq_);
+      for (int i = 0; i < 6; i++) t2[i] = w.v[6 * fb + i] - w.v[6 * J + i] - vp[i];
+      cross_mm(s, t2, t1);
+      se3_actinv_motion(of, t1, dv_);
+      se3_actinv_motion(of, wj, wl);
+      for (int r = 0; r < 6; r++) Jc[r] = w.Jf[(6 * f + r) * NV + j];
+      mat6_vec(w.JlAd + 36 * c, Jc, dlog);
+      for (int r = 0; r < 6; r++) {
+        w.DL[(6 * c + r) * FNZ + j] = -dq_[r] - (-cfg.kp[r] * dlog[r] + cfg.kd[r] * wl[r]);
+        w.DL[(6 * c + r) * FNZ + NV + j] = dv_[r] + cfg.kd[r] * Jc[r];
+      }
+    }
+    SYNC();
+    PAR_FOR(e, m.nanc) {
+      int i = m.anc_i[e], j = m.anc_j[e];
+      w.X[i * FNZ + j] = dot6(w.S + 6 * i, w.top + 6 * j);
+      w.X[i * FNZ + NV + j] = dot6(w.S + 6 * i, w.top + 6 * (NV + j));
+    }
+    SYNC();
+    chol_solve_par(w.M, NV, NV, w.X, FNZ, FNZ); // X = M^-1 R1
+    PAR_FOR(e, nk * FNZ) {
+      int r = e / FNZ, z = e % FNZ;
+      const double *Jr = w.Jf + (6 * w.act[r / 6] + r % 6) * NV;
+      double s = -w.DL[e];
+      for (int i = 0; i < NV; i++) s += Jr[i] * w.X[i * FNZ + z];
+      w.DL[e] = s;
+    }
+    SYNC();
+    chol_solve_par(w.G, nk, 12, w.DL, FNZ, FNZ); // dlam
+    PAR_FOR(e, NV * FNZ) {
+      int i = e / FNZ, z = e % FNZ;
+      double s = -w.X[e];
+      for (int r = 0; r < nk; r++) s += w.Y[i * 13 + 1 + r] * w.DL[r * FNZ + z];
+      w.X[e] = s; // da/dz
+    }
+    SYNC();
+  }
+
+  // ---- semi-implicit Euler + gap (App. A2)
+  PAR_FOR(i, NV) { double dv = dt * w.acc[i]; w.dx[NV + i] = dv; w.dx[i] = dt * (w.x[NQ + i] + dv); }
+  mb_cost_terms(m, w, kn.lf_ref, kn.rf_ref, DERIV); // (contains the SYNC making dx visible)
+  PAR_FOR(task, 32 + NJ + NV) {
+    if (task == 0) {
+      double e[12], pn[3];
+      exp6(w.dx, e);
+      mat3_vec(w.oM, e + 9, pn);
+      for (int i = 0; i < 3; i++) w.xnext[i] = w.x[i] + pn[i];
+      quat_integrate(w.x + 3, w.dx + 3, w.xnext + 3);
+      double Mn[12], Mp[12], D[12], lg[6];
+      quat_to_R(w.xn + 3, Mn); Mn[9] = w.xn[0]; Mn[10] = w.xn[1]; Mn[11] = w.xn[2];
+      quat_to_R(w.xnext + 3, Mp); Mp[9] = w.xnext[0]; Mp[10] = w.xnext[1]; Mp[11] = w.xnext[2];
+      se3_inv_mul(Mn, Mp, D);
+      log6(D, lg);
+      for (int i = 0; i < 6; i++) io.gap[i] = w.fbr[i] = lg[i]; // fbr temporarily holds the gap
+      if (DERIV) {
+        double Jl[36], Ad[36], inv[12], id[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0}, Jd[36], einv[12];
+        Jlog6_from_log(lg, Jl);
+        se3_inv_mul(D, id, inv);
+        se3_action_matrix(inv, Ad);
+        mat6_mul(Jl, Ad, w.E6);
+        for (int i = 0; i < 36; i++) w.E6[i] = -w.E6[i];
+        inv6(w.E6, w.T6);
+        for (int i = 0; i < 36; i++) w.T6[i] = -w.T6[i];
+        Jexp6(w.dx, Jd);
+        mat6_mul(Jl, Jd, w.P1);
+        se3_inv_mul(e, id, einv);
+        se3_action_matrix(einv, Ad);
+        mat6_mul(Jl, Ad, w.P2);
+      }
+    } else if (task >= 32 && task < 32 + NJ) {
+      int i = task - 32;
+      w.xnext[7 + i] = w.x[7 + i] + w.dx[6 + i];
+      io.gap[6 + i] = w.fbr[6 + i] = w.xnext[7 + i] - w.xn[7 + i];
+    } else if (task >= 32 + NJ) {
+      int i = task - 32 - NJ;
+      w.xnext[NQ + i] = w.x[NQ + i] + w.dx[NV + i];
+      io.gap[NV + i] = w.fbr[NV + i] = w.xnext[NQ + i] - w.xn[NQ + i];
+    }
+  }
+  SYNC();
+
+  // ---- constraint values, multiplier estimates, activity
+  PAR_FOR(r, FNC) {
+    int type = -1; double hv = 0, lo = 0, hi = 0;
+    if (r < 22) { type = 2; hv = w.u[r]; lo = -rb.tau_max[r]; hi = rb.tau_max[r]; }
+    else if (r < 44) { int i = r - 22; type = 2; hv = -w.x[7 + i]; lo = -rb.q_hi[i]; hi = -rb.q_lo[i]; }
+    else {
+      int f = (r - 44) / 17, rr = (r - 44) % 17;
+      if (w.sidx[f] >= 0) { type = 1; for (int k = 0; k < 6; k++) hv += m.Acone[6 * rr + k] * w.lam[6 * f + k]; }
+    }
+    int act = 0; double prim = 0;
+    double vp = vplus_row(type, hv, io.v_prev[r], io.mu, lo, hi, act, prim);
+    w.ctype[r] = type; w.hval[r] = hv; w.vpl[r] = vp; w.isact[r] = act;
+    w.dbr[r] = io.mu * (vp - io.v[r]);
+    w.rowtmp[r] = fabs(prim);
+    io.h[r] = hv;
+  }
+  PAR_FOR(i, FN) {
+    double lp = io.lam_n_prev[i] + w.fbr[i] / io.mu; // fbr = gap here
+    w.lpl[i] = lp;
+    w.dx[i] = w.fbr[i];                              // keep the gap in dx for the reductions below
+  }
+  SYNC();
+  PAR_FOR(i, FN) w.fbr[i] = io.mu * (w.lpl[i] - io.lam_n[i]);
+  ONE_THREAD {
+    double cost = mb_cost_value(w, cfg.wx, cfg.w_cent, kn.w_lf, kn.w_rf), pen = 0, prim = 0, inner = 0;
+    for (int i = 0; i < FM; i++) { double e = w.u[i] - kn.u_ref[i]; cost += 0.5 * cfg.wu[i] * e * e; }
+    for (int f = 0; f < 2; f++)
+      if (kn.fcost[f] != 0.0) for (int i = 0; i < 6; i++) { double e = w.lam[6 * f + i] - kn.f_ref[6 * f + i]; cost += 0.5 * cfg.w_force[i] * e * e; }
+    int nca = 0;
+    for (int r = 0; r < FNC; r++) {
+      if (w.ctype[r] < 0) continue;
+      double dv = w.vpl[r] - io.v[r];
+      pen += 0.5 * io.mu * (w.vpl[r] * w.vpl[r] + dv * dv);
+      prim = fmax(prim, w.rowtmp[r]);
+      inner = fmax(inner, fabs(w.dbr[r]));
+      if (w.isact[r]) w.act_idx[nca++] = r;
+    }
+    for (int i = 0; i < FN; i++) {
+      double dl = w.lpl[i] - io.lam_n[i];
+      pen += 0.5 * io.mu * (w.lpl[i] * w.lpl[i] + dl * dl);
+      prim = fmax(prim, fabs(w.dx[i]));
+      inner = fmax(inner, fabs(io.mu * dl));
+    }
+    w.nca = nca;
+    w.scal[SC_COST] = cost; w.scal[SC_PEN] = pen; w.scal[SC_PRIM] = prim; w.scal[SC_INNER] = inner; w.scal[SC_DUAL] = 0;
+  }
+  SYNC();
+  if (!DERIV) {
+    PAR_FOR(i, SC_COUNT) io.scal[i] = w.scal[i];
+    return;
+  }
+
+  // ---- LQ blocks to HBM: AB (56 x 78), Lagrangian gradient, cost gradient / Hessian, active constraint rows
+  PAR_FOR(i, FNC) { io.dbar[i] = w.dbr[i]; io.vplus[i] = w.vpl[i]; io.act_idx[i] = (i < w.nca) ? w.act_idx[i] : -1; }
+  PAR_FOR(i, FN) { io.fbar[i] = w.fbr[i]; io.lplus[i] = w.lpl[i]; }
+  PAR_FOR(i, 36) { io.T6[i] = w.T6[i]; io.E6[i] = w.E6[i]; }
+  ONE_THREAD io.nca[0] = w.nca;
+  const double dt2 = dt * dt;
+  PAR_FOR(z, FNZ) {
+    double d6[6], acc = 0;
+    for (int k = 0; k < 6; k++) d6[k] = dt2 * w.X[k * FNZ + z] + ((z == NV + k) ? dt : 0.0);
+    for (int i = 0; i < 6; i++) {
+      double s = (z < 6) ? w.P2[6 * i + z] : 0.0;
+      for (int k = 0; k < 6; k++) s += w.P1[6 * i + k] * d6[k];
+      io.AB[i * FNZ + z] = s; acc += s * io.lam_n[i];
+    }
+    for (int i = 6; i < NV; i++) {
+      double s = dt2 * w.X[i * FNZ + z] + ((z == NV + i) ? dt : 0.0) + ((z == i) ? 1.0 : 0.0);
+      io.AB[i * FNZ + z] = s; acc += s * io.lam_n[i];
+    }
+    for (int i = 0; i < NV; i++) {
+      double s = dt * w.X[i * FNZ + z] + ((z == NV + i) ? 1.0 : 0.0);
+      io.AB[(NV + i) * FNZ + z] = s; acc += s * io.lam_n[NV + i];
+    }
+    // cost gradient
+    double lz = mb_cost_grad(w, cfg.wx, cfg.w_cent, kn.w_lf, kn.w_rf, z);
+    if (z >= FN) lz += cfg.wu[z - FN] * (w.u[z - FN] - kn.u_ref[z - FN]);
+    for (int f = 0; f < 2; f++)
+      if (kn.fcost[f] != 0.0) {
+        const double *Dl = w.DL + 6 * w.sidx[f] * FNZ;
+        for (int r = 0; r < 6; r++) lz += cfg.w_force[r] * Dl[r * FNZ + z] * (w.lam[6 * f + r] - kn.f_ref[6 * f + r]);
+      }
+    w.lxu[z] = lz; io.lxu[z] = lz;
+    // Lagrangian gradient: + C^T v  (+ E_{k-1}^T lam_k: vector part here, base block added by the reduction kernel)
+    double gz = lz + acc;
+    for (int r = 0; r < FNC; r++) {
+      double vr = io.v[r];
+      if (vr == 0.0 || w.ctype[r] < 0) continue;
+      double c;
+      if (r < 22) c = (z == FN + r) ? 1.0 : 0.0;
+      else if (r < 44) c = (z == 6 + r - 22) ? -1.0 : 0.0;
+      else { int f = (r - 44) / 17, rr = (r - 44) % 17; const double *Dl = w.DL + 6 * w.sidx[f] * FNZ; c = 0; for (int k = 0; k < 6; k++) c += m.Acone[6 * rr + k] * Dl[k * FNZ + z]; }
+      gz += c * vr;
+    }
+    if (z < FN) { if (io.k == 0) gz += io.lam_k[z]; else if (z >= 6) gz -= io.lam_k[z]; }
+    w.g[z] = gz; io.g[z] = gz;
+  }
+  PAR_FOR(j, 6) { // E_k^T lam_{k+1}, base block, for the next knot's gradient
+    double s = 0;
+    for (int i = 0; i < 6; i++) s += w.E6[6 * i + j] * io.lam_n[i];
+    io.gE_next[j] = s;
+  }
+  PAR_FOR(e, FNZ * (FNZ + 1) / 2) { // Gauss-Newton Hessian, upper triangle mirrored
+    // decode (a, b), a <= b, from the linear index of the upper triangle
+    int a = 0, rem = e;
+    { // row a has FNZ - a entries
+      double fa = (2.0 * FNZ + 1.0 - sqrt((2.0 * FNZ + 1.0) * (2.0 * FNZ + 1.0) - 8.0 * (double)e)) * 0.5;
+      a = (int)fa;
+      while (a * FNZ - a * (a - 1) / 2 > e) a--;
+      while ((a + 1) * FNZ - (a + 1) * a / 2 <= e) a++;
+      rem = e - (a * FNZ - a * (a - 1) / 2);
+    }
+    int b = a + rem;
+    double hv = mb_cost_hess(w, cfg.wx, cfg.w_cent, kn.w_lf, kn.w_rf, a, b);
+    if (a == b) { hv += io.preg; if (a >= FN) hv += cfg.wu[a - FN]; }
+    for (int f = 0; f < 2; f++)
+      if (kn.fcost[f] != 0.0) {
+        const double *Dl = w.DL + 6 * w.sidx[f] * FNZ;
+        for (int r = 0; r < 6; r++) hv += cfg.w_force[r] * Dl[r * FNZ + a] * Dl[r * FNZ + b];
+      }
+    io.H[a * FNZ + b] = hv; io.H[b * FNZ + a] = hv;
+  }
+  PAR_FOR(e, w.nca * FNZ) { // active constraint rows, compacted
+    int ai = e / FNZ, z = e % FNZ, r = w.act_idx[ai];
+    double c;
+    if (r < 22) c = (z == FN + r) ? 1.0 : 0.0;
+    else if (r < 44) c = (z == 6 + r - 22) ? -1.0 : 0.0;
+    else { int f = (r - 44) / 17, rr = (r - 44) % 17; const double *Dl = w.DL + 6 * w.sidx[f] * FNZ; c = 0; for (int k = 0; k < 6; k++) c += m.Acone[6 * rr + k] * Dl[k * FNZ + z]; }
+    io.CDact[e] = c;
+  }
+  SYNC();
+  ONE_THREAD { // dual residual of this knot without the base block of the x-gradient (finalised in the reduction kernel)
+    double dual = 0;
+    for (int z = 0; z < FNZ; z++) {
+      if (z < 6) continue;
+      if (io.k == 0 && z < FN) continue;
+      dual = fmax(dual, fabs(w.g[z]));
+    }
+    w.scal[SC_DUAL] = dual;
+  }
+  SYNC();
+  PAR_FOR(i, SC_COUNT) io.scal[i] = w.scal[i];
+}
+
+// ------------------------------------------------------------------ terminal knot (fulldynamic_talos.py:234-245, 499-507)
+template <bool DERIV> HD void eval_full_term(const DevModel &m, const KnotIO &io, FullWs &w) {
+  const mpc_config_t &cfg = m.cfg;
+  PAR_FOR(i, NQ + NV) w.x[i] = io.x[i];
+  SYNC();
+  mb_kinematics(m, w);
+  mb_cost_terms(m, w, io.tm->lf_ref, io.tm->rf_ref, DERIV);
+  const bool has_c = io.tm->has_com_cstr != 0.0;
+  PAR_FOR(r, FNC) {
+    int type = -1; double hv = 0;
+    if (r < 3 && has_c) { type = 0; hv = w.com[r] - io.tm->com_ref[r]; }
+    int act = 0; double prim = 0;
+    double vp = vplus_row(type, hv, io.v_prev[r], io.mu, 0, 0, act, prim);
+    w.ctype[r] = type; w.hval[r] = hv; w.vpl[r] = vp; w.isact[r] = act; w.dbr[r] = io.mu * (vp - io.v[r]); w.rowtmp[r] = fabs(prim);
+    io.h[r] = hv;
+  }
+  SYNC();
+  ONE_THREAD {
+    double cost = mb_cost_value(w, cfg.wx_term, cfg.w_cent_term, cfg.w_foot_term, cfg.w_foot_term), pen = 0, prim = 0, inner = 0;
+    int nca = 0;
+    for (int r = 0; r < 3; r++) {
+      if (w.ctype[r] < 0) continue;
+      double dv = w.vpl[r] - io.v[r];
+      pen += 0.5 * io.mu * (w.vpl[r] * w.vpl[r] + dv * dv);
+      prim = fmax(prim, w.rowtmp[r]); inner = fmax(inner, fabs(w.dbr[r]));
+      if (w.isact[r]) w.act_idx[nca++] = r;
+    }
+    w.nca = nca;
+    w.scal[SC_COST] = cost; w.scal[SC_PEN] = pen; w.scal[SC_PRIM] = prim; w.scal[SC_INNER] = inner; w.scal[SC_DUAL] = 0;
+  }
+  SYNC();
+  if (!DERIV) { PAR_FOR(i, SC_COUNT) io.scal[i] = w.scal[i]; return; }
+  PAR_FOR(i, FNC) { io.dbar[i] = w.dbr[i]; io.vplus[i] = w.vpl[i]; io.act_idx[i] = (i < w.nca) ? w.act_idx[i] : -1; }
+  ONE_THREAD io.nca[0] = w.nca;
+  PAR_FOR(z, FNZ) {
+    double lz = (z < FN) ? mb_cost_grad(w, cfg.wx_term, cfg.w_cent_term, cfg.w_foot_term, cfg.w_foot_term, z) : 0.0;
+    io.lxu[z] = lz;
+    double gz = lz;
+    if (z < NV && has_c) for (int r = 0; r < 3; r++) gz += io.v[r] * w.U[6 * z + r] / w.Ic[0];
+    if (z >= 6 && z < FN) gz -= io.lam_k[z];
+    w.g[z] = gz; io.g[z] = gz;
+  }
+  PAR_FOR(e, FNZ * FNZ) {
+    int a = e / FNZ, b = e % FNZ;
+    double hv = 0;
+    if (a < FN && b < FN) { hv = (a <= b) ? mb_cost_hess(w, cfg.wx_term, cfg.w_cent_term, cfg.w_foot_term, cfg.w_foot_term, a, b)
+                                          : mb_cost_hess(w, cfg.wx_term, cfg.w_cent_term, cfg.w_foot_term, cfg.w_foot_term, b, a);
+      if (a == b) hv += io.preg; }
+    io.H[e] = hv;
+  }
+  PAR_FOR(e, w.nca * FNZ) {
+    int ai = e / FNZ, z = e % FNZ, r = w.act_idx[ai];
+    io.CDact[e] = (z < NV) ? w.U[6 * z + r] / w.Ic[0] : 0.0; // Jcom column = lin(Ic_J s_j) / mass
+  }
+  SYNC();
+  ONE_THREAD {
+    double dual = 0;
+    for (int z = 6; z < FN; z++) dual = fmax(dual, fabs(w.g[z]));
+    w.scal[SC_DUAL] = dual;
+  }
+  SYNC();
+  PAR_FOR(i, SC_COUNT) io.scal[i] = w.scal[i];
+}
+
+} // namespace mpcdev

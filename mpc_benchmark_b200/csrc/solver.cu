@@ -1,0 +1,387 @@
+// libmpcb200.so — CUDA kernels (sm_100a) + the C-ABI of include/mpcb200.h.
+//
+// One solver handle = one batch of independent MPC instances on one GPU.  Kernels:
+//   k_init         CTA / instance   run() prologue (warm start copy, x0 forcing, BCL reset)
+//   k_eval<D>      CTA / (instance, knot)   per-knot evaluation (+ derivatives, LQ assembly when D)
+//   k_decide_eval  CTA / instance   reductions + BCL outer-loop logic
+//   k_riccati      CTA / instance   proximal Riccati backward + forward, directional derivative
+//   k_apply_step   CTA / instance   trial point x (+) alpha dx
+//   k_decide_ls    CTA / instance   Armijo test / next alpha / accept
+// There is deliberately NO CPU fallback: every entry point fails if CUDA is unavailable.
+#include "driver.hpp"
+#include "ws_alloc.hpp"
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace mpcdev;
+
+static thread_local std::string g_err;
+static int fail(const std::string &m) { g_err = m; return 1; }
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));          \
+  } while (0)
+
+// ------------------------------------------------------------------ kernels
+__global__ void k_init(Ws w, const double *xs_in, const double *us_in, int max_iters) { init_instance(w, blockIdx.x, xs_in, us_in, max_iters); }
+
+template <bool DERIV> __global__ void __launch_bounds__(128) k_eval(Ws w) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int T1 = w.T + 1;
+  const int b = blockIdx.x / T1, k = blockIdx.x % T1;
+  eval_dispatch<DERIV>(w, b, k, smem_raw);
+}
+
+__global__ void k_decide_eval(Ws w) {
+  __shared__ double red[8];
+  decide_eval(w, blockIdx.x, red);
+}
+
+__global__ void __launch_bounds__(256) k_riccati(Ws w) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  riccati_dispatch(w, blockIdx.x, reinterpret_cast<double *>(smem_raw));
+}
+
+__global__ void k_apply_step(Ws w) {
+  if (blockIdx.x == 0 && threadIdx.x < 2) w.counters[threadIdx.x] = 0;
+  apply_step(w, blockIdx.x);
+}
+
+__global__ void k_decide_ls(Ws w) {
+  __shared__ double red[8];
+  decide_ls(w, blockIdx.x, red);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int mode = w.st[blockIdx.x].mode;
+    if (mode == MODE_LS) atomicAdd(&w.counters[0], 1);
+    if (mode != MODE_DONE) atomicAdd(&w.counters[1], 1);
+  }
+}
+
+// shift the horizon by one knot (replaceStageCircular / cycleAppend, fulldynamic_talos.py:496-497)
+__global__ void k_cycle(Ws w, const mpc_knot_t *last) {
+  const int b = blockIdx.x, nd = sizeof(mpc_knot_t) / 8;
+  double *kn = reinterpret_cast<double *>(w.knots + (size_t)b * w.T);
+  // serial over knots, parallel over the doubles of one knot: knot k <- knot k+1
+  for (int k = 0; k + 1 < w.T; k++) {
+    for (int i = threadIdx.x; i < nd; i += blockDim.x) kn[k * nd + i] = kn[(k + 1) * nd + i];
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < nd; i += blockDim.x) kn[(w.T - 1) * nd + i] = reinterpret_cast<const double *>(last + b)[i];
+}
+
+// fp64 peak micro-benchmark: 8 independent DFMA chains per thread
+__global__ void k_dfma_peak(double *out, int iters) {
+  double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ------------------------------------------------------------------ host side
+struct mpc_solver {
+  int device = 0;
+  Ws w{};
+  DevModel *d_model = nullptr;
+  DevModel h_model;
+  std::vector<void *> allocs;
+  double *d_xs_in = nullptr, *d_us_in = nullptr;
+  int32_t *h_counters = nullptr; // pinned
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  size_t eval_smem = 0, ric_smem = 0;
+  int eval_threads = 128, ric_threads = 256;
+  int last_launches = 0;
+  float last_ms = 0;
+  size_t bytes = 0;
+  bool setup_done = false;
+};
+
+struct CudaBackend {
+  mpc_solver *h;
+  cudaStream_t s;
+  cudaError_t err = cudaSuccess;
+  void eval(bool d) {
+    const int grid = h->w.B * (h->w.T + 1);
+    if (d) k_eval<true><<<grid, h->eval_threads, h->eval_smem, s>>>(h->w); else k_eval<false><<<grid, h->eval_threads, h->eval_smem, s>>>(h->w);
+  }
+  void decide_eval() { k_decide_eval<<<h->w.B, 128, 0, s>>>(h->w); }
+  void riccati() { k_riccati<<<h->w.B, h->ric_threads, h->ric_smem, s>>>(h->w); }
+  void apply_step() { k_apply_step<<<h->w.B, 128, 0, s>>>(h->w); }
+  void decide_ls() { k_decide_ls<<<h->w.B, 128, 0, s>>>(h->w); }
+  void read_counters(int *c) {
+    cudaError_t e = cudaMemcpyAsync(h->h_counters, h->w.counters, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { err = e; c[0] = c[1] = 0; return; }
+    c[0] = h->h_counters[0]; c[1] = h->h_counters[1];
+  }
+};
+
+static int set_kernel_attrs(mpc_solver *h) {
+  if (h->w.kind == MPC_KIND_FULL) { h->eval_smem = sizeof(FullWs); h->eval_threads = 128; h->ric_smem = riccati_smem_doubles<56, 22, 78>() * 8; h->ric_threads = 256; }
+  else { h->eval_smem = sizeof(CentWs); h->eval_threads = 32; h->ric_smem = riccati_smem_doubles<9, 12, 34>() * 8; h->ric_threads = 64; }
+  CK(cudaFuncSetAttribute(k_eval<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FullWs)));
+  CK(cudaFuncSetAttribute(k_eval<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FullWs)));
+  CK(cudaFuncSetAttribute(k_riccati, cudaFuncAttributeMaxDynamicSharedMemorySize, riccati_smem_doubles<56, 22, 78>() * 8));
+  return 0;
+}
+
+extern "C" {
+
+const char *mpc_last_error(void) { return g_err.c_str(); }
+
+mpc_solver_t *mpc_create(const mpc_robot_t *robot, const mpc_config_t *cfg, int32_t batch, int32_t device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_err = "no CUDA device: libmpcb200 has no CPU fallback"; return nullptr; }
+  if (cfg->kind != MPC_KIND_FULL && cfg->kind != MPC_KIND_CENT) { g_err = "model kind not implemented in this build (kinodynamic: next round)"; return nullptr; }
+  if (cudaSetDevice(device) != cudaSuccess) { g_err = "cudaSetDevice failed"; return nullptr; }
+  mpc_solver *h = new mpc_solver;
+  h->device = device;
+  const char *err = nullptr;
+  if (build_dev_model(robot, cfg, &h->h_model, &err)) { g_err = err; delete h; return nullptr; }
+  Ws &w = h->w;
+  std::memset(&w, 0, sizeof w);
+  w.B = batch; w.T = cfg->T; w.kind = cfg->kind;
+  dims_of_kind(cfg->kind, w.nx, w.n, w.m, w.nc);
+  w.nz = w.n + w.m;
+  w.sc = default_consts(cfg->tol, cfg->mu_init);
+  if (cudaMalloc(&h->d_model, sizeof(DevModel)) != cudaSuccess) { g_err = "cudaMalloc(model) failed"; delete h; return nullptr; }
+  cudaMemcpy(h->d_model, &h->h_model, sizeof(DevModel), cudaMemcpyHostToDevice);
+  w.model = h->d_model;
+  cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
+  cudaMallocHost(&h->h_counters, 4 * sizeof(int32_t));
+  if (set_kernel_attrs(h)) { delete h; return nullptr; }
+  return h;
+}
+
+void mpc_destroy(mpc_solver_t *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (void *p : h->allocs) cudaFree(p);
+  if (h->d_xs_in) cudaFree(h->d_xs_in);
+  if (h->d_us_in) cudaFree(h->d_us_in);
+  if (h->d_model) cudaFree(h->d_model);
+  if (h->h_counters) cudaFreeHost(h->h_counters);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int32_t mpc_setup(mpc_solver_t *h, const mpc_knot_t *knots, const mpc_term_t *terms, const double *x0) {
+  CK(cudaSetDevice(h->device));
+  Ws &w = h->w;
+  const size_t T1 = w.T + 1;
+  if (!h->setup_done) {
+    bool ok = true;
+    h->bytes = alloc_ws(w, [&](size_t bytes) -> void * {
+      void *p = nullptr;
+      if (!ok) return nullptr;
+      if (cudaMalloc(&p, bytes ? bytes : 8) != cudaSuccess) { ok = false; return nullptr; }
+      cudaMemsetAsync(p, 0, bytes ? bytes : 8, h->stream);
+      h->allocs.push_back(p);
+      return p;
+    });
+    if (!ok) return fail("cudaMalloc(workspace) failed: batch too large for this GPU");
+    CK(cudaMalloc(&h->d_xs_in, w.B * T1 * w.nx * 8));
+    CK(cudaMalloc(&h->d_us_in, (size_t)w.B * w.T * w.m * 8));
+    h->setup_done = true;
+  } else {
+    // solver.setup() re-creates the workspace: multipliers restart from zero (fulldynamic_talos.py:539)
+    CK(cudaMemsetAsync(w.vs, 0, w.B * T1 * w.nc * 8, h->stream));
+    CK(cudaMemsetAsync(w.lams, 0, w.B * T1 * w.n * 8, h->stream));
+  }
+  CK(cudaMemcpyAsync(w.knots, knots, sizeof(mpc_knot_t) * w.B * w.T, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(w.terms, terms, sizeof(mpc_term_t) * w.B, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(w.x0, x0, 8 * (size_t)w.B * w.nx, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int32_t mpc_update_knots(mpc_solver_t *h, const mpc_knot_t *knots, int32_t first, int32_t count) {
+  CK(cudaSetDevice(h->device));
+  Ws &w = h->w;
+  if (!h->setup_done) return fail("mpc_update_knots before mpc_setup");
+  if (first < 0 || count < 0 || first + count > w.T) return fail("knot range out of bounds");
+  // host layout [batch][count]
+  CK(cudaMemcpy2DAsync(w.knots + first, sizeof(mpc_knot_t) * w.T, knots, sizeof(mpc_knot_t) * count, sizeof(mpc_knot_t) * count, w.B,
+                       cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int32_t mpc_update_terms(mpc_solver_t *h, const mpc_term_t *terms) {
+  CK(cudaSetDevice(h->device));
+  if (!h->setup_done) return fail("mpc_update_terms before mpc_setup");
+  CK(cudaMemcpyAsync(h->w.terms, terms, sizeof(mpc_term_t) * h->w.B, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int32_t mpc_cycle(mpc_solver_t *h, const mpc_knot_t *last) {
+  CK(cudaSetDevice(h->device));
+  if (!h->setup_done) return fail("mpc_cycle before mpc_setup");
+  mpc_knot_t *d_last = nullptr;
+  CK(cudaMalloc(&d_last, sizeof(mpc_knot_t) * h->w.B));
+  CK(cudaMemcpyAsync(d_last, last, sizeof(mpc_knot_t) * h->w.B, cudaMemcpyHostToDevice, h->stream));
+  k_cycle<<<h->w.B, 96, 0, h->stream>>>(h->w, d_last);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(d_last);
+  return 0;
+}
+
+int32_t mpc_set_x0(mpc_solver_t *h, const double *x0) {
+  CK(cudaSetDevice(h->device));
+  if (!h->setup_done) return fail("mpc_set_x0 before mpc_setup");
+  CK(cudaMemcpyAsync(h->w.x0, x0, 8 * (size_t)h->w.B * h->w.nx, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+static int run_impl(mpc_solver *h, const double *d_xs, const double *d_us, int max_iters, cudaStream_t s, bool sync_events) {
+  if (!h->setup_done) return fail("mpc_run before mpc_setup");
+  CK(cudaEventRecord(h->ev0, s));
+  k_init<<<h->w.B, 128, 0, s>>>(h->w, d_xs, d_us, max_iters);
+  CudaBackend be{h, s};
+  h->last_launches = 1 + run_loop(be, max_iters, h->w.sc);
+  CK(cudaEventRecord(h->ev1, s));
+  if (be.err != cudaSuccess) return fail(std::string("kernel failure: ") + cudaGetErrorString(be.err));
+  CK(cudaGetLastError());
+  if (sync_events) { CK(cudaEventSynchronize(h->ev1)); CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1)); }
+  return 0;
+}
+
+int32_t mpc_run(mpc_solver_t *h, const double *xs_init, const double *us_init, int32_t max_iters) {
+  CK(cudaSetDevice(h->device));
+  if (!h->setup_done) return fail("mpc_run before mpc_setup");
+  Ws &w = h->w;
+  const size_t T1 = w.T + 1;
+  CK(cudaMemcpyAsync(h->d_xs_in, xs_init, w.B * T1 * w.nx * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_us_in, us_init, (size_t)w.B * w.T * w.m * 8, cudaMemcpyHostToDevice, h->stream));
+  return run_impl(h, h->d_xs_in, h->d_us_in, max_iters, h->stream, true);
+}
+
+int32_t mpc_run_device(mpc_solver_t *h, uint64_t xs_dev, uint64_t us_dev, int32_t max_iters, uint64_t stream) {
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : h->stream;
+  return run_impl(h, reinterpret_cast<const double *>(xs_dev), reinterpret_cast<const double *>(us_dev), max_iters, s, true);
+}
+
+int32_t mpc_get_results(mpc_solver_t *h, double *xs, double *us, double *K, double *vs, double *lams, mpc_info_t *info) {
+  CK(cudaSetDevice(h->device));
+  if (!h->setup_done) return fail("mpc_get_results before mpc_setup");
+  Ws &w = h->w;
+  const size_t T1 = w.T + 1;
+  cudaStream_t s = h->stream;
+  if (xs) CK(cudaMemcpyAsync(xs, w.xs, w.B * T1 * w.nx * 8, cudaMemcpyDeviceToHost, s));
+  if (us) CK(cudaMemcpyAsync(us, w.us, (size_t)w.B * w.T * w.m * 8, cudaMemcpyDeviceToHost, s));
+  if (K) CK(cudaMemcpyAsync(K, w.Kfb, (size_t)w.B * w.T * w.m * w.n * 8, cudaMemcpyDeviceToHost, s));
+  if (vs) CK(cudaMemcpyAsync(vs, w.vs, w.B * T1 * w.nc * 8, cudaMemcpyDeviceToHost, s));
+  if (lams) CK(cudaMemcpyAsync(lams, w.lams, w.B * T1 * w.n * 8, cudaMemcpyDeviceToHost, s));
+  std::vector<InstState> st;
+  if (info) { st.resize(w.B); CK(cudaMemcpyAsync(st.data(), w.st, sizeof(InstState) * w.B, cudaMemcpyDeviceToHost, s)); }
+  CK(cudaStreamSynchronize(s));
+  if (info)
+    for (int b = 0; b < w.B; b++) {
+      const InstState &t = st[b];
+      info[b].prim_infeas = t.prim_infeas; info[b].dual_infeas = t.dual_infeas; info[b].traj_cost = t.traj_cost; info[b].merit = t.merit;
+      info[b].mu = t.mu; info[b].num_iters = t.num_iters; info[b].al_iters = t.al_iters; info[b].conv = t.conv; info[b].status = t.status;
+    }
+  return 0;
+}
+
+int32_t mpc_result_ptrs(mpc_solver_t *h, uint64_t *xs, uint64_t *us, uint64_t *K, uint64_t *info) {
+  if (!h->setup_done) return fail("mpc_result_ptrs before mpc_setup");
+  if (xs) *xs = (uint64_t)h->w.xs;
+  if (us) *us = (uint64_t)h->w.us;
+  if (K) *K = (uint64_t)h->w.Kfb;
+  if (info) *info = (uint64_t)h->w.st;
+  return 0;
+}
+
+int32_t mpc_get_stage_data(mpc_solver_t *h, int32_t k, double *xdot, double *contact_force) {
+  CK(cudaSetDevice(h->device));
+  if (!h->setup_done) return fail("mpc_get_stage_data before mpc_setup");
+  Ws &w = h->w;
+  if (k < 0 || k >= w.T) return fail("stage index out of range");
+  const size_t T1 = w.T + 1;
+  const int nd = (w.kind == MPC_KIND_CENT) ? 9 : 56;
+  if (xdot) CK(cudaMemcpy2D(xdot, nd * 8, w.xdot + (size_t)k * 56, T1 * 56 * 8, nd * 8, w.B, cudaMemcpyDeviceToHost));
+  if (contact_force) CK(cudaMemcpy2D(contact_force, 12 * 8, w.lamc + (size_t)k * 12, T1 * 12 * 8, 12 * 8, w.B, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int32_t mpc_last_launches(mpc_solver_t *h) { return h->last_launches; }
+double mpc_last_device_ms(mpc_solver_t *h) { return h->last_ms; }
+uint64_t mpc_workspace_bytes(mpc_solver_t *h) { return h->bytes; }
+
+int32_t mpc_debug_lq(mpc_solver_t *h, const double *xs, const double *us, int32_t inst, double *AB, double *H, double *g, double *gap,
+                     double *hval, double *scal) {
+  CK(cudaSetDevice(h->device));
+  if (!h->setup_done) return fail("mpc_debug_lq before mpc_setup");
+  Ws &w = h->w;
+  const size_t T1 = w.T + 1, T = w.T;
+  if (inst < 0 || inst >= w.B) return fail("instance out of range");
+  CK(cudaMemcpyAsync(h->d_xs_in, xs, w.B * T1 * w.nx * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_us_in, us, (size_t)w.B * w.T * w.m * 8, cudaMemcpyHostToDevice, h->stream));
+  k_init<<<w.B, 128, 0, h->stream>>>(w, h->d_xs_in, h->d_us_in, 1);
+  CudaBackend be{h, h->stream};
+  be.eval(true); be.decide_eval();
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  const size_t b = inst;
+  if (AB) CK(cudaMemcpy(AB, w.AB + b * T * w.n * w.nz, T * w.n * w.nz * 8, cudaMemcpyDeviceToHost));
+  if (H) CK(cudaMemcpy(H, w.H + b * T1 * w.nz * w.nz, T1 * w.nz * w.nz * 8, cudaMemcpyDeviceToHost));
+  if (g) CK(cudaMemcpy(g, w.g + b * T1 * w.nz, T1 * w.nz * 8, cudaMemcpyDeviceToHost));
+  if (gap) CK(cudaMemcpy(gap, w.gap + b * T * w.n, T * w.n * 8, cudaMemcpyDeviceToHost));
+  if (hval) CK(cudaMemcpy(hval, w.h + b * T1 * w.nc, T1 * w.nc * 8, cudaMemcpyDeviceToHost));
+  if (scal) CK(cudaMemcpy(scal, w.scal + b * T1 * SC_COUNT, T1 * SC_COUNT * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+double mpc_measure_fp64_peak(int32_t device) {
+  if (cudaSetDevice(device) != cudaSuccess) { g_err = "no CUDA device"; return -1.0; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+  double *out = nullptr;
+  if (cudaMalloc(&out, (size_t)blocks * threads * 8) != cudaSuccess) return -1.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  k_dfma_peak<<<blocks, threads>>>(out, 1024);
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(e0);
+    k_dfma_peak<<<blocks, threads>>>(out, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  cudaFree(out); cudaEventDestroy(e0); cudaEventDestroy(e1);
+  double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+  return flops / (best * 1e-3) / 1e12;
+}
+
+int32_t mpc_abi_sizeof(int32_t which) {
+  switch (which) {
+  case 0: return sizeof(mpc_robot_t);
+  case 1: return sizeof(mpc_config_t);
+  case 2: return sizeof(mpc_knot_t);
+  case 3: return sizeof(mpc_term_t);
+  case 4: return sizeof(mpc_info_t);
+  }
+  return -1;
+}
+
+} // extern "C"

@@ -1,0 +1,79 @@
+// TEST-ONLY host emulation of the CUDA kernel sources (mpc_benchmark_b200/csrc/*.cuh compiled with
+// -DMPC_HOST_EMU: PAR_FOR = serial loop, SYNC = no-op).  Lets the CPU test-suite check kernel LOGIC against the
+// oracle without a GPU.  It is never loaded by the product package and is not a fallback.
+#define MPC_HOST_EMU 1
+#include "../../mpc_benchmark_b200/csrc/driver.hpp"
+#include "../../mpc_benchmark_b200/csrc/ws_alloc.hpp"
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+using namespace mpcdev;
+
+struct EmuBackend {
+  Ws w;
+  std::vector<double> smem;
+  EmuBackend() : smem(40000, 0.0) {}
+  void eval(bool d) {
+    for (int b = 0; b < w.B; b++)
+      for (int k = 0; k <= w.T; k++) { if (d) eval_dispatch<true>(w, b, k, smem.data()); else eval_dispatch<false>(w, b, k, smem.data()); }
+  }
+  void decide_eval() { double red[8]; for (int b = 0; b < w.B; b++) mpcdev::decide_eval(w, b, red); }
+  void riccati() { for (int b = 0; b < w.B; b++) riccati_dispatch(w, b, smem.data()); }
+  void apply_step() { for (int b = 0; b < w.B; b++) mpcdev::apply_step(w, b); }
+  void decide_ls() {
+    double red[8];
+    w.counters[0] = w.counters[1] = 0;
+    for (int b = 0; b < w.B; b++) {
+      mpcdev::decide_ls(w, b, red);
+      if (w.st[b].mode == MODE_LS) w.counters[0]++;
+      if (w.st[b].mode != MODE_DONE) w.counters[1]++;
+    }
+  }
+  void read_counters(int *c) { c[0] = w.counters[0]; c[1] = w.counters[1]; }
+};
+
+extern "C" int emu_solve(const mpc_robot_t *rb, const mpc_config_t *cfg, int batch, const mpc_knot_t *knots, const mpc_term_t *terms,
+                         const double *x0, double *xs, double *us, double *K, double *vs, double *lams, mpc_info_t *info, double *stage0,
+                         int max_iters, double *lq_dump /* optional: AB,H,g of instance 0 after the first derivative pass */) {
+  static_assert(sizeof(FullWs) <= 40000 * 8, "smem");
+  DevModel *model = new DevModel;
+  const char *err = nullptr;
+  if (build_dev_model(rb, cfg, model, &err)) return 1;
+  EmuBackend be;
+  Ws &w = be.w;
+  std::memset(&w, 0, sizeof w);
+  w.B = batch; w.T = cfg->T; w.kind = cfg->kind;
+  dims_of_kind(cfg->kind, w.nx, w.n, w.m, w.nc);
+  w.nz = w.n + w.m; w.model = model; w.sc = default_consts(cfg->tol, cfg->mu_init);
+  std::vector<void *> allocs;
+  alloc_ws(w, [&](size_t bytes) { void *p = calloc(bytes ? bytes : 8, 1); allocs.push_back(p); return p; });
+  const size_t T1 = w.T + 1;
+  std::memcpy(w.knots, knots, sizeof(mpc_knot_t) * batch * w.T);
+  std::memcpy(w.terms, terms, sizeof(mpc_term_t) * batch);
+  std::memcpy(w.x0, x0, 8 * batch * w.nx);
+  if (vs) std::memcpy(w.vs, vs, 8 * batch * T1 * w.nc);
+  if (lams) std::memcpy(w.lams, lams, 8 * batch * T1 * w.n);
+  for (int b = 0; b < batch; b++) init_instance(w, b, xs, us, max_iters);
+  if (lq_dump) { // single derivative pass, dump instance 0
+    be.eval(true); be.decide_eval();
+    size_t o = 0;
+    auto put = [&](const double *p, size_t n) { std::memcpy(lq_dump + o, p, 8 * n); o += n; };
+    put(w.AB, (size_t)w.T * w.n * w.nz); put(w.H, T1 * w.nz * w.nz); put(w.g, T1 * w.nz); put(w.gap, (size_t)w.T * w.n); put(w.h, T1 * w.nc);
+    put(w.scal, T1 * SC_COUNT);
+  } else run_loop(be, max_iters, w.sc);
+  std::memcpy(xs, w.xs, 8 * batch * T1 * w.nx);
+  std::memcpy(us, w.us, 8 * batch * w.T * w.m);
+  if (K) std::memcpy(K, w.Kfb, 8 * (size_t)batch * w.T * w.m * w.n);
+  if (vs) std::memcpy(vs, w.vs, 8 * batch * T1 * w.nc);
+  if (lams) std::memcpy(lams, w.lams, 8 * batch * T1 * w.n);
+  for (int b = 0; b < batch; b++) {
+    const InstState &s = w.st[b];
+    if (info) { mpc_info_t &o = info[b]; o.prim_infeas = s.prim_infeas; o.dual_infeas = s.dual_infeas; o.traj_cost = s.traj_cost; o.merit = s.merit; o.mu = s.mu;
+      o.num_iters = s.num_iters; o.al_iters = s.al_iters; o.conv = s.conv; o.status = s.status; }
+    if (stage0) { std::memcpy(stage0 + b * 68, w.xdot + b * T1 * 56, 8 * 56); std::memcpy(stage0 + b * 68 + 56, w.lamc + b * T1 * 12, 8 * 12); }
+  }
+  for (void *p : allocs) free(p);
+  delete model;
+  return 0;
+}
