@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""bench.py — full-dynamics Talos MPC solves/sec (BASELINE.json metric) on N GPUs of one node.
+
+A "step" = one MPC-tick solve (SolverProxDDP.run with max_iters = 1, warm-started: fulldynamic_talos.py:407,532-540)
+of EVERY instance of the batch.  Workload = BASELINE.json configs[4]: full-dynamics Talos, T = 100, batch 4096 per
+GPU with random contact schedules and perturbed initial states, on the synthetic Talos-shaped
+model.  Instances are independent, so ranks shard them with no data-path collective (weak scaling: 4096 per GPU).
+
+  value  : solves/s with the warm start already resident in HBM (mpc_run_device), whole job over all ranks
+  e2e    : same metric through the host-buffer C-ABI call (mpc_run + result read-back), H2D/D2H inside the timing
+  roofline: the proximal-Riccati kernel against the fp64 DFMA peak measured in this run (fp64-bound path)
+  cpu_baseline: the CPU oracle (OpenMP over instances, all host cores) on a bounded sample — NOT upstream Aligator
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "full-dynamics Talos MPC solves/sec at batch 4096"
+UNIT = "solves/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="instances per GPU")
+    ap.add_argument("--prep-iters", type=int, default=20, help="untimed cold-solve iterations that produce the warm start")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="instances in the CPU-baseline sample (0 = auto, ~10-30 s)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def algorithmic_lq_flops(prob):
+    """SURVEY 8d dense-LQ model: sum over instances and knots of F_back + F_fwd for the knot's contact variant."""
+    from mpc_benchmark_b200.problems import lq_flops
+
+    f_ds, f_ss = lq_flops(56, 22, 78), lq_flops(56, 22, 61)
+    total = 0.0
+    for k in prob["knots"]:
+        both = (k.cs[0] != 0.0) == (k.cs[1] != 0.0)  # [T,T] and [F,F] both use the two-contact stage (full:108-110)
+        total += f_ds if both else f_ss
+    return total
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU path.  Aligator/Pinocchio are not installable here, so this
+    times the repo's CPU oracle (same algorithm, OpenMP over instances, all host cores) — stated in `cpu_baseline.kind`."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    from mpc_benchmark_b200 import problems
+
+    cores = os.cpu_count() or 1
+    sample = args.cpu_sample or max(cores, 16)
+    prob = problems.full_walk_batch(sample, seed=5)
+    warm = oracle_lib.solve(prob, max_iters=min(args.prep_iters, 5), inst_threads=cores)
+    xs, us = warm["xs"], warm["us"]
+    for _ in range(max(1, min(args.warmup, 1))):
+        oracle_lib.solve(prob, max_iters=1, inst_threads=cores, xs=xs, us=us)
+    t0 = time.time()
+    for _ in range(args.steps):
+        oracle_lib.solve(prob, max_iters=1, inst_threads=cores, xs=xs, us=us)
+    dt = time.time() - t0
+    val = sample * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": f"full-dynamics Talos MPC tick, T=100, random contact schedules, CPU sample of {sample} instances/step"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{sample} instances x {args.steps} ticks; CPU oracle (not upstream Aligator, which cannot be installed offline)"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_arm(args)
+    import torch
+    import torch.distributed as dist
+
+    from mpc_benchmark_b200 import _native, problems
+    from mpc_benchmark_b200.batch import BatchSolver
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    B, T = args.batch, 100
+    prob = problems.full_walk_batch(B, seed=5 + rank, T=T)
+    solver = BatchSolver(prob["robot"], prob["cfg"], B, device=local)
+    solver.setup(prob["knots"], prob["terms"], prob["x0"])
+    # untimed preparation: a few ProxDDP iterations from the cold start give the warm start every timed tick re-solves
+    prep = solver.run(prob["xs"], prob["us"], max_iters=args.prep_iters, gains=False)
+    xs_h = torch.from_numpy(prep.xs).pin_memory()
+    us_h = torch.from_numpy(prep.us).pin_memory()
+    xs_d, us_d = xs_h.cuda(non_blocking=True), us_h.cuda(non_blocking=True)
+    solver.setup(prob["knots"], prob["terms"], prob["x0"])  # multipliers restart from zero, as solver.setup does each tick
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream().cuda_stream
+    peak_tf = _native.lib().mpc_measure_fp64_peak(local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def tick_device():
+        solver.run_device(xs_d.data_ptr(), us_d.data_ptr(), max_iters=1, stream=stream)
+
+    xs_np, us_np = xs_h.numpy(), us_h.numpy()
+    out_xs = np.empty_like(xs_np)
+    out_us = np.empty_like(us_np)
+
+    def tick_e2e():
+        solver.run(xs_np, us_np, max_iters=1, fetch=False)
+        # read back what the MPC loop consumes: xs, us and the first feedback gain (fulldynamic_talos.py:548-550)
+        _native.check(_native.lib().mpc_get_results(solver._h, _native.ptr(out_xs), _native.ptr(out_us), None, None, None, None), "mpc_get_results")
+        return solver.feedback(0)
+
+    for _ in range(max(args.warmup, 3)):
+        tick_device()
+    # ---- timed region 1: inputs resident in HBM
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern = {"eval_deriv": 0.0, "riccati": 0.0, "eval_trial": 0.0, "bookkeeping": 0.0}
+    launches = 0
+    nric = 0
+    ev0.record()
+    t0 = time.time()
+    for _ in range(args.steps):
+        tick_device()
+        km = solver.kernel_ms()
+        for k in kern:
+            kern[k] += km[k][0]
+        nric += km["riccati"][1]
+        launches += solver.last_launches
+    ev1.record()
+    barrier()
+    wall = time.time() - t0
+    dev_ms = ev0.elapsed_time(ev1)
+    # ---- timed region 2: end to end through the host-buffer C-ABI
+    tick_e2e()
+    barrier()
+    t1 = time.time()
+    for _ in range(args.steps):
+        tick_e2e()
+    barrier()
+    wall_e2e = time.time() - t1
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    tmax = torch.tensor([dev_ms * 1e-3, wall, wall_e2e], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dev_s, wall_s, e2e_s = [float(v) for v in tmax.cpu()]
+    step_s = max(dev_s, 0.0) / args.steps
+    value = B * world * args.steps / max(dev_s, 1e-12)
+    e2e = B * world * args.steps / e2e_s
+    info = prep.info
+    res_iters = solver.results(gains=False, multipliers=False).num_iters
+
+    if rank == 0:
+        flops = algorithmic_lq_flops(prob)
+        ric_ms = kern["riccati"] / max(nric, 1)
+        achieved = flops / (ric_ms * 1e-3) / 1e12 if ric_ms > 0 else None
+        h2d = xs_np.nbytes + us_np.nbytes
+        d2h = out_xs.nbytes + out_us.nbytes + B * 22 * 56 * 8
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": 1e3 * step_s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[4]: full-dynamics Talos MPC tick (1 ProxDDP iteration, warm start), T=100, random contact "
+                                   "schedules + perturbed x0, synthetic Talos-shaped model", "batch_per_gpu": B, "global_batch": B * world,
+                       "horizon": T, "parallelism": f"instances sharded over {world} GPU(s), no collective on the data path",
+                       "l2": "per-step working set (GBs of LQ blocks) >> 126 MB L2; no flush needed",
+                       "prep_iters": args.prep_iters, "tick_iters_done": int(np.min(res_iters))},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "wall_ms_per_step": 1e3 * wall_s / args.steps,
+            "kernel_ms_per_step": {k: v / args.steps for k, v in kern.items()},
+            "roofline": {"bound": "fp64", "kernel": "k_riccati (proximal Riccati backward+forward)", "achieved": achieved,
+                         "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None, "traffic": None,
+                         "peak_source": "DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no fp64 entry; SURVEY 8d)",
+                         "algorithmic_flops_per_launch": flops,
+                         "note": "algorithmic = dense LQ model of SURVEY 8d; the kernel skips inactive constraint rows, so executed FLOPs are lower"},
+            "clocks": sampler.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, prob, xs_np, us_np)
+        print(json.dumps(line))
+    solver.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, prob, xs, us):
+    """CPU oracle on the box's host cores over a bounded sample of the same workload (same warm start)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    from mpc_benchmark_b200 import problems
+
+    cores = os.cpu_count() or 1
+    probe_n = min(prob["x0"].shape[0], max(cores, 8))
+    sub = problems.sub_problem(prob, 0, probe_n)
+    t0 = time.time()
+    oracle_lib.solve(sub, max_iters=1, inst_threads=cores, xs=xs[:probe_n], us=us[:probe_n])
+    dt = time.time() - t0
+    rate = probe_n / dt
+    n = args.cpu_sample or int(min(prob["x0"].shape[0], max(probe_n, rate * 15.0)))
+    n = max(cores, (n // cores) * cores)
+    n = min(n, prob["x0"].shape[0])
+    sub = problems.sub_problem(prob, 0, n)
+    t0 = time.time()
+    oracle_lib.solve(sub, max_iters=1, inst_threads=cores, xs=xs[:n], us=us[:n])
+    dt = time.time() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first {n} instances of the same batch, one MPC tick each, {dt:.1f} s; CPU oracle with OpenMP over instances "
+                      "(not upstream Aligator: not installable offline)"}
+
+
+if __name__ == "__main__":
+    main()

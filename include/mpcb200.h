@@ -100,7 +100,10 @@ typedef struct mpc_term {
 typedef struct mpc_info {
   double prim_infeas, dual_infeas, traj_cost, merit;
   double mu;
+  double alpha;      /* step length accepted by the last linesearch */
   int32_t num_iters, al_iters, conv, status; /* status: 0 converged,1 max-iters,2 non-finite,3 reg saturated */
+  int32_t ls_evals;  /* trial evaluations spent in linesearches during the run */
+  int32_t pad_;
 } mpc_info_t;
 
 typedef struct mpc_solver mpc_solver_t; /* opaque */
@@ -138,6 +141,14 @@ int32_t mpc_result_ptrs(mpc_solver_t *h, uint64_t *xs, uint64_t *us, uint64_t *K
  * (full:467-480): xdot [batch][ndx], force [batch][12]. */
 int32_t mpc_get_stage_data(mpc_solver_t *h, int32_t k, double *xdot, double *contact_force);
 
+/* controlFeedbacks()[k] of every instance (fulldynamic_talos.py:405,550): K [batch][nu][ndx]. */
+int32_t mpc_get_feedback(mpc_solver_t *h, int32_t k, double *K);
+/* Device time (ms, CUDA events on the launch stream) and launch count of the last run per kernel category:
+ * 0 evaluation+derivatives, 1 proximal Riccati, 2 trial (values-only) evaluation, 3 bookkeeping kernels. */
+double mpc_last_kernel_ms(mpc_solver_t *h, int32_t category);
+int32_t mpc_last_kernel_launches(mpc_solver_t *h, int32_t category);
+void mpc_set_profiling(mpc_solver_t *h, int32_t on);
+
 /* Number of kernels launched by the last mpc_run* call and device time (ms) between its first and
  * last launch as measured with CUDA events on the launch stream. */
 int32_t mpc_last_launches(mpc_solver_t *h);
@@ -148,6 +159,10 @@ double mpc_last_device_ms(mpc_solver_t *h);
  * AB [T][n][n+m], H [T+1][n+m][n+m], g [T+1][n+m] (Lagrangian gradient), gap [T][n], h [T+1][nc], scal [T+1][8]. */
 int32_t mpc_debug_lq(mpc_solver_t *h, const double *xs, const double *us, int32_t inst, double *AB, double *H, double *g,
                      double *gap, double *hval, double *scal);
+/* Unit-test hook of the FP64 tensor-core tile GEMM used by the Riccati kernel: C (8mt x 8nt, ldc) = A^T B with
+ * A [K][lda], B [K][ldb] (host pointers, K % 4 == 0). */
+int32_t mpc_debug_gemm_tn(int32_t mt, int32_t nt, int32_t K, const double *A, int32_t lda, const double *B, int32_t ldb, double *C,
+                          int32_t ldc);
 uint64_t mpc_workspace_bytes(mpc_solver_t *h);
 int32_t mpc_abi_sizeof(int32_t which); /* 0 robot, 1 config, 2 knot, 3 term, 4 info */
 /* fp64 DFMA peak micro-benchmark (TFLOP/s) used as the roofline denominator. */

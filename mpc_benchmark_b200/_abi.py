@@ -96,10 +96,13 @@ class Info(C.Structure):
         ("traj_cost", d),
         ("merit", d),
         ("mu", d),
+        ("alpha", d),
         ("num_iters", i32),
         ("al_iters", i32),
         ("conv", i32),
         ("status", i32),
+        ("ls_evals", i32),
+        ("pad_", i32),
     ]
 
 

@@ -115,6 +115,17 @@ class BatchSolver:
         _native.check(_native.lib().mpc_get_stage_data(self._h, k, _native.ptr(xdot), _native.ptr(force)), "mpc_get_stage_data")
         return xdot, force
 
+    def feedback(self, k=0):
+        """results.controlFeedbacks()[k] for every instance: [batch, nu, ndx]."""
+        K = np.empty((self.batch, self.m, self.n))
+        _native.check(_native.lib().mpc_get_feedback(self._h, k, _native.ptr(K)), "mpc_get_feedback")
+        return K
+
+    def kernel_ms(self):
+        L = _native.lib()
+        names = ["eval_deriv", "riccati", "eval_trial", "bookkeeping"]
+        return {n: (L.mpc_last_kernel_ms(self._h, i), L.mpc_last_kernel_launches(self._h, i)) for i, n in enumerate(names)}
+
     def debug_lq(self, xs, us, inst=0):
         B, T, n, nz, nc = self.batch, self.T, self.n, self.n + self.m, self.nc
         xs = np.ascontiguousarray(xs, dtype=np.float64).reshape(B, T + 1, self.nx)

@@ -16,6 +16,12 @@
 #define ONE_THREAD if (true)
 #define TID 0
 #define NTHREADS 1
+#define IS_WARP0 true
+#define WARP_FOR(i, n) for (int i = 0; i < (n); i++)
+#define WARP_SYNC() ((void)0)
+#define ATOMIC_INC(p) ((*(p))++)
+struct double2 { double x, y; };
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
 #else
 #define HD __device__ __forceinline__
 #define PAR_FOR(i, n) for (int i = threadIdx.x; i < (n); i += blockDim.x)
@@ -23,6 +29,10 @@
 #define ONE_THREAD if (threadIdx.x == 0)
 #define TID ((int)threadIdx.x)
 #define NTHREADS ((int)blockDim.x)
+#define IS_WARP0 (threadIdx.x < 32)
+#define WARP_FOR(i, n) for (int i = (threadIdx.x & 31); i < (n); i += 32)
+#define WARP_SYNC() __syncwarp()
+#define ATOMIC_INC(p) atomicAdd((p), 1)
 #endif
 
 namespace mpcdev {
@@ -284,6 +294,160 @@ HD void chol_solve_par(const double *L, int n, int ld, double *B, int nrhs, int 
     }
   }
   SYNC();
+}
+
+// ------------------------------------------------------------------ blocked Cholesky / triangular solves (panel width 8)
+// In-place lower Cholesky of A (n x n, ld).  Each 8-wide panel is factorised by warp 0 alone (warp-level barriers
+// only: the 8-step sqrt/divide dependency chain is latency-bound anyway), followed by ONE block-wide trailing update.
+// Dinv receives the inverses of the diagonal blocks (8 x 8 lower, row-major, 64 doubles per panel), which turn the
+// triangular solves below into small GEMMs.  2 block barriers per panel.
+constexpr int CB = 8;
+#ifdef MPC_HOST_EMU
+inline double rsqrt(double x) { return 1.0 / sqrt(x); }
+#endif
+HD void chol_blocked(double *A, int n, int ld, double *Dinv) {
+  for (int k0 = 0; k0 < n; k0 += CB) {
+    const int bw = (n - k0 < CB) ? n - k0 : CB;
+    double *Di = Dinv + (k0 / CB) * CB * CB;
+    if (IS_WARP0) {
+      // (a) factor the bw x bw diagonal block; every lane keeps the 1/L_jj so that no division appears on the chain
+      double dd[CB];
+#pragma unroll
+      for (int j = 0; j < CB; j++) {
+        dd[j] = 1.0;
+        if (j >= bw) continue;
+        const int jj = k0 + j;
+        const double a = A[jj * ld + jj];
+        const double d = rsqrt(a);
+        dd[j] = d;
+        WARP_SYNC();
+        WARP_FOR(i, bw - j) { int r = jj + i; A[r * ld + jj] = (i == 0) ? a * d : A[r * ld + jj] * d; }
+        WARP_SYNC();
+        const int cols = bw - j - 1;
+        WARP_FOR(e, cols * cols) {
+          int r = jj + 1 + e / cols, c = jj + 1 + e % cols;
+          if (c <= r) A[r * ld + c] -= A[r * ld + jj] * A[c * ld + jj];
+        }
+        WARP_SYNC();
+      }
+      // (b) inverse of the diagonal block, one column per lane, multiplications only (dd[r] = 1/L_rr from (a))
+      WARP_FOR(c, CB) {
+        double x[CB];
+#pragma unroll
+        for (int r = 0; r < CB; r++) {
+          double s = (r == c) ? 1.0 : 0.0;
+          if (r < bw) {
+#pragma unroll
+            for (int t = 0; t < CB; t++) if (t < r && t >= c) s -= A[(k0 + r) * ld + k0 + t] * x[t];
+          }
+          x[r] = (r < c || r >= bw || c >= bw) ? 0.0 : s * dd[r];
+        }
+#pragma unroll
+        for (int r = 0; r < CB; r++) Di[r * CB + c] = x[r];
+      }
+    }
+    SYNC();
+    // (c) panel below the diagonal block: L[i, k0:k0+bw] = A[i, k0:k0+bw] * Dinv^T, one row per work item
+    const int rem = n - k0 - bw, r0 = k0 + bw;
+    PAR_FOR(i, rem) {
+      double *row = A + (r0 + i) * ld + k0;
+      double v[CB], o[CB];
+#pragma unroll
+      for (int q = 0; q < CB; q++) v[q] = (q < bw) ? row[q] : 0.0;
+#pragma unroll
+      for (int c = 0; c < CB; c++) { double s = 0; 
+#pragma unroll
+        for (int q = 0; q < CB; q++) if (q <= c) s += v[q] * Di[c * CB + q]; o[c] = s; }
+#pragma unroll
+      for (int q = 0; q < CB; q++) if (q < bw) row[q] = o[q];
+    }
+    SYNC();
+    // (d) trailing update on 2 x 2 tiles of the lower triangle
+    const int th = (rem + 1) / 2;
+    PAR_FOR(t, th * th) {
+      int ti = t / th, tj = t % th;
+      if (tj > ti) continue;
+      int i0 = r0 + 2 * ti, j0 = r0 + 2 * tj;
+      double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
+      bool i1 = i0 + 1 < n, j1 = j0 + 1 < n;
+      for (int q = 0; q < bw; q++) {
+        double li0 = A[i0 * ld + k0 + q], li1 = i1 ? A[(i0 + 1) * ld + k0 + q] : 0.0;
+        double lj0 = A[j0 * ld + k0 + q], lj1 = j1 ? A[(j0 + 1) * ld + k0 + q] : 0.0;
+        a00 += li0 * lj0; a01 += li0 * lj1; a10 += li1 * lj0; a11 += li1 * lj1;
+      }
+      A[i0 * ld + j0] -= a00;
+      if (j1 && j0 + 1 <= i0) A[i0 * ld + j0 + 1] -= a01;
+      if (i1) { A[(i0 + 1) * ld + j0] -= a10; if (j1) A[(i0 + 1) * ld + j0 + 1] -= a11; }
+    }
+    SYNC();
+  }
+}
+// Solve L L^T X = B in place (B: n x nrhs, ldb) with the diagonal-block inverses from chol_blocked.
+HD void trsm_blocked(const double *L, int n, int ld, const double *Dinv, double *B, int nrhs, int ldb) {
+  // forward: L Y = B
+  for (int k0 = 0; k0 < n; k0 += CB) {
+    const int bw = (n - k0 < CB) ? n - k0 : CB;
+    const double *Di = Dinv + (k0 / CB) * CB * CB;
+    PAR_FOR(c, nrhs) {
+      double b[CB], x[CB];
+#pragma unroll
+      for (int r = 0; r < CB; r++) b[r] = (r < bw) ? B[(k0 + r) * ldb + c] : 0.0;
+#pragma unroll
+      for (int r = 0; r < CB; r++) { double s = 0;
+#pragma unroll
+        for (int t = 0; t < CB; t++) if (t <= r) s += Di[r * CB + t] * b[t]; x[r] = s; }
+#pragma unroll
+      for (int r = 0; r < CB; r++) if (r < bw) B[(k0 + r) * ldb + c] = x[r];
+    }
+    SYNC();
+    const int rem = n - k0 - bw, r0 = k0 + bw;
+    const int tc = (nrhs + 3) / 4;
+    PAR_FOR(t, rem * tc) {
+      int i = r0 + t / tc, c0 = (t % tc) * 4;
+      double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      int nc4 = nrhs - c0 < 4 ? nrhs - c0 : 4;
+      for (int q = 0; q < bw; q++) {
+        double l = L[i * ld + k0 + q];
+        const double *xr = B + (k0 + q) * ldb + c0;
+        a0 += l * xr[0]; if (nc4 > 1) a1 += l * xr[1]; if (nc4 > 2) a2 += l * xr[2]; if (nc4 > 3) a3 += l * xr[3];
+      }
+      double *br = B + i * ldb + c0;
+      br[0] -= a0; if (nc4 > 1) br[1] -= a1; if (nc4 > 2) br[2] -= a2; if (nc4 > 3) br[3] -= a3;
+    }
+    SYNC();
+  }
+  // backward: L^T X = Y
+  const int nblk = (n + CB - 1) / CB;
+  for (int kb = nblk - 1; kb >= 0; kb--) {
+    const int k0 = kb * CB, bw = (n - k0 < CB) ? n - k0 : CB;
+    const double *Di = Dinv + kb * CB * CB;
+    PAR_FOR(c, nrhs) {
+      double b[CB], x[CB];
+#pragma unroll
+      for (int r = 0; r < CB; r++) b[r] = (r < bw) ? B[(k0 + r) * ldb + c] : 0.0;
+#pragma unroll
+      for (int r = 0; r < CB; r++) { double s = 0;
+#pragma unroll
+        for (int t = 0; t < CB; t++) if (t >= r) s += Di[t * CB + r] * b[t]; x[r] = s; }
+#pragma unroll
+      for (int r = 0; r < CB; r++) if (r < bw) B[(k0 + r) * ldb + c] = x[r];
+    }
+    SYNC();
+    const int tc = (nrhs + 3) / 4;
+    PAR_FOR(t, k0 * tc) {
+      int i = t / tc, c0 = (t % tc) * 4;
+      double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      int nc4 = nrhs - c0 < 4 ? nrhs - c0 : 4;
+      for (int q = 0; q < bw; q++) {
+        double l = L[(k0 + q) * ld + i];
+        const double *xr = B + (k0 + q) * ldb + c0;
+        a0 += l * xr[0]; if (nc4 > 1) a1 += l * xr[1]; if (nc4 > 2) a2 += l * xr[2]; if (nc4 > 3) a3 += l * xr[3];
+      }
+      double *br = B + i * ldb + c0;
+      br[0] -= a0; if (nc4 > 1) br[1] -= a1; if (nc4 > 2) br[2] -= a2; if (nc4 > 3) br[3] -= a3;
+    }
+    SYNC();
+  }
 }
 
 } // namespace mpcdev

@@ -1,25 +1,35 @@
 // Host-side launch sequence of one solver.run() over a batch (shared by solver.cu and the test-only host
 // emulation).  Mirrors the loop structure of aligator::SolverProxDDPTpl::run (fulldynamic_talos.py:393-397).
+// Kernels run over COMPACTED instance lists so that the cost of late linesearch rounds / late iterations is
+// proportional to the number of instances still working, not to the batch.
 #pragma once
 #include "solver_core.cuh"
 
 namespace mpcdev {
 
-// Backend: eval(bool deriv), decide_eval(), riccati(), apply_step(), decide_ls(), read_counters(int[2])
-template <class Backend> int run_loop(Backend &be, int max_iters, const SolverConst &sc) {
-  int launches = 0;
+// Backend: reset_counters(), eval(deriv, list, n), decide_eval(list, n, next_eval), riccati(list, n), apply_step(list, n),
+//          decide_ls(list, n, ls_out, next_eval), read_counters(int[4])
+template <class Backend> int run_loop(Backend &be, const Ws &w, int max_iters, const SolverConst &sc) {
+  int launches = 0, n_eval = w.B, cur = 0;
   const int guard = max_iters + sc.max_al_iters + 2;
-  for (int pass = 0; pass < guard; pass++) {
-    be.eval(true); be.decide_eval(); be.riccati();
-    launches += 3;
-    int c[2] = {0, 0};
-    for (int ls = 0; ls <= sc.ls_max_steps; ls++) {
-      be.apply_step(); be.eval(false); be.decide_ls();
+  for (int pass = 0; pass < guard && n_eval > 0; pass++) {
+    int32_t *L = eval_list(w, cur), *Lnext = eval_list(w, cur + 1);
+    be.reset_counters();
+    be.eval(true, L, n_eval); be.decide_eval(L, n_eval, Lnext); be.riccati(L, n_eval);
+    be.apply_step(L, n_eval); be.eval(false, L, n_eval); be.decide_ls(L, n_eval, ls_list(w, 0), Lnext);
+    launches += 6;
+    int c[4] = {0, 0, 0, 0};
+    be.read_counters(c);
+    int n_ls = c[0];
+    for (int r = 0; n_ls > 0 && r <= sc.ls_max_steps; r++) {
+      int32_t *Lin = ls_list(w, r), *Lout = ls_list(w, r + 1);
+      be.apply_step(Lin, n_ls); be.eval(false, Lin, n_ls); be.decide_ls(Lin, n_ls, Lout, Lnext);
       launches += 3;
       be.read_counters(c);
-      if (c[0] == 0) break;
+      n_ls = c[0];
     }
-    if (c[1] == 0) break;
+    n_eval = c[2];
+    cur ^= 1;
   }
   return launches;
 }

@@ -49,7 +49,7 @@ struct FullWs {
   double M[NV * NV], bvec[NV], acc[NV];
   double ofoot[24], Jf[2 * 6 * NV];
   double vc[12], gam[12], astar[12], c1Mc2[24], JlAd[72], lam[12];
-  double Y[NV * 13], G[144], rhs[12];
+  double Y[NV * 13], G[144], rhs[12], dinvM[4 * 64], dinvG[2 * 64];
   double X[NV * FNZ];
   double DL[12 * FNZ];
   double top[2 * NV * 6];
@@ -61,7 +61,7 @@ struct FullWs {
   double lxu[FNZ], g[FNZ];
   double hval[FNC], vpl[FNC], dbr[FNC], rowtmp[FNC];
   double lpl[FN], fbr[FN];
-  double com[3], scal[SC_COUNT];
+  double com[3], scal[SC_COUNT], part[32];
   int32_t act[2], nact, sidx[2], ctype[FNC], isact[FNC], act_idx[FNC], nca;
 };
 
@@ -312,8 +312,8 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
     for (int r = 0; r < nk; r++) w.Y[j * 13 + 1 + r] = w.Jf[(6 * w.act[r / 6] + r % 6) * NV + j];
   }
   SYNC();
-  chol_par(w.M, NV, NV);
-  chol_solve_par(w.M, NV, NV, w.Y, 1 + nk, 13);
+  chol_blocked(w.M, NV, NV, w.dinvM);
+  trsm_blocked(w.M, NV, NV, w.dinvM, w.Y, 1 + nk, 13);
   PAR_FOR(e, nk * (nk + 1)) {
     int r = e / (nk + 1), c = e % (nk + 1);
     const double *Jr = w.Jf + (6 * w.act[r / 6] + r % 6) * NV;
@@ -323,8 +323,8 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
     else w.G[r * 12 + c - 1] = s + ((r == c - 1) ? cfg.mu_contact : 0.0);
   }
   SYNC();
-  chol_par(w.G, nk, 12);
-  chol_solve_par(w.G, nk, 12, w.rhs, 1, 1);
+  chol_blocked(w.G, nk, 12, w.dinvG);
+  trsm_blocked(w.G, nk, 12, w.dinvG, w.rhs, 1, 1);
   PAR_FOR(i, NV) {
     double s = w.Y[i * 13];
     for (int r = 0; r < nk; r++) s += w.Y[i * 13 + 1 + r] * w.rhs[r];
@@ -457,7 +457,7 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
       w.X[i * FNZ + NV + j] = dot6(w.S + 6 * i, w.top + 6 * (NV + j));
     }
     SYNC();
-    chol_solve_par(w.M, NV, NV, w.X, FNZ, FNZ); // X = M^-1 R1
+    trsm_blocked(w.M, NV, NV, w.dinvM, w.X, FNZ, FNZ); // X = M^-1 R1
     PAR_FOR(e, nk * FNZ) {
       int r = e / FNZ, z = e % FNZ;
       const double *Jr = w.Jf + (6 * w.act[r / 6] + r % 6) * NV;
@@ -466,7 +466,7 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
       w.DL[e] = s;
     }
     SYNC();
-    chol_solve_par(w.G, nk, 12, w.DL, FNZ, FNZ); // dlam
+    trsm_blocked(w.G, nk, 12, w.dinvG, w.DL, FNZ, FNZ); // dlam
     PAR_FOR(e, NV * FNZ) {
       int i = e / FNZ, z = e % FNZ;
       double s = -w.X[e];
@@ -542,27 +542,38 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
   }
   SYNC();
   PAR_FOR(i, FN) w.fbr[i] = io.mu * (w.lpl[i] - io.lam_n[i]);
-  ONE_THREAD {
-    double cost = mb_cost_value(w, cfg.wx, cfg.w_cent, kn.w_lf, kn.w_rf), pen = 0, prim = 0, inner = 0;
-    for (int i = 0; i < FM; i++) { double e = w.u[i] - kn.u_ref[i]; cost += 0.5 * cfg.wu[i] * e * e; }
-    for (int f = 0; f < 2; f++)
-      if (kn.fcost[f] != 0.0) for (int i = 0; i < 6; i++) { double e = w.lam[6 * f + i] - kn.f_ref[6 * f + i]; cost += 0.5 * cfg.w_force[i] * e * e; }
-    int nca = 0;
-    for (int r = 0; r < FNC; r++) {
+  // partial sums over 8 strided chunks (rows, then dynamics coordinates, then cost terms), combined by one thread
+  PAR_FOR(c, 8) {
+    double pen = 0, prim = 0, inner = 0, cost = 0;
+    for (int r = c; r < FNC; r += 8) {
       if (w.ctype[r] < 0) continue;
       double dv = w.vpl[r] - io.v[r];
       pen += 0.5 * io.mu * (w.vpl[r] * w.vpl[r] + dv * dv);
       prim = fmax(prim, w.rowtmp[r]);
       inner = fmax(inner, fabs(w.dbr[r]));
-      if (w.isact[r]) w.act_idx[nca++] = r;
     }
-    for (int i = 0; i < FN; i++) {
+    for (int i = c; i < FN; i += 8) {
       double dl = w.lpl[i] - io.lam_n[i];
       pen += 0.5 * io.mu * (w.lpl[i] * w.lpl[i] + dl * dl);
       prim = fmax(prim, fabs(w.dx[i]));
       inner = fmax(inner, fabs(io.mu * dl));
+      cost += 0.5 * cfg.wx[i] * w.estate[i] * w.estate[i];
     }
+    for (int i = c; i < FM; i += 8) { double e = w.u[i] - kn.u_ref[i]; cost += 0.5 * cfg.wu[i] * e * e; }
+    w.part[4 * c] = cost; w.part[4 * c + 1] = pen; w.part[4 * c + 2] = prim; w.part[4 * c + 3] = inner;
+  }
+  ONE_THREAD {
+    int nca = 0;
+    for (int r = 0; r < FNC; r++) if (w.isact[r]) w.act_idx[nca++] = r;
     w.nca = nca;
+  }
+  SYNC();
+  ONE_THREAD {
+    double cost = 0, pen = 0, prim = 0, inner = 0;
+    for (int c = 0; c < 8; c++) { cost += w.part[4 * c]; pen += w.part[4 * c + 1]; prim = fmax(prim, w.part[4 * c + 2]); inner = fmax(inner, w.part[4 * c + 3]); }
+    for (int i = 0; i < 6; i++) cost += 0.5 * (cfg.w_cent[i] * w.rcent[i] * w.rcent[i] + kn.w_lf[i] * w.rpose[i] * w.rpose[i] + kn.w_rf[i] * w.rpose[6 + i] * w.rpose[6 + i]);
+    for (int f = 0; f < 2; f++)
+      if (kn.fcost[f] != 0.0) for (int i = 0; i < 6; i++) { double e = w.lam[6 * f + i] - kn.f_ref[6 * f + i]; cost += 0.5 * cfg.w_force[i] * e * e; }
     w.scal[SC_COST] = cost; w.scal[SC_PEN] = pen; w.scal[SC_PRIM] = prim; w.scal[SC_INNER] = inner; w.scal[SC_DUAL] = 0;
   }
   SYNC();
@@ -650,17 +661,20 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
     io.CDact[e] = c;
   }
   SYNC();
-  ONE_THREAD { // dual residual of this knot without the base block of the x-gradient (finalised in the reduction kernel)
+  PAR_FOR(c, 8) { // dual residual of this knot without the base block of the x-gradient (finalised in the reduction kernel)
     double dual = 0;
-    for (int z = 0; z < FNZ; z++) {
-      if (z < 6) continue;
+    for (int z = 6 + c; z < FNZ; z += 8) {
       if (io.k == 0 && z < FN) continue;
       dual = fmax(dual, fabs(w.g[z]));
     }
-    w.scal[SC_DUAL] = dual;
+    w.part[c] = dual;
   }
   SYNC();
-  PAR_FOR(i, SC_COUNT) io.scal[i] = w.scal[i];
+  PAR_FOR(i, SC_COUNT) {
+    double v = w.scal[i];
+    if (i == SC_DUAL) for (int c = 0; c < 8; c++) v = fmax(v, w.part[c]);
+    io.scal[i] = v;
+  }
 }
 
 // ------------------------------------------------------------------ terminal knot (fulldynamic_talos.py:234-245, 499-507)

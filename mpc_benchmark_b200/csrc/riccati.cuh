@@ -102,7 +102,7 @@ template <int N, int M, int NC> constexpr int riccati_smem_doubles() {
   constexpr int NZ = N + M, NR = 1 + N;
   constexpr int phase1 = 2 * N * N + 2 * N * NZ;
   constexpr int phase2 = NC * NZ + NC * NC + M * (NR + NC) + NC * NR + M * M;
-  return NZ * NZ + (phase1 > phase2 ? phase1 : phase2) + 8 * NZ + 36 + 2 * NC + 1024 + 16;
+  return NZ * NZ + (phase1 > phase2 ? phase1 : phase2) + 8 * NZ + 36 + 2 * NC + 512 + 64 * ((NC + 7) / 8 + (N + 7) / 8) + 16;
 }
 
 // Backward + forward sweep for one instance.  ws: riccati_smem_doubles<N,M,NC>() doubles of shared memory.
@@ -119,7 +119,7 @@ template <int N, int M, int NC> HD void riccati_instance(const RiccatiIO &io, do
   constexpr int phase2 = NC * NZ + NC * NC + M * (NR + NC) + NC * NR + M * M;
   double *vec = U0 + (phase1 > phase2 ? phase1 : phase2);
   double *p = vec, *pt = p + NZ, *gh = pt + NZ, *fb = gh + NZ, *tmp = fb + NZ, *dx = tmp + NZ, *z = dx + NZ, *dl = z + NZ;
-  double *T6 = dl + NZ, *dbr = T6 + 36, *dva = dbr + NC, *red = dva + NC;
+  double *T6 = dl + NZ, *dbr = T6 + 36, *dva = dbr + NC, *red = dva + NC, *dinv = red + 512;
   // ---- terminal value function: P = H_T[xx] + C'C/mu, p = g_T[x] + C' d/mu
   {
     const double *HT = io.H + (size_t)T * NZ * NZ, *gT = io.g + (size_t)T * NZ;
@@ -164,9 +164,9 @@ template <int N, int M, int NC> HD void riccati_instance(const RiccatiIO &io, do
     PAR_FOR(e, N * N) G[e] = mu_d * P[e] + ((e / N == e % N) ? 1.0 : 0.0);
     PAR_FOR(i, N) { double s = p[i]; for (int j = 0; j < N; j++) s += P[i * N + j] * fb[j]; pt[i] = s; }
     SYNC();
-    chol_par(G, N, N);
-    trsm_par(G, N, N, P, N, N);
-    trsm_par(G, N, N, pt, 1, 1);
+    chol_blocked(G, N, N, dinv);
+    trsm_blocked(G, N, N, dinv, P, N, N);
+    trsm_blocked(G, N, N, dinv, pt, 1, 1);
     // 3. W = Pt [A B];  H = H_k + [A B]' W;  gh = g + [A B]' pt
     PAR_FOR(e, NZ * NZ) H[e] = gH[e];
     gemm_par<false>(N, NZ, N, P, N, AB, NZ, W, NZ, 0.0);
@@ -188,8 +188,8 @@ template <int N, int M, int NC> HD void riccati_instance(const RiccatiIO &io, do
       Z[i * ncol + c] = (c == 0) ? gh[N + i] : (c < NR ? H[(c - 1) * NZ + N + i] : CD[(c - NR) * NZ + N + i]);
     }
     SYNC();
-    chol_par(Rh, M, M);
-    trsm_par(Rh, M, M, Z, ncol, ncol);
+    chol_blocked(Rh, M, M, dinv);
+    trsm_blocked(Rh, M, M, dinv, Z, ncol, ncol);
     // Schur complement Sg = mu I + D Z_D ; right-hand side Kv = [dbar | C] - D [Z_r | Z_S]
     PAR_FOR(e, nca * nca) {
       int r = e / nca, c = e % nca;
@@ -204,7 +204,7 @@ template <int N, int M, int NC> HD void riccati_instance(const RiccatiIO &io, do
       Kv[e] = s;
     }
     SYNC();
-    if (nca > 0) { chol_par(Sg, nca, nca); trsm_par(Sg, nca, nca, Kv, NR, NR); }
+    if (nca > 0) { chol_blocked(Sg, nca, nca, dinv); trsm_blocked(Sg, nca, nca, dinv, Kv, NR, NR); }
     // Ku = -Z0 - Z_D Kv  (into Z0's place)
     PAR_FOR(e, M * NR) {
       int i = e / NR, c = e % NR;

@@ -12,6 +12,7 @@
 #include "ws_alloc.hpp"
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -29,37 +30,31 @@ static int fail(const std::string &m) { g_err = m; return 1; }
 // ------------------------------------------------------------------ kernels
 __global__ void k_init(Ws w, const double *xs_in, const double *us_in, int max_iters) { init_instance(w, blockIdx.x, xs_in, us_in, max_iters); }
 
-template <bool DERIV> __global__ void __launch_bounds__(128) k_eval(Ws w) {
+template <bool DERIV> __global__ void __launch_bounds__(128) k_eval(Ws w, const int32_t *list) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int T1 = w.T + 1;
-  const int b = blockIdx.x / T1, k = blockIdx.x % T1;
+  const int b = list[blockIdx.x / T1], k = blockIdx.x % T1;
   eval_dispatch<DERIV>(w, b, k, smem_raw);
 }
 
-__global__ void k_decide_eval(Ws w) {
+__global__ void k_decide_eval(Ws w, const int32_t *list, int32_t *next_eval) {
   __shared__ double red[8];
-  decide_eval(w, blockIdx.x, red);
+  decide_eval(w, list[blockIdx.x], red, next_eval);
 }
 
-__global__ void __launch_bounds__(256) k_riccati(Ws w) {
+__global__ void __launch_bounds__(256) k_riccati(Ws w, const int32_t *list) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  riccati_dispatch(w, blockIdx.x, reinterpret_cast<double *>(smem_raw));
+  riccati_dispatch(w, list[blockIdx.x], reinterpret_cast<double *>(smem_raw));
 }
 
-__global__ void k_apply_step(Ws w) {
-  if (blockIdx.x == 0 && threadIdx.x < 2) w.counters[threadIdx.x] = 0;
-  apply_step(w, blockIdx.x);
+__global__ void k_apply_step(Ws w, const int32_t *list) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) w.counters[0] = 0; // next linesearch list starts empty
+  apply_step(w, list[blockIdx.x]);
 }
 
-__global__ void k_decide_ls(Ws w) {
+__global__ void k_decide_ls(Ws w, const int32_t *list, int32_t *ls_out, int32_t *next_eval) {
   __shared__ double red[8];
-  decide_ls(w, blockIdx.x, red);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int mode = w.st[blockIdx.x].mode;
-    if (mode == MODE_LS) atomicAdd(&w.counters[0], 1);
-    if (mode != MODE_DONE) atomicAdd(&w.counters[1], 1);
-  }
+  decide_ls(w, list[blockIdx.x], red, ls_out, next_eval);
 }
 
 // shift the horizon by one knot (replaceStageCircular / cycleAppend, fulldynamic_talos.py:496-497)
@@ -102,34 +97,50 @@ struct mpc_solver {
   float last_ms = 0;
   size_t bytes = 0;
   bool setup_done = false;
+  // per-kernel-category device timing of the last run: 0 eval+derivatives, 1 riccati, 2 trial evaluation, 3 bookkeeping
+  std::vector<cudaEvent_t> evpool;
+  std::vector<int> evcat;
+  double cat_ms[4] = {0, 0, 0, 0};
+  int cat_launches[4] = {0, 0, 0, 0};
+  bool profile = true;
 };
 
 struct CudaBackend {
   mpc_solver *h;
   cudaStream_t s;
   cudaError_t err = cudaSuccess;
-  void eval(bool d) {
-    const int grid = h->w.B * (h->w.T + 1);
-    if (d) k_eval<true><<<grid, h->eval_threads, h->eval_smem, s>>>(h->w); else k_eval<false><<<grid, h->eval_threads, h->eval_smem, s>>>(h->w);
+  void mark(int cat) { // event before a launch of category `cat`; the matching end event is the next mark (or run end)
+    if (!h->profile) return;
+    size_t i = h->evcat.size();
+    if (i >= h->evpool.size()) { cudaEvent_t e; cudaEventCreate(&e); h->evpool.push_back(e); }
+    cudaEventRecord(h->evpool[i], s);
+    h->evcat.push_back(cat);
   }
-  void decide_eval() { k_decide_eval<<<h->w.B, 128, 0, s>>>(h->w); }
-  void riccati() { k_riccati<<<h->w.B, h->ric_threads, h->ric_smem, s>>>(h->w); }
-  void apply_step() { k_apply_step<<<h->w.B, 128, 0, s>>>(h->w); }
-  void decide_ls() { k_decide_ls<<<h->w.B, 128, 0, s>>>(h->w); }
+  void reset_counters() { mark(3); cudaMemsetAsync(h->w.counters, 0, 4 * sizeof(int32_t), s); }
+  void eval(bool d, const int32_t *list, int n) {
+    const int grid = n * (h->w.T + 1);
+    mark(d ? 0 : 2);
+    if (d) k_eval<true><<<grid, h->eval_threads, h->eval_smem, s>>>(h->w, list); else k_eval<false><<<grid, h->eval_threads, h->eval_smem, s>>>(h->w, list);
+  }
+  void decide_eval(const int32_t *list, int n, int32_t *next_eval) { mark(3); k_decide_eval<<<n, 128, 0, s>>>(h->w, list, next_eval); }
+  void riccati(const int32_t *list, int n) { mark(1); k_riccati<<<n, h->ric_threads, h->ric_smem, s>>>(h->w, list); }
+  void apply_step(const int32_t *list, int n) { mark(3); k_apply_step<<<n, 128, 0, s>>>(h->w, list); }
+  void decide_ls(const int32_t *list, int n, int32_t *ls_out, int32_t *next_eval) { mark(3); k_decide_ls<<<n, 128, 0, s>>>(h->w, list, ls_out, next_eval); mark(-1); }
   void read_counters(int *c) {
-    cudaError_t e = cudaMemcpyAsync(h->h_counters, h->w.counters, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaMemcpyAsync(h->h_counters, h->w.counters, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) { err = e; c[0] = c[1] = 0; return; }
-    c[0] = h->h_counters[0]; c[1] = h->h_counters[1];
+    if (e != cudaSuccess) { err = e; for (int i = 0; i < 4; i++) c[i] = 0; return; }
+    for (int i = 0; i < 4; i++) c[i] = h->h_counters[i];
   }
 };
 
 static int set_kernel_attrs(mpc_solver *h) {
-  if (h->w.kind == MPC_KIND_FULL) { h->eval_smem = sizeof(FullWs); h->eval_threads = 128; h->ric_smem = riccati_smem_doubles<56, 22, 78>() * 8; h->ric_threads = 256; }
+  if (h->w.kind == MPC_KIND_FULL) { h->eval_smem = sizeof(FullWs); h->eval_threads = 128; h->ric_smem = RicFastLayout<56, 22, 78>::total * 8; h->ric_threads = 256; }
   else { h->eval_smem = sizeof(CentWs); h->eval_threads = 32; h->ric_smem = riccati_smem_doubles<9, 12, 34>() * 8; h->ric_threads = 64; }
+  if (const char *e = getenv("MPCB200_RIC_THREADS")) { int t = atoi(e); if (t >= 32 && t <= 256 && h->w.kind == MPC_KIND_FULL) h->ric_threads = t; }
   CK(cudaFuncSetAttribute(k_eval<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FullWs)));
   CK(cudaFuncSetAttribute(k_eval<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FullWs)));
-  CK(cudaFuncSetAttribute(k_riccati, cudaFuncAttributeMaxDynamicSharedMemorySize, riccati_smem_doubles<56, 22, 78>() * 8));
+  CK(cudaFuncSetAttribute(k_riccati, cudaFuncAttributeMaxDynamicSharedMemorySize, RicFastLayout<56, 22, 78>::total * 8));
   return 0;
 }
 
@@ -167,6 +178,7 @@ void mpc_destroy(mpc_solver_t *h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   for (void *p : h->allocs) cudaFree(p);
+  for (cudaEvent_t e : h->evpool) cudaEventDestroy(e);
   if (h->d_xs_in) cudaFree(h->d_xs_in);
   if (h->d_us_in) cudaFree(h->d_us_in);
   if (h->d_model) cudaFree(h->d_model);
@@ -251,13 +263,27 @@ int32_t mpc_set_x0(mpc_solver_t *h, const double *x0) {
 static int run_impl(mpc_solver *h, const double *d_xs, const double *d_us, int max_iters, cudaStream_t s, bool sync_events) {
   if (!h->setup_done) return fail("mpc_run before mpc_setup");
   CK(cudaEventRecord(h->ev0, s));
-  k_init<<<h->w.B, 128, 0, s>>>(h->w, d_xs, d_us, max_iters);
+  h->evcat.clear();
   CudaBackend be{h, s};
-  h->last_launches = 1 + run_loop(be, max_iters, h->w.sc);
+  be.mark(3);
+  k_init<<<h->w.B, 128, 0, s>>>(h->w, d_xs, d_us, max_iters);
+  h->last_launches = 1 + run_loop(be, h->w, max_iters, h->w.sc);
+  be.mark(-1);
   CK(cudaEventRecord(h->ev1, s));
   if (be.err != cudaSuccess) return fail(std::string("kernel failure: ") + cudaGetErrorString(be.err));
   CK(cudaGetLastError());
-  if (sync_events) { CK(cudaEventSynchronize(h->ev1)); CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1)); }
+  if (sync_events) {
+    CK(cudaEventSynchronize(h->ev1));
+    CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    for (int c = 0; c < 4; c++) { h->cat_ms[c] = 0; h->cat_launches[c] = 0; }
+    for (size_t i = 0; i + 1 < h->evcat.size(); i++) {
+      int c = h->evcat[i];
+      if (c < 0) continue;
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, h->evpool[i], h->evpool[i + 1]));
+      h->cat_ms[c] += ms; h->cat_launches[c]++;
+    }
+  }
   return 0;
 }
 
@@ -295,7 +321,7 @@ int32_t mpc_get_results(mpc_solver_t *h, double *xs, double *us, double *K, doub
     for (int b = 0; b < w.B; b++) {
       const InstState &t = st[b];
       info[b].prim_infeas = t.prim_infeas; info[b].dual_infeas = t.dual_infeas; info[b].traj_cost = t.traj_cost; info[b].merit = t.merit;
-      info[b].mu = t.mu; info[b].num_iters = t.num_iters; info[b].al_iters = t.al_iters; info[b].conv = t.conv; info[b].status = t.status;
+      info[b].mu = t.mu; info[b].alpha = t.alpha; info[b].ls_evals = t.ls_evals; info[b].pad_ = 0; info[b].num_iters = t.num_iters; info[b].al_iters = t.al_iters; info[b].conv = t.conv; info[b].status = t.status;
     }
   return 0;
 }
@@ -322,6 +348,20 @@ int32_t mpc_get_stage_data(mpc_solver_t *h, int32_t k, double *xdot, double *con
 }
 
 int32_t mpc_last_launches(mpc_solver_t *h) { return h->last_launches; }
+double mpc_last_kernel_ms(mpc_solver_t *h, int32_t category) { return (category >= 0 && category < 4) ? h->cat_ms[category] : -1.0; }
+int32_t mpc_last_kernel_launches(mpc_solver_t *h, int32_t category) { return (category >= 0 && category < 4) ? h->cat_launches[category] : -1; }
+void mpc_set_profiling(mpc_solver_t *h, int32_t on) { h->profile = on != 0; }
+
+int32_t mpc_get_feedback(mpc_solver_t *h, int32_t k, double *K) {
+  CK(cudaSetDevice(h->device));
+  if (!h->setup_done) return fail("mpc_get_feedback before mpc_setup");
+  Ws &w = h->w;
+  if (k < 0 || k >= w.T) return fail("stage index out of range");
+  const size_t sz = (size_t)w.m * w.n * 8;
+  CK(cudaMemcpy2DAsync(K, sz, w.Kfb + (size_t)k * w.m * w.n, (size_t)w.T * sz, sz, w.B, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
 double mpc_last_device_ms(mpc_solver_t *h) { return h->last_ms; }
 uint64_t mpc_workspace_bytes(mpc_solver_t *h) { return h->bytes; }
 
@@ -336,7 +376,8 @@ int32_t mpc_debug_lq(mpc_solver_t *h, const double *xs, const double *us, int32_
   CK(cudaMemcpyAsync(h->d_us_in, us, (size_t)w.B * w.T * w.m * 8, cudaMemcpyHostToDevice, h->stream));
   k_init<<<w.B, 128, 0, h->stream>>>(w, h->d_xs_in, h->d_us_in, 1);
   CudaBackend be{h, h->stream};
-  be.eval(true); be.decide_eval();
+  be.reset_counters();
+  be.eval(true, eval_list(w, 0), w.B); be.decide_eval(eval_list(w, 0), w.B, eval_list(w, 1));
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
   const size_t b = inst;
@@ -346,6 +387,30 @@ int32_t mpc_debug_lq(mpc_solver_t *h, const double *xs, const double *us, int32_
   if (gap) CK(cudaMemcpy(gap, w.gap + b * T * w.n, T * w.n * 8, cudaMemcpyDeviceToHost));
   if (hval) CK(cudaMemcpy(hval, w.h + b * T1 * w.nc, T1 * w.nc * 8, cudaMemcpyDeviceToHost));
   if (scal) CK(cudaMemcpy(scal, w.scal + b * T1 * SC_COUNT, T1 * SC_COUNT * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+__global__ void k_gemm_tn_test(int mt, int nt, int K, const double *A, int lda, const double *B, int ldb, double *C, int ldc) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *sA = reinterpret_cast<double *>(smem_raw), *sB = sA + K * lda, *sC = sB + K * ldb;
+  for (int i = threadIdx.x; i < K * lda; i += blockDim.x) sA[i] = A[i];
+  for (int i = threadIdx.x; i < K * ldb; i += blockDim.x) sB[i] = B[i];
+  __syncthreads();
+  mma_tn(mt, nt, K, sA, lda, sB, ldb, sC, ldc, nullptr, 0, 0, 0, false);
+  for (int i = threadIdx.x; i < 8 * mt * ldc; i += blockDim.x) C[i] = sC[i];
+}
+
+// unit-test hook for the DMMA tile GEMM: C (8mt x 8nt) = A^T B, A [K][lda], B [K][ldb], host pointers
+int32_t mpc_debug_gemm_tn(int32_t mt, int32_t nt, int32_t K, const double *A, int32_t lda, const double *B, int32_t ldb, double *C, int32_t ldc) {
+  double *dA, *dB, *dC;
+  size_t sa = (size_t)K * lda * 8, sb = (size_t)K * ldb * 8, sc = (size_t)8 * mt * ldc * 8;
+  CK(cudaMalloc(&dA, sa)); CK(cudaMalloc(&dB, sb)); CK(cudaMalloc(&dC, sc));
+  CK(cudaMemcpy(dA, A, sa, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dB, B, sb, cudaMemcpyHostToDevice));
+  CK(cudaFuncSetAttribute(k_gemm_tn_test, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sa + sb + sc)));
+  k_gemm_tn_test<<<1, 256, sa + sb + sc>>>(mt, nt, K, dA, lda, dB, ldb, dC, ldc);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(C, dC, sc, cudaMemcpyDeviceToHost));
+  cudaFree(dA); cudaFree(dB); cudaFree(dC);
   return 0;
 }
 

@@ -10,6 +10,7 @@
 #include "eval_cent.cuh"
 #include "eval_full.cuh"
 #include "riccati.cuh"
+#include "riccati_fast.cuh"
 
 namespace mpcdev {
 
@@ -36,7 +37,7 @@ struct InstState {
   double mu, inner_tol, prim_tol, preg;
   double prim_infeas, dual_infeas, inner_crit, traj_cost, merit;
   double dphi0, alpha, a_prev, phi_prev;
-  int32_t num_iters, al_iters, conv, status, mode, ls_it, max_iters, pad;
+  int32_t num_iters, al_iters, conv, status, mode, ls_it, max_iters, ls_evals;
 };
 
 struct Ws {
@@ -52,8 +53,11 @@ struct Ws {
   double *gap, *h, *scal, *tscal, *xdot, *lamc;
   double *W, *pt, *K, *Kfb, *dphi;
   InstState *st;
-  int32_t *counters; // [0] instances still in MODE_LS, [1] instances not DONE
+  int32_t *counters; // [0] instances still in MODE_LS (next ls list), [2] instances to evaluate in the next pass
+  int32_t *lists;    // [4][B] compacted instance lists: 0,1 = evaluation lists (double-buffered), 2,3 = linesearch lists
 };
+HDH int32_t *eval_list(const Ws &w, int which) { return w.lists + (size_t)(which & 1) * w.B; }
+HDH int32_t *ls_list(const Ws &w, int which) { return w.lists + (size_t)(2 + (which & 1)) * w.B; }
 
 HD KnotIO make_io(const Ws &w, int b, int k, bool trial) {
   KnotIO io;
@@ -89,12 +93,13 @@ HD void init_instance(const Ws &w, int b, const double *xs_in, const double *us_
   PAR_FOR(i, (int)(T1 * w.n)) w.lams_prev[b * T1 * w.n + i] = w.lams[b * T1 * w.n + i];
   PAR_FOR(i, 6) w.gE[b * T1 * 6 + i] = 0.0;
   ONE_THREAD {
+    eval_list(w, 0)[b] = b;
     InstState &s = w.st[b];
     const SolverConst &c = w.sc;
     s.mu = c.mu_init; s.preg = c.reg_init;
     s.prim_tol = fmax(pow(s.mu, c.prim_alpha), c.tol);
     s.inner_tol = fmax(pow(s.mu, c.dual_alpha), c.tol);
-    s.num_iters = 0; s.al_iters = 0; s.conv = 0; s.status = 1; s.ls_it = 0; s.max_iters = max_iters;
+    s.num_iters = 0; s.al_iters = 0; s.conv = 0; s.status = 1; s.ls_it = 0; s.max_iters = max_iters; s.ls_evals = 0;
     s.mode = (max_iters > 0) ? MODE_EVAL : MODE_DONE;
     s.prim_infeas = s.dual_infeas = s.inner_crit = s.traj_cost = s.merit = 0;
     s.dphi0 = s.alpha = s.a_prev = s.phi_prev = 0;
@@ -102,7 +107,7 @@ HD void init_instance(const Ws &w, int b, const double *xs_in, const double *us_
 }
 
 // ---- after eval<deriv>: reduce the per-knot partials, finish the dual residual (base block of E^T lam), BCL logic
-HD void decide_eval(const Ws &w, int b, double *red /* shared, >= 8 doubles */) {
+HD void decide_eval(const Ws &w, int b, double *red /* shared, >= 8 doubles */, int32_t *next_eval) {
   const size_t T1 = (size_t)w.T + 1;
   InstState &s = w.st[b];
   if (s.mode != MODE_EVAL) return;
@@ -141,6 +146,7 @@ HD void decide_eval(const Ws &w, int b, double *red /* shared, >= 8 doubles */) 
         s.inner_tol = fmax(s.inner_tol, 0.01 * c.tol); s.prim_tol = fmax(s.prim_tol, c.tol);
         s.al_iters++;
         if (s.al_iters >= c.max_al_iters) s.mode = MODE_DONE; // else stays MODE_EVAL: re-evaluate with the new estimates
+        else next_eval[ATOMIC_INC(&w.counters[2])] = b;
       }
     } else s.mode = MODE_STEP;
   }
@@ -188,7 +194,7 @@ HD void start_linesearch(const Ws &w, int b) {
 }
 
 // ---- after eval<values> at the trial point: Armijo test, next alpha or accept (proxsuite-nlp style backtracking)
-HD void decide_ls(const Ws &w, int b, double *red) {
+HD void decide_ls(const Ws &w, int b, double *red, int32_t *ls_out, int32_t *next_eval) {
   const size_t T1 = (size_t)w.T + 1;
   InstState &s = w.st[b];
   if (s.mode != MODE_LS) return;
@@ -197,6 +203,7 @@ HD void decide_ls(const Ws &w, int b, double *red) {
     double cost = 0, pen = 0;
     for (int k = 0; k <= w.T; k++) { const double *sc = w.tscal + (b * T1 + k) * SC_COUNT; cost += sc[SC_COST]; pen += sc[SC_PEN]; }
     const double phi = cost + pen, phi0 = s.merit, dphi0 = s.dphi0, alpha = s.alpha;
+    s.ls_evals++;
     bool accept = (phi <= phi0 + c.ls_c1 * alpha * dphi0) || alpha <= c.ls_alpha_min || s.ls_it + 1 >= c.ls_max_steps;
     red[0] = accept ? 1.0 : 0.0;
     if (accept) {
@@ -227,6 +234,8 @@ HD void decide_ls(const Ws &w, int b, double *red) {
       s.alpha = fmax(a_new, c.ls_alpha_min);
       s.ls_it++;
     }
+    if (s.mode == MODE_LS) ls_out[ATOMIC_INC(&w.counters[0])] = b;
+    else if (s.mode == MODE_EVAL) next_eval[ATOMIC_INC(&w.counters[2])] = b;
   }
   SYNC();
   if (red[0] != 0.0) { // accept: trial -> current
@@ -268,7 +277,7 @@ HD RiccatiIO make_riccati_io(const Ws &w, int b) {
 HD void riccati_dispatch(const Ws &w, int b, double *smem) {
   if (w.st[b].mode != MODE_STEP) return;
   RiccatiIO r = make_riccati_io(w, b);
-  if (w.kind == MPC_KIND_FULL) riccati_instance<56, 22, 78>(r, smem);
+  if (w.kind == MPC_KIND_FULL) riccati_instance_fast<56, 22, 78>(r, smem);
   else if (w.kind == MPC_KIND_CENT) riccati_instance<9, 12, 34>(r, smem);
   start_linesearch(w, b);
 }

@@ -149,3 +149,122 @@ def cent_standing_problem(batch=1, T=100, robot=None, **kw):
     x0[:3] = com0
     return dict(robot=rb, cfg=cfg, knots=knots, terms=terms, x0=np.tile(x0, (batch, 1)), xs=np.tile(x0, (batch, T + 1, 1)),
                 us=np.tile(u0, (batch, T, 1)), lf=lf, rf=rf, com0=com0, mass=mass)
+
+
+# ---------------------------------------------------------------- synthetic walking batches (BASELINE.json configs 4-5)
+def swing_bump(s, apex):
+    """Vertical profile of the degree-8 Bezier swing curve of talos_utils.py:281-296 when start == final
+    (x_forward = 0, fulldynamic_talos.py:352): control points 4 x start, start + apex, 4 x final."""
+    return 70.0 * s ** 4 * (1.0 - s) ** 4 * apex
+
+
+def perturbed_x0(rb, x0, rng, batch):
+    """SURVEY 8d config 4: x0_i = x0 (+) delta_i, sigma = 0.01 (base pos), 0.02 (base ori, joints), 0.05 (velocities);
+    samples violating the joint limits are rejected."""
+    sig = np.concatenate([[0.01] * 3, [0.02] * 3, [0.02] * 22, [0.05] * 28])
+    lo, hi = np.array(rb.q_lo[:]), np.array(rb.q_hi[:])
+    out = np.zeros((batch, 57))
+    from .kinematics import quat_to_R  # noqa: F401  (host-side helper only)
+
+    for i in range(batch):
+        while True:
+            d = rng.normal(size=56) * sig
+            x = x0.copy()
+            # base: p += R * dp (first order is exact enough for the perturbation), quaternion (x) exp(dw)
+            R = quat_to_R(x0[3:7])
+            x[0:3] = x0[0:3] + R @ d[0:3]
+            th = np.linalg.norm(d[3:6])
+            dq = np.concatenate([np.sin(th / 2) * d[3:6] / th, [np.cos(th / 2)]]) if th > 0 else np.array([0, 0, 0, 1.0])
+            qx, qy, qz, qw = x0[3:7]
+            dx_, dy_, dz_, dw_ = dq
+            x[3:7] = [qw * dx_ + qx * dw_ + qy * dz_ - qz * dy_, qw * dy_ - qx * dz_ + qy * dw_ + qz * dx_,
+                      qw * dz_ + qx * dy_ - qy * dx_ + qz * dw_, qw * dw_ - qx * dx_ - qy * dy_ - qz * dz_]
+            x[7:29] = x0[7:29] + d[6:28]
+            x[29:57] = x0[29:57] + d[28:56]
+            if np.all(x[7:29] > lo) and np.all(x[7:29] < hi):
+                out[i] = x
+                break
+    return out
+
+
+def random_schedule(rng, T, min_first_ds=30):
+    """One random walking contact schedule of T knots.  Like the reference gait (fulldynamic_talos.py:248-266) it
+    starts in double support for at least `min_first_ds` knots (the reference's T_ds = 30: the time the robot needs
+    to shift its weight), then alternates single / double support with random durations and a random first swing
+    foot.  Returns (phases, swing_pos, swing_len): contact pair, index inside the current swing and its length."""
+    first = int(rng.integers(min_first_ds, min_first_ds + 31))
+    t_ss = int(rng.integers(60, 101))
+    t_ds = int(rng.integers(20, 41))
+    left_first = bool(rng.integers(0, 2))
+    phases, pos, length = [], [], []
+    phases += [[True, True]] * first
+    pos += [0] * first
+    length += [1] * first
+    stance_left = left_first
+    while len(phases) < T:
+        cs = [True, False] if stance_left else [False, True]
+        phases += [cs] * t_ss
+        pos += list(range(t_ss))
+        length += [t_ss] * t_ss
+        phases += [[True, True]] * t_ds
+        pos += [0] * t_ds
+        length += [1] * t_ds
+        stance_left = not stance_left
+    return phases[:T], pos[:T], length[:T]
+
+
+def full_walk_batch(batch, seed=5, T=100, robot=None, swing_apex=0.15, perturb=True, **kw):
+    """BASELINE.json config 5: batch of full-dynamics MPC problems with RANDOM CONTACT SCHEDULES.
+    Instance i gets its own gait (random initial double-support length, single/double-support durations and first
+    swing foot; `random_schedule`), swing-foot references following the Bezier bump of talos_utils.py:281-296,
+    a perturbed initial state and the terminal CoM equality of the MPC loop
+    (fulldynamic_talos.py:499-507).  Every stage uses force-reference index 0 as the reference does (full:363-366)."""
+    rb, q0, x0, lf, rf, com0, mass = base_setup(robot)
+    cfg = full_config(rb, x0, lf, rf, T=T, **kw)
+    rng = np.random.default_rng(seed)
+    f_half = mass * GRAVITY / 2.0
+    fr = np.array([0, 0, f_half, 0, 0, 0.0])
+    knots = (_abi.Knot * (batch * T))()
+    terms = (_abi.Term * batch)()
+    n_ds = 0
+    for i in range(batch):
+        phases, pos, length = random_schedule(rng, T)
+        for j in range(T):
+            cs = phases[j]
+            lref, rref = np.array(lf, float), np.array(rf, float)
+            if cs != [True, True]:
+                bump = swing_bump(pos[j] / float(length[j]), swing_apex)
+                if cs[0]:
+                    rref[11] += bump  # right foot swings
+                else:
+                    lref[11] += bump
+            else:
+                n_ds += 1
+            knots[i * T + j] = full_knot(cs, lref, rref, fr, fr)
+        com_final = np.array([(lf[9] + rf[9]) / 2, (lf[10] + rf[10]) / 2, com0[2]])
+        terms[i] = make_term(lf, rf, com_final)
+    x0s = perturbed_x0(rb, x0, rng, batch) if perturb else np.tile(x0, (batch, 1))
+    xs = np.repeat(x0s[:, None, :], T + 1, axis=1)
+    us = np.zeros((batch, T, 22))
+    return dict(robot=rb, cfg=cfg, knots=knots, terms=terms, x0=x0s, xs=xs, us=us, lf=lf, rf=rf, com0=com0, mass=mass,
+                ds_fraction=n_ds / float(batch * T))
+
+
+def sub_problem(prob, lo, hi):
+    """Instances [lo, hi) of a batch problem (for bounded CPU-baseline samples and multi-GPU shards)."""
+    T = prob["cfg"].T
+    n = hi - lo
+    knots = (_abi.Knot * (n * T))(*[prob["knots"][i] for i in range(lo * T, hi * T)])
+    terms = (_abi.Term * n)(*[prob["terms"][i] for i in range(lo, hi)])
+    out = dict(prob)
+    out.update(knots=knots, terms=terms, x0=prob["x0"][lo:hi].copy(), xs=prob["xs"][lo:hi].copy(), us=prob["us"][lo:hi].copy())
+    return out
+
+
+def lq_flops(n, m, c):
+    """ALGORITHMIC dense-LQ FLOPs per knot: backward + forward."""
+    s = m + c
+    back = (n ** 3 / 3 + 2 * n ** 3 + 4 * n ** 2) + (2 * n ** 3 + 2 * n * n * m) + (2 * n ** 3 + 2 * n * n * m + 2 * n * m * m + 2 * n * n + 2 * n * m) \
+        + (s ** 3 / 3 + 2 * s * s * (1 + n)) + (2 * n * n * s + 2 * n * s)
+    fwd = 2 * s * n + 2 * n * n + 2 * n * m
+    return back + fwd

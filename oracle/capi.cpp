@@ -226,7 +226,7 @@ int orc_solve(const mpc_robot_t *rb, const mpc_config_t *cfg, int batch, const m
       if (info) {
         mpc_info_t &o = info[b];
         o.prim_infeas = S.prim_infeas; o.dual_infeas = S.dual_infeas; o.traj_cost = S.traj_cost; o.merit = S.merit; o.mu = S.mu;
-        o.num_iters = S.num_iters; o.al_iters = S.al_iters; o.conv = S.conv; o.status = S.status;
+        o.num_iters = S.num_iters; o.al_iters = S.al_iters; o.conv = S.conv; o.status = S.status; o.alpha = S.alpha_last; o.ls_evals = S.ls_evals; o.pad_ = 0;
       }
       if (stage0) { std::copy(S.ev[0].xdot, S.ev[0].xdot + 56, stage0 + (size_t)b * 68); std::copy(S.ev[0].lam, S.ev[0].lam + 12, stage0 + (size_t)b * 68 + 56); }
     }

@@ -76,7 +76,8 @@ struct Solver {
   // results
   double mu = 0, inner_tol = 1, prim_tol = 1, preg = 0;
   double prim_infeas = 0, dual_infeas = 0, inner_crit = 0, traj_cost = 0, merit = 0;
-  int num_iters = 0, al_iters = 0, conv = 0, status = 1;
+  int num_iters = 0, al_iters = 0, conv = 0, status = 1, ls_evals = 0;
+  double alpha_last = 0;
   std::vector<double> alphas;
 
   Solver(const Problem &p, const SolverParams &s) : P(p), prm(s), d(p.d) {}
@@ -267,6 +268,7 @@ struct Solver {
     for (int it = 0;; it++) {
       double c;
       double phi = try_step(in, alpha, &c);
+      ls_evals++;
       phi_out = phi; cost_out = c;
       if (phi <= phi0 + prm.ls_c1 * alpha * dphi0) return alpha;
       if (alpha <= prm.ls_alpha_min || it + 1 >= prm.ls_max_steps) return alpha;
@@ -299,7 +301,7 @@ struct Solver {
     mu = prm.mu_init; preg = prm.reg_init;
     tols_on_failure();
     inner_tol = std::max(inner_tol, prm.tol); prim_tol = std::max(prim_tol, prm.tol);
-    num_iters = 0; al_iters = 0; conv = 0; status = 1;
+    num_iters = 0; al_iters = 0; conv = 0; status = 1; ls_evals = 0; alpha_last = 0;
     alphas.clear();
     while (num_iters < max_iters && al_iters < prm.max_al_iters) {
       evaluate(in, xs.data(), us.data(), true, ev);
@@ -323,7 +325,7 @@ struct Solver {
       double dphi0 = directional_derivative();
       double phi_new, cost_new;
       double alpha = linesearch(in, merit, dphi0, phi_new, cost_new);
-      alphas.push_back(alpha);
+      alphas.push_back(alpha); alpha_last = alpha;
       if (!std::isfinite(phi_new)) { status = 2; break; }
       xs.swap(txs); us.swap(tus); vs.swap(tvs); lams.swap(tlams);
       ev.swap(tr); // values at the accepted point (xdot, contact forces: workspace read-back, full:467-480)

@@ -14,23 +14,19 @@ struct EmuBackend {
   Ws w;
   std::vector<double> smem;
   EmuBackend() : smem(40000, 0.0) {}
-  void eval(bool d) {
-    for (int b = 0; b < w.B; b++)
-      for (int k = 0; k <= w.T; k++) { if (d) eval_dispatch<true>(w, b, k, smem.data()); else eval_dispatch<false>(w, b, k, smem.data()); }
+  void reset_counters() { for (int i = 0; i < 4; i++) w.counters[i] = 0; }
+  void eval(bool d, const int32_t *list, int n) {
+    for (int i = 0; i < n; i++)
+      for (int k = 0; k <= w.T; k++) { if (d) eval_dispatch<true>(w, list[i], k, smem.data()); else eval_dispatch<false>(w, list[i], k, smem.data()); }
   }
-  void decide_eval() { double red[8]; for (int b = 0; b < w.B; b++) mpcdev::decide_eval(w, b, red); }
-  void riccati() { for (int b = 0; b < w.B; b++) riccati_dispatch(w, b, smem.data()); }
-  void apply_step() { for (int b = 0; b < w.B; b++) mpcdev::apply_step(w, b); }
-  void decide_ls() {
+  void decide_eval(const int32_t *list, int n, int32_t *next_eval) { double red[8]; for (int i = 0; i < n; i++) mpcdev::decide_eval(w, list[i], red, next_eval); }
+  void riccati(const int32_t *list, int n) { for (int i = 0; i < n; i++) riccati_dispatch(w, list[i], smem.data()); }
+  void apply_step(const int32_t *list, int n) { w.counters[0] = 0; for (int i = 0; i < n; i++) mpcdev::apply_step(w, list[i]); }
+  void decide_ls(const int32_t *list, int n, int32_t *ls_out, int32_t *next_eval) {
     double red[8];
-    w.counters[0] = w.counters[1] = 0;
-    for (int b = 0; b < w.B; b++) {
-      mpcdev::decide_ls(w, b, red);
-      if (w.st[b].mode == MODE_LS) w.counters[0]++;
-      if (w.st[b].mode != MODE_DONE) w.counters[1]++;
-    }
+    for (int i = 0; i < n; i++) mpcdev::decide_ls(w, list[i], red, ls_out, next_eval);
   }
-  void read_counters(int *c) { c[0] = w.counters[0]; c[1] = w.counters[1]; }
+  void read_counters(int *c) { for (int i = 0; i < 4; i++) c[i] = w.counters[i]; }
 };
 
 extern "C" int emu_solve(const mpc_robot_t *rb, const mpc_config_t *cfg, int batch, const mpc_knot_t *knots, const mpc_term_t *terms,
@@ -56,12 +52,12 @@ extern "C" int emu_solve(const mpc_robot_t *rb, const mpc_config_t *cfg, int bat
   if (lams) std::memcpy(w.lams, lams, 8 * batch * T1 * w.n);
   for (int b = 0; b < batch; b++) init_instance(w, b, xs, us, max_iters);
   if (lq_dump) { // single derivative pass, dump instance 0
-    be.eval(true); be.decide_eval();
+    be.reset_counters(); be.eval(true, eval_list(w, 0), w.B); be.decide_eval(eval_list(w, 0), w.B, eval_list(w, 1));
     size_t o = 0;
     auto put = [&](const double *p, size_t n) { std::memcpy(lq_dump + o, p, 8 * n); o += n; };
     put(w.AB, (size_t)w.T * w.n * w.nz); put(w.H, T1 * w.nz * w.nz); put(w.g, T1 * w.nz); put(w.gap, (size_t)w.T * w.n); put(w.h, T1 * w.nc);
     put(w.scal, T1 * SC_COUNT);
-  } else run_loop(be, max_iters, w.sc);
+  } else run_loop(be, w, max_iters, w.sc);
   std::memcpy(xs, w.xs, 8 * batch * T1 * w.nx);
   std::memcpy(us, w.us, 8 * batch * w.T * w.m);
   if (K) std::memcpy(K, w.Kfb, 8 * (size_t)batch * w.T * w.m * w.n);
@@ -69,7 +65,7 @@ extern "C" int emu_solve(const mpc_robot_t *rb, const mpc_config_t *cfg, int bat
   if (lams) std::memcpy(lams, w.lams, 8 * batch * T1 * w.n);
   for (int b = 0; b < batch; b++) {
     const InstState &s = w.st[b];
-    if (info) { mpc_info_t &o = info[b]; o.prim_infeas = s.prim_infeas; o.dual_infeas = s.dual_infeas; o.traj_cost = s.traj_cost; o.merit = s.merit; o.mu = s.mu;
+    if (info) { mpc_info_t &o = info[b]; o.prim_infeas = s.prim_infeas; o.dual_infeas = s.dual_infeas; o.traj_cost = s.traj_cost; o.merit = s.merit; o.mu = s.mu; o.alpha = s.alpha; o.ls_evals = s.ls_evals; o.pad_ = 0;
       o.num_iters = s.num_iters; o.al_iters = s.al_iters; o.conv = s.conv; o.status = s.status; }
     if (stage0) { std::memcpy(stage0 + b * 68, w.xdot + b * T1 * 56, 8 * 56); std::memcpy(stage0 + b * 68 + 56, w.lamc + b * T1 * 12, 8 * 12); }
   }

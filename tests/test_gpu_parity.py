@@ -84,3 +84,19 @@ def test_mpc_tick_matches_oracle(oracle):
     xdot, force = s.stage_data(0)
     assert rel(force, ref["stage0"][:, 56:]) < RTOL
     s.close()
+
+
+def test_dmma_tile_gemm_matches_numpy():
+    """FP64 tensor-core tile GEMM (mma.sync m8n8k4) used by the Riccati kernel, against numpy."""
+    import ctypes as C
+
+    from mpc_benchmark_b200 import _native
+
+    rng = np.random.default_rng(0)
+    for mt, nt, K, lda, ldb, ldc in [(7, 7, 56, 56, 56, 56), (7, 10, 56, 56, 88, 88), (10, 10, 56, 88, 88, 80), (1, 3, 4, 8, 24, 24)]:
+        A = np.ascontiguousarray(rng.normal(size=(K, lda)))
+        B = np.ascontiguousarray(rng.normal(size=(K, ldb)))
+        Cm = np.zeros((8 * mt, ldc))
+        _native.check(_native.lib().mpc_debug_gemm_tn(mt, nt, K, _native.ptr(A), lda, _native.ptr(B), ldb, _native.ptr(Cm), ldc), "gemm")
+        ref = A[:, : 8 * mt].T @ B[:, : 8 * nt]
+        assert np.abs(Cm[:, : 8 * nt] - ref).max() < 1e-12 * K
