@@ -121,6 +121,10 @@ int32_t mpc_update_knots(mpc_solver_t *h, const mpc_knot_t *knots, int32_t first
 int32_t mpc_update_terms(mpc_solver_t *h, const mpc_term_t *terms);
 /* replaceStageCircular + cycleAppend (full:496-497): drop knot 0, append `last` ([batch]) at T-1. */
 int32_t mpc_cycle(mpc_solver_t *h, const mpc_knot_t *last);
+/* solver.cycleProblem / workspace.cycleAppend (kino:488, full:497): shift the warm multipliers by n knots. */
+int32_t mpc_shift_multipliers(mpc_solver_t *h, int32_t n);
+/* New robot / weight constants for the same kind, horizon and batch (the shim re-derives them from the object graph at every run). */
+int32_t mpc_reconfigure(mpc_solver_t *h, const mpc_robot_t *robot, const mpc_config_t *cfg);
 /* problem.x0_init = x (full:536); host pointer [batch][nx]. */
 int32_t mpc_set_x0(mpc_solver_t *h, const double *x0);
 

@@ -37,7 +37,7 @@ class BatchResults:
 
 
 class BatchSolver:
-    def __init__(self, robot, cfg, batch, device=0):
+    def __init__(self, robot, cfg, batch, device=0, **_unused):
         self.robot, self.cfg, self.batch, self.device = robot, cfg, int(batch), int(device)
         self.nx, self.n, self.m, self.nc = _abi.DIMS[cfg.kind]
         self.T = cfg.T
@@ -73,6 +73,13 @@ class BatchSolver:
     def cycle(self, last_knots):
         assert len(last_knots) == self.batch
         _native.check(_native.lib().mpc_cycle(self._h, C.cast(last_knots, C.c_void_p)), "mpc_cycle")
+
+    def reconfigure(self, robot, cfg):
+        self.robot, self.cfg = robot, cfg
+        _native.check(_native.lib().mpc_reconfigure(self._h, C.byref(robot), C.byref(cfg)), "mpc_reconfigure")
+
+    def shift_multipliers(self, n=1):
+        _native.check(_native.lib().mpc_shift_multipliers(self._h, int(n)), "mpc_shift_multipliers")
 
     def set_x0(self, x0):
         x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(self.batch, self.nx)

@@ -252,6 +252,40 @@ int32_t mpc_cycle(mpc_solver_t *h, const mpc_knot_t *last) {
   return 0;
 }
 
+// shift the warm multipliers by `n` knots: vs[k] <- vs[k+n], lams[k] <- lams[k+n], tail zeroed
+__global__ void k_shift_multipliers(Ws w, int n) {
+  const size_t b = blockIdx.x, T1 = (size_t)w.T + 1;
+  double *V = w.vs + b * T1 * w.nc, *L = w.lams + b * T1 * w.n;
+  for (int k = 0; k <= w.T; k++) {
+    const bool src = (k + n <= w.T);
+    for (int i = threadIdx.x; i < w.nc; i += blockDim.x) V[(size_t)k * w.nc + i] = src ? V[(size_t)(k + n) * w.nc + i] : 0.0;
+    for (int i = threadIdx.x; i < w.n; i += blockDim.x) L[(size_t)k * w.n + i] = src ? L[(size_t)(k + n) * w.n + i] : 0.0;
+    __syncthreads();
+  }
+}
+
+int32_t mpc_shift_multipliers(mpc_solver_t *h, int32_t n) {
+  CK(cudaSetDevice(h->device));
+  if (!h->setup_done) return fail("mpc_shift_multipliers before mpc_setup");
+  if (n <= 0) return 0;
+  k_shift_multipliers<<<h->w.B, 128, 0, h->stream>>>(h->w, n);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// swap in new model / weight constants without touching the workspace (same kind, horizon and batch)
+int32_t mpc_reconfigure(mpc_solver_t *h, const mpc_robot_t *robot, const mpc_config_t *cfg) {
+  CK(cudaSetDevice(h->device));
+  if (cfg->kind != h->w.kind || cfg->T != h->w.T) return fail("mpc_reconfigure: kind / horizon must not change");
+  const char *err = nullptr;
+  if (build_dev_model(robot, cfg, &h->h_model, &err)) return fail(err);
+  h->w.sc = default_consts(cfg->tol, cfg->mu_init);
+  CK(cudaMemcpyAsync(h->d_model, &h->h_model, sizeof(DevModel), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 int32_t mpc_set_x0(mpc_solver_t *h, const double *x0) {
   CK(cudaSetDevice(h->device));
   if (!h->setup_done) return fail("mpc_set_x0 before mpc_setup");

@@ -1,0 +1,56 @@
+"""ctypes binding of tests/_emu/libemu.so: the CUDA kernel SOURCES (mpc_benchmark_b200/csrc/*.cuh) compiled for the host
+with serial PAR_FOR loops.  TEST-ONLY: checks kernel logic on machines without a GPU; never loaded by the product."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from mpc_benchmark_b200 import _abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB = os.path.join(ROOT, "tests", "_emu", "libemu.so")
+dp = C.POINTER(C.c_double)
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "emu")], stdout=subprocess.DEVNULL)
+        _lib = C.CDLL(_LIB)
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(dp) if a is not None else None
+
+
+def solve(prob, max_iters, dump=False, xs=None, us=None, vs=None, lams=None):
+    cfg = prob["cfg"]
+    nx, n, m, nc = _abi.DIMS[cfg.kind]
+    T, B, nz = cfg.T, prob["x0"].shape[0], n + m
+    xs = np.ascontiguousarray(prob["xs"] if xs is None else xs, float).copy()
+    us = np.ascontiguousarray(prob["us"] if us is None else us, float).copy()
+    K = np.zeros((B, T, m, n))
+    vs = np.zeros((B, T + 1, nc)) if vs is None else vs.copy()
+    lams = np.zeros((B, T + 1, n)) if lams is None else lams.copy()
+    info = (_abi.Info * B)()
+    st = np.zeros((B, 68))
+    d = np.zeros(T * n * nz + (T + 1) * nz * nz + (T + 1) * nz + T * n + (T + 1) * nc + (T + 1) * 8) if dump else None
+    rc = lib().emu_solve(C.byref(prob["robot"]), C.byref(cfg), B, prob["knots"], prob["terms"], _p(np.ascontiguousarray(prob["x0"], float)),
+                         _p(xs), _p(us), _p(K), _p(vs), _p(lams), info, _p(st), int(max_iters), _p(d))
+    assert rc == 0
+    out = dict(xs=xs, us=us, K=K, vs=vs, lams=lams, info=info, stage0=st)
+    if dump:
+        o = 0
+
+        def take(sh):
+            nonlocal o
+            s = int(np.prod(sh))
+            a = d[o:o + s].reshape(sh)
+            o += s
+            return a
+
+        out.update(AB=take((T, n, nz)), H=take((T + 1, nz, nz)), g=take((T + 1, nz)), gap=take((T, n)), h=take((T + 1, nc)), scal=take((T + 1, 8)))
+    return out

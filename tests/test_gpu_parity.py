@@ -100,3 +100,104 @@ def test_dmma_tile_gemm_matches_numpy():
         _native.check(_native.lib().mpc_debug_gemm_tn(mt, nt, K, _native.ptr(A), lda, _native.ptr(B), ldb, _native.ptr(Cm), ldc), "gemm")
         ref = A[:, : 8 * mt].T @ B[:, : 8 * nt]
         assert np.abs(Cm[:, : 8 * nt] - ref).max() < 1e-12 * K
+
+
+@pytest.mark.parametrize("name", ["ref_flat_full.npz", "ref_flat_cent.npz"])
+def test_golden_reference_script_problems(name):
+    """Descriptors flattened from the unmodified reference scripts (tests/golden/make_golden.py): cold solve on the GPU vs the
+    committed oracle solution — same iteration count, trajectories within 1e-6 relative."""
+    import golden_util
+
+    prob, z = golden_util.load(name)
+    s = BatchSolver(prob["robot"], prob["cfg"], 1)
+    s.setup(prob["knots"], prob["terms"], prob["x0"])
+    res = s.run(prob["xs"], prob["us"])
+    assert list(res.num_iters) == list(z["sol_num_iters"]) and list(res.conv) == [bool(c) for c in z["sol_conv"]]
+    assert rel(res.xs, z["sol_xs"]) < RTOL and rel(res.us, z["sol_us"]) < RTOL
+    assert abs(res.prim_infeas[0] - z["sol_prim_infeas"][0]) < 1e-6 * max(1e-6, z["sol_prim_infeas"][0]) + 1e-10
+    assert abs(res.dual_infeas[0] - z["sol_dual_infeas"][0]) < 1e-4 * max(1e-6, z["sol_dual_infeas"][0]) + 1e-10
+    s.close()
+
+
+def test_golden_walking_active_constraints():
+    """Random-schedule walking instances: single support, active cone/box rows, non-zero multipliers, backtracking linesearch."""
+    import golden_util
+
+    prob, z = golden_util.load("walk_full.npz")
+    B = prob["x0"].shape[0]
+    s = BatchSolver(prob["robot"], prob["cfg"], B)
+    s.setup(prob["knots"], prob["terms"], prob["x0"])
+    res = s.run(prob["xs"], prob["us"], max_iters=6)
+    assert list(res.num_iters) == list(z["sol_num_iters"])
+    assert [i.ls_evals for i in res.info] == list(z["sol_ls_evals"])
+    assert rel(res.xs, z["sol_xs"]) < RTOL and rel(res.us, z["sol_us"]) < RTOL and rel(res.vs, z["sol_vs"]) < 1e-5
+    s.setup(prob["knots"], prob["terms"], prob["x0"])
+    tick = s.run(z["sol_xs"], z["sol_us"], max_iters=1)
+    assert rel(tick.xs, z["tick_xs"]) < RTOL and rel(tick.us, z["tick_us"]) < RTOL
+    xdot, force = s.stage_data(0)
+    assert rel(force, z["tick_stage0"][:, 56:]) < RTOL and rel(xdot, z["tick_stage0"][:, :56]) < RTOL
+    s.close()
+
+
+def test_large_batch_properties(oracle):
+    """Size-independent checks at bench scale (batch 512 here): (1) instance results do not depend on the batch they are
+    solved in or on their position in it (independent units): bitwise equality; (2) a sampled instance equals the oracle."""
+    B = 512
+    prob = problems.full_walk_batch(B, seed=21, T=100)
+    s = BatchSolver(prob["robot"], prob["cfg"], B)
+    s.setup(prob["knots"], prob["terms"], prob["x0"])
+    res = s.run(prob["xs"], prob["us"], max_iters=2, gains=False)
+    s.close()
+    pick = [0, 77, 300, 511]
+    sub = dict(prob)
+    T = prob["cfg"].T
+    sub["knots"] = (_abi.Knot * (len(pick) * T))(*[prob["knots"][i * T + k] for i in pick for k in range(T)])
+    sub["terms"] = (_abi.Term * len(pick))(*[prob["terms"][i] for i in pick])
+    sub["x0"], sub["xs"], sub["us"] = prob["x0"][pick], prob["xs"][pick], prob["us"][pick]
+    s2 = BatchSolver(sub["robot"], sub["cfg"], len(pick))
+    s2.setup(sub["knots"], sub["terms"], sub["x0"])
+    r2 = s2.run(sub["xs"], sub["us"], max_iters=2, gains=False)
+    s2.close()
+    assert np.array_equal(r2.xs, res.xs[pick]) and np.array_equal(r2.us, res.us[pick])
+    ref = oracle.solve(sub, max_iters=2, inst_threads=4)
+    assert rel(r2.xs, ref["xs"]) < RTOL and rel(r2.us, ref["us"]) < RTOL
+    assert np.isfinite(res.xs).all() and (res.num_iters == 2).all()
+
+
+def test_shim_end_to_end_centroidal(oracle):
+    """The aligator-compatible surface on the GPU: build the centroidal problem through the public API, setup / run /
+    results / workspace, horizon cycling — against the oracle on the flattened descriptor."""
+    import mpc_benchmark_b200 as aligator
+    from mpc_benchmark_b200 import flatten, pin
+    from test_reference_scripts import _build_cent
+
+    ns = _build_cent(aligator, pin, T=20)
+    problem = ns["problem"]
+    solver = aligator.SolverProxDDP(1e-5, 1e-8)
+    solver.rollout_type = aligator.ROLLOUT_LINEAR
+    solver.linear_solver_choice = aligator.LQ_SOLVER_PARALLEL
+    solver.force_initial_condition = True
+    solver.setNumThreads(2)
+    solver.max_iters = 100
+    solver.setup(problem)
+    conv = solver.run(problem, [ns["x0"]] * 21, [ns["u0"] for _ in range(20)])
+    flat = flatten.flatten_problem(problem, 1e-5, 1e-8, 100)
+    ref = oracle.solve(dict(robot=flat.robot, cfg=flat.cfg, knots=flat.knots, terms=flat.terms, x0=flat.x0,
+                            xs=np.tile(ns["x0"], (1, 21, 1)), us=np.tile(ns["u0"], (1, 20, 1))))
+    r = solver.results
+    assert conv and r.num_iters == ref["info"][0].num_iters
+    assert rel(np.array(r.xs.tolist()), ref["xs"][0]) < RTOL and rel(np.array(r.us.tolist()), ref["us"][0]) < RTOL
+    K0 = r.controlFeedbacks()[0]
+    assert K0.shape == (12, 9) and rel(K0, ref["K"][0, 0]) < 1e-5
+    xdot = solver.workspace.problem_data.stage_data[0].dynamics_data.continuous_data.xdot
+    assert xdot.shape == (9,)
+    # one MPC tick: rotate the horizon, shift the warm start, one iteration (centroidal_talos.py:454-462)
+    xs, us = r.xs.tolist(), r.us.tolist()
+    problem.replaceStageCircular(ns["stages"][0])
+    solver.cycleProblem(problem, ns["stages"][0].createData())
+    solver.max_iters = 1
+    xs, us = xs[1:] + [xs[-1]], us[1:] + [us[-1]]
+    problem.x0_init = xs[0]
+    solver.setup(problem)
+    solver.run(problem, xs, us)
+    assert solver.results.num_iters <= 1 and np.isfinite(np.array(solver.results.xs.tolist())).all()
