@@ -305,46 +305,62 @@ constexpr int CB = 8;
 #ifdef MPC_HOST_EMU
 inline double rsqrt(double x) { return 1.0 / sqrt(x); }
 #endif
+// 1/sqrt(a) without the slow-path handling of the library routine: fp32 seed + two Newton steps in fp64 (<= 2 ulp).
+HD double fast_rsqrt(double a) {
+#ifdef MPC_HOST_EMU
+  return 1.0 / sqrt(a);
+#else
+  if (a > 1e-30 && a < 1e30) {
+    double y = (double)rsqrtf((float)a); // ~22 bits; two Newton steps -> full fp64
+    double t = a * y, e = fma(-t, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    t = a * y; e = fma(-t, y, 1.0);
+    return fma(0.5 * y, e, y);
+  }
+  return rsqrt(a);
+#endif
+}
 HD void chol_blocked(double *A, int n, int ld, double *Dinv) {
   for (int k0 = 0; k0 < n; k0 += CB) {
     const int bw = (n - k0 < CB) ? n - k0 : CB;
     double *Di = Dinv + (k0 / CB) * CB * CB;
-    if (IS_WARP0) {
-      // (a) factor the bw x bw diagonal block; every lane keeps the 1/L_jj so that no division appears on the chain
-      double dd[CB];
+    // (a)+(b) ONE thread factors the bw x bw diagonal block and inverts it entirely in registers (fully unrolled, no
+    // barriers, no shared-memory round trips on the dependency chain; rows/cols >= bw are padded with the identity)
+    ONE_THREAD {
+      double L[CB][CB], X[CB][CB], dd[CB];
+#pragma unroll
+      for (int r = 0; r < CB; r++)
+#pragma unroll
+        for (int c = 0; c < CB; c++) L[r][c] = (c <= r) ? ((r < bw) ? A[(k0 + r) * ld + k0 + c] : ((r == c) ? 1.0 : 0.0)) : 0.0;
 #pragma unroll
       for (int j = 0; j < CB; j++) {
-        dd[j] = 1.0;
-        if (j >= bw) continue;
-        const int jj = k0 + j;
-        const double a = A[jj * ld + jj];
-        const double d = rsqrt(a);
+        const double d = fast_rsqrt(L[j][j]);
         dd[j] = d;
-        WARP_SYNC();
-        WARP_FOR(i, bw - j) { int r = jj + i; A[r * ld + jj] = (i == 0) ? a * d : A[r * ld + jj] * d; }
-        WARP_SYNC();
-        const int cols = bw - j - 1;
-        WARP_FOR(e, cols * cols) {
-          int r = jj + 1 + e / cols, c = jj + 1 + e % cols;
-          if (c <= r) A[r * ld + c] -= A[r * ld + jj] * A[c * ld + jj];
-        }
-        WARP_SYNC();
+        L[j][j] = L[j][j] * d;
+#pragma unroll
+        for (int r = j + 1; r < CB; r++) L[r][j] *= d;
+#pragma unroll
+        for (int r = j + 1; r < CB; r++)
+#pragma unroll
+          for (int c = j + 1; c <= r; c++) L[r][c] -= L[r][j] * L[c][j];
       }
-      // (b) inverse of the diagonal block, one column per lane, multiplications only (dd[r] = 1/L_rr from (a))
-      WARP_FOR(c, CB) {
-        double x[CB];
+#pragma unroll
+      for (int c = 0; c < CB; c++)
 #pragma unroll
         for (int r = 0; r < CB; r++) {
+          if (r < c) { X[r][c] = 0.0; continue; }
           double s = (r == c) ? 1.0 : 0.0;
-          if (r < bw) {
 #pragma unroll
-            for (int t = 0; t < CB; t++) if (t < r && t >= c) s -= A[(k0 + r) * ld + k0 + t] * x[t];
-          }
-          x[r] = (r < c || r >= bw || c >= bw) ? 0.0 : s * dd[r];
+          for (int t = c; t < r; t++) s -= L[r][t] * X[t][c];
+          X[r][c] = s * dd[r];
         }
 #pragma unroll
-        for (int r = 0; r < CB; r++) Di[r * CB + c] = x[r];
-      }
+      for (int r = 0; r < CB; r++)
+#pragma unroll
+        for (int c = 0; c < CB; c++) {
+          if (r < bw && c <= r) A[(k0 + r) * ld + k0 + c] = L[r][c];
+          Di[r * CB + c] = (r < bw && c < bw) ? X[r][c] : 0.0;
+        }
     }
     SYNC();
     // (c) panel below the diagonal block: L[i, k0:k0+bw] = A[i, k0:k0+bw] * Dinv^T, one row per work item

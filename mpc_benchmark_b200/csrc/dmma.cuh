@@ -36,35 +36,43 @@ HD void mma_tn(int mt, int nt, int K, const double *A, int lda, const double *B,
 #else
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int g = lane >> 2, t = lane & 3;
-  // each warp takes pairs of horizontally adjacent tiles (shares the A fragment)
-  const int ntp = (nt + 1) / 2;
-  for (int p = warp; p < mt * ntp; p += nwarps) {
-    const int ti = p / ntp, tj = (p % ntp) * 2;
-    const bool two = (tj + 1 < nt);
-    if (upper_only && tj + (two ? 1 : 0) < ti) continue;
-    const int row = ti * 8 + g, col0 = tj * 8 + 2 * t, col1 = col0 + 8;
-    double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
-    if (Cinit && row < vr) {
-      if (col0 < vc) c00 = Cinit[row * ldci + col0];
-      if (col0 + 1 < vc) c01 = Cinit[row * ldci + col0 + 1];
-      if (two && col1 < vc) c10 = Cinit[row * ldci + col1];
-      if (two && col1 + 1 < vc) c11 = Cinit[row * ldci + col1 + 1];
-    }
+  // each warp takes 2 x 2 blocks of tiles: 4 independent accumulator chains per warp, A and B fragments shared
+  const int mtp = (mt + 1) / 2, ntp = (nt + 1) / 2;
+  for (int p = warp; p < mtp * ntp; p += nwarps) {
+    const int ti = (p / ntp) * 2, tj = (p % ntp) * 2;
+    const bool r2 = (ti + 1 < mt), c2 = (tj + 1 < nt);
+    if (upper_only && tj + (c2 ? 1 : 0) < ti) continue;
+    double c[2][2][2];
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+      for (int b = 0; b < 2; b++) {
+        c[a][b][0] = 0.0; c[a][b][1] = 0.0;
+        const int row = (ti + a) * 8 + g, col = (tj + b) * 8 + 2 * t;
+        if (Cinit && row < vr && (a == 0 || r2) && (b == 0 || c2)) {
+          if (col < vc) c[a][b][0] = Cinit[row * ldci + col];
+          if (col + 1 < vc) c[a][b][1] = Cinit[row * ldci + col + 1];
+        }
+      }
     const double *ap = A + t * lda + ti * 8 + g;
     const double *bp = B + t * ldb + tj * 8 + g;
-    if (two) {
+    const int ao = r2 ? 8 : 0, bo = c2 ? 8 : 0; // out-of-range partner tiles recompute tile 0 (discarded)
 #pragma unroll 2
-      for (int k0 = 0; k0 < K; k0 += 4) {
-        double a = ap[k0 * lda], b0 = bp[k0 * ldb], b1 = bp[k0 * ldb + 8];
-        dmma_8x8x4(c00, c01, a, b0);
-        dmma_8x8x4(c10, c11, a, b1);
-      }
-    } else {
-#pragma unroll 2
-      for (int k0 = 0; k0 < K; k0 += 4) dmma_8x8x4(c00, c01, ap[k0 * lda], bp[k0 * ldb]);
+    for (int k0 = 0; k0 < K; k0 += 4) {
+      const double a0 = ap[k0 * lda], a1 = ap[k0 * lda + ao], b0 = bp[k0 * ldb], b1 = bp[k0 * ldb + bo];
+      dmma_8x8x4(c[0][0][0], c[0][0][1], a0, b0);
+      dmma_8x8x4(c[0][1][0], c[0][1][1], a0, b1);
+      dmma_8x8x4(c[1][0][0], c[1][0][1], a1, b0);
+      dmma_8x8x4(c[1][1][0], c[1][1][1], a1, b1);
     }
-    *reinterpret_cast<double2 *>(C + row * ldc + col0) = make_double2(c00, c01);
-    if (two) *reinterpret_cast<double2 *>(C + row * ldc + col1) = make_double2(c10, c11);
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+      for (int b = 0; b < 2; b++) {
+        if ((a == 1 && !r2) || (b == 1 && !c2)) continue;
+        const int row = (ti + a) * 8 + g, col = (tj + b) * 8 + 2 * t;
+        *reinterpret_cast<double2 *>(C + row * ldc + col) = make_double2(c[a][b][0], c[a][b][1]);
+      }
   }
 #endif
   SYNC();

@@ -17,6 +17,18 @@
 
 namespace mpcdev {
 
+// optional per-phase cycle counters of the evaluation kernel (-DMPC_PHASE_TIMING builds; knot 1 of instance 0)
+#if defined(MPC_PHASE_TIMING) && !defined(MPC_HOST_EMU)
+#define EPH_DECL long long eph_last = clock64(); long long eph_acc[16] = {0}
+#define EPH(i) do { __syncthreads(); if (threadIdx.x == 0) { long long t_ = clock64(); eph_acc[i] += t_ - eph_last; eph_last = t_; } } while (0)
+#define EPH_DUMP(ptr) do { if (threadIdx.x == 0 && (ptr)) for (int i_ = 0; i_ < 16; i_++) (ptr)[i_] = (double)eph_acc[i_]; } while (0)
+#else
+#define EPH_DECL
+#define EPH(i)
+#define EPH_DUMP(ptr)
+#endif
+
+
 constexpr int FN = 56, FM = 22, FNZ = 78, FNC = 78;
 
 // merit / infeasibility partials written per knot
@@ -37,37 +49,47 @@ struct KnotIO {
   int32_t *nca, *act_idx;
   // outputs (both passes)
   double *gap, *h, *scal, *xdot, *lamc;
+  double *phase_out; // profiling builds only
 };
 
-struct FullWs {
+template <bool WITH_DERIV> struct FullWsT {
+  static constexpr int XS = WITH_DERIV ? NV * FNZ : 8, DLS = WITH_DERIV ? 12 * FNZ : 8, TOPS = WITH_DERIV ? 2 * NV * 6 : 8, BCS = WITH_DERIV ? NB * 36 : 8;
+  static constexpr int CJ1 = WITH_DERIV ? 6 * FN : 8, CJ2 = WITH_DERIV ? 2 * 6 * NV : 8, M6 = WITH_DERIV ? 36 : 1, ZS = WITH_DERIV ? FNZ : 8;
   double x[NQ + NV], u[FM], xn[NQ + NV];
   double kn[sizeof(mpc_knot_t) / 8];
   double oM[NB * 12], S[NV * 6], v[NB * 6], a[NB * 6], I[NB * 10], Ic[NB * 10];
   double hb[NB * 6], hsub[NB * 6], f[NB * 6], Fsub[NB * 6];
-  double Bc[NB * 36];
+  union { // Bc is dead once the derivative columns are built; the cost Jacobians are built afterwards
+    double Bc[BCS];
+    struct { double Jcent[CJ1], Jpose[CJ2]; } cj;
+  };
   double U[NV * 6];
-  double M[NV * NV], bvec[NV], acc[NV];
+  union { // the mass-matrix factor is dead after X = M^-1 R1; the output-phase vectors live afterwards
+    double M[NV * NV];
+    struct {
+      double P1[M6], P2[M6], E6[M6], T6[M6], Jlg[M6], Jrg[M6], AdD[M6], AdDi[M6], Jd[M6], Ade[M6];
+      double lxu[ZS], g[ZS], hval[FNC], vpl[FNC], dbr[FNC], rowtmp[FNC];
+    } late;
+  };
+  double bvec[NV], acc[NV];
   double ofoot[24], Jf[2 * 6 * NV];
-  double vc[12], gam[12], astar[12], c1Mc2[24], JlAd[72], lam[12];
+  double vc[12], gam[12], astar[12], c1Mc2[24], JlAd[2 * M6], lam[12], lgc[12];
   double Y[NV * 13], G[144], rhs[12], dinvM[4 * 64], dinvG[2 * 64];
-  double X[NV * FNZ];
-  double DL[12 * FNZ];
-  double top[2 * NV * 6];
-  double Jcent[6 * FN], rcent[6];
-  double Jpose[2 * 6 * NV], rpose[12];
-  double estate[FN], Jls[36];
-  double dx[FN], xnext[NQ + NV];
-  double P1[36], P2[36], E6[36], T6[36];
-  double lxu[FNZ], g[FNZ];
-  double hval[FNC], vpl[FNC], dbr[FNC], rowtmp[FNC];
+  double X[XS];
+  double DL[DLS];
+  double top[TOPS];
+  double rcent[6], rpose[12], Jlp[2 * M6];
+  double estate[FN], Jls[M6];
+  double dx[FN], xnext[NQ + NV], lgap[6], eexp[12], Dgap[12];
   double lpl[FN], fbr[FN];
   double com[3], scal[SC_COUNT], part[32];
   int32_t act[2], nact, sidx[2], ctype[FNC], isact[FNC], act_idx[FNC], nca;
 };
+using FullWs = FullWsT<true>;
 
 // ------------------------------------------------------------------ kinematics shared by running / terminal knots
 // fills oM, S, I, v, hb, Ic, hsub, com, ofoot, Jf
-HD void mb_kinematics(const DevModel &m, FullWs &w) {
+template <class WS> HD void mb_kinematics(const DevModel &m, WS &w) {
   const mpc_robot_t &rb = m.rb;
   const double *q = w.x, *qd = w.x + NQ;
   for (int l = 0; l < m.nlevels; l++) {
@@ -143,22 +165,36 @@ HD void mb_kinematics(const DevModel &m, FullWs &w) {
   SYNC();
 }
 
-// centroidal momentum residual + Jacobian [dh/dq | A_g] (6 x 56), pose residuals + Jacobians, state error.
-HD void mb_cost_terms(const DevModel &m, FullWs &w, const double *lf_ref, const double *rf_ref, bool derivs) {
+// centroidal momentum residual + Jacobian [dh/dq | A_g] (6 x 56), pose residuals + Jacobians, state error and — for running
+// knots (gap_out != nullptr) — the base part of the semi-implicit Euler step, the shooting gap and the 6x6 Lie-group blocks
+// P1 = Jlog6(D) Jexp6(dq), P2 = Jlog6(D) Ad(exp6(dq))^-1, E6 = -Jlog6(D) Ad(D^-1), T6 = -E6^-1 = Ad(D) Jexp6(log6 D).
+// The single-thread Lie-group tasks are spread over the 4 warps in two dependent stages, the 6x6 products over all threads.
+template <class WS> HD void mb_cost_terms(const DevModel &m, WS &w, const double *lf_ref, const double *rf_ref, bool derivs, double *gap_out) {
   const mpc_robot_t &rb = m.rb;
-  // small single-thread tasks spread over distinct warps
   PAR_FOR(task, 4 * 32) {
-    if (task == 0) { // centroidal momentum value
+    if (task == 0) { // centroidal momentum value; integrator base block and gap
       const double *h = w.hsub;
       double c[3];
       cross3(w.com, h, c);
       for (int i = 0; i < 3; i++) { w.rcent[i] = h[i]; w.rcent[3 + i] = h[3 + i] - c[i]; }
+      if (gap_out) {
+        double pn[3], Mn[12], Mp[12];
+        exp6(w.dx, w.eexp);
+        mat3_vec(w.oM, w.eexp + 9, pn);
+        for (int i = 0; i < 3; i++) w.xnext[i] = w.x[i] + pn[i];
+        quat_integrate(w.x + 3, w.dx + 3, w.xnext + 3);
+        quat_to_R(w.xn + 3, Mn); Mn[9] = w.xn[0]; Mn[10] = w.xn[1]; Mn[11] = w.xn[2];
+        quat_to_R(w.xnext + 3, Mp); Mp[9] = w.xnext[0]; Mp[10] = w.xnext[1]; Mp[11] = w.xnext[2];
+        se3_inv_mul(Mn, Mp, w.Dgap);
+        log6(w.Dgap, w.lgap);
+        for (int i = 0; i < 6; i++) gap_out[i] = w.fbr[i] = w.lgap[i]; // fbr temporarily holds the gap
+      }
     } else if (task == 32 || task == 64) { // foot pose residuals
       int f = task == 32 ? 0 : 1;
       double D[12];
       se3_inv_mul(f == 0 ? lf_ref : rf_ref, w.ofoot + 12 * f, D);
       log6(D, w.rpose + 6 * f);
-      if (derivs) Jlog6_from_log(w.rpose + 6 * f, w.JlAd + 36 * f); // temporarily parked in JlAd; consumed below
+      if (derivs) Jlog6_from_log(w.rpose + 6 * f, w.Jlp + 36 * f);
     } else if (task == 96) { // state error e = x (-) x_ref
       double Mr[12], Mx[12], D[12];
       quat_to_R(m.cfg.x_ref + 3, Mr); Mr[9] = m.cfg.x_ref[0]; Mr[10] = m.cfg.x_ref[1]; Mr[11] = m.cfg.x_ref[2];
@@ -172,14 +208,27 @@ HD void mb_cost_terms(const DevModel &m, FullWs &w, const double *lf_ref, const 
     int a = 6 + i;
     w.estate[a] = (a < NV) ? (w.x[7 + a - 6] - m.cfg.x_ref[7 + a - 6]) : (w.x[NQ + a - NV] - m.cfg.x_ref[NQ + a - NV]);
   }
+  if (gap_out) {
+    PAR_FOR(i, NJ) { w.xnext[7 + i] = w.x[7 + i] + w.dx[6 + i]; gap_out[6 + i] = w.fbr[6 + i] = w.xnext[7 + i] - w.xn[7 + i]; }
+    PAR_FOR(i, NV) { w.xnext[NQ + i] = w.x[NQ + i] + w.dx[NV + i]; gap_out[NV + i] = w.fbr[NV + i] = w.xnext[NQ + i] - w.xn[NQ + i]; }
+  }
   SYNC();
   if (!derivs) return;
+  if (gap_out) {
+    PAR_FOR(task, 4 * 32) {
+      const double id[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+      if (task == 0) { double inv[12]; Jlog6_from_log(w.lgap, w.late.Jlg); se3_inv_mul(w.Dgap, id, inv); se3_action_matrix(inv, w.late.AdDi); }
+      else if (task == 32) Jexp6(w.dx, w.late.Jd);
+      else if (task == 64) { double einv[12]; se3_inv_mul(w.eexp, id, einv); se3_action_matrix(einv, w.late.Ade); se3_action_matrix(w.Dgap, w.late.AdD); }
+      else if (task == 96) Jexp6(w.lgap, w.late.Jrg);
+    }
+  }
   PAR_FOR(e, 2 * 6 * NV) { // Jpose = Jlog6 * Jf
     int f = e / (6 * NV), r = (e / NV) % 6, j = e % NV;
-    const double *Jl = w.JlAd + 36 * f;
+    const double *Jl = w.Jlp + 36 * f;
     double s = 0;
     for (int k = 0; k < 6; k++) s += Jl[6 * r + k] * w.Jf[(6 * f + k) * NV + j];
-    w.Jpose[e] = s;
+    w.cj.Jpose[e] = s;
   }
   PAR_FOR(j, NV) { // centroidal derivative columns
     int J = body_of_dof(j), pJ = rb.parent[J];
@@ -196,34 +245,45 @@ HD void mb_cost_terms(const DevModel &m, FullWs &w, const double *lf_ref, const 
     double c1[3], c2[3], c3[3];
     cross3(dc, w.hsub, c1); cross3(w.com, dho, c2); cross3(w.com, Is, c3);
     for (int r = 0; r < 3; r++) {
-      w.Jcent[r * FN + j] = dho[r]; w.Jcent[(3 + r) * FN + j] = dho[3 + r] - c1[r] - c2[r];
-      w.Jcent[r * FN + NV + j] = Is[r]; w.Jcent[(3 + r) * FN + NV + j] = Is[3 + r] - c3[r];
+      w.cj.Jcent[r * FN + j] = dho[r]; w.cj.Jcent[(3 + r) * FN + j] = dho[3 + r] - c1[r] - c2[r];
+      w.cj.Jcent[r * FN + NV + j] = Is[r]; w.cj.Jcent[(3 + r) * FN + NV + j] = Is[3 + r] - c3[r];
     }
   }
   SYNC();
+  if (gap_out) {
+    PAR_FOR(e, 4 * 36) {
+      int which = e / 36, i = (e % 36) / 6, j = e % 6;
+      const double *A = (which == 3) ? w.late.AdD : w.late.Jlg;
+      const double *B = (which == 0) ? w.late.AdDi : (which == 1) ? w.late.Jd : (which == 2) ? w.late.Ade : w.late.Jrg;
+      double sacc = 0;
+      for (int k = 0; k < 6; k++) sacc += A[6 * i + k] * B[6 * k + j];
+      if (which == 0) w.late.E6[6 * i + j] = -sacc; else if (which == 1) w.late.P1[6 * i + j] = sacc; else if (which == 2) w.late.P2[6 * i + j] = sacc; else w.late.T6[6 * i + j] = sacc;
+    }
+    SYNC();
+  }
 }
 
 // value + gradient + Gauss-Newton Hessian contributions of the multibody cost stack at (a, b) / z
-HD double mb_cost_value(const FullWs &w, const double *wx, const double *wcent, const double *wlf, const double *wrf) {
+template <class WS> HD double mb_cost_value(const WS &w, const double *wx, const double *wcent, const double *wlf, const double *wrf) {
   double c = 0;
   for (int i = 0; i < FN; i++) c += 0.5 * wx[i] * w.estate[i] * w.estate[i];
   for (int i = 0; i < 6; i++) c += 0.5 * (wcent[i] * w.rcent[i] * w.rcent[i] + wlf[i] * w.rpose[i] * w.rpose[i] + wrf[i] * w.rpose[6 + i] * w.rpose[6 + i]);
   return c;
 }
-HD double mb_cost_grad(const FullWs &w, const double *wx, const double *wcent, const double *wlf, const double *wrf, int z) {
+template <class WS> HD double mb_cost_grad(const WS &w, const double *wx, const double *wcent, const double *wlf, const double *wrf, int z) {
   double g = 0;
   if (z < 6) { for (int r = 0; r < 6; r++) g += wx[r] * w.Jls[6 * r + z] * w.estate[r]; }
   else if (z < FN) g += wx[z] * w.estate[z];
-  if (z < FN) for (int r = 0; r < 6; r++) g += wcent[r] * w.Jcent[r * FN + z] * w.rcent[r];
-  if (z < NV) for (int r = 0; r < 6; r++) g += wlf[r] * w.Jpose[r * NV + z] * w.rpose[r] + wrf[r] * w.Jpose[(6 + r) * NV + z] * w.rpose[6 + r];
+  if (z < FN) for (int r = 0; r < 6; r++) g += wcent[r] * w.cj.Jcent[r * FN + z] * w.rcent[r];
+  if (z < NV) for (int r = 0; r < 6; r++) g += wlf[r] * w.cj.Jpose[r * NV + z] * w.rpose[r] + wrf[r] * w.cj.Jpose[(6 + r) * NV + z] * w.rpose[6 + r];
   return g;
 }
-HD double mb_cost_hess(const FullWs &w, const double *wx, const double *wcent, const double *wlf, const double *wrf, int a, int b) {
+template <class WS> HD double mb_cost_hess(const WS &w, const double *wx, const double *wcent, const double *wlf, const double *wrf, int a, int b) {
   double h = 0; // a <= b
   if (b < 6) { for (int r = 0; r < 6; r++) h += wx[r] * w.Jls[6 * r + a] * w.Jls[6 * r + b]; }
   else if (a == b && a < FN) h += wx[a];
-  if (b < FN) for (int r = 0; r < 6; r++) if (wcent[r] != 0.0) h += wcent[r] * w.Jcent[r * FN + a] * w.Jcent[r * FN + b];
-  if (b < NV) for (int r = 0; r < 6; r++) h += wlf[r] * w.Jpose[r * NV + a] * w.Jpose[r * NV + b] + wrf[r] * w.Jpose[(6 + r) * NV + a] * w.Jpose[(6 + r) * NV + b];
+  if (b < FN) for (int r = 0; r < 6; r++) if (wcent[r] != 0.0) h += wcent[r] * w.cj.Jcent[r * FN + a] * w.cj.Jcent[r * FN + b];
+  if (b < NV) for (int r = 0; r < 6; r++) h += wlf[r] * w.cj.Jpose[r * NV + a] * w.cj.Jpose[r * NV + b] + wrf[r] * w.cj.Jpose[(6 + r) * NV + a] * w.cj.Jpose[(6 + r) * NV + b];
   return h;
 }
 
@@ -241,7 +301,8 @@ HD double vplus_row(int type, double h, double ve, double mu, double lo, double 
 }
 
 // ------------------------------------------------------------------ running knot
-template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io, FullWs &w) {
+template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io, FullWsT<DERIV> &w) {
+  EPH_DECL;
   const mpc_robot_t &rb = m.rb;
   const mpc_config_t &cfg = m.cfg;
   const double dt = cfg.dt;
@@ -257,7 +318,9 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
     if (l) { w.sidx[0] = w.nact; w.act[w.nact++] = 0; }
     if (r) { w.sidx[1] = w.nact; w.act[w.nact++] = 1; }
   }
+  EPH(0);
   mb_kinematics(m, w);
+  EPH(1);
   const int nact = w.nact, nk = 6 * nact;
   const double a0[6] = {-rb.gravity[0], -rb.gravity[1], -rb.gravity[2], 0, 0, 0};
   // bias accelerations (qdd = 0, gravity folded in) and bias forces
@@ -302,7 +365,7 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
     double lg[6];
     log6(w.c1Mc2 + 12 * c, lg);
     for (int r = 0; r < 6; r++) w.astar[6 * c + r] = cfg.kp[r] * lg[r] - cfg.kd[r] * w.vc[6 * c + r];
-    if (DERIV) w.rowtmp[6 * c] = lg[0], w.rowtmp[6 * c + 1] = lg[1], w.rowtmp[6 * c + 2] = lg[2], w.rowtmp[6 * c + 3] = lg[3], w.rowtmp[6 * c + 4] = lg[4], w.rowtmp[6 * c + 5] = lg[5];
+    for (int r = 0; r < 6; r++) w.lgc[6 * c + r] = lg[r];
   }
   SYNC();
   PAR_FOR(j, NV) { // b = S^T Fsub ; rhs column 0 = tau - b ; columns 1.. = J^T
@@ -312,7 +375,9 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
     for (int r = 0; r < nk; r++) w.Y[j * 13 + 1 + r] = w.Jf[(6 * w.act[r / 6] + r % 6) * NV + j];
   }
   SYNC();
+  EPH(2);
   chol_blocked(w.M, NV, NV, w.dinvM);
+  EPH(3);
   trsm_blocked(w.M, NV, NV, w.dinvM, w.Y, 1 + nk, 13);
   PAR_FOR(e, nk * (nk + 1)) {
     int r = e / (nk + 1), c = e % (nk + 1);
@@ -335,11 +400,12 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
   PAR_FOR(i, NV) { io.xdot[i] = w.x[NQ + i]; io.xdot[NV + i] = w.acc[i]; }
   PAR_FOR(i, 12) io.lamc[i] = w.lam[i];
 
+  EPH(4);
   if (DERIV) {
     // ---- inverse-dynamics tangent at (q, v, a) with the contact wrenches as external forces
     PAR_FOR(c, nact) { // JlAd = Jlog6(c1Mc2) * Ad(c2Mc1)
       double Jl[36], Ad[36], inv[12], id[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
-      Jlog6_from_log(w.rowtmp + 6 * c, Jl);
+      Jlog6_from_log(w.lgc + 6 * c, Jl);
       se3_inv_mul(w.c1Mc2 + 12 * c, id, inv);
       se3_action_matrix(inv, Ad);
       mat6_mul(Jl, Ad, w.JlAd + 36 * c);
@@ -375,6 +441,7 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
       for (int d = b; d < NB; d++) if (mask >> d & 1) s += w.f[6 * d + c];
       w.Fsub[e] = s;
     }
+    EPH(5);
     PAR_FOR(e, NB * 6) { // composite B: Bc_b e_c = sum_{k in sub(b)} I_k (e_c x v_k) + e_c x* (I_k v_k) + v_k x* (I_k e_c)
       int b = e / 6, c = e % 6;
       uint32_t mask = m.sub_mask[b];
@@ -393,6 +460,7 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
       for (int i = 0; i < 6; i++) w.Bc[36 * b + 6 * i + c] = col[i];
     }
     SYNC();
+    EPH(6);
     PAR_FOR(e, 2 * m.npairs) {
       int kind = e / m.npairs, p = e % m.npairs;
       int j = m.pair_j[p], mb = m.pair_m[p], J = body_of_dof(j), pJ = rb.parent[J];
@@ -457,7 +525,9 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
       w.X[i * FNZ + NV + j] = dot6(w.S + 6 * i, w.top + 6 * (NV + j));
     }
     SYNC();
+    EPH(7);
     trsm_blocked(w.M, NV, NV, w.dinvM, w.X, FNZ, FNZ); // X = M^-1 R1
+    EPH(8);
     PAR_FOR(e, nk * FNZ) {
       int r = e / FNZ, z = e % FNZ;
       const double *Jr = w.Jf + (6 * w.act[r / 6] + r % 6) * NV;
@@ -476,49 +546,13 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
     SYNC();
   }
 
+  EPH(9);
   // ---- semi-implicit Euler + gap (App. A2)
   PAR_FOR(i, NV) { double dv = dt * w.acc[i]; w.dx[NV + i] = dv; w.dx[i] = dt * (w.x[NQ + i] + dv); }
-  mb_cost_terms(m, w, kn.lf_ref, kn.rf_ref, DERIV); // (contains the SYNC making dx visible)
-  PAR_FOR(task, 32 + NJ + NV) {
-    if (task == 0) {
-      double e[12], pn[3];
-      exp6(w.dx, e);
-      mat3_vec(w.oM, e + 9, pn);
-      for (int i = 0; i < 3; i++) w.xnext[i] = w.x[i] + pn[i];
-      quat_integrate(w.x + 3, w.dx + 3, w.xnext + 3);
-      double Mn[12], Mp[12], D[12], lg[6];
-      quat_to_R(w.xn + 3, Mn); Mn[9] = w.xn[0]; Mn[10] = w.xn[1]; Mn[11] = w.xn[2];
-      quat_to_R(w.xnext + 3, Mp); Mp[9] = w.xnext[0]; Mp[10] = w.xnext[1]; Mp[11] = w.xnext[2];
-      se3_inv_mul(Mn, Mp, D);
-      log6(D, lg);
-      for (int i = 0; i < 6; i++) io.gap[i] = w.fbr[i] = lg[i]; // fbr temporarily holds the gap
-      if (DERIV) {
-        double Jl[36], Ad[36], inv[12], id[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0}, Jd[36], einv[12];
-        Jlog6_from_log(lg, Jl);
-        se3_inv_mul(D, id, inv);
-        se3_action_matrix(inv, Ad);
-        mat6_mul(Jl, Ad, w.E6);
-        for (int i = 0; i < 36; i++) w.E6[i] = -w.E6[i];
-        inv6(w.E6, w.T6);
-        for (int i = 0; i < 36; i++) w.T6[i] = -w.T6[i];
-        Jexp6(w.dx, Jd);
-        mat6_mul(Jl, Jd, w.P1);
-        se3_inv_mul(e, id, einv);
-        se3_action_matrix(einv, Ad);
-        mat6_mul(Jl, Ad, w.P2);
-      }
-    } else if (task >= 32 && task < 32 + NJ) {
-      int i = task - 32;
-      w.xnext[7 + i] = w.x[7 + i] + w.dx[6 + i];
-      io.gap[6 + i] = w.fbr[6 + i] = w.xnext[7 + i] - w.xn[7 + i];
-    } else if (task >= 32 + NJ) {
-      int i = task - 32 - NJ;
-      w.xnext[NQ + i] = w.x[NQ + i] + w.dx[NV + i];
-      io.gap[NV + i] = w.fbr[NV + i] = w.xnext[NQ + i] - w.xn[NQ + i];
-    }
-  }
   SYNC();
+  mb_cost_terms(m, w, kn.lf_ref, kn.rf_ref, DERIV, io.gap);
 
+  EPH(10);
   // ---- constraint values, multiplier estimates, activity
   PAR_FOR(r, FNC) {
     int type = -1; double hv = 0, lo = 0, hi = 0;
@@ -530,9 +564,9 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
     }
     int act = 0; double prim = 0;
     double vp = vplus_row(type, hv, io.v_prev[r], io.mu, lo, hi, act, prim);
-    w.ctype[r] = type; w.hval[r] = hv; w.vpl[r] = vp; w.isact[r] = act;
-    w.dbr[r] = io.mu * (vp - io.v[r]);
-    w.rowtmp[r] = fabs(prim);
+    w.ctype[r] = type; w.late.hval[r] = hv; w.late.vpl[r] = vp; w.isact[r] = act;
+    w.late.dbr[r] = io.mu * (vp - io.v[r]);
+    w.late.rowtmp[r] = fabs(prim);
     io.h[r] = hv;
   }
   PAR_FOR(i, FN) {
@@ -547,10 +581,10 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
     double pen = 0, prim = 0, inner = 0, cost = 0;
     for (int r = c; r < FNC; r += 8) {
       if (w.ctype[r] < 0) continue;
-      double dv = w.vpl[r] - io.v[r];
-      pen += 0.5 * io.mu * (w.vpl[r] * w.vpl[r] + dv * dv);
-      prim = fmax(prim, w.rowtmp[r]);
-      inner = fmax(inner, fabs(w.dbr[r]));
+      double dv = w.late.vpl[r] - io.v[r];
+      pen += 0.5 * io.mu * (w.late.vpl[r] * w.late.vpl[r] + dv * dv);
+      prim = fmax(prim, w.late.rowtmp[r]);
+      inner = fmax(inner, fabs(w.late.dbr[r]));
     }
     for (int i = c; i < FN; i += 8) {
       double dl = w.lpl[i] - io.lam_n[i];
@@ -582,18 +616,19 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
     return;
   }
 
+  EPH(11);
   // ---- LQ blocks to HBM: AB (56 x 78), Lagrangian gradient, cost gradient / Hessian, active constraint rows
-  PAR_FOR(i, FNC) { io.dbar[i] = w.dbr[i]; io.vplus[i] = w.vpl[i]; io.act_idx[i] = (i < w.nca) ? w.act_idx[i] : -1; }
+  PAR_FOR(i, FNC) { io.dbar[i] = w.late.dbr[i]; io.vplus[i] = w.late.vpl[i]; io.act_idx[i] = (i < w.nca) ? w.act_idx[i] : -1; }
   PAR_FOR(i, FN) { io.fbar[i] = w.fbr[i]; io.lplus[i] = w.lpl[i]; }
-  PAR_FOR(i, 36) { io.T6[i] = w.T6[i]; io.E6[i] = w.E6[i]; }
+  PAR_FOR(i, 36) { io.T6[i] = w.late.T6[i]; io.E6[i] = w.late.E6[i]; }
   ONE_THREAD io.nca[0] = w.nca;
   const double dt2 = dt * dt;
   PAR_FOR(z, FNZ) {
     double d6[6], acc = 0;
     for (int k = 0; k < 6; k++) d6[k] = dt2 * w.X[k * FNZ + z] + ((z == NV + k) ? dt : 0.0);
     for (int i = 0; i < 6; i++) {
-      double s = (z < 6) ? w.P2[6 * i + z] : 0.0;
-      for (int k = 0; k < 6; k++) s += w.P1[6 * i + k] * d6[k];
+      double s = (z < 6) ? w.late.P2[6 * i + z] : 0.0;
+      for (int k = 0; k < 6; k++) s += w.late.P1[6 * i + k] * d6[k];
       io.AB[i * FNZ + z] = s; acc += s * io.lam_n[i];
     }
     for (int i = 6; i < NV; i++) {
@@ -612,7 +647,7 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
         const double *Dl = w.DL + 6 * w.sidx[f] * FNZ;
         for (int r = 0; r < 6; r++) lz += cfg.w_force[r] * Dl[r * FNZ + z] * (w.lam[6 * f + r] - kn.f_ref[6 * f + r]);
       }
-    w.lxu[z] = lz; io.lxu[z] = lz;
+    w.late.lxu[z] = lz; io.lxu[z] = lz;
     // Lagrangian gradient: + C^T v  (+ E_{k-1}^T lam_k: vector part here, base block added by the reduction kernel)
     double gz = lz + acc;
     for (int r = 0; r < FNC; r++) {
@@ -625,33 +660,58 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
       gz += c * vr;
     }
     if (z < FN) { if (io.k == 0) gz += io.lam_k[z]; else if (z >= 6) gz -= io.lam_k[z]; }
-    w.g[z] = gz; io.g[z] = gz;
+    w.late.g[z] = gz; io.g[z] = gz;
   }
   PAR_FOR(j, 6) { // E_k^T lam_{k+1}, base block, for the next knot's gradient
     double s = 0;
-    for (int i = 0; i < 6; i++) s += w.E6[6 * i + j] * io.lam_n[i];
+    for (int i = 0; i < 6; i++) s += w.late.E6[6 * i + j] * io.lam_n[i];
     io.gE_next[j] = s;
   }
-  PAR_FOR(e, FNZ * (FNZ + 1) / 2) { // Gauss-Newton Hessian, upper triangle mirrored
-    // decode (a, b), a <= b, from the linear index of the upper triangle
-    int a = 0, rem = e;
-    { // row a has FNZ - a entries
-      double fa = (2.0 * FNZ + 1.0 - sqrt((2.0 * FNZ + 1.0) * (2.0 * FNZ + 1.0) - 8.0 * (double)e)) * 0.5;
-      a = (int)fa;
-      while (a * FNZ - a * (a - 1) / 2 > e) a--;
-      while ((a + 1) * FNZ - (a + 1) * a / 2 <= e) a++;
-      rem = e - (a * FNZ - a * (a - 1) / 2);
-    }
-    int b = a + rem;
-    double hv = mb_cost_hess(w, cfg.wx, cfg.w_cent, kn.w_lf, kn.w_rf, a, b);
-    if (a == b) { hv += io.preg; if (a >= FN) hv += cfg.wu[a - FN]; }
-    for (int f = 0; f < 2; f++)
-      if (kn.fcost[f] != 0.0) {
-        const double *Dl = w.DL + 6 * w.sidx[f] * FNZ;
-        for (int r = 0; r < 6; r++) hv += cfg.w_force[r] * Dl[r * FNZ + a] * Dl[r * FNZ + b];
+  EPH(12);
+  { // Gauss-Newton Hessian H = sum_r w_r J_r' J_r (+ state/control diagonals) on 4 x 4 register tiles of the upper triangle
+    constexpr int HT = (FNZ + 3) / 4;
+    PAR_FOR(t, HT * HT) {
+      const int ta = t / HT, tb = t % HT;
+      if (tb < ta) continue;
+      const int a0 = 4 * ta, b0 = 4 * tb;
+      double acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+      auto rank1 = [&](const double *J, int ncols, double wgt) {
+        double va[4], vb[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { va[i] = (a0 + i < ncols) ? wgt * J[a0 + i] : 0.0; vb[i] = (b0 + i < ncols) ? J[b0 + i] : 0.0; }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) acc[i][j] += va[i] * vb[j];
+      };
+      for (int f = 0; f < 2; f++)
+        if (kn.fcost[f] != 0.0) for (int r = 0; r < 6; r++) rank1(w.DL + (6 * w.sidx[f] + r) * FNZ, FNZ, cfg.w_force[r]);
+      if (a0 < FN) {
+        for (int r = 0; r < 6; r++) if (cfg.w_cent[r] != 0.0) rank1(w.cj.Jcent + r * FN, FN, cfg.w_cent[r]);
+        if (a0 < NV && b0 < NV)
+          for (int r = 0; r < 6; r++) {
+            if (kn.w_lf[r] != 0.0) rank1(w.cj.Jpose + r * NV, NV, kn.w_lf[r]);
+            if (kn.w_rf[r] != 0.0) rank1(w.cj.Jpose + (6 + r) * NV, NV, kn.w_rf[r]);
+          }
+        if (b0 < 8 && a0 < 8) for (int r = 0; r < 6; r++) rank1(w.Jls + 6 * r, 6, cfg.wx[r]);
       }
-    io.H[a * FNZ + b] = hv; io.H[b * FNZ + a] = hv;
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int a = a0 + i, b = b0 + j;
+          if (a >= FNZ || b >= FNZ || b < a) continue;
+          double hv = acc[i][j];
+          if (a == b) { hv += io.preg; if (a >= FN) hv += cfg.wu[a - FN]; else if (a >= 6) hv += cfg.wx[a]; }
+          io.H[a * FNZ + b] = hv; io.H[b * FNZ + a] = hv;
+        }
+    }
   }
+  EPH(13);
   PAR_FOR(e, w.nca * FNZ) { // active constraint rows, compacted
     int ai = e / FNZ, z = e % FNZ, r = w.act_idx[ai];
     double c;
@@ -665,7 +725,7 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
     double dual = 0;
     for (int z = 6 + c; z < FNZ; z += 8) {
       if (io.k == 0 && z < FN) continue;
-      dual = fmax(dual, fabs(w.g[z]));
+      dual = fmax(dual, fabs(w.late.g[z]));
     }
     w.part[c] = dual;
   }
@@ -675,22 +735,24 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
     if (i == SC_DUAL) for (int c = 0; c < 8; c++) v = fmax(v, w.part[c]);
     io.scal[i] = v;
   }
+  EPH(14);
+  EPH_DUMP(io.phase_out);
 }
 
 // ------------------------------------------------------------------ terminal knot (fulldynamic_talos.py:234-245, 499-507)
-template <bool DERIV> HD void eval_full_term(const DevModel &m, const KnotIO &io, FullWs &w) {
+template <bool DERIV> HD void eval_full_term(const DevModel &m, const KnotIO &io, FullWsT<DERIV> &w) {
   const mpc_config_t &cfg = m.cfg;
   PAR_FOR(i, NQ + NV) w.x[i] = io.x[i];
   SYNC();
   mb_kinematics(m, w);
-  mb_cost_terms(m, w, io.tm->lf_ref, io.tm->rf_ref, DERIV);
+  mb_cost_terms(m, w, io.tm->lf_ref, io.tm->rf_ref, DERIV, nullptr);
   const bool has_c = io.tm->has_com_cstr != 0.0;
   PAR_FOR(r, FNC) {
     int type = -1; double hv = 0;
     if (r < 3 && has_c) { type = 0; hv = w.com[r] - io.tm->com_ref[r]; }
     int act = 0; double prim = 0;
     double vp = vplus_row(type, hv, io.v_prev[r], io.mu, 0, 0, act, prim);
-    w.ctype[r] = type; w.hval[r] = hv; w.vpl[r] = vp; w.isact[r] = act; w.dbr[r] = io.mu * (vp - io.v[r]); w.rowtmp[r] = fabs(prim);
+    w.ctype[r] = type; w.late.hval[r] = hv; w.late.vpl[r] = vp; w.isact[r] = act; w.late.dbr[r] = io.mu * (vp - io.v[r]); w.late.rowtmp[r] = fabs(prim);
     io.h[r] = hv;
   }
   SYNC();
@@ -699,9 +761,9 @@ template <bool DERIV> HD void eval_full_term(const DevModel &m, const KnotIO &io
     int nca = 0;
     for (int r = 0; r < 3; r++) {
       if (w.ctype[r] < 0) continue;
-      double dv = w.vpl[r] - io.v[r];
-      pen += 0.5 * io.mu * (w.vpl[r] * w.vpl[r] + dv * dv);
-      prim = fmax(prim, w.rowtmp[r]); inner = fmax(inner, fabs(w.dbr[r]));
+      double dv = w.late.vpl[r] - io.v[r];
+      pen += 0.5 * io.mu * (w.late.vpl[r] * w.late.vpl[r] + dv * dv);
+      prim = fmax(prim, w.late.rowtmp[r]); inner = fmax(inner, fabs(w.late.dbr[r]));
       if (w.isact[r]) w.act_idx[nca++] = r;
     }
     w.nca = nca;
@@ -709,7 +771,7 @@ template <bool DERIV> HD void eval_full_term(const DevModel &m, const KnotIO &io
   }
   SYNC();
   if (!DERIV) { PAR_FOR(i, SC_COUNT) io.scal[i] = w.scal[i]; return; }
-  PAR_FOR(i, FNC) { io.dbar[i] = w.dbr[i]; io.vplus[i] = w.vpl[i]; io.act_idx[i] = (i < w.nca) ? w.act_idx[i] : -1; }
+  PAR_FOR(i, FNC) { io.dbar[i] = w.late.dbr[i]; io.vplus[i] = w.late.vpl[i]; io.act_idx[i] = (i < w.nca) ? w.act_idx[i] : -1; }
   ONE_THREAD io.nca[0] = w.nca;
   PAR_FOR(z, FNZ) {
     double lz = (z < FN) ? mb_cost_grad(w, cfg.wx_term, cfg.w_cent_term, cfg.w_foot_term, cfg.w_foot_term, z) : 0.0;
@@ -717,7 +779,7 @@ template <bool DERIV> HD void eval_full_term(const DevModel &m, const KnotIO &io
     double gz = lz;
     if (z < NV && has_c) for (int r = 0; r < 3; r++) gz += io.v[r] * w.U[6 * z + r] / w.Ic[0];
     if (z >= 6 && z < FN) gz -= io.lam_k[z];
-    w.g[z] = gz; io.g[z] = gz;
+    w.late.g[z] = gz; io.g[z] = gz;
   }
   PAR_FOR(e, FNZ * FNZ) {
     int a = e / FNZ, b = e % FNZ;
@@ -734,7 +796,7 @@ template <bool DERIV> HD void eval_full_term(const DevModel &m, const KnotIO &io
   SYNC();
   ONE_THREAD {
     double dual = 0;
-    for (int z = 6; z < FN; z++) dual = fmax(dual, fabs(w.g[z]));
+    for (int z = 6; z < FN; z++) dual = fmax(dual, fabs(w.late.g[z]));
     w.scal[SC_DUAL] = dual;
   }
   SYNC();

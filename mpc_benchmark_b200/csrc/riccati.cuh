@@ -96,6 +96,7 @@ struct RiccatiIO {
   double *Kfb;           // [T][M][N]        controlFeedbacks()
   double *dxs, *dus, *dvs, *dlams; // [T+1][N], [T][M], [T+1][NC], [T+1][N]
   double *dphi;          // scalar
+  double *phase_out;     // optional 16 per-phase cycle counters (MPC_PHASE_TIMING builds), else nullptr
 };
 
 template <int N, int M, int NC> constexpr int riccati_smem_doubles() {

@@ -11,6 +11,17 @@
 
 namespace mpcdev {
 
+// optional per-phase cycle counters (thread 0 of the CTA handling instance 0), enabled with -DMPC_PHASE_TIMING
+#if defined(MPC_PHASE_TIMING) && !defined(MPC_HOST_EMU)
+#define PHASE_DECL long long ph_last = clock64(); long long ph_acc[16] = {0}
+#define PHASE(i) do { if (threadIdx.x == 0) { long long t_ = clock64(); ph_acc[i] += t_ - ph_last; ph_last = t_; } } while (0)
+#define PHASE_DUMP(ptr) do { if (threadIdx.x == 0 && (ptr)) for (int i_ = 0; i_ < 16; i_++) (ptr)[i_] = (double)ph_acc[i_]; } while (0)
+#else
+#define PHASE_DECL
+#define PHASE(i)
+#define PHASE_DUMP(ptr)
+#endif
+
 template <int N, int M, int NC> struct RicFastLayout {
   static constexpr int NZ = N + M, NR = 1 + N, S = M + NC;
   static constexpr int NBLK = N / 8;
@@ -31,6 +42,7 @@ template <int N, int M, int NC> HD void riccati_instance_fast(const RiccatiIO &i
   static_assert(N % 8 == 0, "fast Riccati needs n % 8 == 0");
   const int T = io.T;
   const double mu = io.mu, mu_d = io.mu_d;
+  PHASE_DECL;
   // ---- carve shared memory
   double *H = ws;                              // ZP x LDH, zero padded; [0:N,0:N] carries the value-function Hessian between knots
   double *U0 = H + ZP * LDH;
@@ -85,11 +97,14 @@ template <int N, int M, int NC> HD void riccati_instance_fast(const RiccatiIO &i
     PAR_FOR(e, 6 * N) { int i = e / N, j = e % N; P[i * LDN + j] = W[e]; }
     PAR_FOR(i, 6) p[i] = tmp[i];
     SYNC();
+    PHASE(0);
     // 2. G = chol(I + mu_d P);  pv = p + P f
     PAR_FOR(e, N * N) { int i = e / N, j = e % N; G[i * LDN + j] = mu_d * P[i * LDN + j] + ((i == j) ? 1.0 : 0.0); }
     PAR_FOR(i, N) { double s = p[i]; for (int j = 0; j < N; j++) s += P[i * LDN + j] * fb[j]; pv[i] = s; }
     SYNC();
+    PHASE(1);
     chol_blocked(G, N, LDN, dinv);
+    PHASE(2);
     // 3. Linv = G^-1 (lower triangular): independent forward-substitution chains, one per 8-column block and warp
     {
 #ifdef MPC_HOST_EMU
@@ -120,10 +135,12 @@ template <int N, int M, int NC> HD void riccati_instance_fast(const RiccatiIO &i
       }
       SYNC();
     }
+    PHASE(3);
     // 4. Lambda^-1 = Linv' Linv (into G);  5. Pt = Lambda^-1 P (into Li), pt = Lambda^-1 pv
     mma_tn(NBLK, NBLK, N, Li, LDN, Li, LDN, G, LDN, nullptr, 0, 0, 0, false);
     PAR_FOR(i, N) { double s = 0; for (int j = 0; j < N; j++) s += G[i * LDN + j] * pv[j]; pt[i] = s; }
     mma_tn(NBLK, NBLK, N, G, LDN, P, LDN, Li, LDN, nullptr, 0, 0, 0, false);
+    PHASE(4);
     // 6. W = Pt [A B];  7. H = H_k + [A B]' W;  gh = g + [A B]' pt
     mma_tn(NBLK, ZP / 8, N, Li, LDN, AB, LDZ, W, LDZ, nullptr, 0, 0, 0, false);
     mma_tn(ZP / 8, ZP / 8, N, AB, LDZ, W, LDZ, H, LDH, gH, NZ, NZ, NZ, false);
@@ -134,6 +151,7 @@ template <int N, int M, int NC> HD void riccati_instance_fast(const RiccatiIO &i
     }
     PAR_FOR(i, N) io.pt[(size_t)k * N + i] = pt[i];
     SYNC();
+    PHASE(5);
     // 8. KKT by block elimination (phase-2 buffers alias P/G/Li/AB/W, all dead now)
     const int ncol = NR + nca; // Z columns: [rh | Sh' | D']
     const double *gCD = io.CDact + (size_t)k * NC * NZ;
@@ -147,8 +165,11 @@ template <int N, int M, int NC> HD void riccati_instance_fast(const RiccatiIO &i
       Z[i * ncol + c] = (c == 0) ? gh[N + i] : (c < NR ? H[(c - 1) * LDH + N + i] : CD[(c - NR) * NZ + N + i]);
     }
     SYNC();
+    PHASE(6);
     chol_blocked(Rh, M, M, dinv);
+    PHASE(7);
     trsm_blocked(Rh, M, M, dinv, Z, ncol, ncol);
+    PHASE(8);
     PAR_FOR(e, nca * nca) {
       int r = e / nca, c = e % nca;
       double s = (r == c) ? mu : 0.0;
@@ -162,7 +183,9 @@ template <int N, int M, int NC> HD void riccati_instance_fast(const RiccatiIO &i
       Kv[e] = s;
     }
     SYNC();
+    PHASE(9);
     if (nca > 0) { chol_blocked(Sg, nca, nca, dinv); trsm_blocked(Sg, nca, nca, dinv, Kv, NR, NR); }
+    PHASE(10);
     PAR_FOR(e, M * NR) {
       int i = e / NR, c = e % NR;
       double s = -Z[i * ncol + c];
@@ -173,13 +196,34 @@ template <int N, int M, int NC> HD void riccati_instance_fast(const RiccatiIO &i
     double *gK = io.K + (size_t)k * S * NR;
     PAR_FOR(e, M * NR) { int i = e / NR, c = e % NR; double v = Z[i * ncol + c]; gK[e] = v; if (c > 0) io.Kfb[((size_t)k * M + i) * N + c - 1] = v; }
     PAR_FOR(e, nca * NR) gK[M * NR + e] = Kv[e];
+    PHASE(11);
     // 9. P = Qh + Sh Ku + C' Kv, p = qh + Sh ku + C' kv : in place in H[0:N,0:N] / p, then symmetrise
-    PAR_FOR(e, N * NR) {
-      int i = e / NR, c = e % NR;
-      double s = (c == 0) ? gh[i] : H[i * LDH + c - 1];
-      for (int l = 0; l < M; l++) s += H[i * LDH + N + l] * Z[l * ncol + c];
-      for (int r = 0; r < nca; r++) s += CD[r * NZ + i] * Kv[r * NR + c];
-      if (c == 0) p[i] = s; else H[i * LDH + c - 1] = s;
+    { // 2 x 4 register tiles over (row i, column c of [p | P]); column 0 is the vector p
+      constexpr int TC = (NR + 3) / 4;
+      PAR_FOR(t, (N / 2) * TC) {
+        const int i0 = (t / TC) * 2, c0 = (t % TC) * 4;
+        double a[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+#pragma unroll
+          for (int q = 0; q < 4; q++) { int c = c0 + q; a[r][q] = (c >= NR) ? 0.0 : ((c == 0) ? gh[i0 + r] : H[(i0 + r) * LDH + c - 1]); }
+        for (int l = 0; l < M; l++) {
+          const double h0 = H[i0 * LDH + N + l], h1 = H[(i0 + 1) * LDH + N + l];
+          const double *zr = Z + l * ncol + c0;
+#pragma unroll
+          for (int q = 0; q < 4; q++) { double zv = (c0 + q < NR) ? zr[q] : 0.0; a[0][q] += h0 * zv; a[1][q] += h1 * zv; }
+        }
+        for (int r = 0; r < nca; r++) {
+          const double h0 = CD[r * NZ + i0], h1 = CD[r * NZ + i0 + 1];
+          const double *kr = Kv + r * NR + c0;
+#pragma unroll
+          for (int q = 0; q < 4; q++) { double kv = (c0 + q < NR) ? kr[q] : 0.0; a[0][q] += h0 * kv; a[1][q] += h1 * kv; }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+#pragma unroll
+          for (int q = 0; q < 4; q++) { int c = c0 + q; if (c == 0) p[i0 + r] = a[r][q]; else if (c < NR) H[(i0 + r) * LDH + c - 1] = a[r][q]; }
+      }
     }
     SYNC();
     PAR_FOR(e, N * N) {
@@ -187,8 +231,10 @@ template <int N, int M, int NC> HD void riccati_instance_fast(const RiccatiIO &i
       if (i < j) { double s = 0.5 * (H[i * LDH + j] + H[j * LDH + i]); H[i * LDH + j] = s; H[j * LDH + i] = s; }
     }
     SYNC();
+    PHASE(12);
   }
   // ---- forward sweep, dx0 = 0 (force_initial_condition, fulldynamic_talos.py:384)
+  PHASE(13);
   double acc = 0.0;
   PAR_FOR(i, N) { dx[i] = 0.0; io.dxs[i] = 0.0; io.dlams[i] = -p[i]; }
   SYNC();
@@ -243,6 +289,8 @@ template <int N, int M, int NC> HD void riccati_instance_fast(const RiccatiIO &i
     }
     SYNC();
   }
+  PHASE(14);
+  PHASE_DUMP(io.phase_out);
   red[TID] = acc;
   SYNC();
   ONE_THREAD { double s = 0; for (int t = 0; t < NTHREADS; t++) s += red[t]; io.dphi[0] = s; }

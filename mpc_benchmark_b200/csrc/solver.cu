@@ -30,7 +30,7 @@ static int fail(const std::string &m) { g_err = m; return 1; }
 // ------------------------------------------------------------------ kernels
 __global__ void k_init(Ws w, const double *xs_in, const double *us_in, int max_iters) { init_instance(w, blockIdx.x, xs_in, us_in, max_iters); }
 
-template <bool DERIV> __global__ void __launch_bounds__(128) k_eval(Ws w, const int32_t *list) {
+template <bool DERIV> __global__ void __launch_bounds__(128, DERIV ? 3 : 4) k_eval(Ws w, const int32_t *list) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int T1 = w.T + 1;
   const int b = list[blockIdx.x / T1], k = blockIdx.x % T1;
@@ -91,7 +91,7 @@ struct mpc_solver {
   int32_t *h_counters = nullptr; // pinned
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  size_t eval_smem = 0, ric_smem = 0;
+  size_t eval_smem = 0, eval_smem_values = 0, ric_smem = 0;
   int eval_threads = 128, ric_threads = 256;
   int last_launches = 0;
   float last_ms = 0;
@@ -120,7 +120,7 @@ struct CudaBackend {
   void eval(bool d, const int32_t *list, int n) {
     const int grid = n * (h->w.T + 1);
     mark(d ? 0 : 2);
-    if (d) k_eval<true><<<grid, h->eval_threads, h->eval_smem, s>>>(h->w, list); else k_eval<false><<<grid, h->eval_threads, h->eval_smem, s>>>(h->w, list);
+    if (d) k_eval<true><<<grid, h->eval_threads, h->eval_smem, s>>>(h->w, list); else k_eval<false><<<grid, h->eval_threads, h->eval_smem_values, s>>>(h->w, list);
   }
   void decide_eval(const int32_t *list, int n, int32_t *next_eval) { mark(3); k_decide_eval<<<n, 128, 0, s>>>(h->w, list, next_eval); }
   void riccati(const int32_t *list, int n) { mark(1); k_riccati<<<n, h->ric_threads, h->ric_smem, s>>>(h->w, list); }
@@ -135,11 +135,11 @@ struct CudaBackend {
 };
 
 static int set_kernel_attrs(mpc_solver *h) {
-  if (h->w.kind == MPC_KIND_FULL) { h->eval_smem = sizeof(FullWs); h->eval_threads = 128; h->ric_smem = RicFastLayout<56, 22, 78>::total * 8; h->ric_threads = 256; }
-  else { h->eval_smem = sizeof(CentWs); h->eval_threads = 32; h->ric_smem = riccati_smem_doubles<9, 12, 34>() * 8; h->ric_threads = 64; }
+  if (h->w.kind == MPC_KIND_FULL) { h->eval_smem = sizeof(FullWsT<true>); h->eval_smem_values = sizeof(FullWsT<false>); h->eval_threads = 128; h->ric_smem = RicFastLayout<56, 22, 78>::total * 8; h->ric_threads = 256; }
+  else { h->eval_smem = h->eval_smem_values = sizeof(CentWs); h->eval_threads = 32; h->ric_smem = riccati_smem_doubles<9, 12, 34>() * 8; h->ric_threads = 64; }
   if (const char *e = getenv("MPCB200_RIC_THREADS")) { int t = atoi(e); if (t >= 32 && t <= 256 && h->w.kind == MPC_KIND_FULL) h->ric_threads = t; }
-  CK(cudaFuncSetAttribute(k_eval<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FullWs)));
-  CK(cudaFuncSetAttribute(k_eval<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FullWs)));
+  CK(cudaFuncSetAttribute(k_eval<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FullWsT<true>)));
+  CK(cudaFuncSetAttribute(k_eval<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FullWsT<true>)));
   CK(cudaFuncSetAttribute(k_riccati, cudaFuncAttributeMaxDynamicSharedMemorySize, RicFastLayout<56, 22, 78>::total * 8));
   return 0;
 }
@@ -398,6 +398,13 @@ int32_t mpc_get_feedback(mpc_solver_t *h, int32_t k, double *K) {
 }
 double mpc_last_device_ms(mpc_solver_t *h) { return h->last_ms; }
 uint64_t mpc_workspace_bytes(mpc_solver_t *h) { return h->bytes; }
+// per-phase cycle counters of the Riccati kernel for instance 0 (all zero unless built with -DMPC_PHASE_TIMING)
+int32_t mpc_debug_phases(mpc_solver_t *h, double *out16) {
+  CK(cudaSetDevice(h->device));
+  if (!h->setup_done) return fail("mpc_debug_phases before mpc_setup");
+  CK(cudaMemcpy(out16, h->w.phase, 32 * 8, cudaMemcpyDeviceToHost)); // [0:16) Riccati, [16:32) evaluation kernel
+  return 0;
+}
 
 int32_t mpc_debug_lq(mpc_solver_t *h, const double *xs, const double *us, int32_t inst, double *AB, double *H, double *g, double *gap,
                      double *hval, double *scal) {

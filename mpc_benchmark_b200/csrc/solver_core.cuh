@@ -21,7 +21,7 @@ struct SolverConst {
   int max_al_iters;
   double prim_alpha, prim_beta, dual_alpha, dual_beta, mu_update_factor, mu_lower_bound;
   double reg_init, reg_min, reg_max, reg_inc, reg_dec;
-  double ls_c1, ls_alpha_min, ls_contr_min, ls_contr_max;
+  double ls_c1, ls_alpha_min, ls_contr_min, ls_contr_max, ls_dphi_rel;
   int ls_max_steps;
 };
 inline SolverConst default_consts(double tol, double mu_init) {
@@ -29,7 +29,7 @@ inline SolverConst default_consts(double tol, double mu_init) {
   c.tol = tol; c.mu_init = mu_init; c.max_al_iters = 100;
   c.prim_alpha = 0.1; c.prim_beta = 0.9; c.dual_alpha = 1.0; c.dual_beta = 1.0; c.mu_update_factor = 0.01; c.mu_lower_bound = 1e-8;
   c.reg_init = 1e-9; c.reg_min = 1e-10; c.reg_max = 1e9; c.reg_inc = 10.0; c.reg_dec = 1.0 / 3.0;
-  c.ls_c1 = 1e-4; c.ls_alpha_min = 1e-7; c.ls_contr_min = 0.5; c.ls_contr_max = 0.8; c.ls_max_steps = 20;
+  c.ls_c1 = 1e-4; c.ls_alpha_min = 1e-7; c.ls_contr_min = 0.5; c.ls_contr_max = 0.8; c.ls_max_steps = 20; c.ls_dphi_rel = 1e-11;
   return c;
 }
 
@@ -54,6 +54,7 @@ struct Ws {
   double *W, *pt, *K, *Kfb, *dphi;
   InstState *st;
   int32_t *counters; // [0] instances still in MODE_LS (next ls list), [2] instances to evaluate in the next pass
+  double *phase;     // 16 doubles: per-phase cycle counters of instance 0 (MPC_PHASE_TIMING builds)
   int32_t *lists;    // [4][B] compacted instance lists: 0,1 = evaluation lists (double-buffered), 2,3 = linesearch lists
 };
 HDH int32_t *eval_list(const Ws &w, int which) { return w.lists + (size_t)(which & 1) * w.B; }
@@ -79,6 +80,7 @@ HD KnotIO make_io(const Ws &w, int b, int k, bool trial) {
   io.CDact = w.CDact + kb * w.nc * w.nz; io.nca = w.nca + kb; io.act_idx = w.act_idx + kb * w.nc;
   io.gap = w.gap + kT * w.n; io.h = w.h + kb * w.nc; io.scal = (trial ? w.tscal : w.scal) + kb * SC_COUNT;
   io.xdot = w.xdot + kb * 56; io.lamc = w.lamc + kb * 12;
+  io.phase_out = (b == 0 && k == 1 && !trial) ? w.phase + 16 : nullptr;
   return io;
 }
 
@@ -204,7 +206,8 @@ HD void decide_ls(const Ws &w, int b, double *red, int32_t *ls_out, int32_t *nex
     for (int k = 0; k <= w.T; k++) { const double *sc = w.tscal + (b * T1 + k) * SC_COUNT; cost += sc[SC_COST]; pen += sc[SC_PEN]; }
     const double phi = cost + pen, phi0 = s.merit, dphi0 = s.dphi0, alpha = s.alpha;
     s.ls_evals++;
-    bool accept = (phi <= phi0 + c.ls_c1 * alpha * dphi0) || alpha <= c.ls_alpha_min || s.ls_it + 1 >= c.ls_max_steps;
+    bool accept = (phi <= phi0 + c.ls_c1 * alpha * dphi0) || alpha <= c.ls_alpha_min || s.ls_it + 1 >= c.ls_max_steps ||
+                  (fabs(dphi0) <= c.ls_dphi_rel * fmax(1.0, fabs(phi0)) && isfinite(phi)); // decrease below merit resolution
     red[0] = accept ? 1.0 : 0.0;
     if (accept) {
       if (!isfinite(phi)) { s.status = 2; s.mode = MODE_DONE; red[0] = 0.0; }
@@ -252,7 +255,7 @@ template <bool DERIV> HD void eval_dispatch(const Ws &w, int b, int k, void *sme
   if (mode != (DERIV ? MODE_EVAL : MODE_LS)) return;
   KnotIO io = make_io(w, b, k, !DERIV);
   if (w.kind == MPC_KIND_FULL) {
-    FullWs &f = *reinterpret_cast<FullWs *>(smem);
+    FullWsT<DERIV> &f = *reinterpret_cast<FullWsT<DERIV> *>(smem);
     if (k < w.T) eval_full_knot<DERIV>(*w.model, io, f); else eval_full_term<DERIV>(*w.model, io, f);
   } else if (w.kind == MPC_KIND_CENT) {
     CentWs &c = *reinterpret_cast<CentWs *>(smem);
@@ -271,6 +274,7 @@ HD RiccatiIO make_riccati_io(const Ws &w, int b) {
   r.W = w.W + b * T * w.n * w.nz; r.pt = w.pt + b * T * w.n; r.K = w.K + b * T * (w.m + w.nc) * (1 + w.n); r.Kfb = w.Kfb + b * T * w.m * w.n;
   r.dxs = w.dxs + b * T1 * w.n; r.dus = w.dus + b * T * w.m; r.dvs = w.dvs + b * T1 * w.nc; r.dlams = w.dlams + b * T1 * w.n;
   r.dphi = w.dphi + b;
+  r.phase_out = (b == 0) ? w.phase : nullptr;
   return r;
 }
 

@@ -12,6 +12,8 @@
 #include <algorithm>
 #include <cmath>
 #include <limits>
+#include <cstdio>
+#include <cstdlib>
 
 namespace orc {
 
@@ -23,6 +25,7 @@ struct SolverParams {
   double reg_init = 1e-9, reg_min = 1e-10, reg_max = 1e9, reg_inc = 10.0, reg_dec = 1.0 / 3.0;
   double ls_c1 = 1e-4, ls_alpha_min = 1e-7, ls_contr_min = 0.5, ls_contr_max = 0.8;
   int ls_max_steps = 20;
+  double ls_dphi_rel = 1e-11; // predicted decrease below the fp64 resolution of the merit: Armijo is meaningless, take the step
   bool par_knots = false; // OpenMP over knots (reference: setNumThreads(8), fulldynamic_talos.py:385)
 };
 
@@ -271,6 +274,7 @@ struct Solver {
       ls_evals++;
       phi_out = phi; cost_out = c;
       if (phi <= phi0 + prm.ls_c1 * alpha * dphi0) return alpha;
+      if (std::fabs(dphi0) <= prm.ls_dphi_rel * std::max(1.0, std::fabs(phi0)) && std::isfinite(phi)) return alpha;
       if (alpha <= prm.ls_alpha_min || it + 1 >= prm.ls_max_steps) return alpha;
       double a_new;
       if (it == 0) a_new = -dphi0 * alpha * alpha / (2.0 * (phi - phi0 - dphi0 * alpha));
@@ -326,6 +330,7 @@ struct Solver {
       double phi_new, cost_new;
       double alpha = linesearch(in, merit, dphi0, phi_new, cost_new);
       alphas.push_back(alpha); alpha_last = alpha;
+      if (getenv("ORC_VERBOSE")) fprintf(stderr, "it %3d prim %.3e dual %.3e inner %.3e merit %.10e dphi0 %.3e alpha %.3e ls %d preg %.1e mu %.1e al %d\n", num_iters, prim_infeas, dual_infeas, inner_crit, merit, dphi0, alpha, ls_evals, preg, mu, al_iters);
       if (!std::isfinite(phi_new)) { status = 2; break; }
       xs.swap(txs); us.swap(tus); vs.swap(tvs); lams.swap(tlams);
       ev.swap(tr); // values at the accepted point (xdot, contact forces: workspace read-back, full:467-480)

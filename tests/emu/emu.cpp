@@ -32,7 +32,7 @@ struct EmuBackend {
 extern "C" int emu_solve(const mpc_robot_t *rb, const mpc_config_t *cfg, int batch, const mpc_knot_t *knots, const mpc_term_t *terms,
                          const double *x0, double *xs, double *us, double *K, double *vs, double *lams, mpc_info_t *info, double *stage0,
                          int max_iters, double *lq_dump /* optional: AB,H,g of instance 0 after the first derivative pass */) {
-  static_assert(sizeof(FullWs) <= 40000 * 8, "smem");
+  static_assert(sizeof(FullWsT<true>) <= 40000 * 8, "smem");
   DevModel *model = new DevModel;
   const char *err = nullptr;
   if (build_dev_model(rb, cfg, model, &err)) return 1;
