@@ -96,6 +96,7 @@ struct RiccatiIO {
   double *Kfb;           // [T][M][N]        controlFeedbacks()
   double *dxs, *dus, *dvs, *dlams; // [T+1][N], [T][M], [T+1][NC], [T+1][N]
   double *dphi;          // scalar
+  int32_t *overflow;     // set to 1 when a knot has more active rows than the kernel's shared-memory capacity
   double *phase_out;     // optional 16 per-phase cycle counters (MPC_PHASE_TIMING builds), else nullptr
 };
 

@@ -22,22 +22,23 @@ namespace mpcdev {
 #define PHASE_DUMP(ptr)
 #endif
 
-template <int N, int M, int NC> struct RicFastLayout {
+template <int N, int M, int NC, int NCAP = NC> struct RicFastLayout {
   static constexpr int NZ = N + M, NR = 1 + N, S = M + NC;
   static constexpr int NBLK = N / 8;
   static constexpr int ZP = (NZ + 7) / 8 * 8;                       // padded n+m
   static constexpr int LDN = (N % 16 == 8) ? N : N + 8;             // ld of N x N buffers
   static constexpr int LDZ = (ZP % 16 == 8) ? ZP : ZP + 8;          // ld of N x ZP buffers (AB, W)
   static constexpr int LDH = ZP;                                    // ld of the Hessian buffer
-  static constexpr int phase1 = 3 * N * LDN + 2 * N * LDZ;
-  static constexpr int phase2 = NC * NZ + NC * NC + M * (NR + NC) + NC * NR + M * M;
+  static_assert(N * LDZ <= 2 * N * LDN, "W must fit over the dead [P | G] buffers");
+  static constexpr int phase1 = 3 * N * LDN + N * LDZ;  // P, G (later reused as W), Li, AB
+  static constexpr int phase2 = NCAP * NZ + NCAP * NCAP + M * (NR + NCAP) + NCAP * NR + M * M; // sized for NCAP active rows
   static constexpr int un = phase1 > phase2 ? phase1 : phase2;
   static constexpr int vecs = 8 * ZP + 36 + 2 * NC + 256 + 64 * ((NC + 7) / 8) + 8 * 64 + 16;
   static constexpr int total = ZP * LDH + un + vecs;
 };
 
-template <int N, int M, int NC> HD void riccati_instance_fast(const RiccatiIO &io, double *ws) {
-  using Lay = RicFastLayout<N, M, NC>;
+template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(const RiccatiIO &io, double *ws) {
+  using Lay = RicFastLayout<N, M, NC, NCAP>;
   constexpr int NZ = Lay::NZ, NR = Lay::NR, S = Lay::S, ZP = Lay::ZP, LDN = Lay::LDN, LDZ = Lay::LDZ, LDH = Lay::LDH, NBLK = Lay::NBLK;
   static_assert(N % 8 == 0, "fast Riccati needs n % 8 == 0");
   const int T = io.T;
@@ -46,8 +47,8 @@ template <int N, int M, int NC> HD void riccati_instance_fast(const RiccatiIO &i
   // ---- carve shared memory
   double *H = ws;                              // ZP x LDH, zero padded; [0:N,0:N] carries the value-function Hessian between knots
   double *U0 = H + ZP * LDH;
-  double *P = U0, *G = P + N * LDN, *Li = G + N * LDN, *AB = Li + N * LDN, *W = AB + N * LDZ;                // phase 1
-  double *CD = U0, *Sg = CD + NC * NZ, *Z = Sg + NC * NC, *Kv = Z + M * (NR + NC), *Rh = Kv + NC * NR;        // phase 2
+  double *P = U0, *G = P + N * LDN, *Li = G + N * LDN, *AB = Li + N * LDN, *W = P;  // phase 1 (W overwrites the dead P, G)
+  double *CD = U0, *Sg = CD + NCAP * NZ, *Z = Sg + NCAP * NCAP, *Kv = Z + M * (NR + NCAP), *Rh = Kv + NCAP * NR;  // phase 2
   double *vec = U0 + Lay::un;
   double *p = vec, *pt = p + ZP, *gh = pt + ZP, *fb = gh + ZP, *tmp = fb + ZP, *dx = tmp + ZP, *z = dx + ZP, *pv = z + ZP;
   double *T6 = pv + ZP, *dbr = T6 + 36, *dva = dbr + NC, *red = dva + NC, *dinv = red + 256, *wtmp = dinv + 64 * ((NC + 7) / 8);
@@ -74,7 +75,8 @@ template <int N, int M, int NC> HD void riccati_instance_fast(const RiccatiIO &i
   }
   for (int k = T - 1; k >= 0; k--) {
     const double *gAB = io.AB + (size_t)k * N * NZ, *gH = io.H + (size_t)k * NZ * NZ;
-    const int nca = io.nca[k];
+    int nca = io.nca[k];
+    if (nca > NCAP) { nca = NCAP; ONE_THREAD { if (io.overflow) *io.overflow = 1; } } // more active rows than the shared-memory KKT holds
     // 1. stage [A B] (zero-padded columns), P <- value Hessian, E normalisation P <- T' P T, p <- T' p
     PAR_FOR(e, N * (ZP / 2)) {
       int i = e / (ZP / 2), j = (e % (ZP / 2)) * 2;
@@ -85,18 +87,18 @@ template <int N, int M, int NC> HD void riccati_instance_fast(const RiccatiIO &i
     PAR_FOR(e, N * N) { int i = e / N, j = e % N; P[i * LDN + j] = H[i * LDH + j]; }
     PAR_FOR(e, 36) T6[e] = io.T6[(size_t)k * 36 + e];
     PAR_FOR(i, N) fb[i] = io.fbar[(size_t)k * N + i];
-    PAR_FOR(e, N * LDN) Li[e] = 0.0;
     SYNC();
-    PAR_FOR(e, N * 6) { int i = e / 6, j = e % 6; double s = 0; for (int l = 0; l < 6; l++) s += P[i * LDN + l] * T6[6 * l + j]; W[e] = s; }
+    PAR_FOR(e, N * 6) { int i = e / 6, j = e % 6; double s = 0; for (int l = 0; l < 6; l++) s += P[i * LDN + l] * T6[6 * l + j]; Li[e] = s; }
     SYNC();
-    PAR_FOR(e, N * 6) { int i = e / 6, j = e % 6; P[i * LDN + j] = W[e]; }
+    PAR_FOR(e, N * 6) { int i = e / 6, j = e % 6; P[i * LDN + j] = Li[e]; }
     SYNC();
-    PAR_FOR(e, 6 * N) { int i = e / N, j = e % N; double s = 0; for (int l = 0; l < 6; l++) s += T6[6 * l + i] * P[l * LDN + j]; W[e] = s; }
+    PAR_FOR(e, 6 * N) { int i = e / N, j = e % N; double s = 0; for (int l = 0; l < 6; l++) s += T6[6 * l + i] * P[l * LDN + j]; Li[e] = s; }
     PAR_FOR(i, 6) { double s = 0; for (int l = 0; l < 6; l++) s += T6[6 * l + i] * p[l]; tmp[i] = s; }
     SYNC();
-    PAR_FOR(e, 6 * N) { int i = e / N, j = e % N; P[i * LDN + j] = W[e]; }
+    PAR_FOR(e, 6 * N) { int i = e / N, j = e % N; P[i * LDN + j] = Li[e]; }
     PAR_FOR(i, 6) p[i] = tmp[i];
     SYNC();
+    PAR_FOR(e, N * LDN) Li[e] = 0.0;
     PHASE(0);
     // 2. G = chol(I + mu_d P);  pv = p + P f
     PAR_FOR(e, N * N) { int i = e / N, j = e % N; G[i * LDN + j] = mu_d * P[i * LDN + j] + ((i == j) ? 1.0 : 0.0); }

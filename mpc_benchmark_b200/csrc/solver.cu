@@ -30,11 +30,11 @@ static int fail(const std::string &m) { g_err = m; return 1; }
 // ------------------------------------------------------------------ kernels
 __global__ void k_init(Ws w, const double *xs_in, const double *us_in, int max_iters) { init_instance(w, blockIdx.x, xs_in, us_in, max_iters); }
 
-template <bool DERIV> __global__ void __launch_bounds__(128, DERIV ? 3 : 4) k_eval(Ws w, const int32_t *list) {
+template <int KIND, bool DERIV> __global__ void __launch_bounds__(128, DERIV ? 3 : 4) k_eval(Ws w, const int32_t *list) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int T1 = w.T + 1;
   const int b = list[blockIdx.x / T1], k = blockIdx.x % T1;
-  eval_dispatch<DERIV>(w, b, k, smem_raw);
+  eval_dispatch<KIND, DERIV>(w, b, k, smem_raw);
 }
 
 __global__ void k_decide_eval(Ws w, const int32_t *list, int32_t *next_eval) {
@@ -42,9 +42,9 @@ __global__ void k_decide_eval(Ws w, const int32_t *list, int32_t *next_eval) {
   decide_eval(w, list[blockIdx.x], red, next_eval);
 }
 
-__global__ void __launch_bounds__(256) k_riccati(Ws w, const int32_t *list) {
+template <int KIND> __global__ void __launch_bounds__(256) k_riccati(Ws w, const int32_t *list) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  riccati_dispatch(w, list[blockIdx.x], reinterpret_cast<double *>(smem_raw));
+  riccati_dispatch<KIND>(w, list[blockIdx.x], reinterpret_cast<double *>(smem_raw));
 }
 
 __global__ void k_apply_step(Ws w, const int32_t *list) {
@@ -120,10 +120,24 @@ struct CudaBackend {
   void eval(bool d, const int32_t *list, int n) {
     const int grid = n * (h->w.T + 1);
     mark(d ? 0 : 2);
-    if (d) k_eval<true><<<grid, h->eval_threads, h->eval_smem, s>>>(h->w, list); else k_eval<false><<<grid, h->eval_threads, h->eval_smem_values, s>>>(h->w, list);
+    const int th = h->eval_threads;
+    const size_t sm = d ? h->eval_smem : h->eval_smem_values;
+    switch (h->w.kind * 2 + (d ? 1 : 0)) {
+    case MPC_KIND_FULL * 2 + 1: k_eval<MPC_KIND_FULL, true><<<grid, th, sm, s>>>(h->w, list); break;
+    case MPC_KIND_FULL * 2 + 0: k_eval<MPC_KIND_FULL, false><<<grid, th, sm, s>>>(h->w, list); break;
+    case MPC_KIND_KINO * 2 + 1: k_eval<MPC_KIND_KINO, true><<<grid, th, sm, s>>>(h->w, list); break;
+    case MPC_KIND_KINO * 2 + 0: k_eval<MPC_KIND_KINO, false><<<grid, th, sm, s>>>(h->w, list); break;
+    case MPC_KIND_CENT * 2 + 1: k_eval<MPC_KIND_CENT, true><<<grid, th, sm, s>>>(h->w, list); break;
+    default: k_eval<MPC_KIND_CENT, false><<<grid, th, sm, s>>>(h->w, list); break;
+    }
   }
   void decide_eval(const int32_t *list, int n, int32_t *next_eval) { mark(3); k_decide_eval<<<n, 128, 0, s>>>(h->w, list, next_eval); }
-  void riccati(const int32_t *list, int n) { mark(1); k_riccati<<<n, h->ric_threads, h->ric_smem, s>>>(h->w, list); }
+  void riccati(const int32_t *list, int n) {
+    mark(1);
+    if (h->w.kind == MPC_KIND_FULL) k_riccati<MPC_KIND_FULL><<<n, h->ric_threads, h->ric_smem, s>>>(h->w, list);
+    else if (h->w.kind == MPC_KIND_KINO) k_riccati<MPC_KIND_KINO><<<n, h->ric_threads, h->ric_smem, s>>>(h->w, list);
+    else k_riccati<MPC_KIND_CENT><<<n, h->ric_threads, h->ric_smem, s>>>(h->w, list);
+  }
   void apply_step(const int32_t *list, int n) { mark(3); k_apply_step<<<n, 128, 0, s>>>(h->w, list); }
   void decide_ls(const int32_t *list, int n, int32_t *ls_out, int32_t *next_eval) { mark(3); k_decide_ls<<<n, 128, 0, s>>>(h->w, list, ls_out, next_eval); mark(-1); }
   void read_counters(int *c) {
@@ -136,11 +150,18 @@ struct CudaBackend {
 
 static int set_kernel_attrs(mpc_solver *h) {
   if (h->w.kind == MPC_KIND_FULL) { h->eval_smem = sizeof(FullWsT<true>); h->eval_smem_values = sizeof(FullWsT<false>); h->eval_threads = 128; h->ric_smem = RicFastLayout<56, 22, 78>::total * 8; h->ric_threads = 256; }
+  else if (h->w.kind == MPC_KIND_KINO) { h->eval_smem = sizeof(KinoWsT<true>); h->eval_smem_values = sizeof(KinoWsT<false>); h->eval_threads = 128;
+    h->ric_smem = RicFastLayout<56, 34, 68, KINO_NCAP>::total * 8; h->ric_threads = 256; }
   else { h->eval_smem = h->eval_smem_values = sizeof(CentWs); h->eval_threads = 32; h->ric_smem = riccati_smem_doubles<9, 12, 34>() * 8; h->ric_threads = 64; }
-  if (const char *e = getenv("MPCB200_RIC_THREADS")) { int t = atoi(e); if (t >= 32 && t <= 256 && h->w.kind == MPC_KIND_FULL) h->ric_threads = t; }
-  CK(cudaFuncSetAttribute(k_eval<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FullWsT<true>)));
-  CK(cudaFuncSetAttribute(k_eval<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FullWsT<true>)));
-  CK(cudaFuncSetAttribute(k_riccati, cudaFuncAttributeMaxDynamicSharedMemorySize, RicFastLayout<56, 22, 78>::total * 8));
+  if (const char *e = getenv("MPCB200_RIC_THREADS")) { int t = atoi(e); if (t >= 32 && t <= 256 && h->w.kind != MPC_KIND_CENT) h->ric_threads = t; }
+  static_assert(RicFastLayout<56, 22, 78>::total * 8 <= 232448 && RicFastLayout<56, 34, 68, KINO_NCAP>::total * 8 <= 232448,
+                "Riccati shared memory exceeds the 227 KB opt-in limit");
+  CK(cudaFuncSetAttribute(k_eval<MPC_KIND_FULL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FullWsT<true>)));
+  CK(cudaFuncSetAttribute(k_eval<MPC_KIND_FULL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FullWsT<false>)));
+  CK(cudaFuncSetAttribute(k_eval<MPC_KIND_KINO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KinoWsT<true>)));
+  CK(cudaFuncSetAttribute(k_eval<MPC_KIND_KINO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KinoWsT<false>)));
+  CK(cudaFuncSetAttribute(k_riccati<MPC_KIND_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, RicFastLayout<56, 22, 78>::total * 8));
+  CK(cudaFuncSetAttribute(k_riccati<MPC_KIND_KINO>, cudaFuncAttributeMaxDynamicSharedMemorySize, RicFastLayout<56, 34, 68, KINO_NCAP>::total * 8));
   return 0;
 }
 
@@ -151,7 +172,7 @@ const char *mpc_last_error(void) { return g_err.c_str(); }
 mpc_solver_t *mpc_create(const mpc_robot_t *robot, const mpc_config_t *cfg, int32_t batch, int32_t device) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_err = "no CUDA device: libmpcb200 has no CPU fallback"; return nullptr; }
-  if (cfg->kind != MPC_KIND_FULL && cfg->kind != MPC_KIND_CENT) { g_err = "model kind not implemented in this build (kinodynamic: next round)"; return nullptr; }
+  if (cfg->kind != MPC_KIND_FULL && cfg->kind != MPC_KIND_CENT && cfg->kind != MPC_KIND_KINO) { g_err = "unknown model kind"; return nullptr; }
   if (cudaSetDevice(device) != cudaSuccess) { g_err = "cudaSetDevice failed"; return nullptr; }
   mpc_solver *h = new mpc_solver;
   h->device = device;

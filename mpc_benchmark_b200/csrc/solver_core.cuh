@@ -9,12 +9,14 @@
 #pragma once
 #include "eval_cent.cuh"
 #include "eval_full.cuh"
+#include "eval_kino.cuh"
 #include "riccati.cuh"
 #include "riccati_fast.cuh"
 
 namespace mpcdev {
 
 enum { MODE_EVAL = 0, MODE_STEP = 1, MODE_LS = 2, MODE_DONE = 3 };
+constexpr int KINO_NCAP = 56; // active rows the kinodynamic Riccati keeps in shared memory (68 possible; > 56 flags status 3)
 
 struct SolverConst {
   double tol, mu_init;
@@ -54,6 +56,7 @@ struct Ws {
   double *W, *pt, *K, *Kfb, *dphi;
   InstState *st;
   int32_t *counters; // [0] instances still in MODE_LS (next ls list), [2] instances to evaluate in the next pass
+  int32_t *overflow; // [B] Riccati active-row overflow flags
   double *phase;     // 16 doubles: per-phase cycle counters of instance 0 (MPC_PHASE_TIMING builds)
   int32_t *lists;    // [4][B] compacted instance lists: 0,1 = evaluation lists (double-buffered), 2,3 = linesearch lists
 };
@@ -249,15 +252,19 @@ HD void decide_ls(const Ws &w, int b, double *red, int32_t *ls_out, int32_t *nex
   }
 }
 
-// ---- one (instance, knot) evaluation; dispatch on the model kind. ws_smem: FullWs or CentWs storage.
-template <bool DERIV> HD void eval_dispatch(const Ws &w, int b, int k, void *smem) {
+// ---- one (instance, knot) evaluation; KIND is a compile-time parameter so every model gets its own kernel (registers,
+// shared memory and spills of one stage type do not tax the others).  smem: FullWsT / KinoWsT / CentWs storage.
+template <int KIND, bool DERIV> HD void eval_dispatch(const Ws &w, int b, int k, void *smem) {
   const int mode = w.st[b].mode;
   if (mode != (DERIV ? MODE_EVAL : MODE_LS)) return;
   KnotIO io = make_io(w, b, k, !DERIV);
-  if (w.kind == MPC_KIND_FULL) {
+  if (KIND == MPC_KIND_FULL) {
     FullWsT<DERIV> &f = *reinterpret_cast<FullWsT<DERIV> *>(smem);
     if (k < w.T) eval_full_knot<DERIV>(*w.model, io, f); else eval_full_term<DERIV>(*w.model, io, f);
-  } else if (w.kind == MPC_KIND_CENT) {
+  } else if (KIND == MPC_KIND_KINO) {
+    KinoWsT<DERIV> &f = *reinterpret_cast<KinoWsT<DERIV> *>(smem);
+    if (k < w.T) eval_kino_knot<DERIV>(*w.model, io, f); else eval_kino_term<DERIV>(*w.model, io, f);
+  } else {
     CentWs &c = *reinterpret_cast<CentWs *>(smem);
     if (k < w.T) eval_cent_knot<DERIV>(*w.model, io, c); else eval_cent_term<DERIV>(*w.model, io, c);
   }
@@ -275,14 +282,18 @@ HD RiccatiIO make_riccati_io(const Ws &w, int b) {
   r.dxs = w.dxs + b * T1 * w.n; r.dus = w.dus + b * T * w.m; r.dvs = w.dvs + b * T1 * w.nc; r.dlams = w.dlams + b * T1 * w.n;
   r.dphi = w.dphi + b;
   r.phase_out = (b == 0) ? w.phase : nullptr;
+  r.overflow = w.overflow + b;
   return r;
 }
 
-HD void riccati_dispatch(const Ws &w, int b, double *smem) {
+template <int KIND> HD void riccati_dispatch(const Ws &w, int b, double *smem) {
   if (w.st[b].mode != MODE_STEP) return;
   RiccatiIO r = make_riccati_io(w, b);
-  if (w.kind == MPC_KIND_FULL) riccati_instance_fast<56, 22, 78>(r, smem);
-  else if (w.kind == MPC_KIND_CENT) riccati_instance<9, 12, 34>(r, smem);
+  if (KIND == MPC_KIND_FULL) riccati_instance_fast<56, 22, 78>(r, smem);
+  else if (KIND == MPC_KIND_KINO) riccati_instance_fast<56, 34, 68, KINO_NCAP>(r, smem);
+  else riccati_instance<9, 12, 34>(r, smem);
+  ONE_THREAD { if (w.overflow[b]) { w.st[b].status = 3; w.st[b].mode = MODE_DONE; w.overflow[b] = 0; } }
+  SYNC();
   start_linesearch(w, b);
 }
 

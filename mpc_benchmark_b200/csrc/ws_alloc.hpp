@@ -34,14 +34,14 @@ template <class Alloc> size_t alloc_ws(Ws &w, Alloc &&alloc) {
   D(w.xdot, B * T1 * 56); D(w.lamc, B * T1 * 12);
   D(w.W, B * T * n * nz); D(w.pt, B * T * n); D(w.K, B * T * (m + nc) * (1 + n)); D(w.Kfb, B * T * m * n); D(w.dphi, B); D(w.phase, 32);
   w.st = (InstState *)alloc(B * sizeof(InstState)); total += B * sizeof(InstState);
-  I(w.counters, 4); I(w.lists, 4 * B);
+  I(w.counters, 4); I(w.lists, 4 * B); I(w.overflow, B);
   return total;
 }
 
 template <class Free> void free_ws(Ws &w, Free &&fr) {
   void *ptrs[] = {w.knots, w.terms, w.x0, w.xs, w.us, w.vs, w.lams, w.vs_prev, w.lams_prev, w.txs, w.tus, w.tvs, w.tlams, w.dxs, w.dus, w.dvs,
                   w.dlams, w.AB, w.H, w.lxu, w.g, w.T6, w.E6, w.gE, w.fbar, w.dbar, w.vplus, w.lplus, w.CDact, w.nca, w.act_idx, w.gap, w.h,
-                  w.scal, w.tscal, w.xdot, w.lamc, w.W, w.pt, w.K, w.Kfb, w.dphi, w.phase, w.st, w.counters, w.lists};
+                  w.scal, w.tscal, w.xdot, w.lamc, w.W, w.pt, w.K, w.Kfb, w.dphi, w.phase, w.st, w.counters, w.lists, w.overflow};
   for (void *p : ptrs) if (p) fr(p);
 }
 

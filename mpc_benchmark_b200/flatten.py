@@ -308,6 +308,117 @@ def _flatten_cent(problem, tol, mu_init, max_iters):
     return FlatProblem(rb, c, knots, terms, np.array(problem.x0_init, float).reshape(1, -1))
 
 
+# ---------------------------------------------------------------- kinodynamics
+def _flatten_kino_stage(stage, G):
+    dyn = stage.dynamics
+    if not isinstance(dyn, api.IntegratorSemiImplEuler):
+        raise NotImplementedError("kinodynamic stage must use IntegratorSemiImplEuler (kinodynamic_talos.py:111)")
+    ode = dyn.differential_dynamics
+    model = ode.model
+    if len(ode.contact_states) != 2 or ode.force_size != 6:
+        raise NotImplementedError("kinodynamic model: two 6-D contacts expected (kinodynamic_talos.py:41-43)")
+    if [_foot_index(model, frame_id=i) for i in ode.contact_ids] != [0, 1]:
+        raise NotImplementedError("contact_ids must be [left_sole_link, right_sole_link] (kinodynamic_talos.py:69)")
+    k = _abi.Knot()
+    cs = [bool(ode.contact_states[0]), bool(ode.contact_states[1])]
+    k.cs[0], k.cs[1] = float(cs[0]), float(cs[1])
+    nv, nu = model.nv, ode.nu
+    glob = dict(dt=dyn.timestep, gravity=ode.gravity)
+    for key, c, wgt in stage.cost.items():
+        if wgt != 1.0:
+            raise NotImplementedError("CostStack component weights other than 1 are not supported")
+        if isinstance(c, api.QuadraticStateCost):
+            glob["x_ref"], glob["wx"] = c.target, _diag(c.weights, 2 * nv, "QuadraticStateCost")
+        elif isinstance(c, api.QuadraticControlCost):
+            _set(k.u_ref, c.target)
+            glob["wu"] = _diag(c.weights, nu, "QuadraticControlCost")
+        elif isinstance(c, api.QuadraticResidualCost):
+            r = c.residual
+            if isinstance(r, api.CentroidalMomentumResidual):
+                if np.abs(r.ref).max() > 0:
+                    raise NotImplementedError("CentroidalMomentumResidual reference must be zero")
+                glob["w_cent"] = _diag(c.weights, 6, "centroidal momentum cost")
+            elif isinstance(r, api.CentroidalMomentumDerivativeResidual):
+                if [bool(x) for x in r.contact_states] != cs:
+                    raise NotImplementedError("CentroidalMomentumDerivativeResidual contact states differ from the dynamics")
+                glob["w_centder"] = _diag(c.weights, 6, "centroidal momentum derivative cost")
+            elif isinstance(r, api.FramePlacementResidual):
+                f = _foot_index(model, frame_id=r.frame_id)
+                _set(k.w_lf if f == 0 else k.w_rf, _diag(c.weights, 6, "frame placement cost"))
+                _set(k.lf_ref if f == 0 else k.rf_ref, r.ref.to12())
+            else:
+                raise NotImplementedError(f"unsupported residual in a kinodynamic cost: {type(r).__name__}")
+        else:
+            raise NotImplementedError(f"unsupported cost component {type(c).__name__}")
+    cones, vels = [False, False], [False, False]
+    for func, cset in zip(stage.constraints.funcs, stage.constraints.sets):
+        if isinstance(func, api.SlicedResidual) and isinstance(func.base, api.StateErrorResidual) and isinstance(cset, api.BoxConstraint):
+            if func.indices != list(range(6, nv)):
+                raise NotImplementedError("joint-limit constraint must be StateErrorResidual[6:nv] (kinodynamic_talos.py:161)")
+            glob["q_hi"], glob["q_lo"] = -cset.lower_limit, -cset.upper_limit
+        elif isinstance(func, api.CentroidalWrenchConeResidual) and isinstance(cset, api.NegativeOrthant):
+            cones[func.k] = True
+            glob["cone"] = np.array([func.mu, func.half_length, func.half_width])
+        elif isinstance(func, api.FrameVelocityResidual) and isinstance(cset, api.EqualityConstraintSet):
+            if func.ref_frame != _pin.LOCAL or np.abs(np.asarray(func.ref.np, float)).max() > 0:
+                raise NotImplementedError("frame-velocity constraint must be zero velocity in the LOCAL frame (kinodynamic_talos.py:129-130)")
+            vels[_foot_index(model, frame_id=func.frame_id)] = True
+        else:
+            raise NotImplementedError(f"unsupported stage constraint {type(func).__name__} / {type(cset).__name__}")
+    if cones != cs or vels != cs:
+        raise NotImplementedError("cone + zero-velocity constraints must be present exactly on the active contacts (kinodynamic_talos.py:164-171)")
+    for key, val in glob.items():
+        if key in G:
+            _same(G[key], val, key)
+        else:
+            G[key] = val
+    G.setdefault("model", model)
+    return k
+
+
+def _flatten_kino(problem, tol, mu_init, max_iters):
+    T = len(problem.stages)
+    G = {}
+    knots = (_abi.Knot * T)()
+    cache = {}
+    for j, st in enumerate(problem.stages):
+        if id(st) not in cache:
+            cache[id(st)] = _flatten_kino_stage(st, G)
+        knots[j] = cache[id(st)]
+    if problem.term_cost.size() != 0:
+        raise NotImplementedError("kinodynamic problem: empty terminal cost expected (kinodynamic_talos.py:175)")
+    model = G["model"]
+    t = _abi.Term()
+    ident = _pin.SE3().to12()
+    _set(t.lf_ref, ident)
+    _set(t.rf_ref, ident)
+    if len(problem.term_constraints) > 1:
+        raise NotImplementedError("at most one terminal constraint (CoM equality) is supported")
+    for func, cset in zip(problem.term_constraints.funcs, problem.term_constraints.sets):
+        if isinstance(func, api.CenterOfMassTranslationResidual) and isinstance(cset, api.EqualityConstraintSet):
+            _set(t.com_ref, func.ref)
+            t.has_com_cstr = 1.0
+        else:
+            raise NotImplementedError(f"unsupported terminal constraint {type(func).__name__}")
+    rb = _abi.Robot.from_buffer_copy(_robot_from_model(model))
+    _set(rb.gravity, G["gravity"])
+    if "q_lo" in G:
+        _set(rb.q_lo, G["q_lo"])
+        _set(rb.q_hi, G["q_hi"])
+    c = _abi.Config()
+    c.kind, c.T, c.dt = _abi.KIND_KINO, T, G["dt"]
+    _set(c.x_ref, G.get("x_ref", np.concatenate([_pin.neutral(model), np.zeros(model.nv)])))
+    _set(c.wx, G.get("wx", np.zeros(2 * model.nv)))
+    _set(c.wu, G.get("wu", np.zeros(34)))
+    _set(c.w_cent, G.get("w_cent", np.zeros(6)))
+    _set(c.w_centder, G.get("w_centder", np.zeros(6)))
+    cone = G.get("cone", np.array([0.8, 0.1, 0.075]))
+    c.mu_fric, c.foot_L, c.foot_W = cone
+    c.tol, c.mu_init, c.max_iters, c.force_initial_condition = tol, mu_init, max_iters, 1
+    terms = (_abi.Term * 1)(t)
+    return FlatProblem(rb, c, knots, terms, np.array(problem.x0_init, float).reshape(1, -1))
+
+
 def flatten_problem(problem, tol, mu_init, max_iters):
     if not problem.stages:
         raise ValueError("TrajOptProblem has no stages")
@@ -317,6 +428,5 @@ def flatten_problem(problem, tol, mu_init, max_iters):
     if isinstance(ode, api.MultibodyConstraintFwdDynamics):
         return _flatten_full(problem, tol, mu_init, max_iters)
     if isinstance(ode, api.KinodynamicsFwdDynamics):
-        raise NotImplementedError("kinodynamic model: the modelling classes exist, the CUDA stage kernel is scheduled for the next round "
-                                  "(DESIGN.md, scope table row D2)")
+        return _flatten_kino(problem, tol, mu_init, max_iters)
     raise NotImplementedError(f"unsupported dynamics {type(ode).__name__}")

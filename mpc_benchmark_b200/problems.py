@@ -268,3 +268,54 @@ def lq_flops(n, m, c):
         + (s ** 3 / 3 + 2 * s * s * (1 + n)) + (2 * n * n * s + 2 * n * s)
     fwd = 2 * s * n + 2 * n * n + 2 * n * m
     return back + fwd
+
+
+# ---------------------------------------------------------------- kinodynamics
+W_X_KINO = 10.0 * np.array(
+    [0, 0, 1000, 1000, 1000, 1000] + [0.1] * 6 + [0.1] * 6 + [1, 1000] + [1, 1, 10, 10] + [1, 1, 10, 10]
+    + [0.1, 0.1, 0.1, 1000, 1000, 1000] + [1] * 6 + [1] * 6 + [0.1, 100] + [10] * 4 + [10] * 4,
+    dtype=float,
+)  # kinodynamic_talos.py:74-88
+
+
+def kino_config(rb, x0, T=100, dt=0.01, tol=1e-5, mu_init=1e-8, max_iters=100):
+    c = _abi.Config()
+    c.kind, c.T, c.dt = _abi.KIND_KINO, T, dt
+    _set(c.x_ref, x0)
+    _set(c.wx, W_X_KINO)
+    _set(c.wu, [0.001, 0.001, 0.01, 0.1, 0.1, 0.1] * 2 + [1e-4] * 22)  # kino:89-98
+    _set(c.w_cent, [0, 0, 1, 0.1, 0.1, 10])  # kino:100-102
+    _set(c.w_centder, [0, 0, 0, 0.1, 0.1, 0.1])  # kino:103-105
+    c.mu_fric, c.foot_L, c.foot_W = 0.8, 0.1, 0.075  # kino:45,48-49
+    c.tol, c.mu_init, c.max_iters, c.force_initial_condition = tol, mu_init, max_iters, 1
+    return c
+
+
+def kino_knot(cs, lf_ref, rf_ref, u_ref, w_lfrf=1e5):
+    """createStage(contact_state, LF_pose, RF_pose, uforce) of kinodynamic_talos.py:117-173."""
+    k = _abi.Knot()
+    cl, cr = bool(cs[0]), bool(cs[1])
+    k.cs[0], k.cs[1] = float(cl), float(cr)
+    _set(k.w_rf, [w_lfrf if cl else 0.0] * 6)  # kino:145-148
+    _set(k.w_lf, [w_lfrf if cr else 0.0] * 6)
+    _set(k.lf_ref, lf_ref)
+    _set(k.rf_ref, rf_ref)
+    _set(k.u_ref, u_ref)
+    return k
+
+
+def kino_standing_problem(batch=1, T=100, robot=None, **kw):
+    """Cold-solve problem of kinodynamic_talos.py:269-304: all-double-support, terminal CoM equality on com0."""
+    rb, q0, x0, lf, rf, com0, mass = base_setup(robot)
+    cfg = kino_config(rb, x0, T=T, **kw)
+    f_half = mass * GRAVITY / 2.0
+    uref0 = np.zeros(34)
+    uref0[2] = uref0[8] = f_half  # urefs[0] (kino:205-212 with i = 0, j = 0)
+    knot = kino_knot([True, True], lf, rf, uref0)
+    knots = (_abi.Knot * (batch * T))(*([knot] * (batch * T)))
+    ident = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0.0])
+    terms = (_abi.Term * batch)(*([make_term(ident, ident, com0)] * batch))
+    u_init = np.zeros(34)
+    u_init[2] = u_init[8] = f_half  # u_ref = [f_ref, f_ref, 0] (kino:296-298)
+    return dict(robot=rb, cfg=cfg, knots=knots, terms=terms, x0=np.tile(x0, (batch, 1)), xs=np.tile(x0, (batch, T + 1, 1)),
+                us=np.tile(u_init, (batch, T, 1)), lf=lf, rf=rf, com0=com0, mass=mass)

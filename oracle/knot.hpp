@@ -373,6 +373,167 @@ inline void eval_knot_full(const Problem &P, const mpc_knot_t &kn, const double 
     }
 }
 
+// ============================================================ kinodynamics (kino:107-173)
+// u = [w_L(6), w_R(6), a_joint(22)], wrenches (f, tau) in world axes applied at the sole-frame origins.
+// hdot' = [sum f_i ; sum (p_i - c) x f_i + tau_i] over active contacts (gravity is folded into F_g, see rbd.hpp).
+template <class T> struct KinoVals {
+  V6<T> hd;        // hdot' (without the m g term)
+  T a[NV];         // generalized acceleration [a_base; a_joint]
+  V3<T> p[2];      // sole origins
+};
+template <class T> void solve6(const T *A, const T *b, T *x) { // Gaussian elimination with partial pivoting, 6 x 6
+  T M[6][7];
+  for (int i = 0; i < 6; i++) { for (int j = 0; j < 6; j++) M[i][j] = A[6 * i + j]; M[i][6] = b[i]; }
+  for (int c = 0; c < 6; c++) {
+    int pv = c;
+    for (int r = c + 1; r < 6; r++) if (std::fabs(val(M[r][c])) > std::fabs(val(M[pv][c]))) pv = r;
+    if (pv != c) for (int j = 0; j < 7; j++) std::swap(M[pv][j], M[c][j]);
+    for (int r = c + 1; r < 6; r++) { T f = M[r][c] / M[c][c]; for (int j = c; j < 7; j++) M[r][j] -= f * M[c][j]; }
+  }
+  for (int i = 5; i >= 0; i--) { T sacc = M[i][6]; for (int j = i + 1; j < 6; j++) sacc -= M[i][j] * x[j]; x[i] = sacc / M[i][i]; }
+}
+// centroidal momentum matrix A_g (6 x NV) from the composite inertias: column j = shift_to_com(Ic_J s_j)
+template <class T> void centroidal_map(const Kin<T> &k, T *Ag) {
+  for (int j = 0; j < NV; j++) {
+    V6<T> Is = mul(k.Ic[body_of_dof(j)], k.S[j]);
+    V3<T> l = lin(Is), aa = sub(ang(Is), cross(k.com, l));
+    for (int r = 0; r < 3; r++) { Ag[r * NV + j] = l[r]; Ag[(3 + r) * NV + j] = aa[r]; }
+  }
+}
+template <class T> void kino_dynamics(const Tree &tr, const mpc_robot_t &rb, const bool active[2], const Kin<T> &k, const T *v, const T *u, KinoVals<T> &o) {
+  V3<T> fl = {T(0), T(0), T(0)}, fa = {T(0), T(0), T(0)};
+  for (int i = 0; i < 2; i++) {
+    SE3<T> oMf = mul(k.oM[rb.foot_body[i]], se3_cast<T>(rb.foot_place[i]));
+    o.p[i] = oMf.p;
+    if (!active[i]) continue;
+    V3<T> f = {u[6 * i], u[6 * i + 1], u[6 * i + 2]}, t = {u[6 * i + 3], u[6 * i + 4], u[6 * i + 5]};
+    fl = add(fl, f);
+    fa = add(fa, add(cross(sub(oMf.p, k.com), f), t));
+  }
+  o.hd = mk6(fl, fa);
+  // F_g(q, v, [0; a_j]) with a_world = -g, then A_b a_b = hd - F_g0
+  T qdd[NV];
+  for (int i = 0; i < 6; i++) qdd[i] = T(0);
+  for (int i = 0; i < NJ; i++) qdd[6 + i] = u[12 + i];
+  V6<T> F0 = centroidal_rate<T>(tr, k, v, qdd);
+  T Ag[6 * NV], Ab[36], rhs[6], ab[6];
+  centroidal_map<T>(k, Ag);
+  for (int i = 0; i < 6; i++) { rhs[i] = o.hd[i] - F0[i]; for (int j = 0; j < 6; j++) Ab[6 * i + j] = Ag[i * NV + j]; }
+  solve6<T>(Ab, rhs, ab);
+  for (int i = 0; i < 6; i++) o.a[i] = ab[i];
+  for (int i = 0; i < NJ; i++) o.a[6 + i] = u[12 + i];
+}
+
+inline void eval_knot_kino(const Problem &P, const mpc_knot_t &kn, const double *x, const double *u, const double *xn, bool derivs, KnotEval &o) {
+  const mpc_config_t &c = P.cfg;
+  const mpc_robot_t &rb = *P.rb;
+  const int n = 56, m = 34, nz = 90;
+  const double *v = x + NQ;
+  bool active[2] = {kn.cs[0] != 0.0, kn.cs[1] != 0.0};
+  static thread_local Kin<double> kin;
+  forward_kin<double>(P.tree, x, v, kin);
+  KinoVals<double> kv;
+  kino_dynamics<double>(P.tree, rb, active, kin, v, u, kv);
+  for (int i = 0; i < NV; i++) { o.xdot[i] = v[i]; o.xdot[NV + i] = kv.a[i]; }
+  for (int i = 0; i < 12; i++) o.lam[i] = (active[i / 6]) ? u[i] : 0.0;
+  std::vector<double> ax(NV * n, 0.0), au(NV * m, 0.0), hdq(6 * NV, 0.0), hdu(6 * m, 0.0);
+  FootKin fk[2];
+  for (int f = 0; f < 2; f++) foot_kin(P.tree, kin, f, fk[f]);
+  double Jc[3 * NV];
+  com_jacobian(kin, Jc);
+  if (derivs) {
+    // d hdot'/dq (angular rows) and d hdot'/du
+    for (int i = 0; i < 2; i++) {
+      if (!active[i]) continue;
+      V3<double> f = {u[6 * i], u[6 * i + 1], u[6 * i + 2]};
+      M3<double> px = skew(sub(kv.p[i], kin.com));
+      for (int r = 0; r < 3; r++) {
+        hdu[r * m + 6 * i + r] = 1.0; hdu[(3 + r) * m + 6 * i + 3 + r] = 1.0;
+        for (int cc = 0; cc < 3; cc++) hdu[(3 + r) * m + 6 * i + cc] = px[3 * r + cc];
+      }
+      int fb = rb.foot_body[i];
+      for (int j = 0; j < NV; j++) {
+        V3<double> dp = {0, 0, 0};
+        if (P.tree.anc[body_of_dof(j)][fb]) dp = add(lin(kin.S[j]), cross(ang(kin.S[j]), kv.p[i]));
+        V3<double> dc = {Jc[j], Jc[NV + j], Jc[2 * NV + j]};
+        V3<double> d = cross(sub(dp, dc), f);
+        for (int r = 0; r < 3; r++) hdq[(3 + r) * NV + j] += d[r];
+      }
+    }
+    // d F_g / d(q, v) at fixed a
+    V6<double> a[NB], Fs[NB];
+    double tau[NV];
+    rnea<double>(P.tree, kin, v, kv.a, nullptr, tau, a, Fs);
+    double dFq[6 * NV], dFv[6 * NV], Ag[6 * NV], Ab[36];
+    total_force_derivatives(P.tree, kin, a, Fs, dFq, dFv);
+    centroidal_map<double>(kin, Ag);
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) Ab[6 * i + j] = Ag[i * NV + j];
+    V3<double> Fl = lin(Fs[0]);
+    for (int j = 0; j < n + m; j++) {
+      double rhs[6] = {0, 0, 0, 0, 0, 0}, sol[6];
+      if (j < NV) {
+        V3<double> dl = {dFq[j], dFq[NV + j], dFq[2 * NV + j]}, da = {dFq[3 * NV + j], dFq[4 * NV + j], dFq[5 * NV + j]};
+        V3<double> dc = {Jc[j], Jc[NV + j], Jc[2 * NV + j]};
+        V3<double> dag = sub(sub(da, cross(dc, Fl)), cross(kin.com, dl));
+        for (int r = 0; r < 3; r++) { rhs[r] = hdq[r * NV + j] - dl[r]; rhs[3 + r] = hdq[(3 + r) * NV + j] - dag[r]; }
+      } else if (j < n) {
+        int jj = j - NV;
+        V3<double> dl = {dFv[jj], dFv[NV + jj], dFv[2 * NV + jj]}, da = {dFv[3 * NV + jj], dFv[4 * NV + jj], dFv[5 * NV + jj]};
+        V3<double> dag = sub(da, cross(kin.com, dl));
+        for (int r = 0; r < 3; r++) { rhs[r] = -dl[r]; rhs[3 + r] = -dag[r]; }
+      } else {
+        int jj = j - n;
+        if (jj < 12) for (int r = 0; r < 6; r++) rhs[r] = hdu[r * m + jj];
+        else for (int r = 0; r < 6; r++) rhs[r] = -Ag[r * NV + 6 + (jj - 12)];
+      }
+      solve6<double>(Ab, rhs, sol);
+      for (int r = 0; r < 6; r++) { if (j < n) ax[r * n + j] = sol[r]; else au[r * m + (j - n)] = sol[r]; }
+    }
+    for (int i = 0; i < NJ; i++) au[(6 + i) * m + 12 + i] = 1.0;
+  }
+  semi_implicit_euler(c.dt, x, kv.a, ax.data(), au.data(), m, xn, derivs, o);
+  // ---- costs: state, control, centroidal momentum, its derivative, foot poses (kino:137-157)
+  std::vector<double> grad(nz, 0.0);
+  multibody_costs(P, kin, x, c.wx, c.w_cent, kn.w_lf, kn.w_rf, kn.lf_ref, kn.rf_ref, nz, o.cost, grad.data(), o.H.data());
+  for (int i = 0; i < m; i++) {
+    double e = u[i] - kn.u_ref[i];
+    o.cost += 0.5 * c.wu[i] * e * e; grad[n + i] += c.wu[i] * e; o.H[(n + i) * nz + n + i] += c.wu[i];
+  }
+  {
+    double r[6];
+    for (int i = 0; i < 3; i++) { r[i] = kv.hd[i] + kin.mass * rb.gravity[i]; r[3 + i] = kv.hd[3 + i]; }
+    std::vector<double> J(6 * nz, 0.0);
+    for (int i = 0; i < 6; i++) { for (int j = 0; j < NV; j++) J[i * nz + j] = hdq[i * NV + j]; for (int j = 0; j < m; j++) J[i * nz + n + j] = hdu[i * m + j]; }
+    add_residual_cost(r, c.w_centder, 6, J.data(), nz, o.cost, grad.data(), o.H.data());
+  }
+  for (int i = 0; i < n; i++) o.lx[i] = grad[i];
+  for (int i = 0; i < m; i++) o.lu[i] = grad[n + i];
+  // ---- constraints: joint box, then per contact cone(17) + zero LOCAL frame velocity(6) (kino:161-171)
+  for (int i = 0; i < NJ; i++) {
+    o.ctype[i] = SET_BOX; o.h[i] = -x[7 + i]; o.lo[i] = -rb.q_hi[i]; o.hi[i] = -rb.q_lo[i]; o.Cx[i * n + 6 + i] = -1.0;
+  }
+  for (int f = 0; f < 2; f++) {
+    int base = 22 + 23 * f, fb = rb.foot_body[f];
+    for (int r = 0; r < 23; r++) o.ctype[base + r] = active[f] ? (r < 17 ? SET_NEG : SET_EQ) : SET_NONE;
+    if (!active[f]) continue;
+    for (int r = 0; r < 17; r++) {
+      double sacc = 0;
+      for (int k2 = 0; k2 < 6; k2++) { sacc += P.Acone[6 * r + k2] * u[6 * f + k2]; o.Cu[(base + r) * m + 6 * f + k2] = P.Acone[6 * r + k2]; }
+      o.h[base + r] = sacc;
+    }
+    V6<double> vl = actinv_motion(fk[f].oMf, kin.v[fb]);
+    for (int r = 0; r < 6; r++) o.h[base + 17 + r] = vl[r];
+    if (derivs)
+      for (int j = 0; j < NV; j++) {
+        if (!P.tree.anc[body_of_dof(j)][fb]) continue;
+        int J = body_of_dof(j), pJ = rb.parent[J];
+        V6<double> vp = pJ >= 0 ? kin.v[pJ] : zero6<double>();
+        V6<double> wl = actinv_motion(fk[f].oMf, cross_mm(kin.S[j], vp));
+        for (int r = 0; r < 6; r++) { o.Cx[(base + 17 + r) * n + j] = -wl[r]; o.Cx[(base + 17 + r) * n + NV + j] = fk[f].J[r * NV + j]; }
+      }
+  }
+}
+
 // terminal cost + constraint. Outputs into o: cost, lx, H (n x n block used, stored with stride n+m), h[0:3], Cx rows 0..2
 inline void eval_term(const Problem &P, const mpc_term_t &tm, const double *x, KnotEval &o) {
   const mpc_config_t &c = P.cfg;
@@ -401,6 +562,7 @@ inline void eval_term(const Problem &P, const mpc_term_t &tm, const double *x, K
 inline void eval_knot(const Problem &P, const mpc_knot_t &kn, const double *x, const double *u, const double *xn, bool derivs, KnotEval &o) {
   o.zero();
   if (P.cfg.kind == MPC_KIND_CENT) eval_knot_cent(P, kn, x, u, xn, derivs, o);
+  else if (P.cfg.kind == MPC_KIND_KINO) eval_knot_kino(P, kn, x, u, xn, derivs, o);
   else eval_knot_full(P, kn, x, u, xn, derivs, o);
 }
 

@@ -410,4 +410,41 @@ inline void centroidal_derivatives(const Tree &tr, const Kin<double> &k, double 
   }
 }
 
+// ------------------------------------------------------------------ centroidal momentum RATE (kinodynamics, App. A5)
+// F_g(q, v, a) = A_g a + dA_g v + (gravity folded in as a_world = -g): total inertial force of the tree expressed at the
+// CoM, [linear; angular].  With a_world = -g this equals hdot_g - m g, so the kinodynamic base-acceleration equation reads
+// F_g(q,v,a) = [sum f_i ; sum (p_i - c) x f_i + tau_i].
+template <class T> V6<T> centroidal_rate(const Tree &tr, const Kin<T> &k, const T *v, const T *qdd) {
+  T tau[NV];
+  V6<T> F[NB];
+  rnea<T>(tr, k, v, qdd, nullptr, tau, nullptr, F);
+  V3<T> l = lin(F[0]);
+  return mk6(l, sub(ang(F[0]), cross(k.com, l)));
+}
+// d F_o / d q_j and d F_o / d v_j of the TOTAL force about the world origin (6 x NV each): the "top" vectors of id_derivatives
+inline void total_force_derivatives(const Tree &tr, const Kin<double> &k, const V6<double> *a /*with gravity*/, const V6<double> *Fsub,
+                                    double *dFq, double *dFv) {
+  const mpc_robot_t &rb = *tr.rb;
+  V6<double> a_world = zero6<double>();
+  a_world[0] = -rb.gravity[0]; a_world[1] = -rb.gravity[1]; a_world[2] = -rb.gravity[2];
+  for (int j = 0; j < NV; j++) {
+    int J = body_of_dof(j), pJ = rb.parent[J];
+    V6<double> s = k.S[j];
+    V6<double> vp = pJ >= 0 ? k.v[pJ] : zero6<double>();
+    V6<double> ap = pJ >= 0 ? a[pJ] : a_world;
+    V6<double> w = cross_mm(s, vp);
+    V6<double> cj = sub(cross_mm(s, ap), cross_mm(w, vp));
+    V6<double> eJ = add(k.v[J], vp);
+    V6<double> Gq = zero6<double>(), Gv = zero6<double>();
+    for (int b = 0; b < NB; b++) {
+      if (!tr.anc[J][b]) continue;
+      V6<double> Iv = mul(k.I[b], k.v[b]);
+      Gq = add(Gq, add(add(mul(k.I[b], add(cj, cross_mm(w, k.v[b]))), cross_mf(w, Iv)), cross_mf(k.v[b], mul(k.I[b], w))));
+      Gv = add(Gv, add(add(mul(k.I[b], cross_mm(s, sub(k.v[b], eJ))), cross_mf(s, Iv)), cross_mf(k.v[b], mul(k.I[b], s))));
+    }
+    V6<double> top = sub(cross_mf(s, Fsub[J]), Gq);
+    for (int r = 0; r < 6; r++) { dFq[r * NV + j] = top[r]; dFv[r * NV + j] = Gv[r]; }
+  }
+}
+
 } // namespace orc

@@ -17,10 +17,25 @@ struct EmuBackend {
   void reset_counters() { for (int i = 0; i < 4; i++) w.counters[i] = 0; }
   void eval(bool d, const int32_t *list, int n) {
     for (int i = 0; i < n; i++)
-      for (int k = 0; k <= w.T; k++) { if (d) eval_dispatch<true>(w, list[i], k, smem.data()); else eval_dispatch<false>(w, list[i], k, smem.data()); }
+      for (int k = 0; k <= w.T; k++) {
+        switch (w.kind * 2 + (d ? 1 : 0)) {
+        case MPC_KIND_FULL * 2 + 1: eval_dispatch<MPC_KIND_FULL, true>(w, list[i], k, smem.data()); break;
+        case MPC_KIND_FULL * 2 + 0: eval_dispatch<MPC_KIND_FULL, false>(w, list[i], k, smem.data()); break;
+        case MPC_KIND_KINO * 2 + 1: eval_dispatch<MPC_KIND_KINO, true>(w, list[i], k, smem.data()); break;
+        case MPC_KIND_KINO * 2 + 0: eval_dispatch<MPC_KIND_KINO, false>(w, list[i], k, smem.data()); break;
+        case MPC_KIND_CENT * 2 + 1: eval_dispatch<MPC_KIND_CENT, true>(w, list[i], k, smem.data()); break;
+        default: eval_dispatch<MPC_KIND_CENT, false>(w, list[i], k, smem.data()); break;
+        }
+      }
   }
   void decide_eval(const int32_t *list, int n, int32_t *next_eval) { double red[8]; for (int i = 0; i < n; i++) mpcdev::decide_eval(w, list[i], red, next_eval); }
-  void riccati(const int32_t *list, int n) { for (int i = 0; i < n; i++) riccati_dispatch(w, list[i], smem.data()); }
+  void riccati(const int32_t *list, int n) {
+    for (int i = 0; i < n; i++) {
+      if (w.kind == MPC_KIND_FULL) riccati_dispatch<MPC_KIND_FULL>(w, list[i], smem.data());
+      else if (w.kind == MPC_KIND_KINO) riccati_dispatch<MPC_KIND_KINO>(w, list[i], smem.data());
+      else riccati_dispatch<MPC_KIND_CENT>(w, list[i], smem.data());
+    }
+  }
   void apply_step(const int32_t *list, int n) { w.counters[0] = 0; for (int i = 0; i < n; i++) mpcdev::apply_step(w, list[i]); }
   void decide_ls(const int32_t *list, int n, int32_t *ls_out, int32_t *next_eval) {
     double red[8];
@@ -32,7 +47,7 @@ struct EmuBackend {
 extern "C" int emu_solve(const mpc_robot_t *rb, const mpc_config_t *cfg, int batch, const mpc_knot_t *knots, const mpc_term_t *terms,
                          const double *x0, double *xs, double *us, double *K, double *vs, double *lams, mpc_info_t *info, double *stage0,
                          int max_iters, double *lq_dump /* optional: AB,H,g of instance 0 after the first derivative pass */) {
-  static_assert(sizeof(FullWsT<true>) <= 40000 * 8, "smem");
+  static_assert(sizeof(FullWsT<true>) <= 40000 * 8 && sizeof(KinoWsT<true>) <= 40000 * 8, "smem");
   DevModel *model = new DevModel;
   const char *err = nullptr;
   if (build_dev_model(rb, cfg, model, &err)) return 1;

@@ -3,8 +3,8 @@
 
     python tests/golden/make_golden.py
 
-1. ref_flat_{full,cent}.npz — the flat descriptor obtained by executing the TOP HALF of the unmodified reference script
-   (/root/reference/{fulldynamic,centroidal}_talos.py up to the cold solve) through this package's aligator/pinocchio
+1. ref_flat_{full,kino,cent}.npz — the flat descriptor obtained by executing the TOP HALF of the unmodified reference script
+   (/root/reference/{fulldynamic,kinodynamic,centroidal}_talos.py up to the cold solve) through this package's aligator/pinocchio
    shim (tests/ref_harness.py), plus the cold-solve result of the CPU ORACLE on that descriptor.
 2. walk_full.npz — 4 instances of the synthetic random-schedule workload (bench.py) with 6 oracle iterations and one
    warm MPC tick (active cone / box constraints, non-zero multipliers).
@@ -41,11 +41,11 @@ def info_arrays(info):
 
 def main():
     if H.available():
-        for script, tag in [("fulldynamic_talos.py", "full"), ("centroidal_talos.py", "cent")]:
+        for script, tag in [("fulldynamic_talos.py", "full"), ("kinodynamic_talos.py", "kino"), ("centroidal_talos.py", "cent")]:
             ns, cap = H.run_top_half(script)
             flat, xs, us = cap[-1][1], cap[-1][2], cap[-1][3]
             prob = dict(robot=flat.robot, cfg=flat.cfg, knots=flat.knots, terms=flat.terms, x0=flat.x0, xs=xs[None], us=us[None])
-            r = O.solve(prob)
+            r = O.solve(prob, knot_threads=8)
             out = pack(prob)
             out.update({"sol_" + k: r[k] for k in ["xs", "us", "K", "vs", "lams", "stage0"]})
             out.update({"sol_" + k: v for k, v in info_arrays(r["info"]).items()})

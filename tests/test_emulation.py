@@ -14,7 +14,7 @@ def rel(a, b):
     return np.abs(a - b).max() / max(1e-12, np.abs(b).max())
 
 
-@pytest.mark.parametrize("maker", [problems.cent_standing_problem, problems.full_standing_problem])
+@pytest.mark.parametrize("maker", [problems.cent_standing_problem, problems.full_standing_problem, problems.kino_standing_problem])
 def test_lq_blocks(oracle, maker):
     prob = maker(T=6)
     cfg = prob["cfg"]
@@ -36,7 +36,7 @@ def test_lq_blocks(oracle, maker):
         assert abs(o["cost"] - e["scal"][k, 0]) <= 1e-11 * max(1, abs(o["cost"]))
 
 
-@pytest.mark.parametrize("maker,T", [(problems.cent_standing_problem, 100), (problems.full_standing_problem, 25)])
+@pytest.mark.parametrize("maker,T", [(problems.cent_standing_problem, 100), (problems.full_standing_problem, 25), (problems.kino_standing_problem, 25)])
 def test_cold_solve(oracle, maker, T):
     prob = maker(T=T)
     r = oracle.solve(prob)

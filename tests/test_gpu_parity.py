@@ -29,7 +29,7 @@ def perturbed(prob, oracle, seed, sx=0.02, su=1.0):
     return xs, us
 
 
-@pytest.mark.parametrize("maker", [problems.cent_standing_problem, problems.full_standing_problem])
+@pytest.mark.parametrize("maker", [problems.cent_standing_problem, problems.full_standing_problem, problems.kino_standing_problem])
 def test_lq_blocks_match_oracle(oracle, maker):
     prob = maker(batch=2, T=8)
     cfg = prob["cfg"]
@@ -54,7 +54,7 @@ def test_lq_blocks_match_oracle(oracle, maker):
 
 
 @pytest.mark.parametrize("maker,T,iters", [(problems.cent_standing_problem, 100, 100), (problems.full_standing_problem, 20, 100),
-                                           (problems.full_standing_problem, 100, 100)])
+                                           (problems.full_standing_problem, 100, 100), (problems.kino_standing_problem, 100, 100)])
 def test_cold_solve_matches_oracle(oracle, maker, T, iters):
     prob = maker(batch=2, T=T)
     s = BatchSolver(prob["robot"], prob["cfg"], 2)
@@ -102,7 +102,7 @@ def test_dmma_tile_gemm_matches_numpy():
         assert np.abs(Cm[:, : 8 * nt] - ref).max() < 1e-12 * K
 
 
-@pytest.mark.parametrize("name", ["ref_flat_full.npz", "ref_flat_cent.npz"])
+@pytest.mark.parametrize("name", ["ref_flat_full.npz", "ref_flat_kino.npz", "ref_flat_cent.npz"])
 def test_golden_reference_script_problems(name):
     """Descriptors flattened from the unmodified reference scripts (tests/golden/make_golden.py): cold solve on the GPU vs the
     committed oracle solution — same iteration count, trajectories within 1e-6 relative."""

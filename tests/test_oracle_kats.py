@@ -165,6 +165,41 @@ def test_centroidal_knot_jacobians_match_finite_differences(oracle):
         assert (o["ctype"][:17] == 1).all() and ((o["ctype"][17:] == 1).all() == bool(cs[1]))
 
 
+@pytest.mark.parametrize("cs", [(1, 1), (1, 0), (0, 1)])
+def test_kinodynamic_knot_jacobians(oracle, cs):
+    """Kinodynamic stage (kinodynamic_talos.py:107-173): dynamics Jacobians vs forward-mode AD of the templated value code,
+    constraint / cost Jacobians vs central differences."""
+    import ctypes as C
+
+    p = problems.kino_standing_problem(T=3)
+    rb, cfg = p["robot"], p["cfg"]
+    rng = np.random.default_rng(8)
+    kn = problems.kino_knot(list(cs), p["lf"], p["rf"], p["us"][0, 0])
+    x = oracle.integrate(p["x0"][0], rng.normal(size=56) * 0.1)
+    u = p["us"][0, 0] + rng.normal(size=34) * 5
+    oracle.lib().orc_check_kino.restype = C.c_double
+    err = oracle.lib().orc_check_kino(C.byref(rb), C.byref(cfg), C.byref(kn), oracle._p(np.ascontiguousarray(x)), oracle._p(np.ascontiguousarray(u)))
+    assert err < 1e-8
+    o = oracle.eval_knot(rb, cfg, kn, x, u, x)
+    eps = 1e-6
+    nC, ng = np.zeros((68, 90)), np.zeros(90)
+    for j in range(90):
+        def at(s):
+            if j < 56:
+                d = np.zeros(56); d[j] = s
+                return oracle.eval_knot(rb, cfg, kn, oracle.integrate(x, d), u, x, derivs=False)
+            uu = u.copy(); uu[j - 56] += s
+            return oracle.eval_knot(rb, cfg, kn, x, uu, x, derivs=False)
+        a, b = at(eps), at(-eps)
+        nC[:, j] = (a["h"] - b["h"]) / (2 * eps)
+        ng[j] = (a["cost"] - b["cost"]) / (2 * eps)
+    assert np.abs(np.hstack([o["Cx"], o["Cu"]]) - nC).max() < 1e-6
+    g = np.concatenate([o["lx"], o["lu"]])
+    assert np.abs(g - ng).max() < 1e-6 * max(1, np.abs(g).max())
+    n_active = sum(cs)
+    assert (o["ctype"] == 1).sum() == 17 * n_active and (o["ctype"] == 0).sum() == 6 * n_active and (o["ctype"] == 2).sum() == 22
+
+
 def test_cold_solves_converge(oracle):
     """centroidal cold solve converges to TOL = 1e-5 (centroidal_talos.py:265); so does the standing full model."""
     r = oracle.solve(problems.cent_standing_problem())
@@ -176,13 +211,18 @@ def test_cold_solves_converge(oracle):
     assert i.conv == 1 and i.num_iters <= 15 and max(i.prim_infeas, i.dual_infeas) <= 1e-5
     mg = pf["mass"] * 9.81
     assert abs(r["stage0"][0, 56 + 2] + r["stage0"][0, 56 + 8] - mg) < 1e-3 * mg  # contact forces carry the weight
+    pk = problems.kino_standing_problem()
+    r = oracle.solve(pk, knot_threads=4)
+    i = r["info"][0]
+    assert i.conv == 1 and i.num_iters <= 15 and max(i.prim_infeas, i.dual_infeas) <= 1e-5
+    assert abs(r["us"][0, 0, 2] + r["us"][0, 0, 8] - mg) < 1e-2 * mg  # kinodynamic wrenches carry the weight too
 
 
 def test_golden_fixtures_reproduce(oracle):
     """The committed golden vectors are what the oracle computes today (guards against silent oracle drift)."""
     import golden_util
 
-    for name in ["ref_flat_full.npz", "ref_flat_cent.npz"]:
+    for name in ["ref_flat_full.npz", "ref_flat_kino.npz", "ref_flat_cent.npz"]:
         prob, z = golden_util.load(name)
         r = oracle.solve(prob, knot_threads=4)
         assert [i.num_iters for i in r["info"]] == list(z["sol_num_iters"])

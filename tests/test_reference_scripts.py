@@ -17,6 +17,7 @@ def _doubles(x):
 
 @needs_ref
 @pytest.mark.parametrize("script,maker,golden", [("fulldynamic_talos.py", problems.full_standing_problem, "ref_flat_full.npz"),
+                                                 ("kinodynamic_talos.py", problems.kino_standing_problem, "ref_flat_kino.npz"),
                                                  ("centroidal_talos.py", problems.cent_standing_problem, "ref_flat_cent.npz")])
 def test_script_top_half_flattens_to_expected_descriptor(script, maker, golden):
     ns, cap = ref_harness.run_top_half(script)
@@ -28,13 +29,6 @@ def test_script_top_half_flattens_to_expected_descriptor(script, maker, golden):
     assert np.array_equal(flat.x0, ref["x0"]) and np.array_equal(xs, ref["xs"][0]) and np.array_equal(us, ref["us"][0])
     gp, z = golden_util.load(golden)
     assert bytes(flat.cfg) == bytes(gp["cfg"]) and bytes(flat.knots) == bytes(gp["knots"])  # committed fixture is current
-
-
-@needs_ref
-def test_kinodynamic_script_constructs_but_solver_is_scheduled_next():
-    """kinodynamic_talos.py builds its whole object graph on the shim; the CUDA stage kernel for it is not in this round."""
-    with pytest.raises(NotImplementedError, match="kinodynamic"):
-        ref_harness.run_top_half("kinodynamic_talos.py")
 
 
 def test_mutation_through_aliases_is_seen_by_flatten():
