@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--prep-iters", type=int, default=20, help="untimed cold-solve iterations that produce the warm start")
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances in the CPU-baseline sample (0 = auto, ~10-30 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--latency-ticks", type=int, default=200, help="warm single-instance MPC ticks for the p50 latency (0 = skip)")
     return ap.parse_args()
 
 
@@ -233,12 +234,48 @@ def main():
                          "note": "algorithmic = dense LQ model of SURVEY 8d; the kernel skips inactive constraint rows, so executed FLOPs are lower"},
             "clocks": sampler.summary(),
         }
+        if args.latency_ticks > 0:
+            line["latency"] = single_instance_latency(args, prob, local, not args.no_cpu_baseline and world == 1)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, prob, xs_np, us_np)
         print(json.dumps(line))
     solver.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def single_instance_latency(args, prob, device, with_cpu):
+    """Second half of the BASELINE metric: single-solve p50 latency (ms) of a warm MPC tick (batch 1, max_iters = 1, host buffers
+    in / results out through the C-ABI call, as fulldynamic_talos.py:538-541 times it).  Instance 0 of the bench batch."""
+    from mpc_benchmark_b200 import problems
+    from mpc_benchmark_b200.batch import BatchSolver
+
+    sub = problems.sub_problem(prob, 0, 1)
+    s = BatchSolver(sub["robot"], sub["cfg"], 1, device=device)
+    s.setup(sub["knots"], sub["terms"], sub["x0"])
+    warm = s.run(sub["xs"], sub["us"], max_iters=args.prep_iters, gains=False)
+    xs, us = warm.xs.copy(), warm.us.copy()
+    ts = []
+    for i in range(args.latency_ticks + 10):
+        s.setup(sub["knots"], sub["terms"], sub["x0"])  # the reference re-runs solver.setup inside its timed region
+        t0 = time.perf_counter()
+        s.run(xs, us, max_iters=1, gains=False)
+        ts.append(1e3 * (time.perf_counter() - t0))
+    ts = np.array(ts[10:])
+    out = {"p50_ms": float(np.percentile(ts, 50)), "p90_ms": float(np.percentile(ts, 90)), "ticks": int(len(ts)),
+           "what": "warm MPC tick, batch 1, host buffers in/out (mpc_run + mpc_get_results)"}
+    s.close()
+    if with_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib
+
+        cts = []
+        for i in range(6):
+            t0 = time.perf_counter()
+            oracle_lib.solve(sub, max_iters=1, knot_threads=8, xs=xs, us=us)
+            cts.append(1e3 * (time.perf_counter() - t0))
+        out["cpu_oracle_8_threads_p50_ms"] = float(np.percentile(cts[1:], 50))
+    return out
 
 
 def cpu_baseline(args, prob, xs, us):
