@@ -136,6 +136,12 @@ int32_t mpc_run(mpc_solver_t *h, const double *xs_init, const double *us_init, i
  * asynchronous on `stream` (a cudaStream_t); used when inputs live in HBM. */
 int32_t mpc_run_device(mpc_solver_t *h, uint64_t xs_dev, uint64_t us_dev, int32_t max_iters, uint64_t stream);
 
+/* One closed-loop MPC tick on the device (the loop body of fulldynamic_talos.py:496-497,532-540):
+ * append `last` ([batch], may be NULL) at the end of the horizon, shift the previous solution by one knot as warm start,
+ * x0 <- x_meas ([batch][nx] host) or the model prediction xs[1] when NULL (ideal plant), multipliers reset (setup per tick)
+ * or shifted (keep_multipliers, kinodynamic_talos.py:488), then max_iters ProxDDP iterations. */
+int32_t mpc_tick(mpc_solver_t *h, const mpc_knot_t *last, const double *x_meas, int32_t keep_multipliers, int32_t max_iters);
+
 /* solver.results: xs, us, controlFeedbacks() [batch][T][nu][ndx], vs, lams; any pointer may be NULL. */
 int32_t mpc_get_results(mpc_solver_t *h, double *xs, double *us, double *K, double *vs, double *lams,
                         mpc_info_t *info);

@@ -93,6 +93,14 @@ class BatchSolver:
         _native.check(_native.lib().mpc_run(self._h, _native.ptr(xs), _native.ptr(us), mi), "mpc_run")
         return self.results(gains=gains) if fetch else None
 
+    def tick(self, last_knots=None, x_meas=None, keep_multipliers=False, max_iters=1):
+        """One closed-loop MPC tick on the device: rotate the horizon, shift the warm start, new x0, solve."""
+        if last_knots is not None:
+            assert len(last_knots) == self.batch
+        xm = None if x_meas is None else np.ascontiguousarray(x_meas, dtype=np.float64).reshape(self.batch, self.nx)
+        _native.check(_native.lib().mpc_tick(self._h, C.cast(last_knots, C.c_void_p) if last_knots is not None else None, _native.ptr(xm),
+                                             int(bool(keep_multipliers)), int(max_iters)), "mpc_tick")
+
     # same with trajectories already in HBM (torch tensors or raw device pointers)
     def run_device(self, xs_ptr, us_ptr, max_iters=None, stream=0):
         mi = self.cfg.max_iters if max_iters is None else int(max_iters)

@@ -57,7 +57,7 @@ template <bool WITH_DERIV> struct FullWsT {
   static constexpr int CJ1 = WITH_DERIV ? 6 * FN : 8, CJ2 = WITH_DERIV ? 2 * 6 * NV : 8, M6 = WITH_DERIV ? 36 : 1, ZS = WITH_DERIV ? FNZ : 8;
   double x[NQ + NV], u[FM], xn[NQ + NV];
   double kn[sizeof(mpc_knot_t) / 8];
-  double oM[NB * 12], S[NV * 6], v[NB * 6], a[NB * 6], I[NB * 10], Ic[NB * 10];
+  double oM[NB * 12], S[NV * 6], v[NB * 6], a[NB * 6], I[NB * 10], Ic[NB * 10], sc[2 * NB];
   double hb[NB * 6], hsub[NB * 6], f[NB * 6], Fsub[NB * 6];
   union { // Bc is dead once the derivative columns are built; the cost Jacobians are built afterwards
     double Bc[BCS];
@@ -74,7 +74,10 @@ template <bool WITH_DERIV> struct FullWsT {
   double bvec[NV], acc[NV];
   double ofoot[24], Jf[2 * 6 * NV];
   double vc[12], gam[12], astar[12], c1Mc2[24], JlAd[2 * M6], lam[12], lgc[12];
-  double Y[NV * 13], G[144], rhs[12], dinvM[4 * 64], dinvG[2 * 64];
+  union { // the contact-solve scratch is dead once da/dlam are formed; the multipliers are staged into it afterwards
+    struct { double Y[NV * 13], G[144], rhs[12], dinvM[4 * 64], dinvG[2 * 64]; };
+    struct { double mv[FNC], mvp[FNC], mln[FN], mlnp[FN], mlk[FN]; }; // v, v_prev, lam_{k+1}, its estimate, lam_k
+  };
   double X[XS];
   double DL[DLS];
   double top[TOPS];
@@ -92,6 +95,8 @@ using FullWs = FullWsT<true>;
 template <class WS> HD void mb_kinematics(const DevModel &m, WS &w) {
   const mpc_robot_t &rb = m.rb;
   const double *q = w.x, *qd = w.x + NQ;
+  PAR_FOR(b, NB) { double sn = 0, cs = 1; if (b > 0) sincos(q[6 + b], &sn, &cs); w.sc[2 * b] = sn; w.sc[2 * b + 1] = cs; } // off the level chain
+  SYNC();
   for (int l = 0; l < m.nlevels; l++) {
     int n = m.level_start[l + 1] - m.level_start[l];
     PAR_FOR(t, n) {
@@ -99,9 +104,12 @@ template <class WS> HD void mb_kinematics(const DevModel &m, WS &w) {
       double *o = w.oM + 12 * b;
       if (b == 0) { quat_to_R(q + 3, o); o[9] = q[0]; o[10] = q[1]; o[11] = q[2]; }
       else {
-        double ax[3] = {rb.axis[b][0] * q[6 + b], rb.axis[b][1] * q[6 + b], rb.axis[b][2] * q[6 + b]};
-        double jr[12], t1[12];
-        exp3(ax, jr); jr[9] = jr[10] = jr[11] = 0;
+        // Rodrigues with the unit joint axis: R = I + sin(q) [a]x + (1 - cos q) [a]x^2
+        double jr[12], t1[12], K[9], K2[9];
+        skew3(rb.axis[b], K); mat3_mul(K, K, K2);
+        const double sn = w.sc[2 * b], omc = 1.0 - w.sc[2 * b + 1];
+        for (int i = 0; i < 9; i++) jr[i] = ((i % 4 == 0) ? 1.0 : 0.0) + sn * K[i] + omc * K2[i];
+        jr[9] = jr[10] = jr[11] = 0;
         se3_mul(rb.jplace[b], jr, t1);
         se3_mul(w.oM + 12 * rb.parent[b], t1, o);
       }
@@ -549,6 +557,9 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
   EPH(9);
   // ---- semi-implicit Euler + gap (App. A2)
   PAR_FOR(i, NV) { double dv = dt * w.acc[i]; w.dx[NV + i] = dv; w.dx[i] = dt * (w.x[NQ + i] + dv); }
+  // stage the multipliers (their global-load latency hides behind the cost-term phase)
+  PAR_FOR(i, FNC) { w.mv[i] = io.v[i]; w.mvp[i] = io.v_prev[i]; }
+  PAR_FOR(i, FN) { w.mln[i] = io.lam_n[i]; w.mlnp[i] = io.lam_n_prev[i]; w.mlk[i] = io.lam_k[i]; }
   SYNC();
   mb_cost_terms(m, w, kn.lf_ref, kn.rf_ref, DERIV, io.gap);
 
@@ -563,31 +574,31 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
       if (w.sidx[f] >= 0) { type = 1; for (int k = 0; k < 6; k++) hv += m.Acone[6 * rr + k] * w.lam[6 * f + k]; }
     }
     int act = 0; double prim = 0;
-    double vp = vplus_row(type, hv, io.v_prev[r], io.mu, lo, hi, act, prim);
+    double vp = vplus_row(type, hv, w.mvp[r], io.mu, lo, hi, act, prim);
     w.ctype[r] = type; w.late.hval[r] = hv; w.late.vpl[r] = vp; w.isact[r] = act;
-    w.late.dbr[r] = io.mu * (vp - io.v[r]);
+    w.late.dbr[r] = io.mu * (vp - w.mv[r]);
     w.late.rowtmp[r] = fabs(prim);
     io.h[r] = hv;
   }
   PAR_FOR(i, FN) {
-    double lp = io.lam_n_prev[i] + w.fbr[i] / io.mu; // fbr = gap here
+    double lp = w.mlnp[i] + w.fbr[i] / io.mu; // fbr = gap here
     w.lpl[i] = lp;
     w.dx[i] = w.fbr[i];                              // keep the gap in dx for the reductions below
   }
   SYNC();
-  PAR_FOR(i, FN) w.fbr[i] = io.mu * (w.lpl[i] - io.lam_n[i]);
+  PAR_FOR(i, FN) w.fbr[i] = io.mu * (w.lpl[i] - w.mln[i]);
   // partial sums over 8 strided chunks (rows, then dynamics coordinates, then cost terms), combined by one thread
   PAR_FOR(c, 8) {
     double pen = 0, prim = 0, inner = 0, cost = 0;
     for (int r = c; r < FNC; r += 8) {
       if (w.ctype[r] < 0) continue;
-      double dv = w.late.vpl[r] - io.v[r];
+      double dv = w.late.vpl[r] - w.mv[r];
       pen += 0.5 * io.mu * (w.late.vpl[r] * w.late.vpl[r] + dv * dv);
       prim = fmax(prim, w.late.rowtmp[r]);
       inner = fmax(inner, fabs(w.late.dbr[r]));
     }
     for (int i = c; i < FN; i += 8) {
-      double dl = w.lpl[i] - io.lam_n[i];
+      double dl = w.lpl[i] - w.mln[i];
       pen += 0.5 * io.mu * (w.lpl[i] * w.lpl[i] + dl * dl);
       prim = fmax(prim, fabs(w.dx[i]));
       inner = fmax(inner, fabs(io.mu * dl));
@@ -629,15 +640,15 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
     for (int i = 0; i < 6; i++) {
       double s = (z < 6) ? w.late.P2[6 * i + z] : 0.0;
       for (int k = 0; k < 6; k++) s += w.late.P1[6 * i + k] * d6[k];
-      io.AB[i * FNZ + z] = s; acc += s * io.lam_n[i];
+      io.AB[i * FNZ + z] = s; acc += s * w.mln[i];
     }
     for (int i = 6; i < NV; i++) {
       double s = dt2 * w.X[i * FNZ + z] + ((z == NV + i) ? dt : 0.0) + ((z == i) ? 1.0 : 0.0);
-      io.AB[i * FNZ + z] = s; acc += s * io.lam_n[i];
+      io.AB[i * FNZ + z] = s; acc += s * w.mln[i];
     }
     for (int i = 0; i < NV; i++) {
       double s = dt * w.X[i * FNZ + z] + ((z == NV + i) ? 1.0 : 0.0);
-      io.AB[(NV + i) * FNZ + z] = s; acc += s * io.lam_n[NV + i];
+      io.AB[(NV + i) * FNZ + z] = s; acc += s * w.mln[NV + i];
     }
     // cost gradient
     double lz = mb_cost_grad(w, cfg.wx, cfg.w_cent, kn.w_lf, kn.w_rf, z);
@@ -651,7 +662,7 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
     // Lagrangian gradient: + C^T v  (+ E_{k-1}^T lam_k: vector part here, base block added by the reduction kernel)
     double gz = lz + acc;
     for (int r = 0; r < FNC; r++) {
-      double vr = io.v[r];
+      double vr = w.mv[r];
       if (vr == 0.0 || w.ctype[r] < 0) continue;
       double c;
       if (r < 22) c = (z == FN + r) ? 1.0 : 0.0;
@@ -659,12 +670,12 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
       else { int f = (r - 44) / 17, rr = (r - 44) % 17; const double *Dl = w.DL + 6 * w.sidx[f] * FNZ; c = 0; for (int k = 0; k < 6; k++) c += m.Acone[6 * rr + k] * Dl[k * FNZ + z]; }
       gz += c * vr;
     }
-    if (z < FN) { if (io.k == 0) gz += io.lam_k[z]; else if (z >= 6) gz -= io.lam_k[z]; }
+    if (z < FN) { if (io.k == 0) gz += w.mlk[z]; else if (z >= 6) gz -= w.mlk[z]; }
     w.late.g[z] = gz; io.g[z] = gz;
   }
   PAR_FOR(j, 6) { // E_k^T lam_{k+1}, base block, for the next knot's gradient
     double s = 0;
-    for (int i = 0; i < 6; i++) s += w.late.E6[6 * i + j] * io.lam_n[i];
+    for (int i = 0; i < 6; i++) s += w.late.E6[6 * i + j] * w.mln[i];
     io.gE_next[j] = s;
   }
   EPH(12);

@@ -30,7 +30,10 @@ static int fail(const std::string &m) { g_err = m; return 1; }
 // ------------------------------------------------------------------ kernels
 __global__ void k_init(Ws w, const double *xs_in, const double *us_in, int max_iters) { init_instance(w, blockIdx.x, xs_in, us_in, max_iters); }
 
-template <int KIND, bool DERIV> __global__ void __launch_bounds__(128, DERIV ? 3 : 4) k_eval(Ws w, const int32_t *list) {
+#ifndef MPC_VALUES_CTAS
+#define MPC_VALUES_CTAS 4
+#endif
+template <int KIND, bool DERIV> __global__ void __launch_bounds__(128, DERIV ? 3 : MPC_VALUES_CTAS) k_eval(Ws w, const int32_t *list) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int T1 = w.T + 1;
   const int b = list[blockIdx.x / T1], k = blockIdx.x % T1;
@@ -87,7 +90,8 @@ struct mpc_solver {
   DevModel *d_model = nullptr;
   DevModel h_model;
   std::vector<void *> allocs;
-  double *d_xs_in = nullptr, *d_us_in = nullptr;
+  double *d_xs_in = nullptr, *d_us_in = nullptr, *d_meas = nullptr;
+  mpc_knot_t *d_last = nullptr;
   int32_t *h_counters = nullptr; // pinned
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -202,6 +206,8 @@ void mpc_destroy(mpc_solver_t *h) {
   for (cudaEvent_t e : h->evpool) cudaEventDestroy(e);
   if (h->d_xs_in) cudaFree(h->d_xs_in);
   if (h->d_us_in) cudaFree(h->d_us_in);
+  if (h->d_meas) cudaFree(h->d_meas);
+  if (h->d_last) cudaFree(h->d_last);
   if (h->d_model) cudaFree(h->d_model);
   if (h->h_counters) cudaFreeHost(h->h_counters);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -340,6 +346,47 @@ static int run_impl(mpc_solver *h, const double *d_xs, const double *d_us, int m
     }
   }
   return 0;
+}
+
+static int run_impl(mpc_solver *h, const double *d_xs, const double *d_us, int max_iters, cudaStream_t s, bool sync_events);
+// closed-loop warm start (fulldynamic_talos.py:532-536): xs <- xs[1:] + [xs[-1]], us <- us[1:] + [us[-1]], x0 <- measured state
+// (x_meas, or the model prediction xs[1] when x_meas == nullptr: ideal plant)
+__global__ void k_shift_warmstart(Ws w, double *xs_in, double *us_in, const double *x_meas) {
+  const size_t b = blockIdx.x, T1 = (size_t)w.T + 1, T = w.T;
+  const double *X = w.xs + b * T1 * w.nx, *U = w.us + b * T * w.m;
+  double *Xo = xs_in + b * T1 * w.nx, *Uo = us_in + b * T * w.m;
+  for (size_t i = threadIdx.x; i < T1 * w.nx; i += blockDim.x) { size_t k = i / w.nx, c = i % w.nx; Xo[i] = X[(k < T ? k + 1 : T) * w.nx + c]; }
+  for (size_t i = threadIdx.x; i < T * w.m; i += blockDim.x) { size_t k = i / w.m, c = i % w.m; Uo[i] = U[(k + 1 < T ? k + 1 : T - 1) * w.m + c]; }
+  for (int i = threadIdx.x; i < w.nx; i += blockDim.x) w.x0[b * w.nx + i] = x_meas ? x_meas[b * w.nx + i] : X[w.nx + i];
+}
+
+// One closed-loop MPC tick entirely on the device (fulldynamic_talos.py:496-497,532-540):
+// rotate the horizon (append `last`), shift the warm start, take x0 from x_meas (host [batch][nx]) or from the model
+// prediction, reset (setup-per-tick, full/cent) or shift (cycleProblem, kino) the multipliers, run max_iters iterations.
+int32_t mpc_tick(mpc_solver_t *h, const mpc_knot_t *last, const double *x_meas, int32_t keep_multipliers, int32_t max_iters) {
+  CK(cudaSetDevice(h->device));
+  if (!h->setup_done) return fail("mpc_tick before mpc_setup");
+  Ws &w = h->w;
+  const size_t T1 = w.T + 1;
+  if (last) {
+    if (!h->d_last) CK(cudaMalloc(&h->d_last, sizeof(mpc_knot_t) * w.B));
+    CK(cudaMemcpyAsync(h->d_last, last, sizeof(mpc_knot_t) * w.B, cudaMemcpyHostToDevice, h->stream));
+    k_cycle<<<w.B, 96, 0, h->stream>>>(w, h->d_last);
+  }
+  double *d_meas = nullptr;
+  if (x_meas) {
+    if (!h->d_meas) CK(cudaMalloc(&h->d_meas, (size_t)w.B * w.nx * 8));
+    CK(cudaMemcpyAsync(h->d_meas, x_meas, (size_t)w.B * w.nx * 8, cudaMemcpyHostToDevice, h->stream));
+    d_meas = h->d_meas;
+  }
+  k_shift_warmstart<<<w.B, 128, 0, h->stream>>>(w, h->d_xs_in, h->d_us_in, d_meas);
+  if (keep_multipliers) k_shift_multipliers<<<w.B, 128, 0, h->stream>>>(w, 1);
+  else {
+    CK(cudaMemsetAsync(w.vs, 0, w.B * T1 * w.nc * 8, h->stream));
+    CK(cudaMemsetAsync(w.lams, 0, w.B * T1 * w.n * 8, h->stream));
+  }
+  CK(cudaGetLastError());
+  return run_impl(h, h->d_xs_in, h->d_us_in, max_iters, h->stream, true);
 }
 
 int32_t mpc_run(mpc_solver_t *h, const double *xs_init, const double *us_init, int32_t max_iters) {

@@ -327,6 +327,7 @@ struct Solver {
       }
       solve_lq();
       double dphi0 = directional_derivative();
+      if (getenv("ORC_CHECK_DPHI")) { double c_; for (double eps : {1e-4, 1e-6, 1e-8}) { double pe = try_step(in, eps, &c_); fprintf(stderr, "   dphi0 %.6e  fd(eps=%.0e) %.6e\n", dphi0, eps, (pe - merit) / eps); } }
       double phi_new, cost_new;
       double alpha = linesearch(in, merit, dphi0, phi_new, cost_new);
       alphas.push_back(alpha); alpha_last = alpha;

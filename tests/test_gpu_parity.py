@@ -201,3 +201,38 @@ def test_shim_end_to_end_centroidal(oracle):
     solver.setup(problem)
     solver.run(problem, xs, us)
     assert solver.results.num_iters <= 1 and np.isfinite(np.array(solver.results.xs.tolist())).all()
+
+
+def test_closed_loop_ticks_match_host_driven_oracle(oracle):
+    """Device-side closed-loop tick (mpc_tick: horizon rotation, warm-start shift, x0 from the model prediction) against the
+    same loop driven on the host with the oracle (fulldynamic_talos.py:496-497,532-540)."""
+    from mpc_benchmark_b200.closed_loop import ClosedLoop
+
+    B, T = 3, 30
+    prob = problems.full_walk_batch(B, seed=3, T=T)
+    # stage stream: after the window, keep appending double-support standing knots
+    stand = problems.full_standing_problem(batch=1, T=1)["knots"][0]
+    nxt = (_abi.Knot * B)(*[stand] * B)
+    s = BatchSolver(prob["robot"], prob["cfg"], B)
+    s.setup(prob["knots"], prob["terms"], prob["x0"])
+    cold = s.run(prob["xs"], prob["us"], max_iters=8)
+    ref = oracle.solve(prob, max_iters=8, inst_threads=3)
+    assert rel(cold.xs, ref["xs"]) < RTOL
+    loop = ClosedLoop(s, lambda t: nxt)
+    xs, us = ref["xs"], ref["us"]
+    hp = dict(prob)
+    knots = list(prob["knots"])
+    for tick in range(3):
+        loop.step(max_iters=1)
+        # host-driven reference: rotate knots, shift warm start, x0 <- previous xs[1]
+        for b in range(B):
+            knots[b * T:(b + 1) * T] = knots[b * T + 1:(b + 1) * T] + [stand]
+        hp["knots"] = (_abi.Knot * (B * T))(*knots)
+        hp["x0"] = xs[:, 1].copy()
+        xs_ws = np.concatenate([xs[:, 1:], xs[:, -1:]], axis=1)
+        us_ws = np.concatenate([us[:, 1:], us[:, -1:]], axis=1)
+        r = oracle.solve(hp, max_iters=1, inst_threads=3, xs=xs_ws, us=us_ws)
+        xs, us = r["xs"], r["us"]
+        got = s.results(gains=False, multipliers=False)
+        assert rel(got.xs, xs) < RTOL and rel(got.us, us) < RTOL, tick
+    s.close()
