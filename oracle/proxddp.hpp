@@ -14,6 +14,7 @@
 #include <limits>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 
 namespace orc {
 
@@ -308,8 +309,11 @@ struct Solver {
     num_iters = 0; al_iters = 0; conv = 0; status = 1; ls_evals = 0; alpha_last = 0;
     alphas.clear();
     while (num_iters < max_iters && al_iters < prm.max_al_iters) {
+      auto t0_ = std::chrono::steady_clock::now();
       evaluate(in, xs.data(), us.data(), true, ev);
+      auto t1_ = std::chrono::steady_clock::now();
       assemble();
+      auto t2_ = std::chrono::steady_clock::now();
       merit = merit_value(ev, vs.data(), lams.data(), &traj_cost);
       if (!std::isfinite(merit)) { status = 2; break; }
       if (inner_crit <= inner_tol) { // inner problem solved: BCL outer update
@@ -326,11 +330,14 @@ struct Solver {
         continue;
       }
       solve_lq();
+      auto t3_ = std::chrono::steady_clock::now();
       double dphi0 = directional_derivative();
       if (getenv("ORC_CHECK_DPHI")) { double c_; for (double eps : {1e-4, 1e-6, 1e-8}) { double pe = try_step(in, eps, &c_); fprintf(stderr, "   dphi0 %.6e  fd(eps=%.0e) %.6e\n", dphi0, eps, (pe - merit) / eps); } }
       double phi_new, cost_new;
       double alpha = linesearch(in, merit, dphi0, phi_new, cost_new);
       alphas.push_back(alpha); alpha_last = alpha;
+      if (getenv("ORC_TIMING")) { auto t4_ = std::chrono::steady_clock::now(); auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "eval %.1f ms  assemble %.1f ms  lq %.1f ms  dphi+linesearch %.1f ms\n", ms(t0_, t1_), ms(t1_, t2_), ms(t2_, t3_), ms(t3_, t4_)); }
       if (getenv("ORC_VERBOSE")) fprintf(stderr, "it %3d prim %.3e dual %.3e inner %.3e merit %.10e dphi0 %.3e alpha %.3e ls %d preg %.1e mu %.1e al %d\n", num_iters, prim_infeas, dual_infeas, inner_crit, merit, dphi0, alpha, ls_evals, preg, mu, al_iters);
       if (!std::isfinite(phi_new)) { status = 2; break; }
       xs.swap(txs); us.swap(tus); vs.swap(tvs); lams.swap(tlams);

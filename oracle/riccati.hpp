@@ -31,10 +31,12 @@ inline void ldlt(double *K, int s) {
 }
 inline void ldlt_solve(const double *K, int s, double *b, int nrhs) { // b: s x nrhs row-major
   for (int i = 0; i < s; i++)
-    for (int k = 0; k < i; k++) { double l = K[i * s + k]; if (l != 0.0) for (int c = 0; c < nrhs; c++) b[i * nrhs + c] -= l * b[k * nrhs + c]; }
+    for (int k = 0; k < i; k++) { double l = K[i * s + k]; if (l != 0.0) { double *bi = b + i * nrhs; const double *bk = b + k * nrhs;
+_Pragma("GCC ivdep") for (int c = 0; c < nrhs; c++) bi[c] -= l * bk[c]; } }
   for (int i = 0; i < s; i++) { double d = 1.0 / K[i * s + i]; for (int c = 0; c < nrhs; c++) b[i * nrhs + c] *= d; }
   for (int i = s - 1; i >= 0; i--)
-    for (int k = i + 1; k < s; k++) { double l = K[k * s + i]; if (l != 0.0) for (int c = 0; c < nrhs; c++) b[i * nrhs + c] -= l * b[k * nrhs + c]; }
+    for (int k = i + 1; k < s; k++) { double l = K[k * s + i]; if (l != 0.0) { double *bi = b + i * nrhs; const double *bk = b + k * nrhs;
+_Pragma("GCC ivdep") for (int c = 0; c < nrhs; c++) bi[c] -= l * bk[c]; } }
 }
 inline void chol_d(double *A, int n) {
   for (int j = 0; j < n; j++) {
@@ -51,23 +53,27 @@ inline void chol_d(double *A, int n) {
 }
 inline void chol_solve_d(const double *L, int n, double *b, int nrhs) { // b: n x nrhs row-major
   for (int i = 0; i < n; i++) {
-    for (int k = 0; k < i; k++) { double l = L[i * n + k]; for (int c = 0; c < nrhs; c++) b[i * nrhs + c] -= l * b[k * nrhs + c]; }
+    for (int k = 0; k < i; k++) { double l = L[i * n + k]; double *bi = b + i * nrhs; const double *bk = b + k * nrhs;
+_Pragma("GCC ivdep") for (int c = 0; c < nrhs; c++) bi[c] -= l * bk[c]; }
     double d = 1.0 / L[i * n + i]; for (int c = 0; c < nrhs; c++) b[i * nrhs + c] *= d;
   }
   for (int i = n - 1; i >= 0; i--) {
-    for (int k = i + 1; k < n; k++) { double l = L[k * n + i]; for (int c = 0; c < nrhs; c++) b[i * nrhs + c] -= l * b[k * nrhs + c]; }
+    for (int k = i + 1; k < n; k++) { double l = L[k * n + i]; double *bi = b + i * nrhs; const double *bk = b + k * nrhs;
+_Pragma("GCC ivdep") for (int c = 0; c < nrhs; c++) bi[c] -= l * bk[c]; }
     double d = 1.0 / L[i * n + i]; for (int c = 0; c < nrhs; c++) b[i * nrhs + c] *= d;
   }
 }
 // C (m x n) += A^T (k x m)^T * B (k x n)
-inline void gemm_tn(int m, int n, int k, const double *A, const double *B, double *C) {
+inline void gemm_tn(int m, int n, int k, const double *__restrict A, const double *__restrict B, double *__restrict C) {
   for (int p = 0; p < k; p++)
-    for (int i = 0; i < m; i++) { double a = A[p * m + i]; if (a == 0.0) continue; for (int j = 0; j < n; j++) C[i * n + j] += a * B[p * n + j]; }
+    for (int i = 0; i < m; i++) { double a = A[p * m + i]; if (a == 0.0) continue; double *ci = C + i * n; const double *bp = B + p * n;
+_Pragma("GCC ivdep") for (int j = 0; j < n; j++) ci[j] += a * bp[j]; }
 }
 // C (m x n) += A (m x k) * B (k x n)
-inline void gemm_nn(int m, int n, int k, const double *A, const double *B, double *C) {
+inline void gemm_nn(int m, int n, int k, const double *__restrict A, const double *__restrict B, double *__restrict C) {
   for (int i = 0; i < m; i++)
-    for (int p = 0; p < k; p++) { double a = A[i * k + p]; if (a == 0.0) continue; for (int j = 0; j < n; j++) C[i * n + j] += a * B[p * n + j]; }
+    for (int p = 0; p < k; p++) { double a = A[i * k + p]; if (a == 0.0) continue; double *ci = C + i * n; const double *bp = B + p * n;
+_Pragma("GCC ivdep") for (int j = 0; j < n; j++) ci[j] += a * bp[j]; }
 }
 inline void inv6(const double *A, double *Ai) { // Gauss-Jordan with partial pivoting
   double M[6][12];
@@ -108,7 +114,7 @@ inline void riccati_solve(int n, int m, int nc, int T, const LQKnot *kn, const d
   const int nz = n + m, s = m + nc, nr = 1 + n;
   sol.n = n; sol.m = m; sol.nc = nc; sol.T = T; sol.nct = nct;
   sol.K.assign((size_t)T * s * nr, 0.0); sol.W.assign((size_t)T * n * nz, 0.0); sol.pt.assign((size_t)T * n, 0.0); sol.T6.assign((size_t)T * 36, 0.0);
-  std::vector<double> P(n * n), p(n), Pt(n * n), G(n * n), W(n * nz), AB(n * nz), Hh(nz * nz), gh(nz), KK(s * s), rhs(s * nr), tmp(n), ptil(n);
+  std::vector<double> P(n * n), p(n), Pt(n * n), G(n * n), W(n * nz), AB(n * nz), Hh(nz * nz), gh(nz), KK(s * s), rhs(s * nr), tmp(n), ptil(n), Wk_scratch;
   // terminal value function
   for (int i = 0; i < n; i++) { p[i] = gT[i]; for (int j = 0; j < n; j++) P[i * n + j] = HT[i * ldh + j]; }
   for (int r = 0; r < nct; r++)
@@ -144,14 +150,30 @@ inline void riccati_solve(int n, int m, int nc, int T, const LQKnot *kn, const d
     for (int i = 0; i < nz; i++) { double t = q.g[i]; for (int l = 0; l < n; l++) t += AB[l * nz + i] * ptil[l]; gh[i] = t; }
     std::memcpy(&sol.W[(size_t)k * n * nz], W.data(), sizeof(double) * n * nz);
     std::memcpy(&sol.pt[(size_t)k * n], ptil.data(), sizeof(double) * n);
-    // 4. KKT [Rh D'; D -mu I] X = -[rh Sh'; d C]
-    std::fill(KK.begin(), KK.end(), 0.0);
-    for (int i = 0; i < m; i++) for (int j = 0; j < m; j++) KK[i * s + j] = 0.5 * (Hh[(n + i) * nz + n + j] + Hh[(n + j) * nz + n + i]);
-    for (int r = 0; r < nc; r++) { for (int j = 0; j < m; j++) { KK[(m + r) * s + j] = q.D[r * m + j]; KK[j * s + m + r] = q.D[r * m + j]; } KK[(m + r) * s + m + r] = -mu; }
-    for (int i = 0; i < m; i++) { rhs[i * nr] = -gh[n + i]; for (int j = 0; j < n; j++) rhs[i * nr + 1 + j] = -Hh[j * nz + n + i]; }
-    for (int r = 0; r < nc; r++) { rhs[(m + r) * nr] = -q.d[r]; for (int j = 0; j < n; j++) rhs[(m + r) * nr + 1 + j] = -q.C[r * n + j]; }
-    ldlt(KK.data(), s);
-    ldlt_solve(KK.data(), s, rhs.data(), nr);
+    // 4. KKT [Rh D'; D -mu I] X = -[rh Sh'; d C].  Rows of (C, D) that are entirely zero (inactive constraints) decouple
+    //    exactly to kv = d/mu, Kv = 0 and are eliminated before the factorisation (same solution, smaller LDL').
+    int nact = 0;
+    std::vector<int> arow(nc);
+    for (int r = 0; r < nc; r++) {
+      bool nzr = false;
+      for (int j = 0; j < n && !nzr; j++) nzr = q.C[r * n + j] != 0.0;
+      for (int j = 0; j < m && !nzr; j++) nzr = q.D[r * m + j] != 0.0;
+      if (nzr) arow[nact++] = r;
+    }
+    const int sa = m + nact;
+    std::fill(KK.begin(), KK.begin() + sa * sa, 0.0);
+    for (int i = 0; i < m; i++) for (int j = 0; j < m; j++) KK[i * sa + j] = 0.5 * (Hh[(n + i) * nz + n + j] + Hh[(n + j) * nz + n + i]);
+    for (int a = 0; a < nact; a++) { int r = arow[a]; for (int j = 0; j < m; j++) { KK[(m + a) * sa + j] = q.D[r * m + j]; KK[j * sa + m + a] = q.D[r * m + j]; } KK[(m + a) * sa + m + a] = -mu; }
+    std::vector<double> &ra = Wk_scratch;
+    ra.assign((size_t)sa * nr, 0.0);
+    for (int i = 0; i < m; i++) { ra[i * nr] = -gh[n + i]; for (int j = 0; j < n; j++) ra[i * nr + 1 + j] = -Hh[j * nz + n + i]; }
+    for (int a = 0; a < nact; a++) { int r = arow[a]; ra[(m + a) * nr] = -q.d[r]; for (int j = 0; j < n; j++) ra[(m + a) * nr + 1 + j] = -q.C[r * n + j]; }
+    ldlt(KK.data(), sa);
+    ldlt_solve(KK.data(), sa, ra.data(), nr);
+    std::fill(rhs.begin(), rhs.end(), 0.0);
+    std::memcpy(rhs.data(), ra.data(), sizeof(double) * m * nr);
+    for (int r = 0; r < nc; r++) rhs[(m + r) * nr] = q.d[r] / mu; // inactive rows; active ones overwritten next
+    for (int a = 0; a < nact; a++) std::memcpy(&rhs[(m + arow[a]) * nr], &ra[(m + a) * nr], sizeof(double) * nr);
     std::memcpy(&sol.K[(size_t)k * s * nr], rhs.data(), sizeof(double) * s * nr);
     // 5. P = Qh + Sh Ku + C' Kv (symmetrised); p = qh + Sh ku + C' kv
     for (int i = 0; i < n; i++) {
@@ -159,12 +181,12 @@ inline void riccati_solve(int n, int m, int nc, int T, const LQKnot *kn, const d
       for (int l = 0; l < m; l++) t += Hh[i * nz + n + l] * rhs[l * nr];
       for (int r = 0; r < nc; r++) t += q.C[r * n + i] * rhs[(m + r) * nr];
       p[i] = t;
-      for (int j = 0; j < n; j++) {
-        double u = Hh[i * nz + j];
-        for (int l = 0; l < m; l++) u += Hh[i * nz + n + l] * rhs[l * nr + 1 + j];
-        for (int r = 0; r < nc; r++) { double c = q.C[r * n + i]; if (c != 0.0) u += c * rhs[(m + r) * nr + 1 + j]; }
-        Pt[i * n + j] = u;
-      }
+      double *row = &Pt[i * n];
+      for (int j = 0; j < n; j++) row[j] = Hh[i * nz + j];
+      for (int l = 0; l < m; l++) { double h = Hh[i * nz + n + l]; const double *kr = &rhs[l * nr + 1];
+_Pragma("GCC ivdep") for (int j = 0; j < n; j++) row[j] += h * kr[j]; }
+      for (int r = 0; r < nc; r++) { double c = q.C[r * n + i]; if (c == 0.0) continue; const double *kr = &rhs[(m + r) * nr + 1];
+_Pragma("GCC ivdep") for (int j = 0; j < n; j++) row[j] += c * kr[j]; }
     }
     for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) P[i * n + j] = 0.5 * (Pt[i * n + j] + Pt[j * n + i]);
   }
