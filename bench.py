@@ -26,6 +26,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "full-dynamics Talos MPC solves/sec at batch 4096"
 UNIT = "solves/s"
+WORKLOAD = ("BASELINE configs[4]: full-dynamics Talos MPC tick (solver.setup + 1 ProxDDP iteration), T=100, one random contact schedule "
+            "per instance, warm start = converged solve of the nominal problem, measured state x0 perturbed per instance "
+            "(sigma 0.01 m / 0.02 rad / 0.05 s^-1), synthetic Talos-shaped model")
 
 
 def parse():
@@ -96,8 +99,9 @@ def reference_arm(args):
     cores = os.cpu_count() or 1
     sample = args.cpu_sample or max(cores, 16)
     prob = problems.full_walk_batch(sample, seed=5)
-    warm = oracle_lib.solve(prob, max_iters=min(args.prep_iters, 5), inst_threads=cores)
-    xs, us = warm["xs"], warm["us"]
+    nominal = dict(prob, x0=prob["x0_nominal"])
+    warm = oracle_lib.solve(nominal, max_iters=args.prep_iters, inst_threads=cores)
+    xs, us = problems.warm_tick_inputs(prob, warm["xs"]), warm["us"]
     for _ in range(max(1, min(args.warmup, 1))):
         oracle_lib.solve(prob, max_iters=1, inst_threads=cores, xs=xs, us=us)
     t0 = time.time()
@@ -107,7 +111,7 @@ def reference_arm(args):
     val = sample * args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": f"full-dynamics Talos MPC tick, T=100, random contact schedules, CPU sample of {sample} instances/step"},
+            "data": "synthetic", "config": {"workload": f"{WORKLOAD}; CPU sample of {sample} instances/step", "prep_iters": args.prep_iters},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{sample} instances x {args.steps} ticks; CPU oracle (not upstream Aligator, which cannot be installed offline)"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -136,13 +140,14 @@ def main():
     B, T = args.batch, 100
     prob = problems.full_walk_batch(B, seed=5 + rank, T=T)
     solver = BatchSolver(prob["robot"], prob["cfg"], B, device=local)
-    solver.setup(prob["knots"], prob["terms"], prob["x0"])
-    # untimed preparation: a few ProxDDP iterations from the cold start give the warm start every timed tick re-solves
+    # untimed preparation = the reference's first solve (fulldynamic_talos.py:386-397): ProxDDP from the cold start at the
+    # NOMINAL state; every timed tick then re-solves from that solution with the instance's MEASURED (perturbed) state at knot 0
+    solver.setup(prob["knots"], prob["terms"], prob["x0_nominal"])
     prep = solver.run(prob["xs"], prob["us"], max_iters=args.prep_iters, gains=False)
-    xs_h = torch.from_numpy(prep.xs).pin_memory()
+    xs_h = torch.from_numpy(problems.warm_tick_inputs(prob, prep.xs)).pin_memory()
     us_h = torch.from_numpy(prep.us).pin_memory()
     xs_d, us_d = xs_h.cuda(non_blocking=True), us_h.cuda(non_blocking=True)
-    solver.setup(prob["knots"], prob["terms"], prob["x0"])  # multipliers restart from zero, as solver.setup does each tick
+    solver.set_x0(prob["x0"])
     torch.cuda.synchronize()
     stream = torch.cuda.current_stream().cuda_stream
     peak_tf = _native.lib().mpc_measure_fp64_peak(local)
@@ -153,6 +158,7 @@ def main():
         torch.cuda.synchronize()
 
     def tick_device():
+        solver.reset_multipliers(stream)  # the reference calls solver.setup(problem) inside every tick (full:539)
         solver.run_device(xs_d.data_ptr(), us_d.data_ptr(), max_iters=1, stream=stream)
 
     xs_np, us_np = xs_h.numpy(), us_h.numpy()
@@ -160,6 +166,7 @@ def main():
     out_us = np.empty_like(us_np)
 
     def tick_e2e():
+        solver.reset_multipliers()
         solver.run(xs_np, us_np, max_iters=1, fetch=False)
         # read back what the MPC loop consumes: xs, us and the first feedback gain (fulldynamic_talos.py:548-550)
         _native.check(_native.lib().mpc_get_results(solver._h, _native.ptr(out_xs), _native.ptr(out_us), None, None, None, None), "mpc_get_results")
@@ -218,8 +225,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": 1e3 * step_s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[4]: full-dynamics Talos MPC tick (1 ProxDDP iteration, warm start), T=100, random contact "
-                                   "schedules + perturbed x0, synthetic Talos-shaped model", "batch_per_gpu": B, "global_batch": B * world,
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
                        "horizon": T, "parallelism": f"instances sharded over {world} GPU(s), no collective on the data path",
                        "l2": "per-step working set (GBs of LQ blocks) >> 126 MB L2; no flush needed",
                        "prep_iters": args.prep_iters, "tick_iters_done": int(np.min(res_iters))},
@@ -252,13 +258,14 @@ def single_instance_latency(args, prob, device, with_cpu):
 
     sub = problems.sub_problem(prob, 0, 1)
     s = BatchSolver(sub["robot"], sub["cfg"], 1, device=device)
-    s.setup(sub["knots"], sub["terms"], sub["x0"])
+    s.setup(sub["knots"], sub["terms"], sub["x0_nominal"])
     warm = s.run(sub["xs"], sub["us"], max_iters=args.prep_iters, gains=False)
-    xs, us = warm.xs.copy(), warm.us.copy()
+    xs, us = problems.warm_tick_inputs(sub, warm.xs), warm.us.copy()
+    s.set_x0(sub["x0"])
     ts = []
     for i in range(args.latency_ticks + 10):
-        s.setup(sub["knots"], sub["terms"], sub["x0"])  # the reference re-runs solver.setup inside its timed region
         t0 = time.perf_counter()
+        s.reset_multipliers()  # the reference re-runs solver.setup inside its timed region
         s.run(xs, us, max_iters=1, gains=False)
         ts.append(1e3 * (time.perf_counter() - t0))
     ts = np.array(ts[10:])

@@ -136,6 +136,10 @@ int32_t mpc_run(mpc_solver_t *h, const double *xs_init, const double *us_init, i
  * asynchronous on `stream` (a cudaStream_t); used when inputs live in HBM. */
 int32_t mpc_run_device(mpc_solver_t *h, uint64_t xs_dev, uint64_t us_dev, int32_t max_iters, uint64_t stream);
 
+/* What the per-tick solver.setup(problem) of the reference does to the solver state (full:539, cent:461) without
+ * re-uploading the problem: multipliers vs / lams back to zero.  Asynchronous on `stream` (0 = the handle's own stream). */
+int32_t mpc_reset_multipliers(mpc_solver_t *h, uint64_t stream);
+
 /* One closed-loop MPC tick on the device (the loop body of fulldynamic_talos.py:496-497,532-540):
  * append `last` ([batch], may be NULL) at the end of the horizon, shift the previous solution by one knot as warm start,
  * x0 <- x_meas ([batch][nx] host) or the model prediction xs[1] when NULL (ideal plant), multipliers reset (setup per tick)
@@ -173,7 +177,9 @@ int32_t mpc_debug_lq(mpc_solver_t *h, const double *xs, const double *us, int32_
  * A [K][lda], B [K][ldb] (host pointers, K % 4 == 0). */
 int32_t mpc_debug_gemm_tn(int32_t mt, int32_t nt, int32_t K, const double *A, int32_t lda, const double *B, int32_t ldb, double *C,
                           int32_t ldc);
-int32_t mpc_debug_phases(mpc_solver_t *h, double *out16); /* Riccati per-phase cycle counters (profiling builds only) */
+/* Per-phase cycle counters (all zero unless built with -DMPC_PHASE_TIMING): out48 = 16 Riccati phases, 16 phases of the
+ * derivative evaluation kernel, 16 phases of the values-only (linesearch trial) evaluation kernel. */
+int32_t mpc_debug_phases(mpc_solver_t *h, double *out48);
 uint64_t mpc_workspace_bytes(mpc_solver_t *h);
 int32_t mpc_abi_sizeof(int32_t which); /* 0 robot, 1 config, 2 knot, 3 term, 4 info */
 /* fp64 DFMA peak micro-benchmark (TFLOP/s) used as the roofline denominator. */

@@ -16,7 +16,7 @@ EXPORTS = [
     "mpc_create", "mpc_destroy", "mpc_last_error", "mpc_setup", "mpc_update_knots", "mpc_update_terms", "mpc_cycle", "mpc_set_x0", "mpc_shift_multipliers", "mpc_reconfigure",
     "mpc_run", "mpc_run_device", "mpc_tick", "mpc_get_results", "mpc_result_ptrs", "mpc_get_stage_data", "mpc_last_launches", "mpc_last_device_ms",
     "mpc_get_feedback", "mpc_last_kernel_ms", "mpc_last_kernel_launches", "mpc_set_profiling",
-    "mpc_debug_lq", "mpc_debug_gemm_tn", "mpc_debug_phases", "mpc_workspace_bytes", "mpc_abi_sizeof", "mpc_measure_fp64_peak",
+    "mpc_reset_multipliers", "mpc_debug_lq", "mpc_debug_gemm_tn", "mpc_debug_phases", "mpc_workspace_bytes", "mpc_abi_sizeof", "mpc_measure_fp64_peak",
 ]
 
 
@@ -58,6 +58,7 @@ def lib():
         L.mpc_debug_lq.argtypes = [C.c_void_p, dp, dp, C.c_int32] + [dp] * 6
         L.mpc_debug_gemm_tn.argtypes = [C.c_int32, C.c_int32, C.c_int32, dp, C.c_int32, dp, C.c_int32, dp, C.c_int32]
         L.mpc_debug_phases.argtypes = [C.c_void_p, dp]
+        L.mpc_reset_multipliers.argtypes = [C.c_void_p, C.c_uint64]
         L.mpc_workspace_bytes.argtypes = [C.c_void_p]
         L.mpc_workspace_bytes.restype = C.c_uint64
         L.mpc_abi_sizeof.argtypes = [C.c_int32]

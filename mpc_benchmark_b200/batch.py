@@ -81,6 +81,10 @@ class BatchSolver:
     def shift_multipliers(self, n=1):
         _native.check(_native.lib().mpc_shift_multipliers(self._h, int(n)), "mpc_shift_multipliers")
 
+    def reset_multipliers(self, stream=0):
+        """The solver-state part of a per-tick `solver.setup` (full:539): multipliers back to zero, problem kept."""
+        _native.check(_native.lib().mpc_reset_multipliers(self._h, int(stream)), "mpc_reset_multipliers")
+
     def set_x0(self, x0):
         x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(self.batch, self.nx)
         _native.check(_native.lib().mpc_set_x0(self._h, _native.ptr(x0)), "mpc_set_x0")

@@ -389,6 +389,17 @@ int32_t mpc_tick(mpc_solver_t *h, const mpc_knot_t *last, const double *x_meas, 
   return run_impl(h, h->d_xs_in, h->d_us_in, max_iters, h->stream, true);
 }
 
+int32_t mpc_reset_multipliers(mpc_solver_t *h, uint64_t stream) {
+  CK(cudaSetDevice(h->device));
+  if (!h->setup_done) return fail("mpc_reset_multipliers before mpc_setup");
+  Ws &w = h->w;
+  const size_t T1 = w.T + 1;
+  cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : h->stream;
+  CK(cudaMemsetAsync(w.vs, 0, w.B * T1 * w.nc * 8, s));
+  CK(cudaMemsetAsync(w.lams, 0, w.B * T1 * w.n * 8, s));
+  return 0;
+}
+
 int32_t mpc_run(mpc_solver_t *h, const double *xs_init, const double *us_init, int32_t max_iters) {
   CK(cudaSetDevice(h->device));
   if (!h->setup_done) return fail("mpc_run before mpc_setup");
@@ -467,10 +478,10 @@ int32_t mpc_get_feedback(mpc_solver_t *h, int32_t k, double *K) {
 double mpc_last_device_ms(mpc_solver_t *h) { return h->last_ms; }
 uint64_t mpc_workspace_bytes(mpc_solver_t *h) { return h->bytes; }
 // per-phase cycle counters of the Riccati kernel for instance 0 (all zero unless built with -DMPC_PHASE_TIMING)
-int32_t mpc_debug_phases(mpc_solver_t *h, double *out16) {
+int32_t mpc_debug_phases(mpc_solver_t *h, double *out48) {
   CK(cudaSetDevice(h->device));
   if (!h->setup_done) return fail("mpc_debug_phases before mpc_setup");
-  CK(cudaMemcpy(out16, h->w.phase, 32 * 8, cudaMemcpyDeviceToHost)); // [0:16) Riccati, [16:32) evaluation kernel
+  CK(cudaMemcpy(out48, h->w.phase, 48 * 8, cudaMemcpyDeviceToHost)); // [0:16) Riccati, [16:32) derivative eval, [32:48) values eval
   return 0;
 }
 

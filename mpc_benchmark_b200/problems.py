@@ -218,7 +218,10 @@ def full_walk_batch(batch, seed=5, T=100, robot=None, swing_apex=0.15, perturb=T
     Instance i gets its own gait (random initial double-support length, single/double-support durations and first
     swing foot; `random_schedule`), swing-foot references following the Bezier bump of talos_utils.py:281-296,
     a perturbed initial state and the terminal CoM equality of the MPC loop
-    (fulldynamic_talos.py:499-507).  Every stage uses force-reference index 0 as the reference does (full:363-366)."""
+    (fulldynamic_talos.py:499-507).  Every stage uses force-reference index 0 as the reference does (full:363-366).
+    `x0` is the perturbed ("measured") state of each instance, `x0_nominal` the unperturbed one; the cold start `xs`
+    repeats the nominal state as the reference's first solve does (full:390-391).  An MPC tick warm-starts from the
+    solution of the nominal problem and forces the measured state at knot 0: see `warm_tick_inputs`."""
     rb, q0, x0, lf, rf, com0, mass = base_setup(robot)
     cfg = full_config(rb, x0, lf, rf, T=T, **kw)
     rng = np.random.default_rng(seed)
@@ -244,10 +247,19 @@ def full_walk_batch(batch, seed=5, T=100, robot=None, swing_apex=0.15, perturb=T
         com_final = np.array([(lf[9] + rf[9]) / 2, (lf[10] + rf[10]) / 2, com0[2]])
         terms[i] = make_term(lf, rf, com_final)
     x0s = perturbed_x0(rb, x0, rng, batch) if perturb else np.tile(x0, (batch, 1))
-    xs = np.repeat(x0s[:, None, :], T + 1, axis=1)
+    x0n = np.tile(x0, (batch, 1))
+    xs = np.repeat(x0n[:, None, :], T + 1, axis=1)
     us = np.zeros((batch, T, 22))
-    return dict(robot=rb, cfg=cfg, knots=knots, terms=terms, x0=x0s, xs=xs, us=us, lf=lf, rf=rf, com0=com0, mass=mass,
+    return dict(robot=rb, cfg=cfg, knots=knots, terms=terms, x0=x0s, x0_nominal=x0n, xs=xs, us=us, lf=lf, rf=rf, com0=com0, mass=mass,
                 ds_fraction=n_ds / float(batch * T))
+
+
+def warm_tick_inputs(prob, warm_xs):
+    """Inputs of one closed-loop MPC tick (fulldynamic_talos.py:532-540): the previous solution as the warm start, with
+    the MEASURED state of each instance (prob["x0"]) at knot 0 — the solver is run with force_initial_condition."""
+    xs = np.array(warm_xs, dtype=float, copy=True)
+    xs[:, 0, :] = prob["x0"]
+    return xs
 
 
 def sub_problem(prob, lo, hi):
@@ -258,6 +270,8 @@ def sub_problem(prob, lo, hi):
     terms = (_abi.Term * n)(*[prob["terms"][i] for i in range(lo, hi)])
     out = dict(prob)
     out.update(knots=knots, terms=terms, x0=prob["x0"][lo:hi].copy(), xs=prob["xs"][lo:hi].copy(), us=prob["us"][lo:hi].copy())
+    if "x0_nominal" in prob:
+        out["x0_nominal"] = prob["x0_nominal"][lo:hi].copy()
     return out
 
 
