@@ -177,9 +177,9 @@ int32_t mpc_debug_lq(mpc_solver_t *h, const double *xs, const double *us, int32_
  * A [K][lda], B [K][ldb] (host pointers, K % 4 == 0). */
 int32_t mpc_debug_gemm_tn(int32_t mt, int32_t nt, int32_t K, const double *A, int32_t lda, const double *B, int32_t ldb, double *C,
                           int32_t ldc);
-/* Per-phase cycle counters (all zero unless built with -DMPC_PHASE_TIMING): out48 = 16 Riccati phases, 16 phases of the
- * derivative evaluation kernel, 16 phases of the values-only (linesearch trial) evaluation kernel. */
-int32_t mpc_debug_phases(mpc_solver_t *h, double *out48);
+/* Per-phase cycle counters (all zero unless built with -DMPC_PHASE_TIMING): out64 = 16 Riccati phases, 16 phases of the
+ * derivative evaluation kernel, 16 phases of the values-only (linesearch trial) evaluation kernel, 16 Riccati sub-phases. */
+int32_t mpc_debug_phases(mpc_solver_t *h, double *out64);
 uint64_t mpc_workspace_bytes(mpc_solver_t *h);
 int32_t mpc_abi_sizeof(int32_t which); /* 0 robot, 1 config, 2 knot, 3 term, 4 info */
 /* fp64 DFMA peak micro-benchmark (TFLOP/s) used as the roofline denominator. */

@@ -20,6 +20,16 @@
 #define WARP_FOR(i, n) for (int i = 0; i < (n); i++)
 #define WARP_SYNC() ((void)0)
 #define ATOMIC_INC(p) ((*(p))++)
+#define WARP_ROW_FOR(i, n) for (int i = 0; i < (n); i++)
+#define LANE_FOR(j, n) for (int j = 0; j < (n); j++)
+#define WARP_SUM(x) (x)
+#define LANE0 true
+#define PREFETCH_L2(p) ((void)0)
+#define ASYNC_COPY16(dst, src) do { (dst)[0] = (src)[0]; (dst)[1] = (src)[1]; } while (0)
+#define ASYNC_COPY8(dst, src) do { (dst)[0] = (src)[0]; } while (0)
+#define ASYNC_COMMIT() ((void)0)
+#define ASYNC_WAIT_PREV() ((void)0)
+#define ASYNC_WAIT() ((void)0)
 struct double2 { double x, y; };
 inline double2 make_double2(double x, double y) { return double2{x, y}; }
 #else
@@ -33,9 +43,31 @@ inline double2 make_double2(double x, double y) { return double2{x, y}; }
 #define WARP_FOR(i, n) for (int i = (threadIdx.x & 31); i < (n); i += 32)
 #define WARP_SYNC() __syncwarp()
 #define ATOMIC_INC(p) atomicAdd((p), 1)
+// matrix-vector pattern: rows over warps, columns over lanes (coalesced / conflict-free), butterfly reduction
+#define WARP_ROW_FOR(i, n) for (int i = (threadIdx.x >> 5); i < (n); i += (blockDim.x >> 5))
+#define LANE_FOR(j, n) for (int j = (threadIdx.x & 31); j < (n); j += 32)
+#define WARP_SUM(x) mpcdev::warp_sum(x)
+#define LANE0 ((threadIdx.x & 31) == 0)
+#define PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+// 16-byte asynchronous global -> shared copy (cp.async, bypasses registers); dst/src are double pointers, 16-byte aligned
+#define ASYNC_COPY16(dst, src) \
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory")
+#define ASYNC_COPY8(dst, src) \
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory")
+#define ASYNC_COMMIT() asm volatile("cp.async.commit_group;" ::: "memory")
+#define ASYNC_WAIT_PREV() asm volatile("cp.async.wait_group 1;" ::: "memory") /* all but the most recent group */
+#define ASYNC_WAIT() asm volatile("cp.async.wait_all;" ::: "memory")
 #endif
 
 namespace mpcdev {
+
+#ifndef MPC_HOST_EMU
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+#endif
 
 // ------------------------------------------------------------------ 3-vectors / 3x3 (row-major)
 HD void cross3(const double *a, const double *b, double *c) {

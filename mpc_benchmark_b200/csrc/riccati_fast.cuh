@@ -13,9 +13,9 @@ namespace mpcdev {
 
 // optional per-phase cycle counters (thread 0 of the CTA handling instance 0), enabled with -DMPC_PHASE_TIMING
 #if defined(MPC_PHASE_TIMING) && !defined(MPC_HOST_EMU)
-#define PHASE_DECL long long ph_last = clock64(); long long ph_acc[16] = {0}
-#define PHASE(i) do { if (threadIdx.x == 0) { long long t_ = clock64(); ph_acc[i] += t_ - ph_last; ph_last = t_; } } while (0)
-#define PHASE_DUMP(ptr) do { if (threadIdx.x == 0 && (ptr)) for (int i_ = 0; i_ < 16; i_++) (ptr)[i_] = (double)ph_acc[i_]; } while (0)
+#define PHASE_DECL long long ph_last = clock64(); long long ph_acc[32] = {0}
+#define PHASE(i) do { __syncthreads(); if (threadIdx.x == 0) { long long t_ = clock64(); ph_acc[i] += t_ - ph_last; ph_last = t_; } } while (0)
+#define PHASE_DUMP(ptr) do { if (threadIdx.x == 0 && (ptr)) for (int i_ = 0; i_ < 16; i_++) { (ptr)[i_] = (double)ph_acc[i_]; (ptr)[48 + i_] = (double)ph_acc[16 + i_]; } } while (0)
 #else
 #define PHASE_DECL
 #define PHASE(i)
@@ -31,7 +31,8 @@ template <int N, int M, int NC, int NCAP = NC> struct RicFastLayout {
   static constexpr int LDH = ZP;                                    // ld of the Hessian buffer
   static_assert(N * LDZ <= 2 * N * LDN, "W must fit over the dead [P | G] buffers");
   static constexpr int phase1 = 3 * N * LDN + N * LDZ;  // P, G (later reused as W), Li, AB
-  static constexpr int phase2 = NCAP * NZ + NCAP * NCAP + M * (NR + NCAP) + NCAP * NR + M * M; // sized for NCAP active rows
+  static constexpr int MP = (M + 3) / 4 * 4;                        // Z rows padded to the DMMA k-step (zero rows)
+  static constexpr int phase2 = NCAP * NZ + NCAP * NCAP + MP * (NR + NCAP) + NCAP * NR + M * M; // sized for NCAP active rows
   static constexpr int un = phase1 > phase2 ? phase1 : phase2;
   static constexpr int vecs = 8 * ZP + 36 + 2 * NC + 256 + 64 * ((NC + 7) / 8) + 8 * 64 + 16;
   static constexpr int total = ZP * LDH + un + vecs;
@@ -39,7 +40,7 @@ template <int N, int M, int NC, int NCAP = NC> struct RicFastLayout {
 
 template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(const RiccatiIO &io, double *ws) {
   using Lay = RicFastLayout<N, M, NC, NCAP>;
-  constexpr int NZ = Lay::NZ, NR = Lay::NR, S = Lay::S, ZP = Lay::ZP, LDN = Lay::LDN, LDZ = Lay::LDZ, LDH = Lay::LDH, NBLK = Lay::NBLK;
+  constexpr int NZ = Lay::NZ, NR = Lay::NR, S = Lay::S, ZP = Lay::ZP, LDN = Lay::LDN, LDZ = Lay::LDZ, LDH = Lay::LDH, NBLK = Lay::NBLK, MP = Lay::MP;
   static_assert(N % 8 == 0, "fast Riccati needs n % 8 == 0");
   const int T = io.T;
   const double mu = io.mu, mu_d = io.mu_d;
@@ -48,7 +49,7 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
   double *H = ws;                              // ZP x LDH, zero padded; [0:N,0:N] carries the value-function Hessian between knots
   double *U0 = H + ZP * LDH;
   double *P = U0, *G = P + N * LDN, *Li = G + N * LDN, *AB = Li + N * LDN, *W = P;  // phase 1 (W overwrites the dead P, G)
-  double *CD = U0, *Sg = CD + NCAP * NZ, *Z = Sg + NCAP * NCAP, *Kv = Z + M * (NR + NCAP), *Rh = Kv + NCAP * NR;  // phase 2
+  double *CD = U0, *Sg = CD + NCAP * NZ, *Z = Sg + NCAP * NCAP, *Kv = Z + MP * (NR + NCAP), *Rh = Kv + NCAP * NR;  // phase 2
   double *vec = U0 + Lay::un;
   double *p = vec, *pt = p + ZP, *gh = pt + ZP, *fb = gh + ZP, *tmp = fb + ZP, *dx = tmp + ZP, *z = dx + ZP, *pv = z + ZP;
   double *T6 = pv + ZP, *dbr = T6 + 36, *dva = dbr + NC, *red = dva + NC, *dinv = red + 256, *wtmp = dinv + 64 * ((NC + 7) / 8);
@@ -73,21 +74,30 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
     }
     SYNC();
   }
+  // [A B] of a knot goes global -> shared with cp.async (NZ even: 16-byte chunks), issued one knot ahead so that the copy
+  // overlaps the tail of the previous knot; the padding columns NZ..ZP-1 are zeroed with plain stores
+  auto stage_AB_async = [&](int kk) {
+    const double *src = io.AB + (size_t)kk * N * NZ;
+    PAR_FOR(e, N * (NZ / 2)) { int i = e / (NZ / 2), j = (e % (NZ / 2)) * 2; ASYNC_COPY16(AB + i * LDZ + j, src + i * NZ + j); }
+    PAR_FOR(e, N * (ZP - NZ)) { int i = e / (ZP - NZ), j = NZ + e % (ZP - NZ); AB[i * LDZ + j] = 0.0; }
+  };
+  if (T > 0) stage_AB_async(T - 1);
   for (int k = T - 1; k >= 0; k--) {
-    const double *gAB = io.AB + (size_t)k * N * NZ, *gH = io.H + (size_t)k * NZ * NZ;
+    const double *gH = io.H + (size_t)k * NZ * NZ;
     int nca = io.nca[k];
     if (nca > NCAP) { nca = NCAP; ONE_THREAD { if (io.overflow) *io.overflow = 1; } } // more active rows than the shared-memory KKT holds
-    // 1. stage [A B] (zero-padded columns), P <- value Hessian, E normalisation P <- T' P T, p <- T' p
-    PAR_FOR(e, N * (ZP / 2)) {
-      int i = e / (ZP / 2), j = (e % (ZP / 2)) * 2;
-      double2 v = make_double2(0.0, 0.0);
-      if (j < NZ) v = *reinterpret_cast<const double2 *>(gAB + i * NZ + j); // NZ even, rows 16-byte aligned
-      *reinterpret_cast<double2 *>(AB + i * LDZ + j) = v;
+    // 1. P <- symmetrised value Hessian (left in H by the previous knot), then H <- H_k asynchronously (lands before the
+    //    Hessian update needs it); E normalisation P <- T' P T, p <- T' p
+    PAR_FOR(e, N * N) { // lanes: 8 consecutive j x 4 consecutive i, which keeps the transposed read at 8-way bank conflicts
+      const int blk = e >> 5, l = e & 31, i = (blk / (N / 8)) * 4 + (l >> 3), j = (blk % (N / 8)) * 8 + (l & 7);
+      P[i * LDN + j] = 0.5 * (H[i * LDH + j] + H[j * LDH + i]);
     }
-    PAR_FOR(e, N * N) { int i = e / N, j = e % N; P[i * LDN + j] = H[i * LDH + j]; }
     PAR_FOR(e, 36) T6[e] = io.T6[(size_t)k * 36 + e];
     PAR_FOR(i, N) fb[i] = io.fbar[(size_t)k * N + i];
+    ASYNC_WAIT(); // [A B] of this knot
     SYNC();
+    PAR_FOR(e, NZ * (NZ / 2)) { int i = e / (NZ / 2), j = (e % (NZ / 2)) * 2; ASYNC_COPY16(H + i * LDH + j, gH + i * NZ + j); }
+    PHASE(16);
     PAR_FOR(e, N * 6) { int i = e / 6, j = e % 6; double s = 0; for (int l = 0; l < 6; l++) s += P[i * LDN + l] * T6[6 * l + j]; Li[e] = s; }
     SYNC();
     PAR_FOR(e, N * 6) { int i = e / 6, j = e % 6; P[i * LDN + j] = Li[e]; }
@@ -145,7 +155,11 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
     PHASE(4);
     // 6. W = Pt [A B];  7. H = H_k + [A B]' W;  gh = g + [A B]' pt
     mma_tn(NBLK, ZP / 8, N, Li, LDN, AB, LDZ, W, LDZ, nullptr, 0, 0, 0, false);
-    mma_tn(ZP / 8, ZP / 8, N, AB, LDZ, W, LDZ, H, LDH, gH, NZ, NZ, NZ, false);
+    PHASE(17);
+    ASYNC_WAIT(); // H_k
+    SYNC();
+    mma_tn(ZP / 8, ZP / 8, N, AB, LDZ, W, LDZ, H, LDH, H, LDH, ZP, ZP, false); // in place: H = H_k + [A B]' W (padding stays zero)
+    PHASE(18);
     PAR_FOR(i, NZ) { double s = io.g[(size_t)k * NZ + i]; for (int l = 0; l < N; l++) s += AB[l * LDZ + i] * pt[l]; gh[i] = s; }
     PAR_FOR(e, N * (NZ / 2)) {
       int i = e / (NZ / 2), j = (e % (NZ / 2)) * 2;
@@ -166,6 +180,7 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
       int i = e / ncol, c = e % ncol;
       Z[i * ncol + c] = (c == 0) ? gh[N + i] : (c < NR ? H[(c - 1) * LDH + N + i] : CD[(c - NR) * NZ + N + i]);
     }
+    PAR_FOR(e, (MP - M) * ncol) Z[M * ncol + e] = 0.0; // zero rows up to the DMMA k-step (value update below)
     SYNC();
     PHASE(6);
     chol_blocked(Rh, M, M, dinv);
@@ -199,97 +214,147 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
     PAR_FOR(e, M * NR) { int i = e / NR, c = e % NR; double v = Z[i * ncol + c]; gK[e] = v; if (c > 0) io.Kfb[((size_t)k * M + i) * N + c - 1] = v; }
     PAR_FOR(e, nca * NR) gK[M * NR + e] = Kv[e];
     PHASE(11);
-    // 9. P = Qh + Sh Ku + C' Kv, p = qh + Sh ku + C' kv : in place in H[0:N,0:N] / p, then symmetrise
-    { // 2 x 4 register tiles over (row i, column c of [p | P]); column 0 is the vector p
-      constexpr int TC = (NR + 3) / 4;
+    // 9. P = Qh + Sh Ku + C' Kv, p = qh + Sh ku + C' kv : in place in H[0:N,0:N] / p (symmetrised when the next knot loads it).
+    //    Sh Ku = H[N:, 0:N]' Z[:, 1:] runs on the DMMA pipe (K = MP, zero rows beyond M); the active-row part is usually empty.
+    PAR_FOR(i, N) {
+      double s = gh[i];
+      for (int l = 0; l < M; l++) s += H[i * LDH + N + l] * Z[l * ncol];
+      for (int r = 0; r < nca; r++) s += CD[r * NZ + i] * Kv[r * NR];
+      p[i] = s;
+    }
+    mma_tn(NBLK, NBLK, MP, H + N * LDH, LDH, Z + 1, ncol, H, LDH, H, LDH, N, N, false);
+    if (nca > 0) { // 2 x 4 register tiles over (row i, column c)
+      constexpr int TC = N / 4;
       PAR_FOR(t, (N / 2) * TC) {
         const int i0 = (t / TC) * 2, c0 = (t % TC) * 4;
         double a[2][4];
 #pragma unroll
         for (int r = 0; r < 2; r++)
 #pragma unroll
-          for (int q = 0; q < 4; q++) { int c = c0 + q; a[r][q] = (c >= NR) ? 0.0 : ((c == 0) ? gh[i0 + r] : H[(i0 + r) * LDH + c - 1]); }
-        for (int l = 0; l < M; l++) {
-          const double h0 = H[i0 * LDH + N + l], h1 = H[(i0 + 1) * LDH + N + l];
-          const double *zr = Z + l * ncol + c0;
-#pragma unroll
-          for (int q = 0; q < 4; q++) { double zv = (c0 + q < NR) ? zr[q] : 0.0; a[0][q] += h0 * zv; a[1][q] += h1 * zv; }
-        }
+          for (int q = 0; q < 4; q++) a[r][q] = H[(i0 + r) * LDH + c0 + q];
         for (int r = 0; r < nca; r++) {
           const double h0 = CD[r * NZ + i0], h1 = CD[r * NZ + i0 + 1];
-          const double *kr = Kv + r * NR + c0;
+          const double *kr = Kv + r * NR + 1 + c0;
 #pragma unroll
-          for (int q = 0; q < 4; q++) { double kv = (c0 + q < NR) ? kr[q] : 0.0; a[0][q] += h0 * kv; a[1][q] += h1 * kv; }
+          for (int q = 0; q < 4; q++) { a[0][q] += h0 * kr[q]; a[1][q] += h1 * kr[q]; }
         }
 #pragma unroll
         for (int r = 0; r < 2; r++)
 #pragma unroll
-          for (int q = 0; q < 4; q++) { int c = c0 + q; if (c == 0) p[i0 + r] = a[r][q]; else if (c < NR) H[(i0 + r) * LDH + c - 1] = a[r][q]; }
+          for (int q = 0; q < 4; q++) H[(i0 + r) * LDH + c0 + q] = a[r][q];
       }
+      SYNC();
     }
-    SYNC();
-    PAR_FOR(e, N * N) {
-      int i = e / N, j = e % N;
-      if (i < j) { double s = 0.5 * (H[i * LDH + j] + H[j * LDH + i]); H[i * LDH + j] = s; H[j * LDH + i] = s; }
-    }
-    SYNC();
+    PHASE(19);
+    if (k > 0) stage_AB_async(k - 1); // Sg / Z (aliasing the [A B] buffer) are dead now
     PHASE(12);
   }
   // ---- forward sweep, dx0 = 0 (force_initial_condition, fulldynamic_talos.py:384)
   PHASE(13);
   double acc = 0.0;
   PAR_FOR(i, N) { dx[i] = 0.0; io.dxs[i] = 0.0; io.dlams[i] = -p[i]; }
+  // everything that does not depend on the sequential chain is done for all knots at once: default multiplier steps
+  // dv = dbar / mu of the inactive rows and their part of the directional derivative
+  PAR_FOR(e, (T + 1) * NC) {
+    const int kk = e / NC, r = e % NC, na = io.nca[kk];
+    const int32_t *ak = io.act_idx + (size_t)kk * NC;
+    const double db = io.dbar[e];
+    bool active = false;
+    for (int q = 0; q < na; q++) active |= (ak[q] == r);
+    io.dvs[e] = db / mu;
+    if (!active) acc -= db * db / mu;
+  }
+  // W_k, [A B]_k, the small per-knot vectors and the first KROWS gain rows of each knot are staged global -> shared one knot
+  // ahead (cp.async, two stages in the now dead H / phase buffers): the dependent chain dx_k -> du_k -> dx_{k+1} never waits on HBM
+  constexpr int FW = N * NZ;
+  constexpr int FX = 4 * N + NZ + 36; // pt_k, fbar_k, lplus_{k+1}, lam_{k+1}, lxu_k, T6_k
+  constexpr int KROWS = (((ZP * LDH + Lay::un - 4 * FW - 2 * FX) / 2) / NR) & ~1;
+  constexpr int FSTAGE = 2 * FW + FX + KROWS * NR;
+  static_assert(KROWS >= M && 2 * FSTAGE <= ZP * LDH + Lay::un && FSTAGE % 2 == 0, "forward staging does not fit");
+  auto stage_fwd = [&](int kk) {
+    double *bw = ws + (kk & 1) * FSTAGE, *ba = bw + FW, *bx = ba + FW, *bk = bx + FX;
+    const double *gw = io.W + (size_t)kk * FW, *ga = io.AB + (size_t)kk * FW, *gk = io.K + (size_t)kk * S * NR;
+    PAR_FOR(e, FW / 2) { ASYNC_COPY16(bw + 2 * e, gw + 2 * e); ASYNC_COPY16(ba + 2 * e, ga + 2 * e); }
+    int rows = M + io.nca[kk];
+    if (rows > KROWS) rows = KROWS;
+    PAR_FOR(e, rows * NR) ASYNC_COPY8(bk + e, gk + e);
+    PAR_FOR(i, N) {
+      ASYNC_COPY8(bx + i, io.pt + (size_t)kk * N + i);
+      ASYNC_COPY8(bx + N + i, io.fbar + (size_t)kk * N + i);
+      ASYNC_COPY8(bx + 2 * N + i, io.lplus + (size_t)(kk + 1) * N + i);
+      ASYNC_COPY8(bx + 3 * N + i, io.lam + (size_t)(kk + 1) * N + i);
+    }
+    PAR_FOR(i, NZ) ASYNC_COPY8(bx + 4 * N + i, io.lxu + (size_t)kk * NZ + i);
+    PAR_FOR(i, 36) ASYNC_COPY8(bx + 4 * N + NZ + i, io.T6 + (size_t)kk * 36 + i);
+  };
   SYNC();
-  for (int k = 0; k <= T; k++) {
+  if (T > 0) stage_fwd(0);
+  ASYNC_COMMIT();
+  for (int k = 0; k < T; k++) {
     const int nca = io.nca[k];
-    const int32_t *ai = io.act_idx + (size_t)k * NC;
-    const double *gdb = io.dbar + (size_t)k * NC, *gvp = io.vplus + (size_t)k * NC, *gv = io.v + (size_t)k * NC;
-    double *gdv = io.dvs + (size_t)k * NC;
-    if (k < T) {
-      const double *gK = io.K + (size_t)k * S * NR;
-      PAR_FOR(i, M + nca) {
-        double s = gK[i * NR];
-        for (int j = 0; j < N; j++) s += gK[i * NR + 1 + j] * dx[j];
+    if (k + 1 < T) stage_fwd(k + 1);
+    ASYNC_COMMIT();
+    ASYNC_WAIT_PREV(); // stage k has landed
+    SYNC();
+    const double *sW = ws + (k & 1) * FSTAGE, *sAB = sW + FW, *sX = sAB + FW, *sK = sX + FX;
+    const double *gK = io.K + (size_t)k * S * NR;
+    WARP_ROW_FOR(i, M + nca) { // du, dv of the active rows: rows over warps, columns over lanes
+      const double *row = (i < KROWS) ? sK + i * NR : gK + i * NR;
+      double s = 0;
+      LANE_FOR(j, N) s += row[1 + j] * dx[j];
+      s = WARP_SUM(s);
+      if (LANE0) {
+        s += row[0];
         if (i < M) { z[N + i] = s; io.dus[(size_t)k * M + i] = s; } else dva[i - M] = s;
       }
-      PAR_FOR(i, N) z[i] = dx[i];
-      PAR_FOR(e, N * (NZ / 2)) {
-        int i = e / (NZ / 2), j = (e % (NZ / 2)) * 2;
-        *reinterpret_cast<double2 *>(AB + i * LDZ + j) = *reinterpret_cast<const double2 *>(io.AB + (size_t)k * N * NZ + i * NZ + j);
-        *reinterpret_cast<double2 *>(W + i * LDZ + j) = *reinterpret_cast<const double2 *>(io.W + (size_t)k * N * NZ + i * NZ + j);
+    }
+    PAR_FOR(i, N) z[i] = dx[i];
+    SYNC();
+    if (nca > 0) {
+      const int32_t *ai = io.act_idx + (size_t)k * NC;
+      const double *gdb = io.dbar + (size_t)k * NC, *gvp = io.vplus + (size_t)k * NC, *gv = io.v + (size_t)k * NC;
+      PAR_FOR(r, nca) {
+        const int row = ai[r];
+        io.dvs[(size_t)k * NC + row] = dva[r];
+        acc += (2.0 * gvp[row] - gv[row]) * (mu * dva[r] - gdb[row]) - gdb[row] * dva[r];
       }
-      PAR_FOR(e, 36) T6[e] = io.T6[(size_t)k * 36 + e];
-    } else {
-      const double *CT = io.CDact + (size_t)T * NC * NZ;
-      PAR_FOR(r, nca) { double s = gdb[ai[r]]; for (int j = 0; j < N; j++) s += CT[r * NZ + j] * dx[j]; dva[r] = s / mu; }
-      PAR_FOR(i, N) z[i] = dx[i];
     }
-    PAR_FOR(r, NC) gdv[r] = gdb[r] / mu;
-    SYNC();
-    PAR_FOR(r, nca) gdv[ai[r]] = dva[r];
-    PAR_FOR(i, (k < T ? NZ : N)) acc += io.lxu[(size_t)k * NZ + i] * z[i];
-    PAR_FOR(r, nca) { int row = ai[r]; acc += (2.0 * gvp[row] - gv[row]) * (mu * dva[r] - gdb[row]) - gdb[row] * dva[r]; }
-    PAR_FOR(r, NC) {
-      bool active = false;
-      for (int q = 0; q < nca; q++) active |= (ai[q] == r);
-      if (!active) acc -= gdb[r] * gdb[r] / mu;
-    }
-    if (k == T) break;
-    PAR_FOR(i, N) {
-      double s = io.pt[(size_t)k * N + i], a = io.fbar[(size_t)k * N + i];
-      for (int j = 0; j < NZ; j++) { s += W[i * LDZ + j] * z[j]; a += AB[i * LDZ + j] * z[j]; }
-      tmp[i] = a - mu_d * s;
-      io.dlams[(size_t)(k + 1) * N + i] = s;
-      double fbi = io.fbar[(size_t)k * N + i], lp = io.lplus[(size_t)(k + 1) * N + i], lm = io.lam[(size_t)(k + 1) * N + i];
-      acc += (2.0 * lp - lm) * (mu_d * s - fbi) - fbi * s;
+    PAR_FOR(i, NZ) acc += sX[4 * N + i] * z[i];
+    WARP_ROW_FOR(i, N) { // dlam_{k+1} = pt + W z ; tmp = A dx + B du + fbar - mu_d dlam
+      double sl = 0, a = 0;
+      LANE_FOR(j, NZ) { const double zj = z[j]; sl += sW[i * NZ + j] * zj; a += sAB[i * NZ + j] * zj; }
+      sl = WARP_SUM(sl); a = WARP_SUM(a);
+      if (LANE0) {
+        const double fbi = sX[N + i], lp = sX[2 * N + i], lm = sX[3 * N + i];
+        sl += sX[i];
+        tmp[i] = a + fbi - mu_d * sl;
+        io.dlams[(size_t)(k + 1) * N + i] = sl;
+        acc += (2.0 * lp - lm) * (mu_d * sl - fbi) - fbi * sl;
+      }
     }
     SYNC();
     PAR_FOR(i, N) {
-      double s;
-      if (i < 6) { s = 0; for (int l = 0; l < 6; l++) s += T6[6 * i + l] * tmp[l]; } else s = tmp[i];
-      dx[i] = s; io.dxs[(size_t)(k + 1) * N + i] = s;
+      double v;
+      if (i < 6) { v = 0; for (int l = 0; l < 6; l++) v += sX[4 * N + NZ + 6 * i + l] * tmp[l]; } else v = tmp[i];
+      dx[i] = v; io.dxs[(size_t)(k + 1) * N + i] = v;
     }
+    PHASE(20);
     SYNC();
+  }
+  { // terminal knot: dv of the active terminal rows and the terminal cost gradient
+    const int nca = io.nca[T];
+    const int32_t *ai = io.act_idx + (size_t)T * NC;
+    const double *gdb = io.dbar + (size_t)T * NC, *gvp = io.vplus + (size_t)T * NC, *gv = io.v + (size_t)T * NC;
+    const double *CT = io.CDact + (size_t)T * NC * NZ;
+    PAR_FOR(r, nca) {
+      const int row = ai[r];
+      double sv = gdb[row];
+      for (int j = 0; j < N; j++) sv += CT[r * NZ + j] * dx[j];
+      sv /= mu;
+      io.dvs[(size_t)T * NC + row] = sv;
+      acc += (2.0 * gvp[row] - gv[row]) * (mu * sv - gdb[row]) - gdb[row] * sv;
+    }
+    PAR_FOR(i, N) acc += io.lxu[(size_t)T * NZ + i] * dx[i];
   }
   PHASE(14);
   PHASE_DUMP(io.phase_out);

@@ -478,10 +478,10 @@ int32_t mpc_get_feedback(mpc_solver_t *h, int32_t k, double *K) {
 double mpc_last_device_ms(mpc_solver_t *h) { return h->last_ms; }
 uint64_t mpc_workspace_bytes(mpc_solver_t *h) { return h->bytes; }
 // per-phase cycle counters of the Riccati kernel for instance 0 (all zero unless built with -DMPC_PHASE_TIMING)
-int32_t mpc_debug_phases(mpc_solver_t *h, double *out48) {
+int32_t mpc_debug_phases(mpc_solver_t *h, double *out64) {
   CK(cudaSetDevice(h->device));
   if (!h->setup_done) return fail("mpc_debug_phases before mpc_setup");
-  CK(cudaMemcpy(out48, h->w.phase, 48 * 8, cudaMemcpyDeviceToHost)); // [0:16) Riccati, [16:32) derivative eval, [32:48) values eval
+  CK(cudaMemcpy(out64, h->w.phase, 64 * 8, cudaMemcpyDeviceToHost)); // [0:16)+[48:64) Riccati, [16:32) derivative eval, [32:48) values eval
   return 0;
 }
 

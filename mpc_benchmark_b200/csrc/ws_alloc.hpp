@@ -32,7 +32,7 @@ template <class Alloc> size_t alloc_ws(Ws &w, Alloc &&alloc) {
   I(w.nca, B * T1); I(w.act_idx, B * T1 * nc);
   D(w.gap, B * T * n); D(w.h, B * T1 * nc); D(w.scal, B * T1 * SC_COUNT); D(w.tscal, B * T1 * SC_COUNT);
   D(w.xdot, B * T1 * 56); D(w.lamc, B * T1 * 12);
-  D(w.W, B * T * n * nz); D(w.pt, B * T * n); D(w.K, B * T * (m + nc) * (1 + n)); D(w.Kfb, B * T * m * n); D(w.dphi, B); D(w.phase, 48);
+  D(w.W, B * T * n * nz); D(w.pt, B * T * n); D(w.K, B * T * (m + nc) * (1 + n)); D(w.Kfb, B * T * m * n); D(w.dphi, B); D(w.phase, 64);
   w.st = (InstState *)alloc(B * sizeof(InstState)); total += B * sizeof(InstState);
   I(w.counters, 4); I(w.lists, 4 * B); I(w.overflow, B);
   return total;

@@ -20,12 +20,13 @@ def main():
     warm = s.run(prob["xs"], prob["us"], max_iters=3, gains=False)
     s.setup(prob["knots"], prob["terms"], prob["x0"])
     s.run(warm.xs, warm.us, max_iters=1, gains=False)
-    out = (C.c_double * 48)()
+    out = (C.c_double * 64)()
     _native.check(_native.lib().mpc_debug_phases(s._h, out), "mpc_debug_phases")
     ph = np.array(out[:])
     print("riccati phases (cycles):", [int(v) for v in ph[:16]], "sum", int(ph[:16].sum()))
     print("eval<deriv>  phases (cycles):", [int(v) for v in ph[16:32]], "sum", int(ph[16:32].sum()))
-    print("eval<values> phases (cycles):", [int(v) for v in ph[32:]], "sum", int(ph[32:].sum()))
+    print("eval<values> phases (cycles):", [int(v) for v in ph[32:48]], "sum", int(ph[32:48].sum()))
+    print("riccati sub-phases 16.. (cycles):", [int(v) for v in ph[48:]], "sum", int(ph[48:].sum()))
     print("kernel ms:", s.kernel_ms())
 
 
