@@ -24,6 +24,8 @@
 #define LANE_FOR(j, n) for (int j = 0; j < (n); j++)
 #define WARP_SUM(x) (x)
 #define LANE0 true
+#define WARP_ID 0
+#define NWARPS 1
 #define PREFETCH_L2(p) ((void)0)
 #define ASYNC_COPY16(dst, src) do { (dst)[0] = (src)[0]; (dst)[1] = (src)[1]; } while (0)
 #define ASYNC_COPY8(dst, src) do { (dst)[0] = (src)[0]; } while (0)
@@ -48,6 +50,8 @@ inline double2 make_double2(double x, double y) { return double2{x, y}; }
 #define LANE_FOR(j, n) for (int j = (threadIdx.x & 31); j < (n); j += 32)
 #define WARP_SUM(x) mpcdev::warp_sum(x)
 #define LANE0 ((threadIdx.x & 31) == 0)
+#define WARP_ID ((int)(threadIdx.x >> 5))
+#define NWARPS ((int)(blockDim.x >> 5))
 #define PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 // 16-byte asynchronous global -> shared copy (cp.async, bypasses registers); dst/src are double pointers, 16-byte aligned
 #define ASYNC_COPY16(dst, src) \

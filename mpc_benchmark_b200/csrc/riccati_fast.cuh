@@ -34,6 +34,12 @@ template <int N, int M, int NC, int NCAP = NC> struct RicFastLayout {
   static constexpr int MP = (M + 3) / 4 * 4;                        // Z rows padded to the DMMA k-step (zero rows)
   static constexpr int phase2 = NCAP * NZ + NCAP * NCAP + MP * (NR + NCAP) + NCAP * NR + M * M; // sized for NCAP active rows
   static constexpr int un = phase1 > phase2 ? phase1 : phase2;
+  // phase-2 order [Z | Kv | Rh | CD | Sg]; [A B] sits at the END of the union so that knots with few active rows never
+  // touch it in phase 2 and the next knot's [A B] can be prefetched early
+  static constexpr int offKv = MP * (NR + NCAP), offRh = offKv + NCAP * NR, offCD = offRh + M * M, offSg = offCD + NCAP * NZ;
+  static constexpr int offAB = un - N * LDZ;
+  static_assert(offAB >= 3 * N * LDN, "[A B] overlaps P / G / Li");
+  static_assert(un % 2 == 0 && offAB % 2 == 0 && (ZP * LDH) % 2 == 0, "16-byte alignment of the cp.async destinations");
   static constexpr int vecs = 8 * ZP + 36 + 2 * NC + 256 + 64 * ((NC + 7) / 8) + 8 * 64 + 16;
   static constexpr int total = ZP * LDH + un + vecs;
 };
@@ -48,8 +54,8 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
   // ---- carve shared memory
   double *H = ws;                              // ZP x LDH, zero padded; [0:N,0:N] carries the value-function Hessian between knots
   double *U0 = H + ZP * LDH;
-  double *P = U0, *G = P + N * LDN, *Li = G + N * LDN, *AB = Li + N * LDN, *W = P;  // phase 1 (W overwrites the dead P, G)
-  double *CD = U0, *Sg = CD + NCAP * NZ, *Z = Sg + NCAP * NCAP, *Kv = Z + MP * (NR + NCAP), *Rh = Kv + NCAP * NR;  // phase 2
+  double *P = U0, *G = P + N * LDN, *Li = G + N * LDN, *AB = U0 + Lay::offAB, *W = P;  // phase 1 (W overwrites the dead P, G)
+  double *Z = U0, *Kv = U0 + Lay::offKv, *Rh = U0 + Lay::offRh, *CD = U0 + Lay::offCD, *Sg = U0 + Lay::offSg;  // phase 2
   double *vec = U0 + Lay::un;
   double *p = vec, *pt = p + ZP, *gh = pt + ZP, *fb = gh + ZP, *tmp = fb + ZP, *dx = tmp + ZP, *z = dx + ZP, *pv = z + ZP;
   double *T6 = pv + ZP, *dbr = T6 + 36, *dva = dbr + NC, *red = dva + NC, *dinv = red + 256, *wtmp = dinv + 64 * ((NC + 7) / 8);
@@ -80,6 +86,8 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
     const double *src = io.AB + (size_t)kk * N * NZ;
     PAR_FOR(e, N * (NZ / 2)) { int i = e / (NZ / 2), j = (e % (NZ / 2)) * 2; ASYNC_COPY16(AB + i * LDZ + j, src + i * NZ + j); }
     PAR_FOR(e, N * (ZP - NZ)) { int i = e / (ZP - NZ), j = NZ + e % (ZP - NZ); AB[i * LDZ + j] = 0.0; }
+    PAR_FOR(e, 36 / 2) ASYNC_COPY16(T6 + 2 * e, io.T6 + (size_t)kk * 36 + 2 * e);
+    PAR_FOR(i, N / 2) ASYNC_COPY16(fb + 2 * i, io.fbar + (size_t)kk * N + 2 * i);
   };
   if (T > 0) stage_AB_async(T - 1);
   for (int k = T - 1; k >= 0; k--) {
@@ -92,9 +100,7 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
       const int blk = e >> 5, l = e & 31, i = (blk / (N / 8)) * 4 + (l >> 3), j = (blk % (N / 8)) * 8 + (l & 7);
       P[i * LDN + j] = 0.5 * (H[i * LDH + j] + H[j * LDH + i]);
     }
-    PAR_FOR(e, 36) T6[e] = io.T6[(size_t)k * 36 + e];
-    PAR_FOR(i, N) fb[i] = io.fbar[(size_t)k * N + i];
-    ASYNC_WAIT(); // [A B] of this knot
+    ASYNC_WAIT(); // [A B], T6 and fbar of this knot
     SYNC();
     PAR_FOR(e, NZ * (NZ / 2)) { int i = e / (NZ / 2), j = (e % (NZ / 2)) * 2; ASYNC_COPY16(H + i * LDH + j, gH + i * NZ + j); }
     PHASE(16);
@@ -167,6 +173,9 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
     }
     PAR_FOR(i, N) io.pt[(size_t)k * N + i] = pt[i];
     SYNC();
+    // [A B]_k is dead: when the active rows of this knot keep phase 2 clear of the buffer, fetch the next knot's now
+    const bool early = ((nca == 0) ? Lay::offCD : ((Lay::offCD + nca * NZ > Lay::offSg + nca * nca) ? Lay::offCD + nca * NZ : Lay::offSg + nca * nca)) <= Lay::offAB;
+    if (k > 0 && early) stage_AB_async(k - 1);
     PHASE(5);
     // 8. KKT by block elimination (phase-2 buffers alias P/G/Li/AB/W, all dead now)
     const int ncol = NR + nca; // Z columns: [rh | Sh' | D']
@@ -246,7 +255,7 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
       SYNC();
     }
     PHASE(19);
-    if (k > 0) stage_AB_async(k - 1); // Sg / Z (aliasing the [A B] buffer) are dead now
+    if (k > 0 && !early) stage_AB_async(k - 1); // the phase-2 buffers aliasing [A B] are dead now
     PHASE(12);
   }
   // ---- forward sweep, dx0 = 0 (force_initial_condition, fulldynamic_talos.py:384)
@@ -298,14 +307,30 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
     SYNC();
     const double *sW = ws + (k & 1) * FSTAGE, *sAB = sW + FW, *sX = sAB + FW, *sK = sX + FX;
     const double *gK = io.K + (size_t)k * S * NR;
-    WARP_ROW_FOR(i, M + nca) { // du, dv of the active rows: rows over warps, columns over lanes
-      const double *row = (i < KROWS) ? sK + i * NR : gK + i * NR;
-      double s = 0;
-      LANE_FOR(j, N) s += row[1 + j] * dx[j];
-      s = WARP_SUM(s);
+    // du, dv of the active rows: RA rows per warp at a time (independent reduction chains), columns over lanes
+    constexpr int RA = 3;
+    for (int base = WARP_ID * RA; base < M + nca; base += NWARPS * RA) {
+      double sa[RA];
+#pragma unroll
+      for (int r = 0; r < RA; r++) sa[r] = 0.0;
+      LANE_FOR(j, N) {
+        const double dj = dx[j];
+#pragma unroll
+        for (int r = 0; r < RA; r++) {
+          const int i = base + r;
+          if (i < M + nca) sa[r] += ((i < KROWS) ? sK[i * NR + 1 + j] : gK[i * NR + 1 + j]) * dj;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < RA; r++) sa[r] = WARP_SUM(sa[r]);
       if (LANE0) {
-        s += row[0];
-        if (i < M) { z[N + i] = s; io.dus[(size_t)k * M + i] = s; } else dva[i - M] = s;
+#pragma unroll
+        for (int r = 0; r < RA; r++) {
+          const int i = base + r;
+          if (i >= M + nca) continue;
+          const double v = sa[r] + ((i < KROWS) ? sK[i * NR] : gK[i * NR]);
+          if (i < M) { z[N + i] = v; io.dus[(size_t)k * M + i] = v; } else dva[i - M] = v;
+        }
       }
     }
     PAR_FOR(i, N) z[i] = dx[i];
@@ -320,16 +345,30 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
       }
     }
     PAR_FOR(i, NZ) acc += sX[4 * N + i] * z[i];
-    WARP_ROW_FOR(i, N) { // dlam_{k+1} = pt + W z ; tmp = A dx + B du + fbar - mu_d dlam
-      double sl = 0, a = 0;
-      LANE_FOR(j, NZ) { const double zj = z[j]; sl += sW[i * NZ + j] * zj; a += sAB[i * NZ + j] * zj; }
-      sl = WARP_SUM(sl); a = WARP_SUM(a);
+    // dlam_{k+1} = pt + W z ; tmp = A dx + B du + fbar - mu_d dlam : RB rows per warp at a time
+    constexpr int RB = 7;
+    for (int base = WARP_ID * RB; base < N; base += NWARPS * RB) {
+      double sl[RB], sa[RB];
+#pragma unroll
+      for (int r = 0; r < RB; r++) { sl[r] = 0.0; sa[r] = 0.0; }
+      LANE_FOR(j, NZ) {
+        const double zj = z[j];
+#pragma unroll
+        for (int r = 0; r < RB; r++)
+          if (base + r < N) { sl[r] += sW[(base + r) * NZ + j] * zj; sa[r] += sAB[(base + r) * NZ + j] * zj; }
+      }
+#pragma unroll
+      for (int r = 0; r < RB; r++) { sl[r] = WARP_SUM(sl[r]); sa[r] = WARP_SUM(sa[r]); }
       if (LANE0) {
-        const double fbi = sX[N + i], lp = sX[2 * N + i], lm = sX[3 * N + i];
-        sl += sX[i];
-        tmp[i] = a + fbi - mu_d * sl;
-        io.dlams[(size_t)(k + 1) * N + i] = sl;
-        acc += (2.0 * lp - lm) * (mu_d * sl - fbi) - fbi * sl;
+#pragma unroll
+        for (int r = 0; r < RB; r++) {
+          const int i = base + r;
+          if (i >= N) continue;
+          const double fbi = sX[N + i], lp = sX[2 * N + i], lm = sX[3 * N + i], dl = sl[r] + sX[i];
+          tmp[i] = sa[r] + fbi - mu_d * dl;
+          io.dlams[(size_t)(k + 1) * N + i] = dl;
+          acc += (2.0 * lp - lm) * (mu_d * dl - fbi) - fbi * dl;
+        }
       }
     }
     SYNC();
