@@ -20,6 +20,9 @@
 #define WARP_FOR(i, n) for (int i = 0; i < (n); i++)
 #define WARP_SYNC() ((void)0)
 #define ATOMIC_INC(p) ((*(p))++)
+#define PAR_FOR_REST(i, n) for (int i = 0; i < (n); i++)
+#define WARP_TILE_FOR(p, n) for (int p = 0; p < (n); p++)
+#define WARP_TILE_FOR_REST(p, n) for (int p = 0; p < (n); p++)
 #define WARP_ROW_FOR(i, n) for (int i = 0; i < (n); i++)
 #define LANE_FOR(j, n) for (int j = 0; j < (n); j++)
 #define WARP_SUM(x) (x)
@@ -45,6 +48,12 @@ inline double2 make_double2(double x, double y) { return double2{x, y}; }
 #define WARP_FOR(i, n) for (int i = (threadIdx.x & 31); i < (n); i += 32)
 #define WARP_SYNC() __syncwarp()
 #define ATOMIC_INC(p) atomicAdd((p), 1)
+// work items over all threads except warp 0 (which runs a serial task in the same phase); whole CTA if it is a single warp
+#define PAR_FOR_REST(i, n) \
+  for (int i = (blockDim.x > 32) ? (int)threadIdx.x - 32 : (int)threadIdx.x; i >= 0 && i < (n); i += (blockDim.x > 32) ? blockDim.x - 32 : blockDim.x)
+// one 8 x 8 tile per warp: over all warps / over all warps except warp 0
+#define WARP_TILE_FOR(p, n) for (int p = (threadIdx.x >> 5); p < (n); p += (blockDim.x >> 5))
+#define WARP_TILE_FOR_REST(p, n) for (int p = (int)(threadIdx.x >> 5) - 1; p >= 0 && p < (n); p += (blockDim.x >> 5) - 1)
 // matrix-vector pattern: rows over warps, columns over lanes (coalesced / conflict-free), butterfly reduction
 #define WARP_ROW_FOR(i, n) for (int i = (threadIdx.x >> 5); i < (n); i += (blockDim.x >> 5))
 #define LANE_FOR(j, n) for (int j = (threadIdx.x & 31); j < (n); j += 32)
@@ -356,51 +365,65 @@ HD double fast_rsqrt(double a) {
   return rsqrt(a);
 #endif
 }
-HD void chol_blocked(double *A, int n, int ld, double *Dinv) {
+// ONE thread factors the bw x bw diagonal block at k0 and inverts it entirely in registers (fully unrolled, no barriers,
+// no shared-memory round trips on the dependency chain; rows/cols >= bw are padded with the identity).
+HD void chol_diag_block(double *A, int k0, int bw, int ld, double *Di) {
+  double L[CB][CB], X[CB][CB], dd[CB];
+#pragma unroll
+  for (int r = 0; r < CB; r++)
+#pragma unroll
+    for (int c = 0; c < CB; c++) L[r][c] = (c <= r) ? ((r < bw) ? A[(k0 + r) * ld + k0 + c] : ((r == c) ? 1.0 : 0.0)) : 0.0;
+#pragma unroll
+  for (int j = 0; j < CB; j++) {
+    const double d = fast_rsqrt(L[j][j]);
+    dd[j] = d;
+    L[j][j] = L[j][j] * d;
+#pragma unroll
+    for (int r = j + 1; r < CB; r++) L[r][j] *= d;
+#pragma unroll
+    for (int r = j + 1; r < CB; r++)
+#pragma unroll
+      for (int c = j + 1; c <= r; c++) L[r][c] -= L[r][j] * L[c][j];
+  }
+#pragma unroll
+  for (int c = 0; c < CB; c++)
+#pragma unroll
+    for (int r = 0; r < CB; r++) {
+      if (r < c) { X[r][c] = 0.0; continue; }
+      double s = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+      for (int t = c; t < r; t++) s -= L[r][t] * X[t][c];
+      X[r][c] = s * dd[r];
+    }
+#pragma unroll
+  for (int r = 0; r < CB; r++)
+#pragma unroll
+    for (int c = 0; c < CB; c++) {
+      if (r < bw && c <= r) A[(k0 + r) * ld + k0 + c] = L[r][c];
+      Di[r * CB + c] = (r < bw && c < bw) ? X[r][c] : 0.0;
+    }
+}
+// Blocked Cholesky (lower, in place): per 8-wide panel, one thread factors + inverts the diagonal block, the panel below it
+// is multiplied by the inverse, and the trailing matrix is updated on 2 x 2 register tiles.
+// LOOKAHEAD (used for the 56 x 56 Lambda of the Riccati kernel, 8 warps): after the panel solve the whole CTA first updates
+// only the NEXT panel's columns; then thread 0 factors the next diagonal block while the other warps finish the rest of the
+// trailing update, which takes part of the serial 8 x 8 factorisation off the critical path.  For small matrices / CTAs the
+// extra phase costs more than it hides, so the evaluation kernels keep the plain schedule.
+template <bool LOOKAHEAD = false> HD void chol_blocked(double *A, int n, int ld, double *Dinv) {
+  if (LOOKAHEAD) {
+    ONE_THREAD chol_diag_block(A, 0, (n < CB) ? n : CB, ld, Dinv);
+    SYNC();
+  }
   for (int k0 = 0; k0 < n; k0 += CB) {
     const int bw = (n - k0 < CB) ? n - k0 : CB;
-    double *Di = Dinv + (k0 / CB) * CB * CB;
-    // (a)+(b) ONE thread factors the bw x bw diagonal block and inverts it entirely in registers (fully unrolled, no
-    // barriers, no shared-memory round trips on the dependency chain; rows/cols >= bw are padded with the identity)
-    ONE_THREAD {
-      double L[CB][CB], X[CB][CB], dd[CB];
-#pragma unroll
-      for (int r = 0; r < CB; r++)
-#pragma unroll
-        for (int c = 0; c < CB; c++) L[r][c] = (c <= r) ? ((r < bw) ? A[(k0 + r) * ld + k0 + c] : ((r == c) ? 1.0 : 0.0)) : 0.0;
-#pragma unroll
-      for (int j = 0; j < CB; j++) {
-        const double d = fast_rsqrt(L[j][j]);
-        dd[j] = d;
-        L[j][j] = L[j][j] * d;
-#pragma unroll
-        for (int r = j + 1; r < CB; r++) L[r][j] *= d;
-#pragma unroll
-        for (int r = j + 1; r < CB; r++)
-#pragma unroll
-          for (int c = j + 1; c <= r; c++) L[r][c] -= L[r][j] * L[c][j];
-      }
-#pragma unroll
-      for (int c = 0; c < CB; c++)
-#pragma unroll
-        for (int r = 0; r < CB; r++) {
-          if (r < c) { X[r][c] = 0.0; continue; }
-          double s = (r == c) ? 1.0 : 0.0;
-#pragma unroll
-          for (int t = c; t < r; t++) s -= L[r][t] * X[t][c];
-          X[r][c] = s * dd[r];
-        }
-#pragma unroll
-      for (int r = 0; r < CB; r++)
-#pragma unroll
-        for (int c = 0; c < CB; c++) {
-          if (r < bw && c <= r) A[(k0 + r) * ld + k0 + c] = L[r][c];
-          Di[r * CB + c] = (r < bw && c < bw) ? X[r][c] : 0.0;
-        }
+    const double *Di = Dinv + (k0 / CB) * CB * CB;
+    if (!LOOKAHEAD) {
+      ONE_THREAD chol_diag_block(A, k0, bw, ld, Dinv + (k0 / CB) * CB * CB);
+      SYNC();
     }
-    SYNC();
-    // (c) panel below the diagonal block: L[i, k0:k0+bw] = A[i, k0:k0+bw] * Dinv^T, one row per work item
+    // panel below the diagonal block: L[i, k0:k0+bw] = A[i, k0:k0+bw] * Dinv^T, one row per work item
     const int rem = n - k0 - bw, r0 = k0 + bw;
+    if (rem <= 0) break;
     PAR_FOR(i, rem) {
       double *row = A + (r0 + i) * ld + k0;
       double v[CB], o[CB];
@@ -414,22 +437,41 @@ HD void chol_blocked(double *A, int n, int ld, double *Dinv) {
       for (int q = 0; q < CB; q++) if (q < bw) row[q] = o[q];
     }
     SYNC();
-    // (d) trailing update on 2 x 2 tiles of the lower triangle
-    const int th = (rem + 1) / 2;
-    PAR_FOR(t, th * th) {
-      int ti = t / th, tj = t % th;
-      if (tj > ti) continue;
-      int i0 = r0 + 2 * ti, j0 = r0 + 2 * tj;
-      double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
-      bool i1 = i0 + 1 < n, j1 = j0 + 1 < n;
-      for (int q = 0; q < bw; q++) {
-        double li0 = A[i0 * ld + k0 + q], li1 = i1 ? A[(i0 + 1) * ld + k0 + q] : 0.0;
-        double lj0 = A[j0 * ld + k0 + q], lj1 = j1 ? A[(j0 + 1) * ld + k0 + q] : 0.0;
-        a00 += li0 * lj0; a01 += li0 * lj1; a10 += li1 * lj0; a11 += li1 * lj1;
+    int r1 = r0; // first row / column of the part updated on 2 x 2 tiles
+    if (LOOKAHEAD) {
+      // critical part of the trailing update: the next panel's columns [r0, r0 + bwn)
+      const int bwn = (rem < CB) ? rem : CB;
+      PAR_FOR(e, rem * bwn) {
+        const int i = r0 + e / bwn, j = r0 + e % bwn;
+        if (j > i) continue;
+        double s = 0;
+        for (int q = 0; q < bw; q++) s += A[i * ld + k0 + q] * A[j * ld + k0 + q];
+        A[i * ld + j] -= s;
       }
-      A[i0 * ld + j0] -= a00;
-      if (j1 && j0 + 1 <= i0) A[i0 * ld + j0 + 1] -= a01;
-      if (i1) { A[(i0 + 1) * ld + j0] -= a10; if (j1) A[(i0 + 1) * ld + j0 + 1] -= a11; }
+      SYNC();
+      ONE_THREAD chol_diag_block(A, r0, bwn, ld, Dinv + (r0 / CB) * CB * CB);
+      r1 = r0 + bwn;
+    }
+    const int rem2 = n - r1;
+    if (rem2 > 0) {
+      const int th = (rem2 + 1) / 2;
+      auto tile = [&](int t) {
+        int ti = t / th, tj = t % th;
+        if (tj > ti) return;
+        int i0 = r1 + 2 * ti, j0 = r1 + 2 * tj;
+        double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
+        bool i1 = i0 + 1 < n, j1 = j0 + 1 < n;
+        for (int q = 0; q < bw; q++) {
+          double li0 = A[i0 * ld + k0 + q], li1 = i1 ? A[(i0 + 1) * ld + k0 + q] : 0.0;
+          double lj0 = A[j0 * ld + k0 + q], lj1 = j1 ? A[(j0 + 1) * ld + k0 + q] : 0.0;
+          a00 += li0 * lj0; a01 += li0 * lj1; a10 += li1 * lj0; a11 += li1 * lj1;
+        }
+        A[i0 * ld + j0] -= a00;
+        if (j1 && j0 + 1 <= i0) A[i0 * ld + j0 + 1] -= a01;
+        if (i1) { A[(i0 + 1) * ld + j0] -= a10; if (j1) A[(i0 + 1) * ld + j0 + 1] -= a11; }
+      };
+      if (LOOKAHEAD) { PAR_FOR_REST(t, th * th) tile(t); }
+      else { PAR_FOR(t, th * th) tile(t); }
     }
     SYNC();
   }

@@ -78,4 +78,71 @@ HD void mma_tn(int mt, int nt, int K, const double *A, int lda, const double *B,
   SYNC();
 }
 
+// ---- warp-level 8 x 8 tile kernels of the tensor-core Cholesky (all operands inside one row-major matrix A, leading dim ld)
+// C(i0.., j0..) -= L(i0.., k0..k0+8) * L(j0.., k0..k0+8)^T
+HD void tile_syrk(double *A, int ld, int i0, int j0, int k0) {
+#ifdef MPC_HOST_EMU
+  for (int r = 0; r < 8; r++)
+    for (int c = 0; c < 8; c++) {
+      double s = 0;
+      for (int q = 0; q < 8; q++) s += A[(i0 + r) * ld + k0 + q] * A[(j0 + c) * ld + k0 + q];
+      A[(i0 + r) * ld + j0 + c] -= s;
+    }
+#else
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const double *ar = A + (i0 + g) * ld + k0 + t, *br = A + (j0 + g) * ld + k0 + t;
+  const double a0 = -ar[0], a1 = -ar[4], b0 = br[0], b1 = br[4];
+  double2 *cp = reinterpret_cast<double2 *>(A + (i0 + g) * ld + j0 + 2 * t);
+  double2 c = *cp;
+  dmma_8x8x4(c.x, c.y, a0, b0);
+  dmma_8x8x4(c.x, c.y, a1, b1);
+  *cp = c;
+#endif
+}
+// L(i0.., k0..k0+8) = A(i0.., k0..k0+8) * Di^T   (Di: 8 x 8 row-major inverse of the diagonal block's factor), in place
+HD void tile_trsm(double *A, int ld, int i0, int k0, const double *Di) {
+#ifdef MPC_HOST_EMU
+  for (int r = 0; r < 8; r++) {
+    double o[8];
+    for (int c = 0; c < 8; c++) { double s = 0; for (int q = 0; q <= c; q++) s += A[(i0 + r) * ld + k0 + q] * Di[c * 8 + q]; o[c] = s; }
+    for (int c = 0; c < 8; c++) A[(i0 + r) * ld + k0 + c] = o[c];
+  }
+#else
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const double *ar = A + (i0 + g) * ld + k0 + t;
+  const double a0 = ar[0], a1 = ar[4], b0 = Di[g * 8 + t], b1 = Di[g * 8 + 4 + t];
+  double2 c = make_double2(0.0, 0.0);
+  dmma_8x8x4(c.x, c.y, a0, b0);
+  dmma_8x8x4(c.x, c.y, a1, b1);
+  __syncwarp();
+  *reinterpret_cast<double2 *>(A + (i0 + g) * ld + k0 + 2 * t) = c;
+#endif
+}
+
+// Tensor-core blocked Cholesky (lower, in place) for n = 8 NB with a one-panel lookahead: per panel the tiles below the
+// diagonal block are solved (one warp per tile), the next panel's column of tiles is updated, then thread 0 factors and
+// inverts the next diagonal block in registers while warps 1.. update the remaining tiles of the trailing matrix.
+// Only the lower triangle (and the full diagonal tiles) of A is referenced; Dinv receives the NB inverses of the diagonal blocks.
+template <int NB> HD void chol_mma(double *A, int ld, double *Dinv) {
+  ONE_THREAD chol_diag_block(A, 0, 8, ld, Dinv);
+  SYNC();
+  for (int kb = 0; kb + 1 < NB; kb++) {
+    const int k0 = 8 * kb, nt = NB - 1 - kb;
+    const double *Di = Dinv + 64 * kb;
+    WARP_TILE_FOR(p, nt) tile_trsm(A, ld, 8 * (kb + 1 + p), k0, Di);
+    SYNC();
+    WARP_TILE_FOR(p, nt) tile_syrk(A, ld, 8 * (kb + 1 + p), 8 * (kb + 1), k0);
+    SYNC();
+    ONE_THREAD chol_diag_block(A, 8 * (kb + 1), 8, ld, Dinv + 64 * (kb + 1));
+    const int m = nt - 1;
+    WARP_TILE_FOR_REST(p, m * (m + 1) / 2) {
+      int ti = 0;
+      while ((ti + 1) * (ti + 2) / 2 <= p) ti++;
+      const int tj = p - ti * (ti + 1) / 2;
+      tile_syrk(A, ld, 8 * (kb + 2 + ti), 8 * (kb + 2 + tj), k0);
+    }
+    SYNC();
+  }
+}
+
 } // namespace mpcdev

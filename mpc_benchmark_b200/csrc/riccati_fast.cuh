@@ -121,7 +121,7 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
     PAR_FOR(i, N) { double s = p[i]; for (int j = 0; j < N; j++) s += P[i * LDN + j] * fb[j]; pv[i] = s; }
     SYNC();
     PHASE(1);
-    chol_blocked(G, N, LDN, dinv);
+    chol_mma<NBLK>(G, LDN, dinv);
     PHASE(2);
     // 3. Linv = G^-1 (lower triangular): independent forward-substitution chains, one per 8-column block and warp
     {
