@@ -385,16 +385,19 @@ HD void chol_diag_block(double *A, int k0, int bw, int ld, double *Di) {
 #pragma unroll
       for (int c = j + 1; c <= r; c++) L[r][c] -= L[r][j] * L[c][j];
   }
+  // X = L^-1 column by column in right-looking order: as soon as X[t][c] is known it is folded into the partial sums of the
+  // rows below, so the dependent chain per row is one multiply + one FMA (the 8 columns are independent chains)
 #pragma unroll
-  for (int c = 0; c < CB; c++)
+  for (int c = 0; c < CB; c++) {
 #pragma unroll
-    for (int r = 0; r < CB; r++) {
-      if (r < c) { X[r][c] = 0.0; continue; }
-      double s = (r == c) ? 1.0 : 0.0;
+    for (int r = 0; r < CB; r++) X[r][c] = (r == c) ? 1.0 : 0.0;
 #pragma unroll
-      for (int t = c; t < r; t++) s -= L[r][t] * X[t][c];
-      X[r][c] = s * dd[r];
+    for (int t = c; t < CB; t++) {
+      X[t][c] *= dd[t];
+#pragma unroll
+      for (int r = t + 1; r < CB; r++) X[r][c] -= L[r][t] * X[t][c];
     }
+  }
 #pragma unroll
   for (int r = 0; r < CB; r++)
 #pragma unroll

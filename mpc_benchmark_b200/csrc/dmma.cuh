@@ -23,8 +23,10 @@ __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, dou
 //   init: 0 (Cinit == nullptr) or Cinit (ldci) restricted to rows < vr and cols < vc (zero outside) — lets the
 //   Hessian update read H_k straight from global memory while keeping the shared copy zero-padded.
 // upper_only: skip tiles strictly below the block diagonal (caller mirrors).
+// lower_tri_operands: A and B are lower-triangular K x K matrices (A[k][i] = 0 for k < i): the k-loop of tile (i, j) starts at
+// 8 max(i, j) — exact, it only skips products with structural zeros.
 HD void mma_tn(int mt, int nt, int K, const double *A, int lda, const double *B, int ldb, double *C, int ldc, const double *Cinit, int ldci,
-               int vr, int vc, bool upper_only) {
+               int vr, int vc, bool upper_only, bool lower_tri_operands = false) {
 #ifdef MPC_HOST_EMU
   for (int i = 0; i < 8 * mt; i++)
     for (int j = 0; j < 8 * nt; j++) {
@@ -58,7 +60,7 @@ HD void mma_tn(int mt, int nt, int K, const double *A, int lda, const double *B,
     const double *bp = B + t * ldb + tj * 8 + g;
     const int ao = r2 ? 8 : 0, bo = c2 ? 8 : 0; // out-of-range partner tiles recompute tile 0 (discarded)
 #pragma unroll 2
-    for (int k0 = 0; k0 < K; k0 += 4) {
+    for (int k0 = lower_tri_operands ? 8 * (ti > tj ? ti : tj) : 0; k0 < K; k0 += 4) {
       const double a0 = ap[k0 * lda], a1 = ap[k0 * lda + ao], b0 = bp[k0 * ldb], b1 = bp[k0 * ldb + bo];
       dmma_8x8x4(c[0][0][0], c[0][0][1], a0, b0);
       dmma_8x8x4(c[0][1][0], c[0][1][1], a0, b1);

@@ -128,34 +128,57 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
 #ifdef MPC_HOST_EMU
       for (int jb = 0; jb < NBLK; jb++) {
         double *tt = wtmp;
-#else
-      for (int jb = (threadIdx.x >> 5); jb < NBLK; jb += (blockDim.x >> 5)) {
-        double *tt = wtmp + 64 * (threadIdx.x >> 5);
-#endif
         for (int ib = jb; ib < NBLK; ib++) {
-          WARP_FOR(e, 64) { // tt = E_ij - sum_k L_ik X_kj
+          for (int e = 0; e < 64; e++) { // tt = E_ij - sum_k L_ik X_kj
             int r = e >> 3, c = e & 7;
             double s = (ib == jb && r == c) ? 1.0 : 0.0;
             for (int kb = jb; kb < ib; kb++)
               for (int q = 0; q < 8; q++) s -= G[(8 * ib + r) * LDN + 8 * kb + q] * Li[(8 * kb + q) * LDN + 8 * jb + c];
             tt[e] = s;
           }
-          WARP_SYNC();
-          WARP_FOR(e, 64) { // X_ij = Dinv_i tt
+          for (int e = 0; e < 64; e++) { // X_ij = Dinv_i tt
             int r = e >> 3, c = e & 7;
             const double *Di = dinv + 64 * ib;
             double s = 0;
             for (int q = 0; q <= r; q++) s += Di[r * 8 + q] * tt[q * 8 + c];
             Li[(8 * ib + r) * LDN + 8 * jb + c] = s;
           }
-          WARP_SYNC();
         }
       }
+#else
+      // one warp per block column jb; every 8 x 8 tile product runs on the DMMA pipe:
+      //   X_jj = Dinv_j ,  X_ij = -Dinv_i (sum_{k=j}^{i-1} L_ik X_kj)
+      const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+      for (int jb = (threadIdx.x >> 5); jb < NBLK; jb += (blockDim.x >> 5)) {
+        double *tt = wtmp + 64 * (threadIdx.x >> 5);
+        for (int ib = jb; ib < NBLK; ib++) {
+          const double *Di = dinv + 64 * ib;
+          if (ib == jb) {
+            for (int e = lane; e < 64; e += 32) Li[(8 * ib + (e >> 3)) * LDN + 8 * jb + (e & 7)] = Di[e];
+          } else {
+            double c0 = 0.0, c1 = 0.0;
+            for (int kb = jb; kb < ib; kb++) {
+              const double *pa = G + (8 * ib + g) * LDN + 8 * kb + t;  // L_ik [g][t]
+              const double *pb = Li + (8 * kb + t) * LDN + 8 * jb + g; // X_kj [t][g]
+              dmma_8x8x4(c0, c1, pa[0], pb[0]);
+              dmma_8x8x4(c0, c1, pa[4], pb[4 * LDN]);
+            }
+            *reinterpret_cast<double2 *>(tt + g * 8 + 2 * t) = make_double2(c0, c1);
+            __syncwarp();
+            double d0 = 0.0, d1 = 0.0;
+            dmma_8x8x4(d0, d1, Di[g * 8 + t], tt[t * 8 + g]);
+            dmma_8x8x4(d0, d1, Di[g * 8 + 4 + t], tt[(4 + t) * 8 + g]);
+            *reinterpret_cast<double2 *>(Li + (8 * ib + g) * LDN + 8 * jb + 2 * t) = make_double2(-d0, -d1);
+          }
+          __syncwarp();
+        }
+      }
+#endif
       SYNC();
     }
     PHASE(3);
     // 4. Lambda^-1 = Linv' Linv (into G);  5. Pt = Lambda^-1 P (into Li), pt = Lambda^-1 pv
-    mma_tn(NBLK, NBLK, N, Li, LDN, Li, LDN, G, LDN, nullptr, 0, 0, 0, false);
+    mma_tn(NBLK, NBLK, N, Li, LDN, Li, LDN, G, LDN, nullptr, 0, 0, 0, false, true);
     PAR_FOR(i, N) { double s = 0; for (int j = 0; j < N; j++) s += G[i * LDN + j] * pv[j]; pt[i] = s; }
     mma_tn(NBLK, NBLK, N, G, LDN, P, LDN, Li, LDN, nullptr, 0, 0, 0, false);
     PHASE(4);
