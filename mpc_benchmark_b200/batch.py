@@ -35,6 +35,14 @@ class BatchResults:
     def traj_cost(self):
         return np.array([i.traj_cost for i in self.info])
 
+    @property
+    def ls_evals(self):
+        return np.array([i.ls_evals for i in self.info])
+
+    @property
+    def alpha(self):
+        return np.array([i.alpha for i in self.info])
+
 
 class BatchSolver:
     def __init__(self, robot, cfg, batch, device=0, **_unused):

@@ -40,7 +40,10 @@ inline double2 make_double2(double x, double y) { return double2{x, y}; }
 #else
 #define HD __device__ __forceinline__
 #define PAR_FOR(i, n) for (int i = threadIdx.x; i < (n); i += blockDim.x)
-#define SYNC() __syncthreads()
+// A CTA holds blockDim.y independent GROUPS of blockDim.x threads (one work item each; evaluation kernels: one knot per
+// group, several knots per CTA so that the groups run the same code side by side and share instruction fetches).  All
+// cooperative phases are per group: work is spread over threadIdx.x and SYNC() is the group's own named barrier.
+#define SYNC() asm volatile("bar.sync %0, %1;" ::"r"((int)threadIdx.y + 1), "r"((int)blockDim.x) : "memory")
 #define ONE_THREAD if (threadIdx.x == 0)
 #define TID ((int)threadIdx.x)
 #define NTHREADS ((int)blockDim.x)

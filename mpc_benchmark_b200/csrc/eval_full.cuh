@@ -20,7 +20,7 @@ namespace mpcdev {
 // optional per-phase cycle counters of the evaluation kernel (-DMPC_PHASE_TIMING builds; knot 1 of instance 0)
 #if defined(MPC_PHASE_TIMING) && !defined(MPC_HOST_EMU)
 #define EPH_DECL long long eph_last = clock64(); long long eph_acc[16] = {0}
-#define EPH(i) do { __syncthreads(); if (threadIdx.x == 0) { long long t_ = clock64(); eph_acc[i] += t_ - eph_last; eph_last = t_; } } while (0)
+#define EPH(i) do { SYNC(); if (threadIdx.x == 0) { long long t_ = clock64(); eph_acc[i] += t_ - eph_last; eph_last = t_; } } while (0)
 #define EPH_DUMP(ptr) do { if (threadIdx.x == 0 && (ptr)) for (int i_ = 0; i_ < 16; i_++) (ptr)[i_] = (double)eph_acc[i_]; } while (0)
 #else
 #define EPH_DECL

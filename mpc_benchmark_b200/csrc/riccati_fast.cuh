@@ -14,7 +14,7 @@ namespace mpcdev {
 // optional per-phase cycle counters (thread 0 of the CTA handling instance 0), enabled with -DMPC_PHASE_TIMING
 #if defined(MPC_PHASE_TIMING) && !defined(MPC_HOST_EMU)
 #define PHASE_DECL long long ph_last = clock64(); long long ph_acc[32] = {0}
-#define PHASE(i) do { __syncthreads(); if (threadIdx.x == 0) { long long t_ = clock64(); ph_acc[i] += t_ - ph_last; ph_last = t_; } } while (0)
+#define PHASE(i) do { SYNC(); if (threadIdx.x == 0) { long long t_ = clock64(); ph_acc[i] += t_ - ph_last; ph_last = t_; } } while (0)
 #define PHASE_DUMP(ptr) do { if (threadIdx.x == 0 && (ptr)) for (int i_ = 0; i_ < 16; i_++) { (ptr)[i_] = (double)ph_acc[i_]; (ptr)[48 + i_] = (double)ph_acc[16 + i_]; } } while (0)
 #else
 #define PHASE_DECL

@@ -31,13 +31,35 @@ static int fail(const std::string &m) { g_err = m; return 1; }
 __global__ void k_init(Ws w, const double *xs_in, const double *us_in, int max_iters) { init_instance(w, blockIdx.x, xs_in, us_in, max_iters); }
 
 #ifndef MPC_VALUES_CTAS
-#define MPC_VALUES_CTAS 4
+#define MPC_VALUES_CTAS 4 /* values-only knots resident per SM */
 #endif
-template <int KIND, bool DERIV> __global__ void __launch_bounds__(128, DERIV ? 3 : MPC_VALUES_CTAS) k_eval(Ws w, const int32_t *list) {
+#ifndef MPC_VALUES_G
+#define MPC_VALUES_G 2 /* of which per CTA */
+#endif
+// Evaluation kernel launch shape: G knots per CTA (one group of TH threads each, own shared-memory slice and named barrier).
+// The groups of a CTA start together and run the same instruction stream, which is what keeps the (large, mostly
+// straight-line) evaluation code from being fetched G times per SM: ncu showed 59 % instruction-cache hits and
+// "no instruction" as the second stall reason with one knot per CTA.
+template <int KIND, bool DERIV> struct EvalShape {
+  static constexpr int TH = (KIND == MPC_KIND_CENT) ? 32 : 128;
+  static constexpr int G = (KIND == MPC_KIND_CENT) ? 4 : (DERIV ? 3 : MPC_VALUES_G);           // knots per CTA
+  static constexpr int CTAS = (KIND == MPC_KIND_CENT || DERIV) ? 1 : MPC_VALUES_CTAS / MPC_VALUES_G; // CTAs per SM
+  static constexpr size_t raw = (KIND == MPC_KIND_FULL) ? sizeof(FullWsT<DERIV>) : (KIND == MPC_KIND_KINO) ? sizeof(KinoWsT<DERIV>) : sizeof(CentWs);
+  static constexpr size_t slice = (raw + 15) / 16 * 16;
+  static_assert(G * slice <= 232448, "evaluation groups exceed the 227 KB opt-in shared memory");
+};
+template <int KIND, bool DERIV> __global__ void __launch_bounds__(EvalShape<KIND, DERIV>::TH * EvalShape<KIND, DERIV>::G, EvalShape<KIND, DERIV>::CTAS)
+k_eval(Ws w, const int32_t *list, int nitems) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int T1 = w.T + 1;
-  const int b = list[blockIdx.x / T1], k = blockIdx.x % T1;
-  eval_dispatch<KIND, DERIV>(w, b, k, smem_raw);
+  const int item = blockIdx.x * EvalShape<KIND, DERIV>::G + threadIdx.y;
+  if (item >= nitems) return;
+  const int b = list[item / T1], k = item % T1;
+  eval_dispatch<KIND, DERIV>(w, b, k, smem_raw + threadIdx.y * EvalShape<KIND, DERIV>::slice);
+}
+template <int KIND, bool DERIV> static void launch_eval(const Ws &w, const int32_t *list, int nitems, cudaStream_t s) {
+  using Sh = EvalShape<KIND, DERIV>;
+  k_eval<KIND, DERIV><<<(nitems + Sh::G - 1) / Sh::G, dim3(Sh::TH, Sh::G), Sh::G * Sh::slice, s>>>(w, list, nitems);
 }
 
 __global__ void k_decide_eval(Ws w, const int32_t *list, int32_t *next_eval) {
@@ -122,17 +144,15 @@ struct CudaBackend {
   }
   void reset_counters() { mark(3); cudaMemsetAsync(h->w.counters, 0, 4 * sizeof(int32_t), s); }
   void eval(bool d, const int32_t *list, int n) {
-    const int grid = n * (h->w.T + 1);
+    const int nitems = n * (h->w.T + 1);
     mark(d ? 0 : 2);
-    const int th = h->eval_threads;
-    const size_t sm = d ? h->eval_smem : h->eval_smem_values;
     switch (h->w.kind * 2 + (d ? 1 : 0)) {
-    case MPC_KIND_FULL * 2 + 1: k_eval<MPC_KIND_FULL, true><<<grid, th, sm, s>>>(h->w, list); break;
-    case MPC_KIND_FULL * 2 + 0: k_eval<MPC_KIND_FULL, false><<<grid, th, sm, s>>>(h->w, list); break;
-    case MPC_KIND_KINO * 2 + 1: k_eval<MPC_KIND_KINO, true><<<grid, th, sm, s>>>(h->w, list); break;
-    case MPC_KIND_KINO * 2 + 0: k_eval<MPC_KIND_KINO, false><<<grid, th, sm, s>>>(h->w, list); break;
-    case MPC_KIND_CENT * 2 + 1: k_eval<MPC_KIND_CENT, true><<<grid, th, sm, s>>>(h->w, list); break;
-    default: k_eval<MPC_KIND_CENT, false><<<grid, th, sm, s>>>(h->w, list); break;
+    case MPC_KIND_FULL * 2 + 1: launch_eval<MPC_KIND_FULL, true>(h->w, list, nitems, s); break;
+    case MPC_KIND_FULL * 2 + 0: launch_eval<MPC_KIND_FULL, false>(h->w, list, nitems, s); break;
+    case MPC_KIND_KINO * 2 + 1: launch_eval<MPC_KIND_KINO, true>(h->w, list, nitems, s); break;
+    case MPC_KIND_KINO * 2 + 0: launch_eval<MPC_KIND_KINO, false>(h->w, list, nitems, s); break;
+    case MPC_KIND_CENT * 2 + 1: launch_eval<MPC_KIND_CENT, true>(h->w, list, nitems, s); break;
+    default: launch_eval<MPC_KIND_CENT, false>(h->w, list, nitems, s); break;
     }
   }
   void decide_eval(const int32_t *list, int n, int32_t *next_eval) { mark(3); k_decide_eval<<<n, 128, 0, s>>>(h->w, list, next_eval); }
@@ -160,10 +180,10 @@ static int set_kernel_attrs(mpc_solver *h) {
   if (const char *e = getenv("MPCB200_RIC_THREADS")) { int t = atoi(e); if (t >= 32 && t <= 256 && h->w.kind != MPC_KIND_CENT) h->ric_threads = t; }
   static_assert(RicFastLayout<56, 22, 78>::total * 8 <= 232448 && RicFastLayout<56, 34, 68, KINO_NCAP>::total * 8 <= 232448,
                 "Riccati shared memory exceeds the 227 KB opt-in limit");
-  CK(cudaFuncSetAttribute(k_eval<MPC_KIND_FULL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FullWsT<true>)));
-  CK(cudaFuncSetAttribute(k_eval<MPC_KIND_FULL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FullWsT<false>)));
-  CK(cudaFuncSetAttribute(k_eval<MPC_KIND_KINO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KinoWsT<true>)));
-  CK(cudaFuncSetAttribute(k_eval<MPC_KIND_KINO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KinoWsT<false>)));
+#define EVAL_ATTR(KIND, D) CK(cudaFuncSetAttribute(k_eval<KIND, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EvalShape<KIND, D>::G * EvalShape<KIND, D>::slice)))
+  EVAL_ATTR(MPC_KIND_FULL, true); EVAL_ATTR(MPC_KIND_FULL, false); EVAL_ATTR(MPC_KIND_KINO, true); EVAL_ATTR(MPC_KIND_KINO, false);
+  EVAL_ATTR(MPC_KIND_CENT, true); EVAL_ATTR(MPC_KIND_CENT, false);
+#undef EVAL_ATTR
   CK(cudaFuncSetAttribute(k_riccati<MPC_KIND_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, RicFastLayout<56, 22, 78>::total * 8));
   CK(cudaFuncSetAttribute(k_riccati<MPC_KIND_KINO>, cudaFuncAttributeMaxDynamicSharedMemorySize, RicFastLayout<56, 34, 68, KINO_NCAP>::total * 8));
   return 0;
