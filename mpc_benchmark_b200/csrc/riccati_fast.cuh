@@ -31,22 +31,24 @@ template <int N, int M, int NC, int NCAP = NC> struct RicFastLayout {
   static constexpr int LDH = ZP;                                    // ld of the Hessian buffer
   static_assert(N * LDZ <= 2 * N * LDN, "W must fit over the dead [P | G] buffers");
   static constexpr int phase1 = 3 * N * LDN + N * LDZ;  // P, G (later reused as W), Li, AB
-  static constexpr int MP = (M + 3) / 4 * 4;                        // Z rows padded to the DMMA k-step (zero rows)
-  static constexpr int phase2 = NCAP * NZ + NCAP * NCAP + MP * (NR + NCAP) + NCAP * NR + M * M; // sized for NCAP active rows
+  static constexpr int MR = (M + 7) / 8 * 8;                        // control block padded to whole 8 x 8 tiles (identity / zero padding)
+  static constexpr int LDR = (MR % 16 == 8) ? MR : MR + 8;          // ld of the padded R^ buffer
+  static constexpr int LDZMAX = (NR + NCAP + 7) / 8 * 8;            // ld of Z for NCAP active rows (runtime ld: round8(NR + nca))
+  static constexpr int phase2 = NCAP * NZ + NCAP * NCAP + MR * LDZMAX + NCAP * NR + MR * LDR; // sized for NCAP active rows
   static constexpr int un = phase1 > phase2 ? phase1 : phase2;
   // phase-2 order [Z | Kv | Rh | CD | Sg]; [A B] sits at the END of the union so that knots with few active rows never
   // touch it in phase 2 and the next knot's [A B] can be prefetched early
-  static constexpr int offKv = MP * (NR + NCAP), offRh = offKv + NCAP * NR, offCD = offRh + M * M, offSg = offCD + NCAP * NZ;
+  static constexpr int offKv = MR * LDZMAX, offRh = offKv + NCAP * NR, offCD = offRh + MR * LDR, offSg = offCD + NCAP * NZ;
   static constexpr int offAB = un - N * LDZ;
   static_assert(offAB >= 3 * N * LDN, "[A B] overlaps P / G / Li");
   static_assert(un % 2 == 0 && offAB % 2 == 0 && (ZP * LDH) % 2 == 0, "16-byte alignment of the cp.async destinations");
-  static constexpr int vecs = 8 * ZP + 36 + 2 * NC + 256 + 64 * ((NC + 7) / 8) + 8 * 64 + 16;
+  static constexpr int vecs = 8 * ZP + 36 + 2 * NC + 64 * ((NC + 7) / 8) + 8 * 64 + 16; // the final reduction reuses wtmp
   static constexpr int total = ZP * LDH + un + vecs;
 };
 
 template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(const RiccatiIO &io, double *ws) {
   using Lay = RicFastLayout<N, M, NC, NCAP>;
-  constexpr int NZ = Lay::NZ, NR = Lay::NR, S = Lay::S, ZP = Lay::ZP, LDN = Lay::LDN, LDZ = Lay::LDZ, LDH = Lay::LDH, NBLK = Lay::NBLK, MP = Lay::MP;
+  constexpr int NZ = Lay::NZ, NR = Lay::NR, S = Lay::S, ZP = Lay::ZP, LDN = Lay::LDN, LDZ = Lay::LDZ, LDH = Lay::LDH, NBLK = Lay::NBLK, MR = Lay::MR, LDR = Lay::LDR;
   static_assert(N % 8 == 0, "fast Riccati needs n % 8 == 0");
   const int T = io.T;
   const double mu = io.mu, mu_d = io.mu_d;
@@ -58,7 +60,7 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
   double *Z = U0, *Kv = U0 + Lay::offKv, *Rh = U0 + Lay::offRh, *CD = U0 + Lay::offCD, *Sg = U0 + Lay::offSg;  // phase 2
   double *vec = U0 + Lay::un;
   double *p = vec, *pt = p + ZP, *gh = pt + ZP, *fb = gh + ZP, *tmp = fb + ZP, *dx = tmp + ZP, *z = dx + ZP, *pv = z + ZP;
-  double *T6 = pv + ZP, *dbr = T6 + 36, *dva = dbr + NC, *red = dva + NC, *dinv = red + 256, *wtmp = dinv + 64 * ((NC + 7) / 8);
+  double *T6 = pv + ZP, *dbr = T6 + 36, *dva = dbr + NC, *dinv = dva + NC, *wtmp = dinv + 64 * ((NC + 7) / 8), *red = wtmp;  // (red: one slot per thread, <= 512 threads)
   // ---- zero the padding of H once; terminal value function: P = H_T[xx] + C'C/mu, p = g_T[x] + C' d/mu
   PAR_FOR(e, ZP * LDH) H[e] = 0.0;
   SYNC();
@@ -201,34 +203,100 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
     if (k > 0 && early) stage_AB_async(k - 1);
     PHASE(5);
     // 8. KKT by block elimination (phase-2 buffers alias P/G/Li/AB/W, all dead now)
-    const int ncol = NR + nca; // Z columns: [rh | Sh' | D']
+    const int ncol = NR + nca, ldz = (ncol + 7) & ~7; // Z columns: [rh | Sh' | D'], padded with zero columns to whole tiles
     const double *gCD = io.CDact + (size_t)k * NC * NZ;
     const int32_t *ai = io.act_idx + (size_t)k * NC;
     PAR_FOR(e, nca * NZ) CD[e] = gCD[e];
     PAR_FOR(r, nca) dbr[r] = io.dbar[(size_t)k * NC + ai[r]];
-    PAR_FOR(e, M * M) { int i = e / M, j = e % M; Rh[e] = 0.5 * (H[(N + i) * LDH + N + j] + H[(N + j) * LDH + N + i]); }
-    SYNC();
-    PAR_FOR(e, M * ncol) {
-      int i = e / ncol, c = e % ncol;
-      Z[i * ncol + c] = (c == 0) ? gh[N + i] : (c < NR ? H[(c - 1) * LDH + N + i] : CD[(c - NR) * NZ + N + i]);
+    PAR_FOR(e, MR * MR) { // R^ = sym(H_uu), padded with the identity to MR x MR
+      int i = e / MR, j = e % MR;
+      Rh[i * LDR + j] = (i < M && j < M) ? 0.5 * (H[(N + i) * LDH + N + j] + H[(N + j) * LDH + N + i]) : ((i == j) ? 1.0 : 0.0);
     }
-    PAR_FOR(e, (MP - M) * ncol) Z[M * ncol + e] = 0.0; // zero rows up to the DMMA k-step (value update below)
+    SYNC();
+    PAR_FOR(e, MR * ldz) {
+      int i = e / ldz, c = e % ldz;
+      Z[e] = (i >= M || c >= ncol) ? 0.0 : ((c == 0) ? gh[N + i] : (c < NR ? H[(c - 1) * LDH + N + i] : CD[(c - NR) * NZ + N + i]));
+    }
     SYNC();
     PHASE(6);
-    chol_blocked(Rh, M, M, dinv);
+#ifdef MPC_HOST_EMU
+    chol_blocked(Rh, MR, LDR, dinv);
+    trsm_blocked(Rh, MR, LDR, dinv, Z, ncol, ldz);
+#else
+    // Z <- R^-1 Z on the tensor pipe: blocked Cholesky, in-place inverse X = L^-1 of the factor (one warp, block columns
+    // left to right: column j only needs the columns >= j of L), then Z <- X Z (tile rows bottom-up) and Z <- X' Z (top-down),
+    // both in place with one warp per 8-column tile of Z
+    chol_mma<MR / 8>(Rh, LDR, dinv);
     PHASE(7);
-    trsm_blocked(Rh, M, M, dinv, Z, ncol, ncol);
+    {
+      constexpr int NBR = MR / 8;
+      const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+      if (warp == 0) {
+        for (int jb = 0; jb < NBR; jb++) {
+          for (int e = lane; e < 64; e += 32) Rh[(8 * jb + (e >> 3)) * LDR + 8 * jb + (e & 7)] = dinv[64 * jb + e];
+          __syncwarp();
+          for (int ib = jb + 1; ib < NBR; ib++) {
+            double c0 = 0.0, c1 = 0.0;
+            for (int kb = jb; kb < ib; kb++) {
+              const double *pa = Rh + (8 * ib + g) * LDR + 8 * kb + t; // L_ik [g][t]
+              const double *pb = Rh + (8 * kb + t) * LDR + 8 * jb + g; // X_kj [t][g]
+              dmma_8x8x4(c0, c1, pa[0], pb[0]);
+              dmma_8x8x4(c0, c1, pa[4], pb[4 * LDR]);
+            }
+            double *tt = wtmp;
+            *reinterpret_cast<double2 *>(tt + g * 8 + 2 * t) = make_double2(c0, c1);
+            __syncwarp();
+            const double *Di = dinv + 64 * ib;
+            double d0 = 0.0, d1 = 0.0;
+            dmma_8x8x4(d0, d1, Di[g * 8 + t], tt[t * 8 + g]);
+            dmma_8x8x4(d0, d1, Di[g * 8 + 4 + t], tt[(4 + t) * 8 + g]);
+            *reinterpret_cast<double2 *>(Rh + (8 * ib + g) * LDR + 8 * jb + 2 * t) = make_double2(-d0, -d1);
+            __syncwarp();
+          }
+        }
+      }
+      SYNC();
+      for (int ct = warp; ct < ldz / 8; ct += nwarps) {
+        double *zc = Z + 8 * ct;
+        for (int ib = NBR - 1; ib >= 0; ib--) { // Y_i = sum_{k <= i} X_ik Z_k
+          double c0 = 0.0, c1 = 0.0;
+          for (int kb = 0; kb <= ib; kb++) {
+            const double *pa = Rh + (8 * ib + g) * LDR + 8 * kb + t;
+            const double *pb = zc + (8 * kb + t) * ldz + g;
+            dmma_8x8x4(c0, c1, pa[0], pb[0]);
+            dmma_8x8x4(c0, c1, pa[4], pb[4 * ldz]);
+          }
+          __syncwarp();
+          *reinterpret_cast<double2 *>(zc + (8 * ib + g) * ldz + 2 * t) = make_double2(c0, c1);
+          __syncwarp();
+        }
+        for (int ib = 0; ib < NBR; ib++) { // Zsol_i = sum_{k >= i} X_ki' Y_k
+          double c0 = 0.0, c1 = 0.0;
+          for (int kb = ib; kb < NBR; kb++) {
+            const double *pa = Rh + (8 * kb + t) * LDR + 8 * ib + g; // (X_ki)'[g][t] = X_ki[t][g]
+            const double *pb = zc + (8 * kb + t) * ldz + g;
+            dmma_8x8x4(c0, c1, pa[0], pb[0]);
+            dmma_8x8x4(c0, c1, pa[4 * LDR], pb[4 * ldz]);
+          }
+          __syncwarp();
+          *reinterpret_cast<double2 *>(zc + (8 * ib + g) * ldz + 2 * t) = make_double2(c0, c1);
+          __syncwarp();
+        }
+      }
+      SYNC();
+    }
+#endif
     PHASE(8);
     PAR_FOR(e, nca * nca) {
       int r = e / nca, c = e % nca;
       double s = (r == c) ? mu : 0.0;
-      for (int l = 0; l < M; l++) s += CD[r * NZ + N + l] * Z[l * ncol + NR + c];
+      for (int l = 0; l < M; l++) s += CD[r * NZ + N + l] * Z[l * ldz + NR + c];
       Sg[e] = s;
     }
     PAR_FOR(e, nca * NR) {
       int r = e / NR, c = e % NR;
       double s = (c == 0) ? dbr[r] : CD[r * NZ + c - 1];
-      for (int l = 0; l < M; l++) s -= CD[r * NZ + N + l] * Z[l * ncol + c];
+      for (int l = 0; l < M; l++) s -= CD[r * NZ + N + l] * Z[l * ldz + c];
       Kv[e] = s;
     }
     SYNC();
@@ -237,24 +305,24 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
     PHASE(10);
     PAR_FOR(e, M * NR) {
       int i = e / NR, c = e % NR;
-      double s = -Z[i * ncol + c];
-      for (int r = 0; r < nca; r++) s -= Z[i * ncol + NR + r] * Kv[r * NR + c];
-      Z[i * ncol + c] = s;
+      double s = -Z[i * ldz + c];
+      for (int r = 0; r < nca; r++) s -= Z[i * ldz + NR + r] * Kv[r * NR + c];
+      Z[i * ldz + c] = s;
     }
     SYNC();
     double *gK = io.K + (size_t)k * S * NR;
-    PAR_FOR(e, M * NR) { int i = e / NR, c = e % NR; double v = Z[i * ncol + c]; gK[e] = v; if (c > 0) io.Kfb[((size_t)k * M + i) * N + c - 1] = v; }
+    PAR_FOR(e, M * NR) { int i = e / NR, c = e % NR; double v = Z[i * ldz + c]; gK[e] = v; if (c > 0) io.Kfb[((size_t)k * M + i) * N + c - 1] = v; }
     PAR_FOR(e, nca * NR) gK[M * NR + e] = Kv[e];
     PHASE(11);
     // 9. P = Qh + Sh Ku + C' Kv, p = qh + Sh ku + C' kv : in place in H[0:N,0:N] / p (symmetrised when the next knot loads it).
     //    Sh Ku = H[N:, 0:N]' Z[:, 1:] runs on the DMMA pipe (K = MP, zero rows beyond M); the active-row part is usually empty.
     PAR_FOR(i, N) {
       double s = gh[i];
-      for (int l = 0; l < M; l++) s += H[i * LDH + N + l] * Z[l * ncol];
+      for (int l = 0; l < M; l++) s += H[i * LDH + N + l] * Z[l * ldz];
       for (int r = 0; r < nca; r++) s += CD[r * NZ + i] * Kv[r * NR];
       p[i] = s;
     }
-    mma_tn(NBLK, NBLK, MP, H + N * LDH, LDH, Z + 1, ncol, H, LDH, H, LDH, N, N, false);
+    mma_tn(NBLK, NBLK, MR, H + N * LDH, LDH, Z + 1, ldz, H, LDH, H, LDH, N, N, false);
     if (nca > 0) { // 2 x 4 register tiles over (row i, column c)
       constexpr int TC = N / 4;
       PAR_FOR(t, (N / 2) * TC) {
