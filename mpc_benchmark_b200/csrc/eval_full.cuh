@@ -83,7 +83,7 @@ template <bool WITH_DERIV> struct FullWsT {
   double top[TOPS];
   double rcent[6], rpose[12], Jlp[2 * M6];
   double estate[FN], Jls[M6];
-  double dx[FN], xnext[NQ + NV], lgap[6], eexp[12], Dgap[12];
+  double dx[FN], xnext[NQ + NV], lgap[6], eexp[12], Dgap[12], Dl[36];
   double lpl[FN], fbr[FN];
   double com[3], scal[SC_COUNT], part[32];
   int32_t act[2], nact, sidx[2], ctype[FNC], isact[FNC], act_idx[FNC], nca;
@@ -179,8 +179,9 @@ template <class WS> HD void mb_kinematics(const DevModel &m, WS &w) {
 // The single-thread Lie-group tasks are spread over the 4 warps in two dependent stages, the 6x6 products over all threads.
 template <class WS> HD void mb_cost_terms(const DevModel &m, WS &w, const double *lf_ref, const double *rf_ref, bool derivs, double *gap_out) {
   const mpc_robot_t &rb = m.rb;
+  // stage 1a: the relative placements whose logarithms are needed: both foot poses, the state error and the shooting gap
   PAR_FOR(task, 4 * 32) {
-    if (task == 0) { // centroidal momentum value; integrator base block and gap
+    if (task == 0) { // centroidal momentum value; integrator base block and gap placement
       const double *h = w.hsub;
       double c[3];
       cross3(w.com, h, c);
@@ -194,24 +195,28 @@ template <class WS> HD void mb_cost_terms(const DevModel &m, WS &w, const double
         quat_to_R(w.xn + 3, Mn); Mn[9] = w.xn[0]; Mn[10] = w.xn[1]; Mn[11] = w.xn[2];
         quat_to_R(w.xnext + 3, Mp); Mp[9] = w.xnext[0]; Mp[10] = w.xnext[1]; Mp[11] = w.xnext[2];
         se3_inv_mul(Mn, Mp, w.Dgap);
-        log6(w.Dgap, w.lgap);
-        for (int i = 0; i < 6; i++) gap_out[i] = w.fbr[i] = w.lgap[i]; // fbr temporarily holds the gap
       }
-    } else if (task == 32 || task == 64) { // foot pose residuals
+    } else if (task == 32 || task == 64) { // foot pose placements
       int f = task == 32 ? 0 : 1;
-      double D[12];
-      se3_inv_mul(f == 0 ? lf_ref : rf_ref, w.ofoot + 12 * f, D);
-      log6(D, w.rpose + 6 * f);
-      if (derivs) Jlog6_from_log(w.rpose + 6 * f, w.Jlp + 36 * f);
+      se3_inv_mul(f == 0 ? lf_ref : rf_ref, w.ofoot + 12 * f, w.Dl + 12 * f);
     } else if (task == 96) { // state error e = x (-) x_ref
-      double Mr[12], Mx[12], D[12];
+      double Mr[12], Mx[12];
       quat_to_R(m.cfg.x_ref + 3, Mr); Mr[9] = m.cfg.x_ref[0]; Mr[10] = m.cfg.x_ref[1]; Mr[11] = m.cfg.x_ref[2];
       for (int i = 0; i < 12; i++) Mx[i] = w.oM[i];
-      se3_inv_mul(Mr, Mx, D);
-      log6(D, w.estate);
-      if (derivs) Jlog6_from_log(w.estate, w.Jls);
+      se3_inv_mul(Mr, Mx, w.Dl + 24);
     }
   }
+  SYNC();
+  // stage 1b: ONE copy of log6 / Jlog6 run by up to four lanes of a warp side by side (the evaluation kernels are
+  // instruction-fetch bound: every inlined copy of these long routines costs cold instruction-cache misses)
+  PAR_FOR(item, gap_out ? 4 : 3) {
+    const double *D = (item == 3) ? w.Dgap : w.Dl + 12 * item;
+    double *out = (item < 2) ? w.rpose + 6 * item : (item == 2) ? w.estate : w.lgap;
+    log6(D, out);
+    if (derivs) Jlog6_from_log(out, (item < 2) ? w.Jlp + 36 * item : (item == 2) ? w.Jls : w.late.Jlg);
+  }
+  SYNC();
+  if (gap_out) PAR_FOR(i, 6) gap_out[i] = w.fbr[i] = w.lgap[i]; // fbr temporarily holds the gap
   PAR_FOR(i, FN - 6) {
     int a = 6 + i;
     w.estate[a] = (a < NV) ? (w.x[7 + a - 6] - m.cfg.x_ref[7 + a - 6]) : (w.x[NQ + a - NV] - m.cfg.x_ref[NQ + a - NV]);
@@ -225,10 +230,9 @@ template <class WS> HD void mb_cost_terms(const DevModel &m, WS &w, const double
   if (gap_out) {
     PAR_FOR(task, 4 * 32) {
       const double id[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
-      if (task == 0) { double inv[12]; Jlog6_from_log(w.lgap, w.late.Jlg); se3_inv_mul(w.Dgap, id, inv); se3_action_matrix(inv, w.late.AdDi); }
-      else if (task == 32) Jexp6(w.dx, w.late.Jd);
+      if (task == 0) { double inv[12]; se3_inv_mul(w.Dgap, id, inv); se3_action_matrix(inv, w.late.AdDi); }
+      else if (task == 32 || task == 33) Jexp6(task == 32 ? w.dx : w.lgap, task == 32 ? w.late.Jd : w.late.Jrg); // two lanes, one copy
       else if (task == 64) { double einv[12]; se3_inv_mul(w.eexp, id, einv); se3_action_matrix(einv, w.late.Ade); se3_action_matrix(w.Dgap, w.late.AdD); }
-      else if (task == 96) Jexp6(w.lgap, w.late.Jrg);
     }
   }
   PAR_FOR(e, 2 * 6 * NV) { // Jpose = Jlog6 * Jf

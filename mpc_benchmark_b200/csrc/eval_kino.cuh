@@ -40,7 +40,7 @@ template <bool WITH_DERIV> struct KinoWsT {
   double Cvel[CV];    // zero-frame-velocity constraint rows [dq | dv] for both feet (12 x 56)
   double rcent[6], rpose[12], Jlp[2 * M6];
   double estate[FN], Jls[M6];
-  double dx[FN], xnext[NQ + NV], lgap[6], eexp[12], Dgap[12];
+  double dx[FN], xnext[NQ + NV], lgap[6], eexp[12], Dgap[12], Dl[36];
   double lpl[FN], fbr[FN];
   double com[3], scal[SC_COUNT], part[32];
   int32_t active[2], ctype[KNC], isact[KNC], act_idx[KNC], nca;
