@@ -97,7 +97,7 @@ def reference_arm(args):
     from mpc_benchmark_b200 import problems
 
     cores = os.cpu_count() or 1
-    sample = args.cpu_sample or max(cores, 16)
+    sample = args.cpu_sample or 16 * cores  # bounded sample, ~1 s of CPU work per step with all cores busy
     prob = problems.full_walk_batch(sample, seed=5)
     nominal = dict(prob, x0=prob["x0_nominal"])
     warm = oracle_lib.solve(nominal, max_iters=args.prep_iters, inst_threads=cores)
@@ -220,6 +220,13 @@ def main():
         flops = algorithmic_lq_flops(prob)
         ric_ms = kern["riccati"] / max(nric, 1)
         achieved = flops / (ric_ms * 1e-3) / 1e12 if ric_ms > 0 else None
+        traffic, traffic_src = measured_traffic(B)
+        hbm_peak, hbm_src = hbm_peak_gbs()
+        hbm = None
+        if traffic and ric_ms > 0:
+            gbs = traffic / (ric_ms * 1e-3) / 1e9
+            hbm = {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": hbm_src,
+                   "note": "secondary roofline of the same kernel: DRAM traffic / duration; far from the HBM bound, the kernel is fp64 / latency bound"}
         h2d = xs_np.nbytes + us_np.nbytes
         d2h = out_xs.nbytes + out_us.nbytes + B * 22 * 56 * 8
         line = {
@@ -234,7 +241,7 @@ def main():
             "wall_ms_per_step": 1e3 * wall_s / args.steps,
             "kernel_ms_per_step": {k: v / args.steps for k, v in kern.items()},
             "roofline": {"bound": "fp64", "kernel": "k_riccati (proximal Riccati backward+forward)", "achieved": achieved,
-                         "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None, "traffic": None,
+                         "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic, "traffic_source": traffic_src, "hbm": hbm,
                          "peak_source": "DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no fp64 entry; SURVEY 8d)",
                          "algorithmic_flops_per_launch": flops,
                          "note": "algorithmic = dense LQ model of SURVEY 8d; the kernel skips inactive constraint rows, so executed FLOPs are lower"},
@@ -248,6 +255,28 @@ def main():
     solver.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def hbm_peak_gbs():
+    """Measured HBM copy bandwidth of this pool (driver-written MEASURED_PEAKS.json), else the profiling recipe's fallback."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "of fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def measured_traffic(batch):
+    """DRAM bytes of one k_riccati launch at this batch, scaled per instance from the committed `ncu --set full` capture
+    (profiles/r1_traffic.json; instances are independent CTAs, so the traffic is linear in the batch)."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        per_inst = (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["batch"]
+        return per_inst * batch, f"profiles/r1_traffic.json: {per_inst / 1e6:.1f} MB/instance measured at batch {t['batch']} (algorithmic {t['algorithmic_bytes_per_instance'] / 1e6:.1f} MB), scaled to batch {batch}"
+    except (OSError, KeyError, ValueError):
+        return None, None
 
 
 def single_instance_latency(args, prob, device, with_cpu):
