@@ -249,6 +249,7 @@ def main():
         }
         if args.latency_ticks > 0:
             line["latency"] = single_instance_latency(args, prob, local, not args.no_cpu_baseline and world == 1)
+            line["latency"]["other_models"] = other_model_latencies(args, local, not args.no_cpu_baseline and world == 1)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, prob, xs_np, us_np)
         print(json.dumps(line))
@@ -311,6 +312,40 @@ def single_instance_latency(args, prob, device, with_cpu):
             oracle_lib.solve(sub, max_iters=1, knot_threads=8, xs=xs, us=us)
             cts.append(1e3 * (time.perf_counter() - t0))
         out["cpu_oracle_8_threads_p50_ms"] = float(np.percentile(cts[1:], 50))
+    return out
+
+
+def other_model_latencies(args, device, with_cpu):
+    """BASELINE configs[0] / configs[1] (parity-test cases, reported for reference only): warm single-instance MPC tick of the
+    centroidal and kinodynamic problems of the reference scripts' cold-solve setup (standing, T = 100)."""
+    from mpc_benchmark_b200 import problems
+    from mpc_benchmark_b200.batch import BatchSolver
+
+    out = {}
+    for name, maker in (("centroidal", problems.cent_standing_problem), ("kinodynamic", problems.kino_standing_problem)):
+        prob = maker(batch=1, T=100)
+        s = BatchSolver(prob["robot"], prob["cfg"], 1, device=device)
+        s.setup(prob["knots"], prob["terms"], prob["x0"])
+        warm = s.run(prob["xs"], prob["us"], max_iters=args.prep_iters, gains=False)
+        xs, us = warm.xs.copy(), warm.us.copy()
+        ts = []
+        for _ in range(min(args.latency_ticks, 50) + 5):
+            t0 = time.perf_counter()
+            s.reset_multipliers()
+            s.run(xs, us, max_iters=1, gains=False)
+            ts.append(1e3 * (time.perf_counter() - t0))
+        s.close()
+        out[name] = {"p50_ms": float(np.percentile(ts[5:], 50))}
+        if with_cpu:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_lib
+
+            cts = []
+            for _ in range(4):
+                t0 = time.perf_counter()
+                oracle_lib.solve(prob, max_iters=1, knot_threads=8, xs=xs, us=us)
+                cts.append(1e3 * (time.perf_counter() - t0))
+            out[name]["cpu_oracle_8_threads_p50_ms"] = float(np.percentile(cts[1:], 50))
     return out
 
 

@@ -236,3 +236,48 @@ def test_closed_loop_ticks_match_host_driven_oracle(oracle):
         got = s.results(gains=False, multipliers=False)
         assert rel(got.xs, xs) < RTOL and rel(got.us, us) < RTOL, tick
     s.close()
+
+
+def test_bench_workload_tick_matches_oracle(oracle):
+    """The bench's timed step on a few walking instances (bench.py): warm start = solve of the NOMINAL problem,
+    multipliers reset (per-tick solver.setup), measured state forced at knot 0, one iteration.  Repeating the tick after
+    mpc_reset_multipliers must reproduce it bit for bit (no state leaks between ticks)."""
+    B, T = 4, 60
+    prob = problems.full_walk_batch(B, seed=9, T=T)
+    s = BatchSolver(prob["robot"], prob["cfg"], B)
+    s.setup(prob["knots"], prob["terms"], prob["x0_nominal"])
+    warm = s.run(prob["xs"], prob["us"], max_iters=10, gains=False)
+    nominal = dict(prob, x0=prob["x0_nominal"])
+    wref = oracle.solve(nominal, max_iters=10, inst_threads=B)
+    assert rel(warm.xs, wref["xs"]) < RTOL and rel(warm.us, wref["us"]) < RTOL
+    xs_in = problems.warm_tick_inputs(prob, wref["xs"])
+    assert np.array_equal(xs_in[:, 0], prob["x0"]) and np.array_equal(xs_in[:, 1:], wref["xs"][:, 1:])
+    s.set_x0(prob["x0"])
+    s.reset_multipliers()
+    t1 = s.run(xs_in, wref["us"], max_iters=1)
+    ref = oracle.solve(prob, max_iters=1, inst_threads=B, xs=xs_in, us=wref["us"])
+    assert list(t1.num_iters) == [1] * B
+    assert list(t1.ls_evals) == [i.ls_evals for i in ref["info"]]
+    assert rel(t1.xs, ref["xs"]) < RTOL and rel(t1.us, ref["us"]) < RTOL and rel(t1.K, ref["K"]) < 1e-5
+    s.reset_multipliers()
+    t2 = s.run(xs_in, wref["us"], max_iters=1)
+    assert np.array_equal(t1.xs, t2.xs) and np.array_equal(t1.us, t2.us) and np.array_equal(t1.vs, t2.vs)
+    s.close()
+
+
+def test_call_order_and_argument_errors():
+    """Error behaviour of the C-ABI: non-zero status + message, raised as NativeError by the host layer."""
+    from mpc_benchmark_b200 import _native
+
+    prob = problems.cent_standing_problem(batch=2, T=10)
+    s = BatchSolver(prob["robot"], prob["cfg"], 2)
+    with pytest.raises(_native.NativeError):
+        s.run(prob["xs"], prob["us"], max_iters=1)  # run before setup
+    with pytest.raises(_native.NativeError):
+        s.reset_multipliers()
+    s.setup(prob["knots"], prob["terms"], prob["x0"])
+    with pytest.raises(_native.NativeError):
+        s.update_knots((_abi.Knot * 10)(*[prob["knots"][0]] * 10), 8, 5)  # range beyond the horizon
+    r0 = s.run(prob["xs"], prob["us"], max_iters=0)  # nothing to do: inputs come back unchanged
+    assert list(r0.num_iters) == [0, 0] and np.array_equal(r0.us, prob["us"])
+    s.close()
