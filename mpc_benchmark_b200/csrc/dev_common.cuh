@@ -20,16 +20,13 @@
 #define WARP_FOR(i, n) for (int i = 0; i < (n); i++)
 #define WARP_SYNC() ((void)0)
 #define ATOMIC_INC(p) ((*(p))++)
-#define PAR_FOR_REST(i, n) for (int i = 0; i < (n); i++)
 #define WARP_TILE_FOR(p, n) for (int p = 0; p < (n); p++)
 #define WARP_TILE_FOR_REST(p, n) for (int p = 0; p < (n); p++)
-#define WARP_ROW_FOR(i, n) for (int i = 0; i < (n); i++)
 #define LANE_FOR(j, n) for (int j = 0; j < (n); j++)
 #define WARP_SUM(x) (x)
 #define LANE0 true
 #define WARP_ID 0
 #define NWARPS 1
-#define PREFETCH_L2(p) ((void)0)
 #define ASYNC_COPY16(dst, src) do { (dst)[0] = (src)[0]; (dst)[1] = (src)[1]; } while (0)
 #define ASYNC_COPY8(dst, src) do { (dst)[0] = (src)[0]; } while (0)
 #define ASYNC_COMMIT() ((void)0)
@@ -51,20 +48,15 @@ inline double2 make_double2(double x, double y) { return double2{x, y}; }
 #define WARP_FOR(i, n) for (int i = (threadIdx.x & 31); i < (n); i += 32)
 #define WARP_SYNC() __syncwarp()
 #define ATOMIC_INC(p) atomicAdd((p), 1)
-// work items over all threads except warp 0 (which runs a serial task in the same phase); whole CTA if it is a single warp
-#define PAR_FOR_REST(i, n) \
-  for (int i = (blockDim.x > 32) ? (int)threadIdx.x - 32 : (int)threadIdx.x; i >= 0 && i < (n); i += (blockDim.x > 32) ? blockDim.x - 32 : blockDim.x)
 // one 8 x 8 tile per warp: over all warps / over all warps except warp 0
 #define WARP_TILE_FOR(p, n) for (int p = (threadIdx.x >> 5); p < (n); p += (blockDim.x >> 5))
 #define WARP_TILE_FOR_REST(p, n) for (int p = (int)(threadIdx.x >> 5) - 1; p >= 0 && p < (n); p += (blockDim.x >> 5) - 1)
 // matrix-vector pattern: rows over warps, columns over lanes (coalesced / conflict-free), butterfly reduction
-#define WARP_ROW_FOR(i, n) for (int i = (threadIdx.x >> 5); i < (n); i += (blockDim.x >> 5))
 #define LANE_FOR(j, n) for (int j = (threadIdx.x & 31); j < (n); j += 32)
 #define WARP_SUM(x) mpcdev::warp_sum(x)
 #define LANE0 ((threadIdx.x & 31) == 0)
 #define WARP_ID ((int)(threadIdx.x >> 5))
 #define NWARPS ((int)(blockDim.x >> 5))
-#define PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 // 16-byte asynchronous global -> shared copy (cp.async, bypasses registers); dst/src are double pointers, 16-byte aligned
 #define ASYNC_COPY16(dst, src) \
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory")
@@ -205,13 +197,6 @@ HD double vinv_coeff(double t2) {
   sincos(t, &s, &co);
   return (1.0 - t * s / (2.0 * (1.0 - co))) / t2;
 }
-HD void exp3(const double *w, double *R) {
-  double t2 = dot3(w, w), a, b, c;
-  so3_coeffs(t2, a, b, c);
-  double W[9], W2[9];
-  skew3(w, W); mat3_mul(W, W, W2);
-  for (int i = 0; i < 9; i++) R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + a * W[i] + b * W2[i];
-}
 HD void exp6(const double *xi, double *M) {
   const double *w = xi + 3;
   double t2 = dot3(w, w), a, b, c;
@@ -311,44 +296,9 @@ HD void inv6(const double *A, double *Ai) {
   for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) Ai[6 * i + j] = M[i][6 + j];
 }
 
-// ------------------------------------------------------------------ block-cooperative dense kernels (shared memory)
-// In-place lower Cholesky of the n x n matrix A (leading dimension ld). Right-looking, 2 barriers per column.
-HD void chol_par(double *A, int n, int ld) {
-  for (int j = 0; j < n; j++) {
-    double d = sqrt(A[j * ld + j]);
-    SYNC();
-    PAR_FOR(i, n - j) { int r = j + i; A[r * ld + j] = (i == 0) ? d : A[r * ld + j] / d; }
-    SYNC();
-    int rem = n - j - 1;
-    PAR_FOR(e, rem * rem) {
-      int r = j + 1 + e / rem, c = j + 1 + e % rem;
-      if (c <= r) A[r * ld + c] -= A[r * ld + j] * A[c * ld + j];
-    }
-    SYNC();
-  }
-}
-// Solve L L^T X = B in place for nrhs columns of B (row-major n x ldb); one work item per column.
-HD void chol_solve_par(const double *L, int n, int ld, double *B, int nrhs, int ldb) {
-  PAR_FOR(c, nrhs) {
-    for (int i = 0; i < n; i++) {
-      double s = B[i * ldb + c];
-      for (int k = 0; k < i; k++) s -= L[i * ld + k] * B[k * ldb + c];
-      B[i * ldb + c] = s / L[i * ld + i];
-    }
-    for (int i = n - 1; i >= 0; i--) {
-      double s = B[i * ldb + c];
-      for (int k = i + 1; k < n; k++) s -= L[k * ld + i] * B[k * ldb + c];
-      B[i * ldb + c] = s / L[i * ld + i];
-    }
-  }
-  SYNC();
-}
-
 // ------------------------------------------------------------------ blocked Cholesky / triangular solves (panel width 8)
-// In-place lower Cholesky of A (n x n, ld).  Each 8-wide panel is factorised by warp 0 alone (warp-level barriers
-// only: the 8-step sqrt/divide dependency chain is latency-bound anyway), followed by ONE block-wide trailing update.
-// Dinv receives the inverses of the diagonal blocks (8 x 8 lower, row-major, 64 doubles per panel), which turn the
-// triangular solves below into small GEMMs.  2 block barriers per panel.
+// In-place lower Cholesky of A (n x n, ld) by 8-wide panels.  Dinv receives the inverses of the diagonal blocks (8 x 8
+// lower, row-major, 64 doubles per panel), which turn the triangular solves below into small GEMMs.
 constexpr int CB = 8;
 #ifdef MPC_HOST_EMU
 inline double rsqrt(double x) { return 1.0 / sqrt(x); }
@@ -410,23 +360,15 @@ HD void chol_diag_block(double *A, int k0, int bw, int ld, double *Di) {
     }
 }
 // Blocked Cholesky (lower, in place): per 8-wide panel, one thread factors + inverts the diagonal block, the panel below it
-// is multiplied by the inverse, and the trailing matrix is updated on 2 x 2 register tiles.
-// LOOKAHEAD (used for the 56 x 56 Lambda of the Riccati kernel, 8 warps): after the panel solve the whole CTA first updates
-// only the NEXT panel's columns; then thread 0 factors the next diagonal block while the other warps finish the rest of the
-// trailing update, which takes part of the serial 8 x 8 factorisation off the critical path.  For small matrices / CTAs the
-// extra phase costs more than it hides, so the evaluation kernels keep the plain schedule.
-template <bool LOOKAHEAD = false> HD void chol_blocked(double *A, int n, int ld, double *Dinv) {
-  if (LOOKAHEAD) {
-    ONE_THREAD chol_diag_block(A, 0, (n < CB) ? n : CB, ld, Dinv);
-    SYNC();
-  }
+// is multiplied by the inverse, and the trailing matrix is updated on 2 x 2 register tiles.  (The 56 x 56 and padded control
+// blocks of the Riccati kernel use the tensor-core version with look-ahead, chol_mma in dmma.cuh; a look-ahead variant of
+// this SIMT routine was measured and lost on the small matrices / 128-thread groups of the evaluation kernels.)
+HD void chol_blocked(double *A, int n, int ld, double *Dinv) {
   for (int k0 = 0; k0 < n; k0 += CB) {
     const int bw = (n - k0 < CB) ? n - k0 : CB;
     const double *Di = Dinv + (k0 / CB) * CB * CB;
-    if (!LOOKAHEAD) {
-      ONE_THREAD chol_diag_block(A, k0, bw, ld, Dinv + (k0 / CB) * CB * CB);
-      SYNC();
-    }
+    ONE_THREAD chol_diag_block(A, k0, bw, ld, Dinv + (k0 / CB) * CB * CB);
+    SYNC();
     // panel below the diagonal block: L[i, k0:k0+bw] = A[i, k0:k0+bw] * Dinv^T, one row per work item
     const int rem = n - k0 - bw, r0 = k0 + bw;
     if (rem <= 0) break;
@@ -443,41 +385,22 @@ template <bool LOOKAHEAD = false> HD void chol_blocked(double *A, int n, int ld,
       for (int q = 0; q < CB; q++) if (q < bw) row[q] = o[q];
     }
     SYNC();
-    int r1 = r0; // first row / column of the part updated on 2 x 2 tiles
-    if (LOOKAHEAD) {
-      // critical part of the trailing update: the next panel's columns [r0, r0 + bwn)
-      const int bwn = (rem < CB) ? rem : CB;
-      PAR_FOR(e, rem * bwn) {
-        const int i = r0 + e / bwn, j = r0 + e % bwn;
-        if (j > i) continue;
-        double s = 0;
-        for (int q = 0; q < bw; q++) s += A[i * ld + k0 + q] * A[j * ld + k0 + q];
-        A[i * ld + j] -= s;
+    // trailing update on 2 x 2 tiles of the lower triangle
+    const int th = (rem + 1) / 2;
+    PAR_FOR(t, th * th) {
+      int ti = t / th, tj = t % th;
+      if (tj > ti) continue;
+      int i0 = r0 + 2 * ti, j0 = r0 + 2 * tj;
+      double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
+      bool i1 = i0 + 1 < n, j1 = j0 + 1 < n;
+      for (int q = 0; q < bw; q++) {
+        double li0 = A[i0 * ld + k0 + q], li1 = i1 ? A[(i0 + 1) * ld + k0 + q] : 0.0;
+        double lj0 = A[j0 * ld + k0 + q], lj1 = j1 ? A[(j0 + 1) * ld + k0 + q] : 0.0;
+        a00 += li0 * lj0; a01 += li0 * lj1; a10 += li1 * lj0; a11 += li1 * lj1;
       }
-      SYNC();
-      ONE_THREAD chol_diag_block(A, r0, bwn, ld, Dinv + (r0 / CB) * CB * CB);
-      r1 = r0 + bwn;
-    }
-    const int rem2 = n - r1;
-    if (rem2 > 0) {
-      const int th = (rem2 + 1) / 2;
-      auto tile = [&](int t) {
-        int ti = t / th, tj = t % th;
-        if (tj > ti) return;
-        int i0 = r1 + 2 * ti, j0 = r1 + 2 * tj;
-        double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
-        bool i1 = i0 + 1 < n, j1 = j0 + 1 < n;
-        for (int q = 0; q < bw; q++) {
-          double li0 = A[i0 * ld + k0 + q], li1 = i1 ? A[(i0 + 1) * ld + k0 + q] : 0.0;
-          double lj0 = A[j0 * ld + k0 + q], lj1 = j1 ? A[(j0 + 1) * ld + k0 + q] : 0.0;
-          a00 += li0 * lj0; a01 += li0 * lj1; a10 += li1 * lj0; a11 += li1 * lj1;
-        }
-        A[i0 * ld + j0] -= a00;
-        if (j1 && j0 + 1 <= i0) A[i0 * ld + j0 + 1] -= a01;
-        if (i1) { A[(i0 + 1) * ld + j0] -= a10; if (j1) A[(i0 + 1) * ld + j0 + 1] -= a11; }
-      };
-      if (LOOKAHEAD) { PAR_FOR_REST(t, th * th) tile(t); }
-      else { PAR_FOR(t, th * th) tile(t); }
+      A[i0 * ld + j0] -= a00;
+      if (j1 && j0 + 1 <= i0) A[i0 * ld + j0 + 1] -= a01;
+      if (i1) { A[(i0 + 1) * ld + j0] -= a10; if (j1) A[(i0 + 1) * ld + j0 + 1] -= a11; }
     }
     SYNC();
   }

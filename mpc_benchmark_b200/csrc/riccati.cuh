@@ -44,33 +44,6 @@ template <bool TA> HD void gemm_par(int M, int N, int K, const double *A, int ld
   }
   SYNC();
 }
-// y (M) = beta*y + A^T x (A: K x M) or A x (A: M x K)
-template <bool TA> HD void gemv_par(int M, int K, const double *A, int lda, const double *x, double *y, double beta) {
-  PAR_FOR(i, M) {
-    double s = 0;
-    for (int k = 0; k < K; k++) s += (TA ? A[k * lda + i] : A[i * lda + k]) * x[k];
-    y[i] = (beta == 0.0 ? 0.0 : beta * y[i]) + s;
-  }
-  SYNC();
-}
-// Solve L L^T X = B in place, B row-major n x nrhs (ldb). Right-looking, all threads on every rank-1 update.
-HD void trsm_par(const double *L, int n, int ld, double *B, int nrhs, int ldb) {
-  for (int k = 0; k < n; k++) {
-    double d = 1.0 / L[k * ld + k];
-    PAR_FOR(c, nrhs) B[k * ldb + c] *= d;
-    SYNC();
-    int rem = n - k - 1;
-    PAR_FOR(e, rem * nrhs) { int i = k + 1 + e / nrhs, c = e % nrhs; B[i * ldb + c] -= L[i * ld + k] * B[k * ldb + c]; }
-    SYNC();
-  }
-  for (int k = n - 1; k >= 0; k--) {
-    double d = 1.0 / L[k * ld + k];
-    PAR_FOR(c, nrhs) B[k * ldb + c] *= d;
-    SYNC();
-    PAR_FOR(e, k * nrhs) { int i = e / nrhs, c = e % nrhs; B[i * ldb + c] -= L[k * ld + i] * B[k * ldb + c]; }
-    SYNC();
-  }
-}
 
 // per-instance pointers (all device/global unless noted)
 struct RiccatiIO {
