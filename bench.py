@@ -125,7 +125,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from mpc_benchmark_b200 import _native, problems
+    from mpc_benchmark_b200 import _abi, _native, problems
     from mpc_benchmark_b200.batch import BatchSolver
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -206,10 +206,22 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    tmax = torch.tensor([dev_ms * 1e-3, wall, wall_e2e], device="cuda", dtype=torch.float64)
+    # ---- closed-loop ticks on the device (horizon rotation + warm-start shift + x0 from the model
+    # prediction inside mpc_tick; the stage entering each horizon comes from the host), same batch, ideal plant
+    stand = problems.full_standing_problem(batch=1, T=1)["knots"][0]
+    nxt = (_abi.Knot * B)(*[stand] * B)
+    solver.tick(nxt, None, keep_multipliers=False, max_iters=1)
+    barrier()
+    t2 = time.time()
+    for _ in range(args.steps):
+        solver.tick(nxt, None, keep_multipliers=False, max_iters=1)
+    barrier()
+    wall_cl = time.time() - t2
+
+    tmax = torch.tensor([dev_ms * 1e-3, wall, wall_e2e, wall_cl], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    dev_s, wall_s, e2e_s = [float(v) for v in tmax.cpu()]
+    dev_s, wall_s, e2e_s, cl_s = [float(v) for v in tmax.cpu()]
     step_s = max(dev_s, 0.0) / args.steps
     value = B * world * args.steps / max(dev_s, 1e-12)
     e2e = B * world * args.steps / e2e_s
@@ -238,6 +250,8 @@ def main():
                        "prep_iters": args.prep_iters, "tick_iters_done": int(np.min(res_iters))},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
+            "closed_loop": {"value": B * world * args.steps / cl_s, "unit": "robot-ticks/s",
+                            "what": "mpc_tick (SURVEY 8f-2): horizon rotation, warm-start shift, x0 <- model prediction, 1 iteration; new stage H2D per tick"},
             "wall_ms_per_step": 1e3 * wall_s / args.steps,
             "kernel_ms_per_step": {k: v / args.steps for k, v in kern.items()},
             "roofline": {"bound": "fp64", "kernel": "k_riccati (proximal Riccati backward+forward)", "achieved": achieved,

@@ -114,27 +114,33 @@ class Data:
 class Model:
     """Carrier of the robot tree with the pinocchio attribute names the scripts read."""
 
-    def __init__(self, robot=None):
+    def __init__(self, robot=None, joint_names=None, reference_configurations=None, link_frames=None):
+        """robot: `_abi.Robot` (default: the synthetic Talos-shaped tree); joint_names / reference_configurations / link_frames
+        come from `urdf.build_robot` when the tree was loaded from a URDF (`model_from_urdf`)."""
         self.robot = robot if robot is not None else talos_like.talos_like_robot()
         rb = self.robot
+        names = list(joint_names) if joint_names is not None else list(talos_like.JOINT_NAMES)
         self.nq, self.nv = _abi.NQ, _abi.NV
         self.njoints = rb.nb + 1  # + universe
-        self.names = np.array(["universe"] + list(talos_like.JOINT_NAMES), dtype=object)
-        lo, hi, tau = talos_like.joint_limits()
+        self.names = np.array(["universe"] + names, dtype=object)
         big = 1e30
-        self.lowerPositionLimit = np.concatenate([[-big] * 7, lo])
-        self.upperPositionLimit = np.concatenate([[big] * 7, hi])
-        self.effortLimit = np.concatenate([np.zeros(6), tau])
-        self.referenceConfigurations = {"half_sitting": talos_like.half_sitting()}
-        self.gravity = Motion([0, 0, -9.81, 0, 0, 0])
-        # frames: universe, root_joint, the joints, base_link, torso_2_link, soles
+        self.lowerPositionLimit = np.concatenate([[-big] * 7, np.array(rb.q_lo[:])])
+        self.upperPositionLimit = np.concatenate([[big] * 7, np.array(rb.q_hi[:])])
+        self.effortLimit = np.concatenate([np.zeros(6), np.array(rb.tau_max[:])])
+        self.referenceConfigurations = dict(reference_configurations) if reference_configurations is not None else {"half_sitting": talos_like.half_sitting()}
+        self.gravity = Motion([rb.gravity[0], rb.gravity[1], rb.gravity[2], 0, 0, 0])
+        # frames: universe, root_joint, the joints, then link frames (base_link, torso_2_link, soles, ...)
         self.frames = [Frame("universe", 0, SE3())]
-        for j, n in enumerate(talos_like.JOINT_NAMES):
+        for j, n in enumerate(names):
             self.frames.append(Frame(n, j + 1, SE3()))
-        self.frames.append(Frame("base_link", 1, SE3()))
-        self.frames.append(Frame("torso_2_link", 1 + talos_like.JOINT_NAMES.index("torso_2_joint"), SE3()))
-        for f, n in enumerate(["left_sole_link", "right_sole_link"]):
-            self.frames.append(Frame(n, rb.foot_body[f] + 1, SE3.from12(rb.foot_place[f][:])))
+        if link_frames is None:
+            self.frames.append(Frame("base_link", 1, SE3()))
+            self.frames.append(Frame("torso_2_link", 1 + names.index("torso_2_joint"), SE3()))
+            for f, n in enumerate(["left_sole_link", "right_sole_link"]):
+                self.frames.append(Frame(n, rb.foot_body[f] + 1, SE3.from12(rb.foot_place[f][:])))
+        else:
+            for n, (body, place) in link_frames.items():
+                self.frames.append(Frame(n, body + 1, SE3.from12(place)))
 
     def copy(self):
         return self  # immutable carrier
@@ -195,3 +201,16 @@ def load_talos_like():
     m = Model()
     q0 = m.referenceConfigurations["half_sitting"]
     return m, m, q0.copy(), q0.copy()
+
+
+def model_from_urdf(urdf_text, srdf_text=None, locked_joints=(), posture="half_sitting", foot_frames=("left_sole_link", "right_sole_link")):
+    """`example_robot_data.load(...)` + `buildReducedRobot(locked_joints, q_ref)` of talos_utils.py:31-41 without Pinocchio
+    (SURVEY 8f row f-1): parse the URDF (+ SRDF posture), freeze `locked_joints` (names or complete-model joint ids) at the
+    posture and return the reduced `Model`; `model.robot` is the `mpc_robot_t` the solver consumes."""
+    from . import urdf
+
+    m = urdf.parse_urdf(urdf_text)
+    post = urdf.parse_srdf_posture(srdf_text, posture) if srdf_text else {}
+    rb, info = urdf.build_robot(m, locked=list(locked_joints), q_locked=post, foot_frames=foot_frames)
+    ref = {posture: urdf.reduced_configuration(info, post)} if srdf_text else None
+    return Model(robot=rb, joint_names=info["joint_names"], reference_configurations=ref, link_frames=info["frames"])
