@@ -8,21 +8,19 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from mpc_benchmark_b200 import _abi, problems  # noqa: E402
+from mpc_benchmark_b200 import problems  # noqa: E402
 from mpc_benchmark_b200.batch import BatchSolver  # noqa: E402
 from mpc_benchmark_b200.closed_loop import ClosedLoop  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 50
-prob = problems.full_walk_batch(B, seed=1)
-stand = problems.full_standing_problem(batch=1, T=1)["knots"][0]
-nxt = (_abi.Knot * B)(*[stand] * B)
+prob = problems.full_walk_batch(B, seed=1, stream_ticks=N)  # every robot's gait continues N knots past the horizon
 s = BatchSolver(prob["robot"], prob["cfg"], B)
-s.setup(prob["knots"], prob["terms"], prob["x0"])
+s.setup(prob["knots"], prob["terms"], prob["x0_nominal"])
 t0 = time.time()
 cold = s.run(prob["xs"], prob["us"], max_iters=30, gains=False)
 print(f"cold solve: {time.time() - t0:.2f} s, converged {cold.conv.sum()}/{B}, median prim infeas {np.median(cold.prim_infeas):.2e}")
-loop = ClosedLoop(s, lambda t: nxt)
+loop = ClosedLoop(s, prob["stream"])
 t0 = time.time()
 res = loop.run(N)
 dt = time.time() - t0

@@ -13,10 +13,12 @@ from . import _abi
 
 
 class ClosedLoop:
-    def __init__(self, solver, knot_stream, plant=None, keep_multipliers=False):
+    def __init__(self, solver, knot_stream, plant=None, keep_multipliers=False, term_stream=None):
         """solver: a set-up BatchSolver holding the cold-solve result; knot_stream(t) -> ctypes Knot array [batch] with the stage
-        entering the horizon at tick t; plant(t, xs, us, K0) -> measured states [batch, nx] or None for the ideal plant."""
-        self.solver, self.knot_stream, self.plant, self.keep = solver, knot_stream, plant, keep_multipliers
+        entering the horizon at tick t; plant(t, xs, us, K0) -> measured states [batch, nx] or None for the ideal plant;
+        term_stream(t) -> ctypes Term array [batch] or None: the terminal cost references / CoM equality swapped in at tick t
+        (fulldynamic_talos.py:499-510)."""
+        self.solver, self.knot_stream, self.plant, self.keep, self.term_stream = solver, knot_stream, plant, keep_multipliers, term_stream
         self.t = 0
         self.tick_ms = []
 
@@ -27,6 +29,10 @@ class ClosedLoop:
             r = s.results(gains=False, multipliers=False)
             x_meas = self.plant(self.t, r.xs, r.us, s.feedback(0))
         t0 = time.perf_counter()
+        if self.term_stream is not None:
+            terms = self.term_stream(self.t)
+            if terms is not None:
+                s.update_terms(terms)
         s.tick(self.knot_stream(self.t), x_meas, keep_multipliers=self.keep, max_iters=max_iters)
         self.tick_ms.append(1e3 * (time.perf_counter() - t0))
         self.t += 1

@@ -5,6 +5,8 @@ These builders produce exactly the `Config` / `Knot` / `Term` blocks that the al
 (fulldynamic_talos.py:100-245, kinodynamic_talos.py:72-180, centroidal_talos.py:185-261); bench.py and
 the tests use them directly to synthesise the BASELINE.json workloads.
 """
+import ctypes as C
+
 import numpy as np
 
 from . import _abi
@@ -213,7 +215,7 @@ def random_schedule(rng, T, min_first_ds=30):
     return phases[:T], pos[:T], length[:T]
 
 
-def full_walk_batch(batch, seed=5, T=100, robot=None, swing_apex=0.15, perturb=True, **kw):
+def full_walk_batch(batch, seed=5, T=100, robot=None, swing_apex=0.15, perturb=True, stream_ticks=0, **kw):
     """BASELINE.json config 5: batch of full-dynamics MPC problems with RANDOM CONTACT SCHEDULES.
     Instance i gets its own gait (random initial double-support length, single/double-support durations and first
     swing foot; `random_schedule`), swing-foot references following the Bezier bump of talos_utils.py:281-296,
@@ -221,7 +223,10 @@ def full_walk_batch(batch, seed=5, T=100, robot=None, swing_apex=0.15, perturb=T
     (fulldynamic_talos.py:499-507).  Every stage uses force-reference index 0 as the reference does (full:363-366).
     `x0` is the perturbed ("measured") state of each instance, `x0_nominal` the unperturbed one; the cold start `xs`
     repeats the nominal state as the reference's first solve does (full:390-391).  An MPC tick warm-starts from the
-    solution of the nominal problem and forces the measured state at knot 0: see `warm_tick_inputs`."""
+    solution of the nominal problem and forces the measured state at knot 0: see `warm_tick_inputs`.
+    With `stream_ticks` > 0 every gait is continued that many knots past the horizon and `stream(t)` returns the stage of
+    each instance entering its horizon at closed-loop tick t (the `stages_full[t]` of fulldynamic_talos.py:496); the first T
+    knots do not depend on `stream_ticks`."""
     rb, q0, x0, lf, rf, com0, mass = base_setup(robot)
     cfg = full_config(rb, x0, lf, rf, T=T, **kw)
     rng = np.random.default_rng(seed)
@@ -230,9 +235,10 @@ def full_walk_batch(batch, seed=5, T=100, robot=None, swing_apex=0.15, perturb=T
     knots = (_abi.Knot * (batch * T))()
     terms = (_abi.Term * batch)()
     n_ds = 0
+    tail = (_abi.Knot * (batch * stream_ticks))() if stream_ticks else None
     for i in range(batch):
-        phases, pos, length = random_schedule(rng, T)
-        for j in range(T):
+        phases, pos, length = random_schedule(rng, T + stream_ticks)
+        for j in range(T + stream_ticks):
             cs = phases[j]
             lref, rref = np.array(lf, float), np.array(rf, float)
             if cs != [True, True]:
@@ -241,17 +247,23 @@ def full_walk_batch(batch, seed=5, T=100, robot=None, swing_apex=0.15, perturb=T
                     rref[11] += bump  # right foot swings
                 else:
                     lref[11] += bump
-            else:
+            elif j < T:
                 n_ds += 1
-            knots[i * T + j] = full_knot(cs, lref, rref, fr, fr)
+            if j < T:
+                knots[i * T + j] = full_knot(cs, lref, rref, fr, fr)
+            else:
+                tail[(j - T) * batch + i] = full_knot(cs, lref, rref, fr, fr)
         com_final = np.array([(lf[9] + rf[9]) / 2, (lf[10] + rf[10]) / 2, com0[2]])
         terms[i] = make_term(lf, rf, com_final)
     x0s = perturbed_x0(rb, x0, rng, batch) if perturb else np.tile(x0, (batch, 1))
     x0n = np.tile(x0, (batch, 1))
     xs = np.repeat(x0n[:, None, :], T + 1, axis=1)
     us = np.zeros((batch, T, 22))
-    return dict(robot=rb, cfg=cfg, knots=knots, terms=terms, x0=x0s, x0_nominal=x0n, xs=xs, us=us, lf=lf, rf=rf, com0=com0, mass=mass,
-                ds_fraction=n_ds / float(batch * T))
+    out = dict(robot=rb, cfg=cfg, knots=knots, terms=terms, x0=x0s, x0_nominal=x0n, xs=xs, us=us, lf=lf, rf=rf, com0=com0, mass=mass,
+               ds_fraction=n_ds / float(batch * T))
+    if stream_ticks:
+        out["stream"] = lambda t: (_abi.Knot * batch).from_buffer(tail, min(t, stream_ticks - 1) * batch * C.sizeof(_abi.Knot))
+    return out
 
 
 def warm_tick_inputs(prob, warm_xs):

@@ -209,25 +209,31 @@ def test_closed_loop_ticks_match_host_driven_oracle(oracle):
     from mpc_benchmark_b200.closed_loop import ClosedLoop
 
     B, T = 3, 30
-    prob = problems.full_walk_batch(B, seed=3, T=T)
-    # stage stream: after the window, keep appending double-support standing knots
-    stand = problems.full_standing_problem(batch=1, T=1)["knots"][0]
-    nxt = (_abi.Knot * B)(*[stand] * B)
+    prob = problems.full_walk_batch(B, seed=3, T=T, stream_ticks=3)  # every gait continues past the horizon
+    assert bytes(prob["knots"]) == bytes(problems.full_walk_batch(B, seed=3, T=T)["knots"])
+
+    def term_at(t):  # terminal references swapped every tick (fulldynamic_talos.py:499-510): the CoM target drifts forward
+        com = np.array(prob["com0"], float)
+        com[0] += 0.002 * (t + 1)
+        return (_abi.Term * B)(*[problems.make_term(prob["lf"], prob["rf"], com)] * B)
+
     s = BatchSolver(prob["robot"], prob["cfg"], B)
     s.setup(prob["knots"], prob["terms"], prob["x0"])
     cold = s.run(prob["xs"], prob["us"], max_iters=8)
     ref = oracle.solve(prob, max_iters=8, inst_threads=3)
     assert rel(cold.xs, ref["xs"]) < RTOL
-    loop = ClosedLoop(s, lambda t: nxt)
+    loop = ClosedLoop(s, prob["stream"], term_stream=term_at)
     xs, us = ref["xs"], ref["us"]
     hp = dict(prob)
     knots = list(prob["knots"])
     for tick in range(3):
         loop.step(max_iters=1)
-        # host-driven reference: rotate knots, shift warm start, x0 <- previous xs[1]
+        # host-driven reference: rotate knots, swap the terminal, shift warm start, x0 <- previous xs[1]
+        nxt = prob["stream"](tick)
         for b in range(B):
-            knots[b * T:(b + 1) * T] = knots[b * T + 1:(b + 1) * T] + [stand]
+            knots[b * T:(b + 1) * T] = knots[b * T + 1:(b + 1) * T] + [nxt[b]]
         hp["knots"] = (_abi.Knot * (B * T))(*knots)
+        hp["terms"] = term_at(tick)
         hp["x0"] = xs[:, 1].copy()
         xs_ws = np.concatenate([xs[:, 1:], xs[:, -1:]], axis=1)
         us_ws = np.concatenate([us[:, 1:], us[:, -1:]], axis=1)
