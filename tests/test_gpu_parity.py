@@ -287,3 +287,22 @@ def test_call_order_and_argument_errors():
     r0 = s.run(prob["xs"], prob["us"], max_iters=0)  # nothing to do: inputs come back unchanged
     assert list(r0.num_iters) == [0, 0] and np.array_equal(r0.us, prob["us"])
     s.close()
+
+
+def test_non_finite_input_is_contained():
+    """A NaN initial state flags that instance (status 2, mpc_info_t) and terminates it; its neighbours in the batch solve
+    exactly as they do alone (independent units, no contamination through shared lists / reductions)."""
+    B, T = 3, 20
+    prob = problems.full_standing_problem(batch=B, T=T)
+    bad = dict(prob)
+    bad["x0"] = prob["x0"].copy()
+    bad["x0"][1, 10] = np.nan
+    s = BatchSolver(bad["robot"], bad["cfg"], B)
+    s.setup(bad["knots"], bad["terms"], bad["x0"])
+    r = s.run(bad["xs"], bad["us"], max_iters=5)
+    status = [i.status for i in r.info]
+    assert status[1] == 2 and status[0] != 2 and status[2] != 2
+    s.setup(prob["knots"], prob["terms"], prob["x0"])
+    good = s.run(prob["xs"], prob["us"], max_iters=5)
+    assert np.array_equal(r.xs[0], good.xs[0]) and np.array_equal(r.us[2], good.us[2])
+    s.close()
