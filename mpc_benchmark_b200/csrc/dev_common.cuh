@@ -296,6 +296,30 @@ HD void inv6(const double *A, double *Ai) {
   for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) Ai[6 * i + j] = M[i][6 + j];
 }
 
+// y[i] = (y0 ? y0[i] : 0) + sum_j A[i * lda + j] x[j] for a matrix in shared memory: rows over warps (RB at a time, independent
+// reduction chains), columns over lanes — consecutive lanes read consecutive doubles, so there are no bank conflicts whatever
+// the leading dimension (a row per thread is a 16-way conflict for ld = 8 mod 16).  No barrier inside.
+template <int RB = 7> HD void matvec_rows(const double *A, int lda, int rows, int cols, const double *x, const double *y0, double *y) {
+  for (int base = WARP_ID * RB; base < rows; base += NWARPS * RB) {
+    double acc[RB];
+#pragma unroll
+    for (int r = 0; r < RB; r++) acc[r] = 0.0;
+    LANE_FOR(j, cols) {
+      const double xj = x[j];
+#pragma unroll
+      for (int r = 0; r < RB; r++)
+        if (base + r < rows) acc[r] += A[(base + r) * lda + j] * xj;
+    }
+#pragma unroll
+    for (int r = 0; r < RB; r++) acc[r] = WARP_SUM(acc[r]);
+    if (LANE0) {
+#pragma unroll
+      for (int r = 0; r < RB; r++)
+        if (base + r < rows) y[base + r] = acc[r] + (y0 ? y0[base + r] : 0.0);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ blocked Cholesky / triangular solves (panel width 8)
 // In-place lower Cholesky of A (n x n, ld) by 8-wide panels.  Dinv receives the inverses of the diagonal blocks (8 x 8
 // lower, row-major, 64 doubles per panel), which turn the triangular solves below into small GEMMs.

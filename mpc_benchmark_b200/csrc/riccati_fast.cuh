@@ -120,7 +120,7 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
     PHASE(0);
     // 2. G = chol(I + mu_d P);  pv = p + P f
     PAR_FOR(e, N * N) { int i = e / N, j = e % N; G[i * LDN + j] = mu_d * P[i * LDN + j] + ((i == j) ? 1.0 : 0.0); }
-    PAR_FOR(i, N) { double s = p[i]; for (int j = 0; j < N; j++) s += P[i * LDN + j] * fb[j]; pv[i] = s; }
+    matvec_rows(P, LDN, N, N, fb, p, pv);
     SYNC();
     PHASE(1);
     chol_mma<NBLK>(G, LDN, dinv);
@@ -181,7 +181,7 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
     PHASE(3);
     // 4. Lambda^-1 = Linv' Linv (into G);  5. Pt = Lambda^-1 P (into Li), pt = Lambda^-1 pv
     mma_tn(NBLK, NBLK, N, Li, LDN, Li, LDN, G, LDN, nullptr, 0, 0, 0, false, true);
-    PAR_FOR(i, N) { double s = 0; for (int j = 0; j < N; j++) s += G[i * LDN + j] * pv[j]; pt[i] = s; }
+    matvec_rows(G, LDN, N, N, pv, nullptr, pt);
     mma_tn(NBLK, NBLK, N, G, LDN, P, LDN, Li, LDN, nullptr, 0, 0, 0, false);
     PHASE(4);
     // 6. W = Pt [A B];  7. H = H_k + [A B]' W;  gh = g + [A B]' pt
@@ -215,7 +215,7 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
     SYNC();
     PAR_FOR(e, MR * ldz) {
       int i = e / ldz, c = e % ldz;
-      Z[e] = (i >= M || c >= ncol) ? 0.0 : ((c == 0) ? gh[N + i] : (c < NR ? H[(c - 1) * LDH + N + i] : CD[(c - NR) * NZ + N + i]));
+      Z[e] = (i >= M || c >= ncol) ? 0.0 : ((c == 0) ? gh[N + i] : (c < NR ? H[(N + i) * LDH + c - 1] : CD[(c - NR) * NZ + N + i])); // H_ux row i (H is symmetric to rounding): conflict-free
     }
     SYNC();
     PHASE(6);
@@ -318,7 +318,7 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
     //    Sh Ku = H[N:, 0:N]' Z[:, 1:] runs on the DMMA pipe (K = MP, zero rows beyond M); the active-row part is usually empty.
     PAR_FOR(i, N) {
       double s = gh[i];
-      for (int l = 0; l < M; l++) s += H[i * LDH + N + l] * Z[l * ldz];
+      for (int l = 0; l < M; l++) s += H[(N + l) * LDH + i] * Z[l * ldz]; // H_ux rows (as the DMMA update below): conflict-free
       for (int r = 0; r < nca; r++) s += CD[r * NZ + i] * Kv[r * NR];
       p[i] = s;
     }
