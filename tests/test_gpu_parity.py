@@ -306,3 +306,39 @@ def test_non_finite_input_is_contained():
     good = s.run(prob["xs"], prob["us"], max_iters=5)
     assert np.array_equal(r.xs[0], good.xs[0]) and np.array_equal(r.us[2], good.us[2])
     s.close()
+
+
+@pytest.mark.parametrize("maker", [problems.cent_standing_problem, problems.full_standing_problem, problems.kino_standing_problem])
+def test_shortest_horizons(oracle, maker):
+    """Edge sizes: horizons of 1 and 2 knots, batch 1 (loop bounds, terminal-only coupling, prefetch one knot ahead)."""
+    for T in (1, 2):
+        prob = maker(batch=1, T=T)
+        xs, us = perturbed(prob, oracle, 11 + T, sx=0.003, su=0.3)
+        prob["x0"] = xs[:, 0].copy()
+        s = BatchSolver(prob["robot"], prob["cfg"], 1)
+        s.setup(prob["knots"], prob["terms"], prob["x0"])
+        res = s.run(xs, us, max_iters=3)
+        ref = oracle.solve(prob, max_iters=3, xs=xs, us=us)
+        assert list(res.num_iters) == [i.num_iters for i in ref["info"]]
+        assert rel(res.xs, ref["xs"]) < RTOL and rel(res.us, ref["us"]) < RTOL, T
+        s.close()
+
+
+def test_single_support_only_horizon(oracle):
+    """A horizon that is in single support throughout (one rigid contact in every knot, 61 constraint rows)."""
+    B, T = 2, 15
+    prob = problems.full_standing_problem(batch=B, T=T)
+    f_full = np.array([0, 0, prob["mass"] * problems.GRAVITY, 0, 0, 0.0])
+    zero = np.zeros(6)
+    lift = np.array(prob["rf"], float)
+    lift[11] += 0.02
+    for b in range(B):
+        for k in range(T):
+            prob["knots"][b * T + k] = problems.full_knot([True, False], prob["lf"], lift, f_full, zero)
+    s = BatchSolver(prob["robot"], prob["cfg"], B)
+    s.setup(prob["knots"], prob["terms"], prob["x0"])
+    res = s.run(prob["xs"], prob["us"], max_iters=4)
+    ref = oracle.solve(prob, max_iters=4, inst_threads=B)
+    assert list(res.num_iters) == [i.num_iters for i in ref["info"]]
+    assert rel(res.xs, ref["xs"]) < RTOL and rel(res.us, ref["us"]) < RTOL
+    s.close()
