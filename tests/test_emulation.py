@@ -36,7 +36,8 @@ def test_lq_blocks(oracle, maker):
         assert abs(o["cost"] - e["scal"][k, 0]) <= 1e-11 * max(1, abs(o["cost"]))
 
 
-@pytest.mark.parametrize("maker,T", [(problems.cent_standing_problem, 100), (problems.full_standing_problem, 25), (problems.kino_standing_problem, 25)])
+@pytest.mark.parametrize("maker,T", [(problems.cent_standing_problem, 100), (problems.full_standing_problem, 25), (problems.kino_standing_problem, 25),
+                                     (problems.cent_standing_problem, 1), (problems.full_standing_problem, 1), (problems.kino_standing_problem, 2)])
 def test_cold_solve(oracle, maker, T):
     prob = maker(T=T)
     r = oracle.solve(prob)
