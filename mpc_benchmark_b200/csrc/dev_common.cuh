@@ -320,6 +320,51 @@ template <int RB = 7> HD void matvec_rows(const double *A, int lda, int rows, in
   }
 }
 
+// Group-wide reduction of four per-thread partials (two sums, two maxima): butterfly inside each warp, one slot per warp in
+// `scratch` (>= 4 * warps doubles), combined by thread 0 into out[0..3] after the barrier.  Under emulation the single
+// "thread" already holds the totals.
+HD void reduce_sum2_max2(double s0, double s1, double m0, double m1, double *scratch, double *out) {
+#ifdef MPC_HOST_EMU
+  out[0] = s0; out[1] = s1; out[2] = m0; out[3] = m1;
+#else
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    m0 = fmax(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+    m1 = fmax(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+  }
+  if (LANE0) { scratch[4 * WARP_ID] = s0; scratch[4 * WARP_ID + 1] = s1; scratch[4 * WARP_ID + 2] = m0; scratch[4 * WARP_ID + 3] = m1; }
+  SYNC();
+  ONE_THREAD {
+    double a = 0, b = 0, c = 0, d = 0;
+    for (int w = 0; w < NWARPS; w++) { a += scratch[4 * w]; b += scratch[4 * w + 1]; c = fmax(c, scratch[4 * w + 2]); d = fmax(d, scratch[4 * w + 3]); }
+    out[0] = a; out[1] = b; out[2] = c; out[3] = d;
+  }
+#endif
+  SYNC();
+}
+// Stable compaction of the indices r < n (n <= threads of the group) whose flag is set: idx[0..count) ascending, *count.
+// Warp ballots + per-warp offsets through `scratch` (>= warps ints); serial under emulation.
+HD void compact_flags(const int32_t *flags, int n, int32_t *idx, int32_t *count, int32_t *scratch) {
+#ifdef MPC_HOST_EMU
+  int c = 0;
+  for (int r = 0; r < n; r++) if (flags[r]) idx[c++] = r;
+  *count = c;
+#else
+  const int t = threadIdx.x, lane = t & 31;
+  const bool f = (t < n) && flags[t] != 0;
+  const unsigned mask = __ballot_sync(0xffffffffu, f);
+  if (lane == 0) scratch[WARP_ID] = __popc(mask);
+  SYNC();
+  int off = 0;
+  for (int w = 0; w < WARP_ID; w++) off += scratch[w];
+  if (f) idx[off + __popc(mask & ((1u << lane) - 1u))] = t;
+  if (t == NTHREADS - 1) *count = off + __popc(mask);
+#endif
+  SYNC();
+}
+
 // ------------------------------------------------------------------ blocked Cholesky / triangular solves (panel width 8)
 // In-place lower Cholesky of A (n x n, ld) by 8-wide panels.  Dinv receives the inverses of the diagonal blocks (8 x 8
 // lower, row-major, 64 doubles per panel), which turn the triangular solves below into small GEMMs.
