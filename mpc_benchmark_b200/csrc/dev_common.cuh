@@ -474,6 +474,57 @@ HD void chol_blocked(double *A, int n, int ld, double *Dinv) {
     SYNC();
   }
 }
+// In-place inverse of an SPD matrix A (n x n, ld; n even): blocked Cholesky, X = L^-1 by one warp per 8-wide block column
+// (independent forward-substitution chains, warp-level barriers only), then A <- X' X on 2 x 2 register tiles (full symmetric
+// result).  Turns every later solve with A into a barrier-free matrix product.  Dinv: 64 doubles per diagonal block;
+// Ls: n * n + 64 * warps doubles of scratch.
+HD void spd_inverse_blocked(double *A, int n, int ld, double *Dinv, double *Ls) {
+  chol_blocked(A, n, ld, Dinv);
+  const int nb = (n + CB - 1) / CB;
+  double *tt = Ls + n * n + 64 * WARP_ID;
+  for (int jb = WARP_ID; jb < nb; jb += NWARPS) {
+    for (int ib = jb; ib < nb; ib++) {
+      WARP_FOR(e, 64) { // tt = E_ij - sum_k L_ik X_kj
+        const int r = e >> 3, c = e & 7, gi = CB * ib + r, gj = CB * jb + c;
+        double s = 0.0;
+        if (gi < n && gj < n) {
+          s = (gi == gj) ? 1.0 : 0.0;
+          for (int kb = jb; kb < ib; kb++)
+            for (int q = 0; q < CB; q++) s -= A[gi * ld + CB * kb + q] * Ls[(CB * kb + q) * n + gj];
+        }
+        tt[e] = s;
+      }
+      WARP_SYNC();
+      WARP_FOR(e, 64) { // X_ij = Dinv_i tt
+        const int r = e >> 3, c = e & 7, gi = CB * ib + r, gj = CB * jb + c;
+        if (gi < n && gj < n) {
+          const double *Di = Dinv + 64 * ib;
+          double s = 0.0;
+          for (int q = 0; q <= r; q++) s += Di[r * CB + q] * tt[q * CB + c];
+          Ls[gi * n + gj] = s;
+        }
+      }
+      WARP_SYNC();
+    }
+  }
+  SYNC();
+  const int th = n / 2;
+  PAR_FOR(t, th * th) {
+    const int ti = t / th, tj = t % th;
+    if (tj > ti) continue;
+    const int i0 = 2 * ti, j0 = 2 * tj;
+    double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
+    for (int k = i0; k < n; k++) { // X is lower triangular: rows k >= max(i, j)
+      const double xi0 = Ls[k * n + i0], xi1 = Ls[k * n + i0 + 1], xj0 = Ls[k * n + j0], xj1 = Ls[k * n + j0 + 1];
+      a00 += xi0 * xj0; a01 += xi0 * xj1; a10 += xi1 * xj0; a11 += xi1 * xj1;
+    }
+    A[i0 * ld + j0] = a00; A[j0 * ld + i0] = a00;
+    A[i0 * ld + j0 + 1] = a01; A[(j0 + 1) * ld + i0] = a01;
+    A[(i0 + 1) * ld + j0] = a10; A[j0 * ld + i0 + 1] = a10;
+    A[(i0 + 1) * ld + j0 + 1] = a11; A[(j0 + 1) * ld + i0 + 1] = a11;
+  }
+  SYNC();
+}
 // Solve L L^T X = B in place (B: n x nrhs, ldb) with the diagonal-block inverses from chol_blocked.
 HD void trsm_blocked(const double *L, int n, int ld, const double *Dinv, double *B, int nrhs, int ldb) {
   // forward: L Y = B

@@ -334,6 +334,10 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
   mb_kinematics(m, w);
   EPH(1);
   const int nact = w.nact, nk = 6 * nact;
+  // derivative kernel: scratch of the explicit mass-matrix inverse, borrowed from X (free until the tangent is built):
+  // [L^-1 (NV x NV) | 4 x 64 warp scratch | raw right-hand sides [tau - b | J'] (NV x 13)]; values kernel: solve in place in Y
+  double *Ls = w.X;
+  double *Yr = DERIV ? Ls + NV * NV + 4 * 64 : w.Y;
   const double a0[6] = {-rb.gravity[0], -rb.gravity[1], -rb.gravity[2], 0, 0, 0};
   // bias accelerations (qdd = 0, gravity folded in) and bias forces
   PAR_FOR(b, NB) {
@@ -383,14 +387,29 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
   PAR_FOR(j, NV) { // b = S^T Fsub ; rhs column 0 = tau - b ; columns 1.. = J^T
     double bj = dot6(w.S + 6 * j, w.Fsub + 6 * body_of_dof(j));
     w.bvec[j] = bj;
-    w.Y[j * 13] = (j >= 6 ? w.u[j - 6] : 0.0) - bj;
-    for (int r = 0; r < nk; r++) w.Y[j * 13 + 1 + r] = w.Jf[(6 * w.act[r / 6] + r % 6) * NV + j];
+    Yr[j * 13] = (j >= 6 ? w.u[j - 6] : 0.0) - bj;
+    for (int r = 0; r < nk; r++) Yr[j * 13 + 1 + r] = w.Jf[(6 * w.act[r / 6] + r % 6) * NV + j];
   }
   SYNC();
   EPH(2);
-  chol_blocked(w.M, NV, NV, w.dinvM);
-  EPH(3);
-  trsm_blocked(w.M, NV, NV, w.dinvM, w.Y, 1 + nk, 13);
+  if (DERIV) {
+    // M <- M^-1 explicitly (one Cholesky + inverse factor + product): every solve with the mass matrix is then a plain matrix
+    // product without barriers (Y here, the 78 right-hand sides of the tangent later).  The values-only kernel has just the
+    // 13 columns of Y and keeps the factor + blocked triangular solves.
+    spd_inverse_blocked(w.M, NV, NV, w.dinvM, Ls);
+    EPH(3);
+    PAR_FOR(e, NV * (1 + nk)) {
+      const int i = e / (1 + nk), c = e % (1 + nk);
+      double s = 0;
+      for (int k = 0; k < NV; k++) s += w.M[i * NV + k] * Yr[k * 13 + c];
+      w.Y[i * 13 + c] = s;
+    }
+    SYNC();
+  } else {
+    chol_blocked(w.M, NV, NV, w.dinvM);
+    EPH(3);
+    trsm_blocked(w.M, NV, NV, w.dinvM, w.Y, 1 + nk, 13);
+  }
   PAR_FOR(e, nk * (nk + 1)) {
     int r = e / (nk + 1), c = e % (nk + 1);
     const double *Jr = w.Jf + (6 * w.act[r / 6] + r % 6) * NV;
@@ -538,7 +557,18 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
     }
     SYNC();
     EPH(7);
-    trsm_blocked(w.M, NV, NV, w.dinvM, w.X, FNZ, FNZ); // X = M^-1 R1
+    PAR_FOR(z, FNZ) { // X = M^-1 R1, one column per thread (column in registers, written back in place)
+      double col[NV];
+#pragma unroll
+      for (int k = 0; k < NV; k++) col[k] = w.X[k * FNZ + z];
+      for (int i = 0; i < NV; i++) {
+        double s = 0;
+#pragma unroll
+        for (int k = 0; k < NV; k++) s += w.M[i * NV + k] * col[k];
+        w.X[i * FNZ + z] = s;
+      }
+    }
+    SYNC();
     EPH(8);
     PAR_FOR(e, nk * FNZ) {
       int r = e / FNZ, z = e % FNZ;
