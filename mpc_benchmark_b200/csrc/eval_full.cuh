@@ -419,8 +419,16 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
     else w.G[r * 12 + c - 1] = s + ((r == c - 1) ? cfg.mu_contact : 0.0);
   }
   SYNC();
-  chol_blocked(w.G, nk, 12, w.dinvG);
-  trsm_blocked(w.G, nk, 12, w.dinvG, w.rhs, 1, 1);
+  if (DERIV) { // G <- G^-1 as well (6 x 6 or 12 x 12): lambda now, the 78 columns of dlambda later, all without triangular solves
+    spd_inverse_blocked(w.G, nk, 12, w.dinvG, w.top); // `top` is free until the tangent columns are built
+    PAR_FOR(r, nk) { double s = 0; for (int c = 0; c < nk; c++) s += w.G[r * 12 + c] * w.rhs[c]; w.astar[r] = s; }
+    SYNC();
+    PAR_FOR(r, nk) w.rhs[r] = w.astar[r];
+    SYNC();
+  } else {
+    chol_blocked(w.G, nk, 12, w.dinvG);
+    trsm_blocked(w.G, nk, 12, w.dinvG, w.rhs, 1, 1);
+  }
   PAR_FOR(i, NV) {
     double s = w.Y[i * 13];
     for (int r = 0; r < nk; r++) s += w.Y[i * 13 + 1 + r] * w.rhs[r];
@@ -570,20 +578,39 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
     }
     SYNC();
     EPH(8);
-    PAR_FOR(e, nk * FNZ) {
-      int r = e / FNZ, z = e % FNZ;
-      const double *Jr = w.Jf + (6 * w.act[r / 6] + r % 6) * NV;
-      double s = -w.DL[e];
-      for (int i = 0; i < NV; i++) s += Jr[i] * w.X[i * FNZ + z];
-      w.DL[e] = s;
-    }
-    SYNC();
-    trsm_blocked(w.G, nk, 12, w.dinvG, w.DL, FNZ, FNZ); // dlam
-    PAR_FOR(e, NV * FNZ) {
-      int i = e / FNZ, z = e % FNZ;
-      double s = -w.X[e];
-      for (int r = 0; r < nk; r++) s += w.Y[i * 13 + 1 + r] * w.DL[r * FNZ + z];
-      w.X[e] = s; // da/dz
+    PAR_FOR(z, FNZ) { // per column of z: dlam = G^-1 (J X - DL), then da/dz = -X + Y dlam (X column and dlam in registers)
+      double xc[NV], t[12], dl[12];
+#pragma unroll
+      for (int i = 0; i < NV; i++) xc[i] = w.X[i * FNZ + z];
+#pragma unroll
+      for (int r = 0; r < 12; r++) {
+        t[r] = 0.0;
+        if (r < nk) {
+          const double *Jr = w.Jf + (6 * w.act[r / 6] + r % 6) * NV;
+          double s = -w.DL[r * FNZ + z];
+#pragma unroll
+          for (int i = 0; i < NV; i++) s += Jr[i] * xc[i];
+          t[r] = s;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 12; r++) {
+        dl[r] = 0.0;
+        if (r < nk) {
+          double s = 0;
+#pragma unroll
+          for (int c = 0; c < 12; c++) if (c < nk) s += w.G[r * 12 + c] * t[c];
+          dl[r] = s;
+          w.DL[r * FNZ + z] = s;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NV; i++) {
+        double s = -xc[i];
+#pragma unroll
+        for (int r = 0; r < 12; r++) if (r < nk) s += w.Y[i * 13 + 1 + r] * dl[r];
+        w.X[i * FNZ + z] = s; // da/dz
+      }
     }
     SYNC();
   }
