@@ -173,6 +173,29 @@ template <class WS> HD void mb_kinematics(const DevModel &m, WS &w) {
   SYNC();
 }
 
+// Composite B of every subtree, Bc_b e_c = sum_{k in sub(b)} I_k (e_c x v_k) + e_c x* (I_k v_k) + v_k x* (I_k e_c):
+// first each body's own 6 x 6 block (one column per work item, all bodies in parallel), then the subtree sums with one
+// thread per matrix element walking the bodies leaves-to-root (bodies are ordered parents-first, so a child is complete
+// before it is added to its parent): no barrier inside the accumulation and no O(subtree) work per item.
+template <class WS> HD void mb_composite_B(const DevModel &m, WS &w) {
+  PAR_FOR(e, NB * 6) {
+    const int b = e / 6, c = e % 6;
+    double ec[6] = {0, 0, 0, 0, 0, 0}, t0[6], t1[6], t2[6], t3[6], t4[6];
+    ec[c] = 1.0;
+    cross_mm(ec, w.v + 6 * b, t0);
+    inertia_mul(w.I + 10 * b, t0, t1);
+    cross_mf(ec, w.hb + 6 * b, t2);
+    inertia_mul(w.I + 10 * b, ec, t3);
+    cross_mf(w.v + 6 * b, t3, t4);
+    for (int i = 0; i < 6; i++) w.Bc[36 * b + 6 * i + c] = t1[i] + t2[i] + t4[i];
+  }
+  SYNC();
+  PAR_FOR(e, 36) {
+    for (int b = NB - 1; b > 0; b--) w.Bc[36 * m.rb.parent[b] + e] += w.Bc[36 * b + e];
+  }
+  SYNC();
+}
+
 // centroidal momentum residual + Jacobian [dh/dq | A_g] (6 x 56), pose residuals + Jacobians, state error and — for running
 // knots (gap_out != nullptr) — the base part of the semi-implicit Euler step, the shooting gap and the 6x6 Lie-group blocks
 // P1 = Jlog6(D) Jexp6(dq), P2 = Jlog6(D) Ad(exp6(dq))^-1, E6 = -Jlog6(D) Ad(D^-1), T6 = -E6^-1 = Ad(D) Jexp6(log6 D).
@@ -481,24 +504,7 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
       w.Fsub[e] = s;
     }
     EPH(5);
-    PAR_FOR(e, NB * 6) { // composite B: Bc_b e_c = sum_{k in sub(b)} I_k (e_c x v_k) + e_c x* (I_k v_k) + v_k x* (I_k e_c)
-      int b = e / 6, c = e % 6;
-      uint32_t mask = m.sub_mask[b];
-      double ec[6] = {0, 0, 0, 0, 0, 0}, col[6] = {0, 0, 0, 0, 0, 0};
-      ec[c] = 1.0;
-      for (int k = b; k < NB; k++)
-        if (mask >> k & 1) {
-          double t0[6], t1[6], t2[6], t3[6], t4[6];
-          cross_mm(ec, w.v + 6 * k, t0);
-          inertia_mul(w.I + 10 * k, t0, t1);
-          cross_mf(ec, w.hb + 6 * k, t2);
-          inertia_mul(w.I + 10 * k, ec, t3);
-          cross_mf(w.v + 6 * k, t3, t4);
-          for (int i = 0; i < 6; i++) col[i] += t1[i] + t2[i] + t4[i];
-        }
-      for (int i = 0; i < 6; i++) w.Bc[36 * b + 6 * i + c] = col[i];
-    }
-    SYNC();
+    mb_composite_B(m, w);
     EPH(6);
     PAR_FOR(e, 2 * m.npairs) {
       int kind = e / m.npairs, p = e % m.npairs;

@@ -149,24 +149,7 @@ template <bool DERIV> HD void eval_kino_knot(const DevModel &m, const KnotIO &io
       for (int d = b; d < NB; d++) if (mask >> d & 1) s += w.f[6 * d + c];
       w.Fsub[e] = s;
     }
-    PAR_FOR(e, NB * 6) { // composite B (same as eval_full)
-      int b = e / 6, c = e % 6;
-      uint32_t mask = m.sub_mask[b];
-      double ec[6] = {0, 0, 0, 0, 0, 0}, col[6] = {0, 0, 0, 0, 0, 0};
-      ec[c] = 1.0;
-      for (int k = b; k < NB; k++)
-        if (mask >> k & 1) {
-          double t0[6], t1[6], t2[6], t3[6], t4[6];
-          cross_mm(ec, w.v + 6 * k, t0);
-          inertia_mul(w.I + 10 * k, t0, t1);
-          cross_mf(ec, w.hb + 6 * k, t2);
-          inertia_mul(w.I + 10 * k, ec, t3);
-          cross_mf(w.v + 6 * k, t3, t4);
-          for (int i = 0; i < 6; i++) col[i] += t1[i] + t2[i] + t4[i];
-        }
-      for (int i = 0; i < 6; i++) w.Bc[36 * b + 6 * i + c] = col[i];
-    }
-    SYNC();
+    mb_composite_B(m, w);
     PAR_FOR(e, 2 * NV) { // top vectors: d F_o/d q_j (kind 0), d F_o/d v_j (kind 1)
       int kind = e / NV, j = e % NV, J = body_of_dof(j), pJ = rb.parent[J];
       const double *s = w.S + 6 * j;
