@@ -57,7 +57,7 @@ template <bool WITH_DERIV> struct FullWsT {
   static constexpr int CJ1 = WITH_DERIV ? 6 * FN : 8, CJ2 = WITH_DERIV ? 2 * 6 * NV : 8, M6 = WITH_DERIV ? 36 : 1, ZS = WITH_DERIV ? FNZ : 8;
   double x[NQ + NV], u[FM], xn[NQ + NV];
   double kn[sizeof(mpc_knot_t) / 8];
-  double oM[NB * 12], S[NV * 6], v[NB * 6], a[NB * 6], I[NB * 10], Ic[NB * 10], sc[2 * NB];
+  double oM[NB * 12], S[NV * 6], v[NB * 6], a[NB * 6], I[NB * 10], Ic[NB * 10];
   double hb[NB * 6], hsub[NB * 6], f[NB * 6], Fsub[NB * 6];
   union { // Bc is dead once the derivative columns are built; the cost Jacobians are built afterwards
     double Bc[BCS];
@@ -95,24 +95,29 @@ using FullWs = FullWsT<true>;
 template <class WS> HD void mb_kinematics(const DevModel &m, WS &w) {
   const mpc_robot_t &rb = m.rb;
   const double *q = w.x, *qd = w.x + NQ;
-  PAR_FOR(b, NB) { double sn = 0, cs = 1; if (b > 0) sincos(q[6 + b], &sn, &cs); w.sc[2 * b] = sn; w.sc[2 * b + 1] = cs; } // off the level chain
+  // every body's placement relative to its parent (joint placement x joint rotation) is independent of the tree: all bodies
+  // in parallel, off the level chain; the chain itself is then one SE(3) product per level
+  PAR_FOR(b, NB) {
+    double *o = w.oM + 12 * b;
+    if (b == 0) { quat_to_R(q + 3, o); o[9] = q[0]; o[10] = q[1]; o[11] = q[2]; }
+    else {
+      // Rodrigues with the unit joint axis: R = I + sin(q) [a]x + (1 - cos q) [a]x^2
+      double sn, cs, jr[12], K[9], K2[9];
+      sincos(q[6 + b], &sn, &cs);
+      skew3(rb.axis[b], K); mat3_mul(K, K, K2);
+      for (int i = 0; i < 9; i++) jr[i] = ((i % 4 == 0) ? 1.0 : 0.0) + sn * K[i] + (1.0 - cs) * K2[i];
+      jr[9] = jr[10] = jr[11] = 0;
+      se3_mul(rb.jplace[b], jr, o);
+    }
+  }
   SYNC();
-  for (int l = 0; l < m.nlevels; l++) {
+  for (int l = 1; l < m.nlevels; l++) {
     int n = m.level_start[l + 1] - m.level_start[l];
     PAR_FOR(t, n) {
       int b = m.level_body[m.level_start[l] + t];
-      double *o = w.oM + 12 * b;
-      if (b == 0) { quat_to_R(q + 3, o); o[9] = q[0]; o[10] = q[1]; o[11] = q[2]; }
-      else {
-        // Rodrigues with the unit joint axis: R = I + sin(q) [a]x + (1 - cos q) [a]x^2
-        double jr[12], t1[12], K[9], K2[9];
-        skew3(rb.axis[b], K); mat3_mul(K, K, K2);
-        const double sn = w.sc[2 * b], omc = 1.0 - w.sc[2 * b + 1];
-        for (int i = 0; i < 9; i++) jr[i] = ((i % 4 == 0) ? 1.0 : 0.0) + sn * K[i] + omc * K2[i];
-        jr[9] = jr[10] = jr[11] = 0;
-        se3_mul(rb.jplace[b], jr, t1);
-        se3_mul(w.oM + 12 * rb.parent[b], t1, o);
-      }
+      double loc[12];
+      for (int i = 0; i < 12; i++) loc[i] = w.oM[12 * b + i];
+      se3_mul(w.oM + 12 * rb.parent[b], loc, w.oM + 12 * b);
     }
     SYNC();
   }

@@ -19,7 +19,7 @@ template <bool WITH_DERIV> struct KinoWsT {
   static constexpr int CV = WITH_DERIV ? 12 * FN : 8, JCD = WITH_DERIV ? 6 * KNZ : 8, HQ = WITH_DERIV ? 6 * NV : 8;
   double x[NQ + NV], u[KM], xn[NQ + NV];
   double kn[sizeof(mpc_knot_t) / 8];
-  double oM[NB * 12], S[NV * 6], v[NB * 6], a[NB * 6], I[NB * 10], Ic[NB * 10], sc[2 * NB];
+  double oM[NB * 12], S[NV * 6], v[NB * 6], a[NB * 6], I[NB * 10], Ic[NB * 10];
   double hb[NB * 6], hsub[NB * 6], f[NB * 6], Fsub[NB * 6];
   union {
     double Bc[BCS];
