@@ -428,6 +428,66 @@ HD void chol_diag_block(double *A, int k0, int bw, int ld, double *Di) {
       Di[r * CB + c] = (r < bw && c < bw) ? X[r][c] : 0.0;
     }
 }
+#ifndef MPC_HOST_EMU
+// Device version called by ALL lanes of the group's warp 0: lane 0 factors the block exactly as above (the dependent
+// rsqrt / FMA chain stays in one thread's registers, no shuffles on it), then the eight columns of the inverse are built
+// by eight lanes side by side from the factor published through Di.  A lone thread is issue-bound on the ~350 instructions
+// of the inverse; eight lanes share them.
+__device__ __forceinline__ void chol_diag_block_warp0(double *A, int k0, int bw, int ld, double *Di) {
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) {
+    double L[CB][CB];
+#pragma unroll
+    for (int r = 0; r < CB; r++)
+#pragma unroll
+      for (int c = 0; c < CB; c++) L[r][c] = (c <= r) ? ((r < bw) ? A[(k0 + r) * ld + k0 + c] : ((r == c) ? 1.0 : 0.0)) : 0.0;
+#pragma unroll
+    for (int j = 0; j < CB; j++) {
+      const double d = fast_rsqrt(L[j][j]);
+      L[j][j] = L[j][j] * d;
+      if (j < bw) A[(k0 + j) * ld + k0 + j] = L[j][j];
+      Di[j * CB + j] = d; // reciprocal of the diagonal entry (scratch for the inverse below)
+#pragma unroll
+      for (int r = j + 1; r < CB; r++) {
+        L[r][j] *= d;
+        if (r < bw) A[(k0 + r) * ld + k0 + j] = L[r][j];
+        Di[r * CB + j] = L[r][j];
+      }
+#pragma unroll
+      for (int r = j + 1; r < CB; r++)
+#pragma unroll
+        for (int c = j + 1; c <= r; c++) L[r][c] -= L[r][j] * L[c][j];
+    }
+  }
+  __syncwarp();
+  double Lf[CB][CB], dd[CB], X[CB];
+  const int c = lane & 7;
+#pragma unroll
+  for (int i = 0; i < CB; i++) {
+    dd[i] = Di[i * CB + i];
+#pragma unroll
+    for (int t = 0; t < CB; t++) Lf[i][t] = (t < i) ? Di[i * CB + t] : 0.0;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int t = 0; t < CB; t++) X[t] = (t == c) ? 1.0 : 0.0;
+#pragma unroll
+  for (int t = 0; t < CB; t++) {
+    X[t] *= dd[t]; // rows above the diagonal stay 0
+#pragma unroll
+    for (int i = t + 1; i < CB; i++) X[i] -= Lf[i][t] * X[t];
+  }
+  if (lane < CB) {
+#pragma unroll
+    for (int i = 0; i < CB; i++) Di[i * CB + c] = (i < bw && c < bw) ? X[i] : 0.0;
+  }
+  __syncwarp();
+}
+#define DIAG_BLOCK(A, k0, bw, ld, Di) do { if (threadIdx.x < 32) mpcdev::chol_diag_block_warp0(A, k0, bw, ld, Di); } while (0)
+#else
+#define DIAG_BLOCK(A, k0, bw, ld, Di) chol_diag_block(A, k0, bw, ld, Di)
+#endif
+
 // Blocked Cholesky (lower, in place): per 8-wide panel, one thread factors + inverts the diagonal block, the panel below it
 // is multiplied by the inverse, and the trailing matrix is updated on 2 x 2 register tiles.  (The 56 x 56 and padded control
 // blocks of the Riccati kernel use the tensor-core version with look-ahead, chol_mma in dmma.cuh; a look-ahead variant of
@@ -436,7 +496,7 @@ HD void chol_blocked(double *A, int n, int ld, double *Dinv) {
   for (int k0 = 0; k0 < n; k0 += CB) {
     const int bw = (n - k0 < CB) ? n - k0 : CB;
     const double *Di = Dinv + (k0 / CB) * CB * CB;
-    ONE_THREAD chol_diag_block(A, k0, bw, ld, Dinv + (k0 / CB) * CB * CB);
+    DIAG_BLOCK(A, k0, bw, ld, Dinv + (k0 / CB) * CB * CB);
     SYNC();
     // panel below the diagonal block: L[i, k0:k0+bw] = A[i, k0:k0+bw] * Dinv^T, one row per work item
     const int rem = n - k0 - bw, r0 = k0 + bw;

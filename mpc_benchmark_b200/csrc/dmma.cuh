@@ -126,7 +126,7 @@ HD void tile_trsm(double *A, int ld, int i0, int k0, const double *Di) {
 // inverts the next diagonal block in registers while warps 1.. update the remaining tiles of the trailing matrix.
 // Only the lower triangle (and the full diagonal tiles) of A is referenced; Dinv receives the NB inverses of the diagonal blocks.
 template <int NB> HD void chol_mma(double *A, int ld, double *Dinv) {
-  ONE_THREAD chol_diag_block(A, 0, 8, ld, Dinv);
+  DIAG_BLOCK(A, 0, 8, ld, Dinv);
   SYNC();
   for (int kb = 0; kb + 1 < NB; kb++) {
     const int k0 = 8 * kb, nt = NB - 1 - kb;
@@ -135,7 +135,7 @@ template <int NB> HD void chol_mma(double *A, int ld, double *Dinv) {
     SYNC();
     WARP_TILE_FOR(p, nt) tile_syrk(A, ld, 8 * (kb + 1 + p), 8 * (kb + 1), k0);
     SYNC();
-    ONE_THREAD chol_diag_block(A, 8 * (kb + 1), 8, ld, Dinv + 64 * (kb + 1));
+    DIAG_BLOCK(A, 8 * (kb + 1), 8, ld, Dinv + 64 * (kb + 1));
     const int m = nt - 1;
     WARP_TILE_FOR_REST(p, m * (m + 1) / 2) {
       int ti = 0;
