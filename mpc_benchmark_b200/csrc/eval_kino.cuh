@@ -257,6 +257,8 @@ template <bool DERIV> HD void eval_kino_knot(const DevModel &m, const KnotIO &io
   mb_cost_terms(m, w, kn.lf_ref, kn.rf_ref, DERIV, io.gap);
 
   // ---- constraint values, multiplier estimates, activity
+  // every thread accumulates the merit pieces of the rows / coordinates it owns; one group-wide reduction at the end
+  double acc_cost = 0.0, acc_pen = 0.0, acc_prim = 0.0, acc_inner = 0.0;
   PAR_FOR(r, KNC) {
     int type = -1; double hv = 0, lo = 0, hi = 0;
     if (r < 22) { type = 2; hv = -w.x[7 + r]; lo = -rb.q_hi[r]; hi = -rb.q_lo[r]; }
@@ -268,51 +270,34 @@ template <bool DERIV> HD void eval_kino_knot(const DevModel &m, const KnotIO &io
       }
     }
     int act = 0; double prim = 0;
-    double vp = vplus_row(type, hv, io.v_prev[r], io.mu, lo, hi, act, prim);
+    const double vp = vplus_row(type, hv, io.v_prev[r], io.mu, lo, hi, act, prim), dv = vp - io.v[r];
     w.ctype[r] = type; w.late.hval[r] = hv; w.late.vpl[r] = vp; w.isact[r] = act;
-    w.late.dbr[r] = io.mu * (vp - io.v[r]);
-    w.late.rowtmp[r] = fabs(prim);
+    w.late.dbr[r] = io.mu * dv;
     io.h[r] = hv;
-  }
-  PAR_FOR(i, FN) { w.lpl[i] = io.lam_n_prev[i] + w.fbr[i] / io.mu; w.dx[i] = w.fbr[i]; }
-  SYNC();
-  PAR_FOR(i, FN) w.fbr[i] = io.mu * (w.lpl[i] - io.lam_n[i]);
-  PAR_FOR(c, 8) {
-    double pen = 0, prim = 0, inner = 0, cost = 0;
-    for (int r = c; r < KNC; r += 8) {
-      if (w.ctype[r] < 0) continue;
-      double dv = w.late.vpl[r] - io.v[r];
-      pen += 0.5 * io.mu * (w.late.vpl[r] * w.late.vpl[r] + dv * dv);
-      prim = fmax(prim, w.late.rowtmp[r]);
-      inner = fmax(inner, fabs(w.late.dbr[r]));
+    if (type >= 0) {
+      acc_pen += 0.5 * io.mu * (vp * vp + dv * dv);
+      acc_prim = fmax(acc_prim, fabs(prim));
+      acc_inner = fmax(acc_inner, fabs(io.mu * dv));
     }
-    for (int i = c; i < FN; i += 8) {
-      double dl = w.lpl[i] - io.lam_n[i];
-      pen += 0.5 * io.mu * (w.lpl[i] * w.lpl[i] + dl * dl);
-      prim = fmax(prim, fabs(w.dx[i]));
-      inner = fmax(inner, fabs(io.mu * dl));
-      cost += 0.5 * cfg.wx[i] * w.estate[i] * w.estate[i];
-    }
-    for (int i = c; i < KM; i += 8) { double e = w.u[i] - kn.u_ref[i]; cost += 0.5 * cfg.wu[i] * e * e; }
-    w.part[4 * c] = cost; w.part[4 * c + 1] = pen; w.part[4 * c + 2] = prim; w.part[4 * c + 3] = inner;
   }
-  ONE_THREAD {
-    int nca = 0;
-    for (int r = 0; r < KNC; r++) if (w.isact[r]) w.act_idx[nca++] = r;
-    w.nca = nca;
+  PAR_FOR(i, FN) {
+    const double gap = w.fbr[i], lp = io.lam_n_prev[i] + gap / io.mu, dl = lp - io.lam_n[i]; // fbr = gap here
+    w.lpl[i] = lp;
+    w.fbr[i] = io.mu * dl;
+    acc_pen += 0.5 * io.mu * (lp * lp + dl * dl);
+    acc_prim = fmax(acc_prim, fabs(gap));
+    acc_inner = fmax(acc_inner, fabs(io.mu * dl));
+    acc_cost += 0.5 * cfg.wx[i] * w.estate[i] * w.estate[i];
   }
-  SYNC();
-  ONE_THREAD {
-    double cost = 0, pen = 0, prim = 0, inner = 0;
-    for (int c = 0; c < 8; c++) { cost += w.part[4 * c]; pen += w.part[4 * c + 1]; prim = fmax(prim, w.part[4 * c + 2]); inner = fmax(inner, w.part[4 * c + 3]); }
-    for (int i = 0; i < 6; i++) {
-      double rcd = w.hd[i] + (i < 3 ? m.total_mass * rb.gravity[i] : 0.0);
-      cost += 0.5 * (cfg.w_cent[i] * w.rcent[i] * w.rcent[i] + kn.w_lf[i] * w.rpose[i] * w.rpose[i] + kn.w_rf[i] * w.rpose[6 + i] * w.rpose[6 + i] +
-                     cfg.w_centder[i] * rcd * rcd);
-    }
-    w.scal[SC_COST] = cost; w.scal[SC_PEN] = pen; w.scal[SC_PRIM] = prim; w.scal[SC_INNER] = inner; w.scal[SC_DUAL] = 0;
+  PAR_FOR(i, KM) { const double e = w.u[i] - kn.u_ref[i]; acc_cost += 0.5 * cfg.wu[i] * e * e; }
+  PAR_FOR(i, 6) {
+    const double rcd = w.hd[i] + (i < 3 ? m.total_mass * rb.gravity[i] : 0.0);
+    acc_cost += 0.5 * (cfg.w_cent[i] * w.rcent[i] * w.rcent[i] + kn.w_lf[i] * w.rpose[i] * w.rpose[i] + kn.w_rf[i] * w.rpose[6 + i] * w.rpose[6 + i] +
+                       cfg.w_centder[i] * rcd * rcd);
   }
-  SYNC();
+  reduce_sum2_max2(acc_cost, acc_pen, acc_prim, acc_inner, w.part, w.part + 16);
+  ONE_THREAD { w.scal[SC_COST] = w.part[16]; w.scal[SC_PEN] = w.part[17]; w.scal[SC_PRIM] = w.part[18]; w.scal[SC_INNER] = w.part[19]; w.scal[SC_DUAL] = 0; }
+  compact_flags(w.isact, KNC, w.act_idx, &w.nca, reinterpret_cast<int32_t *>(w.part));
   if (!DERIV) { PAR_FOR(i, SC_COUNT) io.scal[i] = w.scal[i]; return; }
 
   // ---- LQ blocks to HBM
