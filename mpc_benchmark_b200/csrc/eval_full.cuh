@@ -71,7 +71,7 @@ template <bool WITH_DERIV> struct FullWsT {
       double lxu[ZS], g[ZS], hval[FNC], vpl[FNC], dbr[FNC], rowtmp[FNC];
     } late;
   };
-  double bvec[NV], acc[NV];
+  double acc[NV];
   double ofoot[24], Jf[2 * 6 * NV];
   double vc[12], gam[12], astar[12], c1Mc2[24], JlAd[2 * M6], lam[12], lgc[12];
   union { // the contact-solve scratch is dead once da/dlam are formed; the multipliers are staged into it afterwards
@@ -414,7 +414,6 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
   SYNC();
   PAR_FOR(j, NV) { // b = S^T Fsub ; rhs column 0 = tau - b ; columns 1.. = J^T
     double bj = dot6(w.S + 6 * j, w.Fsub + 6 * body_of_dof(j));
-    w.bvec[j] = bj;
     Yr[j * 13] = (j >= 6 ? w.u[j - 6] : 0.0) - bj;
     for (int r = 0; r < nk; r++) Yr[j * 13 + 1 + r] = w.Jf[(6 * w.act[r / 6] + r % 6) * NV + j];
   }
