@@ -32,6 +32,11 @@
 #define ASYNC_COMMIT() ((void)0)
 #define ASYNC_WAIT_PREV() ((void)0)
 #define ASYNC_WAIT() ((void)0)
+#define MBAR_INIT(bar, count) ((void)0)
+#define MBAR_EXPECT_TX(bar, bytes) ((void)0)
+#define MBAR_WAIT(bar, parity) ((void)0)
+#define FENCE_PROXY_ASYNC() ((void)0)
+#define BULK_G2S(dst, src, bytes, bar) do { for (size_t i_ = 0; i_ < (size_t)(bytes) / 8; i_++) (dst)[i_] = (src)[i_]; } while (0)
 struct double2 { double x, y; };
 inline double2 make_double2(double x, double y) { return double2{x, y}; }
 #else
@@ -65,6 +70,24 @@ inline double2 make_double2(double x, double y) { return double2{x, y}; }
 #define ASYNC_COMMIT() asm volatile("cp.async.commit_group;" ::: "memory")
 #define ASYNC_WAIT_PREV() asm volatile("cp.async.wait_group 1;" ::: "memory") /* all but the most recent group */
 #define ASYNC_WAIT() asm volatile("cp.async.wait_all;" ::: "memory")
+// TMA-style bulk copies (cp.async.bulk, one instruction per contiguous block, completion counted in bytes on an mbarrier):
+// ONE thread arms the barrier with the expected bytes and issues the copies; every consumer waits on the barrier's phase
+// parity.  dst / src 16-byte aligned, bytes a multiple of 16.  FENCE_PROXY_ASYNC orders earlier generic-proxy accesses
+// of a shared buffer before the async proxy overwrites it.
+#define MBAR_INIT(bar, count) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"((unsigned)(count)) : "memory")
+#define MBAR_EXPECT_TX(bar, bytes) \
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"((unsigned)(bytes)) : "memory")
+#define BULK_G2S(dst, src, bytes, bar)                                                                                   \
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(          \
+                   (unsigned)__cvta_generic_to_shared(dst)),                                                             \
+               "l"(src), "r"((unsigned)(bytes)), "r"((unsigned)__cvta_generic_to_shared(bar))                            \
+               : "memory")
+#define MBAR_WAIT(bar, parity)                                                                                                           \
+  asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}" ::"r"( \
+                   (unsigned)__cvta_generic_to_shared(bar)),                                                                             \
+               "r"((unsigned)(parity))                                                                                                   \
+               : "memory")
+#define FENCE_PROXY_ASYNC() asm volatile("fence.proxy.async.shared::cta;" ::: "memory")
 #endif
 
 namespace mpcdev {

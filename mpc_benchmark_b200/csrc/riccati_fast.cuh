@@ -371,31 +371,37 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
   constexpr int KROWS = (((ZP * LDH + Lay::un - 4 * FW - 2 * FX) / 2) / NR) & ~1;
   constexpr int FSTAGE = 2 * FW + FX + KROWS * NR;
   static_assert(KROWS >= M && 2 * FSTAGE <= ZP * LDH + Lay::un && FSTAGE % 2 == 0, "forward staging does not fit");
+  // one thread arms the stage's mbarrier and issues nine bulk copies (cp.async.bulk: W, [A B], gain rows, six small vectors)
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(vec + Lay::vecs - 4);
+  ONE_THREAD { MBAR_INIT(mbar, 1); MBAR_INIT(mbar + 1, 1); }
   auto stage_fwd = [&](int kk) {
-    double *bw = ws + (kk & 1) * FSTAGE, *ba = bw + FW, *bx = ba + FW, *bk = bx + FX;
-    const double *gw = io.W + (size_t)kk * FW, *ga = io.AB + (size_t)kk * FW, *gk = io.K + (size_t)kk * S * NR;
-    PAR_FOR(e, FW / 2) { ASYNC_COPY16(bw + 2 * e, gw + 2 * e); ASYNC_COPY16(ba + 2 * e, ga + 2 * e); }
-    int rows = M + io.nca[kk];
-    if (rows > KROWS) rows = KROWS;
-    PAR_FOR(e, rows * NR) ASYNC_COPY8(bk + e, gk + e);
-    PAR_FOR(i, N) {
-      ASYNC_COPY8(bx + i, io.pt + (size_t)kk * N + i);
-      ASYNC_COPY8(bx + N + i, io.fbar + (size_t)kk * N + i);
-      ASYNC_COPY8(bx + 2 * N + i, io.lplus + (size_t)(kk + 1) * N + i);
-      ASYNC_COPY8(bx + 3 * N + i, io.lam + (size_t)(kk + 1) * N + i);
+    ONE_THREAD {
+      double *bw = ws + (kk & 1) * FSTAGE, *ba = bw + FW, *bx = ba + FW, *bk = bx + FX;
+      unsigned long long *bar = mbar + (kk & 1);
+      int rows = M + io.nca[kk];
+      if (rows > KROWS) rows = KROWS;
+      rows = (rows + 1) & ~1; // whole 16-byte units (an extra row stays inside this knot's gain block)
+      FENCE_PROXY_ASYNC();    // the buffer was last touched through the generic proxy
+      MBAR_EXPECT_TX(bar, (2 * FW + rows * NR + 4 * N + NZ + 36) * 8);
+      BULK_G2S(bw, io.W + (size_t)kk * FW, FW * 8, bar);
+      BULK_G2S(ba, io.AB + (size_t)kk * FW, FW * 8, bar);
+      BULK_G2S(bk, io.K + (size_t)kk * S * NR, rows * NR * 8, bar);
+      BULK_G2S(bx, io.pt + (size_t)kk * N, N * 8, bar);
+      BULK_G2S(bx + N, io.fbar + (size_t)kk * N, N * 8, bar);
+      BULK_G2S(bx + 2 * N, io.lplus + (size_t)(kk + 1) * N, N * 8, bar);
+      BULK_G2S(bx + 3 * N, io.lam + (size_t)(kk + 1) * N, N * 8, bar);
+      BULK_G2S(bx + 4 * N, io.lxu + (size_t)kk * NZ, NZ * 8, bar);
+      BULK_G2S(bx + 4 * N + NZ, io.T6 + (size_t)kk * 36, 36 * 8, bar);
     }
-    PAR_FOR(i, NZ) ASYNC_COPY8(bx + 4 * N + i, io.lxu + (size_t)kk * NZ + i);
-    PAR_FOR(i, 36) ASYNC_COPY8(bx + 4 * N + NZ + i, io.T6 + (size_t)kk * 36 + i);
   };
+  static_assert((FW * 8) % 16 == 0 && (N * 8) % 16 == 0 && (NZ * 8) % 16 == 0 && (FX * 8) % 16 == 0 && (2 * NR * 8) % 16 == 0 && (S * NR * 8) % 16 == 0,
+                "bulk copies need 16-byte sizes and offsets");
   SYNC();
   if (T > 0) stage_fwd(0);
-  ASYNC_COMMIT();
   for (int k = 0; k < T; k++) {
     const int nca = io.nca[k];
     if (k + 1 < T) stage_fwd(k + 1);
-    ASYNC_COMMIT();
-    ASYNC_WAIT_PREV(); // stage k has landed
-    SYNC();
+    MBAR_WAIT(mbar + (k & 1), (k >> 1) & 1); // stage k has landed (each barrier is used every other knot)
     const double *sW = ws + (k & 1) * FSTAGE, *sAB = sW + FW, *sX = sAB + FW, *sK = sX + FX;
     const double *gK = io.K + (size_t)k * S * NR;
     // du, dv of the active rows: RA rows per warp at a time (independent reduction chains), columns over lanes
