@@ -27,11 +27,6 @@
 #define LANE0 true
 #define WARP_ID 0
 #define NWARPS 1
-#define ASYNC_COPY16(dst, src) do { (dst)[0] = (src)[0]; (dst)[1] = (src)[1]; } while (0)
-#define ASYNC_COPY8(dst, src) do { (dst)[0] = (src)[0]; } while (0)
-#define ASYNC_COMMIT() ((void)0)
-#define ASYNC_WAIT_PREV() ((void)0)
-#define ASYNC_WAIT() ((void)0)
 #define MBAR_INIT(bar, count) ((void)0)
 #define MBAR_EXPECT_TX(bar, bytes) ((void)0)
 #define MBAR_WAIT(bar, parity) ((void)0)
@@ -62,14 +57,6 @@ inline double2 make_double2(double x, double y) { return double2{x, y}; }
 #define LANE0 ((threadIdx.x & 31) == 0)
 #define WARP_ID ((int)(threadIdx.x >> 5))
 #define NWARPS ((int)(blockDim.x >> 5))
-// 16-byte asynchronous global -> shared copy (cp.async, bypasses registers); dst/src are double pointers, 16-byte aligned
-#define ASYNC_COPY16(dst, src) \
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory")
-#define ASYNC_COPY8(dst, src) \
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory")
-#define ASYNC_COMMIT() asm volatile("cp.async.commit_group;" ::: "memory")
-#define ASYNC_WAIT_PREV() asm volatile("cp.async.wait_group 1;" ::: "memory") /* all but the most recent group */
-#define ASYNC_WAIT() asm volatile("cp.async.wait_all;" ::: "memory")
 // TMA-style bulk copies (cp.async.bulk, one instruction per contiguous block, completion counted in bytes on an mbarrier):
 // ONE thread arms the barrier with the expected bytes and issues the copies; every consumer waits on the barrier's phase
 // parity.  dst / src 16-byte aligned, bytes a multiple of 16.  FENCE_PROXY_ASYNC orders earlier generic-proxy accesses

@@ -61,6 +61,8 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
   double *vec = U0 + Lay::un;
   double *p = vec, *pt = p + ZP, *gh = pt + ZP, *fb = gh + ZP, *tmp = fb + ZP, *dx = tmp + ZP, *z = dx + ZP, *pv = z + ZP;
   double *T6 = pv + ZP, *dbr = T6 + 36, *dva = dbr + NC, *dinv = dva + NC, *wtmp = dinv + 64 * ((NC + 7) / 8), *red = wtmp;  // (red: one slot per thread, <= 512 threads)
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(vec + Lay::vecs - 8); // four mbarriers in the spare tail of vecs
+  ONE_THREAD { MBAR_INIT(mbar, 1); MBAR_INIT(mbar + 1, 1); MBAR_INIT(mbar + 2, 1); MBAR_INIT(mbar + 3, 1); }
   // ---- zero the padding of H once; terminal value function: P = H_T[xx] + C'C/mu, p = g_T[x] + C' d/mu
   PAR_FOR(e, ZP * LDH) H[e] = 0.0;
   SYNC();
@@ -82,14 +84,20 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
     }
     SYNC();
   }
-  // [A B] of a knot goes global -> shared with cp.async (NZ even: 16-byte chunks), issued one knot ahead so that the copy
-  // overlaps the tail of the previous knot; the padding columns NZ..ZP-1 are zeroed with plain stores
+  // [A B] of a knot goes global -> shared by bulk copies (cp.async.bulk, one 624-byte row per issuing thread into the padded
+  // rows; completion counted on an mbarrier), issued one knot ahead so that the copy overlaps the tail of the previous knot;
+  // the padding columns NZ..ZP-1 are zeroed with plain stores.  mbar[0..1]: forward-sweep stages, [2]: [A B] + T6 + fbar, [3]: H_k
+  static_assert((NZ * 8) % 16 == 0 && (LDZ * 8) % 16 == 0 && (LDH * 8) % 16 == 0 && (N * 8) % 16 == 0, "bulk copies need 16-byte rows");
   auto stage_AB_async = [&](int kk) {
     const double *src = io.AB + (size_t)kk * N * NZ;
-    PAR_FOR(e, N * (NZ / 2)) { int i = e / (NZ / 2), j = (e % (NZ / 2)) * 2; ASYNC_COPY16(AB + i * LDZ + j, src + i * NZ + j); }
+    ONE_THREAD {
+      FENCE_PROXY_ASYNC();
+      MBAR_EXPECT_TX(mbar + 2, (N * NZ + 36 + N) * 8);
+      BULK_G2S(T6, io.T6 + (size_t)kk * 36, 36 * 8, mbar + 2);
+      BULK_G2S(fb, io.fbar + (size_t)kk * N, N * 8, mbar + 2);
+    }
+    PAR_FOR(i, N) { FENCE_PROXY_ASYNC(); BULK_G2S(AB + i * LDZ, src + i * NZ, NZ * 8, mbar + 2); }
     PAR_FOR(e, N * (ZP - NZ)) { int i = e / (ZP - NZ), j = NZ + e % (ZP - NZ); AB[i * LDZ + j] = 0.0; }
-    PAR_FOR(e, 36 / 2) ASYNC_COPY16(T6 + 2 * e, io.T6 + (size_t)kk * 36 + 2 * e);
-    PAR_FOR(i, N / 2) ASYNC_COPY16(fb + 2 * i, io.fbar + (size_t)kk * N + 2 * i);
   };
   if (T > 0) stage_AB_async(T - 1);
   for (int k = T - 1; k >= 0; k--) {
@@ -102,9 +110,10 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
       const int blk = e >> 5, l = e & 31, i = (blk / (N / 8)) * 4 + (l >> 3), j = (blk % (N / 8)) * 8 + (l & 7);
       P[i * LDN + j] = 0.5 * (H[i * LDH + j] + H[j * LDH + i]);
     }
-    ASYNC_WAIT(); // [A B], T6 and fbar of this knot
+    MBAR_WAIT(mbar + 2, (T - 1 - k) & 1); // [A B], T6 and fbar of this knot
     SYNC();
-    PAR_FOR(e, NZ * (NZ / 2)) { int i = e / (NZ / 2), j = (e % (NZ / 2)) * 2; ASYNC_COPY16(H + i * LDH + j, gH + i * NZ + j); }
+    ONE_THREAD MBAR_EXPECT_TX(mbar + 3, NZ * NZ * 8);
+    PAR_FOR(i, NZ) { FENCE_PROXY_ASYNC(); BULK_G2S(H + i * LDH, gH + i * NZ, NZ * 8, mbar + 3); }
     PHASE(16);
     PAR_FOR(e, N * 6) { int i = e / 6, j = e % 6; double s = 0; for (int l = 0; l < 6; l++) s += P[i * LDN + l] * T6[6 * l + j]; Li[e] = s; }
     SYNC();
@@ -187,7 +196,7 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
     // 6. W = Pt [A B];  7. H = H_k + [A B]' W;  gh = g + [A B]' pt
     mma_tn(NBLK, ZP / 8, N, Li, LDN, AB, LDZ, W, LDZ, nullptr, 0, 0, 0, false);
     PHASE(17);
-    ASYNC_WAIT(); // H_k
+    MBAR_WAIT(mbar + 3, (T - 1 - k) & 1); // H_k
     SYNC();
     mma_tn(ZP / 8, ZP / 8, N, AB, LDZ, W, LDZ, H, LDH, H, LDH, ZP, ZP, false); // in place: H = H_k + [A B]' W (padding stays zero)
     PHASE(18);
@@ -372,8 +381,6 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
   constexpr int FSTAGE = 2 * FW + FX + KROWS * NR;
   static_assert(KROWS >= M && 2 * FSTAGE <= ZP * LDH + Lay::un && FSTAGE % 2 == 0, "forward staging does not fit");
   // one thread arms the stage's mbarrier and issues nine bulk copies (cp.async.bulk: W, [A B], gain rows, six small vectors)
-  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(vec + Lay::vecs - 4);
-  ONE_THREAD { MBAR_INIT(mbar, 1); MBAR_INIT(mbar + 1, 1); }
   auto stage_fwd = [&](int kk) {
     ONE_THREAD {
       double *bw = ws + (kk & 1) * FSTAGE, *ba = bw + FW, *bx = ba + FW, *bk = bx + FX;
