@@ -5,6 +5,10 @@
 // all run on the FP64 DMMA pipe out of shared memory (dmma.cuh), and the triangular solve with Lambda is replaced by an
 // explicit inverse of its Cholesky factor built by independent per-warp column chains (no block barriers).
 // Leading dimensions are padded to 8 (mod 16) doubles so the DMMA fragment loads are bank-conflict free.
+// Around them: both Cholesky factorisations (Lambda, padded control block) are tensor-core blocked with a one-panel
+// look-ahead (chol_mma), the control-block solve uses an in-place inverse of its factor and tile-wise triangular products,
+// the value update is a DMMA product, and all operands arrive by cp.async.bulk copies tracked by mbarriers one knot ahead
+// (backward pass: [A B], T6, fbar, H_k; forward sweep: W, [A B], gain rows, small vectors, double-buffered).
 #pragma once
 #include "dmma.cuh"
 #include "riccati.cuh"
@@ -41,7 +45,7 @@ template <int N, int M, int NC, int NCAP = NC> struct RicFastLayout {
   static constexpr int offKv = MR * LDZMAX, offRh = offKv + NCAP * NR, offCD = offRh + MR * LDR, offSg = offCD + NCAP * NZ;
   static constexpr int offAB = un - N * LDZ;
   static_assert(offAB >= 3 * N * LDN, "[A B] overlaps P / G / Li");
-  static_assert(un % 2 == 0 && offAB % 2 == 0 && (ZP * LDH) % 2 == 0, "16-byte alignment of the cp.async destinations");
+  static_assert(un % 2 == 0 && offAB % 2 == 0 && (ZP * LDH) % 2 == 0, "16-byte alignment of the bulk-copy destinations");
   static constexpr int vecs = 8 * ZP + 36 + 2 * NC + 64 * ((NC + 7) / 8) + 8 * 64 + 16; // the final reduction reuses wtmp
   static constexpr int total = ZP * LDH + un + vecs;
 };
@@ -374,7 +378,7 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
     if (!active) acc -= db * db / mu;
   }
   // W_k, [A B]_k, the small per-knot vectors and the first KROWS gain rows of each knot are staged global -> shared one knot
-  // ahead (cp.async, two stages in the now dead H / phase buffers): the dependent chain dx_k -> du_k -> dx_{k+1} never waits on HBM
+  // ahead (bulk copies, two stages in the now dead H / phase buffers): the dependent chain dx_k -> du_k -> dx_{k+1} never waits on HBM
   constexpr int FW = N * NZ;
   constexpr int FX = 4 * N + NZ + 36; // pt_k, fbar_k, lplus_{k+1}, lam_{k+1}, lxu_k, T6_k
   constexpr int KROWS = (((ZP * LDH + Lay::un - 4 * FW - 2 * FX) / 2) / NR) & ~1;
