@@ -517,9 +517,13 @@ HD void chol_blocked(double *A, int n, int ld, double *Dinv) {
 #pragma unroll
       for (int q = 0; q < CB; q++) v[q] = (q < bw) ? row[q] : 0.0;
 #pragma unroll
-      for (int c = 0; c < CB; c++) { double s = 0; 
+      for (int c = 0; c < CB; c++) {
+        double s = 0;
 #pragma unroll
-        for (int q = 0; q < CB; q++) if (q <= c) s += v[q] * Di[c * CB + q]; o[c] = s; }
+        for (int q = 0; q < CB; q++)
+          if (q <= c) s += v[q] * Di[c * CB + q];
+        o[c] = s;
+      }
 #pragma unroll
       for (int q = 0; q < CB; q++) if (q < bw) row[q] = o[q];
     }
@@ -606,9 +610,13 @@ HD void trsm_blocked(const double *L, int n, int ld, const double *Dinv, double 
 #pragma unroll
       for (int r = 0; r < CB; r++) b[r] = (r < bw) ? B[(k0 + r) * ldb + c] : 0.0;
 #pragma unroll
-      for (int r = 0; r < CB; r++) { double s = 0;
+      for (int r = 0; r < CB; r++) {
+        double s = 0;
 #pragma unroll
-        for (int t = 0; t < CB; t++) if (t <= r) s += Di[r * CB + t] * b[t]; x[r] = s; }
+        for (int t = 0; t < CB; t++)
+          if (t <= r) s += Di[r * CB + t] * b[t];
+        x[r] = s;
+      }
 #pragma unroll
       for (int r = 0; r < CB; r++) if (r < bw) B[(k0 + r) * ldb + c] = x[r];
     }
@@ -639,9 +647,13 @@ HD void trsm_blocked(const double *L, int n, int ld, const double *Dinv, double 
 #pragma unroll
       for (int r = 0; r < CB; r++) b[r] = (r < bw) ? B[(k0 + r) * ldb + c] : 0.0;
 #pragma unroll
-      for (int r = 0; r < CB; r++) { double s = 0;
+      for (int r = 0; r < CB; r++) {
+        double s = 0;
 #pragma unroll
-        for (int t = 0; t < CB; t++) if (t >= r) s += Di[t * CB + r] * b[t]; x[r] = s; }
+        for (int t = 0; t < CB; t++)
+          if (t >= r) s += Di[t * CB + r] * b[t];
+        x[r] = s;
+      }
 #pragma unroll
       for (int r = 0; r < CB; r++) if (r < bw) B[(k0 + r) * ldb + c] = x[r];
     }
