@@ -176,8 +176,8 @@ static int set_kernel_attrs(mpc_solver *h) {
   if (h->w.kind == MPC_KIND_FULL) { h->eval_smem = sizeof(FullWsT<true>); h->eval_smem_values = sizeof(FullWsT<false>); h->eval_threads = 128; h->ric_smem = RicFastLayout<56, 22, 78>::total * 8; h->ric_threads = 256; }
   else if (h->w.kind == MPC_KIND_KINO) { h->eval_smem = sizeof(KinoWsT<true>); h->eval_smem_values = sizeof(KinoWsT<false>); h->eval_threads = 128;
     h->ric_smem = RicFastLayout<56, 34, 68, KINO_NCAP>::total * 8; h->ric_threads = 256; }
-  else { h->eval_smem = h->eval_smem_values = sizeof(CentWs); h->eval_threads = 32; h->ric_smem = riccati_smem_doubles<9, 12, 34>() * 8; h->ric_threads = 64; }
-  if (const char *e = getenv("MPCB200_RIC_THREADS")) { int t = atoi(e); if (t >= 32 && t <= 256 && h->w.kind != MPC_KIND_CENT) h->ric_threads = t; }
+  else { h->eval_smem = h->eval_smem_values = sizeof(CentWs); h->eval_threads = 32; h->ric_smem = riccati_smem_doubles<9, 12, 34>() * 8; h->ric_threads = 128; }
+  if (const char *e = getenv("MPCB200_RIC_THREADS")) { int t = atoi(e); if (t >= 32 && t <= 256) h->ric_threads = t; }
   static_assert(RicFastLayout<56, 22, 78>::total * 8 <= 232448 && RicFastLayout<56, 34, 68, KINO_NCAP>::total * 8 <= 232448,
                 "Riccati shared memory exceeds the 227 KB opt-in limit");
 #define EVAL_ATTR(KIND, D) CK(cudaFuncSetAttribute(k_eval<KIND, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EvalShape<KIND, D>::G * EvalShape<KIND, D>::slice)))
