@@ -1,8 +1,10 @@
 #!/usr/bin/env python
 """Batched closed-loop MPC on the GPU (ideal plant): 256 Talos-shaped robots, each with its own random gait, 50 ticks.
-Known limitation: with one iteration per tick the plans stop converging once single support reaches the front of
-the horizon (after ~40-60 ticks on the synthetic model); `tools/closed_loop_trace.py` prints the per-tick statistics.
-Usage: python examples/closed_loop_walk.py [batch] [ticks]"""
+Known limitation: with the reference's mu_init = 1e-8 and one iteration per tick the plans stop converging once single
+support reaches the front of the horizon (after ~40-60 ticks on the synthetic model); `tools/closed_loop_trace.py` prints the
+per-tick statistics.
+Usage: python examples/closed_loop_walk.py [batch] [ticks] [mu_init]
+mu_init defaults to 1e-4, NOT the reference's 1e-8 (note above): 150 ticks then run at alpha = 1 without failures."""
 import os
 import sys
 import time
@@ -16,7 +18,8 @@ from mpc_benchmark_b200.closed_loop import ClosedLoop  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 50
-prob = problems.full_walk_batch(B, seed=1, stream_ticks=N)  # every robot's gait continues N knots past the horizon
+MU = float(sys.argv[3]) if len(sys.argv) > 3 else 1e-4
+prob = problems.full_walk_batch(B, seed=1, stream_ticks=N, mu_init=MU)  # every robot's gait continues N knots past the horizon
 s = BatchSolver(prob["robot"], prob["cfg"], B)
 s.setup(prob["knots"], prob["terms"], prob["x0_nominal"])
 t0 = time.time()

@@ -1,5 +1,5 @@
 """Per-tick statistics of a batched closed-loop walk (ideal plant): primal / dual infeasibility, accepted step lengths,
-linesearch trials.  usage: python tools/closed_loop_trace.py [batch] [ticks] [iters_per_tick] [keep_multipliers]"""
+linesearch trials.  usage: python tools/closed_loop_trace.py [batch] [ticks] [iters_per_tick] [keep_multipliers] [mu_init]"""
 import os
 import sys
 
@@ -14,7 +14,8 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 150
 IT = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 KEEP = bool(int(sys.argv[4])) if len(sys.argv) > 4 else False
-prob = problems.full_walk_batch(B, seed=1, stream_ticks=N)
+MU = float(sys.argv[5]) if len(sys.argv) > 5 else 1e-8
+prob = problems.full_walk_batch(B, seed=1, stream_ticks=N, mu_init=MU)
 s = BatchSolver(prob["robot"], prob["cfg"], B)
 s.setup(prob["knots"], prob["terms"], prob["x0_nominal"])
 cold = s.run(prob["xs"], prob["us"], max_iters=40, gains=False)
