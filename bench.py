@@ -162,8 +162,8 @@ def main():
         solver.run_device(xs_d.data_ptr(), us_d.data_ptr(), max_iters=1, stream=stream)
 
     xs_np, us_np = xs_h.numpy(), us_h.numpy()
-    out_xs = np.empty_like(xs_np)
-    out_us = np.empty_like(us_np)
+    out_xs = torch.empty_like(xs_h).pin_memory().numpy()  # results land in pinned host buffers too
+    out_us = torch.empty_like(us_h).pin_memory().numpy()
 
     def tick_e2e():
         solver.reset_multipliers()
