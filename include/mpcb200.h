@@ -132,8 +132,9 @@ int32_t mpc_set_x0(mpc_solver_t *h, const double *x0);
  * xs [batch][T+1][nx], us [batch][T][nu]; copies in, runs up to max_iters ProxDDP iterations
  * per instance, copies results back with mpc_get_results. */
 int32_t mpc_run(mpc_solver_t *h, const double *xs_init, const double *us_init, int32_t max_iters);
-/* Same, with the trajectories already resident in device memory (device pointers, same layout),
- * asynchronous on `stream` (a cudaStream_t); used when inputs live in HBM. */
+/* Same, with the trajectories already resident in device memory (device pointers, same layout); kernels are
+ * launched on `stream` (a cudaStream_t, 0 = the handle's own).  The call returns after the solve has finished:
+ * the iteration / linesearch control reads per-batch counters back between launches. */
 int32_t mpc_run_device(mpc_solver_t *h, uint64_t xs_dev, uint64_t us_dev, int32_t max_iters, uint64_t stream);
 
 /* What the per-tick solver.setup(problem) of the reference does to the solver state (full:539, cent:461) without

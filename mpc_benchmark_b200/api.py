@@ -4,10 +4,15 @@ the three reference scripts use, implemented as plain Python parameter carriers.
 `import mpc_benchmark_b200 as aligator` + `from mpc_benchmark_b200 import manifolds, dynamics, constraints`
 replaces `import aligator` (fulldynamic_talos.py:8,23-25; kinodynamic_talos.py:10,30-32; centroidal_talos.py:8,30-32).
 Objects only HOLD parameters; `SolverProxDDP.setup/run` flattens the object graph (flatten.py) into the C-ABI
-descriptor on every call, so mutation through any alias (`stages[j].cost.getComponent(k).residual.setReference`,
-`contact_map.contact_poses[i] = p`, the `[stage] * 100` aliasing of fulldynamic_talos.py:371) is always visible.
+descriptor on every call, so mutation through the problem (`problem.stages[j].cost.getComponent(k).residual.setReference`,
+`...contact_map.contact_poses[i] = p`) is always visible.  `TrajOptProblem` stores stages and the terminal cost BY VALUE
+(Aligator >= 0.10 keeps them as `xyz::polymorphic` values and copies the list on construction): the `[stage] * 100` of
+fulldynamic_talos.py:371 becomes 100 independent stages, so the per-knot `setReference` loop of :461-463 gives every
+knot its own swing-foot reference.
 All arithmetic of the solve runs in the CUDA library; nothing here evaluates a cost or a derivative.
 """
+import copy
+
 import numpy as np
 
 from . import _abi
@@ -389,11 +394,19 @@ class StageModel:
         return self.dynamics.nu
 
 
+def _clone(obj):
+    """Value copy of a stage / cost stack (robot models are immutable carriers and stay shared, see pin.Model.__deepcopy__)."""
+    return copy.deepcopy(obj)
+
+
 class TrajOptProblem:
+    """Stages and terminal cost are held by value, as aligator >= 0.10 does: `problem.stages[j]` is the problem's own copy
+    and the object passed in is not aliased (fulldynamic_talos.py:371-372,461-463; kinodynamic_talos.py:274-276,384-385)."""
+
     def __init__(self, x0, stages, term_cost):
         self.x0_init = np.array(x0, float)
-        self.stages = list(stages)
-        self.term_cost = term_cost
+        self.stages = [_clone(s) for s in stages]
+        self.term_cost = _clone(term_cost)
         self.term_constraints = _ConstraintStack()
 
     @property
@@ -409,10 +422,10 @@ class TrajOptProblem:
     def replaceStageCircular(self, stage):
         """Drop stage 0, append `stage` at the end (fulldynamic_talos.py:496)."""
         self.stages.pop(0)
-        self.stages.append(stage)
+        self.stages.append(_clone(stage))
 
     def addStage(self, stage):
-        self.stages.append(stage)
+        self.stages.append(_clone(stage))
 
 
 # ------------------------------------------------------------------ solver

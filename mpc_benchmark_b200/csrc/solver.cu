@@ -196,7 +196,9 @@ const char *mpc_last_error(void) { return g_err.c_str(); }
 mpc_solver_t *mpc_create(const mpc_robot_t *robot, const mpc_config_t *cfg, int32_t batch, int32_t device) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_err = "no CUDA device: libmpcb200 has no CPU fallback"; return nullptr; }
+  if (!robot || !cfg) { g_err = "mpc_create: null robot / config"; return nullptr; }
   if (cfg->kind != MPC_KIND_FULL && cfg->kind != MPC_KIND_CENT && cfg->kind != MPC_KIND_KINO) { g_err = "unknown model kind"; return nullptr; }
+  if (batch <= 0 || cfg->T <= 0) { g_err = "mpc_create: batch and horizon must be positive"; return nullptr; }
   if (cudaSetDevice(device) != cudaSuccess) { g_err = "cudaSetDevice failed"; return nullptr; }
   mpc_solver *h = new mpc_solver;
   h->device = device;
@@ -208,20 +210,23 @@ mpc_solver_t *mpc_create(const mpc_robot_t *robot, const mpc_config_t *cfg, int3
   dims_of_kind(cfg->kind, w.nx, w.n, w.m, w.nc);
   w.nz = w.n + w.m;
   w.sc = default_consts(cfg->tol, cfg->mu_init);
-  if (cudaMalloc(&h->d_model, sizeof(DevModel)) != cudaSuccess) { g_err = "cudaMalloc(model) failed"; delete h; return nullptr; }
-  cudaMemcpy(h->d_model, &h->h_model, sizeof(DevModel), cudaMemcpyHostToDevice);
+  // every failure below releases what was created so far through mpc_destroy (all members start null)
+  auto bail = [&](const char *what, cudaError_t e) -> mpc_solver_t * { g_err = std::string(what) + ": " + cudaGetErrorString(e); mpc_destroy(h); return nullptr; };
+  cudaError_t e;
+  if ((e = cudaMalloc(&h->d_model, sizeof(DevModel))) != cudaSuccess) return bail("cudaMalloc(model)", e);
+  if ((e = cudaMemcpy(h->d_model, &h->h_model, sizeof(DevModel), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy(model)", e);
   w.model = h->d_model;
-  cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-  cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
-  cudaMallocHost(&h->h_counters, 4 * sizeof(int32_t));
-  if (set_kernel_attrs(h)) { delete h; return nullptr; }
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaMallocHost(&h->h_counters, 4 * sizeof(int32_t))) != cudaSuccess) return bail("cudaMallocHost", e);
+  if (set_kernel_attrs(h)) { std::string keep = g_err; mpc_destroy(h); g_err = keep; return nullptr; }
   return h;
 }
 
 void mpc_destroy(mpc_solver_t *h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  cudaStreamSynchronize(h->stream);
+  if (h->stream) cudaStreamSynchronize(h->stream);
   for (void *p : h->allocs) cudaFree(p);
   for (cudaEvent_t e : h->evpool) cudaEventDestroy(e);
   if (h->d_xs_in) cudaFree(h->d_xs_in);
@@ -289,13 +294,11 @@ int32_t mpc_update_terms(mpc_solver_t *h, const mpc_term_t *terms) {
 int32_t mpc_cycle(mpc_solver_t *h, const mpc_knot_t *last) {
   CK(cudaSetDevice(h->device));
   if (!h->setup_done) return fail("mpc_cycle before mpc_setup");
-  mpc_knot_t *d_last = nullptr;
-  CK(cudaMalloc(&d_last, sizeof(mpc_knot_t) * h->w.B));
-  CK(cudaMemcpyAsync(d_last, last, sizeof(mpc_knot_t) * h->w.B, cudaMemcpyHostToDevice, h->stream));
-  k_cycle<<<h->w.B, 96, 0, h->stream>>>(h->w, d_last);
+  if (!h->d_last) CK(cudaMalloc(&h->d_last, sizeof(mpc_knot_t) * h->w.B)); // owned by the handle, released in mpc_destroy
+  CK(cudaMemcpyAsync(h->d_last, last, sizeof(mpc_knot_t) * h->w.B, cudaMemcpyHostToDevice, h->stream));
+  k_cycle<<<h->w.B, 96, 0, h->stream>>>(h->w, h->d_last);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
-  cudaFree(d_last);
   return 0;
 }
 

@@ -115,7 +115,11 @@ HD void init_instance(const Ws &w, int b, const double *xs_in, const double *us_
 HD void decide_eval(const Ws &w, int b, double *red /* shared, >= 8 doubles */, int32_t *next_eval) {
   const size_t T1 = (size_t)w.T + 1;
   InstState &s = w.st[b];
-  if (s.mode != MODE_EVAL) return;
+  // the mode is snapshotted once: thread 0 rewrites s.mode below, and a warp scheduled late must not see the new value,
+  // skip the group barrier and its share of the copies
+  ONE_THREAD red[1] = (double)s.mode;
+  SYNC();
+  if (red[1] != (double)MODE_EVAL) return;
   // add E_{k-1}^T lam_k (base block) to g_k[0:6] and fold it into the dual residual
   const bool has_base = (w.kind != MPC_KIND_CENT);
   if (has_base) {
@@ -202,7 +206,9 @@ HD void start_linesearch(const Ws &w, int b) {
 HD void decide_ls(const Ws &w, int b, double *red, int32_t *ls_out, int32_t *next_eval) {
   const size_t T1 = (size_t)w.T + 1;
   InstState &s = w.st[b];
-  if (s.mode != MODE_LS) return;
+  ONE_THREAD red[1] = (double)s.mode; // snapshot (see decide_eval)
+  SYNC();
+  if (red[1] != (double)MODE_LS) return;
   ONE_THREAD {
     const SolverConst &c = w.sc;
     double cost = 0, pen = 0;

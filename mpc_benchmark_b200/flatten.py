@@ -2,7 +2,7 @@
 
 Only the stage structures the reference scripts build are recognised (fulldynamic_talos.py:153-232, 234-245;
 centroidal_talos.py:208-247; kinodynamic_talos.py:117-173); anything else raises with the offending component named.
-Called on every setup()/run(), so mutation of any aliased object is picked up (<= 100 knots x ~90 doubles: cheap).
+Called on every setup()/run(), so every mutation made through `problem.stages[j]` is picked up (<= 100 knots x ~90 doubles: cheap).
 """
 import numpy as np
 
@@ -182,12 +182,8 @@ def _flatten_full(problem, tol, mu_init, max_iters):
     T = len(problem.stages)
     G = {}
     knots = (_abi.Knot * T)()
-    cache = {}
     for j, st in enumerate(problem.stages):
-        # aliased stages ([stage] * 100, fulldynamic_talos.py:371) are flattened once per call
-        if id(st) not in cache:
-            cache[id(st)] = _flatten_full_stage(st, G, j == 0)
-        knots[j] = cache[id(st)]
+        knots[j] = _flatten_full_stage(st, G, j == 0)
     term = _flatten_full_term(problem, G)
     model = G["model"]
     rb = _abi.Robot.from_buffer_copy(_robot_from_model(model))
@@ -380,11 +376,8 @@ def _flatten_kino(problem, tol, mu_init, max_iters):
     T = len(problem.stages)
     G = {}
     knots = (_abi.Knot * T)()
-    cache = {}
     for j, st in enumerate(problem.stages):
-        if id(st) not in cache:
-            cache[id(st)] = _flatten_kino_stage(st, G)
-        knots[j] = cache[id(st)]
+        knots[j] = _flatten_kino_stage(st, G)
     if problem.term_cost.size() != 0:
         raise NotImplementedError("kinodynamic problem: empty terminal cost expected (kinodynamic_talos.py:175)")
     model = G["model"]

@@ -145,6 +145,9 @@ class Model:
     def copy(self):
         return self  # immutable carrier
 
+    def __deepcopy__(self, memo):
+        return self  # shared by the value copies TrajOptProblem makes of its stages
+
     def createData(self):
         return Data(self)
 

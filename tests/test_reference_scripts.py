@@ -31,23 +31,70 @@ def test_script_top_half_flattens_to_expected_descriptor(script, maker, golden):
     assert bytes(flat.cfg) == bytes(gp["cfg"]) and bytes(flat.knots) == bytes(gp["knots"])  # committed fixture is current
 
 
-def test_mutation_through_aliases_is_seen_by_flatten():
-    """fulldynamic_talos.py:371 aliases ONE stage 100x and :461-463 mutates residual references through problem.stages[j]."""
+def test_mutation_through_problem_stages_is_seen_by_flatten():
+    """centroidal_talos.py:374-384 mutates contact poses through problem.stages[n]; the problem holds its stages BY VALUE
+    (aligator >= 0.10), so the objects passed to the constructor are not aliased."""
     import mpc_benchmark_b200 as aligator
     from mpc_benchmark_b200 import flatten, pin
 
     ns = _build_cent(aligator, pin)
     problem, stages = ns["problem"], ns["stages"]
     f0 = flatten.flatten_problem(problem, 1e-5, 1e-8, 10)
-    stages[3].dynamics.differential_dynamics.contact_map.contact_poses[0] = np.array([0.5, 0.1, 0.0])
+    new = np.array([0.5, 0.1, 0.0])
+    st = problem.stages[3]
+    st.dynamics.differential_dynamics.contact_map.contact_poses[0] = new
     for name in ("angular_acc_cost", "linear_acc_cost"):
-        stages[3].cost.getComponent(name).residual.contact_map.contact_poses[0] = np.array([0.5, 0.1, 0.0])
+        st.cost.getComponent(name).residual.contact_map.contact_poses[0] = new
     f1 = flatten.flatten_problem(problem, 1e-5, 1e-8, 10)
     assert list(f1.knots[3].cpos)[:3] == [0.5, 0.1, 0.0] and list(f0.knots[3].cpos)[:3] != [0.5, 0.1, 0.0]
+    assert list(stages[3].dynamics.differential_dynamics.contact_map.contact_poses[0]) != [0.5, 0.1, 0.0]  # caller's object untouched
     problem.replaceStageCircular(stages[0])
     f2 = flatten.flatten_problem(problem, 1e-5, 1e-8, 10)
     assert list(f2.knots[2].cpos)[:3] == [0.5, 0.1, 0.0]  # horizon rotated by one
     assert problem.term_cost.size() == 0
+
+
+def test_aliased_stage_list_gets_one_reference_per_knot():
+    """fulldynamic_talos.py:371 builds the problem from `[stage] * nsteps` and :461-463 then writes a different swing-foot
+    reference into every problem.stages[j]: each knot must keep its own (value semantics), not the last write."""
+    import mpc_benchmark_b200 as aligator
+    from mpc_benchmark_b200 import constraints, dynamics, flatten, manifolds, pin
+
+    rmodel = pin.Model()
+    rdata = rmodel.createData()
+    q0 = rmodel.referenceConfigurations["half_sitting"]
+    pin.framesForwardKinematics(rmodel, rdata, q0)
+    nv, nu = rmodel.nv, rmodel.nv - 6
+    space = manifolds.MultibodyPhaseSpace(rmodel)
+    x0 = np.concatenate([q0, np.zeros(nv)])
+    act = np.eye(nv, nu, -6)
+    prox = pin.ProximalSettings(1e-9, 1e-10, 1)
+    ids = [rmodel.getFrameId("left_sole_link"), rmodel.getFrameId("right_sole_link")]
+    cms = []
+    for fid, name in zip(ids, ["left_sole_link", "right_sole_link"]):
+        fr = rmodel.frames[fid]
+        cm = pin.RigidConstraintModel(pin.ContactType.CONTACT_6D, rmodel, fr.parentJoint, fr.placement, 0, rdata.oMf[fid], pin.LOCAL)
+        cm.corrector.Kp[:] = (0, 0, 10, 0, 0, 0)
+        cm.corrector.Kd[:] = 50
+        cm.name = name
+        cms.append(cm)
+    rcost = aligator.CostStack(space, nu)
+    rcost.addCost(aligator.QuadraticStateCost(space, nu, x0, np.eye(2 * nv)))
+    rcost.addCost(aligator.QuadraticControlCost(space, np.zeros(nu), 1e-4 * np.eye(nu)))
+    rcost.addCost(aligator.QuadraticResidualCost(space, aligator.CentroidalMomentumResidual(space.ndx, nu, rmodel, np.zeros(6)), np.eye(6)))
+    for fid in ids:
+        rcost.addCost(aligator.QuadraticResidualCost(space, aligator.FramePlacementResidual(space.ndx, nu, rmodel, rdata.oMf[fid].copy(), fid), 2000 * np.eye(6)))
+    stage = aligator.StageModel(rcost, dynamics.IntegratorSemiImplEuler(dynamics.MultibodyConstraintFwdDynamics(space, act, cms, prox), 0.01))
+    T = 5
+    problem = aligator.TrajOptProblem(x0, [stage] * T, aligator.CostStack(space, nu))
+    for j in range(T):
+        ref = rdata.oMf[ids[0]].copy()
+        ref.translation[2] += 0.01 * (j + 1)
+        problem.stages[j].cost.getComponent(3).residual.setReference(ref)
+    flat = flatten.flatten_problem(problem, 1e-5, 1e-8, 10)
+    z0 = rdata.oMf[ids[0]].translation[2]
+    assert np.allclose([flat.knots[j].lf_ref[11] - z0 for j in range(T)], [0.01 * (j + 1) for j in range(T)], atol=1e-15)
+    assert stage.cost.getComponent(3).residual.getReference().translation[2] == z0  # the caller's stage is not aliased
 
 
 def _build_cent(aligator, pin, T=6):
@@ -96,7 +143,7 @@ def test_unsupported_structures_raise_with_a_name():
     from mpc_benchmark_b200 import flatten, pin
 
     ns = _build_cent(aligator, pin)
-    ns["stages"][0].cost.addCost("bad", aligator.QuadraticStateCost(aligator.manifolds.VectorSpace(9), 12, np.zeros(9), np.eye(9)))
+    ns["problem"].stages[0].cost.addCost("bad", aligator.QuadraticStateCost(aligator.manifolds.VectorSpace(9), 12, np.zeros(9), np.eye(9)))
     with pytest.raises(NotImplementedError, match="QuadraticStateCost"):
         flatten.flatten_problem(ns["problem"], 1e-5, 1e-8, 10)
     s = aligator.SolverProxDDP(1e-5, 1e-8)
