@@ -45,6 +45,11 @@ template <int N, int M, int NC, int NCAP = NC> struct RicFastLayout {
   static constexpr int offKv = MR * LDZMAX, offRh = offKv + NCAP * NR, offCD = offRh + MR * LDR, offSg = offCD + NCAP * NZ;
   static constexpr int offAB = un - N * LDZ;
   static_assert(offAB >= 3 * N * LDN, "[A B] overlaps P / G / Li");
+  // knots with MORE than NCAP active rows (possible only when NCAP < NC: a kinodynamic iterate with nearly every cone / box row
+  // violated) use a second carving sized for NC rows in which the compacted rows [C D] stay in global memory: [Z | Kv | Rh | Sg]
+  static constexpr int LDZBIG = (NR + NC + 7) / 8 * 8;
+  static constexpr int offKvB = MR * LDZBIG, offRhB = offKvB + NC * NR, offSgB = offRhB + MR * LDR;
+  static_assert(offSgB + NC * NC <= un, "overflow carving of the KKT buffers does not fit");
   static_assert(un % 2 == 0 && offAB % 2 == 0 && (ZP * LDH) % 2 == 0, "16-byte alignment of the bulk-copy destinations");
   static constexpr int vecs = 8 * ZP + 36 + 2 * NC + 64 * ((NC + 7) / 8) + 8 * 64 + 16; // the final reduction reuses wtmp
   static constexpr int total = ZP * LDH + un + vecs;
@@ -61,7 +66,7 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
   double *H = ws;                              // ZP x LDH, zero padded; [0:N,0:N] carries the value-function Hessian between knots
   double *U0 = H + ZP * LDH;
   double *P = U0, *G = P + N * LDN, *Li = G + N * LDN, *AB = U0 + Lay::offAB, *W = P;  // phase 1 (W overwrites the dead P, G)
-  double *Z = U0, *Kv = U0 + Lay::offKv, *Rh = U0 + Lay::offRh, *CD = U0 + Lay::offCD, *Sg = U0 + Lay::offSg;  // phase 2
+  double *Z = U0, *CDs = U0 + Lay::offCD;  // phase 2 (Kv, Rh, Sg: carved per knot, see `big`)
   double *vec = U0 + Lay::un;
   double *p = vec, *pt = p + ZP, *gh = pt + ZP, *fb = gh + ZP, *tmp = fb + ZP, *dx = tmp + ZP, *z = dx + ZP, *pv = z + ZP;
   double *T6 = pv + ZP, *dbr = T6 + 36, *dva = dbr + NC, *dinv = dva + NC, *wtmp = dinv + 64 * ((NC + 7) / 8), *red = wtmp;  // (red: one slot per thread, <= 512 threads)
@@ -106,8 +111,8 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
   if (T > 0) stage_AB_async(T - 1);
   for (int k = T - 1; k >= 0; k--) {
     const double *gH = io.H + (size_t)k * NZ * NZ;
-    int nca = io.nca[k];
-    if (nca > NCAP) { nca = NCAP; ONE_THREAD { if (io.overflow) *io.overflow = 1; } } // more active rows than the shared-memory KKT holds
+    const int nca = io.nca[k];
+    const bool big = (NCAP < NC) && nca > NCAP; // more active rows than the fast carving holds: [C D] is read from global memory
     // 1. P <- symmetrised value Hessian (left in H by the previous knot), then H <- H_k asynchronously (lands before the
     //    Hessian update needs it); E normalisation P <- T' P T, p <- T' p
     PAR_FOR(e, N * N) { // lanes: 8 consecutive j x 4 consecutive i, which keeps the transposed read at 8-way bank conflicts
@@ -212,14 +217,16 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
     PAR_FOR(i, N) io.pt[(size_t)k * N + i] = pt[i];
     SYNC();
     // [A B]_k is dead: when the active rows of this knot keep phase 2 clear of the buffer, fetch the next knot's now
-    const bool early = ((nca == 0) ? Lay::offCD : ((Lay::offCD + nca * NZ > Lay::offSg + nca * nca) ? Lay::offCD + nca * NZ : Lay::offSg + nca * nca)) <= Lay::offAB;
+    const bool early = !big && ((nca == 0) ? Lay::offCD : ((Lay::offCD + nca * NZ > Lay::offSg + nca * nca) ? Lay::offCD + nca * NZ : Lay::offSg + nca * nca)) <= Lay::offAB;
     if (k > 0 && early) stage_AB_async(k - 1);
     PHASE(5);
     // 8. KKT by block elimination (phase-2 buffers alias P/G/Li/AB/W, all dead now)
     const int ncol = NR + nca, ldz = (ncol + 7) & ~7; // Z columns: [rh | Sh' | D'], padded with zero columns to whole tiles
     const double *gCD = io.CDact + (size_t)k * NC * NZ;
     const int32_t *ai = io.act_idx + (size_t)k * NC;
-    PAR_FOR(e, nca * NZ) CD[e] = gCD[e];
+    double *Kv = big ? U0 + Lay::offKvB : U0 + Lay::offKv, *Rh = big ? U0 + Lay::offRhB : U0 + Lay::offRh, *Sg = big ? U0 + Lay::offSgB : U0 + Lay::offSg;
+    const double *CD = big ? gCD : CDs;
+    if (!big) PAR_FOR(e, nca * NZ) CDs[e] = gCD[e];
     PAR_FOR(r, nca) dbr[r] = io.dbar[(size_t)k * NC + ai[r]];
     PAR_FOR(e, MR * MR) { // R^ = sym(H_uu), padded with the identity to MR x MR
       int i = e / MR, j = e % MR;

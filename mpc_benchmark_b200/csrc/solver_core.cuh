@@ -16,7 +16,7 @@
 namespace mpcdev {
 
 enum { MODE_EVAL = 0, MODE_STEP = 1, MODE_LS = 2, MODE_DONE = 3 };
-constexpr int KINO_NCAP = 56; // active rows the kinodynamic Riccati keeps in shared memory (68 possible; > 56 flags status 3)
+constexpr int KINO_NCAP = 56; // active rows of the kinodynamic Riccati's fast shared-memory carving; knots with more (up to all 68) keep [C D] in global memory
 
 struct SolverConst {
   double tol, mu_init;

@@ -345,3 +345,127 @@ def kino_standing_problem(batch=1, T=100, robot=None, **kw):
     u_init[2] = u_init[8] = f_half  # u_ref = [f_ref, f_ref, 0] (kino:296-298)
     return dict(robot=rb, cfg=cfg, knots=knots, terms=terms, x0=np.tile(x0, (batch, 1)), xs=np.tile(x0, (batch, T + 1, 1)),
                 us=np.tile(u_init, (batch, T, 1)), lf=lf, rf=rf, com0=com0, mass=mass)
+
+
+# ---------------------------------------------------------------- reference-gait walking batches (all three models)
+def _swap_feet_u(u, kind):
+    u = np.array(u, float)
+    if kind in (_abi.KIND_KINO, _abi.KIND_CENT):
+        u[:6], u[6:12] = u[6:12].copy(), u[:6].copy()
+    return u
+
+
+def reference_horizon(kind, tick, mirror, lf, rf, com0, mass, T=100, stairs=False):
+    """What the solver of ONE robot sees at MPC tick `tick` of the reference loop when the feet stand at (lf, rf): per-slot contact
+    phase, index into `contact_phases` / `urefs`, swing-foot references (write-then-rotate order) and the terminal
+    CoM target (gait.GaitPlan; fulldynamic_talos.py:444-510, kinodynamic_talos.py:362-409, centroidal_talos.py:354-384,459).
+    `stairs`: BASELINE configs[3] — every step goes x_forward = 0.3 m ahead and z_height = +0.10 m up (talos_utils.py:187-192 with the
+    stair tread of bullet_robot.py:298-300), and the forward step is kept to the end of the gait."""
+    from . import gait
+
+    kw = dict(x_forward=0.3, z_height=0.10, keep_forward=True) if stairs else {}
+    plan = gait.GaitPlan(kind, lf, rf, com0, nsteps=T, mirror=mirror, **kw)
+    for _ in range(tick):
+        plan.tick(sample=False)
+    LF, RF, _, com_final = plan.tick(sample=True)
+    return dict(phase=plan.h_phase, index=plan.h_index, lf=plan.h_lf, rf=plan.h_rf, com_final=com_final, lf_last=LF[-1], rf_last=RF[-1],
+                lf_refs=LF, rf_refs=RF)
+
+
+def walk_batch(kind, batch, seed=5, T=100, ticks=None, mirror=None, stairs=False, perturb=True, robot=None, **kw):
+    """Batch of MPC problems along the REFERENCE gait of the given model (BASELINE.json configs[0]-[4] as concretised in SURVEY 8d):
+    instance i sits at MPC tick `ticks[i]` (default: uniform over the whole contact-phase list, `default_rng(seed)`) of the
+    schedule of fulldynamic_talos.py:256-266 / kinodynamic_talos.py:191-198 / centroidal_talos.py:108-116, mirrored (first swing
+    with the other foot) with probability 1/2, with the swing references of talos_utils.footTrajectory from the nominal foot
+    placements and a perturbed measured state (config 4 recipe).  Horizons hold single-support knots, moving references /
+    contact positions and ramping force references; `x0_nominal`, `xs`, `us` are the reference's cold start."""
+    from . import gait
+
+    rb, q0, x0mb, lf, rf, com0, mass = base_setup(robot)
+    rng = np.random.default_rng(seed)
+    nph = len(gait.contact_phases(kind, T))
+    ticks = rng.integers(0, nph, size=batch) if ticks is None else np.asarray(ticks, int)
+    mirror = rng.integers(0, 2, size=batch).astype(bool) if mirror is None else np.asarray(mirror, bool)
+    nx, n, m, nc = _abi.DIMS[kind]
+    f_half = mass * GRAVITY / 2.0
+    fr = np.array([0, 0, f_half, 0, 0, 0.0])
+    if kind == _abi.KIND_FULL:
+        cfg = full_config(rb, x0mb, lf, rf, T=T, **kw)
+        x0n, u_init = x0mb, np.zeros(22)
+    elif kind == _abi.KIND_KINO:
+        cfg = kino_config(rb, x0mb, T=T, **kw)
+        x0n = x0mb
+        u_init = np.zeros(34)
+        u_init[2] = u_init[8] = f_half
+        urefs = gait.force_ramp_refs(kind, mass, 34, T)
+    else:
+        cfg = cent_config(rb, com0, mass, T=T, **kw)
+        x0n = np.zeros(9)
+        x0n[:3] = com0
+        u_init = np.zeros(12)
+        u_init[2] = u_init[8] = f_half
+        urefs = gait.force_ramp_refs(kind, mass, 12, T)
+    knots = (_abi.Knot * (batch * T))()
+    terms = (_abi.Term * batch)()
+    ident = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0.0])
+    cache, n_ds = {}, 0
+    for i in range(batch):
+        key = (int(ticks[i]), bool(mirror[i]))
+        if key not in cache:
+            h = reference_horizon(kind, key[0], key[1], lf, rf, com0, mass, T=T, stairs=stairs)
+            ks = []
+            for j in range(T):
+                cs = h["phase"][j]
+                if kind == _abi.KIND_FULL:
+                    ks.append(full_knot(cs, h["lf"][j], h["rf"][j], fr, fr))
+                elif kind == _abi.KIND_KINO:
+                    u = urefs[h["index"][j]]
+                    ks.append(kino_knot(cs, h["lf"][j], h["rf"][j], _swap_feet_u(u, kind) if key[1] else u))
+                else:
+                    u = urefs[h["index"][j]]
+                    # contact positions follow the references for ACTIVE contacts only (cent:374-384); others keep the construction value
+                    lpos = h["lf"][j] if cs[0] else lf
+                    rpos = h["rf"][j] if cs[1] else rf
+                    ks.append(cent_knot(cs, lpos, rpos, _swap_feet_u(u, kind) if key[1] else u))
+            if kind == _abi.KIND_FULL:
+                term = make_term(h["lf_last"], h["rf_last"], h["com_final"])
+            elif kind == _abi.KIND_KINO:
+                term = make_term(ident, ident, h["com_final"])
+            else:
+                term = make_term(lf, rf)
+            cache[key] = (ks, term, sum(1 for p in h["phase"] if p == [True, True]))
+        ks, term, nds = cache[key]
+        knots[i * T:(i + 1) * T] = ks
+        terms[i] = term
+        n_ds += nds
+    x0n_b = np.tile(x0n, (batch, 1))
+    if not perturb:
+        x0s = x0n_b.copy()
+    elif kind == _abi.KIND_CENT:
+        x0s = x0n_b + rng.normal(size=(batch, 9)) * np.array([0.01] * 3 + [0.05 * mass] * 3 + [0.05] * 3)
+    else:
+        x0s = perturbed_x0(rb, x0mb, rng, batch)
+    xs = np.repeat(x0n_b[:, None, :], T + 1, axis=1)
+    us = np.tile(u_init, (batch, T, 1))
+    return dict(robot=rb, cfg=cfg, knots=knots, terms=terms, x0=x0s, x0_nominal=x0n_b, xs=xs, us=us, lf=lf, rf=rf, com0=com0, mass=mass,
+                ticks=ticks, mirror=mirror, ds_fraction=n_ds / float(batch * T))
+
+
+def kino_walk_batch(batch, **kw):
+    """BASELINE configs[1]: kinodynamic_talos.py flat-ground walk (x_forward 0.3, T_ds 20, T_ss 80)."""
+    return walk_batch(_abi.KIND_KINO, batch, **kw)
+
+
+def cent_walk_batch(batch, **kw):
+    """BASELINE configs[0]: centroidal_talos.py flat-ground walk (x_forward 0.2, moving contact positions)."""
+    return walk_batch(_abi.KIND_CENT, batch, **kw)
+
+
+def full_reference_walk_batch(batch, **kw):
+    """BASELINE configs[4]: full-dynamics batch with per-instance offsets into the schedule of fulldynamic_talos.py:256-266."""
+    return walk_batch(_abi.KIND_FULL, batch, **kw)
+
+
+def full_stairs_batch(batch=512, seed=4, **kw):
+    """BASELINE configs[3]: stair climbing (x_forward 0.3, z_height +0.10 per step), perturbed initial states, default_rng(4)."""
+    return walk_batch(_abi.KIND_FULL, batch, seed=seed, stairs=True, **kw)

@@ -58,3 +58,40 @@ def test_walking_instances_with_active_constraints(oracle):
     t = emu_lib.solve(prob, 1, xs=z["sol_xs"], us=z["sol_us"])
     assert rel(t["xs"], z["tick_xs"]) < 1e-6 and rel(t["us"], z["tick_us"]) < 1e-6
     assert rel(t["stage0"], z["tick_stage0"]) < 1e-6
+
+
+@pytest.mark.parametrize("kind,ticks,perturb", [(_abi.KIND_KINO, [99, 60], False), (_abi.KIND_CENT, [99, 150], True)])
+def test_reference_gait_walking_kino_cent(oracle, kind, ticks, perturb):
+    """BASELINE configs[0]-[1]: horizons of the reference walking loops (kinodynamic_talos.py:183-261, centroidal_talos.py:100-183):
+    single-support knots, moving swing references / contact positions, ramping force references, terminal CoM equality."""
+    prob = problems.walk_batch(kind, len(ticks), seed=2, ticks=ticks, mirror=[False, True], perturb=perturb)
+    assert 0.1 < prob["ds_fraction"] < 0.9  # really mixes single and double support
+    r = oracle.solve(prob, max_iters=5, inst_threads=2)
+    e = emu_lib.solve(prob, 5)
+    assert [i.num_iters for i in e["info"]] == [i.num_iters for i in r["info"]]
+    assert [i.ls_evals for i in e["info"]] == [i.ls_evals for i in r["info"]]
+    assert rel(e["xs"], r["xs"]) < 1e-7 and rel(e["us"], r["us"]) < 1e-7 and rel(e["vs"], r["vs"]) < 1e-5
+
+
+def kino_many_active_rows(T=6):
+    """A kinodynamic iterate with 59-65 ACTIVE constraint rows per knot (of 68): pulling contact forces put every wrench-cone row
+    on the wrong side and every joint sits beyond a limit — more than the 56 rows of the Riccati kernel's fast shared-memory
+    carving, so the knots take the carving that keeps [C D] in global memory."""
+    prob = problems.kino_standing_problem(batch=1, T=T)
+    rb = prob["robot"]
+    hi, lo = np.array(rb.q_hi[:]), np.array(rb.q_lo[:])
+    xs, us = prob["xs"].copy(), prob["us"].copy()
+    rng = np.random.default_rng(0)
+    for k in range(1, T + 1):
+        xs[0, k, 7:29] = np.where(rng.random(22) < 0.5, hi + 0.05, lo - 0.05)
+    us[0, :, 2] = us[0, :, 8] = -300.0
+    us[0, :, :12] += rng.normal(size=(T, 12)) * 50
+    return prob, xs, us
+
+
+def test_kino_more_active_rows_than_fast_carving(oracle):
+    prob, xs, us = kino_many_active_rows()
+    r = oracle.solve(prob, max_iters=2, xs=xs, us=us)
+    e = emu_lib.solve(prob, 2, xs=xs, us=us)
+    assert e["info"][0].status != 3 and e["info"][0].num_iters == r["info"][0].num_iters == 2
+    assert rel(e["xs"], r["xs"]) < 1e-7 and rel(e["us"], r["us"]) < 1e-7 and rel(e["vs"], r["vs"]) < 1e-6

@@ -342,3 +342,130 @@ def test_single_support_only_horizon(oracle):
     assert list(res.num_iters) == [i.num_iters for i in ref["info"]]
     assert rel(res.xs, ref["xs"]) < RTOL and rel(res.us, ref["us"]) < RTOL
     s.close()
+
+
+# ---------------------------------------------------------------- reference-gait walking, kinodynamic and centroidal models
+def _rotate(prob, knots, nxt):
+    B, T = prob["x0"].shape[0], prob["cfg"].T
+    out = list(knots)
+    for b in range(B):
+        out[b * T:(b + 1) * T] = out[b * T + 1:(b + 1) * T] + [nxt[b]]
+    return out
+
+
+@pytest.mark.parametrize("kind,ticks,perturb", [(_abi.KIND_KINO, [99, 60, 140], False), (_abi.KIND_CENT, [99, 150, 30], True),
+                                                (_abi.KIND_FULL, [99, 70, 50], True)])
+def test_reference_gait_cold_solve_and_ticks(oracle, kind, ticks, perturb):
+    """BASELINE configs[0]-[2]: horizons of the reference walking loops (single-support knots, moving swing references / contact
+    positions, ramping force references, terminal CoM equality; kinodynamic_talos.py:161-171,183-261, centroidal_talos.py:100-183,
+    374-394): cold solve, then a warm tick with the multipliers RESET (solver.setup per tick: full:539, cent:461) and one with the
+    multipliers SHIFTED (solver.cycleProblem without setup, kinodynamic_talos.py:488 -> mpc_shift_multipliers), each against the
+    oracle run on the host-rotated problem."""
+    B = len(ticks)
+    prob = problems.walk_batch(kind, B, seed=2, ticks=ticks, mirror=[False, True, False], perturb=perturb)
+    T = prob["cfg"].T
+    s = BatchSolver(prob["robot"], prob["cfg"], B)
+    s.setup(prob["knots"], prob["terms"], prob["x0"])
+    res = s.run(prob["xs"], prob["us"], max_iters=6)
+    ref = oracle.solve(prob, max_iters=6, inst_threads=B)
+    assert list(res.num_iters) == [i.num_iters for i in ref["info"]]
+    assert list(res.ls_evals) == [i.ls_evals for i in ref["info"]]
+    assert rel(res.xs, ref["xs"]) < RTOL and rel(res.us, ref["us"]) < RTOL and rel(res.vs, ref["vs"]) < 1e-5
+    assert rel(res.K, ref["K"]) < 1e-5
+    # the stage entering each horizon: the next one of the same gait
+    nxt_prob = problems.walk_batch(kind, B, seed=2, ticks=[t + 1 for t in ticks], mirror=[False, True, False], perturb=perturb)
+    nxt = (_abi.Knot * B)(*[nxt_prob["knots"][b * T + T - 1] for b in range(B)])
+    knots = list(prob["knots"])
+    xs, us, vs, lams = ref["xs"], ref["us"], ref["vs"], ref["lams"]
+    for keep in (False, True):
+        s.tick(nxt, None, keep_multipliers=keep, max_iters=1)
+        got = s.results(gains=False)
+        knots = _rotate(prob, knots, nxt)
+        hp = dict(prob, knots=(_abi.Knot * (B * T))(*knots), x0=xs[:, 1].copy())
+        xs_ws = np.concatenate([xs[:, 1:], xs[:, -1:]], axis=1)
+        us_ws = np.concatenate([us[:, 1:], us[:, -1:]], axis=1)
+        if keep:
+            vs0 = np.concatenate([vs[:, 1:], np.zeros_like(vs[:, :1])], axis=1)
+            lams0 = np.concatenate([lams[:, 1:], np.zeros_like(lams[:, :1])], axis=1)
+            assert np.abs(vs0).max() > 0 and np.abs(lams0).max() > 0
+        else:
+            vs0 = lams0 = None
+        r = oracle.solve(hp, max_iters=1, inst_threads=B, xs=xs_ws, us=us_ws, vs=vs0, lams=lams0)
+        assert list(got.ls_evals) == [i.ls_evals for i in r["info"]], keep
+        assert rel(got.xs, r["xs"]) < RTOL and rel(got.us, r["us"]) < RTOL and rel(got.vs, r["vs"]) < 1e-5 and rel(got.lams, r["lams"]) < 1e-5, keep
+        xs, us, vs, lams = r["xs"], r["us"], r["vs"], r["lams"]
+    s.close()
+
+
+def test_shift_multipliers_entry_point():
+    """mpc_shift_multipliers (solver.cycleProblem, kinodynamic_talos.py:488): vs[k] <- vs[k+n], lams[k] <- lams[k+n], tail zeroed."""
+    prob = problems.walk_batch(_abi.KIND_KINO, 2, seed=4, ticks=[99, 80], mirror=[False, False], perturb=False)
+    s = BatchSolver(prob["robot"], prob["cfg"], 2)
+    s.setup(prob["knots"], prob["terms"], prob["x0"])
+    a = s.run(prob["xs"], prob["us"], max_iters=3, gains=False)
+    assert np.abs(a.vs).max() > 0 and np.abs(a.lams).max() > 0
+    for n in (1, 3):
+        s.shift_multipliers(n)
+        b = s.results(gains=False)
+        assert np.array_equal(b.vs[:, :-n], a.vs[:, n:]) and np.array_equal(b.lams[:, :-n], a.lams[:, n:])
+        assert not b.vs[:, -n:].any() and not b.lams[:, -n:].any()
+        a = b
+    s.close()
+
+
+def test_kino_more_active_rows_than_fast_carving(oracle):
+    """59-65 active rows per knot (> the 56 of the kinodynamic Riccati's fast shared-memory carving, <= 68): solved, no status 3."""
+    from test_emulation import kino_many_active_rows
+
+    prob, xs, us = kino_many_active_rows()
+    s = BatchSolver(prob["robot"], prob["cfg"], 1)
+    s.setup(prob["knots"], prob["terms"], prob["x0"])
+    res = s.run(xs, us, max_iters=2)
+    ref = oracle.solve(prob, max_iters=2, xs=xs, us=us)
+    assert res.info[0].status != 3 and list(res.num_iters) == [2]
+    assert rel(res.xs, ref["xs"]) < RTOL and rel(res.us, ref["us"]) < RTOL and rel(res.vs, ref["vs"]) < 1e-5
+    s.close()
+
+
+def test_batch_4096_sampled_instances(oracle):
+    """BASELINE configs[4] at its full size (batch 4096, T = 100, 97 GB of workspace): eight sampled instances equal the oracle, every
+    instance is finite, and the result of an instance does not depend on the batch it is solved in (independent units)."""
+    B, T = 4096, 100
+    prob = problems.walk_batch(_abi.KIND_FULL, B, seed=5, ticks=np.random.default_rng(5).integers(0, 100, size=B))
+    s = BatchSolver(prob["robot"], prob["cfg"], B)
+    s.setup(prob["knots"], prob["terms"], prob["x0"])
+    res = s.run(prob["xs"], prob["us"], max_iters=2, gains=False)
+    s.close()
+    assert np.isfinite(res.xs).all() and np.isfinite(res.us).all() and (res.num_iters == 2).all()
+    pick = [0, 511, 1024, 2047, 2048, 3000, 3333, 4095]
+    sub = dict(prob)
+    sub["knots"] = (_abi.Knot * (len(pick) * T))(*[prob["knots"][i * T + k] for i in pick for k in range(T)])
+    sub["terms"] = (_abi.Term * len(pick))(*[prob["terms"][i] for i in pick])
+    sub["x0"], sub["xs"], sub["us"] = prob["x0"][pick], prob["xs"][pick], prob["us"][pick]
+    ref = oracle.solve(sub, max_iters=2, inst_threads=8)
+    assert rel(res.xs[pick], ref["xs"]) < RTOL and rel(res.us[pick], ref["us"]) < RTOL
+    assert list(res.ls_evals[pick]) == [i.ls_evals for i in ref["info"]]
+    s2 = BatchSolver(sub["robot"], sub["cfg"], len(pick))
+    s2.setup(sub["knots"], sub["terms"], sub["x0"])
+    r2 = s2.run(sub["xs"], sub["us"], max_iters=2, gains=False)
+    s2.close()
+    assert np.array_equal(r2.xs, res.xs[pick]) and np.array_equal(r2.us, res.us[pick])
+
+
+def test_stairs_batch_sample(oracle):
+    """BASELINE configs[3]: stair climbing (x_forward 0.3, z_height +0.10 per step, talos_utils.py:187-192), perturbed initial states,
+    default_rng(4); batch 512 with four sampled instances against the oracle."""
+    B, T = 512, 100
+    prob = problems.full_stairs_batch(B, ticks=np.random.default_rng(4).integers(0, 100, size=B))
+    s = BatchSolver(prob["robot"], prob["cfg"], B)
+    s.setup(prob["knots"], prob["terms"], prob["x0"])
+    res = s.run(prob["xs"], prob["us"], max_iters=3, gains=False)
+    s.close()
+    assert np.isfinite(res.xs).all() and (res.num_iters == 3).all()
+    pick = [3, 200, 333, 511]
+    sub = problems.sub_problem(prob, 0, 1)
+    sub["knots"] = (_abi.Knot * (len(pick) * T))(*[prob["knots"][i * T + k] for i in pick for k in range(T)])
+    sub["terms"] = (_abi.Term * len(pick))(*[prob["terms"][i] for i in pick])
+    sub["x0"], sub["xs"], sub["us"] = prob["x0"][pick], prob["xs"][pick], prob["us"][pick]
+    ref = oracle.solve(sub, max_iters=3, inst_threads=4)
+    assert rel(res.xs[pick], ref["xs"]) < RTOL and rel(res.us[pick], ref["us"]) < RTOL
