@@ -203,6 +203,13 @@ int orc_solve(const mpc_robot_t *rb, const mpc_config_t *cfg, int batch, const m
   SolverParams prm;
   prm.tol = cfg->tol; prm.mu_init = cfg->mu_init; prm.max_iters = max_iters;
   prm.par_knots = knot_threads > 1;
+  // ablation switches (see SolverParams); unset = the normative algorithm
+  if (const char *e = getenv("ORC_MU_DYN_SCALE")) prm.mu_dyn_scale = atof(e);
+  if (const char *e = getenv("ORC_LS_MODE")) prm.ls_mode = atoi(e);
+  if (const char *e = getenv("ORC_LS_WINDOW")) prm.ls_window = atoi(e);
+  if (const char *e = getenv("ORC_LS_ALPHA_MIN")) prm.ls_alpha_min = atof(e);
+  if (const char *e = getenv("ORC_DUAL_WEIGHT")) prm.dual_weight = atof(e);
+  if (const char *e = getenv("ORC_REG_INIT")) prm.reg_init = atof(e);
   if (knot_threads > 1) omp_set_num_threads(knot_threads);
   else omp_set_num_threads(inst_threads > 0 ? inst_threads : 1);
 #pragma omp parallel if (knot_threads <= 1 && inst_threads > 1)

@@ -28,6 +28,12 @@ struct SolverParams {
   int ls_max_steps = 20;
   double ls_dphi_rel = 1e-11; // predicted decrease below the fp64 resolution of the merit: Armijo is meaningless, take the step
   bool par_knots = false; // OpenMP over knots (reference: setNumThreads(8), fulldynamic_talos.py:385)
+  // ---- ablation switches (tools/closed_loop_oracle.py; defaults = the normative algorithm the CUDA path mirrors).  They bound the
+  // solver details that could not be checked against upstream Aligator (DESIGN "oracle-vs-Aligator ablation"):
+  double mu_dyn_scale = 1.0;  // dynamics penalty mu_d = mu_dyn_scale * mu (upstream had a `dyn_al_scale` in some versions)
+  int ls_mode = 0;            // 0 Armijo backtracking, 1 non-monotone Armijo (reference value = max of the last ls_window merits), 2 always alpha = 1
+  int ls_window = 5;
+  double dual_weight = 1.0;   // weight of the multiplier-distance terms of the PDAL merit
 };
 
 struct Instance {
@@ -84,7 +90,9 @@ struct Solver {
   double alpha_last = 0;
   std::vector<double> alphas;
 
+  std::vector<double> merit_hist; // non-monotone linesearch memory (ls_mode 1); survives across run() calls of one Solver
   Solver(const Problem &p, const SolverParams &s) : P(p), prm(s), d(p.d) {}
+  double mud() const { return mu * prm.mu_dyn_scale; }
 
   void setup(int T_) {
     T = T_;
@@ -126,13 +134,13 @@ struct Solver {
         if (E[k].ctype[r] == SET_NONE) continue;
         double vp = vplus_row(E[k].ctype[r], E[k].h[r], vs_prev[(size_t)k * d.nc + r], mu, E[k].lo[r], E[k].hi[r], a);
         double dv = vp - V[(size_t)k * d.nc + r];
-        pen += 0.5 * mu * (vp * vp + dv * dv);
+        pen += 0.5 * mu * (vp * vp + prm.dual_weight * dv * dv);
       }
       if (k < T)
         for (int i = 0; i < d.n; i++) {
-          double lp = lams_prev[(size_t)(k + 1) * d.n + i] + E[k].gap[i] / mu;
+          double lp = lams_prev[(size_t)(k + 1) * d.n + i] + E[k].gap[i] / mud();
           double dl = lp - L[(size_t)(k + 1) * d.n + i];
-          pen += 0.5 * mu * (lp * lp + dl * dl);
+          pen += 0.5 * mud() * (lp * lp + prm.dual_weight * dl * dl);
         }
     }
     if (cost_out) *cost_out = cost;
@@ -169,8 +177,8 @@ struct Solver {
         for (int i = 0; i < n; i++) {
           size_t id = (size_t)(k + 1) * n + i;
           prim_infeas = std::max(prim_infeas, std::fabs(e.gap[i]));
-          lplus[id] = lams_prev[id] + e.gap[i] / mu;
-          fbar[(size_t)k * n + i] = mu * (lplus[id] - lams[id]);
+          lplus[id] = lams_prev[id] + e.gap[i] / mud();
+          fbar[(size_t)k * n + i] = mud() * (lplus[id] - lams[id]);
           inner_crit = std::max(inner_crit, std::fabs(fbar[(size_t)k * n + i]));
           double l = l1[i];
           if (l != 0.0) { for (int j = 0; j < n; j++) g[j] += e.A[i * n + j] * l; for (int j = 0; j < m; j++) g[n + j] += e.B[i * m + j] * l; }
@@ -208,7 +216,7 @@ struct Solver {
     std::vector<double> HT = ev[T].H;
     for (int i = 0; i < n; i++) HT[i * nz + i] += preg;
     int nct = (P.cfg.kind == MPC_KIND_CENT) ? 0 : 3;
-    riccati_solve(n, m, nc, T, kn.data(), HT.data(), nz, &gq[(size_t)T * nz], &Cact[(size_t)T * nc * n], &dbar[(size_t)T * nc], nct, mu, mu, sol);
+    riccati_solve(n, m, nc, T, kn.data(), HT.data(), nz, &gq[(size_t)T * nz], &Cact[(size_t)T * nc * n], &dbar[(size_t)T * nc], nct, mud(), mu, sol);
     // rows of the terminal constraint beyond nct (and inactive rows everywhere) follow dv = dbar/mu
     for (int k = 0; k <= T; k++)
       for (int r = 0; r < nc; r++) {
@@ -236,9 +244,9 @@ struct Solver {
           double jd = 0;
           for (int j = 0; j < n; j++) jd += e.Cx[r * n + j] * dx[j];
           if (k < T) for (int j = 0; j < m; j++) jd += e.Cu[r * m + j] * du[j];
-          dphi += (2 * vplus[id] - vs[id]) * jd;
+          dphi += ((1 + prm.dual_weight) * vplus[id] - prm.dual_weight * vs[id]) * jd;
         }
-        dphi -= mu * (vplus[id] - vs[id]) * sol.dvs[id];
+        dphi -= prm.dual_weight * mu * (vplus[id] - vs[id]) * sol.dvs[id];
       }
       if (k < T) {
         const double *dxn = &sol.dxs[(size_t)(k + 1) * n];
@@ -248,7 +256,7 @@ struct Solver {
           for (int j = 0; j < n; j++) jd += e.A[i * n + j] * dx[j];
           for (int j = 0; j < m; j++) jd += e.B[i * m + j] * du[j];
           if (i < 6 && n >= 6) { for (int j = 0; j < 6; j++) jd += e.E6[6 * i + j] * dxn[j]; } else jd -= dxn[i];
-          dphi += (2 * lplus[id] - lams[id]) * jd - mu * (lplus[id] - lams[id]) * sol.dlams[id];
+          dphi += ((1 + prm.dual_weight) * lplus[id] - prm.dual_weight * lams[id]) * jd - prm.dual_weight * mud() * (lplus[id] - lams[id]) * sol.dlams[id];
         }
       }
     }
@@ -269,12 +277,15 @@ struct Solver {
   // Armijo backtracking with quadratic/cubic interpolation (proxsuite-nlp ArmijoLinesearch)
   double linesearch(const Instance &in, double phi0, double dphi0, double &phi_out, double &cost_out) {
     double alpha = 1.0, a_prev = 0, phi_prev = 0;
+    double phi_ref = phi0; // Armijo reference value; non-monotone: the largest of the last ls_window accepted merits
+    if (prm.ls_mode == 1) for (double v : merit_hist) phi_ref = std::max(phi_ref, v);
     for (int it = 0;; it++) {
       double c;
       double phi = try_step(in, alpha, &c);
       ls_evals++;
       phi_out = phi; cost_out = c;
-      if (phi <= phi0 + prm.ls_c1 * alpha * dphi0) return alpha;
+      if (prm.ls_mode == 2) return alpha;
+      if (phi <= phi_ref + prm.ls_c1 * alpha * dphi0) return alpha;
       if (std::fabs(dphi0) <= prm.ls_dphi_rel * std::max(1.0, std::fabs(phi0)) && std::isfinite(phi)) return alpha;
       if (alpha <= prm.ls_alpha_min || it + 1 >= prm.ls_max_steps) return alpha;
       double a_new;
@@ -336,6 +347,7 @@ struct Solver {
       double phi_new, cost_new;
       double alpha = linesearch(in, merit, dphi0, phi_new, cost_new);
       alphas.push_back(alpha); alpha_last = alpha;
+      if (prm.ls_mode == 1) { merit_hist.push_back(phi_new); if ((int)merit_hist.size() > prm.ls_window) merit_hist.erase(merit_hist.begin()); }
       if (getenv("ORC_TIMING")) { auto t4_ = std::chrono::steady_clock::now(); auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
         fprintf(stderr, "eval %.1f ms  assemble %.1f ms  lq %.1f ms  dphi+linesearch %.1f ms\n", ms(t0_, t1_), ms(t1_, t2_), ms(t2_, t3_), ms(t3_, t4_)); }
       if (getenv("ORC_VERBOSE")) fprintf(stderr, "it %3d prim %.3e dual %.3e inner %.3e merit %.10e dphi0 %.3e alpha %.3e ls %d preg %.1e mu %.1e al %d\n", num_iters, prim_infeas, dual_infeas, inner_crit, merit, dphi0, alpha, ls_evals, preg, mu, al_iters);
