@@ -2,14 +2,18 @@
 """bench.py — full-dynamics Talos MPC solves/sec (BASELINE.json metric) on N GPUs of one node.
 
 A "step" = one MPC-tick solve (SolverProxDDP.run with max_iters = 1, warm-started: fulldynamic_talos.py:407,532-540)
-of EVERY instance of the batch.  Workload = BASELINE.json configs[4]: full-dynamics Talos, T = 100, batch 4096 per
-GPU with random contact schedules and perturbed initial states, on the synthetic Talos-shaped
-model.  Instances are independent, so ranks shard them with no data-path collective (weak scaling: 4096 per GPU).
+of EVERY instance of the GLOBAL batch.  Workload = BASELINE.json configs[4]: full-dynamics Talos, T = 100, global batch 4096
+(per-instance offset into the contact schedule of fulldynamic_talos.py:256-266 + mirror flag, swing references of
+talos_utils.footTrajectory, perturbed measured states) on the synthetic Talos-shaped model.
+Instances are independent OCPs: the global batch is cut into contiguous shards of 4096 / N instances, one per rank (STRONG
+scaling of the named configuration), and the only collective is the NCCL all-gather of xs / us / K0 / per-instance
+summaries at the end of every step, INSIDE the timed region.  `--batch B` instead fixes the instances per GPU
+(weak scaling).  `--config stairs` runs BASELINE configs[3] (stair climbing, global batch 512).
 
-  value  : solves/s with the warm start already resident in HBM (mpc_run_device), whole job over all ranks
+  value  : solves/s with the warm start already resident in HBM (mpc_run_device + device-side gather), whole job over all ranks
   e2e    : same metric through the host-buffer C-ABI call (mpc_run + result read-back), H2D/D2H inside the timing
-  roofline: the proximal-Riccati kernel against the fp64 DFMA peak measured in this run (fp64-bound path)
-  cpu_baseline: the CPU oracle (OpenMP over instances, all host cores) on a bounded sample — NOT upstream Aligator
+  roofline: the proximal-Riccati kernel against the fp64 peak measured in this run (fp64-bound path)
+  cpu_baseline: the CPU oracle (OpenMP over instances, all host cores, -march=native) on a bounded sample — NOT upstream Aligator
 """
 import argparse
 import json
@@ -26,9 +30,16 @@ sys.path.insert(0, ROOT)
 
 METRIC = "full-dynamics Talos MPC solves/sec at batch 4096"
 UNIT = "solves/s"
-WORKLOAD = ("BASELINE configs[4]: full-dynamics Talos MPC tick (solver.setup + 1 ProxDDP iteration), T=100, one random contact schedule "
-            "per instance, warm start = converged solve of the nominal problem, measured state x0 perturbed per instance "
-            "(sigma 0.01 m / 0.02 rad / 0.05 s^-1), synthetic Talos-shaped model")
+WORKLOADS = {
+    "walk": ("BASELINE configs[4]: full-dynamics Talos MPC tick (solver.setup + 1 ProxDDP iteration), T=100, global batch 4096; instance i sits at tick "
+             "t_i ~ U{0..99} of the reference loop (contact schedule of fulldynamic_talos.py:256-266 entering the horizon, swing references of "
+             "talos_utils.footTrajectory), mirrored with probability 1/2; warm start = converged solve of the nominal problem, measured state x0 "
+             "perturbed per instance (sigma 0.01 m / 0.02 rad / 0.05 s^-1), default_rng(5); synthetic Talos-shaped model"),
+    "random": ("BASELINE configs[4] (round-1 generator): full-dynamics Talos MPC tick, T=100, one random contact schedule per instance "
+               "(problems.random_schedule), warm start = converged solve of the nominal problem, perturbed measured state, synthetic Talos-shaped model"),
+    "stairs": ("BASELINE configs[3]: full-dynamics Talos stair climbing (x_forward 0.3 m, z_height +0.10 m per step, talos_utils.py:187-192), MPC tick, "
+               "T=100, global batch 512 perturbed initial states, default_rng(4); synthetic Talos-shaped model"),
+}
 
 
 def parse():
@@ -37,7 +48,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=4096, help="instances per GPU")
+    ap.add_argument("--global-batch", type=int, default=0, help="instances over ALL GPUs (default 4096; 512 for --config stairs): strong scaling")
+    ap.add_argument("--batch", type=int, default=0, help="instances PER GPU (weak scaling); overrides --global-batch")
+    ap.add_argument("--config", default="walk", choices=["walk", "random", "stairs"], help="walk = BASELINE configs[4] (default), stairs = configs[3]")
+    ap.add_argument("--no-gather", action="store_true", help="skip the NCCL all-gather of the results (multi-GPU only)")
     ap.add_argument("--prep-iters", type=int, default=20, help="untimed cold-solve iterations that produce the warm start")
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances in the CPU-baseline sample (0 = auto, ~10-30 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -86,36 +100,112 @@ def algorithmic_lq_flops(prob):
     return total
 
 
-def reference_arm(args):
-    """--impl reference: the reference's CPU path.  Aligator/Pinocchio are not installable here (SURVEY 8c), so this
-    times the repo's CPU oracle (same algorithm, OpenMP over instances, all host cores) — stated in `cpu_baseline.kind`."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def make_problem(args, count=None, lo=0):
+    """Instances [lo, lo + count) of the global synthetic batch of the selected configuration (every rank derives its shard from
+    the SAME global draw, so the union over ranks is the single-GPU problem)."""
+    from mpc_benchmark_b200 import _abi, problems
+
+    G = global_batch(args, 1)
+    count = G if count is None else count
+    if args.config == "random":
+        prob = problems.full_walk_batch(lo + count, seed=5, T=100, stream_ticks=args.steps + 2)
+        return problems.sub_problem(prob, lo, lo + count) if lo else prob
+    seed = 4 if args.config == "stairs" else 5
+    rng = np.random.default_rng(seed)
+    n = max(G, lo + count)
+    ticks = rng.integers(0, 100, size=n)
+    prob = problems.walk_batch(_abi.KIND_FULL, n, seed=seed, T=100, ticks=ticks, stairs=(args.config == "stairs"))
+    return problems.sub_problem(prob, lo, lo + count) if (lo or count != n) else prob
+
+
+def global_batch(args, world):
+    if args.batch:
+        return args.batch * world
+    return args.global_batch or (512 if args.config == "stairs" else 4096)
+
+
+def config_block(args, world, G, gather):
+    """`config` of the JSON line: identical for both arms (the reference arm states its bounded sample in `cpu_baseline.sample`)."""
+    Bl = G // world
+    par = (f"global batch {G} cut into contiguous shards of {Bl} instances over {world} GPU(s); "
+           + ("NCCL all-gather of xs/us/K0/info inside the timed region" if gather else "no collective on the data path"))
+    return {"workload": WORKLOADS[args.config], "batch_per_gpu": Bl, "global_batch": G, "horizon": 100, "parallelism": par,
+            "l2": "per-step working set (GBs of LQ blocks) >> 126 MB L2; no flush needed", "prep_iters": args.prep_iters}
+
+
+def cpu_sample_size(args, cores, G):
+    """Bounded CPU sample shared by `cpu_baseline` and `--impl reference`: 16 instances per host core (~1 s per step), at most the batch."""
+    return int(min(G, args.cpu_sample or 16 * cores))
+
+
+_NATIVE = None
+
+
+def oracle_native():
+    """Bind the CPU oracle built with -march=native on THIS host (first call builds it); every later oracle call of this process —
+    the CPU-baseline leg, the reference arm, the CPU latency comparisons — then runs that build."""
+    global _NATIVE
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
+
+    if _NATIVE is None:
+        _NATIVE = oracle_lib.use_native() if oracle_lib._lib is None else False
+    return oracle_lib, _NATIVE
+
+
+def cpu_tick_rate(args, oracle_lib, n, cores, steps):
+    """Solves/s of the CPU oracle on the first n instances of the global batch: untimed nominal solve (the warm start), then `steps`
+    timed MPC ticks with OpenMP over instances on all host cores."""
     from mpc_benchmark_b200 import problems
 
-    cores = os.cpu_count() or 1
-    sample = args.cpu_sample or 16 * cores  # bounded sample, ~1 s of CPU work per step with all cores busy
-    prob = problems.full_walk_batch(sample, seed=5)
+    prob = make_problem(args, count=n)
     nominal = dict(prob, x0=prob["x0_nominal"])
     warm = oracle_lib.solve(nominal, max_iters=args.prep_iters, inst_threads=cores)
     xs, us = problems.warm_tick_inputs(prob, warm["xs"]), warm["us"]
-    for _ in range(max(1, min(args.warmup, 1))):
-        oracle_lib.solve(prob, max_iters=1, inst_threads=cores, xs=xs, us=us)
+    oracle_lib.solve(prob, max_iters=1, inst_threads=cores, xs=xs, us=us)
     t0 = time.time()
-    for _ in range(args.steps):
+    for _ in range(steps):
         oracle_lib.solve(prob, max_iters=1, inst_threads=cores, xs=xs, us=us)
     dt = time.time() - t0
-    val = sample * args.steps / dt
+    flops = algorithmic_lq_flops(prob) + eval_flops(prob)
+    return n * steps / dt, dt / steps, flops * steps / dt / 1e9 / cores
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU path.  Aligator/Pinocchio are not installable here (SURVEY 8c), so this
+    times the repo's CPU oracle (same algorithm, OpenMP over instances, all host cores, -march=native build made on this
+    machine) on a bounded sample of the SAME configuration — stated in `cpu_baseline.kind` / `.sample`."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    oracle_lib, native = oracle_native()
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    cores = os.cpu_count() or 1
+    G = global_batch(args, world)
+    n = cpu_sample_size(args, cores, G)
+    val, step_s, gf = cpu_tick_rate(args, oracle_lib, n, cores, args.steps)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": f"{WORKLOAD}; CPU sample of {sample} instances/step", "prep_iters": args.prep_iters},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{sample} instances x {args.steps} ticks; CPU oracle (not upstream Aligator, which cannot be installed offline)"},
+            "ms_per_step": 1e3 * step_s, "higher_is_better": True, "scaling": "weak" if args.batch else "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config_block(args, world, G, world > 1 and not args.no_gather),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "gflops_per_core": gf,
+                             "build": "-O3 -march=native -fopenmp (built on this host)" if native else "-O3 -march=x86-64-v3 -fopenmp",
+                             "sample": f"first {n} instances of the global batch x {args.steps} ticks; CPU oracle (not upstream Aligator, which cannot be installed offline)"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def eval_flops(prob):
+    """Frozen per-knot evaluation FLOPs (counted with the instrumented scalar of tools/count_eval_flops.py)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "eval_flops.json")) as f:
+            t = json.load(f)
+    except (OSError, ValueError):
+        return 0.0
+    total = 0.0
+    for k in prob["knots"]:
+        both = (k.cs[0] != 0.0) == (k.cs[1] != 0.0)
+        total += t["full_ds_deriv"] if both else t["full_ss_deriv"]
+    return total + t.get("full_term_deriv", 0.0) * prob["x0"].shape[0]
 
 
 def main():
@@ -127,6 +217,7 @@ def main():
 
     from mpc_benchmark_b200 import _native, problems
     from mpc_benchmark_b200.batch import BatchSolver
+    from mpc_benchmark_b200.distributed import shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -137,8 +228,13 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    B, T = args.batch, 100
-    prob = problems.full_walk_batch(B, seed=5 + rank, T=T, stream_ticks=args.steps + 1)
+    G, T = global_batch(args, world), 100
+    lo, hi = shard_range(G, rank, world)
+    B = hi - lo
+    if G % world:
+        raise SystemExit("bench.py: the global batch must be divisible by the number of GPUs")
+    gather = world > 1 and not args.no_gather
+    prob = make_problem(args, count=B, lo=lo)
     solver = BatchSolver(prob["robot"], prob["cfg"], B, device=local)
     # untimed preparation = the reference's first solve (fulldynamic_talos.py:386-397): ProxDDP from the cold start at the
     # NOMINAL state; every timed tick then re-solves from that solution with the instance's MEASURED (perturbed) state at knot 0
@@ -150,16 +246,34 @@ def main():
     solver.set_x0(prob["x0"])
     torch.cuda.synchronize()
     stream = torch.cuda.current_stream().cuda_stream
-    peak_tf = _native.lib().mpc_measure_fp64_peak(local)
+    L = _native.lib()
+    peaks = {"dfma": L.mpc_measure_fp64_peak(local), "dmma": L.mpc_measure_fp64_peak_dmma(local), "dgemm": dgemm_peak(torch)}
+    peak_tf = max(peaks.values())
+
+    # device buffers of the gather: per rank [xs | us | K0 | info] for its shard; all_gather concatenates the rank blocks
+    nx, m, n = 57, 22, 56
+    per = (T + 1) * nx + T * m + m * n + 8
+    pack = torch.empty(B * per, dtype=torch.float64, device="cuda")
+    o_us = B * (T + 1) * nx
+    o_k0 = o_us + B * T * m
+    o_info = o_k0 + B * m * n
+    gathered = torch.empty(world * B * per, dtype=torch.float64, device="cuda") if gather else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def export_and_gather():
+        base = pack.data_ptr()
+        solver.export_results_device(base, base + 8 * o_us, base + 8 * o_k0, base + 8 * o_info, stream)
+        if gather:
+            dist.all_gather_into_tensor(gathered, pack)
+
     def tick_device():
         solver.reset_multipliers(stream)  # the reference calls solver.setup(problem) inside every tick (full:539)
         solver.run_device(xs_d.data_ptr(), us_d.data_ptr(), max_iters=1, stream=stream)
+        export_and_gather()
 
     xs_np, us_np = xs_h.numpy(), us_h.numpy()
     out_xs = torch.empty_like(xs_h).pin_memory().numpy()  # results land in pinned host buffers too
@@ -169,8 +283,11 @@ def main():
         solver.reset_multipliers()
         solver.run(xs_np, us_np, max_iters=1, fetch=False)
         # read back what the MPC loop consumes: xs, us and the first feedback gain (fulldynamic_talos.py:548-550)
-        _native.check(_native.lib().mpc_get_results(solver._h, _native.ptr(out_xs), _native.ptr(out_us), None, None, None, None), "mpc_get_results")
-        return solver.feedback(0)
+        _native.check(L.mpc_get_results(solver._h, _native.ptr(out_xs), _native.ptr(out_us), None, None, None, None), "mpc_get_results")
+        k0 = solver.feedback(0)
+        if gather:
+            export_and_gather()
+        return k0
 
     for _ in range(max(args.warmup, 3)):
         tick_device()
@@ -180,8 +297,8 @@ def main():
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kern = {"eval_deriv": 0.0, "riccati": 0.0, "eval_trial": 0.0, "bookkeeping": 0.0}
+    klaunch = {k: 0 for k in kern}
     launches = 0
-    nric = 0
     ev0.record()
     t0 = time.time()
     for _ in range(args.steps):
@@ -189,12 +306,13 @@ def main():
         km = solver.kernel_ms()
         for k in kern:
             kern[k] += km[k][0]
-        nric += km["riccati"][1]
-        launches += solver.last_launches
+            klaunch[k] += km[k][1]
+        launches += solver.last_launches + 1 + (1 if gather else 0)
     ev1.record()
     barrier()
     wall = time.time() - t0
     dev_ms = ev0.elapsed_time(ev1)
+    nric = klaunch["riccati"]
     # ---- timed region 2: end to end through the host-buffer C-ABI
     tick_e2e()
     barrier()
@@ -208,11 +326,15 @@ def main():
 
     # ---- closed-loop ticks on the device (horizon rotation + warm-start shift + x0 from the model
     # prediction inside mpc_tick; the stage entering each horizon comes from the host), same batch, ideal plant
-    solver.tick(prob["stream"](0), None, keep_multipliers=False, max_iters=1)
+    stream_fn = prob.get("stream")
+    if stream_fn is None:
+        last = (type(prob["knots"][0]) * B)(*[prob["knots"][b * T + T - 1] for b in range(B)])
+        stream_fn = lambda t: last  # noqa: E731  (the gait's last stage keeps entering the horizon)
+    solver.tick(stream_fn(0), None, keep_multipliers=False, max_iters=1)
     barrier()
     t2 = time.time()
     for i in range(args.steps):
-        solver.tick(prob["stream"](1 + i), None, keep_multipliers=False, max_iters=1)
+        solver.tick(stream_fn(1 + i), None, keep_multipliers=False, max_iters=1)
     barrier()
     wall_cl = time.time() - t2
 
@@ -221,9 +343,8 @@ def main():
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     dev_s, wall_s, e2e_s, cl_s = [float(v) for v in tmax.cpu()]
     step_s = max(dev_s, 0.0) / args.steps
-    value = B * world * args.steps / max(dev_s, 1e-12)
-    e2e = B * world * args.steps / e2e_s
-    info = prep.info
+    value = G * args.steps / max(dev_s, 1e-12)
+    e2e = G * args.steps / e2e_s
     res_iters = solver.results(gains=False, multipliers=False).num_iters
 
     if rank == 0:
@@ -239,35 +360,67 @@ def main():
                    "note": "secondary roofline of the same kernel: DRAM traffic / duration; far from the HBM bound, the kernel is fp64 / latency bound"}
         h2d = xs_np.nbytes + us_np.nbytes
         d2h = out_xs.nbytes + out_us.nbytes + B * 22 * 56 * 8
+        cfg = config_block(args, world, G, gather)
+        cfg["tick_iters_done"] = int(np.min(res_iters))
+        cfg["double_support_fraction"] = prob.get("ds_fraction")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": 1e3 * step_s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
-                       "horizon": T, "parallelism": f"instances sharded over {world} GPU(s), no collective on the data path",
-                       "l2": "per-step working set (GBs of LQ blocks) >> 126 MB L2; no flush needed",
-                       "prep_iters": args.prep_iters, "tick_iters_done": int(np.min(res_iters))},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "ms_per_step": 1e3 * step_s, "higher_is_better": True, "scaling": "weak" if args.batch else "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": cfg,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world},
             "gpu_launches": int(launches),
-            "closed_loop": {"value": B * world * args.steps / cl_s, "unit": "robot-ticks/s",
+            "gather": {"bytes_per_rank_per_step": int(B * per * 8), "bytes_total_per_step": int(world * B * per * 8), "collective": "ncclAllGather (torch.distributed.all_gather_into_tensor) of [xs|us|K0|info]"} if gather else None,
+            "closed_loop": {"value": G * args.steps / cl_s, "unit": "robot-ticks/s",
                             "what": "mpc_tick (SURVEY 8f-2): horizon rotation, warm-start shift, x0 <- model prediction, 1 iteration; the next stage of every gait H2D per tick"},
             "wall_ms_per_step": 1e3 * wall_s / args.steps,
             "kernel_ms_per_step": {k: v / args.steps for k, v in kern.items()},
             "roofline": {"bound": "fp64", "kernel": "k_riccati (proximal Riccati backward+forward)", "achieved": achieved,
                          "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic, "traffic_source": traffic_src, "hbm": hbm,
-                         "peak_source": "DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no fp64 entry; SURVEY 8d)",
+                         "peak_source": "max of three fp64 micro-benchmarks measured in this run (MEASURED_PEAKS.json has no fp64 entry; SURVEY 8d): " + json.dumps(peaks),
                          "algorithmic_flops_per_launch": flops,
                          "note": "algorithmic = dense LQ model of SURVEY 8d; the kernel skips inactive constraint rows, so executed FLOPs are lower"},
             "clocks": sampler.summary(),
         }
+        ef = eval_flops(prob)
+        if ef and klaunch["eval_deriv"]:
+            ev_ms = kern["eval_deriv"] / klaunch["eval_deriv"]
+            ach = ef / (ev_ms * 1e-3) / 1e12
+            line["roofline_eval"] = {"bound": "fp64", "kernel": "k_eval<FULL, derivatives>", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                                     "algorithmic_flops_per_launch": ef, "ms_per_launch": ev_ms,
+                                     "note": "F_eval frozen by instrumented-scalar counting in the CPU oracle (profiles/eval_flops.json, BASELINE.md section 4)"}
+        if world == 1 and not args.no_cpu_baseline:
+            oracle_native()
         if args.latency_ticks > 0:
             line["latency"] = single_instance_latency(args, prob, local, not args.no_cpu_baseline and world == 1)
             line["latency"]["other_models"] = other_model_latencies(args, local, not args.no_cpu_baseline and world == 1)
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args, prob, xs_np, us_np)
+            line["cpu_baseline"] = cpu_baseline(args, G)
         print(json.dumps(line))
     solver.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def dgemm_peak(torch):
+    """cuBLAS DGEMM 8192^3 (TFLOP/s, best of 3): third candidate of the fp64 roofline denominator."""
+    try:
+        n = 8192
+        a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+        b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+        torch.matmul(a, b)
+        best = 1e30
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        del a, b
+        torch.cuda.empty_cache()
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    except Exception:
+        return 0.0
 
 
 def hbm_peak_gbs():
@@ -361,28 +514,17 @@ def other_model_latencies(args, device, with_cpu):
     return out
 
 
-def cpu_baseline(args, prob, xs, us):
-    """CPU oracle on the box's host cores over a bounded sample of the same workload (same warm start)."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_lib
-    from mpc_benchmark_b200 import problems
-
+def cpu_baseline(args, G):
+    """CPU oracle (-march=native build made on this host) on the box's host cores over the SAME bounded sample the reference arm
+    times: the first 16 x cores instances of the global batch, one warm MPC tick each."""
+    oracle_lib, native = oracle_native()
     cores = os.cpu_count() or 1
-    probe_n = min(prob["x0"].shape[0], max(cores, 8))
-    sub = problems.sub_problem(prob, 0, probe_n)
-    t0 = time.time()
-    oracle_lib.solve(sub, max_iters=1, inst_threads=cores, xs=xs[:probe_n], us=us[:probe_n])
-    dt = time.time() - t0
-    rate = probe_n / dt
-    n = args.cpu_sample or int(min(prob["x0"].shape[0], max(probe_n, rate * 15.0)))
-    n = max(cores, (n // cores) * cores)
-    n = min(n, prob["x0"].shape[0])
-    sub = problems.sub_problem(prob, 0, n)
-    t0 = time.time()
-    oracle_lib.solve(sub, max_iters=1, inst_threads=cores, xs=xs[:n], us=us[:n])
-    dt = time.time() - t0
-    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"first {n} instances of the same batch, one MPC tick each, {dt:.1f} s; CPU oracle with OpenMP over instances "
+    n = cpu_sample_size(args, cores, G)
+    steps = 3
+    val, step_s, gf = cpu_tick_rate(args, oracle_lib, n, cores, steps)
+    return {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "gflops_per_core": gf,
+            "build": "-O3 -march=native -fopenmp (built on this host)" if native else "-O3 -march=x86-64-v3 -fopenmp",
+            "sample": f"first {n} instances of the global batch x {steps} ticks, {step_s:.2f} s per tick; CPU oracle with OpenMP over instances "
                       "(not upstream Aligator: not installable offline)"}
 
 

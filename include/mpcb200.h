@@ -152,6 +152,11 @@ int32_t mpc_get_results(mpc_solver_t *h, double *xs, double *us, double *K, doub
                         mpc_info_t *info);
 /* Device-resident result pointers (for NCCL gathers without a host bounce). */
 int32_t mpc_result_ptrs(mpc_solver_t *h, uint64_t *xs, uint64_t *us, uint64_t *K, uint64_t *info);
+/* Same results, packed into CALLER-OWNED device buffers for a gather over NVLink: xs [batch][T+1][nx], us [batch][T][nu],
+ * K0 [batch][nu][ndx] (controlFeedbacks()[0]), info [batch][8] doubles = prim_infeas, dual_infeas, traj_cost, merit, num_iters,
+ * conv, status, alpha.  Any pointer may be 0.  Asynchronous on `stream` (0 = the handle's own); run it after mpc_run_device on the
+ * same stream and hand the buffers to ncclAllGather / torch.distributed.all_gather_into_tensor. */
+int32_t mpc_export_results_device(mpc_solver_t *h, uint64_t xs_dev, uint64_t us_dev, uint64_t K0_dev, uint64_t info_dev, uint64_t stream);
 /* workspace.problem_data.stage_data[k].dynamics_data.continuous_data.{xdot, contact_force}
  * (full:467-480): xdot [batch][ndx], force [batch][12]. */
 int32_t mpc_get_stage_data(mpc_solver_t *h, int32_t k, double *xdot, double *contact_force);
@@ -185,6 +190,8 @@ uint64_t mpc_workspace_bytes(mpc_solver_t *h);
 int32_t mpc_abi_sizeof(int32_t which); /* 0 robot, 1 config, 2 knot, 3 term, 4 info */
 /* fp64 DFMA peak micro-benchmark (TFLOP/s) used as the roofline denominator. */
 double mpc_measure_fp64_peak(int32_t device);
+/* Same for the fp64 tensor pipe (independent DMMA.8x8x4 chains); the roofline denominator is the larger of the two and cuBLAS DGEMM. */
+double mpc_measure_fp64_peak_dmma(int32_t device);
 
 #ifdef __cplusplus
 }

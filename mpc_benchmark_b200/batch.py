@@ -130,6 +130,11 @@ class BatchSolver:
                                                     C.cast(info, C.c_void_p)), "mpc_get_results")
         return BatchResults(xs, us, K, vs, lams, info)
 
+    def export_results_device(self, xs_ptr=0, us_ptr=0, K0_ptr=0, info_ptr=0, stream=0):
+        """Pack xs / us / K0 / per-instance summary into caller-owned device buffers (raw pointers) for a gather over NVLink."""
+        _native.check(_native.lib().mpc_export_results_device(self._h, int(xs_ptr), int(us_ptr), int(K0_ptr), int(info_ptr), int(stream)),
+                      "mpc_export_results_device")
+
     def result_ptrs(self):
         p = [C.c_uint64(0) for _ in range(4)]
         _native.check(_native.lib().mpc_result_ptrs(self._h, *[C.byref(x) for x in p]), "mpc_result_ptrs")

@@ -105,6 +105,22 @@ __global__ void k_dfma_peak(double *out, int iters) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+// fp64 tensor-pipe peak: 8 independent DMMA.8x8x4 accumulator chains per warp (512 FLOP per warp instruction)
+__global__ void k_dmma_peak(double *out, int iters) {
+  double c[8][2];
+#pragma unroll
+  for (int j = 0; j < 8; j++) { c[j][0] = 0.0; c[j][1] = 0.0; }
+  const double a = 1.0 + threadIdx.x * 1e-9, b = 1e-9 * (threadIdx.x & 7);
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) dmma_8x8x4(c[j][0], c[j][1], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) s += c[j][0] + c[j][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // ------------------------------------------------------------------ host side
 struct mpc_solver {
   int device = 0;
@@ -471,6 +487,31 @@ int32_t mpc_result_ptrs(mpc_solver_t *h, uint64_t *xs, uint64_t *us, uint64_t *K
   return 0;
 }
 
+// pack what the MPC loop consumes (fulldynamic_talos.py:548-550) for a gather over NVLink: xs, us, K0 and the per-instance summary
+__global__ void k_pack_k0_info(Ws w, double *K0, double *info) {
+  const size_t b = blockIdx.x, sz = (size_t)w.m * w.n;
+  if (K0) for (size_t i = threadIdx.x; i < sz; i += blockDim.x) K0[b * sz + i] = w.Kfb[b * (size_t)w.T * sz + i];
+  if (info && threadIdx.x == 0) {
+    const InstState &t = w.st[b];
+    double *o = info + b * 8;
+    o[0] = t.prim_infeas; o[1] = t.dual_infeas; o[2] = t.traj_cost; o[3] = t.merit; o[4] = (double)t.num_iters; o[5] = (double)t.conv; o[6] = (double)t.status; o[7] = t.alpha;
+  }
+}
+
+int32_t mpc_export_results_device(mpc_solver_t *h, uint64_t xs_dev, uint64_t us_dev, uint64_t K0_dev, uint64_t info_dev, uint64_t stream) {
+  CK(cudaSetDevice(h->device));
+  if (!h->setup_done) return fail("mpc_export_results_device before mpc_setup");
+  Ws &w = h->w;
+  cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : h->stream;
+  if (xs_dev) CK(cudaMemcpyAsync(reinterpret_cast<void *>(xs_dev), w.xs, (size_t)w.B * (w.T + 1) * w.nx * 8, cudaMemcpyDeviceToDevice, s));
+  if (us_dev) CK(cudaMemcpyAsync(reinterpret_cast<void *>(us_dev), w.us, (size_t)w.B * w.T * w.m * 8, cudaMemcpyDeviceToDevice, s));
+  if (K0_dev || info_dev) {
+    k_pack_k0_info<<<w.B, 128, 0, s>>>(w, reinterpret_cast<double *>(K0_dev), reinterpret_cast<double *>(info_dev));
+    CK(cudaGetLastError());
+  }
+  return 0;
+}
+
 int32_t mpc_get_stage_data(mpc_solver_t *h, int32_t k, double *xdot, double *contact_force) {
   CK(cudaSetDevice(h->device));
   if (!h->setup_done) return fail("mpc_get_stage_data before mpc_setup");
@@ -578,6 +619,30 @@ double mpc_measure_fp64_peak(int32_t device) {
   }
   cudaFree(out); cudaEventDestroy(e0); cudaEventDestroy(e1);
   double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+  return flops / (best * 1e-3) / 1e12;
+}
+
+double mpc_measure_fp64_peak_dmma(int32_t device) {
+  if (cudaSetDevice(device) != cudaSuccess) { g_err = "no CUDA device"; return -1.0; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+  double *out = nullptr;
+  if (cudaMalloc(&out, (size_t)blocks * threads * 8) != cudaSuccess) return -1.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  k_dmma_peak<<<blocks, threads>>>(out, 256);
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(e0);
+    k_dmma_peak<<<blocks, threads>>>(out, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  cudaFree(out); cudaEventDestroy(e0); cudaEventDestroy(e1);
+  double flops = 512.0 * 8.0 * (double)iters * blocks * (threads / 32);
   return flops / (best * 1e-3) / 1e12;
 }
 

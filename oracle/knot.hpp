@@ -435,7 +435,7 @@ inline void eval_knot_kino(const Problem &P, const mpc_knot_t &kn, const double 
   KinoVals<double> kv;
   kino_dynamics<double>(P.tree, rb, active, kin, v, u, kv);
   for (int i = 0; i < NV; i++) { o.xdot[i] = v[i]; o.xdot[NV + i] = kv.a[i]; }
-  for (int i = 0; i < 12; i++) o.lam[i] = (active[i / 6]) ? u[i] : 0.0;
+  for (int i = 0; i < 12; i++) o.lam[i] = (active[i / 6]) ? u[i] : double(0.0);
   std::vector<double> ax(NV * n, 0.0), au(NV * m, 0.0), hdq(6 * NV, 0.0), hdu(6 * m, 0.0);
   FootKin fk[2];
   for (int f = 0; f < 2; f++) foot_kin(P.tree, kin, f, fk[f]);

@@ -200,6 +200,15 @@ struct Solver {
       }
     }
     inner_crit = std::max(inner_crit, dual_infeas);
+    if (getenv("ORC_DIAG")) { // where the primal infeasibility sits: worst constraint row and worst dynamics gap
+      double bc = 0, bg = 0; int kc = -1, rc = -1, kg = -1, ig = -1;
+      for (int k = 0; k <= T; k++) {
+        for (int r = 0; r < nc; r++) if (ev[k].ctype[r] != SET_NONE) { double v = std::fabs(prim_row(ev[k].ctype[r], ev[k].h[r], vs_prev[(size_t)k * nc + r], mu, ev[k].lo[r], ev[k].hi[r])); if (v > bc) { bc = v; kc = k; rc = r; } }
+        if (k < T) for (int i = 0; i < n; i++) if (std::fabs(ev[k].gap[i]) > bg) { bg = std::fabs(ev[k].gap[i]); kg = k; ig = i; }
+      }
+      int nact = 0; for (size_t i = 0; i < act.size(); i++) nact += act[i];
+      fprintf(stderr, "   diag: worst cstr %.3e at knot %d row %d | worst gap %.3e at knot %d coord %d | active rows %d\n", bc, kc, rc, bg, kg, ig, nact);
+    }
   }
 
   void solve_lq() {
@@ -284,6 +293,7 @@ struct Solver {
       double phi = try_step(in, alpha, &c);
       ls_evals++;
       phi_out = phi; cost_out = c;
+      if (getenv("ORC_DIAG")) fprintf(stderr, "   ls: alpha %.4e phi %.10e (phi0 %.10e, armijo bound %.10e, cost %.6e)\n", alpha, phi, phi0, phi_ref + prm.ls_c1 * alpha * dphi0, c);
       if (prm.ls_mode == 2) return alpha;
       if (phi <= phi_ref + prm.ls_c1 * alpha * dphi0) return alpha;
       if (std::fabs(dphi0) <= prm.ls_dphi_rel * std::max(1.0, std::fabs(phi0)) && std::isfinite(phi)) return alpha;

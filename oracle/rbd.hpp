@@ -327,11 +327,11 @@ inline void constrained_dynamics_derivatives(const Tree &tr, const mpc_config_t 
       V6<double> ap = pJ >= 0 ? ang_[pJ] : zero6<double>();
       V6<double> w = cross_mm(s, vp);
       V6<double> cj = sub(cross_mm(s, ap), cross_mm(w, vp));
-      V6<double> dalpha_q = scale(actinv_motion(cc.oMc, add(cj, cross_mm(w, k.v[cc.body]))), -1.0);
+      V6<double> dalpha_q = scale(actinv_motion(cc.oMc, add(cj, cross_mm(w, k.v[cc.body]))), double(-1.0));
       V6<double> eJ = add(k.v[J], vp);
       V6<double> dalpha_v = actinv_motion(cc.oMc, cross_mm(s, sub(k.v[cc.body], eJ)));
       V6<double> Jc; for (int r = 0; r < 6; r++) Jc[r] = cc.J[r * NV + j];
-      V6<double> dlog = scale(mul(Jl, mul(Adi, Jc)), -1.0);
+      V6<double> dlog = scale(mul(Jl, mul(Adi, Jc)), double(-1.0));
       V6<double> wl = actinv_motion(cc.oMc, w); // d vc/dq = -wl
       for (int r = 0; r < 6; r++) {
         double dastar_q = cfg.kp[r] * dlog[r] + cfg.kd[r] * wl[r];
@@ -348,7 +348,7 @@ inline void constrained_dynamics_derivatives(const Tree &tr, const mpc_config_t 
     std::vector<double> rhs(12 * NV, 0.0);
     for (int r = 0; r < nk; r++)
       for (int j = 0; j < NV; j++) {
-        double s = R2 ? -R2[r * NV + j] : 0.0;
+        double s = R2 ? -R2[r * NV + j] : double(0.0);
         for (int i = 0; i < NV; i++) s += d.Jm[r * NV + i] * X[i * NV + j];
         rhs[r * NV + j] = s;
       }

@@ -227,7 +227,7 @@ inline M6<double> Jexp6(const V6<double> &xi) { // right Jacobian
   double t2 = dot(phi, phi), a, b, c; so3_coeffs(t2, a, b, c);
   M3<double> W = skew(phi), W2 = mul(W, W), J3, Q;
   for (int i = 0; i < 9; i++) J3[i] = (i % 4 == 0 ? 1.0 : 0.0) - b * W[i] + c * W2[i];
-  q_block(scale(rho, -1.0), scale(phi, -1.0), Q);
+  q_block(scale(rho, double(-1.0)), scale(phi, double(-1.0)), Q);
   M6<double> J{};
   for (int i = 0; i < 3; i++)
     for (int j = 0; j < 3; j++) { J[6 * i + j] = J3[3 * i + j]; J[6 * i + 3 + j] = Q[3 * i + j]; J[6 * (i + 3) + 3 + j] = J3[3 * i + j]; }
@@ -239,7 +239,7 @@ inline M6<double> Jlog6(const SE3<double> &M) { // log6(M exp6(d)) ~ log6(M) + J
   double t2 = dot(phi, phi), cp = vinv_coeff(t2);
   M3<double> W = skew(phi), W2 = mul(W, W), J3i, Q;
   for (int i = 0; i < 9; i++) J3i[i] = (i % 4 == 0 ? 1.0 : 0.0) + 0.5 * W[i] + cp * W2[i];
-  q_block(scale(rho, -1.0), scale(phi, -1.0), Q);
+  q_block(scale(rho, double(-1.0)), scale(phi, double(-1.0)), Q);
   M3<double> B = mul(mul(J3i, Q), J3i);
   M6<double> J{};
   for (int i = 0; i < 3; i++)

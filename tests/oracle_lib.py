@@ -10,6 +10,7 @@ from mpc_benchmark_b200 import _abi
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _LIB = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+_LIB_NATIVE = os.path.join(ROOT, "oracle", "_build", "liboracle_native.so")
 
 dp = C.POINTER(C.c_double)
 
@@ -30,6 +31,29 @@ def build():
 
 
 _lib = None
+
+
+def use_native():
+    """CPU-baseline legs of bench.py only: build the oracle with -march=native ON THIS MACHINE and bind that
+    library instead of the portable one.  Must be called before the first lib() call.  Falls back to the portable build if the
+    compiler is unavailable."""
+    global _lib
+    assert _lib is None, "use_native() must come before the first oracle call"
+    try:
+        subprocess.check_call(["make", "-B", "-C", os.path.join(ROOT, "oracle"), "native"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        _bind(_LIB_NATIVE)
+        return True
+    except (subprocess.CalledProcessError, OSError):
+        return False
+
+
+def _bind(path):
+    global _lib
+    _lib = C.CDLL(path)
+    _lib.orc_check_jlog6.restype = C.c_double
+    _lib.orc_check_jexp6.restype = C.c_double
+    _lib.orc_check_centroidal.restype = C.c_double
+    return _lib
 
 
 def lib():

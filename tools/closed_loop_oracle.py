@@ -22,7 +22,9 @@ from mpc_benchmark_b200 import _abi, gait, problems  # noqa: E402
 from mpc_benchmark_b200.kinematics import foot_placements  # noqa: E402
 
 
-def run(B=4, N=300, iters=1, keep=False, mu_init=1e-8, sigma=0.3, verbose=True, threads=8):
+def run(B=4, N=300, iters=1, keep=False, mu_init=1e-8, sigma=0.3, verbose=True, threads=8, plant="model"):
+    """plant = "model": x_meas = f(x0, us[0]), the model's own integrator applied to the first control (an ideal plant that obeys the
+    dynamics); "prediction": x_meas = xs[1] (what mpc_tick does without a measured state — it inherits the shooting gap of the plan)."""
     prob = problems.full_standing_problem(batch=B, mu_init=mu_init)
     rb, cfg, T = prob["robot"], prob["cfg"], prob["cfg"].T
     lf0, rf0, com0, mass = prob["lf"], prob["rf"], prob["com0"], prob["mass"]
@@ -38,8 +40,12 @@ def run(B=4, N=300, iters=1, keep=False, mu_init=1e-8, sigma=0.3, verbose=True, 
     fr = np.array([0, 0, mass * problems.GRAVITY / 2.0, 0, 0, 0.0])
     xs, us, vs, lams = cold["xs"], cold["us"], cold["vs"], cold["lams"]
     hist = []
+    cur_knots = list(prob["knots"])
     for t in range(N):
-        x_meas = xs[:, 1].copy()  # ideal plant: the model's own prediction
+        if plant == "model":
+            x_meas = np.stack([oracle_lib.eval_knot(rb, cfg, cur_knots[b * T], xs[b, 0], us[b, 0], xs[b, 1], derivs=False)["xnext"] for b in range(B)])
+        else:
+            x_meas = xs[:, 1].copy()
         knots = (_abi.Knot * (B * T))()
         terms = (_abi.Term * B)()
         for b in range(B):
@@ -49,6 +55,7 @@ def run(B=4, N=300, iters=1, keep=False, mu_init=1e-8, sigma=0.3, verbose=True, 
             knots[b * T:(b + 1) * T] = [problems.full_knot(p.h_phase[j], p.h_lf[j], p.h_rf[j], fr, fr) for j in range(T)]
             terms[b] = problems.make_term(LF[-1], RF[-1], com_final)
         hp = dict(prob, knots=knots, terms=terms, x0=x_meas)
+        cur_knots = knots
         xs_ws = np.concatenate([xs[:, 1:], xs[:, -1:]], axis=1)
         us_ws = np.concatenate([us[:, 1:], us[:, -1:]], axis=1)
         if keep:
@@ -80,4 +87,4 @@ def run(B=4, N=300, iters=1, keep=False, mu_init=1e-8, sigma=0.3, verbose=True, 
 if __name__ == "__main__":
     a = sys.argv[1:]
     run(B=int(a[0]) if len(a) > 0 else 4, N=int(a[1]) if len(a) > 1 else 300, iters=int(a[2]) if len(a) > 2 else 1,
-        keep=bool(int(a[3])) if len(a) > 3 else False, mu_init=float(a[4]) if len(a) > 4 else 1e-8)
+        keep=bool(int(a[3])) if len(a) > 3 else False, mu_init=float(a[4]) if len(a) > 4 else 1e-8, plant=a[5] if len(a) > 5 else "model")
