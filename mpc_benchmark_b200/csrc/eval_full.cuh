@@ -13,6 +13,8 @@
 //   dtau_i/dq_j = -S_i.(Ic_m c_j + Bc_m w_j),  m = body(i) in subtree(body(j));  ancestors: S_i.(s_j x* F_J - g_J)
 //   dtau_i/dv_j = +S_i.(Ic_m c'_j + Bc_m s_j)
 #pragma once
+#include <cstddef>
+#include "dmma.cuh"
 #include "model.cuh"
 
 namespace mpcdev {
@@ -49,11 +51,13 @@ struct KnotIO {
   int32_t *nca, *act_idx;
   // outputs (both passes)
   double *gap, *h, *scal, *xdot, *lamc;
+  double *scratch;   // derivative pass: this knot's slot of the Riccati W buffer (n x nz doubles, dead until the Riccati kernel writes it):
+                     // holds the tangent X = da/dz (NV x nz) and dlam/dz (12 x nz), which stay L2-resident between the phases
   double *phase_out; // profiling builds only
 };
 
 template <bool WITH_DERIV> struct FullWsT {
-  static constexpr int XS = WITH_DERIV ? NV * FNZ : 8, DLS = WITH_DERIV ? 12 * FNZ : 8, TOPS = WITH_DERIV ? 2 * NV * 6 : 8, BCS = WITH_DERIV ? NB * 36 : 8;
+  static constexpr int TOPS = WITH_DERIV ? 2 * NV * 6 : 8, BCS = WITH_DERIV ? NB * 36 : 8, HROWS = WITH_DERIV ? 40 : 1;
   static constexpr int CJ1 = WITH_DERIV ? 6 * FN : 8, CJ2 = WITH_DERIV ? 2 * 6 * NV : 8, M6 = WITH_DERIV ? 36 : 1, ZS = WITH_DERIV ? FNZ : 8;
   double x[NQ + NV], u[FM], xn[NQ + NV];
   double kn[sizeof(mpc_knot_t) / 8];
@@ -63,6 +67,7 @@ template <bool WITH_DERIV> struct FullWsT {
     double Bc[BCS];
     struct { double Jcent[CJ1], Jpose[CJ2]; } cj;
   };
+  double top[TOPS]; // directly behind Bc: [Bc | top] doubles as the scratch of the explicit mass-matrix inverse (both are free until then)
   double U[NV * 6];
   union { // the mass-matrix factor is dead after X = M^-1 R1; the output-phase vectors live afterwards
     double M[NV * NV];
@@ -78,17 +83,20 @@ template <bool WITH_DERIV> struct FullWsT {
     struct { double Y[NV * 13], G[144], rhs[12], dinvM[4 * 64], dinvG[2 * 64]; };
     struct { double mv[FNC], mvp[FNC], mln[FN], mlnp[FN], mlk[FN]; }; // v, v_prev, lam_{k+1}, its estimate, lam_k
   };
-  double X[XS];
-  double DL[DLS];
-  double top[TOPS];
   double rcent[6], rpose[12], Jlp[2 * M6];
   double estate[FN], Jls[M6];
   double dx[FN], xnext[NQ + NV], lgap[6], eexp[12], Dgap[12], Dl[36];
   double lpl[FN], fbr[FN];
   double com[3], scal[SC_COUNT], part[32];
+  // Gauss-Newton Hessian as ONE tensor-core product H = sum_k w_k J_k' J_k: the weighted residual-Jacobian rows stay where they are
+  // (dlam/dz rows in the global scratch, Jcent, Jpose, Jls in shared memory) and are addressed through this table
+  double hrow_w[HROWS];
+  int32_t hrow_len[HROWS];
   int32_t act[2], nact, sidx[2], ctype[FNC], isact[FNC], act_idx[FNC], nca;
 };
 using FullWs = FullWsT<true>;
+static_assert(offsetof(FullWs, top) == offsetof(FullWs, Bc) + sizeof(double) * FullWs::BCS, "[Bc | top] must be contiguous");
+static_assert(FullWs::BCS + FullWs::TOPS >= NV * NV + 3 * 64, "mass-matrix inverse scratch does not fit in [Bc | top]");
 
 // ------------------------------------------------------------------ kinematics shared by running / terminal knots
 // fills oM, S, I, v, hb, Ic, hsub, com, ofoot, Jf
@@ -208,7 +216,7 @@ template <class WS> HD void mb_composite_B(const DevModel &m, WS &w) {
 template <class WS> HD void mb_cost_terms(const DevModel &m, WS &w, const double *lf_ref, const double *rf_ref, bool derivs, double *gap_out) {
   const mpc_robot_t &rb = m.rb;
   // stage 1a: the relative placements whose logarithms are needed: both foot poses, the state error and the shooting gap
-  PAR_FOR(task, 4 * 32) {
+  PAR_FOR(task, 3 * 32) {
     if (task == 0) { // centroidal momentum value; integrator base block and gap placement
       const double *h = w.hsub;
       double c[3];
@@ -227,7 +235,7 @@ template <class WS> HD void mb_cost_terms(const DevModel &m, WS &w, const double
     } else if (task == 32 || task == 64) { // foot pose placements
       int f = task == 32 ? 0 : 1;
       se3_inv_mul(f == 0 ? lf_ref : rf_ref, w.ofoot + 12 * f, w.Dl + 12 * f);
-    } else if (task == 96) { // state error e = x (-) x_ref
+    } else if (task == 65) { // state error e = x (-) x_ref (second lane of the third warp: groups may have only three warps)
       double Mr[12], Mx[12];
       quat_to_R(m.cfg.x_ref + 3, Mr); Mr[9] = m.cfg.x_ref[0]; Mr[10] = m.cfg.x_ref[1]; Mr[11] = m.cfg.x_ref[2];
       for (int i = 0; i < 12; i++) Mx[i] = w.oM[i];
@@ -256,7 +264,7 @@ template <class WS> HD void mb_cost_terms(const DevModel &m, WS &w, const double
   SYNC();
   if (!derivs) return;
   if (gap_out) {
-    PAR_FOR(task, 4 * 32) {
+    PAR_FOR(task, 3 * 32) {
       const double id[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
       if (task == 0) { double inv[12]; se3_inv_mul(w.Dgap, id, inv); se3_action_matrix(inv, w.late.AdDi); }
       else if (task == 32 || task == 33) Jexp6(task == 32 ? w.dx : w.lgap, task == 32 ? w.late.Jd : w.late.Jrg); // two lanes, one copy
@@ -362,10 +370,11 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
   mb_kinematics(m, w);
   EPH(1);
   const int nact = w.nact, nk = 6 * nact;
-  // derivative kernel: scratch of the explicit mass-matrix inverse, borrowed from X (free until the tangent is built):
-  // [L^-1 (NV x NV) | 4 x 64 warp scratch | raw right-hand sides [tau - b | J'] (NV x 13)]; values kernel: solve in place in Y
-  double *Ls = w.X;
-  double *Yr = DERIV ? Ls + NV * NV + 4 * 64 : w.Y;
+  // derivative kernel: explicit mass-matrix inverse, raw right-hand sides [tau - b | J'] (NV x 13) in Yr; values kernel: solve in place in Y
+  // [L^-1 (NV x NV) | 64 doubles of scratch per warp] in the free [Bc | top] block; the raw right-hand sides go to the global scratch
+  double *Ls = w.Bc;
+  double *X = io.scratch, *DL = io.scratch + NV * FNZ; // derivative pass only (null otherwise)
+  double *Yr = DERIV ? DL : w.Y;
   const double a0[6] = {-rb.gravity[0], -rb.gravity[1], -rb.gravity[2], 0, 0, 0};
   // bias accelerations (qdd = 0, gravity folded in) and bias forces
   PAR_FOR(b, NB) {
@@ -497,8 +506,8 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
         }
       for (int i = 0; i < 6; i++) w.f[6 * b + i] = t1[i];
     }
-    PAR_FOR(e, NV * FNZ) w.X[e] = 0.0;
-    PAR_FOR(e, 12 * FNZ) w.DL[e] = 0.0;
+    PAR_FOR(e, NV * FNZ) X[e] = 0.0;
+    PAR_FOR(e, 12 * FNZ) DL[e] = 0.0;
     SYNC();
     PAR_FOR(e, NB * 6) {
       int b = e / 6, c = e % 6;
@@ -533,14 +542,14 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
       int i0 = first_dof(mb), nd = ndof_of(mb);
       for (int d = 0; d < nd; d++) {
         double val = dot6(w.S + 6 * (i0 + d), g);
-        w.X[(i0 + d) * FNZ + kind * NV + j] = kind == 0 ? -val : val;
+        X[(i0 + d) * FNZ + kind * NV + j] = kind == 0 ? -val : val;
       }
       if (mb == J) {
         if (kind == 0) { cross_mf(s, w.Fsub + 6 * J, t1); for (int i = 0; i < 6; i++) w.top[6 * j + i] = t1[i] - g[i]; }
         else for (int i = 0; i < 6; i++) w.top[6 * (NV + j) + i] = g[i];
       }
     }
-    PAR_FOR(e, NJ) w.X[(6 + e) * FNZ + 2 * NV + e] = -1.0; // R1 for u: -B_act
+    PAR_FOR(e, NJ) X[(6 + e) * FNZ + 2 * NV + e] = -1.0; // R1 for u: -B_act
     // R2 = d(alpha - astar)/d(q,v) for the active contacts
     PAR_FOR(e, nact * NV) {
       int c = e / NV, j = e % NV, f = w.act[c], fb = rb.foot_body[f];
@@ -563,27 +572,28 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
       for (int r = 0; r < 6; r++) Jc[r] = w.Jf[(6 * f + r) * NV + j];
       mat6_vec(w.JlAd + 36 * c, Jc, dlog);
       for (int r = 0; r < 6; r++) {
-        w.DL[(6 * c + r) * FNZ + j] = -dq_[r] - (-cfg.kp[r] * dlog[r] + cfg.kd[r] * wl[r]);
-        w.DL[(6 * c + r) * FNZ + NV + j] = dv_[r] + cfg.kd[r] * Jc[r];
+        DL[(6 * c + r) * FNZ + j] = -dq_[r] - (-cfg.kp[r] * dlog[r] + cfg.kd[r] * wl[r]);
+        DL[(6 * c + r) * FNZ + NV + j] = dv_[r] + cfg.kd[r] * Jc[r];
       }
     }
     SYNC();
     PAR_FOR(e, m.nanc) {
       int i = m.anc_i[e], j = m.anc_j[e];
-      w.X[i * FNZ + j] = dot6(w.S + 6 * i, w.top + 6 * j);
-      w.X[i * FNZ + NV + j] = dot6(w.S + 6 * i, w.top + 6 * (NV + j));
+      X[i * FNZ + j] = dot6(w.S + 6 * i, w.top + 6 * j);
+      X[i * FNZ + NV + j] = dot6(w.S + 6 * i, w.top + 6 * (NV + j));
     }
     SYNC();
     EPH(7);
+#ifdef MPC_HOST_EMU
     PAR_FOR(z, FNZ) { // X = M^-1 R1, one column per thread (column in registers, written back in place)
       double col[NV];
 #pragma unroll
-      for (int k = 0; k < NV; k++) col[k] = w.X[k * FNZ + z];
+      for (int k = 0; k < NV; k++) col[k] = X[k * FNZ + z];
       for (int i = 0; i < NV; i++) {
         double s = 0;
 #pragma unroll
         for (int k = 0; k < NV; k++) s += w.M[i * NV + k] * col[k];
-        w.X[i * FNZ + z] = s;
+        X[i * FNZ + z] = s;
       }
     }
     SYNC();
@@ -591,13 +601,13 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
     PAR_FOR(z, FNZ) { // per column of z: dlam = G^-1 (J X - DL), then da/dz = -X + Y dlam (X column and dlam in registers)
       double xc[NV], t[12], dl[12];
 #pragma unroll
-      for (int i = 0; i < NV; i++) xc[i] = w.X[i * FNZ + z];
+      for (int i = 0; i < NV; i++) xc[i] = X[i * FNZ + z];
 #pragma unroll
       for (int r = 0; r < 12; r++) {
         t[r] = 0.0;
         if (r < nk) {
           const double *Jr = w.Jf + (6 * w.act[r / 6] + r % 6) * NV;
-          double s = -w.DL[r * FNZ + z];
+          double s = -DL[r * FNZ + z];
 #pragma unroll
           for (int i = 0; i < NV; i++) s += Jr[i] * xc[i];
           t[r] = s;
@@ -611,7 +621,7 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
 #pragma unroll
           for (int c = 0; c < 12; c++) if (c < nk) s += w.G[r * 12 + c] * t[c];
           dl[r] = s;
-          w.DL[r * FNZ + z] = s;
+          DL[r * FNZ + z] = s;
         }
       }
 #pragma unroll
@@ -619,10 +629,90 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
         double s = -xc[i];
 #pragma unroll
         for (int r = 0; r < 12; r++) if (r < nk) s += w.Y[i * 13 + 1 + r] * dl[r];
-        w.X[i * FNZ + z] = s; // da/dz
+        X[i * FNZ + z] = s; // da/dz
       }
     }
     SYNC();
+#else
+    { // Tangent of the constrained dynamics on the FP64 tensor pipe, one 8-column tile of z per warp, no block barrier inside:
+      //   X <- M^-1 R1;  T = J X - DL;  dlam = G^-1 T (-> DL);  da/dz = -X + Y dlam (-> X)
+      // Accumulator tiles that feed the next product as its K operand are transposed through a per-warp slice of the dead
+      // [Bc | top] block (32 x 8 for X, 16 x 8 for T / dlam); the right-hand sides of the next tile are fetched from the
+      // L2-resident scratch while the current one is being processed.
+      const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+      double *Xs = w.Bc + 384 * WARP_ID, *Ts = Xs + 256;
+      static_assert(FullWsT<DERIV>::BCS + FullWsT<DERIV>::TOPS >= 3 * 384 || !DERIV, "per-warp transpose tiles do not fit in [Bc | top]");
+      const double *Jb = w.Jf + 6 * w.act[0] * NV; // rows of the active contacts are contiguous in Jf
+      const int ks2 = (nk + 3) / 4;
+      constexpr int NCT = (FNZ + 7) / 8;
+      double bx[7], bnext[7], xn[4][2];
+      { const int cb = 8 * WARP_ID + g;
+#pragma unroll
+        for (int s_ = 0; s_ < 7; s_++) bnext[s_] = (WARP_ID < NCT && cb < FNZ) ? X[(4 * s_ + t) * FNZ + cb] : 0.0; }
+      for (int ct = WARP_ID; ct < NCT; ct += NWARPS) {
+        const int cc = 8 * ct + 2 * t;
+        const bool okc = cc < FNZ;
+#pragma unroll
+        for (int s_ = 0; s_ < 7; s_++) bx[s_] = bnext[s_];
+        { const int cbn = 8 * (ct + NWARPS) + g; // right-hand sides of this warp's next tile
+#pragma unroll
+          for (int s_ = 0; s_ < 7; s_++) bnext[s_] = (ct + NWARPS < NCT && cbn < FNZ) ? X[(4 * s_ + t) * FNZ + cbn] : 0.0; }
+#pragma unroll
+        for (int ti = 0; ti < 4; ti++) {
+          const int row = 8 * ti + g;
+          double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+          for (int s_ = 0; s_ < 7; s_++) dmma_8x8x4(c0, c1, (row < NV) ? w.M[(4 * s_ + t) * NV + row] : 0.0, bx[s_]);
+          xn[ti][0] = c0; xn[ti][1] = c1;
+          *reinterpret_cast<double2 *>(Xs + row * 8 + 2 * t) = make_double2(c0, c1);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int s_ = 0; s_ < 7; s_++) bx[s_] = Xs[(4 * s_ + t) * 8 + g];
+#pragma unroll
+        for (int ti = 0; ti < 2; ti++) {
+          const int row = 8 * ti + g;
+          double c0 = 0.0, c1 = 0.0;
+          if (row < nk && okc) { const double2 d = *reinterpret_cast<const double2 *>(DL + row * FNZ + cc); c0 = -d.x; c1 = -d.y; }
+#pragma unroll
+          for (int s_ = 0; s_ < 7; s_++) dmma_8x8x4(c0, c1, (row < nk) ? Jb[row * NV + 4 * s_ + t] : 0.0, bx[s_]);
+          *reinterpret_cast<double2 *>(Ts + row * 8 + 2 * t) = make_double2(c0, c1);
+        }
+        __syncwarp();
+        double dl[2][2];
+#pragma unroll
+        for (int ti = 0; ti < 2; ti++) {
+          const int row = 8 * ti + g;
+          double c0 = 0.0, c1 = 0.0;
+          for (int s_ = 0; s_ < ks2; s_++) {
+            const int k = 4 * s_ + t;
+            dmma_8x8x4(c0, c1, (row < nk && k < nk) ? w.G[row * 12 + k] : 0.0, (k < nk) ? Ts[k * 8 + g] : 0.0);
+          }
+          dl[ti][0] = c0; dl[ti][1] = c1;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int ti = 0; ti < 2; ti++) {
+          const int row = 8 * ti + g;
+          *reinterpret_cast<double2 *>(Ts + row * 8 + 2 * t) = make_double2(dl[ti][0], dl[ti][1]);
+          if (row < nk && okc) *reinterpret_cast<double2 *>(DL + row * FNZ + cc) = make_double2(dl[ti][0], dl[ti][1]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int ti = 0; ti < 4; ti++) {
+          const int row = 8 * ti + g;
+          double c0 = -xn[ti][0], c1 = -xn[ti][1];
+          for (int s_ = 0; s_ < ks2; s_++) {
+            const int k = 4 * s_ + t;
+            dmma_8x8x4(c0, c1, (row < NV && k < nk) ? w.Y[row * 13 + 1 + k] : 0.0, (k < nk) ? Ts[k * 8 + g] : 0.0);
+          }
+          if (row < NV && okc) *reinterpret_cast<double2 *>(X + row * FNZ + cc) = make_double2(c0, c1);
+        }
+        __syncwarp();
+      }
+    }
+    SYNC();
+#endif
   }
 
   EPH(9);
@@ -635,6 +725,13 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
   mb_cost_terms(m, w, kn.lf_ref, kn.rf_ref, DERIV, io.gap);
 
   EPH(10);
+  if (DERIV) {
+    // the kinematics block [oM | S | v | a | I | Ic] is dead from here on: stage the dlam/dz rows of the active contacts into it, so the
+    // gradient / Hessian / constraint-row phases below read them from shared memory instead of the L2-resident scratch
+    static_assert(NB * 12 + NV * 6 + 2 * NB * 6 + 2 * NB * 10 >= 12 * FNZ, "dlam/dz does not fit in the dead kinematics block");
+    PAR_FOR(e, nk * FNZ) w.oM[e] = DL[e];
+    DL = w.oM; // (the barrier before the first read is the one inside the merit reduction below)
+  }
   // ---- constraint values, multiplier estimates, activity
   // every thread accumulates the merit pieces of the rows / coordinates it owns; one group-wide reduction at the end
   double acc_cost = 0.0, acc_pen = 0.0, acc_prim = 0.0, acc_inner = 0.0;
@@ -677,6 +774,8 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
   compact_flags(w.isact, FNC, w.act_idx, &w.nca, reinterpret_cast<int32_t *>(w.part));
   if (!DERIV) {
     PAR_FOR(i, SC_COUNT) io.scal[i] = w.scal[i];
+    EPH(11);
+    EPH_DUMP(io.phase_out);
     return;
   }
 
@@ -688,19 +787,26 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
   ONE_THREAD io.nca[0] = w.nca;
   const double dt2 = dt * dt;
   PAR_FOR(z, FNZ) {
-    double d6[6], acc = 0;
-    for (int k = 0; k < 6; k++) d6[k] = dt2 * w.X[k * FNZ + z] + ((z == NV + k) ? dt : 0.0);
+    double d6[6], acc = 0, xc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; i++) xc[i] = X[i * FNZ + z]; // one pass over the column of the tangent (L2-resident scratch)
+#pragma unroll
+    for (int k = 0; k < 6; k++) d6[k] = dt2 * xc[k] + ((z == NV + k) ? dt : 0.0);
+#pragma unroll
     for (int i = 0; i < 6; i++) {
       double s = (z < 6) ? w.late.P2[6 * i + z] : 0.0;
+#pragma unroll
       for (int k = 0; k < 6; k++) s += w.late.P1[6 * i + k] * d6[k];
       io.AB[i * FNZ + z] = s; acc += s * w.mln[i];
     }
+#pragma unroll
     for (int i = 6; i < NV; i++) {
-      double s = dt2 * w.X[i * FNZ + z] + ((z == NV + i) ? dt : 0.0) + ((z == i) ? 1.0 : 0.0);
+      double s = dt2 * xc[i] + ((z == NV + i) ? dt : 0.0) + ((z == i) ? 1.0 : 0.0);
       io.AB[i * FNZ + z] = s; acc += s * w.mln[i];
     }
+#pragma unroll
     for (int i = 0; i < NV; i++) {
-      double s = dt * w.X[i * FNZ + z] + ((z == NV + i) ? 1.0 : 0.0);
+      double s = dt * xc[i] + ((z == NV + i) ? 1.0 : 0.0);
       io.AB[(NV + i) * FNZ + z] = s; acc += s * w.mln[NV + i];
     }
     // cost gradient
@@ -708,7 +814,7 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
     if (z >= FN) lz += cfg.wu[z - FN] * (w.u[z - FN] - kn.u_ref[z - FN]);
     for (int f = 0; f < 2; f++)
       if (kn.fcost[f] != 0.0) {
-        const double *Dl = w.DL + 6 * w.sidx[f] * FNZ;
+        const double *Dl = DL + 6 * w.sidx[f] * FNZ;
         for (int r = 0; r < 6; r++) lz += cfg.w_force[r] * Dl[r * FNZ + z] * (w.lam[6 * f + r] - kn.f_ref[6 * f + r]);
       }
     w.late.lxu[z] = lz; io.lxu[z] = lz;
@@ -720,7 +826,7 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
       double c;
       if (r < 22) c = (z == FN + r) ? 1.0 : 0.0;
       else if (r < 44) c = (z == 6 + r - 22) ? -1.0 : 0.0;
-      else { int f = (r - 44) / 17, rr = (r - 44) % 17; const double *Dl = w.DL + 6 * w.sidx[f] * FNZ; c = 0; for (int k = 0; k < 6; k++) c += m.Acone[6 * rr + k] * Dl[k * FNZ + z]; }
+      else { int f = (r - 44) / 17, rr = (r - 44) % 17; const double *Dl = DL + 6 * w.sidx[f] * FNZ; c = 0; for (int k = 0; k < 6; k++) c += m.Acone[6 * rr + k] * Dl[k * FNZ + z]; }
       gz += c * vr;
     }
     if (z < FN) { if (io.k == 0) gz += w.mlk[z]; else if (z >= 6) gz -= w.mlk[z]; }
@@ -732,6 +838,7 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
     io.gE_next[j] = s;
   }
   EPH(12);
+#ifdef MPC_HOST_EMU
   { // Gauss-Newton Hessian H = sum_r w_r J_r' J_r (+ state/control diagonals) on 4 x 4 register tiles of the upper triangle
     constexpr int HT = (FNZ + 3) / 4;
     PAR_FOR(t, HT * HT) {
@@ -753,7 +860,7 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
           for (int j = 0; j < 4; j++) acc[i][j] += va[i] * vb[j];
       };
       for (int f = 0; f < 2; f++)
-        if (kn.fcost[f] != 0.0) for (int r = 0; r < 6; r++) rank1(w.DL + (6 * w.sidx[f] + r) * FNZ, FNZ, cfg.w_force[r]);
+        if (kn.fcost[f] != 0.0) for (int r = 0; r < 6; r++) rank1(DL + (6 * w.sidx[f] + r) * FNZ, FNZ, cfg.w_force[r]);
       if (a0 < FN) {
         for (int r = 0; r < 6; r++) if (cfg.w_cent[r] != 0.0) rank1(w.cj.Jcent + r * FN, FN, cfg.w_cent[r]);
         if (a0 < NV && b0 < NV)
@@ -775,13 +882,61 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
         }
     }
   }
+#else
+  { // Gauss-Newton Hessian H = sum_k w_k J_k' J_k (+ state/control diagonals) as ONE tensor-core product over the 36 weighted
+    // residual-Jacobian rows (12 contact-force rows dlam/dz, 6 centroidal momentum, 12 foot pose, 6 of the base block of the state
+    // error; absent costs keep weight 0).  The rows stay where they are in shared memory and are addressed through a table of
+    // offsets; every warp takes 2 x 2 blocks of 8 x 8 tiles of the FULL matrix, so the result leaves as row-major 16-byte stores.
+    const double *base = reinterpret_cast<const double *>(&w);
+    PAR_FOR(k, 36) {
+      const double *p = w.Jls; int len = 0; double wgt = 0.0;
+      if (k < 12) { const int f = k / 6, r = k % 6; if (kn.fcost[f] != 0.0 && w.sidx[f] >= 0) { p = DL + (6 * w.sidx[f] + r) * FNZ; len = FNZ; wgt = cfg.w_force[r]; } }
+      else if (k < 18) { p = w.cj.Jcent + (k - 12) * FN; len = FN; wgt = cfg.w_cent[k - 12]; }
+      else if (k < 30) { const int j = k - 18, r = j % 6; p = w.cj.Jpose + j * NV; len = NV; wgt = (j < 6) ? kn.w_lf[r] : kn.w_rf[r]; }
+      else { p = w.Jls + 6 * (k - 30); len = 6; wgt = cfg.wx[k - 30]; }
+      w.hrow_len[k] = (int32_t)(p - base) | (len << 20); // offset (doubles) and row length packed in one word
+      w.hrow_w[k] = wgt;
+    }
+    SYNC();
+    constexpr int NBK = ((FNZ + 7) / 8 + 1) / 2; // 5 blocks of 16 per side
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    for (int p = WARP_ID; p < NBK * NBK; p += NWARPS) {
+      const int ti = 2 * (p / NBK), tj = 2 * (p % NBK);
+      const int ia = ti * 8 + g, ib = tj * 8 + g;
+      double c[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};
+#pragma unroll 3
+      for (int k0 = 0; k0 < 36; k0 += 4) {
+        const int packed = w.hrow_len[k0 + t], off = packed & 0xFFFFF, len = packed >> 20;
+        const double wk = w.hrow_w[k0 + t];
+        const double *row = base + off;
+        const double a0 = (ia < len) ? wk * row[ia] : 0.0, a1 = (ia + 8 < len) ? wk * row[ia + 8] : 0.0;
+        const double b0 = (ib < len) ? row[ib] : 0.0, b1 = (ib + 8 < len) ? row[ib + 8] : 0.0;
+        dmma_8x8x4(c[0][0][0], c[0][0][1], a0, b0);
+        dmma_8x8x4(c[0][1][0], c[0][1][1], a0, b1);
+        dmma_8x8x4(c[1][0][0], c[1][0][1], a1, b0);
+        dmma_8x8x4(c[1][1][0], c[1][1][1], a1, b1);
+      }
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+          const int r = (ti + a) * 8 + g, cc = (tj + b) * 8 + 2 * t;
+          if (r >= FNZ || cc >= FNZ) continue;
+          double h0 = c[a][b][0], h1 = c[a][b][1];
+          const double dg = io.preg + ((r >= FN) ? cfg.wu[r - FN] : ((r >= 6) ? cfg.wx[r] : 0.0));
+          if (r == cc) h0 += dg; else if (r == cc + 1) h1 += dg;
+          *reinterpret_cast<double2 *>(io.H + r * FNZ + cc) = make_double2(h0, h1);
+        }
+    }
+  }
+#endif
   EPH(13);
   PAR_FOR(e, w.nca * FNZ) { // active constraint rows, compacted
     int ai = e / FNZ, z = e % FNZ, r = w.act_idx[ai];
     double c;
     if (r < 22) c = (z == FN + r) ? 1.0 : 0.0;
     else if (r < 44) c = (z == 6 + r - 22) ? -1.0 : 0.0;
-    else { int f = (r - 44) / 17, rr = (r - 44) % 17; const double *Dl = w.DL + 6 * w.sidx[f] * FNZ; c = 0; for (int k = 0; k < 6; k++) c += m.Acone[6 * rr + k] * Dl[k * FNZ + z]; }
+    else { int f = (r - 44) / 17, rr = (r - 44) % 17; const double *Dl = DL + 6 * w.sidx[f] * FNZ; c = 0; for (int k = 0; k < 6; k++) c += m.Acone[6 * rr + k] * Dl[k * FNZ + z]; }
     io.CDact[e] = c;
   }
   SYNC();

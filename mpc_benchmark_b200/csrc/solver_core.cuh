@@ -83,6 +83,7 @@ HD KnotIO make_io(const Ws &w, int b, int k, bool trial) {
   io.CDact = w.CDact + kb * w.nc * w.nz; io.nca = w.nca + kb; io.act_idx = w.act_idx + kb * w.nc;
   io.gap = w.gap + kT * w.n; io.h = w.h + kb * w.nc; io.scal = (trial ? w.tscal : w.scal) + kb * SC_COUNT;
   io.xdot = w.xdot + kb * 56; io.lamc = w.lamc + kb * 12;
+  io.scratch = (k < w.T) ? w.W + kT * w.n * w.nz : nullptr;
   io.phase_out = (b == 0 && k == 1) ? w.phase + (trial ? 32 : 16) : nullptr;
   return io;
 }
