@@ -372,7 +372,7 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
   const int nact = w.nact, nk = 6 * nact;
   // derivative kernel: explicit mass-matrix inverse, raw right-hand sides [tau - b | J'] (NV x 13) in Yr; values kernel: solve in place in Y
   // [L^-1 (NV x NV) | 64 doubles of scratch per warp] in the free [Bc | top] block; the raw right-hand sides go to the global scratch
-  double *Ls = w.Bc;
+  double *Ls = reinterpret_cast<double *>(&w) + offsetof(FullWsT<DERIV>, Bc) / sizeof(double); // spans [Bc | top]
   double *X = io.scratch, *DL = io.scratch + NV * FNZ; // derivative pass only (null otherwise)
   double *Yr = DERIV ? DL : w.Y;
   const double a0[6] = {-rb.gravity[0], -rb.gravity[1], -rb.gravity[2], 0, 0, 0};
@@ -640,7 +640,7 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
       // [Bc | top] block (32 x 8 for X, 16 x 8 for T / dlam); the right-hand sides of the next tile are fetched from the
       // L2-resident scratch while the current one is being processed.
       const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-      double *Xs = w.Bc + 384 * WARP_ID, *Ts = Xs + 256;
+      double *Xs = Ls + 384 * WARP_ID, *Ts = Xs + 256;
       static_assert(FullWsT<DERIV>::BCS + FullWsT<DERIV>::TOPS >= 3 * 384 || !DERIV, "per-warp transpose tiles do not fit in [Bc | top]");
       const double *Jb = w.Jf + 6 * w.act[0] * NV; // rows of the active contacts are contiguous in Jf
       const int ks2 = (nk + 3) / 4;
@@ -729,8 +729,9 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
     // the kinematics block [oM | S | v | a | I | Ic] is dead from here on: stage the dlam/dz rows of the active contacts into it, so the
     // gradient / Hessian / constraint-row phases below read them from shared memory instead of the L2-resident scratch
     static_assert(NB * 12 + NV * 6 + 2 * NB * 6 + 2 * NB * 10 >= 12 * FNZ, "dlam/dz does not fit in the dead kinematics block");
-    PAR_FOR(e, nk * FNZ) w.oM[e] = DL[e];
-    DL = w.oM; // (the barrier before the first read is the one inside the merit reduction below)
+    double *DLs = reinterpret_cast<double *>(&w) + offsetof(FullWsT<DERIV>, oM) / sizeof(double); // the whole block, not just oM
+    PAR_FOR(e, nk * FNZ) DLs[e] = DL[e];
+    DL = DLs; // (the barrier before the first read is the one inside the merit reduction below)
   }
   // ---- constraint values, multiplier estimates, activity
   // every thread accumulates the merit pieces of the rows / coordinates it owns; one group-wide reduction at the end
