@@ -439,10 +439,23 @@ HD void chol_diag_block(double *A, int k0, int bw, int ld, double *Di) {
     }
 }
 #ifndef MPC_HOST_EMU
-// Device version called by ALL lanes of the group's warp 0: lane 0 factors the block exactly as above (the dependent
-// rsqrt / FMA chain stays in one thread's registers, no shuffles on it), then the eight columns of the inverse are built
-// by eight lanes side by side from the factor published through Di.  A lone thread is issue-bound on the ~350 instructions
-// of the inverse; eight lanes share them.
+// 1/a for the pivot chain: hardware seed (rcp.approx.ftz.f64, ~20 bits) + two Newton steps = 56 cycles of dependent latency
+// on sm_100a, against 77 for rsqrt() and 83 for a division (tools/ubench/lat.cu).
+__device__ __forceinline__ double fast_rcp(double a) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double e = fma(-a, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-a, y, 1.0);
+  y = fma(y, e, y);
+  if (!(fabs(a) > 1e-30 && fabs(a) < 1e30)) y = 1.0 / a;
+  return y;
+}
+// Device version called by ALL lanes of the group's warp 0.  Lane 0 runs the pivot chain in registers as a square-root-free
+// LDL' elimination (per column: reciprocal of the pivot -> scaled column -> update, 56 + 8.5 + 8.5 cycles of dependent
+// latency; a Cholesky column costs a 77-cycle rsqrt more and the chain is what the whole blocked factorisation waits for).
+// The eight lanes then finish side by side, one column each: r_i = rsqrt(d_i), the unit-triangular inverse by forward
+// substitution (one FMA per dependent step), and the scaling  L = Lt diag(sqrt d),  L^-1 = diag(r) Lt^-1.
 __device__ __forceinline__ void chol_diag_block_warp0(double *A, int k0, int bw, int ld, double *Di) {
   const int lane = threadIdx.x & 31;
   if (lane == 0) {
@@ -453,43 +466,43 @@ __device__ __forceinline__ void chol_diag_block_warp0(double *A, int k0, int bw,
       for (int c = 0; c < CB; c++) L[r][c] = (c <= r) ? ((r < bw) ? A[(k0 + r) * ld + k0 + c] : ((r == c) ? 1.0 : 0.0)) : 0.0;
 #pragma unroll
     for (int j = 0; j < CB; j++) {
-      const double d = fast_rsqrt(L[j][j]);
-      L[j][j] = L[j][j] * d;
-      if (j < bw) A[(k0 + j) * ld + k0 + j] = L[j][j];
-      Di[j * CB + j] = d; // reciprocal of the diagonal entry (scratch for the inverse below)
+      const double rj = fast_rcp(L[j][j]);
+      Di[j * CB + j] = L[j][j]; // pivot d_j (scratch for the finish below)
+      double tcol[CB];
 #pragma unroll
-      for (int r = j + 1; r < CB; r++) {
-        L[r][j] *= d;
-        if (r < bw) A[(k0 + r) * ld + k0 + j] = L[r][j];
-        Di[r * CB + j] = L[r][j];
-      }
+      for (int r = j + 1; r < CB; r++) { tcol[r] = L[r][j] * rj; Di[r * CB + j] = tcol[r]; } // unit-lower factor Lt
 #pragma unroll
       for (int r = j + 1; r < CB; r++)
 #pragma unroll
-        for (int c = j + 1; c <= r; c++) L[r][c] -= L[r][j] * L[c][j];
+        for (int c = j + 1; c <= r; c++) L[r][c] -= tcol[r] * L[c][j];
     }
   }
   __syncwarp();
-  double Lf[CB][CB], dd[CB], X[CB];
+  double Lf[CB][CB], dd[CB], X[CB], lcol[CB];
   const int c = lane & 7;
 #pragma unroll
   for (int i = 0; i < CB; i++) {
-    dd[i] = Di[i * CB + i];
+    dd[i] = rsqrt(Di[i * CB + i]);
+    lcol[i] = Di[i * CB + c]; // own column of Lt (rows below the diagonal; the diagonal slot holds the pivot)
 #pragma unroll
     for (int t = 0; t < CB; t++) Lf[i][t] = (t < i) ? Di[i * CB + t] : 0.0;
   }
+  const double pc = Di[c * CB + c];
   __syncwarp();
+  const double sc = pc * rsqrt(pc); // sqrt(d_c)
 #pragma unroll
   for (int t = 0; t < CB; t++) X[t] = (t == c) ? 1.0 : 0.0;
 #pragma unroll
   for (int t = 0; t < CB; t++) {
-    X[t] *= dd[t]; // rows above the diagonal stay 0
 #pragma unroll
-    for (int i = t + 1; i < CB; i++) X[i] -= Lf[i][t] * X[t];
+    for (int i = t + 1; i < CB; i++) X[i] -= Lf[i][t] * X[t]; // rows above the diagonal stay 0
   }
   if (lane < CB) {
 #pragma unroll
-    for (int i = 0; i < CB; i++) Di[i * CB + c] = (i < bw && c < bw) ? X[i] : 0.0;
+    for (int i = 0; i < CB; i++) {
+      Di[i * CB + c] = (i < bw && c < bw) ? dd[i] * X[i] : 0.0;
+      if (i < bw && c < bw && i >= c) A[(k0 + i) * ld + k0 + c] = (i == c) ? sc : lcol[i] * sc;
+    }
   }
   __syncwarp();
 }

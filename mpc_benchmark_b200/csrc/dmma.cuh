@@ -22,28 +22,38 @@ __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, dou
 // C (8*mt x 8*nt, ldc) = init + A^T B,  K multiple of 4.
 //   init: 0 (Cinit == nullptr) or Cinit (ldci) restricted to rows < vr and cols < vc (zero outside) — lets the
 //   Hessian update read H_k straight from global memory while keeping the shared copy zero-padded.
-// upper_only: skip tiles strictly below the block diagonal (caller mirrors).
+// upper_only: square symmetric result; only the 16 x 16 blocks on / above the block diagonal are computed, the rest is mirrored.
+// Cg: optional global-memory mirror of the result (columns < vcg), written straight from the accumulators.
 // lower_tri_operands: A and B are lower-triangular K x K matrices (A[k][i] = 0 for k < i): the k-loop of tile (i, j) starts at
 // 8 max(i, j) — exact, it only skips products with structural zeros.
 HD void mma_tn(int mt, int nt, int K, const double *A, int lda, const double *B, int ldb, double *C, int ldc, const double *Cinit, int ldci,
-               int vr, int vc, bool upper_only, bool lower_tri_operands = false) {
+               int vr, int vc, bool upper_only, bool lower_tri_operands = false, double *Cg = nullptr, int ldcg = 0, int vcg = 0) {
 #ifdef MPC_HOST_EMU
   for (int i = 0; i < 8 * mt; i++)
     for (int j = 0; j < 8 * nt; j++) {
-      if (upper_only && (j / 8) < (i / 8)) continue;
+      if (upper_only && (j / 16) < (i / 16)) continue;
       double s = (Cinit && i < vr && j < vc) ? Cinit[i * ldci + j] : 0.0;
       for (int k = 0; k < K; k++) s += A[k * lda + i] * B[k * ldb + j];
       C[i * ldc + j] = s;
+      if (Cg && j < vcg) Cg[i * ldcg + j] = s;
     }
+  if (upper_only)
+    for (int i = 0; i < 8 * mt; i++)
+      for (int j = 0; j < 8 * nt; j++)
+        if ((j / 16) < (i / 16) && i < (Cinit ? vc : 8 * nt)) C[i * ldc + j] = C[j * ldc + i];
 #else
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   // each warp takes 2 x 2 blocks of tiles: 4 independent accumulator chains per warp, A and B fragments shared
   const int mtp = (mt + 1) / 2, ntp = (nt + 1) / 2;
-  for (int p = warp; p < mtp * ntp; p += nwarps) {
-    const int ti = (p / ntp) * 2, tj = (p % ntp) * 2;
+  // upper_only (square, symmetric result): only the blocks on or above the block diagonal are computed — enumerated compactly so
+  // that the warps stay balanced — and every tile strictly above the diagonal blocks is also stored transposed (the mirror)
+  const int nwork = upper_only ? mtp * (mtp + 1) / 2 : mtp * ntp, vcm = Cinit ? vc : 8 * nt;
+  for (int p = warp; p < nwork; p += nwarps) {
+    int bi, bj;
+    if (upper_only) { bi = 0; int q = p; while (q >= mtp - bi) { q -= mtp - bi; bi++; } bj = bi + q; } else { bi = p / ntp; bj = p % ntp; }
+    const int ti = bi * 2, tj = bj * 2;
     const bool r2 = (ti + 1 < mt), c2 = (tj + 1 < nt);
-    if (upper_only && tj + (c2 ? 1 : 0) < ti) continue;
     double c[2][2][2];
 #pragma unroll
     for (int a = 0; a < 2; a++)
@@ -74,6 +84,11 @@ HD void mma_tn(int mt, int nt, int K, const double *A, int lda, const double *B,
         if ((a == 1 && !r2) || (b == 1 && !c2)) continue;
         const int row = (ti + a) * 8 + g, col = (tj + b) * 8 + 2 * t;
         *reinterpret_cast<double2 *>(C + row * ldc + col) = make_double2(c[a][b][0], c[a][b][1]);
+        if (Cg && col < vcg) *reinterpret_cast<double2 *>(Cg + row * ldcg + col) = make_double2(c[a][b][0], c[a][b][1]); // vcg, ldcg even
+        if (upper_only && bi < bj) { // mirror (never a tile anyone reads as Cinit); columns >= vcm are scratch and stay out of the rows below
+          if (col < vcm) C[col * ldc + row] = c[a][b][0];
+          if (col + 1 < vcm) C[(col + 1) * ldc + row] = c[a][b][1];
+        }
       }
   }
 #endif
@@ -119,6 +134,74 @@ HD void tile_trsm(double *A, int ld, int i0, int k0, const double *Di) {
   __syncwarp();
   *reinterpret_cast<double2 *>(A + (i0 + g) * ld + k0 + 2 * t) = c;
 #endif
+}
+
+// In-place solve (L L')^-1 B on the tensor pipe, L = 8 NB x 8 NB factor left by chol_mma (strictly-lower tiles of A plus the
+// inverses Dinv of its diagonal blocks).  B consists of `nt` column tiles of 8 columns: tile ct < nt_main lives in Bm (leading
+// dimension ldb, columns 8 ct ..), the remaining tiles in Bx (leading dimension ldx).  ONE WARP PER COLUMN TILE runs the whole
+// forward and backward substitution on its own 8 columns — no block barriers, only warp-level ones; per block row
+//   R_i = B_i - sum_k L_ik Y_k (DMMA, two accumulator chains),  Y_i = Dinv_i R_i (DMMA; the tile itself is the scratch that turns
+// the accumulator layout into the B-fragment layout).  Replaces explicit-inverse products: 2 NB short dependent steps per tile.
+template <int NB> HD void trsm_mma(const double *A, int ld, const double *Dinv, double *Bm, int ldb, int nt_main, double *Bx, int ldx, int nt) {
+#ifdef MPC_HOST_EMU
+  trsm_blocked(A, 8 * NB, ld, Dinv, Bm, 8 * nt_main, ldb);
+  if (nt > nt_main) trsm_blocked(A, 8 * NB, ld, Dinv, Bx, 8 * (nt - nt_main), ldx);
+#else
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  for (int ct = (threadIdx.x >> 5); ct < nt; ct += (blockDim.x >> 5)) {
+    double *zc = (ct < nt_main) ? Bm + 8 * ct : Bx + 8 * (ct - nt_main);
+    const int lz = (ct < nt_main) ? ldb : ldx;
+#pragma unroll
+    for (int ib = 0; ib < NB; ib++) { // forward: Y_i = Dinv_i (B_i - sum_{k<i} L_ik Y_k)
+      double2 *cp = reinterpret_cast<double2 *>(zc + (8 * ib + g) * lz + 2 * t);
+      double2 c = *cp;
+      double e0 = 0.0, e1 = 0.0;
+#pragma unroll
+      for (int kb = 0; kb < ib; kb++) {
+        const double *pa = A + (8 * ib + g) * ld + 8 * kb + t;
+        const double *pb = zc + (8 * kb + t) * lz + g;
+        dmma_8x8x4(c.x, c.y, -pa[0], pb[0]);
+        dmma_8x8x4(e0, e1, -pa[4], pb[4 * lz]);
+      }
+      c.x += e0; c.y += e1;
+      *cp = c;
+      __syncwarp();
+      const double b0 = zc[(8 * ib + t) * lz + g], b1 = zc[(8 * ib + 4 + t) * lz + g];
+      __syncwarp();
+      const double *Di = Dinv + 64 * ib;
+      double2 d = make_double2(0.0, 0.0);
+      dmma_8x8x4(d.x, d.y, Di[g * 8 + t], b0);
+      dmma_8x8x4(d.x, d.y, Di[g * 8 + 4 + t], b1);
+      *cp = d;
+      __syncwarp();
+    }
+#pragma unroll
+    for (int ib = NB - 1; ib >= 0; ib--) { // backward: X_i = Dinv_i' (Y_i - sum_{k>i} L_ki' X_k)
+      double2 *cp = reinterpret_cast<double2 *>(zc + (8 * ib + g) * lz + 2 * t);
+      double2 c = *cp;
+      double e0 = 0.0, e1 = 0.0;
+#pragma unroll
+      for (int kb = ib + 1; kb < NB; kb++) {
+        const double *pa = A + (8 * kb + t) * ld + 8 * ib + g; // (L_ki)'[g][t] = L_ki[t][g]
+        const double *pb = zc + (8 * kb + t) * lz + g;
+        dmma_8x8x4(c.x, c.y, -pa[0], pb[0]);
+        dmma_8x8x4(e0, e1, -pa[4 * ld], pb[4 * lz]);
+      }
+      c.x += e0; c.y += e1;
+      *cp = c;
+      __syncwarp();
+      const double b0 = zc[(8 * ib + t) * lz + g], b1 = zc[(8 * ib + 4 + t) * lz + g];
+      __syncwarp();
+      const double *Di = Dinv + 64 * ib;
+      double2 d = make_double2(0.0, 0.0);
+      dmma_8x8x4(d.x, d.y, Di[t * 8 + g], b0);
+      dmma_8x8x4(d.x, d.y, Di[(4 + t) * 8 + g], b1);
+      *cp = d;
+      __syncwarp();
+    }
+  }
+#endif
+  SYNC();
 }
 
 // Tensor-core blocked Cholesky (lower, in place) for n = 8 NB with a one-panel lookahead: per panel the tiles below the

@@ -33,8 +33,9 @@ template <int N, int M, int NC, int NCAP = NC> struct RicFastLayout {
   static constexpr int LDN = (N % 16 == 8) ? N : N + 8;             // ld of N x N buffers
   static constexpr int LDZ = (ZP % 16 == 8) ? ZP : ZP + 8;          // ld of N x ZP buffers (AB, W)
   static constexpr int LDH = ZP;                                    // ld of the Hessian buffer
-  static_assert(N * LDZ <= 2 * N * LDN, "W must fit over the dead [P | G] buffers");
-  static constexpr int phase1 = 3 * N * LDN + N * LDZ;  // P, G (later reused as W), Li, AB
+  static_assert(N * LDZ <= 2 * N * LDN - 8 * N, "W must fit behind P, next to the [pv | 0] tile");
+  static_assert(ZP > NZ, "the Hessian update needs a spare padding column for pt");
+  static constexpr int phase1 = 3 * N * LDN + N * LDZ;  // P, G + scratch (later reused as W), AB
   static constexpr int MR = (M + 7) / 8 * 8;                        // control block padded to whole 8 x 8 tiles (identity / zero padding)
   static constexpr int LDR = (MR % 16 == 8) ? MR : MR + 8;          // ld of the padded R^ buffer
   static constexpr int LDZMAX = (NR + NCAP + 7) / 8 * 8;            // ld of Z for NCAP active rows (runtime ld: round8(NR + nca))
@@ -65,7 +66,7 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
   // ---- carve shared memory
   double *H = ws;                              // ZP x LDH, zero padded; [0:N,0:N] carries the value-function Hessian between knots
   double *U0 = H + ZP * LDH;
-  double *P = U0, *G = P + N * LDN, *Li = G + N * LDN, *AB = U0 + Lay::offAB, *W = P;  // phase 1 (W overwrites the dead P, G)
+  double *P = U0, *G = P + N * LDN, *AB = U0 + Lay::offAB, *W = G, *PV = G + 2 * N * LDN - 8 * N;  // phase 1 (W overwrites the dead factor G; PV: [pv | 0] tile)
   double *Z = U0, *CDs = U0 + Lay::offCD;  // phase 2 (Kv, Rh, Sg: carved per knot, see `big`)
   double *vec = U0 + Lay::un;
   double *p = vec, *pt = p + ZP, *gh = pt + ZP, *fb = gh + ZP, *tmp = fb + ZP, *dx = tmp + ZP, *z = dx + ZP, *pv = z + ZP;
@@ -113,108 +114,55 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
     const double *gH = io.H + (size_t)k * NZ * NZ;
     const int nca = io.nca[k];
     const bool big = (NCAP < NC) && nca > NCAP; // more active rows than the fast carving holds: [C D] is read from global memory
-    // 1. P <- symmetrised value Hessian (left in H by the previous knot), then H <- H_k asynchronously (lands before the
-    //    Hessian update needs it); E normalisation P <- T' P T, p <- T' p
+    // 1. ONE pass over the value Hessian left in H by the previous knot: P <- T' sym(H) T (E normalisation: T = blockdiag(T6, I)
+    //    touches the 6 base rows / columns only), G <- I + mu_d P, and the normalised gradient tmp <- T' p
+    MBAR_WAIT(mbar + 2, (T - 1 - k) & 1); // [A B], T6 and fbar of this knot (issued one knot ahead)
+    PHASE(21);
     PAR_FOR(e, N * N) { // lanes: 8 consecutive j x 4 consecutive i, which keeps the transposed read at 8-way bank conflicts
       const int blk = e >> 5, l = e & 31, i = (blk / (N / 8)) * 4 + (l >> 3), j = (blk % (N / 8)) * 8 + (l & 7);
-      P[i * LDN + j] = 0.5 * (H[i * LDH + j] + H[j * LDH + i]);
+      double v;
+      if (i >= 6 && j >= 6) v = 0.5 * (H[i * LDH + j] + H[j * LDH + i]);
+      else if (i >= 6) { v = 0; for (int q = 0; q < 6; q++) v += 0.5 * (H[i * LDH + q] + H[q * LDH + i]) * T6[6 * q + j]; }
+      else if (j >= 6) { v = 0; for (int q = 0; q < 6; q++) v += T6[6 * q + i] * (0.5 * (H[q * LDH + j] + H[j * LDH + q])); }
+      else {
+        v = 0;
+        for (int q = 0; q < 6; q++) {
+          double r = 0;
+          for (int m = 0; m < 6; m++) r += 0.5 * (H[q * LDH + m] + H[m * LDH + q]) * T6[6 * m + j];
+          v += T6[6 * q + i] * r;
+        }
+      }
+      P[i * LDN + j] = v;
+      G[i * LDN + j] = mu_d * v + ((i == j) ? 1.0 : 0.0);
     }
-    MBAR_WAIT(mbar + 2, (T - 1 - k) & 1); // [A B], T6 and fbar of this knot
+    PAR_FOR(i, N) { double v = p[i]; if (i < 6) { v = 0; for (int q = 0; q < 6; q++) v += T6[6 * q + i] * p[q]; } tmp[i] = v; }
+    PAR_FOR(e, N * 8) PV[e] = 0.0;
     SYNC();
+    PHASE(16);
+    // H is dead now: H <- H_k asynchronously (lands before the Hessian update needs it);  pv = p + P f
     ONE_THREAD MBAR_EXPECT_TX(mbar + 3, NZ * NZ * 8);
     PAR_FOR(i, NZ) { FENCE_PROXY_ASYNC(); BULK_G2S(H + i * LDH, gH + i * NZ, NZ * 8, mbar + 3); }
-    PHASE(16);
-    PAR_FOR(e, N * 6) { int i = e / 6, j = e % 6; double s = 0; for (int l = 0; l < 6; l++) s += P[i * LDN + l] * T6[6 * l + j]; Li[e] = s; }
+    matvec_rows(P, LDN, N, N, fb, tmp, pv);
     SYNC();
-    PAR_FOR(e, N * 6) { int i = e / 6, j = e % 6; P[i * LDN + j] = Li[e]; }
-    SYNC();
-    PAR_FOR(e, 6 * N) { int i = e / N, j = e % N; double s = 0; for (int l = 0; l < 6; l++) s += T6[6 * l + i] * P[l * LDN + j]; Li[e] = s; }
-    PAR_FOR(i, 6) { double s = 0; for (int l = 0; l < 6; l++) s += T6[6 * l + i] * p[l]; tmp[i] = s; }
-    SYNC();
-    PAR_FOR(e, 6 * N) { int i = e / N, j = e % N; P[i * LDN + j] = Li[e]; }
-    PAR_FOR(i, 6) p[i] = tmp[i];
-    SYNC();
-    PAR_FOR(e, N * LDN) Li[e] = 0.0;
-    PHASE(0);
-    // 2. G = chol(I + mu_d P);  pv = p + P f
-    PAR_FOR(e, N * N) { int i = e / N, j = e % N; G[i * LDN + j] = mu_d * P[i * LDN + j] + ((i == j) ? 1.0 : 0.0); }
-    matvec_rows(P, LDN, N, N, fb, p, pv);
-    SYNC();
+    PAR_FOR(i, N) PV[8 * i] = pv[i];
     PHASE(1);
+    // 2. G = chol(I + mu_d P)
     chol_mma<NBLK>(G, LDN, dinv);
     PHASE(2);
-    // 3. Linv = G^-1 (lower triangular): independent forward-substitution chains, one per 8-column block and warp
-    {
-#ifdef MPC_HOST_EMU
-      for (int jb = 0; jb < NBLK; jb++) {
-        double *tt = wtmp;
-        for (int ib = jb; ib < NBLK; ib++) {
-          for (int e = 0; e < 64; e++) { // tt = E_ij - sum_k L_ik X_kj
-            int r = e >> 3, c = e & 7;
-            double s = (ib == jb && r == c) ? 1.0 : 0.0;
-            for (int kb = jb; kb < ib; kb++)
-              for (int q = 0; q < 8; q++) s -= G[(8 * ib + r) * LDN + 8 * kb + q] * Li[(8 * kb + q) * LDN + 8 * jb + c];
-            tt[e] = s;
-          }
-          for (int e = 0; e < 64; e++) { // X_ij = Dinv_i tt
-            int r = e >> 3, c = e & 7;
-            const double *Di = dinv + 64 * ib;
-            double s = 0;
-            for (int q = 0; q <= r; q++) s += Di[r * 8 + q] * tt[q * 8 + c];
-            Li[(8 * ib + r) * LDN + 8 * jb + c] = s;
-          }
-        }
-      }
-#else
-      // one warp per block column jb; every 8 x 8 tile product runs on the DMMA pipe:
-      //   X_jj = Dinv_j ,  X_ij = -Dinv_i (sum_{k=j}^{i-1} L_ik X_kj)
-      const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-      for (int jb = (threadIdx.x >> 5); jb < NBLK; jb += (blockDim.x >> 5)) {
-        double *tt = wtmp + 64 * (threadIdx.x >> 5);
-        for (int ib = jb; ib < NBLK; ib++) {
-          const double *Di = dinv + 64 * ib;
-          if (ib == jb) {
-            for (int e = lane; e < 64; e += 32) Li[(8 * ib + (e >> 3)) * LDN + 8 * jb + (e & 7)] = Di[e];
-          } else {
-            double c0 = 0.0, c1 = 0.0;
-            for (int kb = jb; kb < ib; kb++) {
-              const double *pa = G + (8 * ib + g) * LDN + 8 * kb + t;  // L_ik [g][t]
-              const double *pb = Li + (8 * kb + t) * LDN + 8 * jb + g; // X_kj [t][g]
-              dmma_8x8x4(c0, c1, pa[0], pb[0]);
-              dmma_8x8x4(c0, c1, pa[4], pb[4 * LDN]);
-            }
-            *reinterpret_cast<double2 *>(tt + g * 8 + 2 * t) = make_double2(c0, c1);
-            __syncwarp();
-            double d0 = 0.0, d1 = 0.0;
-            dmma_8x8x4(d0, d1, Di[g * 8 + t], tt[t * 8 + g]);
-            dmma_8x8x4(d0, d1, Di[g * 8 + 4 + t], tt[(4 + t) * 8 + g]);
-            *reinterpret_cast<double2 *>(Li + (8 * ib + g) * LDN + 8 * jb + 2 * t) = make_double2(-d0, -d1);
-          }
-          __syncwarp();
-        }
-      }
-#endif
-      SYNC();
-    }
-    PHASE(3);
-    // 4. Lambda^-1 = Linv' Linv (into G);  5. Pt = Lambda^-1 P (into Li), pt = Lambda^-1 pv
-    mma_tn(NBLK, NBLK, N, Li, LDN, Li, LDN, G, LDN, nullptr, 0, 0, 0, false, true);
-    matvec_rows(G, LDN, N, N, pv, nullptr, pt);
-    mma_tn(NBLK, NBLK, N, G, LDN, P, LDN, Li, LDN, nullptr, 0, 0, 0, false);
+    // 3. [P | pv] <- Lambda^-1 [P | pv] in place: blocked forward / backward substitution, one warp per 8-column tile
+    trsm_mma<NBLK>(G, LDN, dinv, P, LDN, NBLK, PV, 8, NBLK + 1);
     PHASE(4);
-    // 6. W = Pt [A B];  7. H = H_k + [A B]' W;  gh = g + [A B]' pt
-    mma_tn(NBLK, ZP / 8, N, Li, LDN, AB, LDZ, W, LDZ, nullptr, 0, 0, 0, false);
+    // 4. W = Pt [A B] (into shared memory over the dead factor AND to HBM for the forward sweep, straight from the accumulators)
+    mma_tn(NBLK, ZP / 8, N, P, LDN, AB, LDZ, W, LDZ, nullptr, 0, 0, 0, false, false, io.W + (size_t)k * N * NZ, NZ, NZ);
     PHASE(17);
+    // pt rides in the first padding column of W, so [A B]' pt falls out of the Hessian update (column NZ of H)
+    PAR_FOR(i, N) { const double v = PV[8 * i]; pt[i] = v; W[i * LDZ + NZ] = v; io.pt[(size_t)k * N + i] = v; }
     MBAR_WAIT(mbar + 3, (T - 1 - k) & 1); // H_k
     SYNC();
-    mma_tn(ZP / 8, ZP / 8, N, AB, LDZ, W, LDZ, H, LDH, H, LDH, ZP, ZP, false); // in place: H = H_k + [A B]' W (padding stays zero)
+    // 5. H = H_k + [A B]' W in place (rows / columns >= NZ of H_k read as zero);  gh = g + [A B]' pt
+    mma_tn(ZP / 8, ZP / 8, N, AB, LDZ, W, LDZ, H, LDH, H, LDH, ZP, NZ, true); // symmetric: upper blocks computed, lower mirrored
     PHASE(18);
-    PAR_FOR(i, NZ) { double s = io.g[(size_t)k * NZ + i]; for (int l = 0; l < N; l++) s += AB[l * LDZ + i] * pt[l]; gh[i] = s; }
-    PAR_FOR(e, N * (NZ / 2)) {
-      int i = e / (NZ / 2), j = (e % (NZ / 2)) * 2;
-      *reinterpret_cast<double2 *>(io.W + (size_t)k * N * NZ + i * NZ + j) = *reinterpret_cast<const double2 *>(W + i * LDZ + j);
-    }
-    PAR_FOR(i, N) io.pt[(size_t)k * N + i] = pt[i];
+    PAR_FOR(i, NZ) gh[i] = io.g[(size_t)k * NZ + i] + H[i * LDH + NZ];
     SYNC();
     // [A B]_k is dead: when the active rows of this knot keep phase 2 clear of the buffer, fetch the next knot's now
     const bool early = !big && ((nca == 0) ? Lay::offCD : ((Lay::offCD + nca * NZ > Lay::offSg + nca * nca) ? Lay::offCD + nca * NZ : Lay::offSg + nca * nca)) <= Lay::offAB;
@@ -243,68 +191,10 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
     chol_blocked(Rh, MR, LDR, dinv);
     trsm_blocked(Rh, MR, LDR, dinv, Z, ncol, ldz);
 #else
-    // Z <- R^-1 Z on the tensor pipe: blocked Cholesky, in-place inverse X = L^-1 of the factor (one warp, block columns
-    // left to right: column j only needs the columns >= j of L), then Z <- X Z (tile rows bottom-up) and Z <- X' Z (top-down),
-    // both in place with one warp per 8-column tile of Z
+    // Z <- R^-1 Z on the tensor pipe: blocked Cholesky, then forward / backward substitution with one warp per 8-column tile of Z
     chol_mma<MR / 8>(Rh, LDR, dinv);
     PHASE(7);
-    {
-      constexpr int NBR = MR / 8;
-      const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-      if (warp == 0) {
-        for (int jb = 0; jb < NBR; jb++) {
-          for (int e = lane; e < 64; e += 32) Rh[(8 * jb + (e >> 3)) * LDR + 8 * jb + (e & 7)] = dinv[64 * jb + e];
-          __syncwarp();
-          for (int ib = jb + 1; ib < NBR; ib++) {
-            double c0 = 0.0, c1 = 0.0;
-            for (int kb = jb; kb < ib; kb++) {
-              const double *pa = Rh + (8 * ib + g) * LDR + 8 * kb + t; // L_ik [g][t]
-              const double *pb = Rh + (8 * kb + t) * LDR + 8 * jb + g; // X_kj [t][g]
-              dmma_8x8x4(c0, c1, pa[0], pb[0]);
-              dmma_8x8x4(c0, c1, pa[4], pb[4 * LDR]);
-            }
-            double *tt = wtmp;
-            *reinterpret_cast<double2 *>(tt + g * 8 + 2 * t) = make_double2(c0, c1);
-            __syncwarp();
-            const double *Di = dinv + 64 * ib;
-            double d0 = 0.0, d1 = 0.0;
-            dmma_8x8x4(d0, d1, Di[g * 8 + t], tt[t * 8 + g]);
-            dmma_8x8x4(d0, d1, Di[g * 8 + 4 + t], tt[(4 + t) * 8 + g]);
-            *reinterpret_cast<double2 *>(Rh + (8 * ib + g) * LDR + 8 * jb + 2 * t) = make_double2(-d0, -d1);
-            __syncwarp();
-          }
-        }
-      }
-      SYNC();
-      for (int ct = warp; ct < ldz / 8; ct += nwarps) {
-        double *zc = Z + 8 * ct;
-        for (int ib = NBR - 1; ib >= 0; ib--) { // Y_i = sum_{k <= i} X_ik Z_k
-          double c0 = 0.0, c1 = 0.0;
-          for (int kb = 0; kb <= ib; kb++) {
-            const double *pa = Rh + (8 * ib + g) * LDR + 8 * kb + t;
-            const double *pb = zc + (8 * kb + t) * ldz + g;
-            dmma_8x8x4(c0, c1, pa[0], pb[0]);
-            dmma_8x8x4(c0, c1, pa[4], pb[4 * ldz]);
-          }
-          __syncwarp();
-          *reinterpret_cast<double2 *>(zc + (8 * ib + g) * ldz + 2 * t) = make_double2(c0, c1);
-          __syncwarp();
-        }
-        for (int ib = 0; ib < NBR; ib++) { // Zsol_i = sum_{k >= i} X_ki' Y_k
-          double c0 = 0.0, c1 = 0.0;
-          for (int kb = ib; kb < NBR; kb++) {
-            const double *pa = Rh + (8 * kb + t) * LDR + 8 * ib + g; // (X_ki)'[g][t] = X_ki[t][g]
-            const double *pb = zc + (8 * kb + t) * ldz + g;
-            dmma_8x8x4(c0, c1, pa[0], pb[0]);
-            dmma_8x8x4(c0, c1, pa[4 * LDR], pb[4 * ldz]);
-          }
-          __syncwarp();
-          *reinterpret_cast<double2 *>(zc + (8 * ib + g) * ldz + 2 * t) = make_double2(c0, c1);
-          __syncwarp();
-        }
-      }
-      SYNC();
-    }
+    trsm_mma<MR / 8>(Rh, LDR, dinv, Z, ldz, ldz / 8, nullptr, 0, ldz / 8);
 #endif
     PHASE(8);
     PAR_FOR(e, nca * nca) {
