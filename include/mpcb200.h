@@ -77,6 +77,8 @@ typedef struct mpc_config {
   double tol, mu_init;
   int32_t max_iters;
   int32_t force_initial_condition;
+  int32_t rollout;              /* solver.rollout_type (full:381): 0 = ROLLOUT_LINEAR (every reference script), 1 = ROLLOUT_NONLINEAR */
+  int32_t pad_;
 } mpc_config_t;
 
 /* Per-knot parameter block (one per instance per knot). */

@@ -63,6 +63,8 @@ class Config(C.Structure):
         ("mu_init", d),
         ("max_iters", i32),
         ("force_initial_condition", i32),
+        ("rollout", i32),
+        ("pad_", i32),
     ]
 
 

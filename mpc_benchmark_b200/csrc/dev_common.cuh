@@ -31,6 +31,11 @@
 #define MBAR_EXPECT_TX(bar, bytes) ((void)0)
 #define MBAR_WAIT(bar, parity) ((void)0)
 #define FENCE_PROXY_ASYNC() ((void)0)
+#define PREFETCH_L2(ptr, bytes) ((void)0)
+#define LDCG(p) (*(p))
+#define LANE_ID 0
+#define LANE_IS(r) true
+#define PRELOADED(v, e) (e)
 #define BULK_G2S(dst, src, bytes, bar) do { for (size_t i_ = 0; i_ < (size_t)(bytes) / 8; i_++) (dst)[i_] = (src)[i_]; } while (0)
 struct double2 { double x, y; };
 inline double2 make_double2(double x, double y) { return double2{x, y}; }
@@ -75,6 +80,14 @@ inline double2 make_double2(double x, double y) { return double2{x, y}; }
                "r"((unsigned)(parity))                                                                                                   \
                : "memory")
 #define FENCE_PROXY_ASYNC() asm volatile("fence.proxy.async.shared::cta;" ::: "memory")
+// bulk prefetch of a contiguous global block into L2 (one instruction; address and size multiples of 16 bytes)
+#define PREFETCH_L2(ptr, bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"((unsigned)(bytes)) : "memory")
+#define LDCG(p) __ldcg(p)
+#define LANE_ID ((int)(threadIdx.x & 31))
+// "lane r finishes row r" after a butterfly reduction: values the finishing lane needs are loaded before the reduction
+// (PRELOADED: the early copy on the device; the host emulation has one "lane" that finishes every row and loads on the spot)
+#define LANE_IS(r) ((int)(threadIdx.x & 31) == (r))
+#define PRELOADED(v, e) (v)
 #endif
 
 namespace mpcdev {

@@ -10,6 +10,9 @@
 // Fragment layout (PTX ISA, m8n8k4 .f64): lane = 4*g + t;  a: A^T[row g][k t];  b: B[k t][col g];  c0,c1: C[row g][cols 2t, 2t+1].
 #pragma once
 #include "dev_common.cuh"
+#ifdef MPC_HOST_EMU
+#include <vector>
+#endif
 
 namespace mpcdev {
 
@@ -90,6 +93,179 @@ HD void mma_tn(int mt, int nt, int K, const double *A, int lda, const double *B,
           if (col + 1 < vcm) C[(col + 1) * ldc + row] = c[a][b][1];
         }
       }
+  }
+#endif
+  SYNC();
+}
+
+// Same contraction C = init + A^T B (K rows, compile-time) with one or both operands streamed from GLOBAL memory through L2
+// (AG / BG; ld.global.cg, no shared-memory staging): used for matrices that enter only one or two products per knot.  Columns
+// >= va of A / >= vb of B read as zero (row-major operands whose rows are shorter than the padded tile grid).  C may be null
+// (result only mirrored to Cg).  The k-loop is unrolled in halves so that K/2 rows of both operands are in flight per warp.
+template <int K, bool AG, bool BG>
+HD void mma_tn_g(int mt, int nt, const double *A, int lda, int va, const double *B, int ldb, int vb, double *C, int ldc, const double *Cinit, int ldci,
+                 int vr, int vc, bool upper_only, double *Cg, int ldcg, int vcg) {
+#ifdef MPC_HOST_EMU
+  for (int i = 0; i < 8 * mt; i++)
+    for (int j = 0; j < 8 * nt; j++) {
+      if (upper_only && (j / 16) < (i / 16)) continue;
+      double s = (Cinit && i < vr && j < vc) ? Cinit[i * ldci + j] : 0.0;
+      if (i < va && j < vb)
+        for (int k = 0; k < K; k++) s += A[k * lda + i] * B[k * ldb + j];
+      if (C) C[i * ldc + j] = s;
+      if (Cg && j < vcg) Cg[i * ldcg + j] = s;
+    }
+  if (upper_only && C)
+    for (int i = 0; i < 8 * mt; i++)
+      for (int j = 0; j < 8 * nt; j++)
+        if ((j / 16) < (i / 16) && i < (Cinit ? vc : 8 * nt)) C[i * ldc + j] = C[j * ldc + i];
+#else
+  static_assert(K % 8 == 0, "k-loop is unrolled in two halves of whole 4-row steps");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int mtp = (mt + 1) / 2, ntp = (nt + 1) / 2;
+  const int nwork = upper_only ? mtp * (mtp + 1) / 2 : mtp * ntp, vcm = Cinit ? vc : 8 * nt;
+  for (int p = warp; p < nwork; p += nwarps) {
+    int bi, bj;
+    if (upper_only) { bi = 0; int q = p; while (q >= mtp - bi) { q -= mtp - bi; bi++; } bj = bi + q; } else { bi = p / ntp; bj = p % ntp; }
+    const int ti = bi * 2, tj = bj * 2;
+    const bool r2 = (ti + 1 < mt), c2 = (tj + 1 < nt);
+    double c[2][2][2];
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+      for (int b = 0; b < 2; b++) {
+        c[a][b][0] = 0.0; c[a][b][1] = 0.0;
+        const int row = (ti + a) * 8 + g, col = (tj + b) * 8 + 2 * t;
+        if (Cinit && row < vr && (a == 0 || r2) && (b == 0 || c2)) {
+          if (col < vc) c[a][b][0] = Cinit[row * ldci + col];
+          if (col + 1 < vc) c[a][b][1] = Cinit[row * ldci + col + 1];
+        }
+      }
+    const int ao = r2 ? 8 : 0, bo = c2 ? 8 : 0; // out-of-range partner tiles recompute tile 0 (discarded)
+    const double *ap = A + t * lda + ti * 8 + g;
+    const double *bp = B + t * ldb + tj * 8 + g;
+    const bool am0 = ti * 8 + g < va, am1 = ti * 8 + ao + g < va, bm0 = tj * 8 + g < vb, bm1 = tj * 8 + bo + g < vb;
+    constexpr int KH = K / 2, NS = KH / 4;
+#pragma unroll 1
+    for (int kc = 0; kc < K; kc += KH) {
+      double a0[NS], a1[NS], b0[NS], b1[NS];
+#pragma unroll
+      for (int s = 0; s < NS; s++) {
+        const int k0 = kc + 4 * s;
+        if (AG) { a0[s] = am0 ? __ldcg(ap + k0 * lda) : 0.0; a1[s] = am1 ? __ldcg(ap + k0 * lda + ao) : 0.0; }
+        else { a0[s] = ap[k0 * lda]; a1[s] = ap[k0 * lda + ao]; }
+        if (BG) { b0[s] = bm0 ? __ldcg(bp + k0 * ldb) : 0.0; b1[s] = bm1 ? __ldcg(bp + k0 * ldb + bo) : 0.0; }
+        else { b0[s] = bp[k0 * ldb]; b1[s] = bp[k0 * ldb + bo]; }
+      }
+#pragma unroll
+      for (int s = 0; s < NS; s++) {
+        dmma_8x8x4(c[0][0][0], c[0][0][1], a0[s], b0[s]);
+        dmma_8x8x4(c[0][1][0], c[0][1][1], a0[s], b1[s]);
+        dmma_8x8x4(c[1][0][0], c[1][0][1], a1[s], b0[s]);
+        dmma_8x8x4(c[1][1][0], c[1][1][1], a1[s], b1[s]);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+      for (int b = 0; b < 2; b++) {
+        if ((a == 1 && !r2) || (b == 1 && !c2)) continue;
+        const int row = (ti + a) * 8 + g, col = (tj + b) * 8 + 2 * t;
+        if (C) *reinterpret_cast<double2 *>(C + row * ldc + col) = make_double2(c[a][b][0], c[a][b][1]);
+        if (Cg && col < vcg) *reinterpret_cast<double2 *>(Cg + row * ldcg + col) = make_double2(c[a][b][0], c[a][b][1]); // vcg, ldcg even
+        if (upper_only && bi < bj && C) { // mirror (never a tile anyone reads as Cinit); columns >= vcm are scratch and stay out of the rows below
+          if (col < vcm) C[col * ldc + row] = c[a][b][0];
+          if (col + 1 < vcm) C[(col + 1) * ldc + row] = c[a][b][1];
+        }
+      }
+  }
+#endif
+  SYNC();
+}
+
+// Symmetric update C = Cinit + A^T B (C: 8 nt x 8 nt, result symmetric) whose OUTPUT BUFFER ALIASES THE A OPERAND: every warp keeps
+// the accumulators of all its 16 x 16 blocks (upper block triangle, at most MAXQ per warp) in registers, the CTA synchronises once
+// all operand reads are done, and only then the blocks and their mirrors are stored.  A: shared memory [K][lda]; B: global memory
+// [K][ldb] read through L2; Cinit: global, rows < vr / columns < vc (zero outside).  Mirrored entries whose source column is >= vc
+// are written as zero (those columns are scratch: they must not reach the rows below).
+template <int K, int MAXQ>
+HD void mma_sym_deferred(int nt, const double *A, int lda, const double *B, int ldb, double *C, int ldc, const double *Cinit, int ldci, int vr, int vc) {
+#ifdef MPC_HOST_EMU
+  std::vector<double> out((size_t)64 * nt * nt);
+  for (int i = 0; i < 8 * nt; i++)
+    for (int j = 0; j < 8 * nt; j++) {
+      if ((j / 16) < (i / 16)) continue;
+      double s = (i < vr && j < vc) ? Cinit[i * ldci + j] : 0.0;
+      for (int k = 0; k < K; k++) s += A[k * lda + i] * B[k * ldb + j];
+      out[(size_t)i * 8 * nt + j] = s;
+    }
+  for (int i = 0; i < 8 * nt; i++)
+    for (int j = 0; j < 8 * nt; j++) C[i * ldc + j] = ((j / 16) < (i / 16)) ? ((i < vc) ? out[(size_t)j * 8 * nt + i] : 0.0) : out[(size_t)i * 8 * nt + j];
+#else
+  static_assert(K % 4 == 0, "whole 4-row steps");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int ntp = (nt + 1) / 2, nwork = ntp * (ntp + 1) / 2;
+  double c[MAXQ][2][2][2];
+#pragma unroll
+  for (int q_ = 0; q_ < MAXQ; q_++) {
+    const int p = warp + q_ * nwarps;
+    if (p < nwork) {
+      int bi = 0, q = p;
+      while (q >= ntp - bi) { q -= ntp - bi; bi++; }
+      const int bj = bi + q, ti = bi * 2, tj = bj * 2;
+      const bool r2 = (ti + 1 < nt), c2 = (tj + 1 < nt);
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+          c[q_][a][b][0] = 0.0; c[q_][a][b][1] = 0.0;
+          const int row = (ti + a) * 8 + g, col = (tj + b) * 8 + 2 * t;
+          if (row < vr && (a == 0 || r2) && (b == 0 || c2)) {
+            if (col + 1 < vc) { const double2 v = __ldcg(reinterpret_cast<const double2 *>(Cinit + row * ldci + col)); c[q_][a][b][0] = v.x; c[q_][a][b][1] = v.y; }
+            else if (col < vc) c[q_][a][b][0] = __ldcg(Cinit + row * ldci + col);
+          }
+        }
+      const int ao = r2 ? 8 : 0, bo = c2 ? 8 : 0;
+      const double *ap = A + t * lda + ti * 8 + g;
+      const double *bp = B + t * ldb + tj * 8 + g;
+      constexpr int NS = K / 4;
+      double b0[NS], b1[NS];
+#pragma unroll
+      for (int s = 0; s < NS; s++) { b0[s] = __ldcg(bp + 4 * s * ldb); b1[s] = __ldcg(bp + 4 * s * ldb + bo); }
+#pragma unroll
+      for (int s = 0; s < NS; s++) {
+        const double a0 = ap[4 * s * lda], a1 = ap[4 * s * lda + ao];
+        dmma_8x8x4(c[q_][0][0][0], c[q_][0][0][1], a0, b0[s]);
+        dmma_8x8x4(c[q_][0][1][0], c[q_][0][1][1], a0, b1[s]);
+        dmma_8x8x4(c[q_][1][0][0], c[q_][1][0][1], a1, b0[s]);
+        dmma_8x8x4(c[q_][1][1][0], c[q_][1][1][1], a1, b1[s]);
+      }
+    }
+  }
+  SYNC(); // every read of A (and of anything else the output buffer aliases) is complete
+#pragma unroll
+  for (int q_ = 0; q_ < MAXQ; q_++) {
+    const int p = warp + q_ * nwarps;
+    if (p < nwork) {
+      int bi = 0, q = p;
+      while (q >= ntp - bi) { q -= ntp - bi; bi++; }
+      const int bj = bi + q, ti = bi * 2, tj = bj * 2;
+      const bool r2 = (ti + 1 < nt), c2 = (tj + 1 < nt);
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+          if ((a == 1 && !r2) || (b == 1 && !c2)) continue;
+          const int row = (ti + a) * 8 + g, col = (tj + b) * 8 + 2 * t;
+          *reinterpret_cast<double2 *>(C + row * ldc + col) = make_double2(c[q_][a][b][0], c[q_][a][b][1]);
+          if (bi < bj) {
+            C[col * ldc + row] = (col < vc) ? c[q_][a][b][0] : 0.0;
+            C[(col + 1) * ldc + row] = (col + 1 < vc) ? c[q_][a][b][1] : 0.0;
+          }
+        }
+    }
   }
 #endif
   SYNC();

@@ -64,12 +64,13 @@ struct RiccatiIO {
   const double *vplus, *v;   // [T+1][NC]
   const double *lplus, *lam; // [T+1][N]  (index k+1 belongs to dynamics k)
   // outputs
-  double *W, *pt;        // [T][N][NZ], [T][N]
+  double *W, *pt;        // [T][N][NZ] (fast kernels: [T][N][round8(NZ)], column NZ = pt), [T][N]
   double *K;             // [T][M+NC][1+N]   rows 0..M-1: [ku|Ku]; then compact active [kv|Kv]
   double *Kfb;           // [T][M][N]        controlFeedbacks()
   double *dxs, *dus, *dvs, *dlams; // [T+1][N], [T][M], [T+1][NC], [T+1][N]
   double *dphi;          // scalar
   int32_t *overflow;     // set to 1 when a knot has more active rows than the kernel's shared-memory capacity
+  double *scratch;       // per-instance global block for the KKT buffers of knots whose active rows exceed the shared-memory carving
   double *phase_out;     // optional 16 per-phase cycle counters (MPC_PHASE_TIMING builds), else nullptr
 };
 

@@ -6,9 +6,10 @@
 // explicit inverse of its Cholesky factor built by independent per-warp column chains (no block barriers).
 // Leading dimensions are padded to 8 (mod 16) doubles so the DMMA fragment loads are bank-conflict free.
 // Around them: both Cholesky factorisations (Lambda, padded control block) are tensor-core blocked with a one-panel
-// look-ahead (chol_mma), the control-block solve uses an in-place inverse of its factor and tile-wise triangular products,
-// the value update is a DMMA product, and all operands arrive by cp.async.bulk copies tracked by mbarriers one knot ahead
-// (backward pass: [A B], T6, fbar, H_k; forward sweep: W, [A B], gain rows, small vectors, double-buffered).
+// look-ahead (chol_mma) and followed by in-place blocked substitutions (trsm_mma), the value update is a DMMA product.
+// Shared memory holds only what is reused many times per knot (H, P, the factor): [A B] and W are used twice each and are
+// streamed as DMMA operands straight from L2 (bulk-prefetched one knot ahead), which is what lets TWO instances share an SM
+// (full dynamics: 107 KB per CTA) so that one instance's serial pivot chains hide behind the other's products.
 #pragma once
 #include "dmma.cuh"
 #include "riccati.cuh"
@@ -31,48 +32,47 @@ template <int N, int M, int NC, int NCAP = NC> struct RicFastLayout {
   static constexpr int NBLK = N / 8;
   static constexpr int ZP = (NZ + 7) / 8 * 8;                       // padded n+m
   static constexpr int LDN = (N % 16 == 8) ? N : N + 8;             // ld of N x N buffers
-  static constexpr int LDZ = (ZP % 16 == 8) ? ZP : ZP + 8;          // ld of N x ZP buffers (AB, W)
   static constexpr int LDH = ZP;                                    // ld of the Hessian buffer
-  static_assert(N * LDZ <= 2 * N * LDN - 8 * N, "W must fit behind P, next to the [pv | 0] tile");
-  static_assert(ZP > NZ, "the Hessian update needs a spare padding column for pt");
-  static constexpr int phase1 = 3 * N * LDN + N * LDZ;  // P, G + scratch (later reused as W), AB
+  static constexpr int LDW = ZP;                                    // ld of W in HBM: column NZ carries pt, the rest of the padding is zero
+  static constexpr int LDZ = (ZP % 16 == 8) ? ZP : ZP + 8;          // ld of [A B] staged in shared memory (over the idle H buffer)
+  static_assert(N * LDZ <= ZP * LDH, "[A B] must fit into the H buffer");
+  static constexpr int NQ_SYM = ((ZP / 8 + 1) / 2) * ((ZP / 8 + 1) / 2 + 1) / 2; // 16 x 16 blocks of the upper block triangle of H
+  static constexpr int MAXQ = (NQ_SYM + 3) / 4;                    // per warp, for CTAs of at least 4 warps
   static constexpr int MR = (M + 7) / 8 * 8;                        // control block padded to whole 8 x 8 tiles (identity / zero padding)
   static constexpr int LDR = (MR % 16 == 8) ? MR : MR + 8;          // ld of the padded R^ buffer
-  static constexpr int LDZMAX = (NR + NCAP + 7) / 8 * 8;            // ld of Z for NCAP active rows (runtime ld: round8(NR + nca))
-  static constexpr int phase2 = NCAP * NZ + NCAP * NCAP + MR * LDZMAX + NCAP * NR + MR * LDR; // sized for NCAP active rows
-  static constexpr int un = phase1 > phase2 ? phase1 : phase2;
-  // phase-2 order [Z | Kv | Rh | CD | Sg]; [A B] sits at the END of the union so that knots with few active rows never
-  // touch it in phase 2 and the next knot's [A B] can be prefetched early
-  static constexpr int offKv = MR * LDZMAX, offRh = offKv + NCAP * NR, offCD = offRh + MR * LDR, offSg = offCD + NCAP * NZ;
-  static constexpr int offAB = un - N * LDZ;
-  static_assert(offAB >= 3 * N * LDN, "[A B] overlaps P / G / Li");
-  // knots with MORE than NCAP active rows (possible only when NCAP < NC: a kinodynamic iterate with nearly every cone / box row
-  // violated) use a second carving sized for NC rows in which the compacted rows [C D] stay in global memory: [Z | Kv | Rh | Sg]
-  static constexpr int LDZBIG = (NR + NC + 7) / 8 * 8;
-  static constexpr int offKvB = MR * LDZBIG, offRhB = offKvB + NC * NR, offSgB = offRhB + MR * LDR;
-  static_assert(offSgB + NC * NC <= un, "overflow carving of the KKT buffers does not fit");
-  static_assert(un % 2 == 0 && offAB % 2 == 0 && (ZP * LDH) % 2 == 0, "16-byte alignment of the bulk-copy destinations");
-  static constexpr int vecs = 8 * ZP + 36 + 2 * NC + 64 * ((NC + 7) / 8) + 8 * 64 + 16; // the final reduction reuses wtmp
+  // phase-2 (KKT) buffers [Z | Kv | Rh | CD | Sg] are carved per knot for the knot's number of active rows
+  static constexpr int even(int v) { return (v + 1) & ~1; }
+  static constexpr int ldz_of(int nca) { return (NR + nca + 7) & ~7; }
+  static constexpr int need2(int nca) { return MR * ldz_of(nca) + even(nca * NR) + MR * LDR + even(nca * NZ) + even(nca * nca); }
+  // they alias P | G (dead by then) while the knot has at most NCAP active rows; knots with more run phase 2 out of a
+  // per-instance scratch block in global memory (rare: iterates with most cone / box rows violated)
+  static constexpr int un = (2 * N * LDN > need2(NCAP)) ? 2 * N * LDN : need2(NCAP);
+  static constexpr int need2_all = need2(NC);
+  static constexpr int scratch = need2_all + 64 * ((NC + 7) / 8);   // doubles per instance
+  static constexpr int NDINV = (NBLK > MR / 8 ? NBLK : MR / 8) > (NCAP + 7) / 8 ? (NBLK > MR / 8 ? NBLK : MR / 8) : (NCAP + 7) / 8;
+  static_assert(need2(NCAP) <= un && NCAP <= NC, "fast carving");
+  static_assert(un % 2 == 0 && (ZP * LDH) % 2 == 0 && ZP > NZ, "16-byte alignment of the bulk-copy destinations; spare padding column for pt");
+  static constexpr int vecs = 6 * N + 2 * ZP + 36 + 2 * NC + 64 * NDINV + 8 * N + 32 + 16; // vectors, T6, dbr / dva, dinv, [pv | 0] tile, one reduction slot per warp, 8 mbarriers
   static constexpr int total = ZP * LDH + un + vecs;
 };
 
 template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(const RiccatiIO &io, double *ws) {
   using Lay = RicFastLayout<N, M, NC, NCAP>;
-  constexpr int NZ = Lay::NZ, NR = Lay::NR, S = Lay::S, ZP = Lay::ZP, LDN = Lay::LDN, LDZ = Lay::LDZ, LDH = Lay::LDH, NBLK = Lay::NBLK, MR = Lay::MR, LDR = Lay::LDR;
+  constexpr int NZ = Lay::NZ, NR = Lay::NR, S = Lay::S, ZP = Lay::ZP, LDN = Lay::LDN, LDH = Lay::LDH, LDW = Lay::LDW, LDZ = Lay::LDZ, NBLK = Lay::NBLK, MR = Lay::MR, LDR = Lay::LDR;
   static_assert(N % 8 == 0, "fast Riccati needs n % 8 == 0");
   const int T = io.T;
   const double mu = io.mu, mu_d = io.mu_d;
   PHASE_DECL;
   // ---- carve shared memory
   double *H = ws;                              // ZP x LDH, zero padded; [0:N,0:N] carries the value-function Hessian between knots
+  double *ABs = H;                             // ... and [A B]_k (N x LDZ) between the moment that Hessian is taken out and the Hessian update
   double *U0 = H + ZP * LDH;
-  double *P = U0, *G = P + N * LDN, *AB = U0 + Lay::offAB, *W = G, *PV = G + 2 * N * LDN - 8 * N;  // phase 1 (W overwrites the dead factor G; PV: [pv | 0] tile)
-  double *Z = U0, *CDs = U0 + Lay::offCD;  // phase 2 (Kv, Rh, Sg: carved per knot, see `big`)
+  double *P = U0, *G = P + N * LDN;            // phase 1
   double *vec = U0 + Lay::un;
-  double *p = vec, *pt = p + ZP, *gh = pt + ZP, *fb = gh + ZP, *tmp = fb + ZP, *dx = tmp + ZP, *z = dx + ZP, *pv = z + ZP;
-  double *T6 = pv + ZP, *dbr = T6 + 36, *dva = dbr + NC, *dinv = dva + NC, *wtmp = dinv + 64 * ((NC + 7) / 8), *red = wtmp;  // (red: one slot per thread, <= 512 threads)
-  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(vec + Lay::vecs - 8); // four mbarriers in the spare tail of vecs
-  ONE_THREAD { MBAR_INIT(mbar, 1); MBAR_INIT(mbar + 1, 1); MBAR_INIT(mbar + 2, 1); MBAR_INIT(mbar + 3, 1); }
+  double *p = vec, *pt = p + N, *gh = pt + N, *fb = gh + ZP, *tmp = fb + N, *dx = tmp + N, *z = dx + N, *pv = z + ZP; // gh, z: n + m entries, the others n
+  double *T6 = pv + N, *dbr = T6 + 36, *dva = dbr + NC, *dinv_s = dva + NC, *PV = dinv_s + 64 * Lay::NDINV, *red = PV + 8 * N; // (red: one slot per warp)
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(vec + Lay::vecs - 8); // mbarriers in the spare tail of vecs
+  ONE_THREAD { for (int i_ = 0; i_ < 7; i_++) MBAR_INIT(mbar + i_, 1); } // 2: T6 / fbar, 3: [A B]; forward sweep: 4, 5: gain rows + vectors, 6: W + [A B]
   // ---- zero the padding of H once; terminal value function: P = H_T[xx] + C'C/mu, p = g_T[x] + C' d/mu
   PAR_FOR(e, ZP * LDH) H[e] = 0.0;
   SYNC();
@@ -94,43 +94,55 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
     }
     SYNC();
   }
-  // [A B] of a knot goes global -> shared by bulk copies (cp.async.bulk, one 624-byte row per issuing thread into the padded
-  // rows; completion counted on an mbarrier), issued one knot ahead so that the copy overlaps the tail of the previous knot;
-  // the padding columns NZ..ZP-1 are zeroed with plain stores.  mbar[0..1]: forward-sweep stages, [2]: [A B] + T6 + fbar, [3]: H_k
-  static_assert((NZ * 8) % 16 == 0 && (LDZ * 8) % 16 == 0 && (LDH * 8) % 16 == 0 && (N * 8) % 16 == 0, "bulk copies need 16-byte rows");
-  auto stage_AB_async = [&](int kk) {
-    const double *src = io.AB + (size_t)kk * N * NZ;
+  // T6 and fbar of a knot arrive by bulk copies one knot ahead (mbar[2]); [A B]_k streams into the H buffer once the value Hessian
+  // has been taken out of it (mbar[3]); [A B]_k and H_k are bulk-prefetched into L2 one knot ahead (H_k is read from there as
+  // the initial value of the Hessian update's accumulators).
+  static_assert((NZ * 8) % 16 == 0 && (LDH * 8) % 16 == 0 && (LDZ * 8) % 16 == 0 && (N * 8) % 16 == 0 && (N * NZ * 8) % 16 == 0 && (NZ * NZ * 8) % 16 == 0, "bulk copies need 16-byte rows");
+  auto stage_small = [&](int kk) {
     ONE_THREAD {
       FENCE_PROXY_ASYNC();
-      MBAR_EXPECT_TX(mbar + 2, (N * NZ + 36 + N) * 8);
+      MBAR_EXPECT_TX(mbar + 2, (36 + N) * 8);
       BULK_G2S(T6, io.T6 + (size_t)kk * 36, 36 * 8, mbar + 2);
       BULK_G2S(fb, io.fbar + (size_t)kk * N, N * 8, mbar + 2);
     }
-    PAR_FOR(i, N) { FENCE_PROXY_ASYNC(); BULK_G2S(AB + i * LDZ, src + i * NZ, NZ * 8, mbar + 2); }
-    PAR_FOR(e, N * (ZP - NZ)) { int i = e / (ZP - NZ), j = NZ + e % (ZP - NZ); AB[i * LDZ + j] = 0.0; }
   };
-  if (T > 0) stage_AB_async(T - 1);
+  auto prefetch_knot = [&](int kk) {
+    ONE_THREAD { PREFETCH_L2(io.AB + (size_t)kk * N * NZ, N * NZ * 8); PREFETCH_L2(io.H + (size_t)kk * NZ * NZ, NZ * NZ * 8); }
+  };
+  if (T > 0) { stage_small(T - 1); prefetch_knot(T - 1); }
   for (int k = T - 1; k >= 0; k--) {
-    const double *gH = io.H + (size_t)k * NZ * NZ;
+    const double *gH = io.H + (size_t)k * NZ * NZ, *gAB = io.AB + (size_t)k * N * NZ;
+    double *gW = io.W + (size_t)k * N * LDW;
     const int nca = io.nca[k];
-    const bool big = (NCAP < NC) && nca > NCAP; // more active rows than the fast carving holds: [C D] is read from global memory
+    if (k > 0) prefetch_knot(k - 1);
     // 1. ONE pass over the value Hessian left in H by the previous knot: P <- T' sym(H) T (E normalisation: T = blockdiag(T6, I)
     //    touches the 6 base rows / columns only), G <- I + mu_d P, and the normalised gradient tmp <- T' p
-    MBAR_WAIT(mbar + 2, (T - 1 - k) & 1); // [A B], T6 and fbar of this knot (issued one knot ahead)
+    MBAR_WAIT(mbar + 2, (T - 1 - k) & 1); // T6 and fbar of this knot (issued one knot ahead)
     PHASE(21);
-    PAR_FOR(e, N * N) { // lanes: 8 consecutive j x 4 consecutive i, which keeps the transposed read at 8-way bank conflicts
+    PAR_FOR(e, N * N) { // rows / columns >= 6: plain symmetrisation.  lanes: 8 consecutive j x 4 consecutive i (transposed read: 8-way conflicts)
       const int blk = e >> 5, l = e & 31, i = (blk / (N / 8)) * 4 + (l >> 3), j = (blk % (N / 8)) * 8 + (l & 7);
-      double v;
-      if (i >= 6 && j >= 6) v = 0.5 * (H[i * LDH + j] + H[j * LDH + i]);
-      else if (i >= 6) { v = 0; for (int q = 0; q < 6; q++) v += 0.5 * (H[i * LDH + q] + H[q * LDH + i]) * T6[6 * q + j]; }
-      else if (j >= 6) { v = 0; for (int q = 0; q < 6; q++) v += T6[6 * q + i] * (0.5 * (H[q * LDH + j] + H[j * LDH + q])); }
-      else {
-        v = 0;
+      if (i < 6 || j < 6) continue;
+      const double v = 0.5 * (H[i * LDH + j] + H[j * LDH + i]);
+      P[i * LDN + j] = v;
+      G[i * LDN + j] = mu_d * v + ((i == j) ? 1.0 : 0.0);
+    }
+    // the 6 base rows / columns, enumerated compactly so that no warp diverges over them: corner (36 terms), top edge, left edge
+    PAR_FOR(s_, 36 + 12 * (N - 6)) {
+      int i, j;
+      double v = 0;
+      if (s_ < 36) {
+        i = s_ / 6; j = s_ % 6;
         for (int q = 0; q < 6; q++) {
           double r = 0;
           for (int m = 0; m < 6; m++) r += 0.5 * (H[q * LDH + m] + H[m * LDH + q]) * T6[6 * m + j];
           v += T6[6 * q + i] * r;
         }
+      } else if (s_ < 36 + 6 * (N - 6)) {
+        i = (s_ - 36) / (N - 6); j = 6 + (s_ - 36) % (N - 6);
+        for (int q = 0; q < 6; q++) v += T6[6 * q + i] * (0.5 * (H[q * LDH + j] + H[j * LDH + q]));
+      } else {
+        j = (s_ - 36 - 6 * (N - 6)) / (N - 6); i = 6 + (s_ - 36 - 6 * (N - 6)) % (N - 6);
+        for (int q = 0; q < 6; q++) v += 0.5 * (H[i * LDH + q] + H[q * LDH + i]) * T6[6 * q + j];
       }
       P[i * LDN + j] = v;
       G[i * LDN + j] = mu_d * v + ((i == j) ? 1.0 : 0.0);
@@ -139,42 +151,47 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
     PAR_FOR(e, N * 8) PV[e] = 0.0;
     SYNC();
     PHASE(16);
-    // H is dead now: H <- H_k asynchronously (lands before the Hessian update needs it);  pv = p + P f
-    ONE_THREAD MBAR_EXPECT_TX(mbar + 3, NZ * NZ * 8);
-    PAR_FOR(i, NZ) { FENCE_PROXY_ASYNC(); BULK_G2S(H + i * LDH, gH + i * NZ, NZ * 8, mbar + 3); }
+    // the H buffer is idle until the Hessian update: [A B]_k streams into it (one padded row per bulk copy);  pv = p + P f
+    ONE_THREAD MBAR_EXPECT_TX(mbar + 3, N * NZ * 8);
+    PAR_FOR(i, N) { FENCE_PROXY_ASYNC(); BULK_G2S(ABs + i * LDZ, gAB + i * NZ, NZ * 8, mbar + 3); }
+    PAR_FOR(e, N * (LDZ - NZ)) { const int i = e / (LDZ - NZ), j = NZ + e % (LDZ - NZ); ABs[i * LDZ + j] = 0.0; }
     matvec_rows(P, LDN, N, N, fb, tmp, pv);
     SYNC();
     PAR_FOR(i, N) PV[8 * i] = pv[i];
+    if (k > 0) stage_small(k - 1); // T6 and fbar of this knot are consumed
     PHASE(1);
     // 2. G = chol(I + mu_d P)
-    chol_mma<NBLK>(G, LDN, dinv);
+    chol_mma<NBLK>(G, LDN, dinv_s);
     PHASE(2);
     // 3. [P | pv] <- Lambda^-1 [P | pv] in place: blocked forward / backward substitution, one warp per 8-column tile
-    trsm_mma<NBLK>(G, LDN, dinv, P, LDN, NBLK, PV, 8, NBLK + 1);
+    trsm_mma<NBLK>(G, LDN, dinv_s, P, LDN, NBLK, PV, 8, NBLK + 1);
     PHASE(4);
-    // 4. W = Pt [A B] (into shared memory over the dead factor AND to HBM for the forward sweep, straight from the accumulators)
-    mma_tn(NBLK, ZP / 8, N, P, LDN, AB, LDZ, W, LDZ, nullptr, 0, 0, 0, false, false, io.W + (size_t)k * N * NZ, NZ, NZ);
+    // 4. W = Pt [A B]: the result goes straight from the accumulators to HBM (the forward sweep and the Hessian update read it
+    //    from there); pt rides in the first padding column of W, so [A B]' pt falls out of the Hessian update
+    MBAR_WAIT(mbar + 3, (T - 1 - k) & 1); // [A B]_k
+    mma_tn_g<N, false, false>(NBLK, ZP / 8, P, LDN, N, ABs, LDZ, ZP, nullptr, 0, nullptr, 0, 0, 0, false, gW, LDW, ZP);
     PHASE(17);
-    // pt rides in the first padding column of W, so [A B]' pt falls out of the Hessian update (column NZ of H)
-    PAR_FOR(i, N) { const double v = PV[8 * i]; pt[i] = v; W[i * LDZ + NZ] = v; io.pt[(size_t)k * N + i] = v; }
-    MBAR_WAIT(mbar + 3, (T - 1 - k) & 1); // H_k
+    PAR_FOR(i, N) { const double v = PV[8 * i]; pt[i] = v; gW[i * LDW + NZ] = v; io.pt[(size_t)k * N + i] = v; }
     SYNC();
-    // 5. H = H_k + [A B]' W in place (rows / columns >= NZ of H_k read as zero);  gh = g + [A B]' pt
-    mma_tn(ZP / 8, ZP / 8, N, AB, LDZ, W, LDZ, H, LDH, H, LDH, ZP, NZ, true); // symmetric: upper blocks computed, lower mirrored
+    // 5. H = H_k + [A B]' W (symmetric: upper blocks computed, lower mirrored; H_k from L2, columns >= NZ read as zero).  The
+    //    result overwrites the buffer [A B] sits in: accumulators stay in registers until every warp is done reading it.
+    //    gh = g + [A B]' pt
+    mma_sym_deferred<N, Lay::MAXQ>(ZP / 8, ABs, LDZ, gW, LDW, H, LDH, gH, NZ, NZ, NZ);
     PHASE(18);
     PAR_FOR(i, NZ) gh[i] = io.g[(size_t)k * NZ + i] + H[i * LDH + NZ];
     SYNC();
-    // [A B]_k is dead: when the active rows of this knot keep phase 2 clear of the buffer, fetch the next knot's now
-    const bool early = !big && ((nca == 0) ? Lay::offCD : ((Lay::offCD + nca * NZ > Lay::offSg + nca * nca) ? Lay::offCD + nca * NZ : Lay::offSg + nca * nca)) <= Lay::offAB;
-    if (k > 0 && early) stage_AB_async(k - 1);
     PHASE(5);
-    // 8. KKT by block elimination (phase-2 buffers alias P/G/Li/AB/W, all dead now)
-    const int ncol = NR + nca, ldz = (ncol + 7) & ~7; // Z columns: [rh | Sh' | D'], padded with zero columns to whole tiles
+    // 8. KKT by block elimination.  Buffers [Z | Kv | Rh | CD | Sg] carved for this knot's active rows: over P | G (dead now), or
+    //    in the instance's global scratch block when they do not fit
+    const int ncol = NR + nca, ldz = (NR + nca + 7) & ~7; // Z columns: [rh | Sh' | D'], padded with zero columns to whole tiles
+    const bool fits = nca <= NCAP;
+    double *X2 = fits ? U0 : io.scratch;
+    double *Z = X2, *Kv = Z + MR * ldz, *Rh = Kv + ((nca * NR + 1) & ~1), *CDs = Rh + MR * LDR, *Sg = CDs + ((nca * NZ + 1) & ~1); // = Lay::need2's carving
+    double *dinv = fits ? dinv_s : io.scratch + Lay::need2_all;
     const double *gCD = io.CDact + (size_t)k * NC * NZ;
     const int32_t *ai = io.act_idx + (size_t)k * NC;
-    double *Kv = big ? U0 + Lay::offKvB : U0 + Lay::offKv, *Rh = big ? U0 + Lay::offRhB : U0 + Lay::offRh, *Sg = big ? U0 + Lay::offSgB : U0 + Lay::offSg;
-    const double *CD = big ? gCD : CDs;
-    if (!big) PAR_FOR(e, nca * NZ) CDs[e] = gCD[e];
+    const double *CD = fits ? CDs : gCD;
+    if (fits) PAR_FOR(e, nca * NZ) CDs[e] = gCD[e];
     PAR_FOR(r, nca) dbr[r] = io.dbar[(size_t)k * NC + ai[r]];
     PAR_FOR(e, MR * MR) { // R^ = sym(H_uu), padded with the identity to MR x MR
       int i = e / MR, j = e % MR;
@@ -187,15 +204,10 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
     }
     SYNC();
     PHASE(6);
-#ifdef MPC_HOST_EMU
-    chol_blocked(Rh, MR, LDR, dinv);
-    trsm_blocked(Rh, MR, LDR, dinv, Z, ncol, ldz);
-#else
     // Z <- R^-1 Z on the tensor pipe: blocked Cholesky, then forward / backward substitution with one warp per 8-column tile of Z
     chol_mma<MR / 8>(Rh, LDR, dinv);
     PHASE(7);
     trsm_mma<MR / 8>(Rh, LDR, dinv, Z, ldz, ldz / 8, nullptr, 0, ldz / 8);
-#endif
     PHASE(8);
     PAR_FOR(e, nca * nca) {
       int r = e / nca, c = e % nca;
@@ -256,7 +268,6 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
       SYNC();
     }
     PHASE(19);
-    if (k > 0 && !early) stage_AB_async(k - 1); // the phase-2 buffers aliasing [A B] are dead now
     PHASE(12);
   }
   // ---- forward sweep, dx0 = 0 (force_initial_condition, fulldynamic_talos.py:384)
@@ -274,25 +285,42 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
     io.dvs[e] = db / mu;
     if (!active) acc -= db * db / mu;
   }
-  // W_k, [A B]_k, the small per-knot vectors and the first KROWS gain rows of each knot are staged global -> shared one knot
-  // ahead (bulk copies, two stages in the now dead H / phase buffers): the dependent chain dx_k -> du_k -> dx_{k+1} never waits on HBM
-  constexpr int FW = N * NZ;
-  constexpr int FX = 4 * N + NZ + 36; // pt_k, fbar_k, lplus_{k+1}, lam_{k+1}, lxu_k, T6_k
-  constexpr int KROWS = (((ZP * LDH + Lay::un - 4 * FW - 2 * FX) / 2) / NR) & ~1;
-  constexpr int FSTAGE = 2 * FW + FX + KROWS * NR;
-  static_assert(KROWS >= M && 2 * FSTAGE <= ZP * LDH + Lay::un && FSTAGE % 2 == 0, "forward staging does not fit");
-  // one thread arms the stage's mbarrier and issues nine bulk copies (cp.async.bulk: W, [A B], gain rows, six small vectors)
-  auto stage_fwd = [&](int kk) {
+  // W_k and [A B]_k (single stage), the first KROWS gain rows and the small per-knot vectors (two stages) go global -> shared by bulk
+  // copies into the now dead H / P / G buffers: W / [A B] of knot k + 1 are requested as soon as knot k's mat-vecs are done, gain rows
+  // and vectors two knots ahead; everything is bulk-prefetched from HBM into L2 PF knots ahead of the chain dx_k -> du_k -> dx_{k+1}
+  constexpr int PF = 3;
+  constexpr int FWA = N * LDW + N * NZ;    // W_k | [A B]_k
+  constexpr int FX = 4 * N + NZ + 36;      // pt_k, fbar_k, lplus_{k+1}, lam_{k+1}, lxu_k, T6_k
+  constexpr int KROWS = ((((ZP * LDH + Lay::un - FWA - 2 * FX) / 2) / NR) & ~1) < S ? ((((ZP * LDH + Lay::un - FWA - 2 * FX) / 2) / NR) & ~1) : (S & ~1);
+  constexpr int FKX = KROWS * NR + FX;
+  static_assert(KROWS >= M && FWA + 2 * FKX <= ZP * LDH + Lay::un && FWA % 2 == 0 && FKX % 2 == 0, "forward staging does not fit");
+  static_assert((N * LDW * 8) % 16 == 0 && (N * NZ * 8) % 16 == 0 && (S * NR * 8) % 16 == 0 && (2 * NR * 8) % 16 == 0 && (N * 8) % 16 == 0 && (NZ * 8) % 16 == 0,
+                "bulk copies need 16-byte sizes and offsets");
+  auto prefetch_fwd = [&](int kk) {
     ONE_THREAD {
-      double *bw = ws + (kk & 1) * FSTAGE, *ba = bw + FW, *bx = ba + FW, *bk = bx + FX;
-      unsigned long long *bar = mbar + (kk & 1);
+      const int rows = (M + io.nca[kk] + 1) & ~1;
+      PREFETCH_L2(io.W + (size_t)kk * N * LDW, N * LDW * 8);
+      PREFETCH_L2(io.AB + (size_t)kk * N * NZ, N * NZ * 8);
+      PREFETCH_L2(io.K + (size_t)kk * S * NR, rows * NR * 8);
+    }
+  };
+  auto stage_wa = [&](int kk) {
+    ONE_THREAD {
+      FENCE_PROXY_ASYNC(); // the buffer was last touched through the generic proxy
+      MBAR_EXPECT_TX(mbar + 6, FWA * 8);
+      BULK_G2S(ws, io.W + (size_t)kk * N * LDW, N * LDW * 8, mbar + 6);
+      BULK_G2S(ws + N * LDW, io.AB + (size_t)kk * N * NZ, N * NZ * 8, mbar + 6);
+    }
+  };
+  auto stage_kx = [&](int kk) {
+    ONE_THREAD {
+      double *bk = ws + FWA + (kk & 1) * FKX, *bx = bk + KROWS * NR;
+      unsigned long long *bar = mbar + 4 + (kk & 1);
       int rows = M + io.nca[kk];
       if (rows > KROWS) rows = KROWS;
       rows = (rows + 1) & ~1; // whole 16-byte units (an extra row stays inside this knot's gain block)
-      FENCE_PROXY_ASYNC();    // the buffer was last touched through the generic proxy
-      MBAR_EXPECT_TX(bar, (2 * FW + rows * NR + 4 * N + NZ + 36) * 8);
-      BULK_G2S(bw, io.W + (size_t)kk * FW, FW * 8, bar);
-      BULK_G2S(ba, io.AB + (size_t)kk * FW, FW * 8, bar);
+      FENCE_PROXY_ASYNC();
+      MBAR_EXPECT_TX(bar, (rows * NR + FX) * 8);
       BULK_G2S(bk, io.K + (size_t)kk * S * NR, rows * NR * 8, bar);
       BULK_G2S(bx, io.pt + (size_t)kk * N, N * 8, bar);
       BULK_G2S(bx + N, io.fbar + (size_t)kk * N, N * 8, bar);
@@ -302,16 +330,16 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
       BULK_G2S(bx + 4 * N + NZ, io.T6 + (size_t)kk * 36, 36 * 8, bar);
     }
   };
-  static_assert((FW * 8) % 16 == 0 && (N * 8) % 16 == 0 && (NZ * 8) % 16 == 0 && (FX * 8) % 16 == 0 && (2 * NR * 8) % 16 == 0 && (S * NR * 8) % 16 == 0,
-                "bulk copies need 16-byte sizes and offsets");
   SYNC();
-  if (T > 0) stage_fwd(0);
+  for (int kk = 0; kk < PF && kk < T; kk++) prefetch_fwd(kk);
+  if (T > 0) { stage_kx(0); stage_wa(0); }
+  if (T > 1) stage_kx(1);
   for (int k = 0; k < T; k++) {
     const int nca = io.nca[k];
-    if (k + 1 < T) stage_fwd(k + 1);
-    MBAR_WAIT(mbar + (k & 1), (k >> 1) & 1); // stage k has landed (each barrier is used every other knot)
-    const double *sW = ws + (k & 1) * FSTAGE, *sAB = sW + FW, *sX = sAB + FW, *sK = sX + FX;
+    if (k + PF < T) prefetch_fwd(k + PF);
+    const double *sW = ws, *sAB = ws + N * LDW, *sK = ws + FWA + (k & 1) * FKX, *sX = sK + KROWS * NR;
     const double *gK = io.K + (size_t)k * S * NR;
+    MBAR_WAIT(mbar + 4 + (k & 1), (k >> 1) & 1); // gain rows and vectors of knot k (each barrier is used every other knot)
     // du, dv of the active rows: RA rows per warp at a time (independent reduction chains), columns over lanes
     constexpr int RA = 3;
     for (int base = WARP_ID * RA; base < M + nca; base += NWARPS * RA) {
@@ -323,7 +351,7 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
 #pragma unroll
         for (int r = 0; r < RA; r++) {
           const int i = base + r;
-          if (i < M + nca) sa[r] += ((i < KROWS) ? sK[i * NR + 1 + j] : gK[i * NR + 1 + j]) * dj;
+          if (i < M + nca) sa[r] += ((i < KROWS) ? sK[i * NR + 1 + j] : LDCG(gK + i * NR + 1 + j)) * dj;
         }
       }
 #pragma unroll
@@ -333,7 +361,7 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
         for (int r = 0; r < RA; r++) {
           const int i = base + r;
           if (i >= M + nca) continue;
-          const double v = sa[r] + ((i < KROWS) ? sK[i * NR] : gK[i * NR]);
+          const double v = sa[r] + ((i < KROWS) ? sK[i * NR] : LDCG(gK + i * NR));
           if (i < M) { z[N + i] = v; io.dus[(size_t)k * M + i] = v; } else dva[i - M] = v;
         }
       }
@@ -350,6 +378,7 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
       }
     }
     PAR_FOR(i, NZ) acc += sX[4 * N + i] * z[i];
+    MBAR_WAIT(mbar + 6, k & 1); // W_k, [A B]_k
     // dlam_{k+1} = pt + W z ; tmp = A dx + B du + fbar - mu_d dlam : RB rows per warp at a time
     constexpr int RB = 7;
     for (int base = WARP_ID * RB; base < N; base += NWARPS * RB) {
@@ -360,7 +389,7 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
         const double zj = z[j];
 #pragma unroll
         for (int r = 0; r < RB; r++)
-          if (base + r < N) { sl[r] += sW[(base + r) * NZ + j] * zj; sa[r] += sAB[(base + r) * NZ + j] * zj; }
+          if (base + r < N) { sl[r] += sW[(base + r) * LDW + j] * zj; sa[r] += sAB[(base + r) * NZ + j] * zj; }
       }
 #pragma unroll
       for (int r = 0; r < RB; r++) { sl[r] = WARP_SUM(sl[r]); sa[r] = WARP_SUM(sa[r]); }
@@ -377,6 +406,7 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
       }
     }
     SYNC();
+    if (k + 1 < T) stage_wa(k + 1); // the W / [A B] stage is free
     PAR_FOR(i, N) {
       double v;
       if (i < 6) { v = 0; for (int l = 0; l < 6; l++) v += sX[4 * N + NZ + 6 * i + l] * tmp[l]; } else v = tmp[i];
@@ -384,6 +414,7 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
     }
     PHASE(20);
     SYNC();
+    if (k + 2 < T) stage_kx(k + 2); // this knot's gain / vector stage is free
   }
   { // terminal knot: dv of the active terminal rows and the terminal cost gradient
     const int nca = io.nca[T];
@@ -402,9 +433,10 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
   }
   PHASE(14);
   PHASE_DUMP(io.phase_out);
-  red[TID] = acc;
+  acc = WARP_SUM(acc);
+  if (LANE0) red[WARP_ID] = acc;
   SYNC();
-  ONE_THREAD { double s = 0; for (int t = 0; t < NTHREADS; t++) s += red[t]; io.dphi[0] = s; }
+  ONE_THREAD { double s = 0; for (int t = 0; t < NWARPS; t++) s += red[t]; io.dphi[0] = s; }
   SYNC();
 }
 

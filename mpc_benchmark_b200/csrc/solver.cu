@@ -139,7 +139,8 @@ struct mpc_solver {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   size_t eval_smem = 0, eval_smem_values = 0, ric_smem = 0;
-  int eval_threads = 128, ric_threads = 256;
+  int eval_threads = 128, ric_threads = 256, num_sms = 148;
+  bool ric_threads_auto = true;
   int last_launches = 0;
   float last_ms = 0;
   size_t bytes = 0;
@@ -179,7 +180,8 @@ struct CudaBackend {
   void decide_eval(const int32_t *list, int n, int32_t *next_eval) { mark(3); k_decide_eval<<<n, 128, 0, s>>>(h->w, list, next_eval); }
   void riccati(const int32_t *list, int n) {
     mark(1);
-    if (h->w.kind == MPC_KIND_FULL) k_riccati<MPC_KIND_FULL><<<n, h->ric_threads, h->ric_smem, s>>>(h->w, list);
+    // full dynamics: two 128-thread instances per SM when the launch fills the GPU; 256 threads per instance when SMs would idle (latency)
+    if (h->w.kind == MPC_KIND_FULL) k_riccati<MPC_KIND_FULL><<<n, (h->ric_threads_auto && n <= h->num_sms) ? 256 : h->ric_threads, h->ric_smem, s>>>(h->w, list);
     else if (h->w.kind == MPC_KIND_KINO) k_riccati<MPC_KIND_KINO><<<n, h->ric_threads, h->ric_smem, s>>>(h->w, list);
     else k_riccati<MPC_KIND_CENT><<<n, h->ric_threads, h->ric_smem, s>>>(h->w, list);
   }
@@ -194,18 +196,19 @@ struct CudaBackend {
 };
 
 static int set_kernel_attrs(mpc_solver *h) {
-  if (h->w.kind == MPC_KIND_FULL) { h->eval_smem = sizeof(FullWsT<true>); h->eval_smem_values = sizeof(FullWsT<false>); h->eval_threads = 128; h->ric_smem = RicFastLayout<56, 22, 78>::total * 8; h->ric_threads = 256; }
+  if (h->w.kind == MPC_KIND_FULL) { h->eval_smem = sizeof(FullWsT<true>); h->eval_smem_values = sizeof(FullWsT<false>); h->eval_threads = 128; h->ric_smem = RicFastLayout<56, 22, 78, FULL_NCAP>::total * 8; h->ric_threads = 128; } // two 128-thread instances per SM
   else if (h->w.kind == MPC_KIND_KINO) { h->eval_smem = sizeof(KinoWsT<true>); h->eval_smem_values = sizeof(KinoWsT<false>); h->eval_threads = 128;
     h->ric_smem = RicFastLayout<56, 34, 68, KINO_NCAP>::total * 8; h->ric_threads = 256; }
   else { h->eval_smem = h->eval_smem_values = sizeof(CentWs); h->eval_threads = 32; h->ric_smem = riccati_smem_doubles<9, 12, 34>() * 8; h->ric_threads = 128; }
-  if (const char *e = getenv("MPCB200_RIC_THREADS")) { int t = atoi(e); if (t >= 32 && t <= 256) h->ric_threads = t; }
-  static_assert(RicFastLayout<56, 22, 78>::total * 8 <= 232448 && RicFastLayout<56, 34, 68, KINO_NCAP>::total * 8 <= 232448,
+  if (const char *e = getenv("MPCB200_RIC_THREADS")) { int t = atoi(e); if (t >= 128 && t <= 256) { h->ric_threads = t; h->ric_threads_auto = false; } }
+  { int dev = 0, sms = 0; if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) h->num_sms = sms; }
+  static_assert(RicFastLayout<56, 22, 78, FULL_NCAP>::total * 8 <= 232448 && RicFastLayout<56, 34, 68, KINO_NCAP>::total * 8 <= 232448,
                 "Riccati shared memory exceeds the 227 KB opt-in limit");
 #define EVAL_ATTR(KIND, D) CK(cudaFuncSetAttribute(k_eval<KIND, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EvalShape<KIND, D>::G * EvalShape<KIND, D>::slice)))
   EVAL_ATTR(MPC_KIND_FULL, true); EVAL_ATTR(MPC_KIND_FULL, false); EVAL_ATTR(MPC_KIND_KINO, true); EVAL_ATTR(MPC_KIND_KINO, false);
   EVAL_ATTR(MPC_KIND_CENT, true); EVAL_ATTR(MPC_KIND_CENT, false);
 #undef EVAL_ATTR
-  CK(cudaFuncSetAttribute(k_riccati<MPC_KIND_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, RicFastLayout<56, 22, 78>::total * 8));
+  CK(cudaFuncSetAttribute(k_riccati<MPC_KIND_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, RicFastLayout<56, 22, 78, FULL_NCAP>::total * 8));
   CK(cudaFuncSetAttribute(k_riccati<MPC_KIND_KINO>, cudaFuncAttributeMaxDynamicSharedMemorySize, RicFastLayout<56, 34, 68, KINO_NCAP>::total * 8));
   return 0;
 }

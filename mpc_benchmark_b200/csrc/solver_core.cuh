@@ -16,7 +16,8 @@
 namespace mpcdev {
 
 enum { MODE_EVAL = 0, MODE_STEP = 1, MODE_LS = 2, MODE_DONE = 3 };
-constexpr int KINO_NCAP = 56; // active rows of the kinodynamic Riccati's fast shared-memory carving; knots with more (up to all 68) keep [C D] in global memory
+constexpr int KINO_NCAP = 54; // active rows of the kinodynamic Riccati's shared-memory carving; knots with more (up to all 68) solve their KKT out of global scratch
+constexpr int FULL_NCAP = 23; // full dynamics: what fits over the dead P | G buffers (two instances per SM)
 
 struct SolverConst {
   double tol, mu_init;
@@ -54,6 +55,7 @@ struct Ws {
   int32_t *nca, *act_idx;
   double *gap, *h, *scal, *tscal, *xdot, *lamc;
   double *W, *pt, *K, *Kfb, *dphi;
+  double *ric_scratch; size_t ric_scratch_stride; // per-instance scratch of the Riccati kernel (doubles per instance)
   InstState *st;
   int32_t *counters; // [0] instances still in MODE_LS (next ls list), [2] instances to evaluate in the next pass
   int32_t *overflow; // [B] Riccati active-row overflow flags
@@ -285,7 +287,7 @@ HD RiccatiIO make_riccati_io(const Ws &w, int b) {
   r.T6 = w.T6 + b * T * 36; r.CDact = w.CDact + b * T1 * w.nc * w.nz; r.dbar = w.dbar + b * T1 * w.nc; r.nca = w.nca + b * T1;
   r.act_idx = w.act_idx + b * T1 * w.nc; r.lxu = w.lxu + b * T1 * w.nz; r.vplus = w.vplus + b * T1 * w.nc; r.v = w.vs + b * T1 * w.nc;
   r.lplus = w.lplus + b * T1 * w.n; r.lam = w.lams + b * T1 * w.n;
-  r.W = w.W + b * T * w.n * w.nz; r.pt = w.pt + b * T * w.n; r.K = w.K + b * T * (w.m + w.nc) * (1 + w.n); r.Kfb = w.Kfb + b * T * w.m * w.n;
+  r.W = w.W + b * T * w.n * ((w.nz + 7) & ~7); r.scratch = w.ric_scratch + b * w.ric_scratch_stride; r.pt = w.pt + b * T * w.n; r.K = w.K + b * T * (w.m + w.nc) * (1 + w.n); r.Kfb = w.Kfb + b * T * w.m * w.n;
   r.dxs = w.dxs + b * T1 * w.n; r.dus = w.dus + b * T * w.m; r.dvs = w.dvs + b * T1 * w.nc; r.dlams = w.dlams + b * T1 * w.n;
   r.dphi = w.dphi + b;
   r.phase_out = (b == 0) ? w.phase : nullptr;
@@ -296,7 +298,7 @@ HD RiccatiIO make_riccati_io(const Ws &w, int b) {
 template <int KIND> HD void riccati_dispatch(const Ws &w, int b, double *smem) {
   if (w.st[b].mode != MODE_STEP) return;
   RiccatiIO r = make_riccati_io(w, b);
-  if (KIND == MPC_KIND_FULL) riccati_instance_fast<56, 22, 78>(r, smem);
+  if (KIND == MPC_KIND_FULL) riccati_instance_fast<56, 22, 78, FULL_NCAP>(r, smem);
   else if (KIND == MPC_KIND_KINO) riccati_instance_fast<56, 34, 68, KINO_NCAP>(r, smem);
   else riccati_instance<9, 12, 34>(r, smem);
   ONE_THREAD { if (w.overflow[b]) { w.st[b].status = 3; w.st[b].mode = MODE_DONE; w.overflow[b] = 0; } }

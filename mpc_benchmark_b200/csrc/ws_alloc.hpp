@@ -32,7 +32,9 @@ template <class Alloc> size_t alloc_ws(Ws &w, Alloc &&alloc) {
   I(w.nca, B * T1); I(w.act_idx, B * T1 * nc);
   D(w.gap, B * T * n); D(w.h, B * T1 * nc); D(w.scal, B * T1 * SC_COUNT); D(w.tscal, B * T1 * SC_COUNT);
   D(w.xdot, B * T1 * 56); D(w.lamc, B * T1 * 12);
-  D(w.W, B * T * n * nz); D(w.pt, B * T * n); D(w.K, B * T * (m + nc) * (1 + n)); D(w.Kfb, B * T * m * n); D(w.dphi, B); D(w.phase, 64);
+  D(w.W, B * T * n * ((nz + 7) & ~(size_t)7)); D(w.pt, B * T * n); D(w.K, B * T * (m + nc) * (1 + n)); D(w.Kfb, B * T * m * n); D(w.dphi, B); D(w.phase, 64);
+  w.ric_scratch_stride = (w.kind == MPC_KIND_FULL) ? RicFastLayout<56, 22, 78, FULL_NCAP>::scratch : (w.kind == MPC_KIND_KINO) ? RicFastLayout<56, 34, 68, KINO_NCAP>::scratch : 2;
+  D(w.ric_scratch, B * w.ric_scratch_stride);
   w.st = (InstState *)alloc(B * sizeof(InstState)); total += B * sizeof(InstState);
   I(w.counters, 4); I(w.lists, 4 * B); I(w.overflow, B);
   return total;
@@ -41,7 +43,7 @@ template <class Alloc> size_t alloc_ws(Ws &w, Alloc &&alloc) {
 template <class Free> void free_ws(Ws &w, Free &&fr) {
   void *ptrs[] = {w.knots, w.terms, w.x0, w.xs, w.us, w.vs, w.lams, w.vs_prev, w.lams_prev, w.txs, w.tus, w.tvs, w.tlams, w.dxs, w.dus, w.dvs,
                   w.dlams, w.AB, w.H, w.lxu, w.g, w.T6, w.E6, w.gE, w.fbar, w.dbar, w.vplus, w.lplus, w.CDact, w.nca, w.act_idx, w.gap, w.h,
-                  w.scal, w.tscal, w.xdot, w.lamc, w.W, w.pt, w.K, w.Kfb, w.dphi, w.phase, w.st, w.counters, w.lists, w.overflow};
+                  w.scal, w.tscal, w.xdot, w.lamc, w.W, w.pt, w.K, w.Kfb, w.dphi, w.ric_scratch, w.phase, w.st, w.counters, w.lists, w.overflow};
   for (void *p : ptrs) if (p) fr(p);
 }
 

@@ -203,6 +203,7 @@ int orc_solve(const mpc_robot_t *rb, const mpc_config_t *cfg, int batch, const m
   SolverParams prm;
   prm.tol = cfg->tol; prm.mu_init = cfg->mu_init; prm.max_iters = max_iters;
   prm.par_knots = knot_threads > 1;
+  prm.rollout = cfg->rollout;
   // ablation switches (see SolverParams); unset = the normative algorithm
   if (const char *e = getenv("ORC_MU_DYN_SCALE")) prm.mu_dyn_scale = atof(e);
   if (const char *e = getenv("ORC_LS_MODE")) prm.ls_mode = atoi(e);

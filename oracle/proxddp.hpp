@@ -34,6 +34,7 @@ struct SolverParams {
   int ls_mode = 0;            // 0 Armijo backtracking, 1 non-monotone Armijo (reference value = max of the last ls_window merits), 2 always alpha = 1
   int ls_window = 5;
   double dual_weight = 1.0;   // weight of the multiplier-distance terms of the PDAL merit
+  int rollout = 0;            // 0 ROLLOUT_LINEAR (fulldynamic_talos.py:381 and every other reference script), 1 ROLLOUT_NONLINEAR
 };
 
 struct Instance {
@@ -272,7 +273,59 @@ struct Solver {
     return dphi;
   }
 
+  void state_difference(const double *x0, const double *x1, double *out) const { // x1 (-) x0
+    if (P.cfg.kind == MPC_KIND_CENT) { for (int i = 0; i < d.n; i++) out[i] = x1[i] - x0[i]; return; }
+    mb_difference<double>(x0, x1, out);
+  }
+
+  // ROLLOUT_NONLINEAR (aligator RolloutType::NONLINEAR; BASELINE north_star "nonlinear forward rollout and line search"; no
+  // reference script selects it, so the semantics below are the oracle's — PARITY UNPINNED like the rest of the solver).
+  // The trial point is rolled out through the NONLINEAR dynamics under the affine policy of the LQ solve:
+  //   dx_k = x+_k (-) x_k,  du = alpha ku + Ku dx_k,  dv = alpha kv + Kv dx_k,  dlam' = alpha pt + W [dx_k; du],
+  //   x+_{k+1} = f(x+_k, u+_k) (+) mu_d (lam_e - lam'+),
+  // i.e. the new shooting gap satisfies the dual-regularised dynamics gap = mu_d (lam'+ - lam_e) exactly (the linear rollout
+  // satisfies its linearisation); alpha = 1 on an LQ problem reproduces the linear rollout.
+  double try_step_nonlinear(const Instance &in, double alpha, double *cost_out) {
+    const int n = d.n, m = d.m, nc = d.nc, nz = n + m, nr = 1 + n, s = m + nc;
+    std::vector<double> dx(n), z(nz), slack(n);
+    std::copy(xs.begin(), xs.begin() + d.nx, txs.begin());
+    for (int i = 0; i < n; i++) tlams[i] = lams[i] + alpha * sol.dlams[i];
+    for (int k = 0; k < T; k++) {
+      const double *xt = &txs[(size_t)k * d.nx];
+      state_difference(&xs[(size_t)k * d.nx], xt, dx.data());
+      const double *Kk = &sol.K[(size_t)k * s * nr];
+      for (int i = 0; i < s; i++) {
+        double t = alpha * Kk[i * nr];
+        for (int j = 0; j < n; j++) t += Kk[i * nr + 1 + j] * dx[j];
+        if (i < m) { z[n + i] = t; tus[(size_t)k * m + i] = us[(size_t)k * m + i] + t; }
+        else tvs[(size_t)k * nc + i - m] = vs[(size_t)k * nc + i - m] + t;
+      }
+      for (int j = 0; j < n; j++) z[j] = dx[j];
+      const double *Wk = &sol.W[(size_t)k * n * nz];
+      for (int i = 0; i < n; i++) {
+        double t = alpha * sol.pt[(size_t)k * n + i];
+        for (int j = 0; j < nz; j++) t += Wk[i * nz + j] * z[j];
+        size_t id = (size_t)(k + 1) * n + i;
+        tlams[id] = lams[id] + t;
+        slack[i] = mud() * (lams_prev[id] - tlams[id]);
+      }
+      eval_knot(P, in.knots[k], xt, &tus[(size_t)k * m], xt, false, tr[k]); // (x_{k+1} argument unused: the gap is set below)
+      integrate_state(tr[k].xnext.data(), slack.data(), 1.0, &txs[(size_t)(k + 1) * d.nx]);
+      for (int i = 0; i < n; i++) tr[k].gap[i] = -slack[i];
+    }
+    state_difference(&xs[(size_t)T * d.nx], &txs[(size_t)T * d.nx], dx.data());
+    for (int r = 0; r < nc; r++) {
+      size_t id = (size_t)T * nc + r;
+      double t = alpha * dbar[id];
+      for (int j = 0; j < n; j++) t += Cact[id * n + j] * dx[j];
+      tvs[id] = vs[id] + t / mu;
+    }
+    eval_term(P, in.term, &txs[(size_t)T * d.nx], tr[T]);
+    return merit_value(tr, tvs.data(), tlams.data(), cost_out);
+  }
+
   double try_step(const Instance &in, double alpha, double *cost_out) {
+    if (prm.rollout == 1) return try_step_nonlinear(in, alpha, cost_out);
     const int n = d.n, m = d.m;
     for (int k = 0; k <= T; k++) integrate_state(&xs[(size_t)k * d.nx], &sol.dxs[(size_t)k * n], alpha, &txs[(size_t)k * d.nx]);
     for (size_t i = 0; i < us.size(); i++) tus[i] = us[i] + alpha * sol.dus[i];

@@ -5,6 +5,8 @@
 #include "../../mpc_benchmark_b200/csrc/driver.hpp"
 #include "../../mpc_benchmark_b200/csrc/ws_alloc.hpp"
 #include <cstdlib>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -73,6 +75,9 @@ extern "C" int emu_solve(const mpc_robot_t *rb, const mpc_config_t *cfg, int bat
     put(w.AB, (size_t)w.T * w.n * w.nz); put(w.H, T1 * w.nz * w.nz); put(w.g, T1 * w.nz); put(w.gap, (size_t)w.T * w.n); put(w.h, T1 * w.nc);
     put(w.scal, T1 * SC_COUNT);
   } else run_loop(be, w, max_iters, w.sc);
+  if (getenv("EMU_NCA_HIST")) { // test tooling: active-row counts per knot of the last pass (sizes the kernel's shared-memory fast path)
+    for (int b = 0; b < batch; b++) { fprintf(stderr, "nca[%d]:", b); for (size_t k = 0; k < T1; k++) fprintf(stderr, " %d", w.nca[b * T1 + k]); fprintf(stderr, "\n"); }
+  }
   std::memcpy(xs, w.xs, 8 * batch * T1 * w.nx);
   std::memcpy(us, w.us, 8 * batch * w.T * w.m);
   if (K) std::memcpy(K, w.Kfb, 8 * (size_t)batch * w.T * w.m * w.n);

@@ -11,7 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 def load(name):
     z = np.load(os.path.join(HERE, "golden", name))
-    cfg = _abi.Config.from_buffer_copy(z["cfg"].tobytes())
+    raw = z["cfg"].tobytes()  # fixtures written before mpc_config_t grew its trailing `rollout` field: zero-extend (0 = ROLLOUT_LINEAR)
+    cfg = _abi.Config.from_buffer_copy(raw + bytes(max(0, C.sizeof(_abi.Config) - len(raw))))
     rb = _abi.Robot.from_buffer_copy(z["robot"].tobytes())
     nk = z["knots"].size // C.sizeof(_abi.Knot)
     nt = z["terms"].size // C.sizeof(_abi.Term)

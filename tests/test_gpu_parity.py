@@ -449,7 +449,19 @@ def test_batch_4096_sampled_instances(oracle):
     s2.setup(sub["knots"], sub["terms"], sub["x0"])
     r2 = s2.run(sub["xs"], sub["us"], max_iters=2, gains=False)
     s2.close()
-    assert np.array_equal(r2.xs, res.xs[pick]) and np.array_equal(r2.us, res.us[pick])
+    # launches that fill the GPU run the Riccati kernel with 128 threads per instance (two instances per SM), smaller ones with 256:
+    # the merit's directional derivative is summed per thread, so the two agree to rounding, not bit for bit
+    assert rel(r2.xs, res.xs[pick]) < 1e-11 and rel(r2.us, res.us[pick]) < 1e-11 and list(r2.ls_evals) == list(res.ls_evals[pick])
+    # ... and inside one launch shape the result of an instance is bit-identical whatever batch it is solved in
+    half = dict(sub)
+    half["knots"] = (_abi.Knot * (4 * T))(*[sub["knots"][i * T + k] for i in range(4) for k in range(T)])
+    half["terms"] = (_abi.Term * 4)(*[sub["terms"][i] for i in range(4)])
+    half["x0"], half["xs"], half["us"] = sub["x0"][:4], sub["xs"][:4], sub["us"][:4]
+    s3 = BatchSolver(half["robot"], half["cfg"], 4)
+    s3.setup(half["knots"], half["terms"], half["x0"])
+    r3 = s3.run(half["xs"], half["us"], max_iters=2, gains=False)
+    s3.close()
+    assert np.array_equal(r3.xs, r2.xs[:4]) and np.array_equal(r3.us, r2.us[:4])
 
 
 def test_stairs_batch_sample(oracle):
