@@ -186,10 +186,10 @@ HD void mma_tn_g(int mt, int nt, const double *A, int lda, int va, const double 
 
 // Symmetric update C = Cinit + A^T B (C: 8 nt x 8 nt, result symmetric) whose OUTPUT BUFFER ALIASES THE A OPERAND: every warp keeps
 // the accumulators of all its 16 x 16 blocks (upper block triangle, at most MAXQ per warp) in registers, the CTA synchronises once
-// all operand reads are done, and only then the blocks and their mirrors are stored.  A: shared memory [K][lda]; B: global memory
-// [K][ldb] read through L2; Cinit: global, rows < vr / columns < vc (zero outside).  Mirrored entries whose source column is >= vc
+// all operand reads are done, and only then the blocks and their mirrors are stored.  A: shared memory [K][lda]; B: shared memory, or
+// global memory read through L2 (BG), [K][ldb]; Cinit: global, rows < vr / columns < vc (zero outside).  Mirrored entries whose source column is >= vc
 // are written as zero (those columns are scratch: they must not reach the rows below).
-template <int K, int MAXQ>
+template <int K, int MAXQ, bool BG>
 HD void mma_sym_deferred(int nt, const double *A, int lda, const double *B, int ldb, double *C, int ldc, const double *Cinit, int ldci, int vr, int vc) {
 #ifdef MPC_HOST_EMU
   std::vector<double> out((size_t)64 * nt * nt);
@@ -209,8 +209,12 @@ HD void mma_sym_deferred(int nt, const double *A, int lda, const double *B, int 
   const int ntp = (nt + 1) / 2, nwork = ntp * (ntp + 1) / 2;
   double c[MAXQ][2][2][2];
 #pragma unroll
-  for (int q_ = 0; q_ < MAXQ; q_++) {
+  for (int q_ = 0; q_ < MAXQ; q_++) { // initial values of every block first: all L2 reads of this warp in flight together
     const int p = warp + q_ * nwarps;
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+      for (int b = 0; b < 2; b++) { c[q_][a][b][0] = 0.0; c[q_][a][b][1] = 0.0; }
     if (p < nwork) {
       int bi = 0, q = p;
       while (q >= ntp - bi) { q -= ntp - bi; bi++; }
@@ -220,27 +224,47 @@ HD void mma_sym_deferred(int nt, const double *A, int lda, const double *B, int 
       for (int a = 0; a < 2; a++)
 #pragma unroll
         for (int b = 0; b < 2; b++) {
-          c[q_][a][b][0] = 0.0; c[q_][a][b][1] = 0.0;
           const int row = (ti + a) * 8 + g, col = (tj + b) * 8 + 2 * t;
           if (row < vr && (a == 0 || r2) && (b == 0 || c2)) {
             if (col + 1 < vc) { const double2 v = __ldcg(reinterpret_cast<const double2 *>(Cinit + row * ldci + col)); c[q_][a][b][0] = v.x; c[q_][a][b][1] = v.y; }
             else if (col < vc) c[q_][a][b][0] = __ldcg(Cinit + row * ldci + col);
           }
         }
+    }
+  }
+#pragma unroll
+  for (int q_ = 0; q_ < MAXQ; q_++) {
+    const int p = warp + q_ * nwarps;
+    if (p < nwork) {
+      int bi = 0, q = p;
+      while (q >= ntp - bi) { q -= ntp - bi; bi++; }
+      const int bj = bi + q, ti = bi * 2, tj = bj * 2;
+      const bool r2 = (ti + 1 < nt), c2 = (tj + 1 < nt);
       const int ao = r2 ? 8 : 0, bo = c2 ? 8 : 0;
       const double *ap = A + t * lda + ti * 8 + g;
       const double *bp = B + t * ldb + tj * 8 + g;
       constexpr int NS = K / 4;
-      double b0[NS], b1[NS];
+      if (BG) {
+        double b0[NS], b1[NS];
 #pragma unroll
-      for (int s = 0; s < NS; s++) { b0[s] = __ldcg(bp + 4 * s * ldb); b1[s] = __ldcg(bp + 4 * s * ldb + bo); }
+        for (int s = 0; s < NS; s++) { b0[s] = __ldcg(bp + 4 * s * ldb); b1[s] = __ldcg(bp + 4 * s * ldb + bo); }
 #pragma unroll
-      for (int s = 0; s < NS; s++) {
-        const double a0 = ap[4 * s * lda], a1 = ap[4 * s * lda + ao];
-        dmma_8x8x4(c[q_][0][0][0], c[q_][0][0][1], a0, b0[s]);
-        dmma_8x8x4(c[q_][0][1][0], c[q_][0][1][1], a0, b1[s]);
-        dmma_8x8x4(c[q_][1][0][0], c[q_][1][0][1], a1, b0[s]);
-        dmma_8x8x4(c[q_][1][1][0], c[q_][1][1][1], a1, b1[s]);
+        for (int s = 0; s < NS; s++) {
+          const double a0 = ap[4 * s * lda], a1 = ap[4 * s * lda + ao];
+          dmma_8x8x4(c[q_][0][0][0], c[q_][0][0][1], a0, b0[s]);
+          dmma_8x8x4(c[q_][0][1][0], c[q_][0][1][1], a0, b1[s]);
+          dmma_8x8x4(c[q_][1][0][0], c[q_][1][0][1], a1, b0[s]);
+          dmma_8x8x4(c[q_][1][1][0], c[q_][1][1][1], a1, b1[s]);
+        }
+      } else {
+#pragma unroll 2
+        for (int s = 0; s < NS; s++) {
+          const double a0 = ap[4 * s * lda], a1 = ap[4 * s * lda + ao], b0 = bp[4 * s * ldb], b1 = bp[4 * s * ldb + bo];
+          dmma_8x8x4(c[q_][0][0][0], c[q_][0][0][1], a0, b0);
+          dmma_8x8x4(c[q_][0][1][0], c[q_][0][1][1], a0, b1);
+          dmma_8x8x4(c[q_][1][0][0], c[q_][1][0][1], a1, b0);
+          dmma_8x8x4(c[q_][1][1][0], c[q_][1][1][1], a1, b1);
+        }
       }
     }
   }
@@ -323,56 +347,78 @@ template <int NB> HD void trsm_mma(const double *A, int ld, const double *Dinv, 
   trsm_blocked(A, 8 * NB, ld, Dinv, Bm, 8 * nt_main, ldb);
   if (nt > nt_main) trsm_blocked(A, 8 * NB, ld, Dinv, Bx, 8 * (nt - nt_main), ldx);
 #else
-  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  for (int ct = (threadIdx.x >> 5); ct < nt; ct += (blockDim.x >> 5)) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3, nw = blockDim.x >> 5;
+  // a warp takes TWO column tiles per pass when there are enough of them (ct and ct + nw): two independent substitution chains
+  // interleave in the same instruction stream and hide each other's DMMA / shared-memory latencies
+  for (int ct = (threadIdx.x >> 5); ct < nt; ct += 2 * nw) {
+    const int ct2 = ct + nw;
+    const bool two = ct2 < nt;
     double *zc = (ct < nt_main) ? Bm + 8 * ct : Bx + 8 * (ct - nt_main);
     const int lz = (ct < nt_main) ? ldb : ldx;
+    double *zd = !two ? zc : (ct2 < nt_main) ? Bm + 8 * ct2 : Bx + 8 * (ct2 - nt_main);
+    const int lw = !two ? lz : (ct2 < nt_main) ? ldb : ldx;
 #pragma unroll
     for (int ib = 0; ib < NB; ib++) { // forward: Y_i = Dinv_i (B_i - sum_{k<i} L_ik Y_k)
-      double2 *cp = reinterpret_cast<double2 *>(zc + (8 * ib + g) * lz + 2 * t);
-      double2 c = *cp;
-      double e0 = 0.0, e1 = 0.0;
+      double2 *cp = reinterpret_cast<double2 *>(zc + (8 * ib + g) * lz + 2 * t), *dp = reinterpret_cast<double2 *>(zd + (8 * ib + g) * lw + 2 * t);
+      double2 c = *cp, d = *dp;
+      double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
 #pragma unroll
       for (int kb = 0; kb < ib; kb++) {
         const double *pa = A + (8 * ib + g) * ld + 8 * kb + t;
-        const double *pb = zc + (8 * kb + t) * lz + g;
-        dmma_8x8x4(c.x, c.y, -pa[0], pb[0]);
-        dmma_8x8x4(e0, e1, -pa[4], pb[4 * lz]);
+        const double a0 = -pa[0], a1 = -pa[4];
+        const double *pb = zc + (8 * kb + t) * lz + g, *pd = zd + (8 * kb + t) * lw + g;
+        dmma_8x8x4(c.x, c.y, a0, pb[0]);
+        dmma_8x8x4(e0, e1, a1, pb[4 * lz]);
+        if (two) { dmma_8x8x4(d.x, d.y, a0, pd[0]); dmma_8x8x4(f0, f1, a1, pd[4 * lw]); }
       }
-      c.x += e0; c.y += e1;
+      c.x += e0; c.y += e1; d.x += f0; d.y += f1;
       *cp = c;
+      if (two) *dp = d;
       __syncwarp();
       const double b0 = zc[(8 * ib + t) * lz + g], b1 = zc[(8 * ib + 4 + t) * lz + g];
+      const double h0 = zd[(8 * ib + t) * lw + g], h1 = zd[(8 * ib + 4 + t) * lw + g];
       __syncwarp();
       const double *Di = Dinv + 64 * ib;
-      double2 d = make_double2(0.0, 0.0);
-      dmma_8x8x4(d.x, d.y, Di[g * 8 + t], b0);
-      dmma_8x8x4(d.x, d.y, Di[g * 8 + 4 + t], b1);
-      *cp = d;
+      const double q0 = Di[g * 8 + t], q1 = Di[g * 8 + 4 + t];
+      double2 r = make_double2(0.0, 0.0), u = make_double2(0.0, 0.0);
+      dmma_8x8x4(r.x, r.y, q0, b0);
+      if (two) dmma_8x8x4(u.x, u.y, q0, h0);
+      dmma_8x8x4(r.x, r.y, q1, b1);
+      if (two) dmma_8x8x4(u.x, u.y, q1, h1);
+      *cp = r;
+      if (two) *dp = u;
       __syncwarp();
     }
 #pragma unroll
     for (int ib = NB - 1; ib >= 0; ib--) { // backward: X_i = Dinv_i' (Y_i - sum_{k>i} L_ki' X_k)
-      double2 *cp = reinterpret_cast<double2 *>(zc + (8 * ib + g) * lz + 2 * t);
-      double2 c = *cp;
-      double e0 = 0.0, e1 = 0.0;
+      double2 *cp = reinterpret_cast<double2 *>(zc + (8 * ib + g) * lz + 2 * t), *dp = reinterpret_cast<double2 *>(zd + (8 * ib + g) * lw + 2 * t);
+      double2 c = *cp, d = *dp;
+      double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
 #pragma unroll
       for (int kb = ib + 1; kb < NB; kb++) {
         const double *pa = A + (8 * kb + t) * ld + 8 * ib + g; // (L_ki)'[g][t] = L_ki[t][g]
-        const double *pb = zc + (8 * kb + t) * lz + g;
-        dmma_8x8x4(c.x, c.y, -pa[0], pb[0]);
-        dmma_8x8x4(e0, e1, -pa[4 * ld], pb[4 * lz]);
+        const double a0 = -pa[0], a1 = -pa[4 * ld];
+        const double *pb = zc + (8 * kb + t) * lz + g, *pd = zd + (8 * kb + t) * lw + g;
+        dmma_8x8x4(c.x, c.y, a0, pb[0]);
+        dmma_8x8x4(e0, e1, a1, pb[4 * lz]);
+        if (two) { dmma_8x8x4(d.x, d.y, a0, pd[0]); dmma_8x8x4(f0, f1, a1, pd[4 * lw]); }
       }
-      c.x += e0; c.y += e1;
+      c.x += e0; c.y += e1; d.x += f0; d.y += f1;
       *cp = c;
+      if (two) *dp = d;
       __syncwarp();
       const double b0 = zc[(8 * ib + t) * lz + g], b1 = zc[(8 * ib + 4 + t) * lz + g];
+      const double h0 = zd[(8 * ib + t) * lw + g], h1 = zd[(8 * ib + 4 + t) * lw + g];
       __syncwarp();
       const double *Di = Dinv + 64 * ib;
-      double2 d = make_double2(0.0, 0.0);
-      dmma_8x8x4(d.x, d.y, Di[t * 8 + g], b0);
-      dmma_8x8x4(d.x, d.y, Di[(4 + t) * 8 + g], b1);
-      *cp = d;
+      const double q0 = Di[t * 8 + g], q1 = Di[(4 + t) * 8 + g];
+      double2 r = make_double2(0.0, 0.0), u = make_double2(0.0, 0.0);
+      dmma_8x8x4(r.x, r.y, q0, b0);
+      if (two) dmma_8x8x4(u.x, u.y, q0, h0);
+      dmma_8x8x4(r.x, r.y, q1, b1);
+      if (two) dmma_8x8x4(u.x, u.y, q1, h1);
+      *cp = r;
+      if (two) *dp = u;
       __syncwarp();
     }
   }

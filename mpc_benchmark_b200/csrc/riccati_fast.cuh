@@ -34,8 +34,9 @@ template <int N, int M, int NC, int NCAP = NC> struct RicFastLayout {
   static constexpr int LDN = (N % 16 == 8) ? N : N + 8;             // ld of N x N buffers
   static constexpr int LDH = ZP;                                    // ld of the Hessian buffer
   static constexpr int LDW = ZP;                                    // ld of W in HBM: column NZ carries pt, the rest of the padding is zero
-  static constexpr int LDZ = (ZP % 16 == 8) ? ZP : ZP + 8;          // ld of [A B] staged in shared memory (over the idle H buffer)
-  static_assert(N * LDZ <= ZP * LDH, "[A B] must fit into the H buffer");
+  static constexpr int LDZ = ZP + 4;                                // ld of [A B] and W staged in shared memory (over the idle H buffer): = 4 (mod 8) doubles, so the
+                                                                    // 16 lanes of a half-warp fragment load (4 k-rows x 4 columns of 8 bytes) cover all 32 banks once
+  static_assert(N * LDZ <= ZP * LDH && 2 * N * LDZ <= ZP * LDH + N * LDN, "[A B] must fit into the H buffer, W behind it up to the end of the factor");
   static constexpr int NQ_SYM = ((ZP / 8 + 1) / 2) * ((ZP / 8 + 1) / 2 + 1) / 2; // 16 x 16 blocks of the upper block triangle of H
   static constexpr int MAXQ = (NQ_SYM + 3) / 4;                    // per warp, for CTAs of at least 4 warps
   static constexpr int MR = (M + 7) / 8 * 8;                        // control block padded to whole 8 x 8 tiles (identity / zero padding)
@@ -67,7 +68,8 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
   double *H = ws;                              // ZP x LDH, zero padded; [0:N,0:N] carries the value-function Hessian between knots
   double *ABs = H;                             // ... and [A B]_k (N x LDZ) between the moment that Hessian is taken out and the Hessian update
   double *U0 = H + ZP * LDH;
-  double *P = U0, *G = P + N * LDN;            // phase 1
+  double *G = U0, *P = G + N * LDN;            // phase 1 (the factor first: W spills into its slot, see Ws)
+  double *Ws = H + N * LDZ;                    // W (N x LDZ) between its product and the Hessian update: behind [A B], over the tail of the H buffer and the dead factor
   double *vec = U0 + Lay::un;
   double *p = vec, *pt = p + N, *gh = pt + N, *fb = gh + ZP, *tmp = fb + N, *dx = tmp + N, *z = dx + N, *pv = z + ZP; // gh, z: n + m entries, the others n
   double *T6 = pv + N, *dbr = T6 + 36, *dva = dbr + NC, *dinv_s = dva + NC, *PV = dinv_s + 64 * Lay::NDINV, *red = PV + 8 * N; // (red: one slot per warp)
@@ -115,14 +117,14 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
     double *gW = io.W + (size_t)k * N * LDW;
     const int nca = io.nca[k];
     if (k > 0) prefetch_knot(k - 1);
-    // 1. ONE pass over the value Hessian left in H by the previous knot: P <- T' sym(H) T (E normalisation: T = blockdiag(T6, I)
+    // 1. ONE pass over the value Hessian left in H by the previous knot: P <- T' H T (E normalisation: T = blockdiag(T6, I)
     //    touches the 6 base rows / columns only), G <- I + mu_d P, and the normalised gradient tmp <- T' p
     MBAR_WAIT(mbar + 2, (T - 1 - k) & 1); // T6 and fbar of this knot (issued one knot ahead)
     PHASE(21);
-    PAR_FOR(e, N * N) { // rows / columns >= 6: plain symmetrisation.  lanes: 8 consecutive j x 4 consecutive i (transposed read: 8-way conflicts)
-      const int blk = e >> 5, l = e & 31, i = (blk / (N / 8)) * 4 + (l >> 3), j = (blk % (N / 8)) * 8 + (l & 7);
+    PAR_FOR(e, N * N) { // rows / columns >= 6: a plain copy — the value update mirrors its upper blocks, H is symmetric up to rounding inside the diagonal blocks
+      const int i = e / N, j = e % N;
       if (i < 6 || j < 6) continue;
-      const double v = 0.5 * (H[i * LDH + j] + H[j * LDH + i]);
+      const double v = H[i * LDH + j];
       P[i * LDN + j] = v;
       G[i * LDN + j] = mu_d * v + ((i == j) ? 1.0 : 0.0);
     }
@@ -139,10 +141,10 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
         }
       } else if (s_ < 36 + 6 * (N - 6)) {
         i = (s_ - 36) / (N - 6); j = 6 + (s_ - 36) % (N - 6);
-        for (int q = 0; q < 6; q++) v += T6[6 * q + i] * (0.5 * (H[q * LDH + j] + H[j * LDH + q]));
+        for (int q = 0; q < 6; q++) v += T6[6 * q + i] * H[q * LDH + j];
       } else {
         j = (s_ - 36 - 6 * (N - 6)) / (N - 6); i = 6 + (s_ - 36 - 6 * (N - 6)) % (N - 6);
-        for (int q = 0; q < 6; q++) v += 0.5 * (H[i * LDH + q] + H[q * LDH + i]) * T6[6 * q + j];
+        for (int q = 0; q < 6; q++) v += H[q * LDH + i] * T6[6 * q + j]; // (row q, column i: the same entries as the top edge, so P stays symmetric bit for bit there)
       }
       P[i * LDN + j] = v;
       G[i * LDN + j] = mu_d * v + ((i == j) ? 1.0 : 0.0);
@@ -166,17 +168,18 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
     // 3. [P | pv] <- Lambda^-1 [P | pv] in place: blocked forward / backward substitution, one warp per 8-column tile
     trsm_mma<NBLK>(G, LDN, dinv_s, P, LDN, NBLK, PV, 8, NBLK + 1);
     PHASE(4);
-    // 4. W = Pt [A B]: the result goes straight from the accumulators to HBM (the forward sweep and the Hessian update read it
-    //    from there); pt rides in the first padding column of W, so [A B]' pt falls out of the Hessian update
+    // 4. W = Pt [A B] into shared memory (for the Hessian update) and straight from the accumulators to HBM (for the forward
+    //    sweep); pt rides in the first padding column of W, so [A B]' pt falls out of the Hessian update
     MBAR_WAIT(mbar + 3, (T - 1 - k) & 1); // [A B]_k
-    mma_tn_g<N, false, false>(NBLK, ZP / 8, P, LDN, N, ABs, LDZ, ZP, nullptr, 0, nullptr, 0, 0, 0, false, gW, LDW, ZP);
+    mma_tn_g<N, false, false>(NBLK, ZP / 8, P, LDN, N, ABs, LDZ, ZP, Ws, LDZ, nullptr, 0, 0, 0, false, gW, LDW, ZP);
     PHASE(17);
-    PAR_FOR(i, N) { const double v = PV[8 * i]; pt[i] = v; gW[i * LDW + NZ] = v; io.pt[(size_t)k * N + i] = v; }
+    PAR_FOR(i, N) { const double v = PV[8 * i]; pt[i] = v; Ws[i * LDZ + NZ] = v; gW[i * LDW + NZ] = v; io.pt[(size_t)k * N + i] = v; }
     SYNC();
     // 5. H = H_k + [A B]' W (symmetric: upper blocks computed, lower mirrored; H_k from L2, columns >= NZ read as zero).  The
-    //    result overwrites the buffer [A B] sits in: accumulators stay in registers until every warp is done reading it.
+    //    result overwrites the buffers [A B] and W sit in: accumulators stay in registers until every warp is done reading them.
     //    gh = g + [A B]' pt
-    mma_sym_deferred<N, Lay::MAXQ>(ZP / 8, ABs, LDZ, gW, LDW, H, LDH, gH, NZ, NZ, NZ);
+    PHASE(22);
+    mma_sym_deferred<N, Lay::MAXQ, false>(ZP / 8, ABs, LDZ, Ws, LDZ, H, LDH, gH, NZ, NZ, NZ);
     PHASE(18);
     PAR_FOR(i, NZ) gh[i] = io.g[(size_t)k * NZ + i] + H[i * LDH + NZ];
     SYNC();
@@ -197,10 +200,9 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
       int i = e / MR, j = e % MR;
       Rh[i * LDR + j] = (i < M && j < M) ? 0.5 * (H[(N + i) * LDH + N + j] + H[(N + j) * LDH + N + i]) : ((i == j) ? 1.0 : 0.0);
     }
-    SYNC();
-    PAR_FOR(e, MR * ldz) {
+    PAR_FOR(e, MR * ldz) { // (reads the active rows from global memory: no barrier between the copy above and this loop)
       int i = e / ldz, c = e % ldz;
-      Z[e] = (i >= M || c >= ncol) ? 0.0 : ((c == 0) ? gh[N + i] : (c < NR ? H[(N + i) * LDH + c - 1] : CD[(c - NR) * NZ + N + i])); // H_ux row i (H is symmetric to rounding): conflict-free
+      Z[e] = (i >= M || c >= ncol) ? 0.0 : ((c == 0) ? gh[N + i] : (c < NR ? H[(N + i) * LDH + c - 1] : gCD[(c - NR) * NZ + N + i])); // H_ux row i (H is symmetric to rounding): conflict-free
     }
     SYNC();
     PHASE(6);
@@ -236,7 +238,7 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
     PAR_FOR(e, M * NR) { int i = e / NR, c = e % NR; double v = Z[i * ldz + c]; gK[e] = v; if (c > 0) io.Kfb[((size_t)k * M + i) * N + c - 1] = v; }
     PAR_FOR(e, nca * NR) gK[M * NR + e] = Kv[e];
     PHASE(11);
-    // 9. P = Qh + Sh Ku + C' Kv, p = qh + Sh ku + C' kv : in place in H[0:N,0:N] / p (symmetrised when the next knot loads it).
+    // 9. P = Qh + Sh Ku + C' Kv, p = qh + Sh ku + C' kv : in place in H[0:N,0:N] / p.
     //    Sh Ku = H[N:, 0:N]' Z[:, 1:] runs on the DMMA pipe (K = MP, zero rows beyond M); the active-row part is usually empty.
     PAR_FOR(i, N) {
       double s = gh[i];
@@ -244,7 +246,10 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
       for (int r = 0; r < nca; r++) s += CD[r * NZ + i] * Kv[r * NR];
       p[i] = s;
     }
-    mma_tn(NBLK, NBLK, MR, H + N * LDH, LDH, Z + 1, ldz, H, LDH, H, LDH, N, N, false);
+    //    Without active rows the product is symmetric up to the rounding of well-scaled terms: upper blocks computed, lower mirrored.
+    //    With active rows Ku and Kv carry 1/mu-sized entries that cancel in the sum, and the rounding of that cancellation must be
+    //    averaged out as the oracle does: full product, then P <- (P + P') / 2.
+    mma_tn(NBLK, NBLK, MR, H + N * LDH, LDH, Z + 1, ldz, H, LDH, H, LDH, N, N, nca == 0);
     if (nca > 0) { // 2 x 4 register tiles over (row i, column c)
       constexpr int TC = N / 4;
       PAR_FOR(t, (N / 2) * TC) {
@@ -264,6 +269,11 @@ template <int N, int M, int NC, int NCAP = NC> HD void riccati_instance_fast(con
         for (int r = 0; r < 2; r++)
 #pragma unroll
           for (int q = 0; q < 4; q++) H[(i0 + r) * LDH + c0 + q] = a[r][q];
+      }
+      SYNC();
+      PAR_FOR(e, N * N) { // lanes: 8 consecutive j x 4 consecutive i, which keeps the transposed access at 8-way bank conflicts
+        const int blk = e >> 5, l = e & 31, i = (blk / (N / 8)) * 4 + (l >> 3), j = (blk % (N / 8)) * 8 + (l & 7);
+        if (i < j) { const double v = 0.5 * (H[i * LDH + j] + H[j * LDH + i]); H[i * LDH + j] = v; H[j * LDH + i] = v; }
       }
       SYNC();
     }
