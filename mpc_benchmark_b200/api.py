@@ -518,8 +518,8 @@ class SolverProxDDP:
         return self.num_threads
 
     def _check_options(self):
-        if self.rollout_type != ROLLOUT_LINEAR:
-            raise NotImplementedError("only rollout_type = ROLLOUT_LINEAR is implemented (the option every reference script sets)")
+        if self.rollout_type not in (ROLLOUT_LINEAR, ROLLOUT_NONLINEAR):
+            raise ValueError("rollout_type must be ROLLOUT_LINEAR or ROLLOUT_NONLINEAR")
         if not self.force_initial_condition:
             raise NotImplementedError("force_initial_condition = False is not implemented")
 
@@ -528,7 +528,8 @@ class SolverProxDDP:
         from .batch import BatchSolver
 
         self._check_options()
-        flat = flatten.flatten_problem(problem, tol=self.target_tol, mu_init=self.mu_init, max_iters=self.max_iters)
+        flat = flatten.flatten_problem(problem, tol=self.target_tol, mu_init=self.mu_init, max_iters=self.max_iters,
+                                       rollout=int(self.rollout_type == ROLLOUT_NONLINEAR))
         sig = (flat.cfg.kind, flat.cfg.T)
         if self._bs is None or sig != self._sig:
             if self._bs is not None:
@@ -550,7 +551,8 @@ class SolverProxDDP:
         if self._bs is None:
             raise RuntimeError("SolverProxDDP.run: call setup(problem) first")
         self._check_options()
-        flat = flatten.flatten_problem(problem, tol=self.target_tol, mu_init=self.mu_init, max_iters=self.max_iters)
+        flat = flatten.flatten_problem(problem, tol=self.target_tol, mu_init=self.mu_init, max_iters=self.max_iters,
+                                       rollout=int(self.rollout_type == ROLLOUT_NONLINEAR))
         if (flat.cfg.kind, flat.cfg.T) != self._sig:
             raise RuntimeError("problem structure changed since setup(); call setup(problem) again")
         bs = self._bs

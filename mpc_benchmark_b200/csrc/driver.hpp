@@ -8,7 +8,7 @@
 namespace mpcdev {
 
 // Backend: reset_counters(), eval(deriv, list, n), decide_eval(list, n, next_eval), riccati(list, n), apply_step(list, n),
-//          decide_ls(list, n, ls_out, next_eval), read_counters(int[4])
+//          decide_ls(list, n, ls_out, next_eval), rollout_ls(list, n, next_eval), read_counters(int[4])
 template <class Backend> int run_loop(Backend &be, const Ws &w, int max_iters, const SolverConst &sc) {
   int launches = 0, n_eval = w.B, cur = 0;
   const int guard = max_iters + sc.max_al_iters + 2;
@@ -16,9 +16,17 @@ template <class Backend> int run_loop(Backend &be, const Ws &w, int max_iters, c
     int32_t *L = eval_list(w, cur), *Lnext = eval_list(w, cur + 1);
     be.reset_counters();
     be.eval(true, L, n_eval); be.decide_eval(L, n_eval, Lnext); be.riccati(L, n_eval);
+    int c[4] = {0, 0, 0, 0};
+    if (sc.rollout == 1) { // ROLLOUT_NONLINEAR: rollout and the whole linesearch of every instance in ONE kernel
+      be.rollout_ls(L, n_eval, Lnext);
+      launches += 4;
+      be.read_counters(c);
+      n_eval = c[2];
+      cur ^= 1;
+      continue;
+    }
     be.apply_step(L, n_eval); be.eval(false, L, n_eval); be.decide_ls(L, n_eval, ls_list(w, 0), Lnext);
     launches += 6;
-    int c[4] = {0, 0, 0, 0};
     be.read_counters(c);
     int n_ls = c[0];
     for (int r = 0; n_ls > 0 && r <= sc.ls_max_steps; r++) {

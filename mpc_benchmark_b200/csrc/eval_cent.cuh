@@ -22,7 +22,7 @@ struct CentWs {
   int32_t ctype[CNC], isact[CNC], act_idx[CNC], nca;
 };
 
-template <bool DERIV> HD void eval_cent_knot(const DevModel &m, const KnotIO &io, CentWs &w) {
+template <bool DERIV, bool ROLL = false> HD void eval_cent_knot(const DevModel &m, const KnotIO &io, CentWs &w) {
   const mpc_config_t &cfg = m.cfg;
   const double mass = cfg.mass, dt = cfg.dt;
   PAR_FOR(i, CN) { w.x[i] = io.x[i]; w.xn[i] = io.xn[i]; }
@@ -51,7 +51,11 @@ template <bool DERIV> HD void eval_cent_knot(const DevModel &m, const KnotIO &io
     double fx[9];
     skew3(ft, fx); // d/dc sum (p - c) x f = [f]x
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) w.Fx[(6 + i) * CN + j] = fx[3 * i + j];
-    for (int i = 0; i < CN; i++) { double xn = w.x[i] + dt * w.xd[i]; w.gap[i] = xn - w.xn[i]; io.gap[i] = w.gap[i]; io.xdot[i] = w.xd[i]; }
+    for (int i = 0; i < CN; i++) {
+      double xn = w.x[i] + dt * w.xd[i];
+      if (ROLL) { w.xn[i] = xn + io.slack[i]; io.xn_out[i] = w.xn[i]; } // nonlinear rollout: x_{k+1} := f(x, u) + slack
+      w.gap[i] = xn - w.xn[i]; io.gap[i] = w.gap[i]; io.xdot[i] = w.xd[i];
+    }
     // residual rows: angular acceleration = xdot[6:9] (cent:217-219), linear acceleration = g + sum f / m (cent:214-216)
     for (int i = 0; i < 3; i++) {
       w.r[i] = w.xd[6 + i]; w.wgt[i] = cfg.w_angacc[i];

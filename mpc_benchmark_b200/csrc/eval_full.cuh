@@ -51,6 +51,8 @@ struct KnotIO {
   int32_t *nca, *act_idx;
   // outputs (both passes)
   double *gap, *h, *scal, *xdot, *lamc;
+  // ROLLOUT_NONLINEAR (fused rollout kernel, values pass only): x_{k+1} is not an input but DEFINED here as f(x, u) (+) slack and written out
+  const double *slack; double *xn_out;
   double *scratch;   // derivative pass: this knot's slot of the Riccati W buffer (n x nz doubles, dead until the Riccati kernel writes it):
                      // holds the tangent X = da/dz (NV x nz) and dlam/dz (12 x nz), which stay L2-resident between the phases
   double *phase_out; // profiling builds only
@@ -213,7 +215,7 @@ template <class WS> HD void mb_composite_B(const DevModel &m, WS &w) {
 // knots (gap_out != nullptr) — the base part of the semi-implicit Euler step, the shooting gap and the 6x6 Lie-group blocks
 // P1 = Jlog6(D) Jexp6(dq), P2 = Jlog6(D) Ad(exp6(dq))^-1, E6 = -Jlog6(D) Ad(D^-1), T6 = -E6^-1 = Ad(D) Jexp6(log6 D).
 // The single-thread Lie-group tasks are spread over the 4 warps in two dependent stages, the 6x6 products over all threads.
-template <class WS> HD void mb_cost_terms(const DevModel &m, WS &w, const double *lf_ref, const double *rf_ref, bool derivs, double *gap_out) {
+template <class WS, bool ROLL = false> HD void mb_cost_terms(const DevModel &m, WS &w, const double *lf_ref, const double *rf_ref, bool derivs, double *gap_out, const double *slack = nullptr) {
   const mpc_robot_t &rb = m.rb;
   // stage 1a: the relative placements whose logarithms are needed: both foot poses, the state error and the shooting gap
   PAR_FOR(task, 3 * 32) {
@@ -228,6 +230,12 @@ template <class WS> HD void mb_cost_terms(const DevModel &m, WS &w, const double
         mat3_vec(w.oM, w.eexp + 9, pn);
         for (int i = 0; i < 3; i++) w.xnext[i] = w.x[i] + pn[i];
         quat_integrate(w.x + 3, w.dx + 3, w.xnext + 3);
+        if (ROLL) { // nonlinear rollout: x_{k+1} := f(x, u) (+) slack (base part; joints and velocities below)
+          double es[12], Rn[9], ps[3];
+          exp6(slack, es); quat_to_R(w.xnext + 3, Rn); mat3_vec(Rn, es + 9, ps);
+          for (int i = 0; i < 3; i++) w.xn[i] = w.xnext[i] + ps[i];
+          quat_integrate(w.xnext + 3, slack + 3, w.xn + 3);
+        }
         quat_to_R(w.xn + 3, Mn); Mn[9] = w.xn[0]; Mn[10] = w.xn[1]; Mn[11] = w.xn[2];
         quat_to_R(w.xnext + 3, Mp); Mp[9] = w.xnext[0]; Mp[10] = w.xnext[1]; Mp[11] = w.xnext[2];
         se3_inv_mul(Mn, Mp, w.Dgap);
@@ -258,8 +266,8 @@ template <class WS> HD void mb_cost_terms(const DevModel &m, WS &w, const double
     w.estate[a] = (a < NV) ? (w.x[7 + a - 6] - m.cfg.x_ref[7 + a - 6]) : (w.x[NQ + a - NV] - m.cfg.x_ref[NQ + a - NV]);
   }
   if (gap_out) {
-    PAR_FOR(i, NJ) { w.xnext[7 + i] = w.x[7 + i] + w.dx[6 + i]; gap_out[6 + i] = w.fbr[6 + i] = w.xnext[7 + i] - w.xn[7 + i]; }
-    PAR_FOR(i, NV) { w.xnext[NQ + i] = w.x[NQ + i] + w.dx[NV + i]; gap_out[NV + i] = w.fbr[NV + i] = w.xnext[NQ + i] - w.xn[NQ + i]; }
+    PAR_FOR(i, NJ) { w.xnext[7 + i] = w.x[7 + i] + w.dx[6 + i]; if (ROLL) w.xn[7 + i] = w.xnext[7 + i] + slack[6 + i]; gap_out[6 + i] = w.fbr[6 + i] = w.xnext[7 + i] - w.xn[7 + i]; }
+    PAR_FOR(i, NV) { w.xnext[NQ + i] = w.x[NQ + i] + w.dx[NV + i]; if (ROLL) w.xn[NQ + i] = w.xnext[NQ + i] + slack[NV + i]; gap_out[NV + i] = w.fbr[NV + i] = w.xnext[NQ + i] - w.xn[NQ + i]; }
   }
   SYNC();
   if (!derivs) return;
@@ -349,7 +357,7 @@ HD double vplus_row(int type, double h, double ve, double mu, double lo, double 
 }
 
 // ------------------------------------------------------------------ running knot
-template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io, FullWsT<DERIV> &w) {
+template <bool DERIV, bool ROLL = false> HD void eval_full_knot(const DevModel &m, const KnotIO &io, FullWsT<DERIV> &w) {
   EPH_DECL;
   const mpc_robot_t &rb = m.rb;
   const mpc_config_t &cfg = m.cfg;
@@ -722,7 +730,8 @@ template <bool DERIV> HD void eval_full_knot(const DevModel &m, const KnotIO &io
   PAR_FOR(i, FNC) { w.mv[i] = io.v[i]; w.mvp[i] = io.v_prev[i]; }
   PAR_FOR(i, FN) { w.mln[i] = io.lam_n[i]; w.mlnp[i] = io.lam_n_prev[i]; w.mlk[i] = io.lam_k[i]; }
   SYNC();
-  mb_cost_terms(m, w, kn.lf_ref, kn.rf_ref, DERIV, io.gap);
+  mb_cost_terms<FullWsT<DERIV>, ROLL>(m, w, kn.lf_ref, kn.rf_ref, DERIV, io.gap, io.slack);
+  if (ROLL) PAR_FOR(i, NQ + NV) io.xn_out[i] = w.xn[i];
 
   EPH(10);
   if (DERIV) {

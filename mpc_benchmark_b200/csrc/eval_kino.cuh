@@ -54,7 +54,7 @@ HD double kino_c_entry(const DevModel &m, const double *Cvel, int r, int z) {
   return (z < FN) ? Cvel[(6 * f + rr - 17) * FN + z] : 0.0;
 }
 
-template <bool DERIV> HD void eval_kino_knot(const DevModel &m, const KnotIO &io, KinoWsT<DERIV> &w) {
+template <bool DERIV, bool ROLL = false> HD void eval_kino_knot(const DevModel &m, const KnotIO &io, KinoWsT<DERIV> &w) {
   const mpc_robot_t &rb = m.rb;
   const mpc_config_t &cfg = m.cfg;
   const double dt = cfg.dt;
@@ -254,7 +254,8 @@ template <bool DERIV> HD void eval_kino_knot(const DevModel &m, const KnotIO &io
   // ---- semi-implicit Euler + gap + cost terms
   PAR_FOR(i, NV) { double dv = dt * w.acc[i]; w.dx[NV + i] = dv; w.dx[i] = dt * (w.x[NQ + i] + dv); }
   SYNC();
-  mb_cost_terms(m, w, kn.lf_ref, kn.rf_ref, DERIV, io.gap);
+  mb_cost_terms<KinoWsT<DERIV>, ROLL>(m, w, kn.lf_ref, kn.rf_ref, DERIV, io.gap, io.slack);
+  if (ROLL) PAR_FOR(i, NQ + NV) io.xn_out[i] = w.xn[i];
 
   // ---- constraint values, multiplier estimates, activity
   // every thread accumulates the merit pieces of the rows / coordinates it owns; one group-wide reduction at the end

@@ -72,6 +72,18 @@ __global__ void k_decide_eval(Ws w, const int32_t *list, int32_t *next_eval) {
   decide_eval(w, list[blockIdx.x], red, next_eval);
 }
 
+// ROLLOUT_NONLINEAR: nonlinear forward rollout and the complete Armijo linesearch of one instance per CTA (one evaluation group:
+// the knots are visited in sequence, each trial state is produced by the previous knot's dynamics)
+template <int KIND> struct RolloutShape {
+  static constexpr int TH = EvalShape<KIND, false>::TH;
+  static constexpr size_t smem = EvalShape<KIND, false>::slice + 256 * sizeof(double);
+};
+template <int KIND> __global__ void __launch_bounds__(RolloutShape<KIND>::TH) k_rollout_ls(Ws w, const int32_t *list, int32_t *next_eval) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double red[8];
+  rollout_linesearch<KIND>(w, list[blockIdx.x], smem_raw, reinterpret_cast<double *>(smem_raw + EvalShape<KIND, false>::slice), red, next_eval);
+}
+
 template <int KIND> __global__ void __launch_bounds__(256) k_riccati(Ws w, const int32_t *list) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   riccati_dispatch<KIND>(w, list[blockIdx.x], reinterpret_cast<double *>(smem_raw));
@@ -185,6 +197,13 @@ struct CudaBackend {
     else if (h->w.kind == MPC_KIND_KINO) k_riccati<MPC_KIND_KINO><<<n, h->ric_threads, h->ric_smem, s>>>(h->w, list);
     else k_riccati<MPC_KIND_CENT><<<n, h->ric_threads, h->ric_smem, s>>>(h->w, list);
   }
+  void rollout_ls(const int32_t *list, int n, int32_t *next_eval) {
+    mark(2);
+    if (h->w.kind == MPC_KIND_FULL) k_rollout_ls<MPC_KIND_FULL><<<n, RolloutShape<MPC_KIND_FULL>::TH, RolloutShape<MPC_KIND_FULL>::smem, s>>>(h->w, list, next_eval);
+    else if (h->w.kind == MPC_KIND_KINO) k_rollout_ls<MPC_KIND_KINO><<<n, RolloutShape<MPC_KIND_KINO>::TH, RolloutShape<MPC_KIND_KINO>::smem, s>>>(h->w, list, next_eval);
+    else k_rollout_ls<MPC_KIND_CENT><<<n, RolloutShape<MPC_KIND_CENT>::TH, RolloutShape<MPC_KIND_CENT>::smem, s>>>(h->w, list, next_eval);
+    mark(-1);
+  }
   void apply_step(const int32_t *list, int n) { mark(3); k_apply_step<<<n, 128, 0, s>>>(h->w, list); }
   void decide_ls(const int32_t *list, int n, int32_t *ls_out, int32_t *next_eval) { mark(3); k_decide_ls<<<n, 128, 0, s>>>(h->w, list, ls_out, next_eval); mark(-1); }
   void read_counters(int *c) {
@@ -208,6 +227,9 @@ static int set_kernel_attrs(mpc_solver *h) {
   EVAL_ATTR(MPC_KIND_FULL, true); EVAL_ATTR(MPC_KIND_FULL, false); EVAL_ATTR(MPC_KIND_KINO, true); EVAL_ATTR(MPC_KIND_KINO, false);
   EVAL_ATTR(MPC_KIND_CENT, true); EVAL_ATTR(MPC_KIND_CENT, false);
 #undef EVAL_ATTR
+  CK(cudaFuncSetAttribute(k_rollout_ls<MPC_KIND_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RolloutShape<MPC_KIND_FULL>::smem));
+  CK(cudaFuncSetAttribute(k_rollout_ls<MPC_KIND_KINO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RolloutShape<MPC_KIND_KINO>::smem));
+  CK(cudaFuncSetAttribute(k_rollout_ls<MPC_KIND_CENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RolloutShape<MPC_KIND_CENT>::smem));
   CK(cudaFuncSetAttribute(k_riccati<MPC_KIND_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, RicFastLayout<56, 22, 78, FULL_NCAP>::total * 8));
   CK(cudaFuncSetAttribute(k_riccati<MPC_KIND_KINO>, cudaFuncAttributeMaxDynamicSharedMemorySize, RicFastLayout<56, 34, 68, KINO_NCAP>::total * 8));
   return 0;
@@ -233,7 +255,7 @@ mpc_solver_t *mpc_create(const mpc_robot_t *robot, const mpc_config_t *cfg, int3
   w.B = batch; w.T = cfg->T; w.kind = cfg->kind;
   dims_of_kind(cfg->kind, w.nx, w.n, w.m, w.nc);
   w.nz = w.n + w.m;
-  w.sc = default_consts(cfg->tol, cfg->mu_init);
+  w.sc = default_consts(cfg->tol, cfg->mu_init, cfg->rollout);
   // every failure below releases what was created so far through mpc_destroy (all members start null)
   auto bail = [&](const char *what, cudaError_t e) -> mpc_solver_t * { g_err = std::string(what) + ": " + cudaGetErrorString(e); mpc_destroy(h); return nullptr; };
   cudaError_t e;
@@ -354,7 +376,7 @@ int32_t mpc_reconfigure(mpc_solver_t *h, const mpc_robot_t *robot, const mpc_con
   if (cfg->kind != h->w.kind || cfg->T != h->w.T) return fail("mpc_reconfigure: kind / horizon must not change");
   const char *err = nullptr;
   if (build_dev_model(robot, cfg, &h->h_model, &err)) return fail(err);
-  h->w.sc = default_consts(cfg->tol, cfg->mu_init);
+  h->w.sc = default_consts(cfg->tol, cfg->mu_init, cfg->rollout);
   CK(cudaMemcpyAsync(h->d_model, &h->h_model, sizeof(DevModel), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return 0;

@@ -26,13 +26,15 @@ struct SolverConst {
   double reg_init, reg_min, reg_max, reg_inc, reg_dec;
   double ls_c1, ls_alpha_min, ls_contr_min, ls_contr_max, ls_dphi_rel;
   int ls_max_steps;
+  int rollout; // 0 ROLLOUT_LINEAR (every reference script), 1 ROLLOUT_NONLINEAR (fused rollout + linesearch kernel)
 };
-inline SolverConst default_consts(double tol, double mu_init) {
+inline SolverConst default_consts(double tol, double mu_init, int rollout = 0) {
   SolverConst c;
   c.tol = tol; c.mu_init = mu_init; c.max_al_iters = 100;
   c.prim_alpha = 0.1; c.prim_beta = 0.9; c.dual_alpha = 1.0; c.dual_beta = 1.0; c.mu_update_factor = 0.01; c.mu_lower_bound = 1e-8;
   c.reg_init = 1e-9; c.reg_min = 1e-10; c.reg_max = 1e9; c.reg_inc = 10.0; c.reg_dec = 1.0 / 3.0;
   c.ls_c1 = 1e-4; c.ls_alpha_min = 1e-7; c.ls_contr_min = 0.5; c.ls_contr_max = 0.8; c.ls_max_steps = 20; c.ls_dphi_rel = 1e-11;
+  c.rollout = rollout;
   return c;
 }
 
@@ -86,6 +88,7 @@ HD KnotIO make_io(const Ws &w, int b, int k, bool trial) {
   io.gap = w.gap + kT * w.n; io.h = w.h + kb * w.nc; io.scal = (trial ? w.tscal : w.scal) + kb * SC_COUNT;
   io.xdot = w.xdot + kb * 56; io.lamc = w.lamc + kb * 12;
   io.scratch = (k < w.T) ? w.W + kT * w.n * w.nz : nullptr;
+  io.slack = nullptr; io.xn_out = nullptr;
   io.phase_out = (b == 0 && k == 1) ? w.phase + (trial ? 32 : 16) : nullptr;
   return io;
 }
@@ -249,7 +252,7 @@ HD void decide_ls(const Ws &w, int b, double *red, int32_t *ls_out, int32_t *nex
       s.alpha = fmax(a_new, c.ls_alpha_min);
       s.ls_it++;
     }
-    if (s.mode == MODE_LS) ls_out[ATOMIC_INC(&w.counters[0])] = b;
+    if (s.mode == MODE_LS) { if (ls_out) ls_out[ATOMIC_INC(&w.counters[0])] = b; } // (null: the fused rollout kernel loops by itself)
     else if (s.mode == MODE_EVAL) next_eval[ATOMIC_INC(&w.counters[2])] = b;
   }
   SYNC();
@@ -276,6 +279,102 @@ template <int KIND, bool DERIV> HD void eval_dispatch(const Ws &w, int b, int k,
   } else {
     CentWs &c = *reinterpret_cast<CentWs *>(smem);
     if (k < w.T) eval_cent_knot<DERIV>(*w.model, io, c); else eval_cent_term<DERIV>(*w.model, io, c);
+  }
+}
+
+// ---- ROLLOUT_NONLINEAR: one trial point of the fused rollout + linesearch kernel (one CTA = one evaluation group per instance).
+// The affine policy of the LQ solve is rolled out through the NONLINEAR dynamics, knot after knot (oracle: Solver::try_step_nonlinear):
+//   dx_k = x+_k (-) x_k,  du = alpha ku + Ku dx_k,  dv = alpha kv + Kv dx_k (active rows; alpha dbar/mu otherwise),
+//   dlam' = alpha pt + W [dx_k; du],  x+_{k+1} = f(x+_k, u+_k) (+) mu_d (lam_e - lam'+)   (set inside the knot evaluation),
+// and every knot's merit terms land in tscal exactly as in a linear-rollout trial, so decide_ls applies unchanged.
+// xv: >= 64 + 96 + 64 doubles of shared memory next to the evaluation workspace.
+template <int KIND> HD void rollout_trial(const Ws &w, int b, double alpha, void *smem, double *xv) {
+  const size_t T1 = (size_t)w.T + 1;
+  const int n = w.n, m = w.m, nc = w.nc, nz = w.nz, nx = w.nx, NRk = 1 + n, S = m + nc, T = w.T;
+  const int ldw = (KIND == MPC_KIND_CENT) ? nz : ((nz + 7) & ~7);
+  double *dx = xv, *z = xv + 64, *slack = xv + 160;
+  const double mu = w.st[b].mu, mu_d = mu;
+  const double *xs = w.xs + b * T1 * nx, *us = w.us + (size_t)b * T * m, *vs = w.vs + b * T1 * nc, *lams = w.lams + b * T1 * n;
+  double *txs = w.txs + b * T1 * nx, *tus = w.tus + (size_t)b * T * m, *tvs = w.tvs + b * T1 * nc, *tlams = w.tlams + b * T1 * n;
+  const double *lams_prev = w.lams_prev + b * T1 * n, *dbar = w.dbar + b * T1 * nc;
+  auto state_diff = [&](const double *x0, const double *x1) { // dx = x1 (-) x0
+    if (KIND == MPC_KIND_CENT) { PAR_FOR(i, n) dx[i] = x1[i] - x0[i]; }
+    else {
+      ONE_THREAD {
+        double M0[12], M1[12], D[12];
+        quat_to_R(x0 + 3, M0); M0[9] = x0[0]; M0[10] = x0[1]; M0[11] = x0[2];
+        quat_to_R(x1 + 3, M1); M1[9] = x1[0]; M1[10] = x1[1]; M1[11] = x1[2];
+        se3_inv_mul(M0, M1, D);
+        log6(D, dx);
+      }
+      PAR_FOR(i, NJ + NV) dx[6 + i] = x1[7 + i] - x0[7 + i];
+    }
+  };
+  PAR_FOR(i, nx) txs[i] = xs[i];
+  PAR_FOR(i, n) tlams[i] = lams[i] + alpha * w.dlams[b * T1 * n + i];
+  SYNC();
+  for (int k = 0; k <= T; k++) {
+    const size_t kb = b * T1 + k;
+    const int nca = w.nca[kb];
+    const int32_t *ai = w.act_idx + kb * nc;
+    state_diff(xs + (size_t)k * nx, txs + (size_t)k * nx);
+    PAR_FOR(r, nc) tvs[(size_t)k * nc + r] = vs[(size_t)k * nc + r] + alpha * dbar[(size_t)k * nc + r] / mu; // rows outside the active set
+    SYNC();
+    if (k == T) { // terminal rows: dv = (alpha dbar + C dx) / mu
+      const double *CT = w.CDact + kb * nc * nz;
+      PAR_FOR(a, nca) {
+        const int row = ai[a];
+        double t = alpha * dbar[(size_t)k * nc + row];
+        for (int j = 0; j < n; j++) t += CT[a * nz + j] * dx[j];
+        tvs[(size_t)k * nc + row] = vs[(size_t)k * nc + row] + t / mu;
+      }
+      SYNC();
+      KnotIO io = make_io(w, b, k, true);
+      if (KIND == MPC_KIND_FULL) eval_full_term<false>(*w.model, io, *reinterpret_cast<FullWsT<false> *>(smem));
+      else if (KIND == MPC_KIND_KINO) eval_kino_term<false>(*w.model, io, *reinterpret_cast<KinoWsT<false> *>(smem));
+      else eval_cent_term<false>(*w.model, io, *reinterpret_cast<CentWs *>(smem));
+      SYNC();
+      break;
+    }
+    const double *Kk = w.K + ((size_t)b * T + k) * S * NRk;
+    PAR_FOR(i, m + nca) {
+      double t = alpha * Kk[i * NRk];
+      for (int j = 0; j < n; j++) t += Kk[i * NRk + 1 + j] * dx[j];
+      if (i < m) { z[n + i] = t; tus[(size_t)k * m + i] = us[(size_t)k * m + i] + t; }
+      else { const int row = ai[i - m]; tvs[(size_t)k * nc + row] = vs[(size_t)k * nc + row] + t; }
+    }
+    PAR_FOR(j, n) z[j] = dx[j];
+    SYNC();
+    const double *Wk = w.W + (size_t)b * T * n * ((nz + 7) & ~7) + (size_t)k * n * ldw, // (instance stride as in make_riccati_io)
+                  *ptk = w.pt + ((size_t)b * T + k) * n;
+    PAR_FOR(i, n) {
+      double t = alpha * ptk[i];
+      for (int j = 0; j < nz; j++) t += Wk[i * ldw + j] * z[j];
+      const size_t id = (size_t)(k + 1) * n + i;
+      const double tl = lams[id] + t;
+      tlams[id] = tl;
+      slack[i] = mu_d * (lams_prev[id] - tl);
+    }
+    SYNC();
+    KnotIO io = make_io(w, b, k, true);
+    io.xn = io.x; io.slack = slack; io.xn_out = txs + (size_t)(k + 1) * nx;
+    if (KIND == MPC_KIND_FULL) eval_full_knot<false, true>(*w.model, io, *reinterpret_cast<FullWsT<false> *>(smem));
+    else if (KIND == MPC_KIND_KINO) eval_kino_knot<false, true>(*w.model, io, *reinterpret_cast<KinoWsT<false> *>(smem));
+    else eval_cent_knot<false, true>(*w.model, io, *reinterpret_cast<CentWs *>(smem));
+    SYNC();
+  }
+}
+// the whole linesearch of one instance: trial rollouts until decide_ls accepts (or gives up)
+template <int KIND> HD void rollout_linesearch(const Ws &w, int b, void *smem, double *xv, double *red /* shared, >= 8 */, int32_t *next_eval) {
+  for (int it = 0; it <= w.sc.ls_max_steps; it++) {
+    ONE_THREAD { red[2] = (double)w.st[b].mode; red[3] = w.st[b].alpha; }
+    SYNC();
+    const double mode = red[2], alpha = red[3];
+    SYNC();
+    if (mode != (double)MODE_LS) break;
+    rollout_trial<KIND>(w, b, alpha, smem, xv);
+    decide_ls(w, b, red, nullptr, next_eval);
+    SYNC();
   }
 }
 

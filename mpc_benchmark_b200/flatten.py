@@ -412,14 +412,18 @@ def _flatten_kino(problem, tol, mu_init, max_iters):
     return FlatProblem(rb, c, knots, terms, np.array(problem.x0_init, float).reshape(1, -1))
 
 
-def flatten_problem(problem, tol, mu_init, max_iters):
+def flatten_problem(problem, tol, mu_init, max_iters, rollout=0):
+    """rollout: solver.rollout_type (0 = ROLLOUT_LINEAR, fulldynamic_talos.py:381; 1 = ROLLOUT_NONLINEAR)."""
     if not problem.stages:
         raise ValueError("TrajOptProblem has no stages")
     ode = problem.stages[0].dynamics.differential_dynamics
     if isinstance(ode, api.CentroidalFwdDynamics):
-        return _flatten_cent(problem, tol, mu_init, max_iters)
-    if isinstance(ode, api.MultibodyConstraintFwdDynamics):
-        return _flatten_full(problem, tol, mu_init, max_iters)
-    if isinstance(ode, api.KinodynamicsFwdDynamics):
-        return _flatten_kino(problem, tol, mu_init, max_iters)
-    raise NotImplementedError(f"unsupported dynamics {type(ode).__name__}")
+        flat = _flatten_cent(problem, tol, mu_init, max_iters)
+    elif isinstance(ode, api.MultibodyConstraintFwdDynamics):
+        flat = _flatten_full(problem, tol, mu_init, max_iters)
+    elif isinstance(ode, api.KinodynamicsFwdDynamics):
+        flat = _flatten_kino(problem, tol, mu_init, max_iters)
+    else:
+        raise NotImplementedError(f"unsupported dynamics {type(ode).__name__}")
+    flat.cfg.rollout = int(rollout)
+    return flat

@@ -43,6 +43,14 @@ struct EmuBackend {
     double red[8];
     for (int i = 0; i < n; i++) mpcdev::decide_ls(w, list[i], red, ls_out, next_eval);
   }
+  void rollout_ls(const int32_t *list, int n, int32_t *next_eval) {
+    double red[8], xv[256];
+    for (int i = 0; i < n; i++) {
+      if (w.kind == MPC_KIND_FULL) rollout_linesearch<MPC_KIND_FULL>(w, list[i], smem.data(), xv, red, next_eval);
+      else if (w.kind == MPC_KIND_KINO) rollout_linesearch<MPC_KIND_KINO>(w, list[i], smem.data(), xv, red, next_eval);
+      else rollout_linesearch<MPC_KIND_CENT>(w, list[i], smem.data(), xv, red, next_eval);
+    }
+  }
   void read_counters(int *c) { for (int i = 0; i < 4; i++) c[i] = w.counters[i]; }
 };
 
@@ -58,7 +66,7 @@ extern "C" int emu_solve(const mpc_robot_t *rb, const mpc_config_t *cfg, int bat
   std::memset(&w, 0, sizeof w);
   w.B = batch; w.T = cfg->T; w.kind = cfg->kind;
   dims_of_kind(cfg->kind, w.nx, w.n, w.m, w.nc);
-  w.nz = w.n + w.m; w.model = model; w.sc = default_consts(cfg->tol, cfg->mu_init);
+  w.nz = w.n + w.m; w.model = model; w.sc = default_consts(cfg->tol, cfg->mu_init, cfg->rollout);
   std::vector<void *> allocs;
   alloc_ws(w, [&](size_t bytes) { void *p = calloc(bytes ? bytes : 8, 1); allocs.push_back(p); return p; });
   const size_t T1 = w.T + 1;

@@ -95,3 +95,26 @@ def test_kino_more_active_rows_than_fast_carving(oracle):
     e = emu_lib.solve(prob, 2, xs=xs, us=us)
     assert e["info"][0].status != 3 and e["info"][0].num_iters == r["info"][0].num_iters == 2
     assert rel(e["xs"], r["xs"]) < 1e-7 and rel(e["us"], r["us"]) < 1e-7 and rel(e["vs"], r["vs"]) < 1e-6
+
+
+@pytest.mark.parametrize("maker,T", [(problems.cent_standing_problem, 30), (problems.full_standing_problem, 12), (problems.kino_standing_problem, 12)])
+def test_nonlinear_rollout_cold_solve(oracle, maker, T):
+    """ROLLOUT_NONLINEAR (fused rollout + linesearch, solver_core.cuh rollout_trial) against the oracle's try_step_nonlinear."""
+    prob = maker(batch=2, T=T)
+    prob["cfg"].rollout = 1
+    r = oracle.solve(prob)
+    e = emu_lib.solve(prob, 100)
+    assert e["info"][1].num_iters == r["info"][1].num_iters and e["info"][1].ls_evals == r["info"][1].ls_evals and e["info"][1].conv == 1
+    assert rel(e["xs"], r["xs"]) < 1e-9 and rel(e["us"], r["us"]) < 1e-9 and rel(e["lams"], r["lams"]) < 1e-7
+
+
+def test_nonlinear_rollout_walking_with_backtracking(oracle):
+    """Walking fixture under ROLLOUT_NONLINEAR: active rows (their gains feed back through dx), several backtracking steps."""
+    prob, z = golden_util.load("walk_full.npz")
+    prob["cfg"].rollout = 1
+    r = oracle.solve(prob, max_iters=4)
+    e = emu_lib.solve(prob, 4)
+    assert [i.ls_evals for i in e["info"]] == [i.ls_evals for i in r["info"]] and max(i.ls_evals for i in r["info"]) > 4
+    assert rel(e["xs"], r["xs"]) < 1e-8 and rel(e["us"], r["us"]) < 1e-8 and rel(e["vs"], r["vs"]) < 1e-6
+    lin = oracle.solve(dict(prob, cfg=golden_util.load("walk_full.npz")[0]["cfg"]), max_iters=4)
+    assert rel(lin["xs"], r["xs"]) > 1e-9  # it really is a different rollout

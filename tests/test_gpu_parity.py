@@ -481,3 +481,55 @@ def test_stairs_batch_sample(oracle):
     sub["x0"], sub["xs"], sub["us"] = prob["x0"][pick], prob["xs"][pick], prob["us"][pick]
     ref = oracle.solve(sub, max_iters=3, inst_threads=4)
     assert rel(res.xs[pick], ref["xs"]) < RTOL and rel(res.us[pick], ref["us"]) < RTOL
+
+
+@pytest.mark.parametrize("maker,T", [(problems.cent_standing_problem, 100), (problems.full_standing_problem, 100), (problems.kino_standing_problem, 40)])
+def test_nonlinear_rollout_kernel_cold_solve(oracle, maker, T):
+    """ROLLOUT_NONLINEAR: the fused rollout + linesearch kernel (k_rollout_ls, one CTA per instance: nonlinear dynamics knot after
+    knot under the affine LQ policy, Armijo backtracking inside the kernel) against the oracle's try_step_nonlinear."""
+    prob = maker(batch=2, T=T)
+    prob["cfg"].rollout = 1
+    s = BatchSolver(prob["robot"], prob["cfg"], 2)
+    s.setup(prob["knots"], prob["terms"], prob["x0"])
+    res = s.run(prob["xs"], prob["us"], max_iters=100)
+    ref = oracle.solve(prob, max_iters=100, inst_threads=2)
+    assert list(res.num_iters) == [i.num_iters for i in ref["info"]] and list(res.conv) == [bool(i.conv) for i in ref["info"]]
+    assert [i.ls_evals for i in res.info] == [i.ls_evals for i in ref["info"]]
+    assert rel(res.xs, ref["xs"]) < RTOL and rel(res.us, ref["us"]) < RTOL and rel(res.K, ref["K"]) < 1e-5
+    s.close()
+
+
+def test_nonlinear_rollout_kernel_walking_backtracking(oracle):
+    """ROLLOUT_NONLINEAR on the walking fixture: active cone / box rows feed back through dx, the in-kernel linesearch backtracks."""
+    import golden_util
+
+    prob, z = golden_util.load("walk_full.npz")
+    prob["cfg"].rollout = 1
+    B = prob["x0"].shape[0]
+    s = BatchSolver(prob["robot"], prob["cfg"], B)
+    s.setup(prob["knots"], prob["terms"], prob["x0"])
+    res = s.run(prob["xs"], prob["us"], max_iters=4)
+    ref = oracle.solve(prob, max_iters=4, inst_threads=4)
+    assert [i.ls_evals for i in res.info] == [i.ls_evals for i in ref["info"]] and max(i.ls_evals for i in ref["info"]) > 4
+    assert rel(res.xs, ref["xs"]) < RTOL and rel(res.us, ref["us"]) < RTOL and rel(res.vs, ref["vs"]) < 1e-5
+    assert rel(res.xs, z["sol_xs"]) > 1e-9  # not the linear rollout's iterates
+    s.close()
+
+
+def test_nonlinear_rollout_through_the_shim(oracle):
+    """solver.rollout_type = ROLLOUT_NONLINEAR (aligator's default) through the public surface."""
+    import mpc_benchmark_b200 as aligator
+    from mpc_benchmark_b200 import flatten, pin
+    from test_reference_scripts import _build_cent
+
+    ns = _build_cent(aligator, pin, T=20)
+    solver = aligator.SolverProxDDP(1e-5, 1e-8)
+    assert solver.rollout_type == aligator.ROLLOUT_NONLINEAR
+    solver.max_iters = 100
+    solver.setup(ns["problem"])
+    conv = solver.run(ns["problem"], [ns["x0"]] * 21, [ns["u0"] for _ in range(20)])
+    flat = flatten.flatten_problem(ns["problem"], 1e-5, 1e-8, 100, rollout=1)
+    ref = oracle.solve(dict(robot=flat.robot, cfg=flat.cfg, knots=flat.knots, terms=flat.terms, x0=flat.x0,
+                            xs=np.tile(ns["x0"], (1, 21, 1)), us=np.tile(ns["u0"], (1, 20, 1))))
+    assert conv and solver.results.num_iters == ref["info"][0].num_iters
+    assert rel(np.array(solver.results.xs.tolist()), ref["xs"][0]) < RTOL and rel(np.array(solver.results.us.tolist()), ref["us"][0]) < RTOL

@@ -146,6 +146,8 @@ def test_unsupported_structures_raise_with_a_name():
     ns["problem"].stages[0].cost.addCost("bad", aligator.QuadraticStateCost(aligator.manifolds.VectorSpace(9), 12, np.zeros(9), np.eye(9)))
     with pytest.raises(NotImplementedError, match="QuadraticStateCost"):
         flatten.flatten_problem(ns["problem"], 1e-5, 1e-8, 10)
-    s = aligator.SolverProxDDP(1e-5, 1e-8)
-    with pytest.raises(NotImplementedError, match="ROLLOUT_LINEAR"):
-        s.setup(ns["problem"])  # default rollout is NONLINEAR, as in aligator; the scripts set LINEAR
+    # the default rollout is NONLINEAR, as in aligator (the scripts set LINEAR): it flattens to cfg.rollout = 1
+    assert aligator.SolverProxDDP(1e-5, 1e-8).rollout_type == aligator.ROLLOUT_NONLINEAR
+    ns2 = _build_cent(aligator, pin)
+    assert flatten.flatten_problem(ns2["problem"], 1e-5, 1e-8, 10, rollout=1).cfg.rollout == 1
+    assert flatten.flatten_problem(ns2["problem"], 1e-5, 1e-8, 10).cfg.rollout == 0
