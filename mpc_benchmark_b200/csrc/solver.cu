@@ -219,7 +219,7 @@ static int set_kernel_attrs(mpc_solver *h) {
   else if (h->w.kind == MPC_KIND_KINO) { h->eval_smem = sizeof(KinoWsT<true>); h->eval_smem_values = sizeof(KinoWsT<false>); h->eval_threads = 128;
     h->ric_smem = RicFastLayout<56, 34, 68, KINO_NCAP>::total * 8; h->ric_threads = 256; }
   else { h->eval_smem = h->eval_smem_values = sizeof(CentWs); h->eval_threads = 32; h->ric_smem = riccati_smem_doubles<9, 12, 34>() * 8; h->ric_threads = 128; }
-  if (const char *e = getenv("MPCB200_RIC_THREADS")) { int t = atoi(e); if (t >= 128 && t <= 256) { h->ric_threads = t; h->ric_threads_auto = false; } }
+  if (const char *e = getenv("MPCB200_RIC_THREADS")) { int t = atoi(e); if (t >= 32 && t <= 256 && (t >= 128 || h->w.kind == MPC_KIND_CENT)) { h->ric_threads = t; h->ric_threads_auto = false; } }
   { int dev = 0, sms = 0; if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) h->num_sms = sms; }
   static_assert(RicFastLayout<56, 22, 78, FULL_NCAP>::total * 8 <= 232448 && RicFastLayout<56, 34, 68, KINO_NCAP>::total * 8 <= 232448,
                 "Riccati shared memory exceeds the 227 KB opt-in limit");
