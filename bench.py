@@ -434,13 +434,13 @@ def hbm_peak_gbs():
 
 def measured_traffic(batch):
     """DRAM bytes of one k_riccati launch at this batch, scaled per instance from the committed `ncu --set full` capture
-    (profiles/r1_traffic.json; instances are independent CTAs, so the traffic is linear in the batch)."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    (profiles/r2_traffic.json; instances are independent CTAs, so the traffic is linear in the batch)."""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
     try:
         with open(path) as f:
             t = json.load(f)
         per_inst = (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["batch"]
-        return per_inst * batch, f"profiles/r1_traffic.json: {per_inst / 1e6:.1f} MB/instance measured at batch {t['batch']} (algorithmic {t['algorithmic_bytes_per_instance'] / 1e6:.1f} MB), scaled to batch {batch}"
+        return per_inst * batch, f"profiles/r2_traffic.json: {per_inst / 1e6:.1f} MB/instance measured at batch {t['batch']} (algorithmic {t['algorithmic_bytes_per_instance'] / 1e6:.1f} MB), scaled to batch {batch}"
     except (OSError, KeyError, ValueError):
         return None, None
 
