@@ -32,6 +32,7 @@
 #define MBAR_WAIT(bar, parity) ((void)0)
 #define FENCE_PROXY_ASYNC() ((void)0)
 #define PREFETCH_L2(ptr, bytes) ((void)0)
+#define PREFETCH_LINES(ptr, bytes) ((void)0)
 #define LDCG(p) (*(p))
 #define LANE_ID 0
 #define LANE_IS(r) true
@@ -83,6 +84,8 @@ inline double2 make_double2(double x, double y) { return double2{x, y}; }
 // bulk prefetch of a contiguous global block into L2 (one instruction; address and size multiples of 16 bytes)
 #define PREFETCH_L2(ptr, bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"((unsigned)(bytes)) : "memory")
 #define LDCG(p) __ldcg(p)
+// the same for blocks without 16-byte alignment: one prefetch.global.L2 per 128-byte line, spread over the threads of the group
+#define PREFETCH_LINES(ptr, bytes) do { const char *p_ = reinterpret_cast<const char *>(ptr); for (int o_ = threadIdx.x * 128; o_ < (int)(bytes); o_ += blockDim.x * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p_ + o_)); } while (0)
 #define LANE_ID ((int)(threadIdx.x & 31))
 // "lane r finishes row r" after a butterfly reduction: values the finishing lane needs are loaded before the reduction
 // (PRELOADED: the early copy on the device; the host emulation has one "lane" that finishes every row and loads on the spot)
@@ -451,6 +454,9 @@ HD void chol_diag_block(double *A, int k0, int bw, int ld, double *Di) {
       Di[r * CB + c] = (r < bw && c < bw) ? X[r][c] : 0.0;
     }
 }
+#ifdef MPC_HOST_EMU
+inline double fast_rcp(double a) { return 1.0 / a; }
+#endif
 #ifndef MPC_HOST_EMU
 // 1/a for the pivot chain: hardware seed (rcp.approx.ftz.f64, ~20 bits) + two Newton steps = 56 cycles of dependent latency
 // on sm_100a, against 77 for rsqrt() and 83 for a division (tools/ubench/lat.cu).
@@ -523,6 +529,56 @@ __device__ __forceinline__ void chol_diag_block_warp0(double *A, int k0, int bw,
 #else
 #define DIAG_BLOCK(A, k0, bw, ld, Di) chol_diag_block(A, k0, bw, ld, Di)
 #endif
+
+// Small SPD systems (n <= 12: the centroidal model's 9 x 9 and 12 x 12 blocks): A X = B solved in place in B1 (n x n1, ld1) and
+// B2 (n x n2, ld2).  ONE thread factors A = Lt D Lt' in registers (square-root-free pivot chain, as in the 8 x 8 diagonal blocks;
+// a blocked factorisation would spend a whole padded 8 x 8 block on the ninth row) and leaves Lt (unit lower) / 1/d in A; then
+// every right-hand-side column is one thread's forward / diagonal / backward substitution with broadcast loads of the factor.
+// Two barriers instead of the ~10 of chol_blocked + trsm_blocked at this size.
+template <int n> HD void small_spd_solve(double *A, int ld, double *B1, int n1, int ld1, double *B2, int n2, int ld2) {
+  ONE_THREAD {
+    double L[n][n];
+#pragma unroll
+    for (int r = 0; r < n; r++)
+#pragma unroll
+      for (int c = 0; c <= r; c++) L[r][c] = A[r * ld + c];
+#pragma unroll
+    for (int j = 0; j < n; j++) {
+      const double rj = fast_rcp(L[j][j]);
+      A[j * ld + j] = rj;
+      double tcol[n];
+#pragma unroll
+      for (int r = j + 1; r < n; r++) { tcol[r] = L[r][j] * rj; A[r * ld + j] = tcol[r]; }
+#pragma unroll
+      for (int r = j + 1; r < n; r++)
+#pragma unroll
+        for (int c = j + 1; c <= r; c++) L[r][c] -= tcol[r] * L[c][j];
+    }
+  }
+  SYNC();
+  PAR_FOR(col, n1 + n2) {
+    double *b = (col < n1) ? B1 + col : B2 + (col - n1);
+    const int lb = (col < n1) ? ld1 : ld2;
+    double y[n];
+#pragma unroll
+    for (int i = 0; i < n; i++) y[i] = b[i * lb];
+#pragma unroll
+    for (int j = 0; j < n; j++) {
+#pragma unroll
+      for (int i = j + 1; i < n; i++) y[i] -= A[i * ld + j] * y[j];
+    }
+#pragma unroll
+    for (int j = 0; j < n; j++) y[j] *= A[j * ld + j];
+#pragma unroll
+    for (int j = n - 1; j >= 0; j--) {
+#pragma unroll
+      for (int i = 0; i < j; i++) y[i] -= A[j * ld + i] * y[j];
+    }
+#pragma unroll
+    for (int i = 0; i < n; i++) b[i * lb] = y[i];
+  }
+  SYNC();
+}
 
 // Blocked Cholesky (lower, in place): per 8-wide panel, one thread factors + inverts the diagonal block, the panel below it
 // is multiplied by the inverse, and the trailing matrix is updated on 2 x 2 register tiles.  (The 56 x 56 and padded control

@@ -82,7 +82,8 @@ template <int N, int M, int NC> constexpr int riccati_smem_doubles() {
 }
 
 // Backward + forward sweep for one instance.  ws: riccati_smem_doubles<N,M,NC>() doubles of shared memory.
-template <int N, int M, int NC> HD void riccati_instance(const RiccatiIO &io, double *ws) {
+// LIE6: the first 6 state coordinates live on SE(3) (E-normalisation by T6); false for vector-space models (centroidal: T6 = I)
+template <int N, int M, int NC, bool LIE6 = true> HD void riccati_instance(const RiccatiIO &io, double *ws) {
   constexpr int NZ = N + M, NR = 1 + N, S = M + NC;
   const int T = io.T;
   const double mu = io.mu, mu_d = io.mu_d;
@@ -118,13 +119,17 @@ template <int N, int M, int NC> HD void riccati_instance(const RiccatiIO &io, do
   for (int k = T - 1; k >= 0; k--) {
     const double *gAB = io.AB + (size_t)k * N * NZ, *gH = io.H + (size_t)k * NZ * NZ;
     const int nca = io.nca[k];
+    if (k >= 2) { // the loads below are on the knot's critical path: pull the blocks of knot k - 2 from HBM into L2 now
+      PREFETCH_LINES(io.AB + (size_t)(k - 2) * N * NZ, N * NZ * 8); PREFETCH_LINES(io.H + (size_t)(k - 2) * NZ * NZ, NZ * NZ * 8);
+      PREFETCH_LINES(io.g + (size_t)(k - 2) * NZ, NZ * 8); PREFETCH_LINES(io.fbar + (size_t)(k - 2) * N, N * 8);
+    }
     // 1. load; P <- T' P T, p <- T' p
     PAR_FOR(e, N * N) { int i = e / N, j = e % N; P[e] = H[i * NZ + j]; }
-    PAR_FOR(e, 36) T6[e] = io.T6[(size_t)k * 36 + e];
+    if (LIE6) PAR_FOR(e, 36) T6[e] = io.T6[(size_t)k * 36 + e];
     PAR_FOR(i, N) fb[i] = io.fbar[(size_t)k * N + i];
     PAR_FOR(e, N * NZ) AB[e] = gAB[e];
     SYNC();
-    if (N >= 6) {
+    if (LIE6 && N >= 6) {
       PAR_FOR(e, N * 6) { int i = e / 6, j = e % 6; double s = 0; for (int l = 0; l < 6; l++) s += P[i * N + l] * T6[6 * l + j]; W[e] = s; }
       SYNC();
       PAR_FOR(e, N * 6) { int i = e / 6, j = e % 6; P[i * N + j] = W[e]; }
@@ -140,9 +145,12 @@ template <int N, int M, int NC> HD void riccati_instance(const RiccatiIO &io, do
     PAR_FOR(e, N * N) G[e] = mu_d * P[e] + ((e / N == e % N) ? 1.0 : 0.0);
     PAR_FOR(i, N) { double s = p[i]; for (int j = 0; j < N; j++) s += P[i * N + j] * fb[j]; pt[i] = s; }
     SYNC();
-    chol_blocked(G, N, N, dinv);
-    trsm_blocked(G, N, N, dinv, P, N, N);
-    trsm_blocked(G, N, N, dinv, pt, 1, 1);
+    if (N <= 12) small_spd_solve<(N <= 12 ? N : 1)>(G, N, P, N, N, pt, 1, 1);
+    else {
+      chol_blocked(G, N, N, dinv);
+      trsm_blocked(G, N, N, dinv, P, N, N);
+      trsm_blocked(G, N, N, dinv, pt, 1, 1);
+    }
     // 3. W = Pt [A B];  H = H_k + [A B]' W;  gh = g + [A B]' pt
     PAR_FOR(e, NZ * NZ) H[e] = gH[e];
     gemm_par<false>(N, NZ, N, P, N, AB, NZ, W, NZ, 0.0);
@@ -164,8 +172,11 @@ template <int N, int M, int NC> HD void riccati_instance(const RiccatiIO &io, do
       Z[i * ncol + c] = (c == 0) ? gh[N + i] : (c < NR ? H[(c - 1) * NZ + N + i] : CD[(c - NR) * NZ + N + i]);
     }
     SYNC();
-    chol_blocked(Rh, M, M, dinv);
-    trsm_blocked(Rh, M, M, dinv, Z, ncol, ncol);
+    if (M <= 12) small_spd_solve<(M <= 12 ? M : 1)>(Rh, M, Z, ncol, ncol, nullptr, 0, 0);
+    else {
+      chol_blocked(Rh, M, M, dinv);
+      trsm_blocked(Rh, M, M, dinv, Z, ncol, ncol);
+    }
     // Schur complement Sg = mu I + D Z_D ; right-hand side Kv = [dbar | C] - D [Z_r | Z_S]
     PAR_FOR(e, nca * nca) {
       int r = e / nca, c = e % nca;
@@ -217,6 +228,10 @@ template <int N, int M, int NC> HD void riccati_instance(const RiccatiIO &io, do
     const int32_t *ai = io.act_idx + (size_t)k * NC;
     const double *gdb = io.dbar + (size_t)k * NC, *gvp = io.vplus + (size_t)k * NC, *gv = io.v + (size_t)k * NC;
     double *gdv = io.dvs + (size_t)k * NC;
+    if (k + 2 < T) {
+      PREFETCH_LINES(io.K + (size_t)(k + 2) * S * NR, (M + io.nca[k + 2]) * NR * 8); PREFETCH_LINES(io.AB + (size_t)(k + 2) * N * NZ, N * NZ * 8);
+      PREFETCH_LINES(io.W + (size_t)(k + 2) * N * NZ, N * NZ * 8);
+    }
     if (k < T) {
       const double *gK = io.K + (size_t)k * S * NR;
       PAR_FOR(i, M + nca) {
@@ -226,7 +241,7 @@ template <int N, int M, int NC> HD void riccati_instance(const RiccatiIO &io, do
       }
       PAR_FOR(i, N) z[i] = dx[i];
       PAR_FOR(e, N * NZ) { AB[e] = io.AB[(size_t)k * N * NZ + e]; W[e] = io.W[(size_t)k * N * NZ + e]; }
-      PAR_FOR(e, 36) T6[e] = io.T6[(size_t)k * 36 + e];
+      if (LIE6) PAR_FOR(e, 36) T6[e] = io.T6[(size_t)k * 36 + e];
     } else {
       const double *CT = io.CDact + (size_t)T * NC * NZ;
       PAR_FOR(r, nca) { double s = gdb[ai[r]]; for (int j = 0; j < N; j++) s += CT[r * NZ + j] * dx[j]; dva[r] = s / mu; }
@@ -255,7 +270,7 @@ template <int N, int M, int NC> HD void riccati_instance(const RiccatiIO &io, do
     SYNC();
     PAR_FOR(i, N) {
       double s;
-      if (N >= 6 && i < 6) { s = 0; for (int l = 0; l < 6; l++) s += T6[6 * i + l] * tmp[l]; } else s = tmp[i];
+      if (LIE6 && N >= 6 && i < 6) { s = 0; for (int l = 0; l < 6; l++) s += T6[6 * i + l] * tmp[l]; } else s = tmp[i];
       dx[i] = s; io.dxs[(size_t)(k + 1) * N + i] = s;
     }
     SYNC();

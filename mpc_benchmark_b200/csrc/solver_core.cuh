@@ -399,7 +399,7 @@ template <int KIND> HD void riccati_dispatch(const Ws &w, int b, double *smem) {
   RiccatiIO r = make_riccati_io(w, b);
   if (KIND == MPC_KIND_FULL) riccati_instance_fast<56, 22, 78, FULL_NCAP>(r, smem);
   else if (KIND == MPC_KIND_KINO) riccati_instance_fast<56, 34, 68, KINO_NCAP>(r, smem);
-  else riccati_instance<9, 12, 34>(r, smem);
+  else riccati_instance<9, 12, 34, false>(r, smem);
   ONE_THREAD { if (w.overflow[b]) { w.st[b].status = 3; w.st[b].mode = MODE_DONE; w.overflow[b] = 0; } }
   SYNC();
   start_linesearch(w, b);
