@@ -460,15 +460,13 @@ inline double fast_rcp(double a) { return 1.0 / a; }
 #ifndef MPC_HOST_EMU
 // 1/a for the pivot chain: hardware seed (rcp.approx.ftz.f64, ~20 bits) + two Newton steps = 56 cycles of dependent latency
 // on sm_100a, against 77 for rsqrt() and 83 for a division (tools/ubench/lat.cu).
-__device__ __forceinline__ double fast_rcp(double a) {
+__device__ __forceinline__ double fast_rcp(double a) { // (pivots of SPD blocks: normal range; a non-positive or NaN pivot still ends in NaN)
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
   double e = fma(-a, y, 1.0);
   y = fma(y, e, y);
   e = fma(-a, y, 1.0);
-  y = fma(y, e, y);
-  if (!(fabs(a) > 1e-30 && fabs(a) < 1e30)) y = 1.0 / a;
-  return y;
+  return fma(y, e, y);
 }
 // Device version called by ALL lanes of the group's warp 0.  Lane 0 runs the pivot chain in registers as a square-root-free
 // LDL' elimination (per column: reciprocal of the pivot -> scaled column -> update, 56 + 8.5 + 8.5 cycles of dependent
@@ -499,16 +497,20 @@ __device__ __forceinline__ void chol_diag_block_warp0(double *A, int k0, int bw,
   __syncwarp();
   double Lf[CB][CB], dd[CB], X[CB], lcol[CB];
   const int c = lane & 7;
+  const double pc = Di[c * CB + c];
+  const double rc = rsqrt(pc); // one rsqrt per lane; the eight values are exchanged through the (free) first row of Di's upper triangle + slot 15
 #pragma unroll
   for (int i = 0; i < CB; i++) {
-    dd[i] = rsqrt(Di[i * CB + i]);
     lcol[i] = Di[i * CB + c]; // own column of Lt (rows below the diagonal; the diagonal slot holds the pivot)
 #pragma unroll
     for (int t = 0; t < CB; t++) Lf[i][t] = (t < i) ? Di[i * CB + t] : 0.0;
   }
-  const double pc = Di[c * CB + c];
   __syncwarp();
-  const double sc = pc * rsqrt(pc); // sqrt(d_c)
+  if (lane < CB) Di[(c == 0) ? 15 : c] = rc; // slots (0,1..7) and (1,7): above the diagonal, never read as factor entries
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < CB; i++) dd[i] = Di[(i == 0) ? 15 : i];
+  const double sc = pc * rc; // sqrt(d_c)
 #pragma unroll
   for (int t = 0; t < CB; t++) X[t] = (t == c) ? 1.0 : 0.0;
 #pragma unroll
@@ -516,6 +518,7 @@ __device__ __forceinline__ void chol_diag_block_warp0(double *A, int k0, int bw,
 #pragma unroll
     for (int i = t + 1; i < CB; i++) X[i] -= Lf[i][t] * X[t]; // rows above the diagonal stay 0
   }
+  __syncwarp();
   if (lane < CB) {
 #pragma unroll
     for (int i = 0; i < CB; i++) {

@@ -438,15 +438,21 @@ template <int NB> HD void chol_mma(double *A, int ld, double *Dinv) {
     const double *Di = Dinv + 64 * kb;
     WARP_TILE_FOR(p, nt) tile_trsm(A, ld, 8 * (kb + 1 + p), k0, Di);
     SYNC();
-    WARP_TILE_FOR(p, nt) tile_syrk(A, ld, 8 * (kb + 1 + p), 8 * (kb + 1), k0);
-    SYNC();
+    // warp 0: the next diagonal tile's update, then its factorisation — the serial chain of the whole factorisation never leaves this warp
+    // between two block barriers; the other warps: the rest of the next panel's column and of the trailing matrix
+    if (IS_WARP0) tile_syrk(A, ld, 8 * (kb + 1), 8 * (kb + 1), k0);
+    WARP_SYNC();
     DIAG_BLOCK(A, 8 * (kb + 1), 8, ld, Dinv + 64 * (kb + 1));
     const int m = nt - 1;
-    WARP_TILE_FOR_REST(p, m * (m + 1) / 2) {
-      int ti = 0;
-      while ((ti + 1) * (ti + 2) / 2 <= p) ti++;
-      const int tj = p - ti * (ti + 1) / 2;
-      tile_syrk(A, ld, 8 * (kb + 2 + ti), 8 * (kb + 2 + tj), k0);
+    WARP_TILE_FOR_REST(p, m + m * (m + 1) / 2) {
+      if (p < m) tile_syrk(A, ld, 8 * (kb + 2 + p), 8 * (kb + 1), k0);
+      else {
+        const int q = p - m;
+        int ti = 0;
+        while ((ti + 1) * (ti + 2) / 2 <= q) ti++;
+        const int tj = q - ti * (ti + 1) / 2;
+        tile_syrk(A, ld, 8 * (kb + 2 + ti), 8 * (kb + 2 + tj), k0);
+      }
     }
     SYNC();
   }
