@@ -103,6 +103,35 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 #endif
 
+
+// Reciprocal / square root without the library routines' special-case code (hardware seed + two Newton steps, <= 2 ulp).  The
+// library versions cost a single-lane dependency chain 80-130 cycles and dozens of (partly predicated) instructions per call; the
+// serial sections of the kernels (pivot chains, Lie-group routines) are made of exactly such calls (tools/ubench/lat.cu, diag.cu).
+// Arguments are positive and in the normal range at every call site; NaN / non-positive inputs still propagate as NaN.
+#ifdef MPC_HOST_EMU
+inline double rcp_(double a) { return 1.0 / a; }
+inline double rsqrt_(double a) { return 1.0 / sqrt(a); }
+inline double sqrt_(double a) { return sqrt(a); }
+#else
+__device__ __forceinline__ double rcp_(double a) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double e = fma(-a, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-a, y, 1.0);
+  return fma(y, e, y);
+}
+__device__ __forceinline__ double rsqrt_(double a) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double t = a * y, e = fma(-t, y, 1.0);
+  y = fma(0.5 * y, e, y);
+  t = a * y; e = fma(-t, y, 1.0);
+  return fma(0.5 * y, e, y);
+}
+__device__ __forceinline__ double sqrt_(double a) { return a * rsqrt_(a); } // a > 0
+#endif
+
 // ------------------------------------------------------------------ 3-vectors / 3x3 (row-major)
 HD void cross3(const double *a, const double *b, double *c) {
   double c0 = a[1] * b[2] - a[2] * b[1], c1 = a[2] * b[0] - a[0] * b[2], c2 = a[0] * b[1] - a[1] * b[0];
@@ -212,16 +241,17 @@ HD void so3_coeffs(double t2, double &a, double &b, double &c) {
   if (t2 < 1e-6) {
     a = 1.0 - t2 / 6 + t2 * t2 / 120; b = 0.5 - t2 / 24 + t2 * t2 / 720; c = 1.0 / 6 - t2 / 120 + t2 * t2 / 5040;
   } else {
-    double t = sqrt(t2), s, co;
+    double t = sqrt_(t2), s, co;
     sincos(t, &s, &co);
-    a = s / t; b = (1.0 - co) / t2; c = (t - s) / (t2 * t);
+    const double it = rcp_(t), it2 = it * it;
+    a = s * it; b = (1.0 - co) * it2; c = (t - s) * (it2 * it);
   }
 }
 HD double vinv_coeff(double t2) {
   if (t2 < 1e-6) return 1.0 / 12 + t2 / 720 + t2 * t2 / 30240;
-  double t = sqrt(t2), s, co;
+  double t = sqrt_(t2), s, co;
   sincos(t, &s, &co);
-  return (1.0 - t * s / (2.0 * (1.0 - co))) / t2;
+  return (1.0 - t * s * rcp_(2.0 * (1.0 - co))) * rcp_(t2);
 }
 HD void exp6(const double *xi, double *M) {
   const double *w = xi + 3;
@@ -237,7 +267,7 @@ HD void log3(const double *R, double *w) {
   double ct = (R[0] + R[4] + R[8] - 1.0) * 0.5;
   double s2 = dot3(s, s), f;
   if (s2 < 1e-6 && ct > 0) f = 1.0 + s2 / 6 + s2 * s2 * (3.0 / 40.0) + s2 * s2 * s2 * (15.0 / 336.0);
-  else { double sn = sqrt(s2); f = atan2(sn, ct) / sn; }
+  else { double sn = sqrt(s2); f = atan2(sn, ct) / sn; } // (s2 may be 0 at a half turn: library sqrt / division here)
   w[0] = s[0] * f; w[1] = s[1] * f; w[2] = s[2] * f;
 }
 HD void log6(const double *M, double *xi) {
@@ -256,9 +286,10 @@ HD void q_block(const double *rho, const double *phi, double *Q) {
   if (t2 < 1e-6) {
     c1 = 1.0 / 6 - t2 / 120 + t2 * t2 / 5040; c2 = 1.0 / 24 - t2 / 720 + t2 * t2 / 40320; c3 = 1.0 / 120 - t2 / 2520 + t2 * t2 / 120960;
   } else {
-    double t = sqrt(t2), s, c;
+    double t = sqrt_(t2), s, c;
     sincos(t, &s, &c);
-    c1 = (t - s) / (t2 * t); c2 = (t2 + 2 * c - 2) / (2 * t2 * t2); c3 = (2 * t - 3 * s + t * c) / (2 * t2 * t2 * t);
+    const double it = rcp_(t), it2 = it * it, it4 = it2 * it2;
+    c1 = (t - s) * (it2 * it); c2 = (t2 + 2 * c - 2) * (0.5 * it4); c3 = (2 * t - 3 * s + t * c) * (0.5 * it4 * it);
   }
   double P[9], Rr[9], PR[9], RP[9], PRP[9], PPR[9], RPP[9], PRPP[9], PPRP[9];
   skew3(phi, P); skew3(rho, Rr);
@@ -289,7 +320,7 @@ HD void Jlog6_from_log(const double *xi, double *J) { // xi = log6(M)
 }
 HD void quat_to_R(const double *q, double *R) {
   double x = q[0], y = q[1], z = q[2], w = q[3];
-  double n = x * x + y * y + z * z + w * w, s = 2.0 / n;
+  double n = x * x + y * y + z * z + w * w, s = 2.0 * rcp_(n);
   R[0] = 1 - s * (y * y + z * z); R[1] = s * (x * y - z * w); R[2] = s * (x * z + y * w);
   R[3] = s * (x * y + z * w); R[4] = 1 - s * (x * x + z * z); R[5] = s * (y * z - x * w);
   R[6] = s * (x * z - y * w); R[7] = s * (y * z + x * w); R[8] = 1 - s * (x * x + y * y);
@@ -297,14 +328,14 @@ HD void quat_to_R(const double *q, double *R) {
 HD void quat_integrate(const double *q, const double *w, double *out) {
   double t2 = dot3(w, w), sh, ch;
   if (t2 < 1e-6) { sh = 0.5 - t2 / 48 + t2 * t2 / 3840; ch = 1.0 - t2 / 8 + t2 * t2 / 384; }
-  else { double t = sqrt(t2), s, c; sincos(0.5 * t, &s, &c); sh = s / t; ch = c; }
+  else { double t = sqrt_(t2), s, c; sincos(0.5 * t, &s, &c); sh = s * rcp_(t); ch = c; }
   double dx = w[0] * sh, dy = w[1] * sh, dz = w[2] * sh, dw = ch;
   double x = q[0], y = q[1], z = q[2], ww = q[3];
   double ox = ww * dx + x * dw + y * dz - z * dy;
   double oy = ww * dy - x * dz + y * dw + z * dx;
   double oz = ww * dz + x * dy - y * dx + z * dw;
   double ow = ww * dw - x * dx - y * dy - z * dz;
-  double n = 1.0 / sqrt(ox * ox + oy * oy + oz * oz + ow * ow);
+  double n = rsqrt_(ox * ox + oy * oy + oz * oz + ow * ow);
   out[0] = ox * n; out[1] = oy * n; out[2] = oz * n; out[3] = ow * n;
 }
 // 6x6 inverse by Gauss-Jordan with partial pivoting (single thread)
@@ -315,7 +346,7 @@ HD void inv6(const double *A, double *Ai) {
     int p = c;
     for (int r = c + 1; r < 6; r++) if (fabs(M[r][c]) > fabs(M[p][c])) p = r;
     if (p != c) for (int j = 0; j < 12; j++) { double t = M[p][j]; M[p][j] = M[c][j]; M[c][j] = t; }
-    double d = 1.0 / M[c][c];
+    double d = rcp_(M[c][c]);
     for (int j = 0; j < 12; j++) M[c][j] *= d;
     for (int r = 0; r < 6; r++) if (r != c) { double f = M[r][c]; for (int j = 0; j < 12; j++) M[r][j] -= f * M[c][j]; }
   }
@@ -454,20 +485,8 @@ HD void chol_diag_block(double *A, int k0, int bw, int ld, double *Di) {
       Di[r * CB + c] = (r < bw && c < bw) ? X[r][c] : 0.0;
     }
 }
-#ifdef MPC_HOST_EMU
-inline double fast_rcp(double a) { return 1.0 / a; }
-#endif
+HD double fast_rcp(double a) { return rcp_(a); } // pivot chains: 56 cycles of dependent latency against 83 for a division (tools/ubench/lat.cu)
 #ifndef MPC_HOST_EMU
-// 1/a for the pivot chain: hardware seed (rcp.approx.ftz.f64, ~20 bits) + two Newton steps = 56 cycles of dependent latency
-// on sm_100a, against 77 for rsqrt() and 83 for a division (tools/ubench/lat.cu).
-__device__ __forceinline__ double fast_rcp(double a) { // (pivots of SPD blocks: normal range; a non-positive or NaN pivot still ends in NaN)
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-  double e = fma(-a, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-a, y, 1.0);
-  return fma(y, e, y);
-}
 // Device version called by ALL lanes of the group's warp 0.  Lane 0 runs the pivot chain in registers as a square-root-free
 // LDL' elimination (per column: reciprocal of the pivot -> scaled column -> update, 56 + 8.5 + 8.5 cycles of dependent
 // latency; a Cholesky column costs a 77-cycle rsqrt more and the chain is what the whole blocked factorisation waits for).
@@ -498,7 +517,7 @@ __device__ __forceinline__ void chol_diag_block_warp0(double *A, int k0, int bw,
   double Lf[CB][CB], dd[CB], X[CB], lcol[CB];
   const int c = lane & 7;
   const double pc = Di[c * CB + c];
-  const double rc = rsqrt(pc); // one rsqrt per lane; the eight values are exchanged through the (free) first row of Di's upper triangle + slot 15
+  const double rc = rsqrt_(pc); // one rsqrt per lane; the eight values are exchanged through the (free) first row of Di's upper triangle + slot 15
 #pragma unroll
   for (int i = 0; i < CB; i++) {
     lcol[i] = Di[i * CB + c]; // own column of Lt (rows below the diagonal; the diagonal slot holds the pivot)

@@ -297,7 +297,8 @@ template <class WS, bool ROLL = false> HD void mb_cost_terms(const DevModel &m, 
     inertia_mul(w.Ic + 10 * J, wj, t2);
     for (int i = 0; i < 6; i++) dho[i] = t1[i] - t2[i];
     inertia_mul(w.Ic + 10 * J, s, Is);
-    double dc[3] = {Is[0] / w.Ic[0], Is[1] / w.Ic[0], Is[2] / w.Ic[0]};
+    const double im_ = rcp_(w.Ic[0]);
+    double dc[3] = {Is[0] * im_, Is[1] * im_, Is[2] * im_};
     double c1[3], c2[3], c3[3];
     cross3(dc, w.hsub, c1); cross3(w.com, dho, c2); cross3(w.com, Is, c3);
     for (int r = 0; r < 3; r++) {
@@ -346,11 +347,11 @@ template <class WS> HD double mb_cost_hess(const WS &w, const double *wx, const 
 // normal-cone projection pieces
 HD double vplus_row(int type, double h, double ve, double mu, double lo, double hi, int &act, double &prim) {
   double wv = h + mu * ve;
-  if (type == 0) { act = 1; prim = h; return wv / mu; }
-  if (type == 1) { if (wv > 0) { act = 1; prim = h; return wv / mu; } act = 0; prim = h - wv; return 0.0; }
+  if (type == 0) { act = 1; prim = h; return wv * rcp_(mu); }
+  if (type == 1) { if (wv > 0) { act = 1; prim = h; return wv * rcp_(mu); } act = 0; prim = h - wv; return 0.0; }
   if (type == 2) {
-    if (wv > hi) { act = 1; prim = h - hi; return (wv - hi) / mu; }
-    if (wv < lo) { act = 1; prim = h - lo; return (wv - lo) / mu; }
+    if (wv > hi) { act = 1; prim = h - hi; return (wv - hi) * rcp_(mu); }
+    if (wv < lo) { act = 1; prim = h - lo; return (wv - lo) * rcp_(mu); }
     act = 0; prim = h - wv; return 0.0;
   }
   act = 0; prim = 0; return 0.0;
@@ -765,7 +766,7 @@ template <bool DERIV, bool ROLL = false> HD void eval_full_knot(const DevModel &
     }
   }
   PAR_FOR(i, FN) {
-    const double gap = w.fbr[i], lp = w.mlnp[i] + gap / io.mu, dl = lp - w.mln[i]; // fbr = gap here
+    const double gap = w.fbr[i], lp = w.mlnp[i] + gap * rcp_(io.mu), dl = lp - w.mln[i]; // fbr = gap here
     w.lpl[i] = lp;
     w.fbr[i] = io.mu * dl;
     acc_pen += 0.5 * io.mu * (lp * lp + dl * dl);
@@ -1006,7 +1007,7 @@ template <bool DERIV> HD void eval_full_term(const DevModel &m, const KnotIO &io
     double lz = (z < FN) ? mb_cost_grad(w, cfg.wx_term, cfg.w_cent_term, cfg.w_foot_term, cfg.w_foot_term, z) : 0.0;
     io.lxu[z] = lz;
     double gz = lz;
-    if (z < NV && has_c) for (int r = 0; r < 3; r++) gz += io.v[r] * w.U[6 * z + r] / w.Ic[0];
+    if (z < NV && has_c) for (int r = 0; r < 3; r++) gz += io.v[r] * w.U[6 * z + r] * rcp_(w.Ic[0]);
     if (z >= 6 && z < FN) gz -= io.lam_k[z];
     w.late.g[z] = gz; io.g[z] = gz;
   }
@@ -1020,7 +1021,7 @@ template <bool DERIV> HD void eval_full_term(const DevModel &m, const KnotIO &io
   }
   PAR_FOR(e, w.nca * FNZ) {
     int ai = e / FNZ, z = e % FNZ, r = w.act_idx[ai];
-    io.CDact[e] = (z < NV) ? w.U[6 * z + r] / w.Ic[0] : 0.0; // Jcom column = lin(Ic_J s_j) / mass
+    io.CDact[e] = (z < NV) ? w.U[6 * z + r] * rcp_(w.Ic[0]) : 0.0; // Jcom column = lin(Ic_J s_j) / mass
   }
   SYNC();
   ONE_THREAD {

@@ -171,7 +171,8 @@ template <bool DERIV, bool ROLL = false> HD void eval_kino_knot(const DevModel &
       else for (int i = 0; i < 6; i++) w.top[6 * (NV + j) + i] = g[i];
     }
     PAR_FOR(j, NV) { // d hdot'/dq_j (angular rows): sum_i (dp_i/dq_j - dc/dq_j) x f_i
-      double dc[3] = {w.U[6 * j] / w.Ic[0], w.U[6 * j + 1] / w.Ic[0], w.U[6 * j + 2] / w.Ic[0]}, acc3[3] = {0, 0, 0};
+      const double im_ = rcp_(w.Ic[0]);
+      double dc[3] = {w.U[6 * j] * im_, w.U[6 * j + 1] * im_, w.U[6 * j + 2] * im_}, acc3[3] = {0, 0, 0};
       for (int f = 0; f < 2; f++) {
         if (!w.active[f]) continue;
         double dp[3] = {0, 0, 0};
@@ -204,7 +205,8 @@ template <bool DERIV, bool ROLL = false> HD void eval_kino_knot(const DevModel &
       const double *Fo = w.Fsub; // total force about the origin
       if (z < NV) {
         const double *tq = w.top + 6 * z;
-        double dc[3] = {w.U[6 * z] / w.Ic[0], w.U[6 * z + 1] / w.Ic[0], w.U[6 * z + 2] / w.Ic[0]}, c1[3], c2[3];
+        const double im_ = rcp_(w.Ic[0]);
+        double dc[3] = {w.U[6 * z] * im_, w.U[6 * z + 1] * im_, w.U[6 * z + 2] * im_}, c1[3], c2[3];
         cross3(dc, Fo, c1); cross3(w.com, tq, c2);
         for (int r = 0; r < 3; r++) { rhs[r] = w.hdq[r * NV + z] - tq[r]; rhs[3 + r] = w.hdq[(3 + r) * NV + z] - (tq[3 + r] - c1[r] - c2[r]); }
       } else if (z < FN) {
@@ -282,7 +284,7 @@ template <bool DERIV, bool ROLL = false> HD void eval_kino_knot(const DevModel &
     }
   }
   PAR_FOR(i, FN) {
-    const double gap = w.fbr[i], lp = io.lam_n_prev[i] + gap / io.mu, dl = lp - io.lam_n[i]; // fbr = gap here
+    const double gap = w.fbr[i], lp = io.lam_n_prev[i] + gap * rcp_(io.mu), dl = lp - io.lam_n[i]; // fbr = gap here
     w.lpl[i] = lp;
     w.fbr[i] = io.mu * dl;
     acc_pen += 0.5 * io.mu * (lp * lp + dl * dl);
@@ -442,12 +444,12 @@ template <bool DERIV> HD void eval_kino_term(const DevModel &m, const KnotIO &io
   PAR_FOR(z, KNZ) {
     io.lxu[z] = 0.0;
     double gz = 0;
-    if (z < NV && has_c) for (int r = 0; r < 3; r++) gz += io.v[r] * w.U[6 * z + r] / w.Ic[0];
+    if (z < NV && has_c) for (int r = 0; r < 3; r++) gz += io.v[r] * w.U[6 * z + r] * rcp_(w.Ic[0]);
     if (z >= 6 && z < FN) gz -= io.lam_k[z];
     w.late.g[z] = gz; io.g[z] = gz;
   }
   PAR_FOR(e, KNZ * KNZ) { int a = e / KNZ, b = e % KNZ; io.H[e] = (a == b && a < FN) ? io.preg : 0.0; }
-  PAR_FOR(e, w.nca * KNZ) { int ai = e / KNZ, z = e % KNZ, r = w.act_idx[ai]; io.CDact[e] = (z < NV) ? w.U[6 * z + r] / w.Ic[0] : 0.0; }
+  PAR_FOR(e, w.nca * KNZ) { int ai = e / KNZ, z = e % KNZ, r = w.act_idx[ai]; io.CDact[e] = (z < NV) ? w.U[6 * z + r] * rcp_(w.Ic[0]) : 0.0; }
   SYNC();
   ONE_THREAD {
     double dual = 0;
