@@ -361,12 +361,12 @@ def main():
         h2d = xs_np.nbytes + us_np.nbytes
         d2h = out_xs.nbytes + out_us.nbytes + B * 22 * 56 * 8
         cfg = config_block(args, world, G, gather)
-        cfg["tick_iters_done"] = int(np.min(res_iters))
-        cfg["double_support_fraction"] = prob.get("ds_fraction")
+        # (`config` is identical in both arms: what was measured about the workload goes next to it)
+        workload_stats = {"tick_iters_done": int(np.min(res_iters)), "double_support_fraction": prob.get("ds_fraction")}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": 1e3 * step_s, "higher_is_better": True, "scaling": "weak" if args.batch else "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": cfg,
+            "data": "synthetic", "config": cfg, "workload_stats": workload_stats,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world},
             "gpu_launches": int(launches),
             "gather": {"bytes_per_rank_per_step": int(B * per * 8), "bytes_total_per_step": int(world * B * per * 8), "collective": "ncclAllGather (torch.distributed.all_gather_into_tensor) of [xs|us|K0|info]"} if gather else None,
