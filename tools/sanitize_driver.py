@@ -18,7 +18,14 @@ def run(name, prob, iters):
 
 
 def main():
+    # MPCB200_RIC_THREADS=128 in the environment forces the two-instances-per-SM launch shape of the full-dynamics Riccati kernel
     run("full walk", problems.full_walk_batch(2, seed=3, T=12), 3)
+    cold = problems.full_walk_batch(2, seed=3, T=12)
+    cold["x0"] = problems.perturbed_x0(cold["robot"], cold["x0"][0], __import__("numpy").random.default_rng(2), 2)  # many active rows: scratch path
+    run("full walk, perturbed cold start", cold, 2)
+    nl = problems.full_walk_batch(2, seed=3, T=12)
+    nl["cfg"].rollout = 1
+    run("full walk, nonlinear rollout kernel", nl, 2)
     run("kino standing", problems.kino_standing_problem(batch=2, T=10), 2)
     run("cent standing", problems.cent_standing_problem(batch=2, T=20), 2)
 
