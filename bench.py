@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--global-batch", type=int, default=0, help="instances over ALL GPUs (default 4096; 512 for --config stairs): strong scaling")
     ap.add_argument("--batch", type=int, default=0, help="instances PER GPU (weak scaling); overrides --global-batch")
     ap.add_argument("--config", default="walk", choices=["walk", "random", "stairs"], help="walk = BASELINE configs[4] (default), stairs = configs[3]")
+    ap.add_argument("--e2e-parts", type=int, default=2, help="sub-batches of the pipelined host-buffer call in the end-to-end leg (1 = no overlap)")
     ap.add_argument("--no-gather", action="store_true", help="skip the NCCL all-gather of the results (multi-GPU only)")
     ap.add_argument("--prep-iters", type=int, default=20, help="untimed cold-solve iterations that produce the warm start")
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances in the CPU-baseline sample (0 = auto, ~10-30 s)")
@@ -279,15 +280,17 @@ def main():
     out_xs = torch.empty_like(xs_h).pin_memory().numpy()  # results land in pinned host buffers too
     out_us = torch.empty_like(us_h).pin_memory().numpy()
 
+    out_k0 = torch.empty((B, 22, 56), dtype=torch.float64).pin_memory().numpy()
+
     def tick_e2e():
         solver.reset_multipliers()
-        solver.run(xs_np, us_np, max_iters=1, fetch=False)
-        # read back what the MPC loop consumes: xs, us and the first feedback gain (fulldynamic_talos.py:548-550)
-        _native.check(L.mpc_get_results(solver._h, _native.ptr(out_xs), _native.ptr(out_us), None, None, None, None), "mpc_get_results")
-        k0 = solver.feedback(0)
+        # solver.run on HOST buffers + read-back of what the MPC loop consumes — xs, us and the first feedback gain
+        # (fulldynamic_talos.py:540,548-550) — through the pipelined C-ABI call: uploads / downloads of one half of the batch overlap
+        # the solve of the other half (mpc_run_pipelined; --e2e-parts 1 = plain mpc_run + mpc_get_results ordering)
+        solver.run_pipelined(xs_np, us_np, out_xs, out_us, out_k0, max_iters=1, parts=args.e2e_parts)
         if gather:
             export_and_gather()
-        return k0
+        return out_k0
 
     for _ in range(max(args.warmup, 3)):
         tick_device()

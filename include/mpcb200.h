@@ -134,6 +134,13 @@ int32_t mpc_set_x0(mpc_solver_t *h, const double *x0);
  * xs [batch][T+1][nx], us [batch][T][nu]; copies in, runs up to max_iters ProxDDP iterations
  * per instance, copies results back with mpc_get_results. */
 int32_t mpc_run(mpc_solver_t *h, const double *xs_init, const double *us_init, int32_t max_iters);
+/* solver.run + the results read-back (results.xs / .us / controlFeedbacks()[0], fulldynamic_talos.py:540,548-550) as ONE call on
+ * HOST buffers, pipelined: the batch is cut into `parts` (1..8) contiguous sub-batches; the upload of the next part and the download
+ * of the previous one overlap the solve of the current one on a second stream (pinned host memory makes the copies asynchronous;
+ * pageable memory works, without overlap).  Outputs may be NULL.  Layouts: xs_out [batch][T+1][nx], us_out [batch][T][nu],
+ * K0_out [batch][nu][ndx], info_out [batch].  Instance results are identical to mpc_run + mpc_get_results. */
+int32_t mpc_run_pipelined(mpc_solver_t *h, const double *xs_init, const double *us_init, int32_t max_iters, int32_t parts, double *xs_out,
+                          double *us_out, double *K0_out, mpc_info_t *info_out);
 /* Same, with the trajectories already resident in device memory (device pointers, same layout); kernels are
  * launched on `stream` (a cudaStream_t, 0 = the handle's own).  The call returns after the solve has finished:
  * the iteration / linesearch control reads per-batch counters back between launches. */

@@ -14,7 +14,7 @@ dp = C.POINTER(C.c_double)
 
 EXPORTS = [
     "mpc_create", "mpc_destroy", "mpc_last_error", "mpc_setup", "mpc_update_knots", "mpc_update_terms", "mpc_cycle", "mpc_set_x0", "mpc_shift_multipliers", "mpc_reconfigure",
-    "mpc_run", "mpc_run_device", "mpc_tick", "mpc_get_results", "mpc_export_results_device", "mpc_result_ptrs", "mpc_get_stage_data", "mpc_last_launches", "mpc_last_device_ms",
+    "mpc_run", "mpc_run_pipelined", "mpc_run_device", "mpc_tick", "mpc_get_results", "mpc_export_results_device", "mpc_result_ptrs", "mpc_get_stage_data", "mpc_last_launches", "mpc_last_device_ms",
     "mpc_get_feedback", "mpc_last_kernel_ms", "mpc_last_kernel_launches", "mpc_set_profiling",
     "mpc_reset_multipliers", "mpc_debug_lq", "mpc_debug_gemm_tn", "mpc_debug_phases", "mpc_workspace_bytes", "mpc_abi_sizeof", "mpc_measure_fp64_peak", "mpc_measure_fp64_peak_dmma",
 ]
@@ -42,6 +42,7 @@ def lib():
         L.mpc_shift_multipliers.argtypes = [C.c_void_p, C.c_int32]
         L.mpc_reconfigure.argtypes = [C.c_void_p, C.POINTER(_abi.Robot), C.POINTER(_abi.Config)]
         L.mpc_run.argtypes = [C.c_void_p, dp, dp, C.c_int32]
+        L.mpc_run_pipelined.argtypes = [C.c_void_p, dp, dp, C.c_int32, C.c_int32, dp, dp, dp, C.c_void_p]
         L.mpc_tick.argtypes = [C.c_void_p, C.c_void_p, dp, C.c_int32, C.c_int32]
         L.mpc_run_device.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32, C.c_uint64]
         L.mpc_get_results.argtypes = [C.c_void_p, dp, dp, dp, dp, dp, C.c_void_p]

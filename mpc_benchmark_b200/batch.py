@@ -105,6 +105,19 @@ class BatchSolver:
         _native.check(_native.lib().mpc_run(self._h, _native.ptr(xs), _native.ptr(us), mi), "mpc_run")
         return self.results(gains=gains) if fetch else None
 
+    def run_pipelined(self, xs, us, xs_out, us_out, K0_out=None, max_iters=None, parts=2, info=False):
+        """solver.run + read-back of xs / us / K0 as one pipelined call on host buffers (pinned buffers give the overlap): the upload of
+        the next sub-batch and the download of the previous one run beside the solve of the current one (`mpc_run_pipelined`)."""
+        xs = np.ascontiguousarray(xs, dtype=np.float64).reshape(self.batch, self.T + 1, self.nx)
+        us = np.ascontiguousarray(us, dtype=np.float64).reshape(self.batch, self.T, self.m)
+        for a in (xs_out, us_out, K0_out):
+            assert a is None or (a.dtype == np.float64 and a.flags["C_CONTIGUOUS"])
+        mi = self.cfg.max_iters if max_iters is None else int(max_iters)
+        inf = (_abi.Info * self.batch)() if info else None
+        _native.check(_native.lib().mpc_run_pipelined(self._h, _native.ptr(xs), _native.ptr(us), mi, int(parts), _native.ptr(xs_out), _native.ptr(us_out),
+                                                      _native.ptr(K0_out), C.cast(inf, C.c_void_p) if info else None), "mpc_run_pipelined")
+        return inf
+
     def tick(self, last_knots=None, x_meas=None, keep_multipliers=False, max_iters=1):
         """One closed-loop MPC tick on the device: rotate the horizon, shift the warm start, new x0, solve."""
         if last_knots is not None:

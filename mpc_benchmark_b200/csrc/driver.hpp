@@ -9,11 +9,13 @@ namespace mpcdev {
 
 // Backend: reset_counters(), eval(deriv, list, n), decide_eval(list, n, next_eval), riccati(list, n), apply_step(list, n),
 //          decide_ls(list, n, ls_out, next_eval), rollout_ls(list, n, next_eval), read_counters(int[4])
-template <class Backend> int run_loop(Backend &be, const Ws &w, int max_iters, const SolverConst &sc) {
-  int launches = 0, n_eval = w.B, cur = 0;
+// first / count: the sub-batch [first, first + count) of instances this call advances (the first pass takes its list from the
+// identity list written by the run prologue; later passes use the compacted lists the decide kernels build)
+template <class Backend> int run_loop(Backend &be, const Ws &w, int max_iters, const SolverConst &sc, int first = 0, int count = -1) {
+  int launches = 0, n_eval = (count < 0) ? w.B : count, cur = 0;
   const int guard = max_iters + sc.max_al_iters + 2;
   for (int pass = 0; pass < guard && n_eval > 0; pass++) {
-    int32_t *L = eval_list(w, cur), *Lnext = eval_list(w, cur + 1);
+    int32_t *L = eval_list(w, cur) + (pass == 0 ? first : 0), *Lnext = eval_list(w, cur + 1);
     be.reset_counters();
     be.eval(true, L, n_eval); be.decide_eval(L, n_eval, Lnext); be.riccati(L, n_eval);
     int c[4] = {0, 0, 0, 0};

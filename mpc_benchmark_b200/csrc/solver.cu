@@ -28,7 +28,7 @@ static int fail(const std::string &m) { g_err = m; return 1; }
   } while (0)
 
 // ------------------------------------------------------------------ kernels
-__global__ void k_init(Ws w, const double *xs_in, const double *us_in, int max_iters) { init_instance(w, blockIdx.x, xs_in, us_in, max_iters); }
+__global__ void k_init(Ws w, const double *xs_in, const double *us_in, int max_iters, int first) { init_instance(w, first + blockIdx.x, xs_in, us_in, max_iters); }
 
 #ifndef MPC_VALUES_CTAS
 #define MPC_VALUES_CTAS 5 /* values-only knots resident per SM */
@@ -148,8 +148,10 @@ struct mpc_solver {
   double *d_xs_in = nullptr, *d_us_in = nullptr, *d_meas = nullptr;
   mpc_knot_t *d_last = nullptr;
   int32_t *h_counters = nullptr; // pinned
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t stream = nullptr, stream_copy = nullptr; // stream_copy: uploads / downloads of mpc_run_pipelined
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_part[2 * 8] = {};
+  double *d_k0 = nullptr; // first feedback gains, packed (mpc_run_pipelined)
+  InstState *h_st = nullptr; // pinned copy of the per-instance summaries (mpc_run_pipelined)
   size_t eval_smem = 0, eval_smem_values = 0, ric_smem = 0;
   int eval_threads = 128, ric_threads = 256, num_sms = 148;
   bool ric_threads_auto = true;
@@ -281,6 +283,10 @@ void mpc_destroy(mpc_solver_t *h) {
   if (h->d_last) cudaFree(h->d_last);
   if (h->d_model) cudaFree(h->d_model);
   if (h->h_counters) cudaFreeHost(h->h_counters);
+  if (h->h_st) cudaFreeHost(h->h_st);
+  if (h->d_k0) cudaFree(h->d_k0);
+  for (cudaEvent_t e : h->ev_part) if (e) cudaEventDestroy(e);
+  if (h->stream_copy) cudaStreamDestroy(h->stream_copy);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -396,7 +402,7 @@ static int run_impl(mpc_solver *h, const double *d_xs, const double *d_us, int m
   h->evcat.clear();
   CudaBackend be{h, s};
   be.mark(3);
-  k_init<<<h->w.B, 128, 0, s>>>(h->w, d_xs, d_us, max_iters);
+  k_init<<<h->w.B, 128, 0, s>>>(h->w, d_xs, d_us, max_iters, 0);
   h->last_launches = 1 + run_loop(be, h->w, max_iters, h->w.sc);
   be.mark(-1);
   CK(cudaEventRecord(h->ev1, s));
@@ -477,6 +483,81 @@ int32_t mpc_run(mpc_solver_t *h, const double *xs_init, const double *us_init, i
   CK(cudaMemcpyAsync(h->d_xs_in, xs_init, w.B * T1 * w.nx * 8, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->d_us_in, us_init, (size_t)w.B * w.T * w.m * 8, cudaMemcpyHostToDevice, h->stream));
   return run_impl(h, h->d_xs_in, h->d_us_in, max_iters, h->stream, true);
+}
+
+// first feedback gain of the instances [first, first + gridDim.x), packed [instance][m][n]
+__global__ void k_pack_k0_part(Ws w, double *K0, int first) {
+  const size_t b = first + blockIdx.x, sz = (size_t)w.m * w.n;
+  for (size_t i = threadIdx.x; i < sz; i += blockDim.x) K0[b * sz + i] = w.Kfb[b * (size_t)w.T * sz + i];
+}
+
+int32_t mpc_run_pipelined(mpc_solver_t *h, const double *xs_init, const double *us_init, int32_t max_iters, int32_t parts, double *xs_out,
+                          double *us_out, double *K0_out, mpc_info_t *info_out) {
+  CK(cudaSetDevice(h->device));
+  if (!h->setup_done) return fail("mpc_run_pipelined before mpc_setup");
+  Ws &w = h->w;
+  const size_t T1 = w.T + 1, sx = T1 * w.nx, su = (size_t)w.T * w.m, sk = (size_t)w.m * w.n;
+  if (parts < 1) parts = 1;
+  if (parts > 8) parts = 8;
+  if (parts > w.B) parts = w.B;
+  if (!h->stream_copy) CK(cudaStreamCreateWithFlags(&h->stream_copy, cudaStreamNonBlocking));
+  for (int i = 0; i < 2 * parts; i++) if (!h->ev_part[i]) CK(cudaEventCreateWithFlags(&h->ev_part[i], cudaEventDisableTiming));
+  if (K0_out && !h->d_k0) CK(cudaMalloc(&h->d_k0, (size_t)w.B * sk * 8));
+  if (info_out && !h->h_st) CK(cudaMallocHost(&h->h_st, sizeof(InstState) * w.B));
+  cudaStream_t s = h->stream, sc = h->stream_copy;
+  auto lo = [&](int p) { return (int)((long long)w.B * p / parts); };
+  // every upload is queued at once on the copy stream; the solve of part p waits for its own
+  for (int p = 0; p < parts; p++) {
+    const size_t o = lo(p), n = lo(p + 1) - lo(p);
+    CK(cudaMemcpyAsync(h->d_xs_in + o * sx, xs_init + o * sx, n * sx * 8, cudaMemcpyHostToDevice, sc));
+    CK(cudaMemcpyAsync(h->d_us_in + o * su, us_init + o * su, n * su * 8, cudaMemcpyHostToDevice, sc));
+    CK(cudaEventRecord(h->ev_part[p], sc));
+  }
+  CK(cudaEventRecord(h->ev0, s));
+  h->evcat.clear();
+  CudaBackend be{h, s};
+  int launches = 0;
+  for (int p = 0; p < parts; p++) {
+    const int o = lo(p), n = lo(p + 1) - o;
+    CK(cudaStreamWaitEvent(s, h->ev_part[p], 0));
+    be.mark(3);
+    k_init<<<n, 128, 0, s>>>(w, h->d_xs_in, h->d_us_in, max_iters, o);
+    launches += 1 + run_loop(be, w, max_iters, w.sc, o, n); // returns with the part finished (its last counter read synchronises)
+    be.mark(-1);
+    if (be.err != cudaSuccess) return fail(std::string("kernel failure: ") + cudaGetErrorString(be.err));
+    // the download of this part overlaps the solve of the next one
+    CK(cudaEventRecord(h->ev_part[parts + p], s));
+    CK(cudaStreamWaitEvent(sc, h->ev_part[parts + p], 0));
+    if (xs_out) CK(cudaMemcpyAsync(xs_out + (size_t)o * sx, w.xs + (size_t)o * sx, (size_t)n * sx * 8, cudaMemcpyDeviceToHost, sc));
+    if (us_out) CK(cudaMemcpyAsync(us_out + (size_t)o * su, w.us + (size_t)o * su, (size_t)n * su * 8, cudaMemcpyDeviceToHost, sc));
+    if (K0_out) {
+      k_pack_k0_part<<<n, 128, 0, sc>>>(w, h->d_k0, o);
+      CK(cudaMemcpyAsync(K0_out + (size_t)o * sk, h->d_k0 + (size_t)o * sk, (size_t)n * sk * 8, cudaMemcpyDeviceToHost, sc));
+    }
+    if (info_out) CK(cudaMemcpyAsync(h->h_st + o, w.st + o, sizeof(InstState) * n, cudaMemcpyDeviceToHost, sc));
+  }
+  CK(cudaEventRecord(h->ev1, s));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(sc));
+  CK(cudaEventSynchronize(h->ev1));
+  h->last_launches = launches;
+  CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+  for (int c = 0; c < 4; c++) { h->cat_ms[c] = 0; h->cat_launches[c] = 0; }
+  for (size_t i = 0; i + 1 < h->evcat.size(); i++) {
+    int c = h->evcat[i];
+    if (c < 0) continue;
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, h->evpool[i], h->evpool[i + 1]));
+    h->cat_ms[c] += ms; h->cat_launches[c]++;
+  }
+  if (info_out)
+    for (int b = 0; b < w.B; b++) {
+      const InstState &t = h->h_st[b];
+      info_out[b].prim_infeas = t.prim_infeas; info_out[b].dual_infeas = t.dual_infeas; info_out[b].traj_cost = t.traj_cost; info_out[b].merit = t.merit;
+      info_out[b].mu = t.mu; info_out[b].alpha = t.alpha; info_out[b].ls_evals = t.ls_evals; info_out[b].pad_ = 0; info_out[b].num_iters = t.num_iters;
+      info_out[b].al_iters = t.al_iters; info_out[b].conv = t.conv; info_out[b].status = t.status;
+    }
+  return 0;
 }
 
 int32_t mpc_run_device(mpc_solver_t *h, uint64_t xs_dev, uint64_t us_dev, int32_t max_iters, uint64_t stream) {
@@ -588,7 +669,7 @@ int32_t mpc_debug_lq(mpc_solver_t *h, const double *xs, const double *us, int32_
   if (inst < 0 || inst >= w.B) return fail("instance out of range");
   CK(cudaMemcpyAsync(h->d_xs_in, xs, w.B * T1 * w.nx * 8, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->d_us_in, us, (size_t)w.B * w.T * w.m * 8, cudaMemcpyHostToDevice, h->stream));
-  k_init<<<w.B, 128, 0, h->stream>>>(w, h->d_xs_in, h->d_us_in, 1);
+  k_init<<<w.B, 128, 0, h->stream>>>(w, h->d_xs_in, h->d_us_in, 1, 0);
   CudaBackend be{h, h->stream};
   be.reset_counters();
   be.eval(true, eval_list(w, 0), w.B); be.decide_eval(eval_list(w, 0), w.B, eval_list(w, 1));

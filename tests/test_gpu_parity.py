@@ -533,3 +533,20 @@ def test_nonlinear_rollout_through_the_shim(oracle):
                             xs=np.tile(ns["x0"], (1, 21, 1)), us=np.tile(ns["u0"], (1, 20, 1))))
     assert conv and solver.results.num_iters == ref["info"][0].num_iters
     assert rel(np.array(solver.results.xs.tolist()), ref["xs"][0]) < RTOL and rel(np.array(solver.results.us.tolist()), ref["us"][0]) < RTOL
+
+
+@pytest.mark.parametrize("batch,parts", [(6, 2), (5, 3), (600, 2)])
+def test_pipelined_host_call_equals_plain_run(batch, parts):
+    """mpc_run_pipelined (sub-batches, uploads / downloads on a second stream beside the solve) returns what mpc_run + mpc_get_results
+    return, bit for bit, for every instance — also when the parts are ragged and when they cross the Riccati kernel's launch shapes."""
+    prob = problems.full_walk_batch(batch, seed=9, T=100 if batch < 100 else 30)
+    s = BatchSolver(prob["robot"], prob["cfg"], batch)
+    s.setup(prob["knots"], prob["terms"], prob["x0"])
+    ref = s.run(prob["xs"], prob["us"], max_iters=2)
+    s.reset_multipliers()
+    T = prob["cfg"].T
+    xs_o, us_o, k0_o = np.empty((batch, T + 1, 57)), np.empty((batch, T, 22)), np.empty((batch, 22, 56))
+    info = s.run_pipelined(prob["xs"], prob["us"], xs_o, us_o, k0_o, max_iters=2, parts=parts, info=True)
+    assert np.array_equal(xs_o, ref.xs) and np.array_equal(us_o, ref.us) and np.array_equal(k0_o, ref.K[:, 0])
+    assert [i.num_iters for i in info] == list(ref.num_iters) and [i.ls_evals for i in info] == [i.ls_evals for i in ref.info]
+    s.close()
