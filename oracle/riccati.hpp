@@ -63,18 +63,41 @@ _Pragma("GCC ivdep") for (int c = 0; c < nrhs; c++) bi[c] -= l * bk[c]; }
     double d = 1.0 / L[i * n + i]; for (int c = 0; c < nrhs; c++) b[i * nrhs + c] *= d;
   }
 }
+// Dense products of the recursion, register-blocked (4 rows x 32 columns of C held in vector registers over the whole k loop; GCC
+// vector extensions: AVX-512 / AVX2 code under -march=native, generic SIMD otherwise) — the CPU arm of the benchmark should not
+// lose to the GPU because of a naive GEMM ("blocked or at least vectorised dense kernels").
+typedef double v8d __attribute__((vector_size(64), aligned(8)));
+template <bool TA> inline void gemm_blocked(int m, int n, int k, const double *__restrict A, const double *__restrict B, double *__restrict C) {
+  // TA: A is k x m (C += A^T B); else A is m x k (C += A B).  B: k x n, C: m x n, all row-major.
+  int jb = 0;
+  for (; jb + 32 <= n; jb += 32)
+    for (int ib = 0; ib < m; ib += 4) {
+      const int rows = (m - ib < 4) ? m - ib : 4;
+      v8d acc[4][4];
+      for (int r = 0; r < 4; r++) for (int v = 0; v < 4; v++) { if (r < rows) std::memcpy(&acc[r][v], C + (size_t)(ib + r) * n + jb + 8 * v, 64); else acc[r][v] = v8d{0, 0, 0, 0, 0, 0, 0, 0}; }
+      for (int p = 0; p < k; p++) {
+        v8d b[4];
+        for (int v = 0; v < 4; v++) std::memcpy(&b[v], B + (size_t)p * n + jb + 8 * v, 64);
+        for (int r = 0; r < 4; r++) {
+          const double a = (r < rows) ? (TA ? A[(size_t)p * m + ib + r] : A[(size_t)(ib + r) * k + p]) : 0.0;
+          for (int v = 0; v < 4; v++) acc[r][v] += a * b[v];
+        }
+      }
+      for (int r = 0; r < rows; r++) for (int v = 0; v < 4; v++) std::memcpy(C + (size_t)(ib + r) * n + jb + 8 * v, &acc[r][v], 64);
+    }
+  if (jb < n) // remaining columns: rank-1 updates, vectorised over j
+    for (int p = 0; p < k; p++)
+      for (int i = 0; i < m; i++) {
+        const double a = TA ? A[(size_t)p * m + i] : A[(size_t)i * k + p];
+        if (a == 0.0) continue;
+        double *ci = C + (size_t)i * n; const double *bp = B + (size_t)p * n;
+_Pragma("GCC ivdep") for (int j = jb; j < n; j++) ci[j] += a * bp[j];
+      }
+}
 // C (m x n) += A^T (k x m)^T * B (k x n)
-inline void gemm_tn(int m, int n, int k, const double *__restrict A, const double *__restrict B, double *__restrict C) {
-  for (int p = 0; p < k; p++)
-    for (int i = 0; i < m; i++) { double a = A[p * m + i]; if (a == 0.0) continue; double *ci = C + i * n; const double *bp = B + p * n;
-_Pragma("GCC ivdep") for (int j = 0; j < n; j++) ci[j] += a * bp[j]; }
-}
+inline void gemm_tn(int m, int n, int k, const double *__restrict A, const double *__restrict B, double *__restrict C) { gemm_blocked<true>(m, n, k, A, B, C); }
 // C (m x n) += A (m x k) * B (k x n)
-inline void gemm_nn(int m, int n, int k, const double *__restrict A, const double *__restrict B, double *__restrict C) {
-  for (int i = 0; i < m; i++)
-    for (int p = 0; p < k; p++) { double a = A[i * k + p]; if (a == 0.0) continue; double *ci = C + i * n; const double *bp = B + p * n;
-_Pragma("GCC ivdep") for (int j = 0; j < n; j++) ci[j] += a * bp[j]; }
-}
+inline void gemm_nn(int m, int n, int k, const double *__restrict A, const double *__restrict B, double *__restrict C) { gemm_blocked<false>(m, n, k, A, B, C); }
 inline void inv6(const double *A, double *Ai) { // Gauss-Jordan with partial pivoting
   double M[6][12];
   for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) { M[i][j] = A[6 * i + j]; M[i][6 + j] = i == j; }
