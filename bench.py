@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--prep-iters", type=int, default=20, help="untimed cold-solve iterations that produce the warm start")
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances in the CPU-baseline sample (0 = auto, ~10-30 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-qp", action="store_true", help="skip the batched whole-body QP leg (SURVEY 8f row f-3)")
+    ap.add_argument("--qp-only", action="store_true", help="run only the batched whole-body QP leg and print its object")
     ap.add_argument("--latency-ticks", type=int, default=200, help="warm single-instance MPC ticks for the p50 latency (0 = skip)")
     return ap.parse_args()
 
@@ -213,6 +215,9 @@ def main():
     args = parse()
     if args.impl == "reference":
         return reference_arm(args)
+    if args.qp_only:
+        print(json.dumps({"qp": qp_leg(args, int(os.environ.get("LOCAL_RANK", "0")), not args.no_cpu_baseline)}))
+        return
     import torch
     import torch.distributed as dist
 
@@ -398,6 +403,8 @@ def main():
             line["latency"]["other_models"] = other_model_latencies(args, local, not args.no_cpu_baseline and world == 1)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, G)
+        if world == 1 and not args.no_qp:
+            line["qp"] = qp_leg(args, local, not args.no_cpu_baseline)
         print(json.dumps(line))
     solver.close()
     if world > 1:
@@ -515,6 +522,91 @@ def other_model_latencies(args, device, with_cpu):
                 cts.append(1e3 * (time.perf_counter() - t0))
             out[name]["cpu_oracle_8_threads_p50_ms"] = float(np.percentile(cts[1:], 50))
     return out
+
+
+def qp_leg(args, device, with_cpu, batch=4096, steps=10):
+    """the reference's whole-body inverse-dynamics QP (IDSolver_ulim, QP_utils.py:437-573: n 62, n_eq 40, n_in 18,
+    eps_abs 1e-3, 10 x 10 iterations, duality-gap check) at batch 4096.  Inputs = the committed fixture tests/golden/qp_id_talos.npz
+    (32 perturbed states of the synthetic Talos-shaped model, DS / left / right support) tiled to the batch, desired accelerations and
+    forces perturbed per instance.  value = solve kernel on device-resident QPs; e2e = IDSolver_ulim.solve on host arrays (H2D of M, nle,
+    Jc, gamma, a, forces; device assembly; solve; D2H of x, y, z, info)."""
+    import time
+
+    from mpc_benchmark_b200 import _native, pin, qp_utils
+
+    d = np.load(os.path.join(ROOT, "tests", "golden", "qp_id_talos.npz"))
+    reps = batch // d["M"].shape[0]
+    rng = np.random.default_rng(7)
+    tile = lambda a: np.ascontiguousarray(np.tile(a, (reps,) + (1,) * (a.ndim - 1)))  # noqa: E731
+    cs = tile(d["cs"])
+    a = tile(d["a"]) + rng.normal(0, 0.05, (batch, 28))
+    f = tile(d["forces"]) + rng.normal(0, 1.0, (batch, 12)) * np.repeat(cs, 6, axis=1)
+    M, rbd = tile(d["M"]), qp_utils.RBDTerms(nle=tile(d["nle"]), Jc=tile(d["Jc"]), dJv=tile(d["dJv"]), vf=tile(d["vf"]))
+    MU, FL, FW = 0.8, 0.1, 0.075
+    solver = qp_utils.IDSolver_ulim(pin.load_talos_like()[0], [1, 1], 2, MU, FL, FW, [0, 1], 6, False, batch=batch, device=device)
+    for _ in range(3):
+        solver.solve(rbd, cs, None, a, f, M)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        solver.solve(rbd, cs, None, a, f, M)
+    e2e_s = (time.perf_counter() - t0) / steps
+    info = solver.qp.results.info
+    L, h = _native.lib(), solver.qp._handle()
+    st = solver.qp.settings.to_c(False)
+    import ctypes as C
+
+    ms = []
+    for _ in range(3 + steps):  # device-resident: the handle's own buffers hold the assembled QPs; only the solve kernel is launched
+        if L.mpc_qp_solve_device(h, batch, C.byref(st), *([0, 0] * 9), 0, 0, 0, 0, 0) != 0:
+            raise RuntimeError(L.mpc_qp_last_error().decode())
+        ms.append(L.mpc_qp_last_device_ms(h))
+    dev_ms = float(np.mean(ms[3:]))
+    n, ne, ni = 62, 40, 18
+    newton = float(np.mean(info.iter))
+    outer = float(np.mean(info.iter_ext))
+    # algorithmic FLOPs (dense model, stated in DESIGN.md): per Newton step  K = H + A'A/mu + C'C/mu (symmetric half: n^2 (ne + ni)),
+    # Cholesky n^3/3, two triangular solves 2 n^2, gradient / linesearch mat-vecs 2 * 2 n (n + ne + ni); per outer iteration the
+    # residuals 2 * 2 n (n + ne + ni)
+    fl_newton = n * n * (ne + ni) + n ** 3 / 3 + 2 * n * n + 4 * n * (n + ne + ni)
+    fl_outer = 4 * n * (n + ne + ni)
+    flops = batch * (newton * fl_newton + (outer + 1) * fl_outer)
+    bytes_in = batch * 8 * (ne * n + ne + ni * n + ni) + 8 * (n * n + n + ni)  # A, b, C, l per QP; H, g, u shared
+    bytes_out = batch * (8 * (n + ne + ni) + 48)
+    out = {"metric": "whole-body inverse-dynamics QPs/s at batch 4096 (IDSolver_ulim: n 62, n_eq 40, n_in 18; eps_abs 1e-3, max_iter 10 x 10, duality-gap check)",
+           "value": batch / (dev_ms * 1e-3), "unit": "QPs/s", "ms_per_batch": dev_ms,
+           "e2e": {"value": batch / e2e_s, "unit": "QPs/s", "h2d_bytes_per_step": int(batch * 8 * (784 + 28 + 336 + 12 + 28 + 12 + 1)),
+                   "d2h_bytes_per_step": int(bytes_out), "what": "IDSolver_ulim.solve on host arrays: H2D, assembly kernel, solve kernel, D2H"},
+           "gpu_launches": 2, "solved": int((info.status == 0).sum()), "mean_outer_iters": outer, "mean_newton_steps": newton,
+           "max_pri_res": float(info.pri_res.max()), "max_dua_res": float(info.dua_res.max()),
+           "roofline": {"bound": "fp64 (latency-bound in practice: one 128-thread CTA per QP, 2 QPs per SM)", "achieved": flops / (dev_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+                        "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": int(bytes_in + bytes_out),
+                        "hbm_gbs": (bytes_in + bytes_out) / (dev_ms * 1e-3) / 1e9}}
+    solver.qp.close()
+    if with_cpu:
+        oracle_lib, native = oracle_native()
+        cores = os.cpu_count() or 1
+        nc = min(batch, 64 * cores)
+        A, b, Cm, l = oracle_lib.qp_assemble_id(M[:nc], rbd.nle[:nc], rbd.Jc[:nc], _gamma(rbd, cs, nc), a[:nc], f[:nc], cs[:nc], MU, FL, FW)
+        H = np.zeros((n, n)); H[:28, :28] = np.eye(28); H[28:40, 28:40] = np.eye(12)
+        stc = oracle_lib.qp_default_settings(eps_abs=1e-3, eps_rel=0.0, max_iter=10, max_iter_in=10, check_duality_gap=1)
+        oracle_lib.qp_solve(H, np.zeros(n), A, b, Cm, l, np.full(ni, 1e5), settings=stc)
+        t0 = time.perf_counter()
+        reps_c = 5
+        for _ in range(reps_c):
+            oracle_lib.qp_assemble_id(M[:nc], rbd.nle[:nc], rbd.Jc[:nc], _gamma(rbd, cs, nc), a[:nc], f[:nc], cs[:nc], MU, FL, FW)
+            oracle_lib.qp_solve(H, np.zeros(n), A, b, Cm, l, np.full(ni, 1e5), settings=stc)
+        cs_ = (time.perf_counter() - t0) / reps_c
+        out["cpu_baseline"] = {"value": nc / cs_, "unit": "QPs/s", "cores": cores, "kind": "port",
+                               "build": "-O3 -march=native -fopenmp (built on this host)" if native else "-O3 -march=x86-64-v3 -fopenmp",
+                               "sample": f"first {nc} QPs of the batch x {reps_c} passes (assembly + solve), CPU oracle oracle/qp.hpp with OpenMP over QPs (not proxsuite: not installable offline)"}
+    return out
+
+
+def _gamma(rbd, cs, nc):
+    g = np.array(rbd.dJv[:nc], float).reshape(nc, 2, 6).copy()
+    vf = np.asarray(rbd.vf[:nc], float).reshape(nc, 2, 6)
+    g[:, :, :3] += vf[:, :, :3] + vf[:, :, 3:]
+    return (g * np.asarray(cs[:nc]).reshape(nc, 2, 1)).reshape(nc, 12)
 
 
 def cpu_baseline(args, G):

@@ -116,3 +116,19 @@ DIMS = {  # kind -> (nx, ndx, nu, ncmax)
     KIND_KINO: (57, 56, 34, 68),
     KIND_FULL: (57, 56, 22, 78),
 }
+
+
+# ---- include/mpcqp_b200.h (batched dense QP)
+class QPSettings(C.Structure):
+    _fields_ = [
+        ("eps_abs", d), ("eps_rel", d), ("rho", d), ("mu_eq", d), ("mu_in", d), ("alpha_bcl", d), ("beta_bcl", d),
+        ("mu_update_factor", d), ("mu_min_eq", d), ("mu_min_in", d),
+        ("max_iter", i32), ("max_iter_in", i32), ("check_duality_gap", i32), ("warm_start", i32),
+    ]
+
+
+class QPInfo(C.Structure):
+    _fields_ = [
+        ("status", i32), ("iter", i32), ("iter_in", i32), ("mu_updates", i32),
+        ("pri_res", d), ("dua_res", d), ("duality_gap", d), ("objective", d),
+    ]

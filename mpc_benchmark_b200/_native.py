@@ -16,6 +16,8 @@ EXPORTS = [
     "mpc_create", "mpc_destroy", "mpc_last_error", "mpc_setup", "mpc_update_knots", "mpc_update_terms", "mpc_cycle", "mpc_set_x0", "mpc_shift_multipliers", "mpc_reconfigure",
     "mpc_run", "mpc_run_pipelined", "mpc_run_device", "mpc_tick", "mpc_get_results", "mpc_export_results_device", "mpc_result_ptrs", "mpc_get_stage_data", "mpc_last_launches", "mpc_last_device_ms",
     "mpc_get_feedback", "mpc_last_kernel_ms", "mpc_last_kernel_launches", "mpc_set_profiling",
+    "mpc_qp_create", "mpc_qp_destroy", "mpc_qp_last_error", "mpc_qp_default_settings", "mpc_qp_update", "mpc_qp_solve", "mpc_qp_solve_device",
+    "mpc_qp_last_device_ms", "mpc_qp_abi_sizeof", "mpc_qp_assemble_id",
     "mpc_reset_multipliers", "mpc_debug_lq", "mpc_debug_gemm_tn", "mpc_debug_phases", "mpc_workspace_bytes", "mpc_abi_sizeof", "mpc_measure_fp64_peak", "mpc_measure_fp64_peak_dmma",
 ]
 
@@ -68,6 +70,20 @@ def lib():
         L.mpc_measure_fp64_peak.restype = C.c_double
         L.mpc_measure_fp64_peak_dmma.argtypes = [C.c_int32]
         L.mpc_measure_fp64_peak_dmma.restype = C.c_double
+        # include/mpcqp_b200.h (batched dense QP)
+        i64, u64, i32p = C.c_int64, C.c_uint64, C.POINTER(C.c_int32)
+        L.mpc_qp_create.restype = C.c_void_p
+        L.mpc_qp_create.argtypes = [C.c_int32] * 6
+        L.mpc_qp_destroy.argtypes = [C.c_void_p]
+        L.mpc_qp_last_error.restype = C.c_char_p
+        L.mpc_qp_default_settings.argtypes = [C.POINTER(_abi.QPSettings)]
+        L.mpc_qp_update.argtypes = [C.c_void_p, C.c_int32] + [dp, i64] * 9
+        L.mpc_qp_solve.argtypes = [C.c_void_p, C.POINTER(_abi.QPSettings), dp, dp, dp, C.c_void_p]
+        L.mpc_qp_solve_device.argtypes = [C.c_void_p, C.c_int32, C.POINTER(_abi.QPSettings)] + [u64, i64] * 9 + [u64] * 5
+        L.mpc_qp_last_device_ms.argtypes = [C.c_void_p]
+        L.mpc_qp_last_device_ms.restype = C.c_double
+        L.mpc_qp_abi_sizeof.argtypes = [C.c_int32]
+        L.mpc_qp_assemble_id.argtypes = [C.c_void_p, C.c_int32] + [dp] * 6 + [i32p] + [C.c_double] * 3
         _lib = L
     return _lib
 

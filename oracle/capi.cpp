@@ -2,6 +2,7 @@
 // bench.py's cpu_baseline leg ONLY.  The product path (mpc_benchmark_b200 + libmpcb200.so) never loads this.
 // PARITY UNPINNED against upstream Aligator/Pinocchio (absent from /root/reference, README.md:10-18).
 #include "proxddp.hpp"
+#include "qp.hpp"
 #include <cstdio>
 #include <omp.h>
 
@@ -16,6 +17,8 @@ int orc_sizeof(int which) {
   case 2: return sizeof(mpc_knot_t);
   case 3: return sizeof(mpc_term_t);
   case 4: return sizeof(mpc_info_t);
+  case 5: return sizeof(mpc_qp_settings_t);
+  case 6: return sizeof(mpc_qp_info_t);
   }
   return -1;
 }
@@ -279,4 +282,27 @@ double orc_check_kino(const mpc_robot_t *rb, const mpc_config_t *cfg, const mpc_
 }
 
 int orc_num_procs() { return omp_get_num_procs(); }
+
+// ---- dense QP: batch of QPs, OpenMP over the batch; strides in doubles per QP (0 = shared)
+void orc_qp_default_settings(mpc_qp_settings_t *s) { qp_default_settings(*s); }
+int orc_qp_solve(int n, int ne, int ni, int box, int batch, const mpc_qp_settings_t *st, const double *H, long sH, const double *g, long sg,
+                 const double *A, long sA, const double *b, long sb, const double *C, long sC, const double *l, long sl, const double *u, long su,
+                 const double *lb, long slb, const double *ub, long sub, double *x, double *y, double *z, mpc_qp_info_t *info, int threads) {
+  const int nz = ni + (box ? n : 0);
+  int worst = 0;
+#pragma omp parallel for schedule(dynamic) num_threads(threads > 0 ? threads : omp_get_max_threads()) reduction(max : worst)
+  for (int i = 0; i < batch; i++) {
+    QP q{n, ne, ni, box != 0, H + i * sH, g + i * sg, A + i * sA, b + i * sb, C + i * sC, l + i * sl, u + i * su,
+         box ? lb + i * slb : nullptr, box ? ub + i * sub : nullptr};
+    const int s = qp_solve(q, *st, x + (long)i * n, y + (long)i * ne, z + (long)i * nz, info ? info + i : nullptr);
+    worst = std::max(worst, s);
+  }
+  return worst;
+}
+void orc_qp_assemble_id(int batch, const double *M, const double *nle, const double *Jc, const double *gamma, const double *a, const double *forces,
+                        const int32_t *cs, double mu, double L, double W, double *A, double *b, double *C, double *l) {
+  for (int i = 0; i < batch; i++)
+    qp_assemble_id(M + i * 784, nle + i * 28, Jc + i * 336, gamma + i * 12, a + i * 28, forces + i * 12, cs + i * 2, mu, L, W, A + i * 2480, b + i * 40,
+                   C + i * 1116, l + i * 18);
+}
 }

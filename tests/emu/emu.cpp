@@ -4,6 +4,7 @@
 #define MPC_HOST_EMU 1
 #include "../../mpc_benchmark_b200/csrc/driver.hpp"
 #include "../../mpc_benchmark_b200/csrc/ws_alloc.hpp"
+#include "../../mpc_benchmark_b200/csrc/qp.cuh"
 #include <cstdlib>
 #include <cstdio>
 #include <cstdlib>
@@ -100,4 +101,23 @@ extern "C" int emu_solve(const mpc_robot_t *rb, const mpc_config_t *cfg, int bat
   for (void *p : allocs) free(p);
   delete model;
   return 0;
+}
+
+// ---- batched dense QP (qp.cuh) run serially: same source as k_qp_solve / k_qp_assemble_id
+extern "C" int emu_qp_solve(int n, int ne, int ni, int box, int batch, const mpc_qp_settings_t *st, const double *H, long sH, const double *g, long sg,
+                            const double *A, long sA, const double *b, long sb, const double *C, long sC, const double *l, long sl, const double *u, long su,
+                            const double *lb, long slb, const double *ub, long sub, double *x, double *y, double *z, mpc_qp_info_t *info) {
+  QPArgs P;
+  P.n = n; P.ne = ne; P.ni = ni; P.box = box; P.batch = batch; P.st = *st;
+  P.H = H; P.sH = sH; P.g = g; P.sg = sg; P.A = A; P.sA = sA; P.b = b; P.sb = sb; P.C = C; P.sC = sC; P.l = l; P.sl = sl; P.u = u; P.su = su;
+  P.lb = lb; P.slb = slb; P.ub = ub; P.sub = sub; P.x = x; P.y = y; P.z = z; P.info = info;
+  std::vector<double> smem(qp_smem_doubles(n, ne, ni, box), 0.0);
+  for (int i = 0; i < batch; i++) qp_solve_group(P, i, smem.data());
+  return 0;
+}
+extern "C" void emu_qp_assemble_id(int batch, const double *M, const double *nle, const double *Jc, const double *gamma, const double *a, const double *forces,
+                                   const int32_t *cs, double mu, double L, double W, double *A, double *b, double *C, double *l) {
+  for (int i = 0; i < batch; i++)
+    qp_assemble_id_group(M + i * 784, nle + i * 28, Jc + i * 336, gamma + i * 12, a + i * 28, forces + i * 12, cs + i * 2, mu, L, W, A + i * 2480, b + i * 40,
+                         C + i * 1116, l + i * 18);
 }

@@ -54,3 +54,23 @@ def solve(prob, max_iters, dump=False, xs=None, us=None, vs=None, lams=None):
 
         out.update(AB=take((T, n, nz)), H=take((T + 1, nz, nz)), g=take((T + 1, nz)), gap=take((T, n)), h=take((T + 1, nc)), scal=take((T + 1, 8)))
     return out
+
+
+def qp_solve(H, g, A, b, Cm, l, u, lb=None, ub=None, settings=None, x=None, y=None, z=None):
+    """The kernel source of the batched QP solver (csrc/qp.cuh) run serially on the host."""
+    import oracle_lib
+
+    dims, args, keep, (X, Y, Z), info = oracle_lib.qp_marshal(H, g, A, b, Cm, l, u, lb, ub, x, y, z)
+    st = settings or oracle_lib.qp_default_settings()
+    lib().emu_qp_solve(*dims, C.byref(st), *args, _p(X), _p(Y), _p(Z), info)
+    return X, Y, Z, info
+
+
+def qp_assemble_id(M, nle, Jc, gamma, a, forces, cs, mu, L, W):
+    batch = np.asarray(M).reshape(-1, 28, 28).shape[0]
+    A, b, Cm, l = np.zeros((batch, 40, 62)), np.zeros((batch, 40)), np.zeros((batch, 18, 62)), np.zeros((batch, 18))
+    cs = np.ascontiguousarray(cs, np.int32)
+    f = lambda v: _p(np.ascontiguousarray(v, float))
+    lib().emu_qp_assemble_id(batch, f(M), f(nle), f(Jc), f(gamma), f(a), f(forces), cs.ctypes.data_as(C.POINTER(C.c_int32)), C.c_double(mu),
+                             C.c_double(L), C.c_double(W), _p(A), _p(b), _p(Cm), _p(l))
+    return A, b, Cm, l

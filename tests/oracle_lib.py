@@ -175,3 +175,57 @@ def solve(prob, max_iters=None, inst_threads=1, knot_threads=1, vs=None, lams=No
                     _p(xs), _p(us), _p(K), _p(vs), _p(lams), info, _p(stage0), int(cfg.max_iters if max_iters is None else max_iters),
                     int(inst_threads), int(knot_threads))
     return dict(xs=xs, us=us, K=K, vs=vs, lams=lams, info=info, stage0=stage0)
+
+
+# ---- dense QP oracle (oracle/qp.hpp)
+def qp_default_settings(**kw):
+    s = _abi.QPSettings()
+    lib().orc_qp_default_settings(C.byref(s))
+    for k, v in kw.items():
+        assert hasattr(s, k), k
+        setattr(s, k, v)
+    return s
+
+
+def _bs(a, per):
+    """(contiguous array, batch stride in doubles): arrays without the leading batch axis are shared (stride 0)."""
+    a = np.ascontiguousarray(a, float)
+    return a, (0 if a.size == per else per)
+
+
+def qp_marshal(H, g, A, b, Cm, l, u, lb=None, ub=None, x=None, y=None, z=None):
+    """Shapes, (pointer, stride) argument list and output arrays shared by the oracle and the emulation bindings."""
+    g = np.ascontiguousarray(g, float)
+    n = g.shape[-1]
+    ne, ni = np.asarray(b).shape[-1], np.asarray(l).shape[-1]
+    box = lb is not None
+    nz = ni + (n if box else 0)
+    keep, args, batch = [], [], 1
+    for arr, per in ((H, n * n), (g, n), (A, ne * n), (b, ne), (Cm, ni * n), (l, ni), (u, ni), (lb if box else np.zeros(n), n), (ub if box else np.zeros(n), n)):
+        a, s = _bs(arr, per)
+        if s:
+            batch = max(batch, a.size // per)
+        keep.append(a)
+        args += [_p(a) if a.size else None, C.c_long(s)]
+    X = np.zeros((batch, n)) if x is None else np.ascontiguousarray(x, float).reshape(batch, n).copy()
+    Y = np.zeros((batch, ne)) if y is None else np.ascontiguousarray(y, float).reshape(batch, ne).copy()
+    Z = np.zeros((batch, nz)) if z is None else np.ascontiguousarray(z, float).reshape(batch, nz).copy()
+    return (n, ne, ni, int(box), batch), args, keep, (X, Y, Z), (_abi.QPInfo * batch)()
+
+
+def qp_solve(H, g, A, b, Cm, l, u, lb=None, ub=None, settings=None, x=None, y=None, z=None, threads=0):
+    """Batch of QPs through the CPU oracle.  Leading axis = batch; arrays without it are shared between the QPs."""
+    dims, args, keep, (X, Y, Z), info = qp_marshal(H, g, A, b, Cm, l, u, lb, ub, x, y, z)
+    st = settings or qp_default_settings()
+    lib().orc_qp_solve(*dims, C.byref(st), *args, _p(X), _p(Y), _p(Z), info, threads)
+    return X, Y, Z, info
+
+
+def qp_assemble_id(M, nle, Jc, gamma, a, forces, cs, mu, L, W):
+    batch = np.asarray(M).reshape(-1, 28, 28).shape[0]
+    A, b, Cm, l = np.zeros((batch, 40, 62)), np.zeros((batch, 40)), np.zeros((batch, 18, 62)), np.zeros((batch, 18))
+    cs = np.ascontiguousarray(cs, np.int32)
+    f = lambda v: _p(np.ascontiguousarray(v, float))
+    lib().orc_qp_assemble_id(batch, f(M), f(nle), f(Jc), f(gamma), f(a), f(forces), cs.ctypes.data_as(C.POINTER(C.c_int32)), C.c_double(mu),
+                             C.c_double(L), C.c_double(W), _p(A), _p(b), _p(Cm), _p(l))
+    return A, b, Cm, l

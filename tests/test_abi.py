@@ -10,17 +10,23 @@ from mpc_benchmark_b200 import _abi, _native
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 STRUCTS = [(0, _abi.Robot), (1, _abi.Config), (2, _abi.Knot), (3, _abi.Term), (4, _abi.Info)]
+QP_STRUCTS = [(0, _abi.QPSettings), (1, _abi.QPInfo)]
 
 
 def test_struct_sizes_match_oracle(oracle):
     for which, s in STRUCTS:
         assert oracle.lib().orc_sizeof(which) == C.sizeof(s)
+    for which, s in QP_STRUCTS:
+        assert oracle.lib().orc_sizeof(5 + which) == C.sizeof(s)
 
 
 def _header_functions():
-    src = open(os.path.join(ROOT, "include", "mpcb200.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(mpc_[a-z0-9_]+)\s*\(", src)))
+    names = set()
+    for hdr in ("mpcb200.h", "mpcqp_b200.h"):  # every header under include/
+        src = open(os.path.join(ROOT, "include", hdr)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(mpc_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
 
 
 def test_library_exports_every_declared_symbol():
@@ -36,6 +42,9 @@ def test_library_exports_every_declared_symbol():
     lib.mpc_abi_sizeof.argtypes = [C.c_int32]
     for which, s in STRUCTS:
         assert lib.mpc_abi_sizeof(which) == C.sizeof(s)
+    lib.mpc_qp_abi_sizeof.argtypes = [C.c_int32]
+    for which, s in QP_STRUCTS:
+        assert lib.mpc_qp_abi_sizeof(which) == C.sizeof(s)
 
 
 def test_create_fails_loudly_without_gpu():
