@@ -83,6 +83,9 @@ int32_t mpc_qp_solve_device(mpc_qp_t *h, int32_t batch, const mpc_qp_settings_t 
 /* Device time of the last solve kernel (ms, CUDA events on the launch stream; synchronises). */
 double mpc_qp_last_device_ms(mpc_qp_t *h);
 int32_t mpc_qp_abi_sizeof(int32_t which); /* 0 settings, 1 info */
+/* Cycle counters per phase of the solve kernel, summed over the QPs since the last call (all zero unless built with
+ * -DMPC_QP_PHASE_TIMING): load, residuals, AL gradient, Newton matrix, Cholesky, substitutions, linesearch, multiplier update. */
+int32_t mpc_qp_debug_phases(mpc_qp_t *h, double *out8);
 
 /* Whole-body inverse-dynamics QP of the reference assembled on the device (IDSolver_ulim.computeMatrice, QP_utils.py:514-552;
  * n = 2 nv - 6 + 6 nk, n_eq = nv + 6 nk, n_in = 9 nk with nv = 28, nk = 2): from HOST arrays per instance M [nv][nv], nle [nv],

@@ -52,6 +52,7 @@ struct mpc_qp {
   Slot H, g, A, b, C, l, u, lb, ub;
   double *dx = nullptr, *dy = nullptr, *dz = nullptr, *dscratch = nullptr;
   mpc_qp_info_t *dinfo = nullptr;
+  long long *dphase = nullptr; // instrumented builds only
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   size_t smem_bytes = 0;
@@ -99,6 +100,7 @@ void mpc_qp_destroy(mpc_qp_t *h) {
   if (!h) return;
   cudaSetDevice(h->device);
   for (Slot *s : {&h->H, &h->g, &h->A, &h->b, &h->C, &h->l, &h->u, &h->lb, &h->ub}) cudaFree(s->d);
+  cudaFree(h->dphase);
   cudaFree(h->dx); cudaFree(h->dy); cudaFree(h->dz); cudaFree(h->dinfo); cudaFree(h->dscratch);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -140,6 +142,10 @@ mpc_qp_t *mpc_qp_create(int32_t n, int32_t n_eq, int32_t n_in, int32_t box, int3
       cudaMalloc(&h->dz, 8 * B * (h->nz ? h->nz : 1)) != cudaSuccess || cudaMalloc(&h->dinfo, sizeof(mpc_qp_info_t) * B) != cudaSuccess ||
       cudaMalloc(&h->dscratch, 8 * B * (784 + 28 + 336 + 12 + 28 + 12 + 1)) != cudaSuccess)
     return bail("cudaMalloc of the QP results failed");
+#ifdef MPC_QP_PHASE_TIMING
+  if (cudaMalloc(&h->dphase, 64) != cudaSuccess) return bail("cudaMalloc failed");
+  cudaMemset(h->dphase, 0, 64);
+#endif
   if (cudaStreamCreate(&h->stream) != cudaSuccess || cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess)
     return bail("stream / event creation failed");
   return h;
@@ -161,6 +167,7 @@ int32_t mpc_qp_update(mpc_qp_t *h, int32_t batch, const double *H, int64_t sH, c
 
 static int fill_args(mpc_qp *h, QPArgs &P, const mpc_qp_settings_t *settings) {
   if (!settings) return fail("null settings");
+  P.phase = h->dphase;
   P.n = h->n; P.ne = h->ne; P.ni = h->ni; P.box = h->box; P.batch = h->batch;
   P.st = *settings;
   return 0;
@@ -211,6 +218,14 @@ int32_t mpc_qp_solve_device(mpc_qp_t *h, int32_t batch, const mpc_qp_settings_t 
   P.x = x ? (double *)x : h->dx; P.y = y ? (double *)y : h->dy; P.z = z ? (double *)z : h->dz;
   P.info = info ? (mpc_qp_info_t *)info : h->dinfo;
   return launch(h, P, stream ? (cudaStream_t)stream : h->stream);
+}
+
+/* instrumented builds (-DMPC_QP_PHASE_TIMING, never the product library): cycles per phase summed over the QPs since the last call */
+int32_t mpc_qp_debug_phases(mpc_qp_t *h, double *out8) {
+  long long c[8] = {0};
+  if (h && h->dphase) { cudaMemcpy(c, h->dphase, 64, cudaMemcpyDeviceToHost); cudaMemset(h->dphase, 0, 64); }
+  for (int i = 0; i < 8; i++) out8[i] = (double)c[i];
+  return 0;
 }
 
 double mpc_qp_last_device_ms(mpc_qp_t *h) {

@@ -5,9 +5,14 @@
 // Written in the group idiom of dev_common.cuh (PAR_FOR / SYNC / ONE_THREAD), so the same source runs serially under the
 // test-only host emulation (tests/emu).
 //
-// Shared memory per QP (n = 62, n_eq = 40, n_in = 18: 107 KB, two QPs per SM): H, the Newton matrix K (factored in place),
-// A, C — all with an ODD leading dimension, so that one-row-per-thread and one-column-per-thread sweeps are both free of bank
-// conflicts — and the vectors.  HBM traffic = the QP data once in, (x, y, z, info) once out.
+// Shared memory per QP (n = 62, n_eq = 40, n_in = 18: 103 KB, two QPs per SM): W = [A; C; H] stacked under one ODD leading
+// dimension (row sweeps over lanes and column sweeps over threads are both free of bank conflicts; W v yields A v, C v, H v in one
+// warp-cooperative pass), ONE n x n buffer with the Newton matrix K in its lower triangle and Q = H + rho I + A'A / mu_e — the part
+// of K that only changes with the equality penalty — transposed in its upper triangle, and the vectors.  Scalars (norms, the
+// linesearch's breakpoint search) are reduced by every warp redundantly, so they cost no block barrier.  (Three QPs per SM — H folded
+// into the K buffer, K rebuilt from A in every Newton step — measured 16 % SLOWER: the third CTA takes the instruction-cache hit
+// rate to 64 %.)
+// HBM traffic = the QP data once in, (x, y, z, info) once out.
 #pragma once
 #include "../../include/mpcqp_b200.h"
 #include "dev_common.cuh"
@@ -21,7 +26,26 @@ struct QPArgs {
   double *x, *y, *z;
   mpc_qp_info_t *info;
   mpc_qp_settings_t st;
+  long long *phase; // 8 cycle counters (builds with -DMPC_QP_PHASE_TIMING only), else unused
 };
+
+#if defined(MPC_QP_PHASE_TIMING) && !defined(MPC_HOST_EMU)
+#define QP_T0() long long qt_ = clock64(); long long qacc_[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define QP_TICK(k) do { const long long n_ = clock64(); qacc_[k] += n_ - qt_; qt_ = n_; } while (0)
+#define QP_TDUMP(inst) do { if (threadIdx.x == 0 && P.phase) for (int k_ = 0; k_ < 8; k_++) atomicAdd((unsigned long long *)P.phase + k_, (unsigned long long)qacc_[k_]); } while (0)
+#else
+#define QP_T0() ((void)0)
+#define QP_TICK(k) ((void)0)
+#define QP_TDUMP(inst) ((void)0)
+#endif
+
+// helpers with several call sites are NOT inlined: the solve kernel is one long loop whose body has to stay inside the instruction
+// cache (12 k SASS instructions = 190 KB with everything inlined: "no instruction" was the second largest stall)
+#ifdef MPC_HOST_EMU
+#define QP_NOINLINE inline
+#else
+#define QP_NOINLINE __device__ __noinline__
+#endif
 
 HD int qp_ld(int n) { return n | 1; }
 // doubles of shared memory one QP needs (host + device)
@@ -31,142 +55,96 @@ HD int qp_ld(int n) { return n | 1; }
 #define QP_HOST_DEV inline __host__ __device__
 #endif
 QP_HOST_DEV int qp_smem_doubles(int n, int ne, int ni, int box) {
-  const int ld = n | 1, nz = ni + (box ? n : 0), np = (n + CB - 1) / CB;
-  return 2 * n * ld + ne * ld + ni * ld + np * CB * CB + 7 * n + 5 * ne + 9 * nz + 64 + 32;
+  const int ld = n | 1, nz = ni + (box ? n : 0), np = (n + CB - 1) / CB, nw = ne + ni + n;
+  return (nw + n) * ld + np * CB * CB + 8 * n + 3 * ne + 7 * nz + 2 * nw + ni + 32;
 }
 
-// group-wide reduction: two sums, one maximum, one minimum -> out[0..3] (visible to every thread after the call)
-HD void qp_reduce(double s0, double s1, double mx, double mn, double *scratch, double *out) {
-#ifdef MPC_HOST_EMU
-  out[0] = s0; out[1] = s1; out[2] = mx; out[3] = mn;
-#else
+// NaN-propagating maximum (fmax drops NaNs; the non-finite status relies on them)
+HD double qp_maxn(double a, double b) { return (b > a || b != b) ? b : a; }
+// Warp-wide reductions.  Every warp of the group runs the small reductions of the solver REDUNDANTLY on the same shared-memory
+// data (lanes over the items, butterfly), so all warps hold bitwise identical results and no block barrier is needed for a scalar.
+HD double qp_wsum(double x) { return WARP_SUM(x); }
+HD double qp_wmax(double x) {
+#ifndef MPC_HOST_EMU
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-  }
-  if (LANE0) { scratch[4 * WARP_ID] = s0; scratch[4 * WARP_ID + 1] = s1; scratch[4 * WARP_ID + 2] = mx; scratch[4 * WARP_ID + 3] = mn; }
-  SYNC();
-  ONE_THREAD {
-    double a = 0, b = 0, c = scratch[2], d = scratch[3];
-    for (int w = 0; w < NWARPS; w++) { a += scratch[4 * w]; b += scratch[4 * w + 1]; c = fmax(c, scratch[4 * w + 2]); d = fmin(d, scratch[4 * w + 3]); }
-    out[0] = a; out[1] = b; out[2] = c; out[3] = d;
-  }
+  for (int o = 16; o > 0; o >>= 1) x = qp_maxn(x, __shfl_xor_sync(0xffffffffu, x, o));
 #endif
-  SYNC();
+  return x;
+}
+HD double qp_wmin(double x) {
+#ifndef MPC_HOST_EMU
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x = fmin(x, __shfl_xor_sync(0xffffffffu, x, o));
+#endif
+  return x;
 }
 
 HD bool qp_inf(double v) { return fabs(v) >= 1e20; }
+QP_NOINLINE double qp_pow(double a, double b) { return pow(a, b); }
 
 struct QPView { // carved shared memory of one QP
-  int n, ne, ni, nz, ld, box;
-  double *Hs, *Ks, *As, *Cs, *Dinv;
-  double *x, *xe, *g, *grad, *dx, *hxg, *hd;  // n
-  double *y, *ye, *re, *b, *Adx;              // ne
-  double *z, *ze, *su, *sl, *cd, *lo, *up, *s, *t; // nz
-  double *red, *sc;                            // 64 reduction scratch, 32 scalars
+  int n, ne, ni, nz, nw, ld, box;
+  double *W;    // [A (ne rows); C (ni rows); H (n rows)], one leading dimension: W v gives A v, C v and H v in ONE sweep
+  double *As, *Cs, *Hs;
+  double *KQ;   // n x n: Newton matrix K in the lower triangle incl. diagonal (factored in place; the blocked Cholesky and the
+                // substitutions never touch the strict upper triangle), Q = H + rho I + A'A / mu_e transposed in the strict upper one
+  double *Qd, *Dinv, *act;
+  double *x, *xe, *g, *grad, *dx, *hxg;            // n
+  double *y, *ye, *re;                             // ne
+  double *z, *ze, *su, *sl, *lo, *up, *t;          // nz
+  double *dual;                                    // n
+  double *wx, *wd;                                 // nw = ne + ni + n: W x and W dx
+  double *sc;
 };
 HD QPView qp_carve(double *m, int n, int ne, int ni, int box) {
   QPView v;
-  v.n = n; v.ne = ne; v.ni = ni; v.box = box; v.nz = ni + (box ? n : 0); v.ld = qp_ld(n);
+  v.n = n; v.ne = ne; v.ni = ni; v.box = box; v.nz = ni + (box ? n : 0); v.nw = ne + ni + n; v.ld = qp_ld(n);
   const int np = (n + CB - 1) / CB;
-  v.Hs = m; m += n * v.ld; v.Ks = m; m += n * v.ld; v.As = m; m += ne * v.ld; v.Cs = m; m += ni * v.ld; v.Dinv = m; m += np * CB * CB;
-  v.x = m; m += n; v.xe = m; m += n; v.g = m; m += n; v.grad = m; m += n; v.dx = m; m += n; v.hxg = m; m += n; v.hd = m; m += n;
-  v.y = m; m += ne; v.ye = m; m += ne; v.re = m; m += ne; v.b = m; m += ne; v.Adx = m; m += ne;
-  v.z = m; m += v.nz; v.ze = m; m += v.nz; v.su = m; m += v.nz; v.sl = m; m += v.nz; v.cd = m; m += v.nz; v.lo = m; m += v.nz; v.up = m; m += v.nz;
-  v.s = m; m += v.nz; v.t = m; m += v.nz;
-  v.red = m; m += 64; v.sc = m;
+  v.W = m; v.As = m; v.Cs = m + ne * v.ld; v.Hs = m + (ne + ni) * v.ld; m += v.nw * v.ld;
+  v.KQ = m; m += n * v.ld; v.Dinv = m; m += np * CB * CB;
+  v.x = m; m += n; v.xe = m; m += n; v.g = m; m += n; v.grad = m; m += n; v.dx = m; m += n; v.hxg = m; m += n; v.Qd = m; m += n;
+  v.y = m; m += ne; v.ye = m; m += ne; v.re = m; m += ne;
+  v.z = m; m += v.nz; v.ze = m; m += v.nz; v.su = m; m += v.nz; v.sl = m; m += v.nz; v.lo = m; m += v.nz; v.up = m; m += v.nz; v.t = m; m += v.nz;
+  v.dual = m; m += n;
+  v.wx = m; m += v.nw; v.wd = m; m += v.nw; v.act = m; m += ni; v.sc = m;
   return v;
 }
-// scalar slots in v.sc
-enum { QS_PRI = 0, QS_DUA, QS_GAP, QS_OBJ, QS_PRIS, QS_DUAS, QS_GAPS, QS_A0, QS_B0, QS_LO, QS_HI, QS_ALPHA, QS_R0, QS_R1, QS_R2, QS_R3 };
+enum { QS_PRI = 0, QS_DUA, QS_GAP, QS_OBJ, QS_PRIS, QS_DUAS, QS_GAPS, QS_NACT };
 
-HD double qp_rowdot(const double *row, const double *v, int n) {
-  double s = 0;
-  for (int j = 0; j < n; j++) s += row[j] * v[j];
-  return s;
-}
+// value of inequality row i (general rows, then the identity rows of the box) from a product W v stored in wv, v itself for the box
+HD double qp_ineq(const QPView &v, const double *wv, const double *vec, int i) { return (i < v.ni) ? wv[v.ne + i] : vec[i - v.ni]; }
 
-// primal / dual residuals, duality gap and their scales at (x, y, z) -> v.sc[QS_PRI..QS_GAPS]  (oracle/qp.hpp qp_residuals)
-HD void qp_residuals(const QPView &v) {
-  const int n = v.n, ne = v.ne, nz = v.nz, ld = v.ld;
-  double pri = 0, nAx = 0, nCx = 0, by = 0, bz = 0;
-  PAR_FOR(w, ne + nz) {
-    if (w < ne) {
-      const double ax = qp_rowdot(v.As + w * ld, v.x, n), s = ax - v.b[w];
-      pri = fmax(pri, fabs(s)); nAx = fmax(nAx, fabs(ax)); by += v.b[w] * v.y[w];
-    } else {
-      const int i = w - ne;
-      const double s = (i < v.ni) ? qp_rowdot(v.Cs + i * ld, v.x, n) : v.x[i - v.ni];
-      nCx = fmax(nCx, fabs(s));
-      double viol = 0;
-      if (!qp_inf(v.up[i])) viol += fmax(s - v.up[i], 0.0);
-      if (!qp_inf(v.lo[i])) viol += fmin(s - v.lo[i], 0.0);
-      pri = fmax(pri, fabs(viol));
-      const double zi = v.z[i];
-      if (zi > 0 && !qp_inf(v.up[i])) bz += v.up[i] * zi;
-      if (zi < 0 && !qp_inf(v.lo[i])) bz += v.lo[i] * zi;
-    }
-  }
-  qp_reduce(by, bz, pri, 0.0, v.red, v.sc + QS_R0);
-  const double by_t = v.sc[QS_R0], bz_t = v.sc[QS_R1], pri_t = v.sc[QS_R2];
-  SYNC();
-  qp_reduce(0.0, 0.0, fmax(nAx, nCx), 0.0, v.red, v.sc + QS_R0);
-  const double pris_t = v.sc[QS_R2];
-  SYNC();
-  double xHx = 0, gx = 0, dua = 0, m1 = 0, m2 = 0;
-  PAR_FOR(i, n) {
-    const double hx = qp_rowdot(v.Hs + i * ld, v.x, n);
-    double aty = 0, ctz = 0;
-    for (int r = 0; r < ne; r++) aty += v.As[r * ld + i] * v.y[r];
-    for (int k = 0; k < v.ni; k++) ctz += v.Cs[k * ld + i] * v.z[k];
-    if (v.box) ctz += v.z[v.ni + i];
-    xHx += v.x[i] * hx; gx += v.g[i] * v.x[i];
-    dua = fmax(dua, fabs(hx + v.g[i] + aty + ctz));
-    m1 = fmax(m1, fmax(fabs(hx), fabs(v.g[i])));
-    m2 = fmax(m2, fmax(fabs(aty), fabs(ctz)));
-  }
-  qp_reduce(xHx, gx, dua, 0.0, v.red, v.sc + QS_R0);
-  const double xHx_t = v.sc[QS_R0], gx_t = v.sc[QS_R1], dua_t = v.sc[QS_R2];
-  SYNC();
-  qp_reduce(0.0, 0.0, fmax(m1, m2), 0.0, v.red, v.sc + QS_R0);
-  const double duas_t = v.sc[QS_R2];
-  SYNC();
-  ONE_THREAD {
-    v.sc[QS_PRI] = pri_t; v.sc[QS_DUA] = dua_t; v.sc[QS_GAP] = xHx_t + gx_t + by_t + bz_t; v.sc[QS_OBJ] = 0.5 * xHx_t + gx_t;
-    v.sc[QS_PRIS] = pris_t; v.sc[QS_DUAS] = duas_t;
-    v.sc[QS_GAPS] = fmax(fmax(fabs(xHx_t), fabs(gx_t)), fmax(fabs(by_t), fabs(bz_t)));
-  }
+// out = W vec: rows over warps (7 at a time, independent reduction chains), columns over lanes (consecutive doubles: no bank
+// conflicts), butterfly reduction.  Ends with the group barrier.
+QP_NOINLINE void qp_wmatvec(const QPView &v, const double *vec, double *out) {
+  matvec_rows<7>(v.W, v.ld, v.nw, v.n, vec, nullptr, out);
   SYNC();
 }
 
-// primal residual only (the BCL test)
-HD double qp_primal_residual(const QPView &v) {
-  const int n = v.n, ne = v.ne, nz = v.nz, ld = v.ld;
+// Residuals at (x, y, z) from wx = W x: every warp redundantly.  Needs v.dual[i] = (H x + g + A'y + C'z)_i from the column phase.
+struct QPRes { double pri, dua, gap, obj, pris, duas, gaps; };
+HD double qp_primal_residual(const QPView &v) { // max(|A x - b|, [s - u]+ + [s - l]-): lanes over the rows
   double pri = 0;
-  PAR_FOR(w, ne + nz) {
-    if (w < ne) pri = fmax(pri, fabs(qp_rowdot(v.As + w * ld, v.x, n) - v.b[w]));
+  LANE_FOR(w, v.ne + v.nz) {
+    if (w < v.ne) pri = qp_maxn(pri, fabs(v.wx[w] - v.re[w])); // (v.re holds b here: see the call sites)
     else {
-      const int i = w - ne;
-      const double s = (i < v.ni) ? qp_rowdot(v.Cs + i * ld, v.x, n) : v.x[i - v.ni];
+      const int i = w - v.ne;
+      const double s = qp_ineq(v, v.wx, v.x, i);
       double viol = 0;
       if (!qp_inf(v.up[i])) viol += fmax(s - v.up[i], 0.0);
       if (!qp_inf(v.lo[i])) viol += fmin(s - v.lo[i], 0.0);
-      pri = fmax(pri, fabs(viol));
+      pri = qp_maxn(pri, fabs(viol));
     }
   }
-  qp_reduce(0.0, 0.0, pri, 0.0, v.red, v.sc + QS_R0);
-  const double r = v.sc[QS_R2];
-  SYNC();
-  return r;
+  return qp_wmax(pri);
 }
 
-// K = H + rho I + A'A / mu_e + C_act' C_act / mu_i (lower triangle incl. diagonal), 2 x 2 register tiles
-HD void qp_newton_matrix(const QPView &v, double rho, double mue, double mui) {
+// Q = H + rho I + A'A / mu_e on 2 x 2 register tiles (strict lower part stored transposed in the upper triangle of KQ, diagonal
+// in Qd): formed once per value of mu_e (at the start and after a BCL penalty update), so that a Newton step only adds the few
+// ACTIVE inequality rows to it.
+QP_NOINLINE void qp_form_Q(const QPView &v, double rho, double mue) {
   const int n = v.n, ne = v.ne, ld = v.ld, th = (n + 1) / 2;
-  const double ime = 1.0 / mue, imi = 1.0 / mui;
+  const double ime = 1.0 / mue;
   PAR_FOR(tile, th * th) {
     const int ti = tile / th, tj = tile % th;
     if (tj > ti) continue;
@@ -174,33 +152,58 @@ HD void qp_newton_matrix(const QPView &v, double rho, double mue, double mui) {
     const bool i1 = i0 + 1 < n, j1 = j0 + 1 < n;
     const int i1o = i1 ? 1 : 0, j1o = j1 ? 1 : 0;
     double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
+#pragma unroll 4
     for (int r = 0; r < ne; r++) {
       const double *ar = v.As + r * ld;
       const double x0 = ar[i0], x1 = ar[i0 + i1o], y0 = ar[j0], y1 = ar[j0 + j1o];
       a00 += x0 * y0; a01 += x0 * y1; a10 += x1 * y0; a11 += x1 * y1;
     }
-    a00 *= ime; a01 *= ime; a10 *= ime; a11 *= ime;
-    double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
-    for (int k = 0; k < v.ni; k++) {
-      if (!(v.su[k] > 0 || v.sl[k] < 0)) continue;
-      const double *cr = v.Cs + k * ld;
-      const double x0 = cr[i0], x1 = cr[i0 + i1o], y0 = cr[j0], y1 = cr[j0 + j1o];
-      c00 += x0 * y0; c01 += x0 * y1; c10 += x1 * y0; c11 += x1 * y1;
-    }
-    a00 += c00 * imi; a01 += c01 * imi; a10 += c10 * imi; a11 += c11 * imi;
+    const double q00 = v.Hs[i0 * ld + j0] + a00 * ime, q01 = v.Hs[i0 * ld + j0 + j1o] + a01 * ime;
+    const double q10 = v.Hs[(i0 + i1o) * ld + j0] + a10 * ime, q11 = v.Hs[(i0 + i1o) * ld + j0 + j1o] + a11 * ime;
     if (i0 == j0) {
-      double d0 = rho, d1 = rho;
-      if (v.box) {
-        if (v.su[v.ni + i0] > 0 || v.sl[v.ni + i0] < 0) d0 += imi;
-        if (i1 && (v.su[v.ni + i0 + 1] > 0 || v.sl[v.ni + i0 + 1] < 0)) d1 += imi;
-      }
-      a00 += d0; a11 += d1;
+      v.Qd[i0] = q00 + rho;
+      if (i1) { v.Qd[i0 + 1] = q11 + rho; v.KQ[j0 * ld + i0 + 1] = q10; }
+    } else {
+      v.KQ[j0 * ld + i0] = q00;
+      if (j1) v.KQ[(j0 + 1) * ld + i0] = q01;
+      if (i1) { v.KQ[j0 * ld + i0 + 1] = q10; if (j1) v.KQ[(j0 + 1) * ld + i0 + 1] = q11; }
     }
-    v.Ks[i0 * ld + j0] = v.Hs[i0 * ld + j0] + a00;
-    if (j1 && j0 + 1 <= i0) v.Ks[i0 * ld + j0 + 1] = v.Hs[i0 * ld + j0 + 1] + a01;
-    if (i1) {
-      v.Ks[(i0 + 1) * ld + j0] = v.Hs[(i0 + 1) * ld + j0] + a10;
-      if (j1) v.Ks[(i0 + 1) * ld + j0 + 1] = v.Hs[(i0 + 1) * ld + j0 + 1] + a11;
+  }
+  SYNC();
+}
+// K = Q + C_act' C_act / mu_i (+ 1 / mu_i on the diagonal for active box rows), lower triangle incl. diagonal: 2 x 2 tiles, tile
+// rows over warps, tile columns over lanes; the compacted list of active general rows (v.act, v.sc[QS_NACT]) comes from the
+// gradient phase.
+HD void qp_newton_matrix(const QPView &v, double mui) {
+  const int n = v.n, ld = v.ld, th = (n + 1) / 2, nact = (int)v.sc[QS_NACT];
+  const double imi = 1.0 / mui;
+  WARP_TILE_FOR(ti, th) {
+    LANE_FOR(tj, ti + 1) {
+      const int i0 = 2 * ti, j0 = 2 * tj;
+      const bool i1 = i0 + 1 < n, j1 = j0 + 1 < n;
+      const int i1o = i1 ? 1 : 0, j1o = j1 ? 1 : 0;
+      double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
+      for (int q = 0; q < nact; q++) {
+        const double *cr = v.Cs + (int)v.act[q] * ld;
+        const double x0 = cr[i0], x1 = cr[i0 + i1o], y0 = cr[j0], y1 = cr[j0 + j1o];
+        c00 += x0 * y0; c01 += x0 * y1; c10 += x1 * y0; c11 += x1 * y1;
+      }
+      if (i0 == j0) {
+        double d0 = v.Qd[i0] + c00 * imi, d1 = i1 ? v.Qd[i0 + 1] + c11 * imi : 0.0;
+        if (v.box) {
+          if (v.su[v.ni + i0] > 0 || v.sl[v.ni + i0] < 0) d0 += imi;
+          if (i1 && (v.su[v.ni + i0 + 1] > 0 || v.sl[v.ni + i0 + 1] < 0)) d1 += imi;
+        }
+        v.KQ[i0 * ld + i0] = d0;
+        if (i1) { v.KQ[(i0 + 1) * ld + i0] = v.KQ[i0 * ld + i0 + 1] + c10 * imi; v.KQ[(i0 + 1) * ld + i0 + 1] = d1; }
+      } else {
+        v.KQ[i0 * ld + j0] = v.KQ[j0 * ld + i0] + c00 * imi;
+        if (j1) v.KQ[i0 * ld + j0 + 1] = v.KQ[(j0 + 1) * ld + i0] + c01 * imi;
+        if (i1) {
+          v.KQ[(i0 + 1) * ld + j0] = v.KQ[j0 * ld + i0 + 1] + c10 * imi;
+          if (j1) v.KQ[(i0 + 1) * ld + j0 + 1] = v.KQ[(j0 + 1) * ld + i0 + 1] + c11 * imi;
+        }
+      }
     }
   }
   SYNC();
@@ -212,15 +215,17 @@ HD void qp_solve_group(const QPArgs &P, int inst, double *smem) {
   const QPView v = qp_carve(smem, n, ne, ni, P.box);
   const int nz = v.nz, ld = v.ld;
   const mpc_qp_settings_t &st = P.st;
+  const double *bg = P.b + inst * P.sb; // b is read where it is used (L1 / L2 resident: n_eq doubles)
+  QP_T0();
   // ---- load the QP
   {
     const double *H = P.H + inst * P.sH, *A = P.A + inst * P.sA, *Cm = P.C + inst * P.sC;
     PAR_FOR(e, n * n) v.Hs[(e / n) * ld + e % n] = H[e];
     PAR_FOR(e, ne * n) v.As[(e / n) * ld + e % n] = A[e];
     PAR_FOR(e, ni * n) v.Cs[(e / n) * ld + e % n] = Cm[e];
-    const double *g = P.g + inst * P.sg, *b = P.b + inst * P.sb, *l = P.l + inst * P.sl, *u = P.u + inst * P.su;
+    const double *g = P.g + inst * P.sg, *l = P.l + inst * P.sl, *u = P.u + inst * P.su;
     PAR_FOR(i, n) { v.g[i] = g[i]; v.x[i] = st.warm_start ? P.x[(long long)inst * n + i] : 0.0; }
-    PAR_FOR(r, ne) { v.b[r] = b[r]; v.y[r] = st.warm_start ? P.y[(long long)inst * ne + r] : 0.0; }
+    PAR_FOR(r, ne) v.y[r] = st.warm_start ? P.y[(long long)inst * ne + r] : 0.0;
     PAR_FOR(i, nz) {
       v.lo[i] = (i < ni) ? l[i] : P.lb[inst * P.slb + i - ni];
       v.up[i] = (i < ni) ? u[i] : P.ub[inst * P.sub + i - ni];
@@ -228,112 +233,164 @@ HD void qp_solve_group(const QPArgs &P, int inst, double *smem) {
     }
   }
   SYNC();
+  QP_TICK(0);
   double mue = st.mu_eq, mui = st.mu_in;
-  const double eta_ext_init = pow(0.1, st.alpha_bcl), eps_in_min = fmin(st.eps_abs, 1e-9);
+  const double eta_ext_init = qp_pow(0.1, st.alpha_bcl), eps_in_min = fmin(st.eps_abs, 1e-9);
   double eta_ext = eta_ext_init, eta_in = 1.0;
   int status = 1, it = 0, it_in = 0, mu_updates = 0;
+  QPRes R = {0, 0, 0, 0, 0, 0, 0};
+  qp_form_Q(v, st.rho, mue);
+  QP_TICK(3);
+  qp_wmatvec(v, v.x, v.wx); // wx = [A x; C x; H x] is kept valid for the current x from here on
   for (;; it++) {
-    qp_residuals(v);
-    const double pri = v.sc[QS_PRI], dua = v.sc[QS_DUA], gap = v.sc[QS_GAP];
-    if (!isfinite(pri) || !isfinite(dua)) { status = 2; break; }
-    const bool ok = pri <= st.eps_abs + st.eps_rel * v.sc[QS_PRIS] && dua <= st.eps_abs + st.eps_rel * v.sc[QS_DUAS] &&
-                    (!st.check_duality_gap || fabs(gap) <= st.eps_abs + st.eps_rel * v.sc[QS_GAPS]);
+    // ---- residuals at (x, y, z)  (oracle/qp.hpp qp_residuals): column phase, then every warp reduces redundantly
+    PAR_FOR(i, n) {
+      double aty = 0, ctz = 0;
+#pragma unroll 4
+      for (int r = 0; r < ne; r++) aty += v.As[r * ld + i] * v.y[r];
+#pragma unroll 4
+      for (int k = 0; k < ni; k++) ctz += v.Cs[k * ld + i] * v.z[k];
+      if (P.box) ctz += v.z[ni + i];
+      v.dual[i] = v.wx[ne + ni + i] + v.g[i] + aty + ctz;
+      v.grad[i] = fmax(fabs(aty), fabs(ctz)); // scale of the dual residual (scratch use of grad)
+    }
+    PAR_FOR(r, ne) v.re[r] = bg[r];
+    SYNC();
+    {
+      double pri = 0, nAC = 0, by = 0, bz = 0, xHx = 0, gx = 0, dua = 0, dsc = 0;
+      LANE_FOR(w, ne + nz) {
+        if (w < ne) { const double ax = v.wx[w]; pri = qp_maxn(pri, fabs(ax - v.re[w])); nAC = fmax(nAC, fabs(ax)); by += v.re[w] * v.y[w]; }
+        else {
+          const int i = w - ne;
+          const double s = qp_ineq(v, v.wx, v.x, i), zi = v.z[i];
+          nAC = fmax(nAC, fabs(s));
+          double viol = 0;
+          if (!qp_inf(v.up[i])) viol += fmax(s - v.up[i], 0.0);
+          if (!qp_inf(v.lo[i])) viol += fmin(s - v.lo[i], 0.0);
+          pri = qp_maxn(pri, fabs(viol));
+          if (zi > 0 && !qp_inf(v.up[i])) bz += v.up[i] * zi;
+          if (zi < 0 && !qp_inf(v.lo[i])) bz += v.lo[i] * zi;
+        }
+      }
+      LANE_FOR(i, n) {
+        const double hx = v.wx[ne + ni + i];
+        xHx += v.x[i] * hx; gx += v.g[i] * v.x[i];
+        dua = qp_maxn(dua, fabs(v.dual[i]));
+        dsc = fmax(dsc, fmax(fmax(fabs(hx), fabs(v.g[i])), v.grad[i]));
+      }
+      by = qp_wsum(by); bz = qp_wsum(bz); xHx = qp_wsum(xHx); gx = qp_wsum(gx);
+      R.pri = qp_wmax(pri); R.dua = qp_wmax(dua); R.pris = qp_wmax(nAC); R.duas = qp_wmax(dsc);
+      R.gap = xHx + gx + by + bz; R.obj = 0.5 * xHx + gx;
+      R.gaps = fmax(fmax(fabs(xHx), fabs(gx)), fmax(fabs(by), fabs(bz)));
+    }
+    QP_TICK(1);
+    if (!isfinite(R.pri) || !isfinite(R.dua)) { status = 2; break; }
+    const bool ok = R.pri <= st.eps_abs + st.eps_rel * R.pris && R.dua <= st.eps_abs + st.eps_rel * R.duas &&
+                    (!st.check_duality_gap || fabs(R.gap) <= st.eps_abs + st.eps_rel * R.gaps);
     if (ok) { status = 0; break; }
     if (it >= st.max_iter) break;
+    SYNC(); // (grad / re scratch is rewritten below)
     PAR_FOR(i, n) v.xe[i] = v.x[i];
     PAR_FOR(r, ne) v.ye[r] = v.y[r];
     PAR_FOR(i, nz) v.ze[i] = v.z[i];
     SYNC();
-    bool failed = false;
+    bool failed = false, stalled = false;
+    const double ime = 1.0 / mue, imi = 1.0 / mui; // (the oracle divides: same value to one rounding)
     for (int in = 0;; in++) {
-      // constraint residuals of the augmented Lagrangian
+      // constraint residuals of the augmented Lagrangian from wx
       PAR_FOR(w, ne + nz) {
-        if (w < ne) v.re[w] = qp_rowdot(v.As + w * ld, v.x, n) - v.b[w] + mue * v.ye[w];
+        if (w < ne) v.re[w] = v.wx[w] - bg[w] + mue * v.ye[w];
         else {
           const int i = w - ne;
-          const double s = (i < ni) ? qp_rowdot(v.Cs + i * ld, v.x, n) : v.x[i - ni];
+          const double s = qp_ineq(v, v.wx, v.x, i);
           const double su = qp_inf(v.up[i]) ? -1e300 : s - v.up[i] + mui * v.ze[i];
           const double sl = qp_inf(v.lo[i]) ? 1e300 : s - v.lo[i] + mui * v.ze[i];
           v.su[i] = su; v.sl[i] = sl;
-          v.t[i] = (fmax(su, 0.0) + fmin(sl, 0.0)) / mui;
+          v.t[i] = (fmax(su, 0.0) + fmin(sl, 0.0)) * imi;
         }
       }
       SYNC();
+      ONE_THREAD { // compacted list of the active general rows for the Newton matrix
+        int c = 0;
+        for (int k = 0; k < ni; k++) if (v.su[k] > 0 || v.sl[k] < 0) v.act[c++] = (double)k;
+        v.sc[QS_NACT] = (double)c;
+      }
       PAR_FOR(i, n) {
-        const double hxg = v.g[i] + st.rho * (v.x[i] - v.xe[i]) + qp_rowdot(v.Hs + i * ld, v.x, n);
+        const double hxg = v.g[i] + st.rho * (v.x[i] - v.xe[i]) + v.wx[ne + ni + i];
         double s = 0, c = 0;
+#pragma unroll 4
         for (int r = 0; r < ne; r++) s += v.As[r * ld + i] * v.re[r];
+#pragma unroll 4
         for (int k = 0; k < ni; k++) c += v.Cs[k * ld + i] * v.t[k];
         if (P.box) c += v.t[ni + i];
         v.hxg[i] = hxg;
-        v.grad[i] = hxg + s / mue + c;
+        v.grad[i] = hxg + s * ime + c;
       }
       SYNC();
       double gn = 0;
-      for (int i = 0; i < n; i++) gn = fmax(gn, fabs(v.grad[i])); // every thread: uniform control flow without another barrier
+      LANE_FOR(i, n) gn = qp_maxn(gn, fabs(v.grad[i]));
+      gn = qp_wmax(gn);
+      QP_TICK(2);
       if (!isfinite(gn)) { failed = true; break; }
-      if (gn <= eta_in || in >= st.max_iter_in) break;
+      if (gn <= eta_in || in >= st.max_iter_in || stalled) break;
       // Newton step on the current active set
-      qp_newton_matrix(v, st.rho, mue, mui);
+      qp_newton_matrix(v, mui);
       PAR_FOR(i, n) v.dx[i] = -v.grad[i];
-      chol_blocked(v.Ks, n, ld, v.Dinv);
-      trsm_blocked(v.Ks, n, ld, v.Dinv, v.dx, 1, 1);
+      QP_TICK(3);
+      chol_blocked(v.KQ, n, ld, v.Dinv);
+      QP_TICK(4);
+      trsm_blocked(v.KQ, n, ld, v.Dinv, v.dx, 1, 1);
+      QP_TICK(5);
       it_in++;
-      // exact linesearch on the piecewise quadratic
-      PAR_FOR(w, ne + nz + n) {
-        if (w < ne) v.Adx[w] = qp_rowdot(v.As + w * ld, v.dx, n);
-        else if (w < ne + nz) { const int i = w - ne; v.cd[i] = (i < ni) ? qp_rowdot(v.Cs + i * ld, v.dx, n) : v.dx[i - ni]; }
-        else { const int i = w - ne - nz; v.hd[i] = qp_rowdot(v.Hs + i * ld, v.dx, n); }
-      }
-      SYNC();
+      // exact linesearch on the piecewise quadratic: wd = [A dx; C dx; H dx], then every warp redundantly
+      qp_wmatvec(v, v.dx, v.wd);
       double a0 = 0, b0 = 0;
-      PAR_FOR(w, ne + n) {
-        if (w < ne) { a0 += v.Adx[w] * v.Adx[w] / mue; b0 += v.Adx[w] * v.re[w] / mue; }
-        else { const int i = w - ne; a0 += v.dx[i] * (v.hd[i] + st.rho * v.dx[i]); b0 += v.dx[i] * v.hxg[i]; }
+      LANE_FOR(w, ne + n) {
+        if (w < ne) { const double ad = v.wd[w] * ime; a0 += ad * v.wd[w]; b0 += ad * v.re[w]; }
+        else { const int i = w - ne; a0 += v.dx[i] * (v.wd[ne + ni + i] + st.rho * v.dx[i]); b0 += v.dx[i] * v.hxg[i]; }
       }
-      qp_reduce(a0, b0, 0.0, 0.0, v.red, v.sc + QS_A0); // -> QS_A0, QS_B0 (QS_LO / QS_HI overwritten below)
-      a0 = v.sc[QS_A0]; b0 = v.sc[QS_B0];
-      SYNC();
+      a0 = qp_wsum(a0); b0 = qp_wsum(b0);
       double lo = 0.0, hi = INFINITY;
-      PAR_FOR(c, 2 * nz) {
+      LANE_FOR(c, 2 * nz) {
         const int i = c >> 1;
-        const double sv = (c & 1) ? v.sl[i] : v.su[i], cdi = v.cd[i];
+        const double sv = (c & 1) ? v.sl[i] : v.su[i], cdi = qp_ineq(v, v.wd, v.dx, i);
         if (cdi == 0 || fabs(sv) >= 1e299) continue;
         const double t = -sv / cdi;
         if (!(t > 0)) continue;
         double d = b0 + a0 * t;
-        for (int k = 0; k < nz; k++) d += v.cd[k] * (fmax(v.su[k] + t * v.cd[k], 0.0) + fmin(v.sl[k] + t * v.cd[k], 0.0)) / mui;
+        for (int k = 0; k < nz; k++) { const double ck = qp_ineq(v, v.wd, v.dx, k); d += ck * imi * (fmax(v.su[k] + t * ck, 0.0) + fmin(v.sl[k] + t * ck, 0.0)); }
         if (d < 0) lo = fmax(lo, t); else hi = fmin(hi, t);
       }
-      qp_reduce(0.0, 0.0, lo, hi, v.red, v.sc + QS_R0);
-      lo = v.sc[QS_R2]; hi = v.sc[QS_R3];
-      SYNC();
+      lo = qp_wmax(lo); hi = qp_wmin(hi);
       const double tm = isfinite(hi) ? 0.5 * (lo + hi) : lo + 1.0;
       double slope = 0, icpt = 0;
-      PAR_FOR(i, nz) {
-        const double cdi = v.cd[i];
-        if (v.su[i] + tm * cdi > 0) { slope += cdi * cdi / mui; icpt += cdi * v.su[i] / mui; }
-        if (v.sl[i] + tm * cdi < 0) { slope += cdi * cdi / mui; icpt += cdi * v.sl[i] / mui; }
+      LANE_FOR(i, nz) {
+        const double cdi = qp_ineq(v, v.wd, v.dx, i);
+        const double ci = cdi * imi;
+        if (v.su[i] + tm * cdi > 0) { slope += ci * cdi; icpt += ci * v.su[i]; }
+        if (v.sl[i] + tm * cdi < 0) { slope += ci * cdi; icpt += ci * v.sl[i]; }
       }
-      qp_reduce(slope, icpt, 0.0, 0.0, v.red, v.sc + QS_R0);
-      double alpha = -(b0 + v.sc[QS_R1]) / (a0 + v.sc[QS_R0]);
-      SYNC();
+      slope = qp_wsum(slope); icpt = qp_wsum(icpt);
+      double alpha = -(b0 + icpt) / (a0 + slope);
       alpha = fmin(fmax(alpha, lo), hi);
       if (!isfinite(alpha)) { failed = true; break; }
       double step = 0, xn = 1.0;
-      for (int i = 0; i < n; i++) { step = fmax(step, fabs(alpha * v.dx[i])); xn = fmax(xn, fabs(v.x[i])); } // every thread (uniform)
+      LANE_FOR(i, n) { step = fmax(step, fabs(alpha * v.dx[i])); xn = fmax(xn, fabs(v.x[i])); }
+      step = qp_wmax(step); xn = qp_wmax(xn);
       SYNC();
       PAR_FOR(i, n) v.x[i] += alpha * v.dx[i];
       SYNC();
-      if (step <= 1e-14 * xn) break; // the Newton step is below the rounding level of x
+      qp_wmatvec(v, v.x, v.wx);
+      QP_TICK(6);
+      stalled = step <= 1e-14 * xn; // the Newton step is below the rounding level of x: leave after the next gradient evaluation
     }
     if (failed) { status = 2; break; }
-    // multiplier estimates at the inner solution, BCL test
+    // ---- multiplier estimates at the inner solution (wx is W x for it), BCL test
     PAR_FOR(w, ne + nz) {
-      if (w < ne) v.y[w] = v.ye[w] + (qp_rowdot(v.As + w * ld, v.x, n) - v.b[w]) / mue;
+      if (w < ne) { v.re[w] = bg[w]; v.y[w] = v.ye[w] + (v.wx[w] - bg[w]) / mue; }
       else {
         const int i = w - ne;
-        const double s = (i < ni) ? qp_rowdot(v.Cs + i * ld, v.x, n) : v.x[i - ni];
+        const double s = qp_ineq(v, v.wx, v.x, i);
         const double zu = qp_inf(v.up[i]) ? 0.0 : fmax(v.ze[i] + (s - v.up[i]) / mui, 0.0);
         const double zl = qp_inf(v.lo[i]) ? 0.0 : fmin(v.ze[i] + (s - v.lo[i]) / mui, 0.0);
         v.z[i] = zu + zl;
@@ -342,19 +399,24 @@ HD void qp_solve_group(const QPArgs &P, int inst, double *smem) {
     SYNC();
     const double pri_new = qp_primal_residual(v);
     if (pri_new <= eta_ext) {
-      eta_ext *= pow(mui, st.beta_bcl);
+      eta_ext *= qp_pow(mui, st.beta_bcl);
       eta_in = fmax(eta_in * mui, eps_in_min);
     } else {
+      SYNC();
       PAR_FOR(r, ne) v.y[r] = v.ye[r];
       PAR_FOR(i, nz) v.z[i] = v.ze[i];
       SYNC();
       const double nmui = fmax(mui * st.mu_update_factor, st.mu_min_in), nmue = fmax(mue * st.mu_update_factor, st.mu_min_eq);
       if (nmui != mui || nmue != mue) mu_updates++;
+      if (nmue != mue) { qp_form_Q(v, st.rho, nmue); QP_TICK(3); }
       mui = nmui; mue = nmue;
-      eta_ext = eta_ext_init * pow(mui, st.alpha_bcl);
+      eta_ext = eta_ext_init * qp_pow(mui, st.alpha_bcl);
       eta_in = fmax(mui, eps_in_min);
     }
+    QP_TICK(7);
   }
+  QP_TDUMP(inst);
+  SYNC();
   PAR_FOR(i, n) P.x[(long long)inst * n + i] = v.x[i];
   PAR_FOR(r, ne) P.y[(long long)inst * ne + r] = v.y[r];
   PAR_FOR(i, nz) P.z[(long long)inst * nz + i] = v.z[i];
@@ -362,7 +424,7 @@ HD void qp_solve_group(const QPArgs &P, int inst, double *smem) {
     ONE_THREAD {
       mpc_qp_info_t &o = P.info[inst];
       o.status = status; o.iter = it; o.iter_in = it_in; o.mu_updates = mu_updates;
-      o.pri_res = v.sc[QS_PRI]; o.dua_res = v.sc[QS_DUA]; o.duality_gap = v.sc[QS_GAP]; o.objective = v.sc[QS_OBJ];
+      o.pri_res = R.pri; o.dua_res = R.dua; o.duality_gap = R.gap; o.objective = R.obj;
     }
   }
 }
