@@ -309,3 +309,110 @@ def test_gpu_large_batch_properties():
     lhs = np.einsum("bij,bj->bi", M, anew) + nle - np.einsum("bji,bj->bi", Jc, fnew * cs)
     lhs[:, 6:] -= tau
     assert np.abs(lhs).max() < 2e-3
+
+
+# ------------------------------------------------------------------------ IKIDSolver_f6 mirror (QP_utils.py:584-768)
+def _ikid_inputs(B, seed=9):
+    """Fixture states + synthetic task terms (base / torso Jacobians, momentum matrix, PD errors) of the right shapes."""
+    d = np.load(FIXTURE)
+    rng = np.random.default_rng(seed)
+    reps = -(-B // d["M"].shape[0])
+    tile = lambda a: np.ascontiguousarray(np.tile(a, (reps,) + (1,) * (a.ndim - 1))[:B])  # noqa: E731
+    t = dict(M=tile(d["M"]), nle=tile(d["nle"]), Jc=tile(d["Jc"]), dJv=tile(d["dJv"]), cs=tile(d["cs"]), forces=tile(d["forces"]), v=tile(d["x"])[:, 29:])
+    t.update(J_base=rng.normal(0, 0.5, (B, 3, 28)), dJv_base=rng.normal(0, 0.1, (B, 3)), J_torso=rng.normal(0, 0.5, (B, 3, 28)),
+             dJv_torso=rng.normal(0, 0.1, (B, 3)), Ag=rng.normal(0, 2.0, (B, 6, 28)), dAgv=rng.normal(0, 0.2, (B, 6)), dH=rng.normal(0, 1.0, (B, 6)),
+             q_diff=rng.normal(0, 0.02, (B, 28)), dq_diff=rng.normal(0, 0.05, (B, 28)), LF_diff=rng.normal(0, 0.01, (B, 6)), dLF_diff=rng.normal(0, 0.02, (B, 6)),
+             RF_diff=rng.normal(0, 0.01, (B, 6)), dRF_diff=rng.normal(0, 0.02, (B, 6)), base_diff=rng.normal(0, 0.02, (B, 3)), dbase_diff=rng.normal(0, 0.05, (B, 3)),
+             torso_diff=rng.normal(0, 0.02, (B, 3)), dtorso_diff=rng.normal(0, 0.05, (B, 3)))
+    Kp = lambda k, m: np.eye(m) * k  # noqa: E731
+    t["K_gains"] = [[Kp(100, 28), Kp(20, 28)], [Kp(400, 6), Kp(40, 6)], None, [Kp(100, 3), Kp(20, 3)]]
+    t["weights"] = [1.0, 100.0, 0.1, 10.0, 1e-3]
+    return t
+
+
+def _ikid_reference_cost(t, i):
+    """H[:nv,:nv], g[:nv] of instance i written as QP_utils.py:677-691 writes them (plain 2-D numpy, one instance)."""
+    w, K, nv = t["weights"], t["K_gains"], 28
+    Jc_left, Jc_right, Jc_base, Jc_torso, Ag = t["Jc"][i][:6], t["Jc"][i][6:], t["J_base"][i], t["J_torso"][i], t["Ag"][i]
+    dJl_v, dJr_v = t["dJv"][i][:6], t["dJv"][i][6:]
+    H = w[0] * np.eye(nv)
+    H += w[1] * Jc_left.transpose() @ Jc_left
+    H += w[1] * Jc_right.transpose() @ Jc_right
+    H += w[2] * Ag.transpose() @ Ag
+    H += w[3] * Jc_base.transpose() @ Jc_base
+    H += w[3] * Jc_torso.transpose() @ Jc_torso
+    g = w[0] * (-K[0][0] @ t["q_diff"][i] - K[0][1] @ t["dq_diff"][i])
+    g += w[1] * (dJl_v - K[1][0] @ t["LF_diff"][i] - K[1][1] @ t["dLF_diff"][i]).transpose() @ Jc_left
+    g += w[1] * (dJr_v - K[1][0] @ t["RF_diff"][i] - K[1][1] @ t["dRF_diff"][i]).transpose() @ Jc_right
+    g -= w[2] * (t["dH"][i] - t["dAgv"][i]).transpose() @ Ag
+    g += w[3] * (t["dJv_base"][i] - K[3][0] @ t["base_diff"][i] - K[3][1] @ t["dbase_diff"][i]).transpose() @ Jc_base
+    g += w[3] * (t["dJv_torso"][i] - K[3][0] @ t["torso_diff"][i] - K[3][1] @ t["dtorso_diff"][i]).transpose() @ Jc_torso
+    return H, g
+
+
+class _NoDeviceQP:
+    """Stands in for proxqp.BatchQP where no GPU exists: records what the mirror hands to the solver."""
+
+    def __init__(self, *a, **k):
+        import types
+
+        self.settings, self.calls = types.SimpleNamespace(), {}
+
+    def init(self, *a, **k):
+        self.calls["init"] = a
+
+    def assemble_id(self, *a):
+        self.calls["assemble_id"] = a
+
+
+def test_ikid_cost_assembly_matches_reference_formulas(monkeypatch):
+    from mpc_benchmark_b200 import pin, proxqp, qp_utils
+
+    monkeypatch.setattr(proxqp.dense, "BatchQP", _NoDeviceQP)
+    B = 6
+    t = _ikid_inputs(B)
+    s = qp_utils.IKIDSolver_f6(pin.load_talos_like()[0], t["weights"], t["K_gains"], 2, MU, FOOT_L, FOOT_W, [0, 1], 2, 3, 6, False, batch=B)
+    rbd = qp_utils.RBDTermsIKID(nle=t["nle"], Jc=t["Jc"], dJv=t["dJv"], J_base=t["J_base"], dJv_base=t["dJv_base"], J_torso=t["J_torso"],
+                                dJv_torso=t["dJv_torso"], Ag=t["Ag"], dAgv=t["dAgv"])
+    s.computeMatrice(rbd, t["cs"], t["v"], t["q_diff"], t["dq_diff"], t["LF_diff"], t["dLF_diff"], t["RF_diff"], t["dRF_diff"], t["base_diff"], t["dbase_diff"],
+                     t["torso_diff"], t["dtorso_diff"], t["forces"], t["dH"], t["M"])
+    for i in range(B):
+        H, g = _ikid_reference_cost(t, i)
+        assert np.abs(s.H[i, :28, :28] - H).max() < 1e-9 * np.abs(H).max()
+        assert np.abs(s.g[i, :28] - g).max() < 1e-9 * max(1.0, np.abs(g).max())
+        assert np.array_equal(np.diag(s.H[i])[28:40], np.full(12, t["weights"][4])) and not s.H[i, 40:, :].any() and not s.g[i, 28:].any()
+    a = s.qp.calls["assemble_id"]
+    assert not a[4].any()  # a = 0: the acceleration itself is the unknown (QP_utils.py:717,757)
+    assert np.array_equal(a[3], t["dJv"] * np.repeat(t["cs"], 6, axis=1))  # gamma = dJ v on the active contacts, no Baumgarte term (QP_utils.py:722-727)
+    assert s.l_box[40] == -100.0 and s.u_box[41] == 160.0 and s.l_box[0] == -100000  # torque limits from effortLimit[6:] (QP_utils.py:612-615)
+
+
+@pytest.mark.gpu
+def test_gpu_ikid_solver_matches_oracle(oracle):
+    from mpc_benchmark_b200 import pin, qp_utils
+
+    B = 48
+    t = _ikid_inputs(B)
+    s = qp_utils.IKIDSolver_f6(pin.load_talos_like()[0], t["weights"], t["K_gains"], 2, MU, FOOT_L, FOOT_W, [0, 1], 2, 3, 6, False, batch=B)
+    rbd = qp_utils.RBDTermsIKID(nle=t["nle"], Jc=t["Jc"], dJv=t["dJv"], J_base=t["J_base"], dJv_base=t["dJv_base"], J_torso=t["J_torso"],
+                                dJv_torso=t["dJv_torso"], Ag=t["Ag"], dAgv=t["dAgv"])
+    anew, fnew, tau = s.solve(rbd, t["cs"], t["v"], t["q_diff"], t["dq_diff"], t["LF_diff"], t["dLF_diff"], t["RF_diff"], t["dRF_diff"], t["base_diff"],
+                              t["dbase_diff"], t["torso_diff"], t["dtorso_diff"], t["forces"], t["dH"], t["M"])
+    # the same QPs through the oracle: cost from the literal formulas, constraints from the oracle's assembly with a = 0, gamma = dJ v
+    n = 62
+    H, g = np.zeros((B, n, n)), np.zeros((B, n))
+    for i in range(B):
+        H[i, :28, :28], g[i, :28] = _ikid_reference_cost(t, i)
+        H[i, np.arange(28, 40), np.arange(28, 40)] = t["weights"][4]
+    gamma = t["dJv"] * np.repeat(t["cs"], 6, axis=1)
+    A, b, Cm, l = oracle.qp_assemble_id(t["M"], t["nle"], t["Jc"], gamma, np.zeros((B, 28)), t["forces"], t["cs"], MU, FOOT_L, FOOT_W)
+    st = oracle.qp_default_settings(eps_abs=1e-3, eps_rel=0.0, max_iter=100, max_iter_in=100, check_duality_gap=1)
+    X, Y, Z, info = oracle.qp_solve(H, g, A, b, Cm, l, np.full(18, 1e5), s.l_box, s.u_box, settings=st)
+    r = s.qp.results
+    same = (r.info.iter_ext == [i.iter for i in info]) & (r.info.iter == [i.iter_in for i in info])
+    assert same.mean() >= 0.9 and (r.info.status == [i.status for i in info]).all() and (r.info.status == 0).all()
+    x = np.concatenate([anew, fnew - t["forces"], tau], axis=1)
+    assert np.abs(x - X)[same].max() < 1e-8 * np.abs(X).max()
+    assert np.abs(x - X).max() < 1e-2 * np.abs(X).max()
+    eff = np.asarray(pin.load_talos_like()[0].effortLimit)[6:]
+    assert (np.abs(tau) <= eff + 2e-3).all()  # the torque box holds
