@@ -551,6 +551,21 @@ def qp_leg(args, device, with_cpu, batch=4096, steps=10):
         solver.solve(rbd, cs, None, a, f, M)
     e2e_s = (time.perf_counter() - t0) / steps
     info = solver.qp.results.info
+    # the same step fed from the MEASURED STATES: rigid-body terms (crba, nonLinearEffects, frame Jacobians, dJ v) on the device too
+    from mpc_benchmark_b200 import problems
+    from mpc_benchmark_b200.batch import BatchSolver
+
+    pr = problems.full_standing_problem(batch=1, T=4)
+    bs = BatchSolver(pr["robot"], pr["cfg"], 1, device=device)
+    xs_meas = tile(d["x"])
+    for _ in range(3):
+        solver.solve_from_state(bs, xs_meas, cs, a, f)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        solver.solve_from_state(bs, xs_meas, cs, a, f)
+    state_s = (time.perf_counter() - t0) / steps
+    solved_state = int((solver.qp.results.info.status == 0).sum())
+    bs.close()
     L, h = _native.lib(), solver.qp._handle()
     st = solver.qp.settings.to_c(False)
     import ctypes as C
@@ -576,6 +591,9 @@ def qp_leg(args, device, with_cpu, batch=4096, steps=10):
            "value": batch / (dev_ms * 1e-3), "unit": "QPs/s", "ms_per_batch": dev_ms,
            "e2e": {"value": batch / e2e_s, "unit": "QPs/s", "h2d_bytes_per_step": int(batch * 8 * (784 + 28 + 336 + 12 + 28 + 12 + 1)),
                    "d2h_bytes_per_step": int(bytes_out), "what": "IDSolver_ulim.solve on host arrays: H2D, assembly kernel, solve kernel, D2H"},
+           "e2e_from_state": {"value": batch / state_s, "unit": "QPs/s", "h2d_bytes_per_step": int(batch * (8 * (57 + 28 + 12) + 8)), "d2h_bytes_per_step": int(bytes_out),
+                              "solved": solved_state, "gpu_launches": 4,
+                              "what": "IDSolver_ulim.solve_from_state: measured states in, rigid-body terms (k_rbd_terms), gamma, assembly and solve kernels on the device (kinodynamic_talos.py:425-445 for the whole batch)"},
            "gpu_launches": 2, "solved": int((info.status == 0).sum()), "mean_outer_iters": outer, "mean_newton_steps": newton,
            "max_pri_res": float(info.pri_res.max()), "max_dua_res": float(info.dua_res.max()),
            "roofline": {"bound": "fp64 (latency-bound in practice: one 128-thread CTA per QP, 2 QPs per SM)", "achieved": flops / (dev_ms * 1e-3) / 1e12, "unit": "TFLOP/s",

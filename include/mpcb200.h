@@ -195,6 +195,14 @@ int32_t mpc_debug_gemm_tn(int32_t mt, int32_t nt, int32_t K, const double *A, in
 /* Per-phase cycle counters (all zero unless built with -DMPC_PHASE_TIMING): out64 = 16 Riccati phases, 16 phases of the
  * derivative evaluation kernel, 16 phases of the values-only (linesearch trial) evaluation kernel, 16 Riccati sub-phases. */
 int32_t mpc_debug_phases(mpc_solver_t *h, double *out64);
+/* Rigid-body terms of the reference's whole-body QPs for `count` measured states x [count][nx] (what kinodynamic_talos.py:425-431 /
+ * QP_utils.py:515-528 take from pinocchio: crba, nonLinearEffects, getFrameJacobian / getFrameJacobianTimeVariation(LOCAL) of the two
+ * sole frames, getFrameVelocity): M [count][nv][nv], nle [count][nv], Jc [count][12][nv], dJv [count][12], vf [count][2][6] (LOCAL:
+ * linear, angular).  Host arrays (any output may be NULL) / device pointers + stream (asynchronous).  Uses the handle's robot model only;
+ * not available for MPC_KIND_CENT. */
+int32_t mpc_rbd_terms(mpc_solver_t *h, int32_t count, const double *x, double *M, double *nle, double *Jc, double *dJv, double *vf);
+int32_t mpc_rbd_terms_device(mpc_solver_t *h, int32_t count, uint64_t x_dev, uint64_t M_dev, uint64_t nle_dev, uint64_t Jc_dev, uint64_t dJv_dev,
+                             uint64_t vf_dev, uint64_t stream);
 uint64_t mpc_workspace_bytes(mpc_solver_t *h);
 int32_t mpc_abi_sizeof(int32_t which); /* 0 robot, 1 config, 2 knot, 3 term, 4 info */
 /* fp64 DFMA peak micro-benchmark (TFLOP/s) used as the roofline denominator. */

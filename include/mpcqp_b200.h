@@ -94,6 +94,14 @@ int32_t mpc_qp_debug_phases(mpc_qp_t *h, double *out8);
 int32_t mpc_qp_assemble_id(mpc_qp_t *h, int32_t batch, const double *M, const double *nle, const double *Jc, const double *gamma,
                            const double *a, const double *forces, const int32_t *cs, double mu, double L, double W);
 
+/* The same assembly fed from MEASURED STATES instead of pinocchio results (kinodynamic_talos.py:425-445 in one call): x [batch][57]
+ * host -> rigid-body terms on the device (mpc_rbd_terms_device of `solver`, a libmpcb200 solver handle created for the same robot) ->
+ * gamma = (dJ v + kd (v_lin + v_ang) on the linear rows) on the active contacts (QP_utils.py:524-528) -> A, b, C, l.  Uploads 100 doubles
+ * per robot instead of 1201. */
+struct mpc_solver;
+int32_t mpc_qp_assemble_id_from_state(mpc_qp_t *h, struct mpc_solver *solver, int32_t batch, const double *x, const double *a, const double *forces,
+                                      const int32_t *cs, double mu, double L, double W, double kd);
+
 #ifdef __cplusplus
 }
 #endif

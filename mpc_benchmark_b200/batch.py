@@ -160,6 +160,15 @@ class BatchSolver:
         _native.check(_native.lib().mpc_get_stage_data(self._h, k, _native.ptr(xdot), _native.ptr(force)), "mpc_get_stage_data")
         return xdot, force
 
+    def rbd_terms(self, x):
+        """Rigid-body terms of the whole-body QPs for the states x [count][nx] (what kinodynamic_talos.py:425-431 takes from pinocchio):
+        dict(M, nle, Jc, dJv, vf).  Uses only the handle's robot model."""
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 57)
+        B = x.shape[0]
+        o = dict(M=np.zeros((B, 28, 28)), nle=np.zeros((B, 28)), Jc=np.zeros((B, 12, 28)), dJv=np.zeros((B, 12)), vf=np.zeros((B, 2, 6)))
+        _native.check(_native.lib().mpc_rbd_terms(self._h, B, _native.ptr(x), *[_native.ptr(o[k]) for k in ("M", "nle", "Jc", "dJv", "vf")]), "mpc_rbd_terms")
+        return o
+
     def feedback(self, k=0):
         """results.controlFeedbacks()[k] for every instance: [batch, nu, ndx]."""
         K = np.empty((self.batch, self.m, self.n))

@@ -1,6 +1,7 @@
 // libmpcb200.so — batched dense QP: kernels + the C-ABI of include/mpcqp_b200.h.
 // One CTA (128 threads) per QP, everything in shared memory (qp.cuh).  No CPU fallback: creation fails without a CUDA device.
 #include "qp.cuh"
+#include "../../include/mpcb200.h"
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
@@ -34,6 +35,16 @@ __global__ void __launch_bounds__(QP_THREADS) k_qp_assemble_id(const AsmArgs P) 
                        P.A + (size_t)i * 2480, P.b + i * 40, P.C + (size_t)i * 1116, P.l + i * 18);
 }
 
+// gamma = (dJ v + kd (v_lin + v_ang) on the linear rows) of the active contacts (QP_utils.py:524-528), in place over dJv
+__global__ void k_qp_gamma(double *dJv, const double *vf, const int32_t *cs, double kd, int batch) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= batch * 12) return;
+  const int i = e / 12, r = e % 12, c = r / 6, rr = r % 6;
+  double g = dJv[e];
+  if (rr < 3) g += kd * (vf[i * 12 + c * 6 + rr] + vf[i * 12 + c * 6 + 3 + rr]);
+  dJv[e] = cs[i * 2 + c] ? g : 0.0;
+}
+
 std::string g_err;
 int fail(const std::string &m) { g_err = m; return 1; }
 #define CUQ(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
@@ -50,7 +61,7 @@ struct Slot { // one data array of the handle: device buffer sized for the full 
 struct mpc_qp {
   int n, ne, ni, box, nz, max_batch, device, batch = 0;
   Slot H, g, A, b, C, l, u, lb, ub;
-  double *dx = nullptr, *dy = nullptr, *dz = nullptr, *dscratch = nullptr;
+  double *dx = nullptr, *dy = nullptr, *dz = nullptr, *dscratch = nullptr, *dstate = nullptr; // dstate: [B][57] states + [B][12] frame velocities
   mpc_qp_info_t *dinfo = nullptr;
   long long *dphase = nullptr; // instrumented builds only
   cudaStream_t stream = nullptr;
@@ -100,7 +111,7 @@ void mpc_qp_destroy(mpc_qp_t *h) {
   if (!h) return;
   cudaSetDevice(h->device);
   for (Slot *s : {&h->H, &h->g, &h->A, &h->b, &h->C, &h->l, &h->u, &h->lb, &h->ub}) cudaFree(s->d);
-  cudaFree(h->dphase);
+  cudaFree(h->dphase); cudaFree(h->dstate);
   cudaFree(h->dx); cudaFree(h->dy); cudaFree(h->dz); cudaFree(h->dinfo); cudaFree(h->dscratch);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -140,7 +151,7 @@ mpc_qp_t *mpc_qp_create(int32_t n, int32_t n_eq, int32_t n_in, int32_t box, int3
   }
   if (cudaMalloc(&h->dx, 8 * B * n) != cudaSuccess || cudaMalloc(&h->dy, 8 * B * (n_eq ? n_eq : 1)) != cudaSuccess ||
       cudaMalloc(&h->dz, 8 * B * (h->nz ? h->nz : 1)) != cudaSuccess || cudaMalloc(&h->dinfo, sizeof(mpc_qp_info_t) * B) != cudaSuccess ||
-      cudaMalloc(&h->dscratch, 8 * B * (784 + 28 + 336 + 12 + 28 + 12 + 1)) != cudaSuccess)
+      cudaMalloc(&h->dscratch, 8 * B * (784 + 28 + 336 + 12 + 28 + 12 + 1)) != cudaSuccess || cudaMalloc(&h->dstate, 8 * B * (57 + 12)) != cudaSuccess)
     return bail("cudaMalloc of the QP results failed");
 #ifdef MPC_QP_PHASE_TIMING
   if (cudaMalloc(&h->dphase, 64) != cudaSuccess) return bail("cudaMalloc failed");
@@ -253,6 +264,35 @@ int32_t mpc_qp_assemble_id(mpc_qp_t *h, int32_t batch, const double *M, const do
   CUQ(cudaMemcpyAsync(da, a, 8 * B * 28, cudaMemcpyHostToDevice, h->stream));
   CUQ(cudaMemcpyAsync(df, forces, 8 * B * 12, cudaMemcpyHostToDevice, h->stream));
   CUQ(cudaMemcpyAsync(dcs, cs, 4 * B * 2, cudaMemcpyHostToDevice, h->stream));
+  P.M = dM; P.nle = dn; P.Jc = dJ; P.gamma = dg; P.a = da; P.forces = df; P.cs = dcs; P.mu = mu; P.L = L; P.W = W;
+  P.A = h->A.d; P.b = h->b.d; P.C = h->C.d; P.l = h->l.d; P.batch = batch;
+  k_qp_assemble_id<<<batch, QP_THREADS, 0, h->stream>>>(P);
+  CUQ(cudaGetLastError());
+  h->A.stride = h->A.per; h->b.stride = h->b.per; h->C.stride = h->C.per; h->l.stride = h->l.per;
+  h->A.set = h->b.set = h->C.set = h->l.set = true;
+  h->batch = batch;
+  return 0;
+}
+
+int32_t mpc_qp_assemble_id_from_state(mpc_qp_t *h, struct mpc_solver *solver, int32_t batch, const double *x, const double *a, const double *forces,
+                                      const int32_t *cs, double mu, double L, double W, double kd) {
+  if (!h || !solver) return fail("null handle");
+  if (h->n != 62 || h->ne != 40 || h->ni != 18) return fail("mpc_qp_assemble_id_from_state: handle is not the whole-body ID shape (n 62, n_eq 40, n_in 18)");
+  if (batch <= 0 || batch > h->max_batch) return fail("mpc_qp_assemble_id_from_state: batch out of range");
+  CUQ(cudaSetDevice(h->device));
+  const size_t B = batch;
+  // scratch layout as in mpc_qp_assemble_id (M, nle, Jc, gamma, a, forces, cs); the states go where a / forces do not reach: behind cs
+  double *s = h->dscratch;
+  double *dM = s; s += B * 784; double *dn = s; s += B * 28; double *dJ = s; s += B * 336; double *dg = s; s += B * 12; double *da = s; s += B * 28;
+  double *df = s; s += B * 12; int32_t *dcs = (int32_t *)s;
+  CUQ(cudaMemcpyAsync(h->dstate, x, 8 * B * 57, cudaMemcpyHostToDevice, h->stream));
+  CUQ(cudaMemcpyAsync(da, a, 8 * B * 28, cudaMemcpyHostToDevice, h->stream));
+  CUQ(cudaMemcpyAsync(df, forces, 8 * B * 12, cudaMemcpyHostToDevice, h->stream));
+  CUQ(cudaMemcpyAsync(dcs, cs, 4 * B * 2, cudaMemcpyHostToDevice, h->stream));
+  if (mpc_rbd_terms_device(solver, batch, (uint64_t)h->dstate, (uint64_t)dM, (uint64_t)dn, (uint64_t)dJ, (uint64_t)dg, (uint64_t)(h->dstate + B * 57), (uint64_t)h->stream) != 0)
+    return fail(std::string("mpc_rbd_terms_device: ") + mpc_last_error());
+  k_qp_gamma<<<(batch * 12 + 127) / 128, 128, 0, h->stream>>>(dg, h->dstate + B * 57, dcs, kd, batch);
+  AsmArgs P;
   P.M = dM; P.nle = dn; P.Jc = dJ; P.gamma = dg; P.a = da; P.forces = df; P.cs = dcs; P.mu = mu; P.L = L; P.W = W;
   P.A = h->A.d; P.b = h->b.d; P.C = h->C.d; P.l = h->l.d; P.batch = batch;
   k_qp_assemble_id<<<batch, QP_THREADS, 0, h->stream>>>(P);

@@ -10,6 +10,7 @@
 // There is deliberately NO CPU fallback: every entry point fails if CUDA is unavailable.
 #include "driver.hpp"
 #include "ws_alloc.hpp"
+#include "rbd_terms.cuh"
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
@@ -112,6 +113,15 @@ __global__ void k_cycle(Ws w, const mpc_knot_t *last) {
 }
 
 // fp64 peak micro-benchmark: 8 independent DFMA chains per thread
+// rigid-body terms of the whole-body QPs for `count` states (rbd_terms.cuh): one 128-thread CTA per state
+__global__ void __launch_bounds__(128) k_rbd_terms(const DevModel *model, const double *x, int count, double *M, double *nle, double *Jc, double *dJv, double *vf) {
+  extern __shared__ double rbd_smem[];
+  const int i = blockIdx.x;
+  if (i >= count) return;
+  FullWsT<false> &w = *reinterpret_cast<FullWsT<false> *>(rbd_smem);
+  rbd_terms_group(*model, x + (size_t)i * (NQ + NV), w, M + (size_t)i * NV * NV, nle + (size_t)i * NV, Jc + (size_t)i * 12 * NV, dJv + (size_t)i * 12, vf + (size_t)i * 12);
+}
+
 __global__ void k_dfma_peak(double *out, int iters) {
   double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
   const double m = 1.0000001, c = 1e-9;
@@ -755,6 +765,39 @@ double mpc_measure_fp64_peak_dmma(int32_t device) {
   cudaFree(out); cudaEventDestroy(e0); cudaEventDestroy(e1);
   double flops = 512.0 * 8.0 * (double)iters * blocks * (threads / 32);
   return flops / (best * 1e-3) / 1e12;
+}
+
+// ---- rigid-body terms in front of the whole-body QPs (include/mpcb200.h)
+int32_t mpc_rbd_terms_device(mpc_solver_t *h, int32_t count, uint64_t x_dev, uint64_t M_dev, uint64_t nle_dev, uint64_t Jc_dev, uint64_t dJv_dev, uint64_t vf_dev,
+                             uint64_t stream) {
+  if (!h) return fail("null handle");
+  if (h->w.kind == MPC_KIND_CENT) return fail("mpc_rbd_terms: the centroidal model has no rigid-body tree");
+  if (count <= 0) return fail("mpc_rbd_terms: count out of range");
+  CK(cudaSetDevice(h->device));
+  static bool attr_set = false;
+  const size_t smem = sizeof(FullWsT<false>);
+  if (!attr_set) { CK(cudaFuncSetAttribute(k_rbd_terms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+  k_rbd_terms<<<count, 128, smem, stream ? (cudaStream_t)stream : h->stream>>>(h->d_model, (const double *)x_dev, count, (double *)M_dev, (double *)nle_dev,
+                                                                                  (double *)Jc_dev, (double *)dJv_dev, (double *)vf_dev);
+  CK(cudaGetLastError());
+  return 0;
+}
+int32_t mpc_rbd_terms(mpc_solver_t *h, int32_t count, const double *x, double *M, double *nle, double *Jc, double *dJv, double *vf) {
+  if (!h) return fail("null handle");
+  if (count <= 0) return fail("mpc_rbd_terms: count out of range");
+  CK(cudaSetDevice(h->device));
+  const size_t B = count, per = (NQ + NV) + NV * NV + NV + 12 * NV + 12 + 12;
+  double *d = nullptr;
+  CK(cudaMalloc(&d, 8 * B * per));
+  double *dx = d, *dM = dx + B * (NQ + NV), *dn = dM + B * NV * NV, *dJ = dn + B * NV, *dd = dJ + B * 12 * NV, *dv = dd + B * 12;
+  int rc = 0;
+  if (cudaMemcpyAsync(dx, x, 8 * B * (NQ + NV), cudaMemcpyHostToDevice, h->stream) != cudaSuccess) rc = fail("H2D of the states failed");
+  if (!rc) rc = mpc_rbd_terms_device(h, count, (uint64_t)dx, (uint64_t)dM, (uint64_t)dn, (uint64_t)dJ, (uint64_t)dd, (uint64_t)dv, 0);
+  auto back = [&](double *dst, const double *src, size_t n) { if (!rc && dst && cudaMemcpyAsync(dst, src, 8 * B * n, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) rc = fail("D2H failed"); };
+  back(M, dM, NV * NV); back(nle, dn, NV); back(Jc, dJ, 12 * NV); back(dJv, dd, 12); back(vf, dv, 12);
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess && !rc) rc = fail("mpc_rbd_terms: kernel failed");
+  cudaFree(d);
+  return rc;
 }
 
 int32_t mpc_abi_sizeof(int32_t which) {

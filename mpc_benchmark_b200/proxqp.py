@@ -192,6 +192,20 @@ class BatchQP:
             raise _native.NativeError(f"mpc_qp_assemble_id failed: {lib.mpc_qp_last_error().decode()}")
 
 
+    def assemble_id_from_state(self, solver, x, a, forces, cs, mu, L, W, kd):
+        """Same blocks from MEASURED STATES x [batch][57]: the rigid-body terms are computed on the device by `solver` (a
+        batch.BatchSolver created for the same robot), nothing but x, a, forces, cs is uploaded."""
+        B = self.batch
+        f = lambda v, per: np.ascontiguousarray(np.broadcast_to(np.asarray(v, float).reshape(-1, per), (B, per)))  # noqa: E731
+        xs, aa, ff = f(x, 57), f(a, 28), f(forces, 12)
+        cs = np.ascontiguousarray(np.broadcast_to(np.asarray(cs).reshape(-1, 2), (B, 2)), dtype=np.int32)
+        lib = _native.lib()
+        rc = lib.mpc_qp_assemble_id_from_state(self._handle(), solver._h, B, _native.ptr(xs), _native.ptr(aa), _native.ptr(ff),
+                                               cs.ctypes.data_as(C.POINTER(C.c_int32)), float(mu), float(L), float(W), float(kd))
+        if rc != 0:
+            raise _native.NativeError(f"mpc_qp_assemble_id_from_state failed: {lib.mpc_qp_last_error().decode()}")
+
+
 class QP(BatchQP):
     """proxsuite.proxqp.dense.QP(n, n_eq, n_in[, box_constraints], dense_backend=...): one QP (a batch of one)."""
 

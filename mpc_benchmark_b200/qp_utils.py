@@ -71,6 +71,16 @@ class IDSolver_ulim:
         torque = x[:, nv + nf:]
         return anew, new_forces, torque
 
+    def solve_from_state(self, solver, x_measured, cs, a, forces):
+        """kinodynamic_talos.py:425-445 in one call for the whole batch: the pinocchio step (crba, nonLinearEffects, frame Jacobians and
+        their time variation at the MEASURED states x_measured [batch][57]) runs on the device through `solver` (a batch.BatchSolver of
+        the same robot), then the assembly and the QP."""
+        self.qp.assemble_id_from_state(solver, x_measured, a, forces, cs, self.mu, self.L, self.W, float(self.baum_Kd[0, 0]))
+        self.qp.solve()
+        nv, nf = self.model.nv, self.force_size * self.nk
+        x = self.qp.results.x
+        return np.asarray(a, float).reshape(self.batch, nv) + x[:, :nv], np.asarray(forces, float).reshape(self.batch, nf) + x[:, nv:nv + nf], x[:, nv + nf:]
+
 
 @dataclass
 class RBDTermsIKID:

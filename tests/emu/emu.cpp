@@ -5,6 +5,7 @@
 #include "../../mpc_benchmark_b200/csrc/driver.hpp"
 #include "../../mpc_benchmark_b200/csrc/ws_alloc.hpp"
 #include "../../mpc_benchmark_b200/csrc/qp.cuh"
+#include "../../mpc_benchmark_b200/csrc/rbd_terms.cuh"
 #include <cstdlib>
 #include <cstdio>
 #include <cstdlib>
@@ -120,4 +121,17 @@ extern "C" void emu_qp_assemble_id(int batch, const double *M, const double *nle
   for (int i = 0; i < batch; i++)
     qp_assemble_id_group(M + i * 784, nle + i * 28, Jc + i * 336, gamma + i * 12, a + i * 28, forces + i * 12, cs + i * 2, mu, L, W, A + i * 2480, b + i * 40,
                          C + i * 1116, l + i * 18);
+}
+
+// ---- rigid-body terms in front of the whole-body QPs (rbd_terms.cuh), serial
+extern "C" int emu_rbd_terms(const mpc_robot_t *rb, const mpc_config_t *cfg, int count, const double *x, double *M, double *nle, double *Jc, double *dJv, double *vf) {
+  DevModel *model = new DevModel;
+  const char *err = nullptr;
+  if (build_dev_model(rb, cfg, model, &err)) { delete model; return 1; }
+  std::vector<double> smem(sizeof(FullWsT<false>) / 8 + 8, 0.0);
+  FullWsT<false> &w = *reinterpret_cast<FullWsT<false> *>(smem.data());
+  for (int i = 0; i < count; i++)
+    rbd_terms_group(*model, x + (size_t)i * 57, w, M + (size_t)i * 784, nle + (size_t)i * 28, Jc + (size_t)i * 336, dJv + (size_t)i * 12, vf + (size_t)i * 12);
+  delete model;
+  return 0;
 }

@@ -74,3 +74,13 @@ def qp_assemble_id(M, nle, Jc, gamma, a, forces, cs, mu, L, W):
     lib().emu_qp_assemble_id(batch, f(M), f(nle), f(Jc), f(gamma), f(a), f(forces), cs.ctypes.data_as(C.POINTER(C.c_int32)), C.c_double(mu),
                              C.c_double(L), C.c_double(W), _p(A), _p(b), _p(Cm), _p(l))
     return A, b, Cm, l
+
+
+def rbd_terms(rb, cfg, x):
+    """csrc/rbd_terms.cuh run serially on the host: dict(M, nle, Jc, dJv, vf) for the states x [count][57]."""
+    x = np.ascontiguousarray(x, float).reshape(-1, 57)
+    B = x.shape[0]
+    o = dict(M=np.zeros((B, 28, 28)), nle=np.zeros((B, 28)), Jc=np.zeros((B, 12, 28)), dJv=np.zeros((B, 12)), vf=np.zeros((B, 2, 6)))
+    rc = lib().emu_rbd_terms(C.byref(rb), C.byref(cfg), B, _p(x), *[_p(o[k]) for k in ("M", "nle", "Jc", "dJv", "vf")])
+    assert rc == 0
+    return o

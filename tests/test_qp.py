@@ -416,3 +416,56 @@ def test_gpu_ikid_solver_matches_oracle(oracle):
     assert np.abs(x - X).max() < 1e-2 * np.abs(X).max()
     eff = np.asarray(pin.load_talos_like()[0].effortLimit)[6:]
     assert (np.abs(tau) <= eff + 2e-3).all()  # the torque box holds
+
+
+# ------------------------------------------------- rigid-body terms in front of the QP (csrc/rbd_terms.cuh; kinodynamic_talos.py:425-431)
+def _check_rbd_terms(o, d):
+    """Against the fixture: M, nle from the oracle's rigid-body code (exact to rounding); Jc, dJ v from central differences of the
+    oracle's foot placements (their truncation error bounds the comparison)."""
+    assert np.abs(o["M"] - d["M"]).max() < 1e-10 * np.abs(d["M"]).max()
+    assert np.abs(o["nle"] - d["nle"]).max() < 1e-10 * np.abs(d["nle"]).max()
+    assert np.abs(o["Jc"] - d["Jc"]).max() < 1e-8
+    assert np.abs(o["vf"] - d["vf"]).max() < 1e-8
+    assert np.abs(o["dJv"] - d["dJv"]).max() < 2e-5
+
+
+def test_emulated_rbd_terms_match_oracle_fixture():
+    import emu_lib
+    from mpc_benchmark_b200 import problems
+
+    d = np.load(FIXTURE)
+    prob = problems.full_standing_problem(batch=1, T=4)
+    _check_rbd_terms(emu_lib.rbd_terms(prob["robot"], prob["cfg"], d["x"]), d)
+
+
+@pytest.mark.gpu
+def test_gpu_rbd_terms_and_solve_from_state(oracle):
+    """x -> (M, nle, Jc, dJ v, vf) on the device, and the whole kinodynamic_talos.py:425-445 step (rigid-body terms, assembly, QP) from
+    the measured states alone, against the committed oracle solutions."""
+    from mpc_benchmark_b200 import pin, problems, qp_utils
+    from mpc_benchmark_b200.batch import BatchSolver
+
+    d = np.load(FIXTURE)
+    B = d["M"].shape[0]
+    prob = problems.full_standing_problem(batch=1, T=4)
+    s = BatchSolver(prob["robot"], prob["cfg"], 1)
+    _check_rbd_terms(s.rbd_terms(d["x"]), d)
+    solver = qp_utils.IDSolver_ulim(pin.load_talos_like()[0], [1, 1], 2, MU, FOOT_L, FOOT_W, [0, 1], 6, False, batch=B)
+    anew, fnew, tau = solver.solve_from_state(s, d["x"], d["cs"], d["a"], d["forces"])
+    x = np.concatenate([anew - d["a"], fnew - d["forces"], tau], axis=1)
+    # the fixture's dJ v carries a finite-difference error of ~1e-5 that the exact device value does not: compare at that level
+    assert np.abs(x - d["x_ref"]).max() < 1e-3 * np.abs(d["x_ref"]).max()
+    assert (solver.qp.results.info.status == 0).all()
+    # and exactly against the oracle fed with the device's own terms
+    o = s.rbd_terms(d["x"])
+    g = o["dJv"].reshape(B, 2, 6).copy()
+    g[:, :, :3] += o["vf"][:, :, :3] + o["vf"][:, :, 3:]
+    gamma = (g * d["cs"][:, :, None]).reshape(B, 12)
+    A, b, Cm, l = oracle.qp_assemble_id(o["M"], o["nle"], o["Jc"], gamma, d["a"], d["forces"], d["cs"], MU, FOOT_L, FOOT_W)
+    H = np.zeros((62, 62))
+    H[:40, :40] = np.eye(40)
+    st = oracle.qp_default_settings(eps_abs=1e-3, eps_rel=0.0, max_iter=10, max_iter_in=10, check_duality_gap=1)
+    X, _, _, info = oracle.qp_solve(H, np.zeros(62), A, b, Cm, l, np.full(18, 1e5), settings=st)
+    same = np.asarray(solver.qp.results.info.iter) == [i.iter_in for i in info]
+    assert same.mean() >= 0.9 and np.abs(x - X)[same].max() < 1e-9 * np.abs(X).max()
+    s.close()
