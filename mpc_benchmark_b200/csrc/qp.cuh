@@ -56,7 +56,7 @@ HD int qp_ld(int n) { return n | 1; }
 #endif
 QP_HOST_DEV int qp_smem_doubles(int n, int ne, int ni, int box) {
   const int ld = n | 1, nz = ni + (box ? n : 0), np = (n + CB - 1) / CB, nw = ne + ni + n;
-  return (nw + n) * ld + np * CB * CB + 8 * n + 3 * ne + 7 * nz + 2 * nw + ni + 32;
+  return (nw + n) * ld + np * CB * CB + 8 * n + 4 * ne + 7 * nz + 2 * nw + ni + 32;
 }
 
 // NaN-propagating maximum (fmax drops NaNs; the non-finite status relies on them)
@@ -90,7 +90,7 @@ struct QPView { // carved shared memory of one QP
                 // substitutions never touch the strict upper triangle), Q = H + rho I + A'A / mu_e transposed in the strict upper one
   double *Qd, *Dinv, *act;
   double *x, *xe, *g, *grad, *dx, *hxg;            // n
-  double *y, *ye, *re;                             // ne
+  double *y, *ye, *re, *b;                         // ne
   double *z, *ze, *su, *sl, *lo, *up, *t;          // nz
   double *dual;                                    // n
   double *wx, *wd;                                 // nw = ne + ni + n: W x and W dx
@@ -103,7 +103,7 @@ HD QPView qp_carve(double *m, int n, int ne, int ni, int box) {
   v.W = m; v.As = m; v.Cs = m + ne * v.ld; v.Hs = m + (ne + ni) * v.ld; m += v.nw * v.ld;
   v.KQ = m; m += n * v.ld; v.Dinv = m; m += np * CB * CB;
   v.x = m; m += n; v.xe = m; m += n; v.g = m; m += n; v.grad = m; m += n; v.dx = m; m += n; v.hxg = m; m += n; v.Qd = m; m += n;
-  v.y = m; m += ne; v.ye = m; m += ne; v.re = m; m += ne;
+  v.y = m; m += ne; v.ye = m; m += ne; v.re = m; m += ne; v.b = m; m += ne;
   v.z = m; m += v.nz; v.ze = m; m += v.nz; v.su = m; m += v.nz; v.sl = m; m += v.nz; v.lo = m; m += v.nz; v.up = m; m += v.nz; v.t = m; m += v.nz;
   v.dual = m; m += n;
   v.wx = m; m += v.nw; v.wd = m; m += v.nw; v.act = m; m += ni; v.sc = m;
@@ -126,7 +126,7 @@ struct QPRes { double pri, dua, gap, obj, pris, duas, gaps; };
 HD double qp_primal_residual(const QPView &v) { // max(|A x - b|, [s - u]+ + [s - l]-): lanes over the rows
   double pri = 0;
   LANE_FOR(w, v.ne + v.nz) {
-    if (w < v.ne) pri = qp_maxn(pri, fabs(v.wx[w] - v.re[w])); // (v.re holds b here: see the call sites)
+    if (w < v.ne) pri = qp_maxn(pri, fabs(v.wx[w] - v.b[w]));
     else {
       const int i = w - v.ne;
       const double s = qp_ineq(v, v.wx, v.x, i);
@@ -215,7 +215,6 @@ HD void qp_solve_group(const QPArgs &P, int inst, double *smem) {
   const QPView v = qp_carve(smem, n, ne, ni, P.box);
   const int nz = v.nz, ld = v.ld;
   const mpc_qp_settings_t &st = P.st;
-  const double *bg = P.b + inst * P.sb; // b is read where it is used (L1 / L2 resident: n_eq doubles)
   QP_T0();
   // ---- load the QP
   {
@@ -225,7 +224,8 @@ HD void qp_solve_group(const QPArgs &P, int inst, double *smem) {
     PAR_FOR(e, ni * n) v.Cs[(e / n) * ld + e % n] = Cm[e];
     const double *g = P.g + inst * P.sg, *l = P.l + inst * P.sl, *u = P.u + inst * P.su;
     PAR_FOR(i, n) { v.g[i] = g[i]; v.x[i] = st.warm_start ? P.x[(long long)inst * n + i] : 0.0; }
-    PAR_FOR(r, ne) v.y[r] = st.warm_start ? P.y[(long long)inst * ne + r] : 0.0;
+    const double *bg = P.b + inst * P.sb;
+    PAR_FOR(r, ne) { v.b[r] = bg[r]; v.y[r] = st.warm_start ? P.y[(long long)inst * ne + r] : 0.0; }
     PAR_FOR(i, nz) {
       v.lo[i] = (i < ni) ? l[i] : P.lb[inst * P.slb + i - ni];
       v.up[i] = (i < ni) ? u[i] : P.ub[inst * P.sub + i - ni];
@@ -254,12 +254,11 @@ HD void qp_solve_group(const QPArgs &P, int inst, double *smem) {
       v.dual[i] = v.wx[ne + ni + i] + v.g[i] + aty + ctz;
       v.grad[i] = fmax(fabs(aty), fabs(ctz)); // scale of the dual residual (scratch use of grad)
     }
-    PAR_FOR(r, ne) v.re[r] = bg[r];
     SYNC();
     {
       double pri = 0, nAC = 0, by = 0, bz = 0, xHx = 0, gx = 0, dua = 0, dsc = 0;
       LANE_FOR(w, ne + nz) {
-        if (w < ne) { const double ax = v.wx[w]; pri = qp_maxn(pri, fabs(ax - v.re[w])); nAC = fmax(nAC, fabs(ax)); by += v.re[w] * v.y[w]; }
+        if (w < ne) { const double ax = v.wx[w]; pri = qp_maxn(pri, fabs(ax - v.b[w])); nAC = fmax(nAC, fabs(ax)); by += v.b[w] * v.y[w]; }
         else {
           const int i = w - ne;
           const double s = qp_ineq(v, v.wx, v.x, i), zi = v.z[i];
@@ -289,7 +288,7 @@ HD void qp_solve_group(const QPArgs &P, int inst, double *smem) {
                     (!st.check_duality_gap || fabs(R.gap) <= st.eps_abs + st.eps_rel * R.gaps);
     if (ok) { status = 0; break; }
     if (it >= st.max_iter) break;
-    SYNC(); // (grad / re scratch is rewritten below)
+    SYNC(); // (the grad scratch is rewritten below)
     PAR_FOR(i, n) v.xe[i] = v.x[i];
     PAR_FOR(r, ne) v.ye[r] = v.y[r];
     PAR_FOR(i, nz) v.ze[i] = v.z[i];
@@ -299,7 +298,7 @@ HD void qp_solve_group(const QPArgs &P, int inst, double *smem) {
     for (int in = 0;; in++) {
       // constraint residuals of the augmented Lagrangian from wx
       PAR_FOR(w, ne + nz) {
-        if (w < ne) v.re[w] = v.wx[w] - bg[w] + mue * v.ye[w];
+        if (w < ne) v.re[w] = v.wx[w] - v.b[w] + mue * v.ye[w];
         else {
           const int i = w - ne;
           const double s = qp_ineq(v, v.wx, v.x, i);
@@ -387,7 +386,7 @@ HD void qp_solve_group(const QPArgs &P, int inst, double *smem) {
     if (failed) { status = 2; break; }
     // ---- multiplier estimates at the inner solution (wx is W x for it), BCL test
     PAR_FOR(w, ne + nz) {
-      if (w < ne) { v.re[w] = bg[w]; v.y[w] = v.ye[w] + (v.wx[w] - bg[w]) / mue; }
+      if (w < ne) v.y[w] = v.ye[w] + (v.wx[w] - v.b[w]) / mue;
       else {
         const int i = w - ne;
         const double s = qp_ineq(v, v.wx, v.x, i);
