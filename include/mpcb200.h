@@ -123,7 +123,9 @@ int32_t mpc_update_knots(mpc_solver_t *h, const mpc_knot_t *knots, int32_t first
 int32_t mpc_update_terms(mpc_solver_t *h, const mpc_term_t *terms);
 /* replaceStageCircular + cycleAppend (full:496-497): drop knot 0, append `last` ([batch]) at T-1. */
 int32_t mpc_cycle(mpc_solver_t *h, const mpc_knot_t *last);
-/* solver.cycleProblem / workspace.cycleAppend (kino:488, full:497): shift the warm multipliers by n knots. */
+/* solver.cycleProblem / workspace.cycleAppend (kino:488, full:497): shift the warm multipliers by n knots — the multipliers of the
+ * running knots and the co-states of x_1..x_T move left and repeat their last entry; the terminal multiplier vs[T] and the
+ * initial-condition co-state lams[0] stay in place. */
 int32_t mpc_shift_multipliers(mpc_solver_t *h, int32_t n);
 /* New robot / weight constants for the same kind, horizon and batch (the shim re-derives them from the object graph at every run). */
 int32_t mpc_reconfigure(mpc_solver_t *h, const mpc_robot_t *robot, const mpc_config_t *cfg);

@@ -365,13 +365,19 @@ int32_t mpc_cycle(mpc_solver_t *h, const mpc_knot_t *last) {
 }
 
 // shift the warm multipliers by `n` knots: vs[k] <- vs[k+n], lams[k] <- lams[k+n], tail zeroed
+// Warm-start shift of the multipliers by n knots (solver.cycleProblem without setup, kinodynamic_talos.py:488).  The constraint
+// multipliers of the RUNNING knots and the co-states of x_1 .. x_T move n knots to the left, the vacated slots repeat the last
+// running knot / the last co-state (as the trajectory warm start repeats its last knot); the terminal constraint's multiplier
+// vs[T] and the initial-condition co-state lams[0] belong to constraints that do not move and stay where they are.  (Round 1
+// shifted all T + 1 slots and zero-filled: that puts the terminal multiplier on a running knot and zeroes the last co-state —
+// the kept-multiplier closed loop diverged within 40 ticks with it and is healthy with this, profiles/r2_closed_loop_kino_keep.txt.)
 __global__ void k_shift_multipliers(Ws w, int n) {
   const size_t b = blockIdx.x, T1 = (size_t)w.T + 1;
   double *V = w.vs + b * T1 * w.nc, *L = w.lams + b * T1 * w.n;
-  for (int k = 0; k <= w.T; k++) {
-    const bool src = (k + n <= w.T);
-    for (int i = threadIdx.x; i < w.nc; i += blockDim.x) V[(size_t)k * w.nc + i] = src ? V[(size_t)(k + n) * w.nc + i] : 0.0;
-    for (int i = threadIdx.x; i < w.n; i += blockDim.x) L[(size_t)k * w.n + i] = src ? L[(size_t)(k + n) * w.n + i] : 0.0;
+  for (int k = 0; k < w.T; k++) {
+    const int sv = (k + n < w.T) ? k + n : w.T - 1, sl = (k + 1 + n <= w.T) ? k + 1 + n : w.T;
+    for (int i = threadIdx.x; i < w.nc; i += blockDim.x) V[(size_t)k * w.nc + i] = V[(size_t)sv * w.nc + i];
+    for (int i = threadIdx.x; i < w.n; i += blockDim.x) L[(size_t)(k + 1) * w.n + i] = L[(size_t)sl * w.n + i];
     __syncthreads();
   }
 }

@@ -32,3 +32,44 @@ def test_first_hundred_ticks_track():
     hist = closed_loop_oracle.run(B=1, N=60, iters=1, keep=False, mu_init=1e-8, verbose=False, threads=2)
     assert len(hist) == 60 and all(h[7] == 0 for h in hist)
     assert min(h[5] for h in hist) >= 0.5 and 1.0 < hist[-1][8] < 1.04
+
+
+def test_centroidal_loop_walks_the_whole_gait():
+    """BASELINE configs[0] in closed loop at the reference's settings (mu_init = 1e-8, one iteration per tick, multipliers reset:
+    centroidal_talos.py:270-277,298,461): 20 DS / 80 left / 20 DS / 80 right / ... for 450 ticks, ideal plant.  Full steps all the way,
+    the CoM height holds, the stance foot carries the weight (profiles/r2_closed_loop_cent.txt)."""
+    import closed_loop_oracle_cent
+
+    hist = closed_loop_oracle_cent.run(B=2, N=450, iters=1, mu_init=1e-8, verbose=False, threads=2)
+    assert len(hist) == 450
+    assert all(0.89 < h[5] and h[6] < 0.92 for h in hist)  # CoM height
+    # full steps except for a few ticks right after a contact switch reaches knot 0 (ticks 120-125, 202-208), from which the loop recovers
+    assert sum(1 for h in hist if h[3] < 0.99) <= 25 and min(h[3] for h in hist) >= 0.01 and all(h[3] == 1.0 for h in hist[-150:])
+    assert max(h[1] for h in hist) < 15.0  # primal infeasibility bounded (N / N m on the cone rows)
+
+
+def test_kinodynamic_loop_walks_through_the_first_step():
+    """BASELINE configs[1] in closed loop at the reference's settings (one iteration per tick, mu_init = 1e-8), multipliers reset:
+    the first single-support phase arrives at the front of the horizon at tick 120 and leaves at tick 200 — exactly where the
+    full-dynamics loop degrades; the kinodynamic loop keeps taking full steps (the whole 840-tick gait: profiles/r2_closed_loop_kino_reset.txt)."""
+    import closed_loop_oracle
+    from mpc_benchmark_b200 import _abi
+
+    hist = closed_loop_oracle.run(B=1, N=215, iters=1, keep=False, mu_init=1e-8, verbose=False, threads=2, kind=_abi.KIND_KINO)
+    assert len(hist) == 215 and all(h[7] == 0 for h in hist)
+    # a few short backtracking bursts when a contact switch enters / leaves the horizon (ticks 19-26, 101-109, 120-127, 202), each
+    # followed by full steps again; nothing fails, the infeasibility stays bounded and the base stays at its height
+    assert sum(1 for h in hist if h[5] < 0.99) <= 40 and hist[-1][5] == 1.0 and sum(1 for h in hist[-50:] if h[5] < 0.99) <= 2
+    assert max(h[2] for h in hist) < 10.0 and 1.0 < hist[-1][8] < 1.03
+
+
+def test_kinodynamic_loop_with_kept_multipliers():
+    """kinodynamic_talos.py:488 cycles the problem WITHOUT solver.setup: the multipliers are kept and shifted.  With the shift of
+    mpc_shift_multipliers (running knots / co-states move, terminal multiplier and lams[0] stay, last entry repeated) the loop is healthy;
+    round 1's shift of all T + 1 slots with zero fill diverges within 40 ticks (profiles/r2_closed_loop_kino_keep.txt)."""
+    import closed_loop_oracle
+    from mpc_benchmark_b200 import _abi
+
+    hist = closed_loop_oracle.run(B=1, N=60, iters=1, keep=True, mu_init=1e-8, verbose=False, threads=2, kind=_abi.KIND_KINO)
+    assert len(hist) == 60 and all(h[7] == 0 for h in hist)
+    assert max(h[2] for h in hist) < 0.1 and sum(1 for h in hist if h[5] < 0.99) <= 12 and all(h[5] == 1.0 for h in hist[-20:])

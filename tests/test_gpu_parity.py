@@ -385,8 +385,9 @@ def test_reference_gait_cold_solve_and_ticks(oracle, kind, ticks, perturb):
         xs_ws = np.concatenate([xs[:, 1:], xs[:, -1:]], axis=1)
         us_ws = np.concatenate([us[:, 1:], us[:, -1:]], axis=1)
         if keep:
-            vs0 = np.concatenate([vs[:, 1:], np.zeros_like(vs[:, :1])], axis=1)
-            lams0 = np.concatenate([lams[:, 1:], np.zeros_like(lams[:, :1])], axis=1)
+            # running knots / co-states of x_1..x_T one knot to the left, last entry repeated; terminal multiplier and lams[0] in place
+            vs0 = np.concatenate([vs[:, 1:-1], vs[:, -2:-1], vs[:, -1:]], axis=1)
+            lams0 = np.concatenate([lams[:, :1], lams[:, 2:], lams[:, -1:]], axis=1)
             assert np.abs(vs0).max() > 0 and np.abs(lams0).max() > 0
         else:
             vs0 = lams0 = None
@@ -398,7 +399,8 @@ def test_reference_gait_cold_solve_and_ticks(oracle, kind, ticks, perturb):
 
 
 def test_shift_multipliers_entry_point():
-    """mpc_shift_multipliers (solver.cycleProblem, kinodynamic_talos.py:488): vs[k] <- vs[k+n], lams[k] <- lams[k+n], tail zeroed."""
+    """mpc_shift_multipliers (solver.cycleProblem, kinodynamic_talos.py:488): running-knot multipliers and the co-states of x_1..x_T move
+    n knots to the left and repeat their last entry; the terminal multiplier vs[T] and the initial-condition co-state lams[0] stay."""
     prob = problems.walk_batch(_abi.KIND_KINO, 2, seed=4, ticks=[99, 80], mirror=[False, False], perturb=False)
     s = BatchSolver(prob["robot"], prob["cfg"], 2)
     s.setup(prob["knots"], prob["terms"], prob["x0"])
@@ -407,8 +409,10 @@ def test_shift_multipliers_entry_point():
     for n in (1, 3):
         s.shift_multipliers(n)
         b = s.results(gains=False)
-        assert np.array_equal(b.vs[:, :-n], a.vs[:, n:]) and np.array_equal(b.lams[:, :-n], a.lams[:, n:])
-        assert not b.vs[:, -n:].any() and not b.lams[:, -n:].any()
+        T = a.vs.shape[1] - 1
+        assert np.array_equal(b.vs[:, :T - n], a.vs[:, n:T]) and np.array_equal(b.lams[:, 1:T + 1 - n], a.lams[:, 1 + n:])
+        assert np.array_equal(b.vs[:, T - n:T], np.repeat(a.vs[:, T - 1:T], n, axis=1)) and np.array_equal(b.lams[:, T + 1 - n:], np.repeat(a.lams[:, T:], n, axis=1))
+        assert np.array_equal(b.vs[:, T], a.vs[:, T]) and np.array_equal(b.lams[:, 0], a.lams[:, 0])
         a = b
     s.close()
 
