@@ -16,6 +16,7 @@
 #pragma once
 #include "../../include/mpcqp_b200.h"
 #include "dev_common.cuh"
+#include "dmma.cuh"
 
 namespace mpcdev {
 
@@ -55,8 +56,8 @@ HD int qp_ld(int n) { return n | 1; }
 #define QP_HOST_DEV inline __host__ __device__
 #endif
 QP_HOST_DEV int qp_smem_doubles(int n, int ne, int ni, int box) {
-  const int ld = n | 1, nz = ni + (box ? n : 0), np = (n + CB - 1) / CB, nw = ne + ni + n;
-  return (nw + n) * ld + np * CB * CB + 8 * n + 4 * ne + 7 * nz + 2 * nw + ni + 32;
+  const int ld = n | 1, nz = ni + (box ? n : 0), np = (n + CB - 1) / CB, nw = ne + ni + n, ldk = CB * np + 4;
+  return nw * ld + CB * np * ldk + 2 * np * CB * CB + 8 * n + 4 * ne + 7 * nz + 2 * nw + ni + 32;
 }
 
 // NaN-propagating maximum (fmax drops NaNs; the non-finite status relies on them)
@@ -84,11 +85,13 @@ QP_NOINLINE double qp_pow(double a, double b) { return pow(a, b); }
 
 struct QPView { // carved shared memory of one QP
   int n, ne, ni, nz, nw, ld, box;
+  int np8, ldk; // the Newton-matrix buffer is padded to whole 8 x 8 tiles (identity in the padding); its leading dimension = 4 (mod 8): conflict-free DMMA fragments
   double *W;    // [A (ne rows); C (ni rows); H (n rows)], one leading dimension: W v gives A v, C v and H v in ONE sweep
   double *As, *Cs, *Hs;
-  double *KQ;   // n x n: Newton matrix K in the lower triangle incl. diagonal (factored in place; the blocked Cholesky and the
-                // substitutions never touch the strict upper triangle), Q = H + rho I + A'A / mu_e transposed in the strict upper one
-  double *Qd, *Dinv, *act;
+  double *KQ;   // np8 x np8: Newton matrix K in the lower triangle incl. diagonal (factored in place).  The factorisation touches the
+                // lower BLOCK triangle and the diagonal 8 x 8 tiles only, so Q = H + rho I + A'A / mu_e lives transposed in the strictly
+                // upper block triangle; its entries inside the diagonal tiles are in Qb, its diagonal in Qd
+  double *Qb, *Qd, *Dinv, *act;
   double *x, *xe, *g, *grad, *dx, *hxg;            // n
   double *y, *ye, *re, *b;                         // ne
   double *z, *ze, *su, *sl, *lo, *up, *t;          // nz
@@ -101,7 +104,8 @@ HD QPView qp_carve(double *m, int n, int ne, int ni, int box) {
   v.n = n; v.ne = ne; v.ni = ni; v.box = box; v.nz = ni + (box ? n : 0); v.nw = ne + ni + n; v.ld = qp_ld(n);
   const int np = (n + CB - 1) / CB;
   v.W = m; v.As = m; v.Cs = m + ne * v.ld; v.Hs = m + (ne + ni) * v.ld; m += v.nw * v.ld;
-  v.KQ = m; m += n * v.ld; v.Dinv = m; m += np * CB * CB;
+  v.np8 = CB * np; v.ldk = v.np8 + 4;
+  v.KQ = m; m += v.np8 * v.ldk; v.Dinv = m; m += np * CB * CB; v.Qb = m; m += np * CB * CB;
   v.x = m; m += n; v.xe = m; m += n; v.g = m; m += n; v.grad = m; m += n; v.dx = m; m += n; v.hxg = m; m += n; v.Qd = m; m += n;
   v.y = m; m += ne; v.ye = m; m += ne; v.re = m; m += ne; v.b = m; m += ne;
   v.z = m; m += v.nz; v.ze = m; m += v.nz; v.su = m; m += v.nz; v.sl = m; m += v.nz; v.lo = m; m += v.nz; v.up = m; m += v.nz; v.t = m; m += v.nz;
@@ -110,6 +114,9 @@ HD QPView qp_carve(double *m, int n, int ne, int ni, int box) {
   return v;
 }
 enum { QS_PRI = 0, QS_DUA, QS_GAP, QS_OBJ, QS_PRIS, QS_DUAS, QS_GAPS, QS_NACT };
+
+// Q(i, j), i > j: transposed in the strictly upper block triangle of KQ, or in Qb inside a diagonal 8 x 8 tile
+HD double &qp_Q(const QPView &v, int i, int j) { return ((i >> 3) == (j >> 3)) ? v.Qb[(i >> 3) * 64 + (i & 7) * 8 + (j & 7)] : v.KQ[j * v.ldk + i]; }
 
 // value of inequality row i (general rows, then the identity rows of the box) from a product W v stored in wv, v itself for the box
 HD double qp_ineq(const QPView &v, const double *wv, const double *vec, int i) { return (i < v.ni) ? wv[v.ne + i] : vec[i - v.ni]; }
@@ -162,11 +169,11 @@ QP_NOINLINE void qp_form_Q(const QPView &v, double rho, double mue) {
     const double q10 = v.Hs[(i0 + i1o) * ld + j0] + a10 * ime, q11 = v.Hs[(i0 + i1o) * ld + j0 + j1o] + a11 * ime;
     if (i0 == j0) {
       v.Qd[i0] = q00 + rho;
-      if (i1) { v.Qd[i0 + 1] = q11 + rho; v.KQ[j0 * ld + i0 + 1] = q10; }
+      if (i1) { v.Qd[i0 + 1] = q11 + rho; qp_Q(v, i0 + 1, i0) = q10; }
     } else {
-      v.KQ[j0 * ld + i0] = q00;
-      if (j1) v.KQ[(j0 + 1) * ld + i0] = q01;
-      if (i1) { v.KQ[j0 * ld + i0 + 1] = q10; if (j1) v.KQ[(j0 + 1) * ld + i0 + 1] = q11; }
+      qp_Q(v, i0, j0) = q00;
+      if (j1) qp_Q(v, i0, j0 + 1) = q01;
+      if (i1) { qp_Q(v, i0 + 1, j0) = q10; if (j1) qp_Q(v, i0 + 1, j0 + 1) = q11; }
     }
   }
   SYNC();
@@ -175,7 +182,7 @@ QP_NOINLINE void qp_form_Q(const QPView &v, double rho, double mue) {
 // rows over warps, tile columns over lanes; the compacted list of active general rows (v.act, v.sc[QS_NACT]) comes from the
 // gradient phase.
 HD void qp_newton_matrix(const QPView &v, double mui) {
-  const int n = v.n, ld = v.ld, th = (n + 1) / 2, nact = (int)v.sc[QS_NACT];
+  const int n = v.n, ld = v.ld, ldk = v.ldk, th = (n + 1) / 2, nact = (int)v.sc[QS_NACT];
   const double imi = 1.0 / mui;
   WARP_TILE_FOR(ti, th) {
     LANE_FOR(tj, ti + 1) {
@@ -194,14 +201,14 @@ HD void qp_newton_matrix(const QPView &v, double mui) {
           if (v.su[v.ni + i0] > 0 || v.sl[v.ni + i0] < 0) d0 += imi;
           if (i1 && (v.su[v.ni + i0 + 1] > 0 || v.sl[v.ni + i0 + 1] < 0)) d1 += imi;
         }
-        v.KQ[i0 * ld + i0] = d0;
-        if (i1) { v.KQ[(i0 + 1) * ld + i0] = v.KQ[i0 * ld + i0 + 1] + c10 * imi; v.KQ[(i0 + 1) * ld + i0 + 1] = d1; }
+        v.KQ[i0 * ldk + i0] = d0;
+        if (i1) { v.KQ[(i0 + 1) * ldk + i0] = qp_Q(v, i0 + 1, i0) + c10 * imi; v.KQ[(i0 + 1) * ldk + i0 + 1] = d1; }
       } else {
-        v.KQ[i0 * ld + j0] = v.KQ[j0 * ld + i0] + c00 * imi;
-        if (j1) v.KQ[i0 * ld + j0 + 1] = v.KQ[(j0 + 1) * ld + i0] + c01 * imi;
+        v.KQ[i0 * ldk + j0] = qp_Q(v, i0, j0) + c00 * imi;
+        if (j1) v.KQ[i0 * ldk + j0 + 1] = qp_Q(v, i0, j0 + 1) + c01 * imi;
         if (i1) {
-          v.KQ[(i0 + 1) * ld + j0] = v.KQ[j0 * ld + i0 + 1] + c10 * imi;
-          if (j1) v.KQ[(i0 + 1) * ld + j0 + 1] = v.KQ[(j0 + 1) * ld + i0 + 1] + c11 * imi;
+          v.KQ[(i0 + 1) * ldk + j0] = qp_Q(v, i0 + 1, j0) + c10 * imi;
+          if (j1) v.KQ[(i0 + 1) * ldk + j0 + 1] = qp_Q(v, i0 + 1, j0 + 1) + c11 * imi;
         }
       }
     }
@@ -222,6 +229,10 @@ HD void qp_solve_group(const QPArgs &P, int inst, double *smem) {
     PAR_FOR(e, n * n) v.Hs[(e / n) * ld + e % n] = H[e];
     PAR_FOR(e, ne * n) v.As[(e / n) * ld + e % n] = A[e];
     PAR_FOR(e, ni * n) v.Cs[(e / n) * ld + e % n] = Cm[e];
+    PAR_FOR(e, (v.np8 - n) * v.np8) { // identity in the padding rows of the Newton matrix (never written again: the factor of I is I)
+      const int r = n + e / v.np8, c = e % v.np8;
+      if (c <= r) v.KQ[r * v.ldk + c] = (r == c) ? 1.0 : 0.0;
+    }
     const double *g = P.g + inst * P.sg, *l = P.l + inst * P.sl, *u = P.u + inst * P.su;
     PAR_FOR(i, n) { v.g[i] = g[i]; v.x[i] = st.warm_start ? P.x[(long long)inst * n + i] : 0.0; }
     const double *bg = P.b + inst * P.sb;
@@ -241,7 +252,7 @@ HD void qp_solve_group(const QPArgs &P, int inst, double *smem) {
   QPRes R = {0, 0, 0, 0, 0, 0, 0};
   qp_form_Q(v, st.rho, mue);
   QP_TICK(3);
-  qp_wmatvec(v, v.x, v.wx); // wx = [A x; C x; H x] is kept valid for the current x from here on
+  qp_wmatvec(v, v.x, v.wx); // wx = [A x; C x; H x]: computed once, then updated with every accepted step (wx += alpha W dx)
   for (;; it++) {
     // ---- residuals at (x, y, z)  (oracle/qp.hpp qp_residuals): column phase, then every warp reduces redundantly
     PAR_FOR(i, n) {
@@ -336,9 +347,10 @@ HD void qp_solve_group(const QPArgs &P, int inst, double *smem) {
       qp_newton_matrix(v, mui);
       PAR_FOR(i, n) v.dx[i] = -v.grad[i];
       QP_TICK(3);
-      chol_blocked(v.KQ, n, ld, v.Dinv);
+      // factorisation: tensor-core tiles with one-panel look-ahead for the reference's size (57 <= n <= 64), the SIMT panel routine otherwise
+      if (v.np8 == 64) chol_mma<8>(v.KQ, v.ldk, v.Dinv); else chol_blocked(v.KQ, n, v.ldk, v.Dinv);
       QP_TICK(4);
-      trsm_blocked(v.KQ, n, ld, v.Dinv, v.dx, 1, 1);
+      trsm_blocked(v.KQ, n, v.ldk, v.Dinv, v.dx, 1, 1);
       QP_TICK(5);
       it_in++;
       // exact linesearch on the piecewise quadratic: wd = [A dx; C dx; H dx], then every warp redundantly
@@ -378,8 +390,13 @@ HD void qp_solve_group(const QPArgs &P, int inst, double *smem) {
       step = qp_wmax(step); xn = qp_wmax(xn);
       SYNC();
       PAR_FOR(i, n) v.x[i] += alpha * v.dx[i];
+#ifdef QP_FRESH_WX
       SYNC();
       qp_wmatvec(v, v.x, v.wx);
+#else
+      PAR_FOR(w, v.nw) v.wx[w] += alpha * v.wd[w]; // W (x + alpha dx) = W x + alpha W dx: the products with dx are already there
+      SYNC();
+#endif
       QP_TICK(6);
       stalled = step <= 1e-14 * xn; // the Newton step is below the rounding level of x: leave after the next gradient evaluation
     }

@@ -109,6 +109,13 @@ inline int qp_solve(const QP &q, const mpc_qp_settings_t &st, double *x, double 
   const double eta_ext_init = std::pow(0.1, st.alpha_bcl), eps_in_min = std::fmin(st.eps_abs, 1e-9);
   double eta_ext = eta_ext_init, eta_in = 1.0;
   std::vector<double> xe(n), ye(ne), ze(nz), re(ne), su(nz), sl(nz), grad(n), dx(n), K(n * n), Adx(ne), cd(nz), AtA(n * n, 0.0);
+  // A x, [C; I] x and H x are computed once and then carried along every accepted step (W (x + alpha dx) = W x + alpha W dx, the products with
+  // dx being needed by the linesearch anyway): one O(n^2) sweep less per Newton step, and less cancellation noise in the residuals than
+  // re-evaluating them at a nearly converged x
+  std::vector<double> Ax(ne, 0.0), Sx(nz, 0.0), Hx(n, 0.0), Hdx(n, 0.0);
+  for (int r = 0; r < ne; r++) for (int j = 0; j < n; j++) Ax[r] += q.A[r * n + j] * x[j];
+  for (int i = 0; i < nz; i++) Sx[i] = q.row(i, x);
+  for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) Hx[i] += q.H[i * n + j] * x[j];
   for (int r = 0; r < ne; r++) for (int i = 0; i < n; i++) { const double a = q.A[r * n + i]; if (a != 0) for (int j = 0; j < n; j++) AtA[i * n + j] += a * q.A[r * n + j]; }
   int status = 1, it = 0, it_in = 0, mu_updates = 0;
   QPResiduals R{};
@@ -124,15 +131,14 @@ inline int qp_solve(const QP &q, const mpc_qp_settings_t &st, double *x, double 
     //                                               + (|[s - u + mu_i ze]+|^2 + |[s - l + mu_i ze]-|^2) / (2 mu_i),  s = [C; I] x
     bool failed = false;
     for (int in = 0;; in++) {
-      for (int r = 0; r < ne; r++) { double s = -q.b[r] + mue * ye[r]; for (int j = 0; j < n; j++) s += q.A[r * n + j] * x[j]; re[r] = s; }
+      for (int r = 0; r < ne; r++) re[r] = Ax[r] - q.b[r] + mue * ye[r];
       for (int i = 0; i < nz; i++) {
-        const double s = q.row(i, x);
+        const double s = Sx[i];
         su[i] = QP::inf(q.up(i)) ? -1e300 : s - q.up(i) + mui * ze[i];
         sl[i] = QP::inf(q.lo(i)) ? 1e300 : s - q.lo(i) + mui * ze[i];
       }
       for (int i = 0; i < n; i++) {
-        double s = q.g[i] + st.rho * (x[i] - xe[i]);
-        for (int j = 0; j < n; j++) s += q.H[i * n + j] * x[j];
+        double s = q.g[i] + st.rho * (x[i] - xe[i]) + Hx[i];
         for (int r = 0; r < ne; r++) s += q.A[r * n + i] * re[r] / mue;
         grad[i] = s;
       }
@@ -158,10 +164,11 @@ inline int qp_solve(const QP &q, const mpc_qp_settings_t &st, double *x, double 
       double a0 = 0, b0 = 0;
       for (int r = 0; r < ne; r++) { double s = 0; for (int j = 0; j < n; j++) s += q.A[r * n + j] * dx[j]; Adx[r] = s; a0 += s * s / mue; b0 += s * re[r] / mue; }
       for (int i = 0; i < n; i++) {
-        double hd = 0, hx = 0;
-        for (int j = 0; j < n; j++) { hd += q.H[i * n + j] * dx[j]; hx += q.H[i * n + j] * x[j]; }
+        double hd = 0;
+        for (int j = 0; j < n; j++) hd += q.H[i * n + j] * dx[j];
+        Hdx[i] = hd;
         a0 += dx[i] * (hd + st.rho * dx[i]);
-        b0 += dx[i] * (hx + q.g[i] + st.rho * (x[i] - xe[i]));
+        b0 += dx[i] * (Hx[i] + q.g[i] + st.rho * (x[i] - xe[i]));
       }
       for (int i = 0; i < nz; i++) cd[i] = q.row(i, dx.data());
       auto dphi = [&](double t) {
@@ -190,20 +197,26 @@ inline int qp_solve(const QP &q, const mpc_qp_settings_t &st, double *x, double 
       alpha = std::fmin(std::fmax(alpha, lo), hi);
       if (!std::isfinite(alpha)) { failed = true; break; }
       double step = 0, xn = 1.0;
-      for (int i = 0; i < n; i++) { step = std::fmax(step, std::fabs(alpha * dx[i])); xn = std::fmax(xn, std::fabs(x[i])); x[i] += alpha * dx[i]; }
+      for (int i = 0; i < n; i++) { step = std::fmax(step, std::fabs(alpha * dx[i])); xn = std::fmax(xn, std::fabs(x[i])); x[i] += alpha * dx[i]; Hx[i] += alpha * Hdx[i]; }
+      for (int r = 0; r < ne; r++) Ax[r] += alpha * Adx[r];
+      for (int i = 0; i < nz; i++) Sx[i] += alpha * cd[i];
       if (step <= 1e-14 * xn) break; // the Newton step is below the rounding level of x: the inner tolerance is not reachable in fp64
     }
     if (failed) { status = 2; break; }
     // ---- multiplier estimates at the inner solution and the BCL test
-    for (int r = 0; r < ne; r++) { double s = -q.b[r]; for (int j = 0; j < n; j++) s += q.A[r * n + j] * x[j]; y[r] = ye[r] + s / mue; }
+    double pri_new = 0;
+    for (int r = 0; r < ne; r++) { const double s = Ax[r] - q.b[r]; y[r] = ye[r] + s / mue; pri_new = std::fmax(pri_new, std::fabs(s)); }
     for (int i = 0; i < nz; i++) {
-      const double s = q.row(i, x);
+      const double s = Sx[i];
+      double viol = 0;
+      if (!QP::inf(q.up(i))) viol += std::fmax(s - q.up(i), 0.0);
+      if (!QP::inf(q.lo(i))) viol += std::fmin(s - q.lo(i), 0.0);
+      pri_new = std::fmax(pri_new, std::fabs(viol));
       const double zu = QP::inf(q.up(i)) ? 0.0 : std::fmax(ze[i] + (s - q.up(i)) / mui, 0.0);
       const double zl = QP::inf(q.lo(i)) ? 0.0 : std::fmin(ze[i] + (s - q.lo(i)) / mui, 0.0);
       z[i] = zu + zl;
     }
-    const QPResiduals Rn = qp_residuals(q, x, y, z);
-    if (Rn.pri <= eta_ext) {
+    if (pri_new <= eta_ext) {
       eta_ext *= std::pow(mui, st.beta_bcl);
       eta_in = std::fmax(eta_in * mui, eps_in_min);
     } else {
