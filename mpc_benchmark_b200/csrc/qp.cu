@@ -14,7 +14,7 @@ namespace {
 constexpr int QP_THREADS = 128;
 
 __global__ void __launch_bounds__(QP_THREADS) k_qp_solve(const QPArgs P) {
-  extern __shared__ double qp_smem[];
+  extern __shared__ __align__(16) double qp_smem[];
   for (int inst = blockIdx.x; inst < P.batch; inst += gridDim.x) {
     qp_solve_group(P, inst, qp_smem);
     SYNC();

@@ -57,7 +57,7 @@ HD int qp_ld(int n) { return n | 1; }
 #endif
 QP_HOST_DEV int qp_smem_doubles(int n, int ne, int ni, int box) {
   const int ld = n | 1, nz = ni + (box ? n : 0), np = (n + CB - 1) / CB, nw = ne + ni + n, ldk = CB * np + 4;
-  return nw * ld + CB * np * ldk + 2 * np * CB * CB + 8 * n + 4 * ne + 7 * nz + 2 * nw + ni + 32;
+  return nw * ld + 1 + CB * np * ldk + 2 * np * CB * CB + 8 * n + 4 * ne + 7 * nz + 2 * nw + ni + 32; // + 1: the K buffer starts on a 16-byte boundary
 }
 
 // NaN-propagating maximum (fmax drops NaNs; the non-finite status relies on them)
@@ -104,6 +104,7 @@ HD QPView qp_carve(double *m, int n, int ne, int ni, int box) {
   v.n = n; v.ne = ne; v.ni = ni; v.box = box; v.nz = ni + (box ? n : 0); v.nw = ne + ni + n; v.ld = qp_ld(n);
   const int np = (n + CB - 1) / CB;
   v.W = m; v.As = m; v.Cs = m + ne * v.ld; v.Hs = m + (ne + ni) * v.ld; m += v.nw * v.ld;
+  if ((v.nw * v.ld) & 1) m++; // the tensor-core routines store pairs of doubles into the K buffer: keep it 16-byte aligned
   v.np8 = CB * np; v.ldk = v.np8 + 4;
   v.KQ = m; m += v.np8 * v.ldk; v.Dinv = m; m += np * CB * CB; v.Qb = m; m += np * CB * CB;
   v.x = m; m += n; v.xe = m; m += n; v.g = m; m += n; v.grad = m; m += n; v.dx = m; m += n; v.hxg = m; m += n; v.Qd = m; m += n;
@@ -146,12 +147,30 @@ HD double qp_primal_residual(const QPView &v) { // max(|A x - b|, [s - u]+ + [s 
   return qp_wmax(pri);
 }
 
-// Q = H + rho I + A'A / mu_e on 2 x 2 register tiles (strict lower part stored transposed in the upper triangle of KQ, diagonal
-// in Qd): formed once per value of mu_e (at the start and after a BCL penalty update), so that a Newton step only adds the few
-// ACTIVE inequality rows to it.
+// Q = H + rho I + A'A / mu_e (strict lower part stored transposed in the upper block triangle of KQ / in Qb, diagonal in Qd): formed
+// once per value of mu_e (at the start and after a BCL penalty update), so that a Newton step only adds the few ACTIVE inequality rows
+// to it.  A'A is a dense contraction: for the padded 64 x 64 case it runs on the FP64 tensor pipe (mma_tn, upper 16 x 16 blocks +
+// mirror) straight into the K buffer, which is free at this point; then one pass adds H, scales and moves the entries to where Q lives.
+// Other sizes: 2 x 2 register tiles.
 QP_NOINLINE void qp_form_Q(const QPView &v, double rho, double mue) {
-  const int n = v.n, ne = v.ne, ld = v.ld, th = (n + 1) / 2;
+  const int n = v.n, ne = v.ne, ld = v.ld, ldk = v.ldk, th = (n + 1) / 2;
   const double ime = 1.0 / mue;
+  if (v.np8 == 64 && ne >= 4 && ne % 4 == 0) {
+    // columns n .. 63 of the operand read the first entries of the next row of W (finite): they only reach rows / columns >= n of the result
+    mma_tn(8, 8, ne, v.As, ld, v.As, ld, v.KQ, ldk, nullptr, 0, 0, 0, true);
+    PAR_FOR(e, n * n) {
+      const int i = e / n, j = e % n;
+      if (j > i) continue;
+      const double q = v.Hs[i * ld + j] + v.KQ[i * ldk + j] * ime; // (A'A)(i, j) from the lower triangle; nobody writes there in this pass
+      if (i == j) v.Qd[i] = q + rho; else qp_Q(v, i, j) = q;
+    }
+    PAR_FOR(e, (v.np8 - n) * v.np8) { // the product also wrote the padding rows of the Newton matrix: back to the identity
+      const int r = n + e / v.np8, c = e % v.np8;
+      if (c <= r) v.KQ[r * ldk + c] = (r == c) ? 1.0 : 0.0;
+    }
+    SYNC();
+    return;
+  }
   PAR_FOR(tile, th * th) {
     const int ti = tile / th, tj = tile % th;
     if (tj > ti) continue;
