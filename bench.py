@@ -346,6 +346,35 @@ def main():
     barrier()
     wall_cl = time.time() - t2
 
+    # ---- the same closed loop with the reference's WHOLE per-tick bookkeeping on the device (mpc_gait_tick: sole placements of
+    # the predicted state, update_timings, footTrajectory, the 2 x 100 reference writes and the entering stage of every robot), nothing from the host
+    cl_gait = None
+    if world == 1 and args.config != "random":
+        from mpc_benchmark_b200 import gait as gait_mod
+
+        stairs = args.config == "stairs"
+        gkw = dict(x_forward=0.3, z_height=0.10, keep_forward=True) if stairs else {}
+        solver.gait_setup(gait_mod.device_gait(prob["cfg"].kind, prob["lf"], prob["rf"], prob["com0"], prob["mass"], **gkw), prob.get("mirror"))
+        solver.gait_tick()
+        solver.tick(None, None, keep_multipliers=False, max_iters=1)
+        torch.cuda.synchronize()
+        t3 = time.time()
+        for i in range(args.steps):
+            solver.gait_tick()
+            solver.tick(None, None, keep_multipliers=False, max_iters=1)
+        torch.cuda.synchronize()
+        cl_rate = G * args.steps / (time.time() - t3)
+        t4 = time.time()
+        for i in range(10):
+            solver.gait_tick()
+        torch.cuda.synchronize()
+        gait_ms = 1e3 * (time.time() - t4) / 10
+        cl_gait = {"value": cl_rate, "unit": "robot-ticks/s", "gpu_launches_per_tick_extra": 2, "gait_tick_ms": gait_ms,
+                   "what": "mpc_gait_tick + mpc_tick: every robot restarts its reference gait at tick 0 (a different workload from `value`: the warm starts "
+                           "come from mid-gait horizons, so the first ticks backtrack more); forward kinematics of the predicted state, gait bookkeeping and all T "
+                           "per-knot reference blocks on the device (SURVEY 8f-4), then the tick of 8f-2; no host input per tick.  gait_tick_ms = the two gait "
+                           "kernels alone for the whole batch"}
+
     tmax = torch.tensor([dev_ms * 1e-3, wall, wall_e2e, wall_cl], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -379,7 +408,8 @@ def main():
             "gpu_launches": int(launches),
             "gather": {"bytes_per_rank_per_step": int(B * per * 8), "bytes_total_per_step": int(world * B * per * 8), "collective": "ncclAllGather (torch.distributed.all_gather_into_tensor) of [xs|us|K0|info]"} if gather else None,
             "closed_loop": {"value": G * args.steps / cl_s, "unit": "robot-ticks/s",
-                            "what": "mpc_tick (SURVEY 8f-2): horizon rotation, warm-start shift, x0 <- model prediction, 1 iteration; the next stage of every gait H2D per tick"},
+                            "what": "mpc_tick (SURVEY 8f-2): horizon rotation, warm-start shift, x0 <- model prediction, 1 iteration; the next stage of every gait H2D per tick",
+                            "device_gait": cl_gait},
             "wall_ms_per_step": 1e3 * wall_s / args.steps,
             "kernel_ms_per_step": {k: v / args.steps for k, v in kern.items()},
             "roofline": {"bound": "fp64", "kernel": "k_riccati (proximal Riccati backward+forward)", "achieved": achieved,

@@ -205,6 +205,29 @@ int32_t mpc_debug_phases(mpc_solver_t *h, double *out64);
 int32_t mpc_rbd_terms(mpc_solver_t *h, int32_t count, const double *x, double *M, double *nle, double *Jc, double *dJv, double *vf);
 int32_t mpc_rbd_terms_device(mpc_solver_t *h, int32_t count, uint64_t x_dev, uint64_t M_dev, uint64_t nle_dev, uint64_t Jc_dev, uint64_t dJv_dev,
                              uint64_t vf_dev, uint64_t stream);
+/* ---- Device-side gait / swing-foot reference generation.  Replaces, per MPC tick and for the whole batch, the
+ * Python bookkeeping of the reference loops: update_timings (talos_utils.py:350-373), footTrajectory.updateTrajectory
+ * (talos_utils.py:187-327), the per-stage setReference / contact_poses writes and the stage entering the horizon
+ * (fulldynamic_talos.py:444-510, kinodynamic_talos.py:362-409, centroidal_talos.py:354-384,459). */
+typedef struct mpc_gait {
+  int32_t T_ds, T_ss, cycles, half_cycle; /* contact schedule: T_ds DS, then `cycles` x (T_ss, T_ds, T_ss, T_ds), an extra (T_ss, T_ds) if half_cycle, then 2 T DS */
+  int32_t keep_forward;                   /* 1: never zero the forward step (stairs, BASELINE configs[3]) */
+  int32_t n_uref;                         /* rows of the control-reference table (kino / cent: `urefs`), 0 for full dynamics */
+  double x_forward, y_forward, foot_yaw, y_gap, z_height, swing_apex; /* footTrajectory(...) arguments (full:350-361) */
+  double lf0[12], rf0[12], com0[3];       /* initial sole placements and CoM */
+  double f_half;                          /* m g / 2: contact-force reference of the full-dynamics stages */
+  double w_lfrf;                          /* foot-placement cost weight (full: 2000, kino: 1e5) */
+} mpc_gait_t;
+/* Create the per-robot gait state: mirror [batch] (1 = first swing with the other foot), urefs [n_uref][MPC_MAXU] (may be NULL when n_uref = 0).
+ * The tick counter starts at 0 with the feet at lf0 / rf0. */
+int32_t mpc_gait_setup(mpc_solver_t *h, const mpc_gait_t *gait, const int32_t *mirror, const double *urefs);
+/* One tick of the bookkeeping for every robot: from the measured sole placements lf / rf ([batch][12] host; NULL = the placements of the
+ * soles at the state the next mpc_tick starts from, i.e. the model prediction xs[1], computed on the device) rewrite all T knots and the
+ * terminal block of every instance on the device, then advance the tick counter.  Call it before mpc_tick(h, NULL, x_meas, ...). */
+int32_t mpc_gait_tick(mpc_solver_t *h, const double *lf, const double *rf);
+/* Test hook: the knots [batch][T] and terminal blocks [batch] the solver currently holds. */
+int32_t mpc_get_knots(mpc_solver_t *h, mpc_knot_t *knots, mpc_term_t *terms);
+
 uint64_t mpc_workspace_bytes(mpc_solver_t *h);
 int32_t mpc_abi_sizeof(int32_t which); /* 0 robot, 1 config, 2 knot, 3 term, 4 info */
 /* fp64 DFMA peak micro-benchmark (TFLOP/s) used as the roofline denominator. */

@@ -132,3 +132,12 @@ class QPInfo(C.Structure):
         ("status", i32), ("iter", i32), ("iter_in", i32), ("mu_updates", i32),
         ("pri_res", d), ("dua_res", d), ("duality_gap", d), ("objective", d),
     ]
+
+
+# ---- device-side gait generator (include/mpcb200.h mpc_gait_t)
+class Gait(C.Structure):
+    _fields_ = [
+        ("T_ds", i32), ("T_ss", i32), ("cycles", i32), ("half_cycle", i32), ("keep_forward", i32), ("n_uref", i32),
+        ("x_forward", d), ("y_forward", d), ("foot_yaw", d), ("y_gap", d), ("z_height", d), ("swing_apex", d),
+        ("lf0", d * 12), ("rf0", d * 12), ("com0", d * 3), ("f_half", d), ("w_lfrf", d),
+    ]

@@ -160,6 +160,32 @@ class BatchSolver:
         _native.check(_native.lib().mpc_get_stage_data(self._h, k, _native.ptr(xdot), _native.ptr(force)), "mpc_get_stage_data")
         return xdot, force
 
+    # -- device-side gait / swing-foot references (mirrors gait.GaitPlan)
+    def gait_setup(self, gait, mirror=None, urefs=None):
+        """gait: _abi.Gait (see gait.device_gait); mirror [batch] bools; urefs [n][34] control references of the schedule (kino / cent)."""
+        B = self.batch
+        mir = np.ascontiguousarray(np.zeros(B) if mirror is None else mirror, dtype=np.int32)
+        ur = None
+        if urefs is not None:
+            ur = np.zeros((len(urefs), _abi.MAXU))
+            ur[:, :np.asarray(urefs).shape[1]] = urefs
+            gait.n_uref = len(urefs)
+        _native.check(_native.lib().mpc_gait_setup(self._h, C.byref(gait), mir.ctypes.data_as(C.POINTER(C.c_int32)), _native.ptr(ur)), "mpc_gait_setup")
+
+    def gait_tick(self, lf=None, rf=None):
+        """One tick of the reference's per-tick bookkeeping for the whole batch on the device: all T knots and the terminal block of every
+        robot are rewritten from the measured sole placements lf / rf [batch][12] (None: soles at the model prediction xs[1])."""
+        f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64).reshape(self.batch, 12)  # noqa: E731
+        l, r = f(lf), f(rf)
+        _native.check(_native.lib().mpc_gait_tick(self._h, _native.ptr(l), _native.ptr(r)), "mpc_gait_tick")
+
+    def knots(self):
+        """The per-knot parameter blocks [batch * T] and terminal blocks [batch] the solver currently holds (test hook)."""
+        T = self.cfg.T
+        ks, ts = (_abi.Knot * (self.batch * T))(), (_abi.Term * self.batch)()
+        _native.check(_native.lib().mpc_get_knots(self._h, C.cast(ks, C.c_void_p), C.cast(ts, C.c_void_p)), "mpc_get_knots")
+        return ks, ts
+
     def rbd_terms(self, x):
         """Rigid-body terms of the whole-body QPs for the states x [count][nx] (what kinodynamic_talos.py:425-431 takes from pinocchio):
         dict(M, nle, Jc, dJv, vf).  Uses only the handle's robot model."""

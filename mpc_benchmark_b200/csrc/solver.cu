@@ -11,6 +11,7 @@
 #include "driver.hpp"
 #include "ws_alloc.hpp"
 #include "rbd_terms.cuh"
+#include "gait_host.hpp"
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
@@ -122,6 +123,24 @@ __global__ void __launch_bounds__(128) k_rbd_terms(const DevModel *model, const 
   rbd_terms_group(*model, x + (size_t)i * (NQ + NV), w, M + (size_t)i * NV * NV, nle + (size_t)i * NV, Jc + (size_t)i * 12 * NV, dJv + (size_t)i * 12, vf + (size_t)i * 12);
 }
 
+// device-side gait bookkeeping (gait.cuh): one 128-thread CTA per robot rewrites its T knots and terminal block
+__global__ void __launch_bounds__(128) k_gait_tick(Ws w, const GaitCfg *g, GaitRobot *robots, int t, const double *lf, const double *rf) {
+  __shared__ double sm[16];
+  const size_t b = blockIdx.x;
+  gait_tick_group(*g, robots[b], t, lf + b * 12, rf + b * 12, w.knots + b * w.T, w.terms + b, sm);
+}
+// sole placements at the state the next tick starts from (the model prediction xs[1]): forward kinematics of the evaluation kernel
+__global__ void __launch_bounds__(128) k_feet_of_prediction(Ws w, const DevModel *model, double *lf, double *rf) {
+  extern __shared__ double rbd_smem[];
+  const size_t b = blockIdx.x;
+  FullWsT<false> &ws = *reinterpret_cast<FullWsT<false> *>(rbd_smem);
+  const double *x = w.xs + b * ((size_t)w.T + 1) * w.nx + w.nx;
+  PAR_FOR(i, NQ + NV) ws.x[i] = x[i];
+  SYNC();
+  mb_kinematics(*model, ws);
+  PAR_FOR(i, 12) { lf[b * 12 + i] = ws.ofoot[i]; rf[b * 12 + i] = ws.ofoot[12 + i]; }
+}
+
 __global__ void k_dfma_peak(double *out, int iters) {
   double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
   const double m = 1.0000001, c = 1e-9;
@@ -175,6 +194,13 @@ struct mpc_solver {
   double cat_ms[4] = {0, 0, 0, 0};
   int cat_launches[4] = {0, 0, 0, 0};
   bool profile = true;
+  // device-side gait generator (mpc_gait_setup / mpc_gait_tick)
+  GaitCfg *d_gait = nullptr;
+  GaitRobot *d_gait_robots = nullptr;
+  int8_t *d_gait_phases = nullptr;
+  double *d_gait_urefs = nullptr, *d_feet = nullptr; // d_feet: [2][B][12]
+  int gait_t = 0;
+  bool gait_ready = false;
 };
 
 struct CudaBackend {
@@ -295,6 +321,7 @@ void mpc_destroy(mpc_solver_t *h) {
   if (h->h_counters) cudaFreeHost(h->h_counters);
   if (h->h_st) cudaFreeHost(h->h_st);
   if (h->d_k0) cudaFree(h->d_k0);
+  cudaFree(h->d_gait); cudaFree(h->d_gait_robots); cudaFree(h->d_gait_phases); cudaFree(h->d_gait_urefs); cudaFree(h->d_feet);
   for (cudaEvent_t e : h->ev_part) if (e) cudaEventDestroy(e);
   if (h->stream_copy) cudaStreamDestroy(h->stream_copy);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -806,6 +833,78 @@ int32_t mpc_rbd_terms(mpc_solver_t *h, int32_t count, const double *x, double *M
   return rc;
 }
 
+// ---- device-side gait / swing-foot references (include/mpcb200.h)
+int32_t mpc_gait_setup(mpc_solver_t *h, const mpc_gait_t *gait, const int32_t *mirror, const double *urefs) {
+  if (!h || !gait) return fail("null handle / gait");
+  if (!h->setup_done) return fail("mpc_gait_setup before mpc_setup");
+  if (gait->T_ds <= 0 || gait->T_ss <= 0 || gait->cycles < 0 || gait->cycles > 3) return fail("mpc_gait_setup: schedule out of range (T_ds, T_ss > 0, cycles <= 3)");
+  if (h->w.kind != MPC_KIND_FULL && (gait->n_uref <= 0 || !urefs)) return fail("mpc_gait_setup: the kinodynamic / centroidal gaits need the control-reference table");
+  CK(cudaSetDevice(h->device));
+  Ws &w = h->w;
+  GaitCfg g;
+  std::memset(&g, 0, sizeof g);
+  gait_fill_cfg(*gait, w.kind, w.T, g);
+  std::vector<int8_t> phases;
+  gait_build_schedule(*gait, w.T, phases, g);
+  cudaFree(h->d_gait); cudaFree(h->d_gait_robots); cudaFree(h->d_gait_phases); cudaFree(h->d_gait_urefs); cudaFree(h->d_feet);
+  h->d_gait = nullptr; h->d_gait_robots = nullptr; h->d_gait_phases = nullptr; h->d_gait_urefs = nullptr; h->d_feet = nullptr;
+  CK(cudaMalloc(&h->d_gait, sizeof(GaitCfg)));
+  CK(cudaMalloc(&h->d_gait_robots, sizeof(GaitRobot) * w.B));
+  CK(cudaMalloc(&h->d_gait_phases, phases.size()));
+  CK(cudaMalloc(&h->d_feet, 8 * (size_t)w.B * 24));
+  CK(cudaMemcpy(h->d_gait_phases, phases.data(), phases.size(), cudaMemcpyHostToDevice));
+  g.phases = h->d_gait_phases;
+  if (gait->n_uref > 0 && urefs) {
+    CK(cudaMalloc(&h->d_gait_urefs, 8 * (size_t)gait->n_uref * MPC_MAXU));
+    CK(cudaMemcpy(h->d_gait_urefs, urefs, 8 * (size_t)gait->n_uref * MPC_MAXU, cudaMemcpyHostToDevice));
+    g.urefs = h->d_gait_urefs;
+  }
+  CK(cudaMemcpy(h->d_gait, &g, sizeof g, cudaMemcpyHostToDevice));
+  std::vector<GaitRobot> rs(w.B);
+  for (int b = 0; b < w.B; b++) {
+    for (int i = 0; i < 12; i++) { rs[b].start_l[i] = rs[b].final_l[i] = gait->lf0[i]; rs[b].start_r[i] = rs[b].final_r[i] = gait->rf0[i]; }
+    rs[b].mirror = mirror ? (mirror[b] != 0) : 0; rs[b].pad_ = 0;
+  }
+  CK(cudaMemcpy(h->d_gait_robots, rs.data(), sizeof(GaitRobot) * w.B, cudaMemcpyHostToDevice));
+  h->gait_t = 0;
+  h->gait_ready = true;
+  return 0;
+}
+
+int32_t mpc_gait_tick(mpc_solver_t *h, const double *lf, const double *rf) {
+  if (!h) return fail("null handle");
+  if (!h->gait_ready) return fail("mpc_gait_tick before mpc_gait_setup");
+  if ((lf == nullptr) != (rf == nullptr)) return fail("mpc_gait_tick: pass both measured placements or neither");
+  CK(cudaSetDevice(h->device));
+  Ws &w = h->w;
+  double *dl = h->d_feet, *dr = h->d_feet + (size_t)w.B * 12;
+  if (lf) {
+    CK(cudaMemcpyAsync(dl, lf, 8 * (size_t)w.B * 12, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dr, rf, 8 * (size_t)w.B * 12, cudaMemcpyHostToDevice, h->stream));
+  } else {
+    if (w.kind == MPC_KIND_CENT) return fail("mpc_gait_tick: the centroidal state carries no feet, pass the measured placements");
+    static bool attr_set = false;
+    const size_t smem = sizeof(FullWsT<false>);
+    if (!attr_set) { CK(cudaFuncSetAttribute(k_feet_of_prediction, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+    k_feet_of_prediction<<<w.B, 128, smem, h->stream>>>(w, h->d_model, dl, dr);
+  }
+  k_gait_tick<<<w.B, 128, 0, h->stream>>>(w, h->d_gait, h->d_gait_robots, h->gait_t, dl, dr);
+  CK(cudaGetLastError());
+  h->gait_t++;
+  return 0;
+}
+
+int32_t mpc_get_knots(mpc_solver_t *h, mpc_knot_t *knots, mpc_term_t *terms) {
+  if (!h) return fail("null handle");
+  if (!h->setup_done) return fail("mpc_get_knots before mpc_setup");
+  CK(cudaSetDevice(h->device));
+  Ws &w = h->w;
+  if (knots) CK(cudaMemcpyAsync(knots, w.knots, sizeof(mpc_knot_t) * (size_t)w.B * w.T, cudaMemcpyDeviceToHost, h->stream));
+  if (terms) CK(cudaMemcpyAsync(terms, w.terms, sizeof(mpc_term_t) * (size_t)w.B, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 int32_t mpc_abi_sizeof(int32_t which) {
   switch (which) {
   case 0: return sizeof(mpc_robot_t);
@@ -813,6 +912,7 @@ int32_t mpc_abi_sizeof(int32_t which) {
   case 2: return sizeof(mpc_knot_t);
   case 3: return sizeof(mpc_term_t);
   case 4: return sizeof(mpc_info_t);
+  case 5: return sizeof(mpc_gait_t);
   }
   return -1;
 }

@@ -260,3 +260,21 @@ class GaitPlan:
         self.h_index = self.h_index[1:] + [t]
         self.t += 1
         return LF, RF, self.phases[t], com_final
+
+
+def device_gait(kind, lf0, rf0, com0, mass, swing_apex=0.15, x_forward=None, y_forward=0.0, foot_yaw=0.0, y_gap=0.18, z_height=0.0,
+                keep_forward=False, w_lfrf=None):
+    """Parameter block of the DEVICE gait generator (include/mpcb200.h `mpc_gait_t`, csrc/gait.cuh) for the reference gait of `kind`:
+    the same arguments as GaitPlan, which it mirrors tick for tick (tests/test_gait_device.py)."""
+    T_ds, T_ss, cycles, half = GAITS[kind]
+    g = _abi.Gait()
+    g.T_ds, g.T_ss, g.cycles, g.half_cycle, g.keep_forward, g.n_uref = T_ds, T_ss, cycles, int(half), int(keep_forward), 0
+    g.x_forward = X_FORWARD[kind] if x_forward is None else x_forward
+    g.y_forward, g.foot_yaw, g.y_gap, g.z_height, g.swing_apex = y_forward, foot_yaw, y_gap, z_height, swing_apex
+    for i in range(12):
+        g.lf0[i], g.rf0[i] = float(lf0[i]), float(rf0[i])
+    for i in range(3):
+        g.com0[i] = float(com0[i])
+    g.f_half = mass * GRAVITY / 2.0
+    g.w_lfrf = w_lfrf if w_lfrf is not None else (2000.0 if kind == _abi.KIND_FULL else 1e5)
+    return g

@@ -6,6 +6,7 @@
 #include "../../mpc_benchmark_b200/csrc/ws_alloc.hpp"
 #include "../../mpc_benchmark_b200/csrc/qp.cuh"
 #include "../../mpc_benchmark_b200/csrc/rbd_terms.cuh"
+#include "../../mpc_benchmark_b200/csrc/gait_host.hpp"
 #include <cstdlib>
 #include <cstdio>
 #include <cstdlib>
@@ -133,5 +134,29 @@ extern "C" int emu_rbd_terms(const mpc_robot_t *rb, const mpc_config_t *cfg, int
   for (int i = 0; i < count; i++)
     rbd_terms_group(*model, x + (size_t)i * 57, w, M + (size_t)i * 784, nle + (size_t)i * 28, Jc + (size_t)i * 336, dJv + (size_t)i * 12, vf + (size_t)i * 12);
   delete model;
+  return 0;
+}
+
+// ---- device gait generator (gait.cuh) run serially: `ticks` ticks of `batch` robots; lf / rf [ticks][batch][12] measured sole placements;
+// knots_out [ticks][batch][T], terms_out [ticks][batch]
+extern "C" int emu_gait(int kind, int T, const mpc_gait_t *gait, int batch, const int32_t *mirror, const double *urefs, int ticks, const double *lf,
+                        const double *rf, mpc_knot_t *knots_out, mpc_term_t *terms_out) {
+  GaitCfg g;
+  std::memset(&g, 0, sizeof g);
+  gait_fill_cfg(*gait, kind, T, g);
+  std::vector<int8_t> phases;
+  gait_build_schedule(*gait, T, phases, g);
+  g.phases = phases.data();
+  g.urefs = urefs;
+  std::vector<GaitRobot> rs(batch);
+  for (int b = 0; b < batch; b++) {
+    for (int i = 0; i < 12; i++) { rs[b].start_l[i] = rs[b].final_l[i] = gait->lf0[i]; rs[b].start_r[i] = rs[b].final_r[i] = gait->rf0[i]; }
+    rs[b].mirror = mirror[b] != 0; rs[b].pad_ = 0;
+  }
+  double sm[16];
+  for (int t = 0; t < ticks; t++)
+    for (int b = 0; b < batch; b++)
+      gait_tick_group(g, rs[b], t, lf + ((size_t)t * batch + b) * 12, rf + ((size_t)t * batch + b) * 12, knots_out + ((size_t)t * batch + b) * T,
+                      terms_out + (size_t)t * batch + b, sm);
   return 0;
 }

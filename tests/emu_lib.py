@@ -84,3 +84,19 @@ def rbd_terms(rb, cfg, x):
     rc = lib().emu_rbd_terms(C.byref(rb), C.byref(cfg), B, _p(x), *[_p(o[k]) for k in ("M", "nle", "Jc", "dJv", "vf")])
     assert rc == 0
     return o
+
+
+def gait(kind, T, g, mirror, urefs, lf, rf):
+    """csrc/gait.cuh run serially: lf / rf [ticks][batch][12] -> (knots [ticks][batch * T], terms [ticks][batch])."""
+    lf, rf = np.ascontiguousarray(lf, float), np.ascontiguousarray(rf, float)
+    ticks, batch = lf.shape[0], lf.shape[1]
+    mir = np.ascontiguousarray(mirror, dtype=np.int32)
+    ur = None
+    if urefs is not None:
+        ur = np.zeros((len(urefs), _abi.MAXU))
+        ur[:, :np.asarray(urefs).shape[1]] = urefs
+        g.n_uref = len(urefs)
+    ks, ts = (_abi.Knot * (ticks * batch * T))(), (_abi.Term * (ticks * batch))()
+    rc = lib().emu_gait(int(kind), int(T), C.byref(g), batch, mir.ctypes.data_as(C.POINTER(C.c_int32)), _p(ur), ticks, _p(lf), _p(rf), ks, ts)
+    assert rc == 0
+    return ks, ts

@@ -28,6 +28,25 @@ def main():
     run("full walk, nonlinear rollout kernel", nl, 2)
     run("kino standing", problems.kino_standing_problem(batch=2, T=10), 2)
     run("cent standing", problems.cent_standing_problem(batch=2, T=20), 2)
+    gait_loop()
+
+
+def gait_loop():
+    """Device-side gait bookkeeping (k_feet_of_prediction, k_gait_tick) + closed-loop ticks, full dynamics and kinodynamic."""
+    from mpc_benchmark_b200 import _abi, gait
+
+    for kind, maker in ((_abi.KIND_FULL, problems.full_standing_problem), (_abi.KIND_KINO, problems.kino_standing_problem)):
+        prob = maker(batch=2, T=12)
+        s = BatchSolver(prob["robot"], prob["cfg"], 2, device=0)
+        s.setup(prob["knots"], prob["terms"], prob["x0"])
+        s.run(prob["xs"], prob["us"], max_iters=2)
+        urefs = gait.force_ramp_refs(kind, prob["mass"], 34, 12) if kind == _abi.KIND_KINO else None
+        s.gait_setup(gait.device_gait(kind, prob["lf"], prob["rf"], prob["com0"], prob["mass"]), [False, True], urefs)
+        for _ in range(3):
+            s.gait_tick()
+            s.tick(None, None, keep_multipliers=(kind == _abi.KIND_KINO), max_iters=1)
+        print("gait loop kind", kind, "iters", s.results(gains=False).num_iters)
+        s.close()
 
 
 if __name__ == "__main__":
