@@ -3,7 +3,7 @@
 gait bookkeeping and all per-knot references (mpc_gait_tick), warm-start shift and one ProxDDP iteration (mpc_tick,
 row f-2), ideal plant (x_meas = the model prediction), the reference's solver settings (mu_init = 1e-8, one iteration per tick).
 
-    python examples/reference_gait_walk.py [kino|full] [robots] [ticks]
+    python examples/reference_gait_walk.py [kino|full] [robots] [ticks] [y_gap]
 
 kino (BASELINE configs[1], default): the whole 840-tick gait — three walking cycles — is walked; robots are perturbed copies, half of them
 mirrored.  full (configs[2]): healthy until the first landing knot enters the horizon (tick ~ 110), see DESIGN section 7."""
@@ -20,8 +20,14 @@ from mpc_benchmark_b200.batch import BatchSolver  # noqa: E402
 model = sys.argv[1] if len(sys.argv) > 1 else "kino"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 N = int(sys.argv[3]) if len(sys.argv) > 3 else 840
+Y_GAP = float(sys.argv[4]) if len(sys.argv) > 4 else 0.18  # lateral foot spacing of the planned steps (full:355, kino:260)
 kind = _abi.KIND_KINO if model == "kino" else _abi.KIND_FULL
 prob = (problems.kino_standing_problem if kind == _abi.KIND_KINO else problems.full_standing_problem)(batch=B, mu_init=1e-8)
+# experiment switches (environment): Baumgarte gains of the rigid contacts and the foot-placement weight of the full-dynamics stages
+if kind == _abi.KIND_FULL:
+    for i in range(6):
+        prob["cfg"].kd[i] *= float(os.environ.get("WALK_KD_SCALE", "1"))
+        prob["cfg"].kp[i] *= float(os.environ.get("WALK_KP_SCALE", "1"))
 rng = np.random.default_rng(1)
 x0 = problems.perturbed_x0(prob["robot"], prob["x0"][0], rng, B)
 prob["x0"] = prob["x0"] + 0.3 * (x0 - prob["x0"])
@@ -33,12 +39,12 @@ t0 = time.time()
 cold = s.run(prob["xs"], prob["us"], max_iters=100, gains=False)
 print(f"cold solve: {time.time() - t0:.2f} s, iterations {int(cold.num_iters.min())}..{int(cold.num_iters.max())}")
 urefs = gait.force_ramp_refs(kind, prob["mass"], 34, prob["cfg"].T) if kind == _abi.KIND_KINO else None
-s.gait_setup(gait.device_gait(kind, prob["lf"], prob["rf"], prob["com0"], prob["mass"]), mirror, urefs)
+s.gait_setup(gait.device_gait(kind, prob["lf"], prob["rf"], prob["com0"], prob["mass"], y_gap=Y_GAP, w_lfrf=float(os.environ["WALK_W_FOOT"]) if "WALK_W_FOOT" in os.environ else None), mirror, urefs)
 t0 = time.time()
 for t in range(N):
     s.gait_tick()
     s.tick(None, None, keep_multipliers=False, max_iters=1)
-    if t % 60 == 59 or t == N - 1:
+    if t % (60 if kind == _abi.KIND_KINO else 20) == 19 or t == N - 1:
         r = s.results(gains=False, multipliers=False)
         st = np.array([i.status for i in r.info])
         ks, _ = s.knots()
