@@ -469,3 +469,41 @@ def test_gpu_rbd_terms_and_solve_from_state(oracle):
     same = np.asarray(solver.qp.results.info.iter) == [i.iter_in for i in info]
     assert same.mean() >= 0.9 and np.abs(x - X)[same].max() < 1e-9 * np.abs(X).max()
     s.close()
+
+
+def test_qp_fails_loudly_without_gpu():
+    """No CPU fallback on the QP path either: without a CUDA device creating the native handle raises (and nothing is solved)."""
+    import torch
+
+    from mpc_benchmark_b200 import _native, proxqp
+
+    if torch.cuda.is_available() or not os.path.exists(_native.LIB_PATH):
+        pytest.skip("needs the built library and NO GPU")
+    qp = proxqp.dense.QP(4, 2, 2)
+    with pytest.raises(_native.NativeError):
+        qp.init(np.eye(4), np.zeros(4), np.zeros((2, 4)), np.zeros(2), np.zeros((2, 4)), -np.ones(2), np.ones(2))
+
+
+@pytest.mark.gpu
+def test_gpu_qp_argument_errors():
+    from mpc_benchmark_b200 import _native, proxqp
+
+    with pytest.raises(_native.NativeError):
+        proxqp.dense.BatchQP(65, 2, 2, 3)._handle()  # n above MPC_QP_MAXN
+    qp = proxqp.dense.BatchQP(6, 2, 3, 4)
+    with pytest.raises(RuntimeError):
+        qp.solve()  # before init
+    with pytest.raises(ValueError):
+        qp.init(np.eye(6), np.zeros(6), None, None, np.zeros((3, 6)), np.zeros(3), np.zeros(3))  # A, b missing for n_eq > 0
+    with pytest.raises(ValueError):
+        qp.init(np.eye(6), np.zeros(5), np.zeros((2, 6)), np.zeros(2), np.zeros((3, 6)), np.zeros(3), np.zeros(3))  # wrong size
+    qp.init(np.eye(6), np.ones(6), np.zeros((2, 6)), np.zeros(2), np.zeros((3, 6)), -np.ones(3), np.ones(3))
+    r = qp.solve()
+    assert np.allclose(r.x, -1.0, atol=1e-4) and (r.info.status == 0).all()  # unconstrained minimiser of 1/2 |x|^2 + 1'x
+    # non-finite data is contained: status 2, no hang
+    H = np.eye(6)
+    H[0, 0] = np.nan
+    qp.update(H=H)
+    r = qp.solve()
+    assert (r.info.status == 2).all()
+    qp.close()
