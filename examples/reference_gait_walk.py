@@ -6,7 +6,9 @@ row f-2), ideal plant (x_meas = the model prediction), the reference's solver se
     python examples/reference_gait_walk.py [kino|full] [robots] [ticks] [y_gap]
 
 kino (BASELINE configs[1], default): the whole 840-tick gait — three walking cycles — is walked; robots are perturbed copies, half of them
-mirrored.  full (configs[2]): healthy until the first landing knot enters the horizon (tick ~ 110), see DESIGN section 7."""
+mirrored.  full (configs[2]): the whole 1000-tick gait with the appended knot's control taken from the nearest knot of the same contact phase
+(mpc_set_tail_warmstart(1), the default here; WALK_TAIL=copy selects the scripts' us[1:] + [us[-1]], with which the loop degrades from tick 110 and
+diverges around tick 250)."""
 import os
 import sys
 import time
@@ -39,6 +41,7 @@ t0 = time.time()
 cold = s.run(prob["xs"], prob["us"], max_iters=100, gains=False)
 print(f"cold solve: {time.time() - t0:.2f} s, iterations {int(cold.num_iters.min())}..{int(cold.num_iters.max())}")
 urefs = gait.force_ramp_refs(kind, prob["mass"], 34, prob["cfg"].T) if kind == _abi.KIND_KINO else None
+s.set_tail_warmstart(os.environ.get("WALK_TAIL", "phase") == "phase")  # WALK_TAIL=copy: the reference scripts' warm start of the appended knot
 s.gait_setup(gait.device_gait(kind, prob["lf"], prob["rf"], prob["com0"], prob["mass"], y_gap=Y_GAP, w_lfrf=float(os.environ["WALK_W_FOOT"]) if "WALK_W_FOOT" in os.environ else None), mirror, urefs)
 t0 = time.time()
 for t in range(N):

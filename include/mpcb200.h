@@ -157,6 +157,11 @@ int32_t mpc_reset_multipliers(mpc_solver_t *h, uint64_t stream);
  * x0 <- x_meas ([batch][nx] host) or the model prediction xs[1] when NULL (ideal plant), multipliers reset (setup per tick)
  * or shifted (keep_multipliers, kinodynamic_talos.py:488), then max_iters ProxDDP iterations. */
 int32_t mpc_tick(mpc_solver_t *h, const mpc_knot_t *last, const double *x_meas, int32_t keep_multipliers, int32_t max_iters);
+/* Control warm start of the knot mpc_tick appends: 0 (default) = the previous knot's control, what the scripts pass to solver.run
+ * (us = us[1:] + [us[-1]], fulldynamic_talos.py:534); 1 = the control of the nearest knot of the horizon with the SAME contact phase (not in the reference:
+ * it keeps single-support torques out of the first double-support knot after a swing phase and vice versa, which is what the one-iteration full-dynamics
+ * loop needs to walk). */
+int32_t mpc_set_tail_warmstart(mpc_solver_t *h, int32_t mode);
 
 /* solver.results: xs, us, controlFeedbacks() [batch][T][nu][ndx], vs, lams; any pointer may be NULL. */
 int32_t mpc_get_results(mpc_solver_t *h, double *xs, double *us, double *K, double *vs, double *lams,

@@ -160,6 +160,11 @@ class BatchSolver:
         _native.check(_native.lib().mpc_get_stage_data(self._h, k, _native.ptr(xdot), _native.ptr(force)), "mpc_get_stage_data")
         return xdot, force
 
+    def set_tail_warmstart(self, phase_matched):
+        """Control warm start of the knot `tick` appends: False = the previous knot's (the reference scripts' us[1:] + [us[-1]]), True = the control of the
+        nearest knot of the horizon with the same contact phase (what the one-iteration full-dynamics loop needs to walk)."""
+        _native.check(_native.lib().mpc_set_tail_warmstart(self._h, int(bool(phase_matched))), "mpc_set_tail_warmstart")
+
     # -- device-side gait / swing-foot references (SURVEY 8f row f-4; mirrors gait.GaitPlan)
     def gait_setup(self, gait, mirror=None, urefs=None):
         """gait: _abi.Gait (see gait.device_gait); mirror [batch] bools; urefs [n][34] control references of the schedule (kino / cent)."""

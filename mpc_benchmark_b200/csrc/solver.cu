@@ -201,6 +201,7 @@ struct mpc_solver {
   double *d_gait_urefs = nullptr, *d_feet = nullptr; // d_feet: [2][B][12]
   int gait_t = 0;
   bool gait_ready = false;
+  int tail_mode = 0; // warm start of the knot appended by mpc_tick (mpc_set_tail_warmstart)
 };
 
 struct CudaBackend {
@@ -469,12 +470,28 @@ static int run_impl(mpc_solver *h, const double *d_xs, const double *d_us, int m
 static int run_impl(mpc_solver *h, const double *d_xs, const double *d_us, int max_iters, cudaStream_t s, bool sync_events);
 // closed-loop warm start (fulldynamic_talos.py:532-536): xs <- xs[1:] + [xs[-1]], us <- us[1:] + [us[-1]], x0 <- measured state
 // (x_meas, or the model prediction xs[1] when x_meas == nullptr: ideal plant)
-__global__ void k_shift_warmstart(Ws w, double *xs_in, double *us_in, const double *x_meas) {
+// tail_mode 0: the reference scripts' warm start, us = us[1:] + [us[-1]] (fulldynamic_talos.py:534): the appended knot starts from the previous knot's control.
+// tail_mode 1: it starts from the control of the NEAREST KNOT OF THE HORIZON WITH THE SAME CONTACT PHASE.  With mode 0 the first double-support knot after a
+// swing phase inherits single-support torques (and the first swing knot double-support ones): under the rigid-contact full dynamics that is 36 N of cone
+// violation at the end of the horizon, from which the one-iteration loop does not recover; with mode 1 the same loop walks.
+__global__ void k_shift_warmstart(Ws w, double *xs_in, double *us_in, const double *x_meas, int tail_mode) {
   const size_t b = blockIdx.x, T1 = (size_t)w.T + 1, T = w.T;
   const double *X = w.xs + b * T1 * w.nx, *U = w.us + b * T * w.m;
   double *Xo = xs_in + b * T1 * w.nx, *Uo = us_in + b * T * w.m;
+  __shared__ int tail_src;
+  if (threadIdx.x == 0) {
+    int src = (int)T - 1; // index into the OLD trajectory: old knot T - 1 = new knot T - 2 (the copy of the reference)
+    if (tail_mode == 1 && T >= 2) {
+      const mpc_knot_t *kn = w.knots + b * T; // already rotated: slot j of the new horizon
+      const double c0 = kn[T - 1].cs[0], c1 = kn[T - 1].cs[1];
+      for (int j = (int)T - 2; j >= 0; j--)
+        if (kn[j].cs[0] == c0 && kn[j].cs[1] == c1) { src = j + 1; break; } // new slot j = old knot j + 1
+    }
+    tail_src = src;
+  }
+  __syncthreads();
   for (size_t i = threadIdx.x; i < T1 * w.nx; i += blockDim.x) { size_t k = i / w.nx, c = i % w.nx; Xo[i] = X[(k < T ? k + 1 : T) * w.nx + c]; }
-  for (size_t i = threadIdx.x; i < T * w.m; i += blockDim.x) { size_t k = i / w.m, c = i % w.m; Uo[i] = U[(k + 1 < T ? k + 1 : T - 1) * w.m + c]; }
+  for (size_t i = threadIdx.x; i < T * w.m; i += blockDim.x) { size_t k = i / w.m, c = i % w.m; Uo[i] = U[(k + 1 < T ? k + 1 : (size_t)tail_src) * w.m + c]; }
   for (int i = threadIdx.x; i < w.nx; i += blockDim.x) w.x0[b * w.nx + i] = x_meas ? x_meas[b * w.nx + i] : X[w.nx + i];
 }
 
@@ -497,7 +514,7 @@ int32_t mpc_tick(mpc_solver_t *h, const mpc_knot_t *last, const double *x_meas, 
     CK(cudaMemcpyAsync(h->d_meas, x_meas, (size_t)w.B * w.nx * 8, cudaMemcpyHostToDevice, h->stream));
     d_meas = h->d_meas;
   }
-  k_shift_warmstart<<<w.B, 128, 0, h->stream>>>(w, h->d_xs_in, h->d_us_in, d_meas);
+  k_shift_warmstart<<<w.B, 128, 0, h->stream>>>(w, h->d_xs_in, h->d_us_in, d_meas, h->tail_mode);
   if (keep_multipliers) k_shift_multipliers<<<w.B, 128, 0, h->stream>>>(w, 1);
   else {
     CK(cudaMemsetAsync(w.vs, 0, w.B * T1 * w.nc * 8, h->stream));
@@ -505,6 +522,13 @@ int32_t mpc_tick(mpc_solver_t *h, const mpc_knot_t *last, const double *x_meas, 
   }
   CK(cudaGetLastError());
   return run_impl(h, h->d_xs_in, h->d_us_in, max_iters, h->stream, true);
+}
+
+int32_t mpc_set_tail_warmstart(mpc_solver_t *h, int32_t mode) {
+  if (!h) return fail("null handle");
+  if (mode != 0 && mode != 1) return fail("mpc_set_tail_warmstart: mode must be 0 (previous knot) or 1 (nearest knot of the same contact phase)");
+  h->tail_mode = mode;
+  return 0;
 }
 
 int32_t mpc_reset_multipliers(mpc_solver_t *h, uint64_t stream) {

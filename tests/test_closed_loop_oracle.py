@@ -73,3 +73,19 @@ def test_kinodynamic_loop_with_kept_multipliers():
     hist = closed_loop_oracle.run(B=1, N=60, iters=1, keep=True, mu_init=1e-8, verbose=False, threads=2, kind=_abi.KIND_KINO)
     assert len(hist) == 60 and all(h[7] == 0 for h in hist)
     assert max(h[2] for h in hist) < 0.1 and sum(1 for h in hist if h[5] < 0.99) <= 12 and all(h[5] == 1.0 for h in hist[-20:])
+
+
+def test_full_dynamics_loop_walks_with_phase_matched_tail(monkeypatch):
+    """The full-dynamics loop at the reference's settings (mu_init = 1e-8, one iteration per tick, multipliers reset) WALKS once the knot
+    appended every tick starts from the control of the nearest knot with the same contact phase (mpc_set_tail_warmstart(1)) instead of the
+    previous knot's (the scripts' us[1:] + [us[-1]]): through the first landing (tick 110) and the first two swing phases, full steps at
+    every tick, where the expected-failure test above has diverged by tick 247.  1000 ticks: profiles/r2_closed_loop_full_phase_warmstart.txt;
+    256 robots on the GPU: profiles/r2_gait_walk_full_gpu.txt."""
+    import closed_loop_oracle
+
+    monkeypatch.setenv("ORC_TAIL_U", "phase")
+    hist = closed_loop_oracle.run(B=1, N=260, iters=1, keep=False, mu_init=1e-8, verbose=False, threads=2)
+    assert len(hist) == 260 and all(h[7] == 0 for h in hist)
+    # (the primal infeasibility is reported BEFORE the step: a knot freshly appended at a contact switch shows up with 10 - 20 N on the cone rows once)
+    assert sum(1 for h in hist if h[5] < 0.99) <= 5 and max(h[2] for h in hist) < 40.0 and hist[-1][2] < 5.0
+    assert 1.0 < hist[-1][8] < 1.04

@@ -398,6 +398,43 @@ def test_reference_gait_cold_solve_and_ticks(oracle, kind, ticks, perturb):
     s.close()
 
 
+def test_phase_matched_tail_warmstart_matches_oracle(oracle):
+    """mpc_set_tail_warmstart(1): at the tick where the first double-support knot after a swing phase (robot 0: reference tick 110) / the first knot of
+    the second swing (robot 1: tick 140) enters the horizon, the appended knot's control comes from the nearest knot with the same contact phase;
+    the tick against the oracle started from exactly that warm start."""
+    B, ticks = 2, [109, 139]
+    prob = problems.walk_batch(_abi.KIND_FULL, B, seed=2, ticks=ticks, mirror=[False, False], perturb=True)
+    T = prob["cfg"].T
+    s = BatchSolver(prob["robot"], prob["cfg"], B)
+    s.setup(prob["knots"], prob["terms"], prob["x0"])
+    s.run(prob["xs"], prob["us"], max_iters=4)
+    ref = oracle.solve(prob, max_iters=4, inst_threads=B)
+    nxt_prob = problems.walk_batch(_abi.KIND_FULL, B, seed=2, ticks=[t + 1 for t in ticks], mirror=[False, False], perturb=True)
+    nxt = (_abi.Knot * B)(*[nxt_prob["knots"][b * T + T - 1] for b in range(B)])
+    s.set_tail_warmstart(True)
+    s.tick(nxt, None, keep_multipliers=False, max_iters=1)
+    got = s.results(gains=False)
+    knots = _rotate(prob, list(prob["knots"]), nxt)
+    xs, us = ref["xs"], ref["us"]
+    xs_ws = np.concatenate([xs[:, 1:], xs[:, -1:]], axis=1)
+    us_ws = np.concatenate([us[:, 1:], us[:, -1:]], axis=1)
+    replaced = []
+    for b in range(B):
+        ph = [(k.cs[0], k.cs[1]) for k in knots[b * T:(b + 1) * T]]
+        assert ph[T - 1] != ph[T - 2]  # a contact switch has just entered the horizon
+        for j in range(T - 2, -1, -1):
+            if ph[j] == ph[T - 1]:
+                replaced.append(j)
+                us_ws[b, T - 1] = us_ws[b, j]
+                break
+    assert replaced and replaced[0] < T - 2  # robot 0: double-support knots at the front of the horizon
+    hp = dict(prob, knots=(_abi.Knot * (B * T))(*knots), x0=xs[:, 1].copy())
+    r = oracle.solve(hp, max_iters=1, inst_threads=B, xs=xs_ws, us=us_ws)
+    assert list(got.ls_evals) == [i.ls_evals for i in r["info"]]
+    assert rel(got.xs, r["xs"]) < RTOL and rel(got.us, r["us"]) < RTOL
+    s.close()
+
+
 def test_shift_multipliers_entry_point():
     """mpc_shift_multipliers (solver.cycleProblem, kinodynamic_talos.py:488): running-knot multipliers and the co-states of x_1..x_T move
     n knots to the left and repeat their last entry; the terminal multiplier vs[T] and the initial-condition co-state lams[0] stay."""

@@ -65,6 +65,13 @@ def run(B=4, N=300, iters=1, keep=False, mu_init=1e-8, sigma=0.3, verbose=True, 
         cur_knots = knots
         xs_ws = np.concatenate([xs[:, 1:], xs[:, -1:]], axis=1)
         us_ws = np.concatenate([us[:, 1:], us[:, -1:]], axis=1)
+        if os.environ.get("ORC_TAIL_U") == "phase":  # experiment (NOT the reference's warm start): the appended knot starts from the control of the
+            for b in range(B):                       # nearest knot of the horizon with the same contact phase instead of the previous knot's
+                ph = plans[b].h_phase
+                for j in range(T - 2, -1, -1):
+                    if ph[j] == ph[T - 1]:
+                        us_ws[b, T - 1] = us_ws[b, j]
+                        break
         if keep:
             mode = int(os.environ.get("ORC_SHIFT_MODE", "1"))
             if mode == 0:  # round 1's mpc_shift_multipliers: all T + 1 slots one knot to the left, zeros appended (diverges within 40 ticks)
