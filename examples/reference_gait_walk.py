@@ -22,6 +22,7 @@ from mpc_benchmark_b200.batch import BatchSolver  # noqa: E402
 model = sys.argv[1] if len(sys.argv) > 1 else "kino"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 N = int(sys.argv[3]) if len(sys.argv) > 3 else 840
+KEEP = os.environ.get("WALK_KEEP", "0") == "1"  # 1: multipliers kept and shifted (kinodynamic_talos.py:488 cycles the problem without solver.setup)
 Y_GAP = float(sys.argv[4]) if len(sys.argv) > 4 else 0.18  # lateral foot spacing of the planned steps (full:355, kino:260)
 kind = _abi.KIND_KINO if model == "kino" else _abi.KIND_FULL
 prob = (problems.kino_standing_problem if kind == _abi.KIND_KINO else problems.full_standing_problem)(batch=B, mu_init=1e-8)
@@ -46,7 +47,7 @@ s.gait_setup(gait.device_gait(kind, prob["lf"], prob["rf"], prob["com0"], prob["
 t0 = time.time()
 for t in range(N):
     s.gait_tick()
-    s.tick(None, None, keep_multipliers=False, max_iters=1)
+    s.tick(None, None, keep_multipliers=KEEP, max_iters=1)
     if t % (60 if kind == _abi.KIND_KINO else 20) == 19 or t == N - 1:
         r = s.results(gains=False, multipliers=False)
         st = np.array([i.status for i in r.info])
