@@ -227,7 +227,8 @@ typedef struct mpc_gait {
  * The tick counter starts at 0 with the feet at lf0 / rf0. */
 int32_t mpc_gait_setup(mpc_solver_t *h, const mpc_gait_t *gait, const int32_t *mirror, const double *urefs);
 /* One tick of the bookkeeping for every robot: from the measured sole placements lf / rf ([batch][12] host; NULL = the placements of the
- * soles at the state the next mpc_tick starts from, i.e. the model prediction xs[1], computed on the device) rewrite all T knots and the
+ * soles at the state the next mpc_tick starts from, i.e. the model prediction xs[1], computed on the device; centroidal model: the placements last
+ * tick's plan wanted at this tick, i.e. exact tracking) rewrite all T knots and the
  * terminal block of every instance on the device, then advance the tick counter.  Call it before mpc_tick(h, NULL, x_meas, ...). */
 int32_t mpc_gait_tick(mpc_solver_t *h, const double *lf, const double *rf);
 /* Test hook: the knots [batch][T] and terminal blocks [batch] the solver currently holds. */

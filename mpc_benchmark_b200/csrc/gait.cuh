@@ -25,6 +25,7 @@ struct GaitCfg { // uniform over the batch (device copy owned by the solver hand
 
 struct GaitRobot { // persistent per robot: the poses footTrajectory keeps between ticks
   double start_l[12], final_l[12], start_r[12], final_r[12];
+  double next_l[12], next_r[12]; // the references of the NEXT tick (LF[1], RF[1]): the soles of a robot that tracks them exactly
   int32_t mirror, pad_;
 };
 
@@ -87,6 +88,7 @@ HD void gait_foot_ref(int land, int i, int T_ss, double apex, const double *star
 // Writes the T knots of the horizon the solver sees at this tick and the terminal block.  sm: 2 x 12 + 2 x 3 + 8 doubles of shared scratch.
 HD void gait_tick_group(const GaitCfg &g, GaitRobot &rs, int t, const double *lf, const double *rf, mpc_knot_t *knots, mpc_term_t *term, double *sm) {
   const int T = g.T, mir = rs.mirror ? 1 : 0;
+  if (!lf) { lf = rs.next_l; rf = rs.next_r; } // perfect tracking: the soles are where last tick's plan wanted them now
   double *lgl = sm, *lgr = sm + 3;
   int32_t *heads = reinterpret_cast<int32_t *>(sm + 6); // to_rf, to_lf, la_rf, la_lf
   ONE_THREAD {
@@ -175,6 +177,10 @@ HD void gait_tick_group(const GaitCfg &g, GaitRobot &rs, int t, const double *lf
       term->com_ref[0] = 0.5 * (lT[9] + rT[9]); term->com_ref[1] = 0.5 * (lT[10] + rT[10]); term->com_ref[2] = g.com0[2];
       term->has_com_cstr = 1.0;
     }
+    double nl[12], nr[12];
+    gait_foot_ref(la_lf, 1, g.T_ss, g.apex, rs.start_l, rs.final_l, lgl, nl);
+    gait_foot_ref(la_rf, 1, g.T_ss, g.apex, rs.start_r, rs.final_r, lgr, nr);
+    gait_copy12(nl, rs.next_l); gait_copy12(nr, rs.next_r);
   }
   SYNC();
 }

@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(128) k_rbd_terms(const DevModel *model, const 
 __global__ void __launch_bounds__(128) k_gait_tick(Ws w, const GaitCfg *g, GaitRobot *robots, int t, const double *lf, const double *rf) {
   __shared__ double sm[16];
   const size_t b = blockIdx.x;
-  gait_tick_group(*g, robots[b], t, lf + b * 12, rf + b * 12, w.knots + b * w.T, w.terms + b, sm);
+  gait_tick_group(*g, robots[b], t, lf ? lf + b * 12 : nullptr, rf ? rf + b * 12 : nullptr, w.knots + b * w.T, w.terms + b, sm);
 }
 // sole placements at the state the next tick starts from (the model prediction xs[1]): forward kinematics of the evaluation kernel
 __global__ void __launch_bounds__(128) k_feet_of_prediction(Ws w, const DevModel *model, double *lf, double *rf) {
@@ -886,7 +886,7 @@ int32_t mpc_gait_setup(mpc_solver_t *h, const mpc_gait_t *gait, const int32_t *m
   CK(cudaMemcpy(h->d_gait, &g, sizeof g, cudaMemcpyHostToDevice));
   std::vector<GaitRobot> rs(w.B);
   for (int b = 0; b < w.B; b++) {
-    for (int i = 0; i < 12; i++) { rs[b].start_l[i] = rs[b].final_l[i] = gait->lf0[i]; rs[b].start_r[i] = rs[b].final_r[i] = gait->rf0[i]; }
+    for (int i = 0; i < 12; i++) { rs[b].start_l[i] = rs[b].final_l[i] = rs[b].next_l[i] = gait->lf0[i]; rs[b].start_r[i] = rs[b].final_r[i] = rs[b].next_r[i] = gait->rf0[i]; }
     rs[b].mirror = mirror ? (mirror[b] != 0) : 0; rs[b].pad_ = 0;
   }
   CK(cudaMemcpy(h->d_gait_robots, rs.data(), sizeof(GaitRobot) * w.B, cudaMemcpyHostToDevice));
@@ -905,8 +905,9 @@ int32_t mpc_gait_tick(mpc_solver_t *h, const double *lf, const double *rf) {
   if (lf) {
     CK(cudaMemcpyAsync(dl, lf, 8 * (size_t)w.B * 12, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(dr, rf, 8 * (size_t)w.B * 12, cudaMemcpyHostToDevice, h->stream));
+  } else if (w.kind == MPC_KIND_CENT) {
+    dl = dr = nullptr; // the centroidal state carries no feet: the soles are taken where last tick's plan wanted them (exact tracking)
   } else {
-    if (w.kind == MPC_KIND_CENT) return fail("mpc_gait_tick: the centroidal state carries no feet, pass the measured placements");
     static bool attr_set = false;
     const size_t smem = sizeof(FullWsT<false>);
     if (!attr_set) { CK(cudaFuncSetAttribute(k_feet_of_prediction, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }

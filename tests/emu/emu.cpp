@@ -150,7 +150,7 @@ extern "C" int emu_gait(int kind, int T, const mpc_gait_t *gait, int batch, cons
   g.urefs = urefs;
   std::vector<GaitRobot> rs(batch);
   for (int b = 0; b < batch; b++) {
-    for (int i = 0; i < 12; i++) { rs[b].start_l[i] = rs[b].final_l[i] = gait->lf0[i]; rs[b].start_r[i] = rs[b].final_r[i] = gait->rf0[i]; }
+    for (int i = 0; i < 12; i++) { rs[b].start_l[i] = rs[b].final_l[i] = rs[b].next_l[i] = gait->lf0[i]; rs[b].start_r[i] = rs[b].final_r[i] = rs[b].next_r[i] = gait->rf0[i]; }
     rs[b].mirror = mirror[b] != 0; rs[b].pad_ = 0;
   }
   double sm[16];
