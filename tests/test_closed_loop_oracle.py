@@ -2,9 +2,10 @@
 multipliers reset every tick (fulldynamic_talos.py:375,407,539), reference gait bookkeeping, ideal plant that integrates the
 model.  Runs on the CPU oracle (tools/closed_loop_oracle.py); the CUDA path mirrors the oracle bit-for-tolerance (test_gpu_parity).
 
-Known limitation, documented in DESIGN.md ("oracle-vs-Aligator ablation"): the loop degrades once the first landing knot enters the
-horizon (tick ~ 110) and diverges during the second step; with the tick solved to convergence instead of one iteration the same
-loop walks.  The test is therefore an expected failure — it turns into a pass the day the one-iteration loop is fixed."""
+Documented in DESIGN.md section 7: WITH THE SCRIPTS' WARM START of the appended knot (us[1:] + [us[-1]]) the full-dynamics loop degrades once
+the first landing knot enters the horizon (tick ~ 110) and diverges during the second step — that test stays here as an expected failure —
+while with the appended knot started from the control of the nearest knot of the same contact phase (mpc_set_tail_warmstart(1)) the same loop
+walks the whole gait, as do the centroidal and kinodynamic loops with the scripts' warm start (the passing tests below)."""
 import os
 import sys
 
@@ -14,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 
-@pytest.mark.xfail(reason="one-iteration-per-tick loop at mu_init = 1e-8 diverges during the second step (DESIGN.md ablation table)", strict=False)
+@pytest.mark.xfail(reason="full dynamics with the scripts' warm start of the appended knot: diverges during the second step (DESIGN.md section 7)", strict=False)
 def test_one_iteration_loop_survives_260_ticks():
     import closed_loop_oracle
 
