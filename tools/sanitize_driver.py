@@ -42,6 +42,7 @@ def gait_loop():
         s.run(prob["xs"], prob["us"], max_iters=2)
         urefs = gait.force_ramp_refs(kind, prob["mass"], 34, 12) if kind == _abi.KIND_KINO else None
         s.gait_setup(gait.device_gait(kind, prob["lf"], prob["rf"], prob["com0"], prob["mass"]), [False, True], urefs)
+        s.set_tail_warmstart(kind == _abi.KIND_FULL)  # phase-matched warm start of the appended knot (k_shift_warmstart, mode 1)
         for _ in range(3):
             s.gait_tick()
             s.tick(None, None, keep_multipliers=(kind == _abi.KIND_KINO), max_iters=1)
