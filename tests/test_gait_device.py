@@ -163,3 +163,48 @@ def test_gpu_closed_loop_with_device_gait_matches_host_driven_loop():
         sols.append(s.results(gains=False, multipliers=False))
         s.close()
     assert np.abs(sols[0].xs - sols[1].xs).max() < 1e-9 and np.abs(sols[0].us - sols[1].us).max() < 1e-7
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,ticks,phase_tail", [(_abi.KIND_FULL, 260, True), (_abi.KIND_KINO, 215, False), (_abi.KIND_CENT, 230, False)])
+def test_gpu_reference_gait_closed_loop_walks(kind, ticks, phase_tail):
+    """Closed loop along the reference gait with every tick on the device (mpc_gait_tick + mpc_tick), the reference's solver settings (mu_init = 1e-8,
+    one ProxDDP iteration per tick, multipliers reset), 32 robots (half mirrored, perturbed initial states), ideal plant: through the first landing and
+    into / through the second swing phase nobody fails, (nearly) full steps are taken and the base / CoM stays at its height.  Full dynamics: with the
+    appended knot started from a knot of the same contact phase (mpc_set_tail_warmstart(1)); with the scripts' copy this loop has diverged by tick 260
+    (DESIGN section 7).  Whole gaits: profiles/r2_gait_walk_{cent,kino,full}_gpu.txt."""
+    from mpc_benchmark_b200.batch import BatchSolver
+
+    B = 32
+    maker = {_abi.KIND_FULL: problems.full_standing_problem, _abi.KIND_KINO: problems.kino_standing_problem, _abi.KIND_CENT: problems.cent_standing_problem}[kind]
+    prob = maker(batch=B, mu_init=1e-8)
+    rng = np.random.default_rng(1)
+    if kind == _abi.KIND_CENT:
+        prob["x0"] = prob["x0"] + rng.normal(size=prob["x0"].shape) * np.array([0.003] * 3 + [0.02 * prob["mass"]] * 3 + [0.02] * 3)
+    else:
+        x0 = problems.perturbed_x0(prob["robot"], prob["x0"][0], rng, B)
+        prob["x0"] = prob["x0"] + 0.3 * (x0 - prob["x0"])
+        prob["x0"][:, 3:7] /= np.linalg.norm(prob["x0"][:, 3:7], axis=1, keepdims=True)
+    s = BatchSolver(prob["robot"], prob["cfg"], B)
+    s.setup(prob["knots"], prob["terms"], prob["x0"])
+    s.run(prob["xs"], prob["us"], max_iters=100, gains=False)
+    urefs = gait.force_ramp_refs(kind, prob["mass"], 34 if kind == _abi.KIND_KINO else 12, prob["cfg"].T) if kind != _abi.KIND_FULL else None
+    s.set_tail_warmstart(phase_tail)
+    s.gait_setup(gait.device_gait(kind, prob["lf"], prob["rf"], prob["com0"], prob["mass"]), (np.arange(B) % 2).astype(bool), urefs)
+    z0 = prob["x0"][:, 2].mean()
+    small_steps = 0
+    for t in range(ticks):
+        s.gait_tick()
+        s.tick(None, None, keep_multipliers=False, max_iters=1)
+        if t % 10 == 9 or t == ticks - 1:
+            r = s.results(gains=False, multipliers=False)
+            st = np.array([i.status for i in r.info])
+            assert (st < 2).all() and np.isfinite(r.xs).all(), t
+            assert np.abs(r.xs[:, 0, 2] - z0).max() < 0.05, t  # base / CoM height
+            small_steps += int(np.median(r.alpha) < 0.99)
+    assert small_steps <= 6 and np.median(r.alpha) == 1.0
+    ks, _ = s.knots()
+    ph = gait.contact_phases(kind, prob["cfg"].T)  # robot 0 is not mirrored: knot 0 carries phase (ticks - 1) - (T - 1) of the schedule, past the first swing
+    idx = ticks - prob["cfg"].T
+    assert [bool(ks[0].cs[0]), bool(ks[0].cs[1])] == ph[idx] and any(p != [True, True] for p in ph[:idx])
+    s.close()
