@@ -13,12 +13,15 @@ from . import _abi
 
 
 class ClosedLoop:
-    def __init__(self, solver, knot_stream, plant=None, keep_multipliers=False, term_stream=None):
+    def __init__(self, solver, knot_stream, plant=None, keep_multipliers=False, term_stream=None, phase_matched_tail=None):
         """solver: a set-up BatchSolver holding the cold-solve result; knot_stream(t) -> ctypes Knot array [batch] with the stage
         entering the horizon at tick t; plant(t, xs, us, K0) -> measured states [batch, nx] or None for the ideal plant;
         term_stream(t) -> ctypes Term array [batch] or None: the terminal cost references / CoM equality swapped in at tick t
-        (fulldynamic_talos.py:499-510)."""
+        (fulldynamic_talos.py:499-510); phase_matched_tail: True / False selects the control warm start of the knot appended every tick (the nearest
+        knot of the same contact phase / the previous knot as in the scripts; BatchSolver.set_tail_warmstart), None leaves the solver's setting."""
         self.solver, self.knot_stream, self.plant, self.keep, self.term_stream = solver, knot_stream, plant, keep_multipliers, term_stream
+        if phase_matched_tail is not None:
+            solver.set_tail_warmstart(phase_matched_tail)
         self.t = 0
         self.tick_ms = []
 
