@@ -46,7 +46,7 @@ cold = s.run(prob["xs"], prob["us"], max_iters=100, gains=False)
 print(f"cold solve: {time.time() - t0:.2f} s, iterations {int(cold.num_iters.min())}..{int(cold.num_iters.max())}")
 urefs = gait.force_ramp_refs(kind, prob["mass"], 34 if kind == _abi.KIND_KINO else 12, prob["cfg"].T) if kind != _abi.KIND_FULL else None
 s.set_tail_warmstart(os.environ.get("WALK_TAIL", "phase") == "phase")  # WALK_TAIL=copy: the reference scripts' warm start of the appended knot
-s.gait_setup(gait.device_gait(kind, prob["lf"], prob["rf"], prob["com0"], prob["mass"], y_gap=Y_GAP, w_lfrf=float(os.environ["WALK_W_FOOT"]) if "WALK_W_FOOT" in os.environ else None), mirror, urefs)
+s.gait_setup(gait.device_gait(kind, prob["lf"], prob["rf"], prob["com0"], prob["mass"], x_forward=float(os.environ["WALK_X_FORWARD"]) if "WALK_X_FORWARD" in os.environ else None, y_gap=Y_GAP, w_lfrf=float(os.environ["WALK_W_FOOT"]) if "WALK_W_FOOT" in os.environ else None), mirror, urefs)
 t0 = time.time()
 for t in range(N):
     s.gait_tick()
