@@ -831,9 +831,8 @@ int32_t mpc_rbd_terms_device(mpc_solver_t *h, int32_t count, uint64_t x_dev, uin
   if (h->w.kind == MPC_KIND_CENT) return fail("mpc_rbd_terms: the centroidal model has no rigid-body tree");
   if (count <= 0) return fail("mpc_rbd_terms: count out of range");
   CK(cudaSetDevice(h->device));
-  static bool attr_set = false;
   const size_t smem = sizeof(FullWsT<false>);
-  if (!attr_set) { CK(cudaFuncSetAttribute(k_rbd_terms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+  CK(cudaFuncSetAttribute(k_rbd_terms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); // per device: set on every call (microseconds)
   k_rbd_terms<<<count, 128, smem, stream ? (cudaStream_t)stream : h->stream>>>(h->d_model, (const double *)x_dev, count, (double *)M_dev, (double *)nle_dev,
                                                                                   (double *)Jc_dev, (double *)dJv_dev, (double *)vf_dev);
   CK(cudaGetLastError());
@@ -908,9 +907,8 @@ int32_t mpc_gait_tick(mpc_solver_t *h, const double *lf, const double *rf) {
   } else if (w.kind == MPC_KIND_CENT) {
     dl = dr = nullptr; // the centroidal state carries no feet: the soles are taken where last tick's plan wanted them (exact tracking)
   } else {
-    static bool attr_set = false;
     const size_t smem = sizeof(FullWsT<false>);
-    if (!attr_set) { CK(cudaFuncSetAttribute(k_feet_of_prediction, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+    CK(cudaFuncSetAttribute(k_feet_of_prediction, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); // per device: set on every call
     k_feet_of_prediction<<<w.B, 128, smem, h->stream>>>(w, h->d_model, dl, dr);
   }
   k_gait_tick<<<w.B, 128, 0, h->stream>>>(w, h->d_gait, h->d_gait_robots, h->gait_t, dl, dr);
