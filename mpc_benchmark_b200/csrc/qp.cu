@@ -45,7 +45,7 @@ __global__ void k_qp_gamma(double *dJv, const double *vf, const int32_t *cs, dou
   dJv[e] = cs[i * 2 + c] ? g : 0.0;
 }
 
-std::string g_err;
+thread_local std::string g_err;
 int fail(const std::string &m) { g_err = m; return 1; }
 #define CUQ(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
 
