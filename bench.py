@@ -476,6 +476,13 @@ def single_instance_latency(args, prob, device, with_cpu):
     sub = problems.sub_problem(prob, 0, 1)
     s = BatchSolver(sub["robot"], sub["cfg"], 1, device=device)
     s.setup(sub["knots"], sub["terms"], sub["x0_nominal"])
+    # cold solve: from xs = [x0] * (T + 1), us = 0 to TOL = 1e-5 or 100 iterations (fulldynamic_talos.py:374-397), second run timed
+    s.run(sub["xs"], sub["us"], max_iters=100, gains=False)
+    s.reset_multipliers()
+    t0 = time.perf_counter()
+    cold = s.run(sub["xs"], sub["us"], max_iters=100, gains=False)
+    cold_ms = 1e3 * (time.perf_counter() - t0)
+    s.reset_multipliers()
     warm = s.run(sub["xs"], sub["us"], max_iters=args.prep_iters, gains=False)
     xs, us = problems.warm_tick_inputs(sub, warm.xs), warm.us.copy()
     s.set_x0(sub["x0"])
@@ -487,7 +494,9 @@ def single_instance_latency(args, prob, device, with_cpu):
         ts.append(1e3 * (time.perf_counter() - t0))
     ts = np.array(ts[10:])
     out = {"p50_ms": float(np.percentile(ts, 50)), "p90_ms": float(np.percentile(ts, 90)), "ticks": int(len(ts)),
-           "what": "warm MPC tick, batch 1, host buffers in/out (mpc_run + mpc_get_results)"}
+           "what": "warm MPC tick, batch 1, host buffers in/out (mpc_run + mpc_get_results)",
+           "cold_solve": {"ms": cold_ms, "iterations": int(cold.num_iters[0]), "converged": bool(cold.conv[0]),
+                          "what": "ProxDDP from xs = [x0] * (T + 1), us = 0 to TOL 1e-5 or 100 iterations on this instance's horizon (batch 1)"}}
     s.close()
     if with_cpu:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
